@@ -1,0 +1,227 @@
+/*
+ * iss_cuda.h -- C ABI of the B200 (sm_100a) Cooper-Frye particlization engine.
+ *
+ * This is the drop-in boundary of the hot path.  The reference (chunshen1987/iSS)
+ * has no FFI: its sampler `FSSW` is a C++ class driven by `class iSS`
+ * (reference src/iSS.cpp:130-165 -> src/FSSW.cpp:344-361).  Each entry point
+ * below names the reference code it replaces.  The C++ facade in
+ * iss_b200/host/ (`class iSS`, same public API as reference src/iSS.h:16-102)
+ * is the only intended caller; tests and bench.py bind the same symbols with
+ * ctypes.
+ *
+ * Conventions: plain C types, opaque handle, one handle per GPU, caller-owned
+ * host buffers, `int` status (0 = ok, !=0 = error; text via iss_cuda_last_error).
+ * No exceptions cross this boundary.  There is NO CPU fallback: every call
+ * fails with ISS_ERR_CUDA when no sm_100-class device is usable.
+ */
+#ifndef ISS_CUDA_H_
+#define ISS_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct iss_handle iss_handle;
+
+enum {
+    ISS_OK = 0,
+    ISS_ERR_CUDA = 1,       /* CUDA runtime error / no device                 */
+    ISS_ERR_ARG = 2,        /* bad argument                                   */
+    ISS_ERR_STATE = 3,      /* call order violated (e.g. sample before yields) */
+    ISS_ERR_RANGE = 4,      /* momentum-sampler table range (reference exit(1),
+                               MomentumSamplerBase.cpp:35-43)                 */
+    ISS_ERR_NOMEM = 5
+};
+
+/* Number of float fields per freeze-out cell in the local-rest-frame record
+ * (reference `FO_surf_LRF`, src/data_struct.h:66-76), uploaded as
+ * structure-of-arrays.  Index meaning: */
+enum {
+    ISS_F_TAU = 0, ISS_F_X, ISS_F_Y, ISS_F_ETA,
+    ISS_F_DA0, ISS_F_DA1, ISS_F_DA2, ISS_F_DA3,      /* da_mu_LRF[0..3] */
+    ISS_F_UT, ISS_F_UX, ISS_F_UY, ISS_F_UZ,          /* u_tz[0..3]      */
+    ISS_F_E, ISS_F_T, ISS_F_P, ISS_F_NB,
+    ISS_F_MUB, ISS_F_MUS, ISS_F_MUQ, ISS_F_BULKPI,
+    ISS_F_PIXX, ISS_F_PIXY, ISS_F_PIXZ, ISS_F_PIYY, ISS_F_PIYZ,
+    ISS_F_QX, ISS_F_QY, ISS_F_QZ,
+    ISS_NFIELD = 28
+};
+
+/* One chosen species, in sampling order (mass-sorted, reference
+ * FSSW.cpp:115-162; fields of `particle_info`, data_struct.h:27-50). */
+typedef struct {
+    int32_t pid;        /* Monte-Carlo id (monval)                       */
+    int32_t gspin;
+    int32_t baryon;
+    int32_t strange;
+    int32_t charge;
+    int32_t sign;       /* -1 boson, +1 fermion, 0 Boltzmann             */
+    int32_t decay_idx;  /* row in the decay table (iss_cuda_upload_decay_table) or -1 */
+    int32_t reserved;
+    double mass;
+} iss_species;
+
+/* Options consumed on the FSSW path (reference FSSW.cpp:67-103, 885-894, 950-951). */
+typedef struct {
+    int32_t hydro_mode;                 /* 2: 3+1D; otherwise dN *= (y_RB - y_LB), y ~ U */
+    int32_t include_deltaf_shear;
+    int32_t include_deltaf_bulk;
+    int32_t include_deltaf_diffusion;
+    int32_t bulk_deltaf_kind;           /* 1, 11, 20, 21 active; 0,2,3,4 no-ops as in FSSW */
+    int32_t dN_dy_sampling_model;       /* 30 Poisson (default), 1 floor+Bernoulli      */
+    int32_t local_charge_conservation;
+    int32_t reserved;
+    double dN_dy_sampling_para1;
+    double y_LB, y_RB;
+} iss_options;
+
+/* Table kinds for iss_cuda_upload_table.  `dims`/`grid` meaning per kind:
+ *  BESSEL_K   : data[n0][3]  = K1,K2,K3 on x = grid[0] + i*grid[1]       (FSSW.cpp:1609-1643)
+ *  EXPINT     : data[n0][9]  = E2,E4..E18 on the same x grid               (FSSW.cpp:1635-1641)
+ *  CE         : data[n0*n1][5] rows {e, nB, c2hat, zetahat, etahat}        (FSSW.cpp:1303-1338)
+ *  MOM22      : data[n0*n1][8]                                             (FSSW.cpp:1341-1376)
+ *  MOM14      : data[3][n0(T)][n1(mu)] c0,c1,c2; grid = {T0,dT,mu0,dmu}    (FSSW.cpp:1215-1300)
+ *  KAPPA_B    : data[n0(T)][n1(mu)];           grid = {T0,dT,mu0,dmu}      (FSSW.cpp:1546-1568)
+ *  MOMENTUM_* : data[4][n0] = Etilde, CDF_0, CDF_1, CDF_2 of one sampler   (Boson/FermionMomentumSampler.cpp)
+ *               regime r in {0,1,2}: kind = ISS_TABLE_MOMENTUM_BOSON0 + r etc.
+ */
+enum {
+    ISS_TABLE_BESSEL_K = 1,
+    ISS_TABLE_EXPINT = 2,
+    ISS_TABLE_CE = 3,
+    ISS_TABLE_MOM22 = 4,
+    ISS_TABLE_MOM14 = 5,
+    ISS_TABLE_KAPPA_B = 6,
+    ISS_TABLE_MOMENTUM_BOSON0 = 10,     /* +0,+1,+2 : regimes m0 = 0.05, 30, 50 */
+    ISS_TABLE_MOMENTUM_FERMION0 = 13    /* +0,+1,+2 : regimes m0 = 0,    30, 50 */
+};
+
+/* Decay table (reference particle_decay.cpp:33-172): one row per species of the
+ * pdg list incl. generated anti-baryons; channels flattened. */
+typedef struct {
+    int32_t pid;
+    int32_t stable;
+    int32_t n_channels;
+    int32_t first_channel;      /* index into the channel array */
+    int32_t baryon, strange, charge;
+    int32_t reserved;
+    double mass;
+    double width;
+} iss_decay_species;
+
+typedef struct {
+    int32_t n_part;             /* as listed (may be 1,2,3,4,-2,...) */
+    int32_t daughter[5];        /* row indices into the decay-species array, -1 if none/unknown */
+    double branching_ratio;
+} iss_decay_channel;
+
+/* Output record: identical to the reference `iSS_Hadron` (data_struct.h:79-84), 40 bytes. */
+typedef struct {
+    int32_t pid;
+    float mass;
+    float E, px, py, pz;
+    float t, x, y, z;
+} iss_hadron;
+
+typedef struct {
+    int64_t n_events;           /* events in the sampled batch                  */
+    int64_t n_hadrons;          /* hadrons currently held for the batch         */
+    int64_t n_tries;            /* accept/reject proposals spent (sampler kernel) */
+    int64_t n_cell_redraws;     /* reference "impatience" re-picks (FSSW.cpp:1017-1018) */
+} iss_counts;
+
+/* QA block filled by iss_cuda_histograms (per rank; every entry is a plain sum, so the
+ * caller all-reduces the block across ranks with NCCL).  Layout, in doubles:
+ *   [0]        number of events accumulated
+ *   [1..4]     sum over events of P^mu = (E,px,py,pz);  [5..8] sum over events of (P^mu)^2
+ *   [9..24]    sum over hadrons of p^mu p^nu / p^0   (iSS::construct_Tmunu..., iSS.cpp:296-331)
+ *   [25]       number of hadrons;  [26..28] net baryon number, strangeness, electric charge
+ *   [29..31]   reserved
+ *   then ISS_QA_NSPEC blocks of ISS_QA_PER doubles, one per tracked pid:
+ *     pt_count[NPT], pt_sum[NPT], pt_count_sq[NPT]   Histogram(0,5,100) binning, width 5/99
+ *                                                     (Histogram.cpp:7-36); _sq = sum over events
+ *                                                     of the per-event bin content squared
+ *     y_count[NY] on [-5,5), phi_count[NPHI] on [-pi,pi),
+ *     v2_num[NV2], v2_den[NV2]  (sum cos 2phi, count) in pT bins on [0,3),
+ *     n_total, n_sq (sum over events of N_ev^2)                                        */
+#define ISS_QA_NSPEC 16
+#define ISS_QA_NPT 100
+#define ISS_QA_NY 100
+#define ISS_QA_NPHI 64
+#define ISS_QA_NV2 20
+#define ISS_QA_HEAD 32
+#define ISS_QA_PER (3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + 2*ISS_QA_NV2 + 2)
+
+/* ---- lifetime ---------------------------------------------------------- */
+int iss_cuda_create(int device, iss_handle **out);
+int iss_cuda_destroy(iss_handle *h);
+const char *iss_cuda_last_error(const iss_handle *h);
+/* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*). */
+int iss_cuda_set_stream(iss_handle *h, void *cuda_stream);
+int iss_cuda_synchronize(iss_handle *h);
+
+/* ---- inputs (replace the std::vector<FO_surf_LRF>/particle tables FSSW's ctor takes,
+ *      FSSW.cpp:43-201) -------------------------------------------------- */
+int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], int64_t ncell);
+int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t nspecies);
+int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data,
+                          int64_t n0, int64_t n1, const double *grid4);
+int iss_cuda_upload_decay_table(iss_handle *h, const iss_decay_species *sp, int32_t nsp,
+                                const iss_decay_channel *ch, int32_t nch);
+int iss_cuda_set_options(iss_handle *h, const iss_options *opt);
+
+/* ---- yields: FSSW::calculate_dN_dxtdy_for_one_particle_species for every species
+ *      (FSSW.cpp:565-715, 719-848) + RandomVariable1DArray ctor (RandomVariable1DArray.cpp:25-52).
+ *      dN_species_host[ns]  <- sum over cells (NOT yet multiplied by y_RB - y_LB);
+ *      yields_host (may be NULL) <- [ns][ncell] FP64 per-cell yields.                */
+int iss_cuda_compute_yields(iss_handle *h, double *dN_species_host, double *yields_host);
+
+/* ---- sampling: FSSW::sample_using_dN_dxtdy_4all_particles_conventional (FSSW.cpp:873-1071)
+ *      for events [ev_begin, ev_end): multiplicities, offsets, momenta, boost, emit. */
+int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_end,
+                    iss_counts *out);
+/* multiplicity table of the last batch: counts_host[(ev-ev_begin)*ns + s]              */
+int iss_cuda_get_multiplicities(iss_handle *h, int64_t *counts_host);
+/* Poisson parameters the draws used: lambda[s], mode pmf pm[s] (for bit-exact CPU checks) */
+int iss_cuda_get_poisson_params(iss_handle *h, double *lambda_host, double *pmode_host);
+
+/* ---- decays: FSSW::perform_resonance_feed_down + particle_decay (FSSW.cpp:1746-1779,
+ *      particle_decay.cpp:265-546) on the batch held by the handle.                    */
+int iss_cuda_decay(iss_handle *h, uint64_t seed, iss_counts *out);
+
+/* ---- outputs (replace Hadron_list accessors, FSSW.h:166-184) ------------------- */
+/* event_offsets_host[n_events+1]: exclusive prefix of hadrons per event of the batch.  */
+int iss_cuda_event_offsets(iss_handle *h, int64_t *event_offsets_host);
+int iss_cuda_fetch_event(iss_handle *h, int64_t iev_in_batch, iss_hadron *dst, int64_t cap,
+                         int64_t *n);
+/* whole batch, event-major; dst may be pinned memory. */
+int iss_cuda_fetch_all(iss_handle *h, iss_hadron *dst, int64_t cap, int64_t *n);
+/* device pointer of the batch (for callers that keep the list on the GPU). */
+int iss_cuda_device_hadrons(iss_handle *h, const void **dptr, int64_t *n);
+
+/* ---- QA: iSS::perform_checks + Histogram (iSS.cpp:59-83, 296-363): fills a block of
+ *      doubles on the DEVICE (so that NCCL can reduce it in place) and optionally copies it. */
+int64_t iss_cuda_qa_size(void);                   /* number of doubles in the QA block */
+int iss_cuda_histograms(iss_handle *h, const int32_t *pids, int32_t npid, int accumulate);
+int iss_cuda_qa_device_ptr(iss_handle *h, void **dptr);
+int iss_cuda_qa_fetch(iss_handle *h, double *dst_host);
+
+/* ---- timing: accumulated device time (CUDA events on the handle's stream) per kernel family */
+enum { ISS_T_YIELDS = 0, ISS_T_SCAN, ISS_T_MULT, ISS_T_SAMPLE, ISS_T_DECAY, ISS_T_QA, ISS_T_NKIND };
+int iss_cuda_timing(iss_handle *h, int enable, double *ms_host /*[ISS_T_NKIND]*/,
+                    int64_t *launches_host /*[ISS_T_NKIND]*/, int reset);
+
+/* ---- memory helpers for the host facade (pinned staging buffers, batch sizing) */
+int iss_cuda_mem_info(iss_handle *h, int64_t *free_bytes, int64_t *total_bytes);
+int iss_cuda_host_alloc(iss_handle *h, void **ptr, int64_t bytes);   /* cudaHostAlloc */
+int iss_cuda_host_free(iss_handle *h, void *ptr);
+
+/* ---- FP64 pipe probe: dependent-free DFMA loop, returns achieved TFLOP/s (2 flop per FMA). */
+int iss_cuda_fp64_peak(iss_handle *h, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* ISS_CUDA_H_ */

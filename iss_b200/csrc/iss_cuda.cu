@@ -1,0 +1,545 @@
+// iss_cuda.cu -- C-ABI entry points (include/iss_cuda.h): handle life-time, uploads,
+// orchestration of the kernels in yields.cu / sampler.cu / decay.cu / qa.cu and the
+// device->host accessors that replace FSSW's Hadron_list getters (FSSW.h:166-184).
+#include <cmath>
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <utility>
+
+#include "iss_internal.cuh"
+
+using namespace iss;
+
+namespace {
+
+// SoA [ISS_NFIELD][ncell_pad] -> AoS [ncell][CELL_STRIDE] with t = tau cosh(eta), z = tau sinh(eta)
+// precomputed in double from the float fields exactly as FSSW::add_one_sampled_particle does for
+// eta_s = cell eta (FSSW.cpp:1981-1982).
+__global__ void build_cells_kernel(const float *__restrict__ soa, int64_t ncell, int64_t ncell_pad,
+                                   float *__restrict__ cells) {
+    const int64_t c = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    float rec[CELL_STRIDE];
+#pragma unroll
+    for (int k = 0; k < ISS_NFIELD; k++) rec[k] = soa[static_cast<int64_t>(k)*ncell_pad + c];
+    const double tau = rec[ISS_F_TAU], eta = rec[ISS_F_ETA];
+    rec[CELL_T] = static_cast<float>(tau*cosh(eta));
+    rec[CELL_Z] = static_cast<float>(tau*sinh(eta));
+    rec[30] = 0.f;
+    rec[31] = 0.f;
+    float4 *dst = reinterpret_cast<float4 *>(cells + c*CELL_STRIDE);
+#pragma unroll
+    for (int k = 0; k < CELL_STRIDE/4; k++)
+        dst[k] = make_float4(rec[4*k], rec[4*k + 1], rec[4*k + 2], rec[4*k + 3]);
+}
+
+__global__ void fp64_fma_kernel(double *out, int iters) {
+    double a0 = threadIdx.x*1e-9, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3.;
+    double a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    out[static_cast<size_t>(blockIdx.x)*blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+void free_surface(iss_handle *h) {
+    cudaFree(h->d_surf); h->d_surf = nullptr;
+    cudaFree(h->d_cells); h->d_cells = nullptr;
+    cudaFree(h->d_cellcoef); h->d_cellcoef = nullptr;
+    cudaFree(h->d_yields); h->d_yields = nullptr;
+    cudaFree(h->d_cdf); h->d_cdf = nullptr;
+    cudaFree(h->d_tilesum); h->d_tilesum = nullptr;
+    cudaFree(h->d_tilebase); h->d_tilebase = nullptr;
+    cudaFree(h->d_total); h->d_total = nullptr;
+    h->have_yields = false;
+    h->have_batch = false;
+}
+
+int upload_doubles(iss_handle *h, double **dptr, const double *src, size_t n) {
+    if (*dptr) cudaFree(*dptr);
+    *dptr = nullptr;
+    ISS_CUDA_TRY(h, cudaMalloc(dptr, sizeof(double)*n));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(*dptr, src, sizeof(double)*n, cudaMemcpyHostToDevice,
+                                    h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int iss_cuda_create(int device, iss_handle **out) {
+    if (!out) return ISS_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+        return ISS_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ISS_ERR_CUDA;
+    iss_handle *h = new (std::nothrow) iss_handle();
+    if (!h) return ISS_ERR_NOMEM;
+    h->device = device;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return ISS_ERR_CUDA;
+    }
+    h->own_stream = true;
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    *out = h;
+    return ISS_OK;
+}
+
+int iss_cuda_destroy(iss_handle *h) {
+    if (!h) return ISS_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_surface(h);
+    cudaFree(h->d_species);
+    cudaFree(h->d_bessel); cudaFree(h->d_expint); cudaFree(h->d_ce); cudaFree(h->d_mom22);
+    cudaFree(h->d_mom14); cudaFree(h->d_kappa);
+    for (int r = 0; r < 6; r++) cudaFree(h->d_momtab[r]);
+    cudaFree(h->d_dsp); cudaFree(h->d_dch); cudaFree(h->d_sorted_pid); cudaFree(h->d_sorted_idx);
+    cudaFree(h->d_lambda); cudaFree(h->d_pmode);
+    cudaFree(h->d_mult); cudaFree(h->d_off_out); cudaFree(h->d_off_work);
+    cudaFree(h->d_hadrons); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
+    cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
+    cudaFree(h->d_qa);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return ISS_OK;
+}
+
+const char *iss_cuda_last_error(const iss_handle *h) {
+    return h ? h->err.c_str() : "null handle";
+}
+
+int iss_cuda_set_stream(iss_handle *h, void *cuda_stream) {
+    if (!h) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    h->own_stream = false;
+    return ISS_OK;
+}
+
+int iss_cuda_synchronize(iss_handle *h) {
+    if (!h) return ISS_ERR_ARG;
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], int64_t ncell) {
+    if (!h || !soa || ncell <= 0) return ISS_ERR_ARG;
+    if (ncell >= (int64_t(1) << 31)) ISS_FAIL(h, ISS_ERR_ARG, "ncell must be < 2^31");
+    cudaSetDevice(h->device);
+    free_surface(h);
+    h->ncell = ncell;
+    h->ntile = (ncell + TILE - 1)/TILE;
+    h->ncell_pad = h->ntile*TILE;
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_surf, sizeof(float)*ISS_NFIELD*h->ncell_pad));
+    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_surf, 0, sizeof(float)*ISS_NFIELD*h->ncell_pad,
+                                    h->stream));
+    for (int k = 0; k < ISS_NFIELD; k++) {
+        if (!soa[k]) ISS_FAIL(h, ISS_ERR_ARG, "null field pointer");
+        ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_surf + static_cast<int64_t>(k)*h->ncell_pad, soa[k],
+                                        sizeof(float)*ncell, cudaMemcpyHostToDevice, h->stream));
+    }
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_cells, sizeof(float)*CELL_STRIDE*ncell));
+    build_cells_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(
+        h->d_surf, ncell, h->ncell_pad, h->d_cells);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t nspecies) {
+    if (!h || !species || nspecies <= 0 || nspecies > MAX_SPECIES) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    h->h_species.assign(species, species + nspecies);
+    std::vector<DeviceSpecies> ds(nspecies);
+    for (int i = 0; i < nspecies; i++) {
+        const iss_species &p = species[i];
+        DeviceSpecies &d = ds[i];
+        d.mass = p.mass;
+        d.pid = p.pid;
+        d.gspin = static_cast<int16_t>(p.gspin);
+        d.baryon = static_cast<int16_t>(p.baryon);
+        d.strange = static_cast<int16_t>(p.strange);
+        d.charge = static_cast<int16_t>(p.charge);
+        d.sign = static_cast<int16_t>(p.sign);
+        d.trunc10_mass = (p.mass < 0.7) ? 1 : 0;    // FSSW.cpp:741
+        d.decay_idx = p.decay_idx;
+        d.pad = 0;
+    }
+    if (h->d_species) cudaFree(h->d_species);
+    h->d_species = nullptr;
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_species, sizeof(DeviceSpecies)*nspecies));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_species, ds.data(), sizeof(DeviceSpecies)*nspecies,
+                                    cudaMemcpyHostToDevice, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->nspecies != nspecies && h->d_yields) {
+        // yield buffers are sized by species count
+        cudaFree(h->d_yields); h->d_yields = nullptr;
+        cudaFree(h->d_cdf); h->d_cdf = nullptr;
+        cudaFree(h->d_tilesum); h->d_tilesum = nullptr;
+        cudaFree(h->d_tilebase); h->d_tilebase = nullptr;
+        cudaFree(h->d_total); h->d_total = nullptr;
+        cudaFree(h->d_cellcoef); h->d_cellcoef = nullptr;
+    }
+    h->nspecies = nspecies;
+    h->have_yields = false;
+    return ISS_OK;
+}
+
+int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data, int64_t n0, int64_t n1,
+                          const double *grid4) {
+    if (!h || !data || n0 <= 0) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    h->have_yields = false;
+    switch (kind) {
+    case ISS_TABLE_BESSEL_K:
+    case ISS_TABLE_EXPINT: {
+        if (!grid4) return ISS_ERR_ARG;
+        SfGrid g;
+        g.x_min = grid4[0];
+        g.dx = grid4[1];
+        g.n = static_cast<int>(n0);
+        g.x_max_minus_dx = grid4[2];    // = sf_x_max - sf_dx of the caller
+        h->sf = g;
+        if (kind == ISS_TABLE_BESSEL_K) return upload_doubles(h, &h->d_bessel, data, n0*3);
+        return upload_doubles(h, &h->d_expint, data, n0*9);
+    }
+    case ISS_TABLE_CE:
+        if (n0 != n1) ISS_FAIL(h, ISS_ERR_ARG, "CE table must be square (reference indexes with one length)");
+        h->ce_ne = static_cast<int>(n0);
+        h->ce_nb = static_cast<int>(n1);
+        return upload_doubles(h, &h->d_ce, data, n0*n1*5);
+    case ISS_TABLE_MOM22:
+        if (n0 != n1) ISS_FAIL(h, ISS_ERR_ARG, "22-moment table must be square");
+        h->ce_ne = static_cast<int>(n0);
+        h->ce_nb = static_cast<int>(n1);
+        return upload_doubles(h, &h->d_mom22, data, n0*n1*8);
+    case ISS_TABLE_MOM14:
+        if (!grid4 || n1 <= 0) return ISS_ERR_ARG;
+        h->g14 = Grid2D{grid4[0], grid4[1], grid4[2], grid4[3], static_cast<int>(n0),
+                        static_cast<int>(n1)};
+        return upload_doubles(h, &h->d_mom14, data, 3*n0*n1);
+    case ISS_TABLE_KAPPA_B:
+        if (!grid4 || n1 <= 0) return ISS_ERR_ARG;
+        h->gk = Grid2D{grid4[0], grid4[1], grid4[2], grid4[3], static_cast<int>(n0),
+                       static_cast<int>(n1)};
+        return upload_doubles(h, &h->d_kappa, data, n0*n1);
+    default:
+        if (kind >= ISS_TABLE_MOMENTUM_BOSON0 && kind < ISS_TABLE_MOMENTUM_BOSON0 + 6) {
+            // host-provided momentum table [4][n0] -> interleaved [n0][4]
+            if (!grid4) return ISS_ERR_ARG;
+            const int r = kind - ISS_TABLE_MOMENTUM_BOSON0;
+            std::vector<double> inter(static_cast<size_t>(n0)*4);
+            for (int64_t i = 0; i < n0; i++)
+                for (int c = 0; c < 4; c++) inter[i*4 + c] = data[c*n0 + i];
+            int rc = upload_doubles(h, &h->d_momtab[r], inter.data(), inter.size());
+            if (rc) return rc;
+            MomentumTable &t = h->momtab[r];
+            t.data = h->d_momtab[r];
+            t.n = static_cast<int>(n0);
+            t.m0 = grid4[0];
+            t.trunc = static_cast<int>(grid4[1]);
+            t.e0 = data[0];
+            t.de = data[1] - data[0];
+            return ISS_OK;
+        }
+        ISS_FAIL(h, ISS_ERR_ARG, "unknown table kind");
+    }
+}
+
+int iss_cuda_upload_decay_table(iss_handle *h, const iss_decay_species *sp, int32_t nsp,
+                                const iss_decay_channel *ch, int32_t nch) {
+    if (!h || !sp || !ch || nsp <= 0 || nch <= 0) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_dsp); cudaFree(h->d_dch);
+    h->d_dsp = nullptr; h->d_dch = nullptr;
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_dsp, sizeof(iss_decay_species)*nsp));
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_dch, sizeof(iss_decay_channel)*nch));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_dsp, sp, sizeof(iss_decay_species)*nsp,
+                                    cudaMemcpyHostToDevice, h->stream));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_dch, ch, sizeof(iss_decay_channel)*nch,
+                                    cudaMemcpyHostToDevice, h->stream));
+    // pid-sorted index for look-ups by Monte-Carlo id (the reference searches linearly,
+    // particle_decay.cpp:268-273)
+    std::vector<std::pair<int32_t, int32_t>> order(nsp);
+    for (int i = 0; i < nsp; i++) order[i] = {sp[i].pid, i};
+    std::sort(order.begin(), order.end());
+    std::vector<int32_t> spid(nsp), sidx(nsp);
+    for (int i = 0; i < nsp; i++) {
+        spid[i] = order[i].first;
+        sidx[i] = order[i].second;
+    }
+    cudaFree(h->d_sorted_pid); cudaFree(h->d_sorted_idx);
+    h->d_sorted_pid = h->d_sorted_idx = nullptr;
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_sorted_pid, sizeof(int32_t)*nsp));
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_sorted_idx, sizeof(int32_t)*nsp));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_sorted_pid, spid.data(), sizeof(int32_t)*nsp,
+                                    cudaMemcpyHostToDevice, h->stream));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_sorted_idx, sidx.data(), sizeof(int32_t)*nsp,
+                                    cudaMemcpyHostToDevice, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->ndsp = nsp;
+    h->ndch = nch;
+    return ISS_OK;
+}
+
+int iss_cuda_set_options(iss_handle *h, const iss_options *opt) {
+    if (!h || !opt) return ISS_ERR_ARG;
+    if (opt->dN_dy_sampling_model != 30 && opt->dN_dy_sampling_model != 1)
+        ISS_FAIL(h, ISS_ERR_ARG,
+                 "dN_dy_sampling_model must be 30 (Poisson) or 1 (floor+Bernoulli); "
+                 "NBD models 10/20 are not implemented");
+    const bool changed = !h->have_opt || memcmp(&h->opt, opt, sizeof(*opt)) != 0;
+    h->opt = *opt;
+    h->have_opt = true;
+    if (changed) {
+        h->have_yields = false;
+        // K/E tables depend on include_deltaf_diffusion: rebuild lazily
+    }
+    return ISS_OK;
+}
+
+int iss_cuda_compute_yields(iss_handle *h, double *dN_species_host, double *yields_host) {
+    if (!h) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    int rc = run_yields(h);
+    if (rc) return rc;
+    if (dN_species_host)
+        memcpy(dN_species_host, h->h_total.data(), sizeof(double)*h->nspecies);
+    if (yields_host) {
+        ISS_CUDA_TRY(h, cudaMemcpy2DAsync(yields_host, sizeof(double)*h->ncell, h->d_yields,
+                                          sizeof(double)*h->ncell_pad, sizeof(double)*h->ncell,
+                                          h->nspecies, cudaMemcpyDeviceToHost, h->stream));
+        ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return ISS_OK;
+}
+
+int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_end,
+                    iss_counts *out) {
+    if (!h || ev_end <= ev_begin) return ISS_ERR_ARG;
+    if (!h->have_yields) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_compute_yields must run first");
+    if (ev_end > (int64_t(1) << 32)) ISS_FAIL(h, ISS_ERR_ARG, "event index must be < 2^32");
+    cudaSetDevice(h->device);
+    h->ev_begin = ev_begin;
+    h->ev_end = ev_end;
+    h->have_batch = false;
+    h->decayed = false;
+    const int64_t nev = ev_end - ev_begin;
+    int rc = run_multiplicities(h, seed, nev);
+    if (rc) return rc;
+    rc = run_sampler(h, seed, nev, 0);
+    if (rc) return rc;
+    unsigned long long cnt[8] = {0};
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(cnt, h->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost,
+                                    h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_batch = true;
+    if (out) {
+        out->n_events = nev;
+        out->n_hadrons = h->n_hadrons;
+        out->n_tries = static_cast<int64_t>(cnt[1]);
+        out->n_cell_redraws = static_cast<int64_t>(cnt[2]);
+    }
+    if (cnt[3] != 0) {
+        char buf[160];
+        snprintf(buf, sizeof(buf),
+                 "[MomentumSampler] out of range for %llu hadrons (m/T - mu/T outside the tables)",
+                 cnt[3]);
+        ISS_FAIL(h, ISS_ERR_RANGE, buf);
+    }
+    return ISS_OK;
+}
+
+int iss_cuda_get_multiplicities(iss_handle *h, int64_t *counts_host) {
+    if (!h || !counts_host) return ISS_ERR_ARG;
+    if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    const int64_t n = (h->ev_end - h->ev_begin)*h->nspecies;
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(counts_host, h->d_mult, sizeof(int64_t)*n,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_get_poisson_params(iss_handle *h, double *lambda_host, double *pmode_host) {
+    if (!h) return ISS_ERR_ARG;
+    if (h->h_lambda.empty()) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    if (lambda_host) memcpy(lambda_host, h->h_lambda.data(), sizeof(double)*h->nspecies);
+    if (pmode_host) memcpy(pmode_host, h->h_pmode.data(), sizeof(double)*h->nspecies);
+    return ISS_OK;
+}
+
+int iss_cuda_decay(iss_handle *h, uint64_t seed, iss_counts *out) {
+    if (!h) return ISS_ERR_ARG;
+    if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    if (!h->d_dsp) ISS_FAIL(h, ISS_ERR_STATE, "decay table not uploaded");
+    cudaSetDevice(h->device);
+    int rc = run_decay(h, seed);
+    if (rc) return rc;
+    if (out) {
+        out->n_events = h->ev_end - h->ev_begin;
+        out->n_hadrons = h->n_hadrons;
+        out->n_tries = 0;
+        out->n_cell_redraws = 0;
+    }
+    return ISS_OK;
+}
+
+int iss_cuda_event_offsets(iss_handle *h, int64_t *event_offsets_host) {
+    if (!h || !event_offsets_host) return ISS_ERR_ARG;
+    if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    const int64_t nev = h->ev_end - h->ev_begin;
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(event_offsets_host, h->d_event_off, sizeof(int64_t)*(nev + 1),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+static const iss_hadron *batch_ptr(const iss_handle *h) {
+    return h->decayed ? h->d_hadrons2 : h->d_hadrons;
+}
+
+int iss_cuda_fetch_event(iss_handle *h, int64_t iev, iss_hadron *dst, int64_t cap, int64_t *n) {
+    if (!h || !n) return ISS_ERR_ARG;
+    if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    const int64_t nev = h->ev_end - h->ev_begin;
+    if (iev < 0 || iev >= nev) ISS_FAIL(h, ISS_ERR_ARG, "event index out of range");
+    int64_t off[2];
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(off, h->d_event_off + iev, sizeof(off), cudaMemcpyDeviceToHost,
+                                    h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *n = off[1] - off[0];
+    if (!dst) return ISS_OK;
+    if (*n > cap) ISS_FAIL(h, ISS_ERR_ARG, "destination too small");
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(dst, batch_ptr(h) + off[0], sizeof(iss_hadron)*(*n),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_fetch_all(iss_handle *h, iss_hadron *dst, int64_t cap, int64_t *n) {
+    if (!h || !n) return ISS_ERR_ARG;
+    if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    *n = h->n_hadrons;
+    if (!dst) return ISS_OK;
+    if (*n > cap) ISS_FAIL(h, ISS_ERR_ARG, "destination too small");
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(dst, batch_ptr(h), sizeof(iss_hadron)*(*n),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_device_hadrons(iss_handle *h, const void **dptr, int64_t *n) {
+    if (!h || !dptr || !n) return ISS_ERR_ARG;
+    if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    *dptr = batch_ptr(h);
+    *n = h->n_hadrons;
+    return ISS_OK;
+}
+
+int64_t iss_cuda_qa_size(void) { return ISS_QA_HEAD + static_cast<int64_t>(ISS_QA_NSPEC)*ISS_QA_PER; }
+
+int iss_cuda_histograms(iss_handle *h, const int32_t *pids, int32_t npid, int accumulate) {
+    if (!h || !pids || npid <= 0 || npid > ISS_QA_NSPEC) return ISS_ERR_ARG;
+    if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    cudaSetDevice(h->device);
+    return run_qa(h, pids, npid, accumulate);
+}
+
+int iss_cuda_qa_device_ptr(iss_handle *h, void **dptr) {
+    if (!h || !dptr) return ISS_ERR_ARG;
+    if (!h->d_qa) ISS_FAIL(h, ISS_ERR_STATE, "no QA block (call iss_cuda_histograms)");
+    *dptr = h->d_qa;
+    return ISS_OK;
+}
+
+int iss_cuda_qa_fetch(iss_handle *h, double *dst_host) {
+    if (!h || !dst_host) return ISS_ERR_ARG;
+    if (!h->d_qa) ISS_FAIL(h, ISS_ERR_STATE, "no QA block (call iss_cuda_histograms)");
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(dst_host, h->d_qa, sizeof(double)*iss_cuda_qa_size(),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_timing(iss_handle *h, int enable, double *ms_host, int64_t *launches_host,
+                    int reset) {
+    if (!h) return ISS_ERR_ARG;
+    if (ms_host) memcpy(ms_host, h->t_ms, sizeof(h->t_ms));
+    if (launches_host) memcpy(launches_host, h->t_launch, sizeof(h->t_launch));
+    if (reset) {
+        memset(h->t_ms, 0, sizeof(h->t_ms));
+        memset(h->t_launch, 0, sizeof(h->t_launch));
+    }
+    h->timing = (enable != 0);
+    return ISS_OK;
+}
+
+int iss_cuda_mem_info(iss_handle *h, int64_t *free_bytes, int64_t *total_bytes) {
+    if (!h) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    size_t f = 0, t = 0;
+    ISS_CUDA_TRY(h, cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = static_cast<int64_t>(f);
+    if (total_bytes) *total_bytes = static_cast<int64_t>(t);
+    return ISS_OK;
+}
+
+int iss_cuda_host_alloc(iss_handle *h, void **ptr, int64_t bytes) {
+    if (!h || !ptr || bytes <= 0) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    *ptr = nullptr;
+    ISS_CUDA_TRY(h, cudaHostAlloc(ptr, static_cast<size_t>(bytes), cudaHostAllocDefault));
+    return ISS_OK;
+}
+
+int iss_cuda_host_free(iss_handle *h, void *ptr) {
+    if (!h) return ISS_ERR_ARG;
+    if (ptr) ISS_CUDA_TRY(h, cudaFreeHost(ptr));
+    return ISS_OK;
+}
+
+int iss_cuda_fp64_peak(iss_handle *h, double *tflops) {
+    if (!h || !tflops) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+    const int blocks = nsm*8, threads = 256, iters = 1 << 16;
+    double *d_out = nullptr;
+    ISS_CUDA_TRY(h, cudaMalloc(&d_out, sizeof(double)*blocks*threads));
+    fp64_fma_kernel<<<blocks, threads, 0, h->stream>>>(d_out, 1024);   // warm-up
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(e0, h->stream);
+        fp64_fma_kernel<<<blocks, threads, 0, h->stream>>>(d_out, iters);
+        cudaEventRecord(e1, h->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    const double flops = 2.0*8.0*static_cast<double>(iters)*blocks*threads;
+    *tflops = flops/(best*1e-3)/1e12;
+    return ISS_OK;
+}
+
+}  // extern "C"

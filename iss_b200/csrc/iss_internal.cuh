@@ -1,0 +1,200 @@
+// iss_internal.cuh -- handle layout and helpers shared by the CUDA translation units.
+#ifndef ISS_INTERNAL_CUH_
+#define ISS_INTERNAL_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <cstdio>
+
+#include "../../include/iss_cuda.h"
+#include "iss_rng.h"
+
+namespace iss {
+
+constexpr double HBARC = 0.197327053;     // reference data_struct.h:9
+constexpr int TILE = 1024;                // cells per CDF tile (scan granularity)
+constexpr int MAX_SPECIES = 1024;
+
+// special-function table grid (FSSW.cpp:1611-1615)
+struct SfGrid {
+    double x_min, dx, x_max_minus_dx;
+    int n;
+};
+
+// 2-D coefficient grid (T, mu) for kappa_B and the 14-moment tables
+struct Grid2D {
+    double x0, dx, y0, dy;
+    int nx, ny;
+};
+
+struct MomentumTable {      // one Boson/FermionMomentumSampler instance
+    const double *data;     // [n][4]: Etilde, CDF_0, CDF_1, CDF_2 (interleaved, 32 B per point)
+    int n;
+    int trunc;              // trunc_order_
+    double m0;              // regime base (m0_)
+    double e0, de;          // Etilde_[0], Etilde_[1] - Etilde_[0]
+};
+
+constexpr int CELL_STRIDE = 32;   // floats per AoS cell record (28 fields + t, z + 2 spare)
+constexpr int CELL_T = 28;        // tau*cosh(eta)
+constexpr int CELL_Z = 29;        // tau*sinh(eta)
+constexpr int COEF_STRIDE = 8;
+
+struct DeviceSpecies {      // what the kernels read per species (smem-friendly, 32 B)
+    double mass;
+    int32_t pid;
+    int16_t gspin, baryon, strange, charge, sign;
+    int16_t trunc10_mass;   // 1 if mass < 0.7 (series of 10 terms when also T > 0.05)
+    int32_t decay_idx;
+    int32_t pad;
+};
+
+}  // namespace iss
+
+struct iss_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // surface
+    int64_t ncell = 0;
+    float *d_surf = nullptr;            // [ISS_NFIELD][ncell_pad]
+    int64_t ncell_pad = 0;              // multiple of TILE
+    int64_t ntile = 0;
+    float *d_cells = nullptr;           // [ncell][32] AoS copy for the sampler's random access
+    double *d_cellcoef = nullptr;       // [ncell][8] delta-f coefficients c0..c5, kappa, spare
+
+    // species
+    int nspecies = 0;
+    std::vector<iss_species> h_species;
+    iss::DeviceSpecies *d_species = nullptr;
+
+    // options
+    iss_options opt{};
+    bool have_opt = false;
+
+    // tables
+    double *d_bessel = nullptr; iss::SfGrid sf{};
+    double *d_expint = nullptr;
+    double *d_ce = nullptr; int ce_ne = 0, ce_nb = 0;
+    double *d_mom22 = nullptr;
+    double *d_mom14 = nullptr; iss::Grid2D g14{};
+    double *d_kappa = nullptr; iss::Grid2D gk{};
+    double *d_momtab[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    iss::MomentumTable momtab[6]{};     // 0..2 boson regimes, 3..5 fermion regimes
+
+    // decay table
+    iss_decay_species *d_dsp = nullptr; int ndsp = 0;
+    iss_decay_channel *d_dch = nullptr; int ndch = 0;
+    int32_t *d_sorted_pid = nullptr;    // pid-sorted view of the decay table
+    int32_t *d_sorted_idx = nullptr;
+
+    // yields / CDF
+    double *d_yields = nullptr;         // [ns][ncell_pad]  raw yields
+    double *d_cdf = nullptr;            // [ns][ncell_pad]  inclusive scan inside each tile
+    double *d_tilesum = nullptr;        // [ns][ntile]
+    double *d_tilebase = nullptr;       // [ns][ntile+1]    exclusive prefix over tiles
+    double *d_total = nullptr;          // [ns]
+    bool have_yields = false;
+    std::vector<double> h_total;        // dN per species (3+1D sum)
+    std::vector<double> h_lambda, h_pmode;
+    double *d_lambda = nullptr, *d_pmode = nullptr;
+
+    // sampling batch
+    int64_t ev_begin = 0, ev_end = 0;
+    int64_t *d_mult = nullptr;          // [nev][ns]
+    int64_t *d_off_out = nullptr;       // [nev*ns + 1] event-major exclusive prefix
+    int64_t *d_off_work = nullptr;      // [ns*nev + 1] species-major exclusive prefix
+    int64_t mult_cap = 0;
+    iss_hadron *d_hadrons = nullptr;
+    int64_t hadron_cap = 0;
+    int64_t n_hadrons = 0;
+    int64_t *d_event_off = nullptr;     // [nev+1]
+    int64_t event_off_cap = 0;
+    unsigned long long *d_counters = nullptr;   // [8] tries, redraws, error flags...
+    bool have_batch = false;
+    bool decayed = false;
+    iss_hadron *d_hadrons2 = nullptr;   // decay output
+    int64_t hadron2_cap = 0;
+    int64_t *d_decay_cnt = nullptr;     // per-primary final multiplicity / offsets
+    int64_t decay_cnt_cap = 0;
+    void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+
+    // QA
+    double *d_qa = nullptr;
+
+    // timing
+    bool timing = false;
+    double t_ms[ISS_T_NKIND] = {0};
+    int64_t t_launch[ISS_T_NKIND] = {0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define ISS_CUDA_TRY(h, expr)                                                        \
+    do {                                                                             \
+        cudaError_t e__ = (expr);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);          \
+            return ISS_ERR_CUDA;                                                     \
+        }                                                                            \
+    } while (0)
+
+#define ISS_FAIL(h, code, msg)                                                       \
+    do {                                                                             \
+        (h)->err = (msg);                                                            \
+        return (code);                                                               \
+    } while (0)
+
+namespace iss {
+
+struct ScopedTimer {
+    iss_handle *h;
+    int kind;
+    int launches;
+    ScopedTimer(iss_handle *h_, int kind_, int launches_ = 1)
+        : h(h_), kind(kind_), launches(launches_) {
+        if (h->timing) cudaEventRecord(h->ev0, h->stream);
+    }
+    ~ScopedTimer() {
+        h->t_launch[kind] += launches;
+        if (h->timing) {
+            cudaEventRecord(h->ev1, h->stream);
+            cudaEventSynchronize(h->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            h->t_ms[kind] += ms;
+        }
+    }
+};
+
+// exclusive scan of int64 on the handle's stream (own kernels, see scan.cu)
+int device_exclusive_scan_i64(iss_handle *h, const int64_t *d_in, int64_t *d_out, int64_t n,
+                              int64_t *h_total);
+
+int run_yields(iss_handle *h);
+int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev);
+int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t total);
+int run_decay(iss_handle *h, uint64_t seed);
+int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate);
+
+template <typename T>
+int ensure_capacity(iss_handle *h, T **ptr, int64_t *cap, int64_t need) {
+    if (need <= *cap && *ptr) return ISS_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    int64_t newcap = need + need/8 + 1024;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(ptr), sizeof(T)*newcap);
+    if (e != cudaSuccess) {
+        *cap = 0;
+        h->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        return ISS_ERR_NOMEM;
+    }
+    *cap = newcap;
+    return ISS_OK;
+}
+
+}  // namespace iss
+#endif  // ISS_INTERNAL_CUH_

@@ -1,0 +1,148 @@
+// iss_rng.h -- counter-based RNG and the integer multiplicity draw, shared by the
+// device kernels and the host facade.  Replaces RandomUtil::Random (reference
+// src/Random.h:11-22, std::mt19937) and gsl_ran_poisson (FSSW.cpp:293-298).
+//
+// Everything here is plain integer arithmetic or single IEEE-754 double
+// operations that are never contracted (explicit __dmul_rn/__dadd_rn/__ddiv_rn on
+// the device, -ffp-contract=off on the host), so that the integer bookkeeping is
+// bit-identical on CPU and GPU (see oracle/iss_oracle.py for the independent
+// numpy restatement the tests compare with).
+#ifndef ISS_RNG_H_
+#define ISS_RNG_H_
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ISS_HD __host__ __device__ __forceinline__
+#else
+#define ISS_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define ISS_MUL(a, b) __dmul_rn((a), (b))
+#define ISS_ADD(a, b) __dadd_rn((a), (b))
+#define ISS_SUB(a, b) __dadd_rn((a), -(b))
+#define ISS_DIV(a, b) __ddiv_rn((a), (b))
+#else
+#define ISS_MUL(a, b) ((a)*(b))
+#define ISS_ADD(a, b) ((a) + (b))
+#define ISS_SUB(a, b) ((a) - (b))
+#define ISS_DIV(a, b) ((a)/(b))
+#endif
+
+namespace iss {
+
+// random streams (upper byte of counter word 3)
+enum { STREAM_MULT = 1, STREAM_SAMPLE = 2, STREAM_DECAY = 3 };
+
+struct Philox {
+    uint32_t c[4];
+    uint32_t k[2];
+};
+
+ISS_HD void philox_mulhilo(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+#if defined(__CUDA_ARCH__)
+    lo = a*b;
+    hi = __umulhi(a, b);
+#else
+    uint64_t p = static_cast<uint64_t>(a)*static_cast<uint64_t>(b);
+    lo = static_cast<uint32_t>(p);
+    hi = static_cast<uint32_t>(p >> 32);
+#endif
+}
+
+// Philox4x32-10 (Salmon et al., SC'11): 10 rounds, Weyl key schedule.
+ISS_HD void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0, lo0, hi1, lo1;
+        philox_mulhilo(0xD2511F53u, c0, hi0, lo0);
+        philox_mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n1 = lo1;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        uint32_t n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit uniform in [0,1) from two 32-bit words.
+ISS_HD double u53(uint32_t hi, uint32_t lo) {
+    uint64_t v = (static_cast<uint64_t>(hi >> 5) << 26) | static_cast<uint64_t>(lo >> 6);
+    return static_cast<double>(v)*(1.0/9007199254740992.0);
+}
+
+// A per-object random stream: key = seed, counter = (block, draw_lo, event, species|stream<<24).
+// Each Philox block yields two 53-bit uniforms; next() hands them out in order.
+struct Stream {
+    uint32_t ctr[4];
+    uint32_t key[2];
+    uint32_t buf[4];
+    int have;   // uniforms left in buf (0..2)
+
+    ISS_HD void init(uint64_t seed, uint32_t stream, uint32_t species, uint32_t event,
+                     uint32_t draw, uint32_t block0 = 0) {
+        key[0] = static_cast<uint32_t>(seed);
+        key[1] = static_cast<uint32_t>(seed >> 32);
+        ctr[0] = block0;
+        ctr[1] = draw;
+        ctr[2] = event;
+        ctr[3] = (stream << 24) | (species & 0xFFFFFFu);
+        have = 0;
+    }
+    ISS_HD double next() {
+        if (have == 0) {
+            philox4x32_10(ctr, key, buf);
+            ctr[0]++;
+            have = 2;
+        }
+        double u = (have == 2) ? u53(buf[0], buf[1]) : u53(buf[2], buf[3]);
+        have--;
+        return u;
+    }
+};
+
+// Exact Poisson draw by inversion from the mode ("chop-down" outward from
+// m = floor(lambda)).  pmode = Poisson pmf at m, computed once per species on the
+// host.  Only +,-,*,/ on doubles: bit-identical on CPU and GPU.  Expected number
+// of steps ~ 1.6 sqrt(lambda).  lambda < 1e-15 -> 0 as in FSSW.cpp:294-295.
+ISS_HD int64_t poisson_from_mode(double lambda, double pmode, double u) {
+    if (lambda < 1e-15) return 0;
+    int64_t m = static_cast<int64_t>(lambda);
+    u = ISS_SUB(u, pmode);
+    if (u < 0.0) return m;
+    int64_t k_hi = m, k_lo = m;
+    double p_hi = pmode, p_lo = pmode;
+    for (;;) {
+        k_hi++;
+        p_hi = ISS_MUL(p_hi, ISS_DIV(lambda, static_cast<double>(k_hi)));
+        u = ISS_SUB(u, p_hi);
+        if (u < 0.0) return k_hi;
+        if (k_lo > 0) {
+            p_lo = ISS_MUL(p_lo, ISS_DIV(static_cast<double>(k_lo), lambda));
+            k_lo--;
+            u = ISS_SUB(u, p_lo);
+            if (u < 0.0) return k_lo;
+        }
+        // numerical tail: both arms exhausted (sum of pmf < 1 by rounding)
+        if (p_hi < 1e-300 && (k_lo == 0 || p_lo < 1e-300)) return m;
+    }
+}
+
+// dN_dy_sampling_model == 1 (FSSW.cpp:269-274): floor + Bernoulli(fraction).
+ISS_HD int64_t floor_plus_bernoulli(double dN, double u) {
+    int64_t n = static_cast<int64_t>(dN);
+    double frac = ISS_SUB(dN, static_cast<double>(n));
+    if (u < frac) n++;
+    return n;
+}
+
+}  // namespace iss
+#endif  // ISS_RNG_H_

@@ -1,0 +1,751 @@
+// sampler.cu -- multiplicities, offsets and the persistent momentum sampler.
+//
+// Replaces the event/particle loops of
+// FSSW::sample_using_dN_dxtdy_4all_particles_conventional (FSSW.cpp:873-1071):
+//   K4  multiplicity_kernel : N[ev][s] ~ Poisson(dN_s) per (species, event)
+//                             (FSSW::determine_number_to_sample, FSSW.cpp:250-309), Philox
+//                             stream (event, species), exact inversion from the mode.
+//       + integer exclusive scans (scan.cu) -> output offsets (event-major, species-major
+//       inside an event exactly like Hadron_list) and work offsets (species-major).
+//   K5  sampler_kernel      : persistent, warp-compacted accept/reject loop.  Every lane owns
+//                             one hadron; a warp refills its idle lanes in batches from a
+//                             dynamically grabbed chunk of the species-major work list, so that
+//                             the proposal loop runs with >= 50 % of the lanes busy regardless of
+//                             the acceptance rate.  Per hadron:
+//                               cell pick   RandomVariable1DArray::rand + binarySearch
+//                                           (RandomVariable1DArray.cpp:63-67, arsenal.cpp:644-678)
+//                               |p| draw    MomentumSamplerShell/Base (MomentumSamplerShell.cpp:24-48,
+//                                           MomentumSamplerBase.cpp:20-93)
+//                               accept      FSSW::sample_momemtum_from_a_fluid_cell (FSSW.cpp:1852-1966)
+//                               boost+emit  boost_vector_back_to_lab_frame + add_one_sampled_particle
+//                                           (FSSW.cpp:2001-2010, 1969-1996), fused.
+// Random numbers: Philox4x32-10 keyed by the seed, counter (block, draw, event, species):
+// the hadron list is a pure function of (seed, event, species, draw) and therefore
+// identical for any number of GPUs, launch geometry or lane assignment.
+#include "coefficients.cuh"
+
+namespace iss {
+
+// ---------------------------------------------------------------------------------
+// momentum-sampler tables (Boson/FermionMomentumSampler.cpp)
+// ---------------------------------------------------------------------------------
+template <bool FERMION>
+__host__ __device__ inline void cdf_012(double Et, double m0, int trunc, double &c0, double &c1,
+                                        double &c2) {
+    // series in n = 0..trunc-1 with e^{-m0 n} and e^{(m0-Et)(n+1)}
+    c1 = 0.;
+    c2 = 0.;
+    double s0 = 0.;
+    double sign = 1.;
+    for (int n = 0; n < trunc; n++) {
+        const int n1 = n + 1;
+        const double a = exp(-m0*n);
+        const double b = exp((m0 - Et)*n1);
+        if (FERMION) {
+            // integer division sign/n1 of the reference (FermionMomentumSampler.cpp:43-51):
+            // only n = 0 contributes
+            if (n == 0) s0 += a*(1. - b);
+        } else {
+            s0 += (1./n1)*a*(1. - b);
+        }
+        c1 += ((FERMION ? sign : 1.)/(static_cast<double>(n1)*n1)*a
+               *((m0*n1 + 1) - b*(Et*n1 + 1)));
+        // CDF_2 carries no alternating sign for fermions either
+        // (FermionMomentumSampler.cpp:80-93)
+        c2 += (1./(static_cast<double>(n1)*n1*n1)*a
+               *((m0*n1*(m0*n1 + 2) + 2) - b*(Et*n1*(Et*n1 + 2) + 2)));
+        sign = -sign;
+    }
+    if (trunc > 5) {
+        if (FERMION) {
+            c0 = -exp(m0)*log((1. + exp(-Et))/(1. + exp(-m0)));
+        } else {
+            c0 = exp(m0)*log((1. - exp(-Et))/(1. - exp(-m0)));
+        }
+    } else {
+        c0 = s0;
+    }
+}
+
+__global__ void build_momentum_table_kernel(double *tab, int n, double e0, double de, double m0,
+                                            int trunc, int fermion) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double Et = e0 + i*de;
+    double c0, c1, c2;
+    if (fermion) {
+        cdf_012<true>(Et, m0, trunc, c0, c1, c2);
+    } else {
+        cdf_012<false>(Et, m0, trunc, c0, c1, c2);
+    }
+    tab[i*4 + 0] = Et;
+    tab[i*4 + 1] = c0;
+    tab[i*4 + 2] = c1;
+    tab[i*4 + 3] = c2;
+}
+
+static int ensure_momentum_tables(iss_handle *h) {
+    // MomentumSamplerShell ctor (MomentumSamplerShell.cpp:6-21)
+    const double m0_b[3] = {0.05, 30., 50.};
+    const double m0_f[3] = {0., 30., 50.};
+    const int trunc[3] = {10, 2, 1};
+    for (int r = 0; r < 6; r++) {
+        if (h->d_momtab[r]) continue;
+        const bool fermion = r >= 3;
+        const double m0 = fermion ? m0_f[r - 3] : m0_b[r];
+        // same double arithmetic as the reference constructors
+        double E_min, E_max, dE;
+        if (fermion) {
+            E_min = m0;
+            E_max = E_min + 40.;
+            dE = 0.02;
+        } else {
+            E_min = m0 + 0.05;
+            E_max = E_min + 50.;
+            dE = 0.05;
+        }
+        const int npoints = (E_max - E_min)/dE + 1;
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_momtab[r], sizeof(double)*4*npoints));
+        build_momentum_table_kernel<<<(npoints + 127)/128, 128, 0, h->stream>>>(
+            h->d_momtab[r], npoints, E_min, dE, m0, trunc[r % 3], fermion ? 1 : 0);
+        ISS_CUDA_TRY(h, cudaGetLastError());
+        MomentumTable &t = h->momtab[r];
+        t.data = h->d_momtab[r];
+        t.n = npoints;
+        t.trunc = trunc[r % 3];
+        t.m0 = m0;
+        t.e0 = E_min;
+        t.de = (E_min + dE) - E_min;    // Etilde_[1] - Etilde_[0]
+    }
+    return ISS_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// K4: multiplicities
+// ---------------------------------------------------------------------------------
+__global__ void multiplicity_kernel(const double *__restrict__ lambda,
+                                    const double *__restrict__ pmode,
+                                    const DeviceSpecies *__restrict__ species, int ns, int64_t nev,
+                                    int64_t ev_begin, uint64_t seed, int model, int lcc,
+                                    int64_t *__restrict__ mult,       // [nev][ns] draws
+                                    int64_t *__restrict__ out_count,  // [nev*ns] hadrons written
+                                    int64_t *__restrict__ work_count  // [ns*nev] draws
+) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (i >= nev*ns) return;
+    const int64_t ev = i/ns;
+    const int s = static_cast<int>(i - ev*ns);
+    Stream rng;
+    rng.init(seed, STREAM_MULT, s, static_cast<uint32_t>(ev_begin + ev), 0);
+    const double u = rng.next();
+    int64_t n;
+    if (model == 1) {
+        n = floor_plus_bernoulli(lambda[s], u);
+    } else {
+        n = poisson_from_mode(lambda[s], pmode[s], u);
+    }
+    int64_t nout = n;
+    if (lcc == 1) {
+        // FSSW.cpp:931-938, 1035-1048: negative species skipped, positive ones paired
+        const int q = species[s].charge;
+        if (q < 0) {
+            n = 0;
+            nout = 0;
+        } else if (q > 0) {
+            nout = 2*n;
+        }
+    }
+    mult[i] = n;
+    out_count[i] = nout;
+    work_count[static_cast<int64_t>(s)*nev + ev] = n;
+}
+
+// per-event offsets = off_out[ev*ns]
+__global__ void event_offset_kernel(const int64_t *__restrict__ off_out, int ns, int64_t nev,
+                                    int64_t *__restrict__ event_off) {
+    const int64_t ev = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (ev <= nev) event_off[ev] = off_out[ev*ns];
+}
+
+// ---------------------------------------------------------------------------------
+// K5: persistent sampler
+// ---------------------------------------------------------------------------------
+struct SamplerArgs {
+    const float *cells;             // [ncell][CELL_STRIDE]
+    const double *cellcoef;         // [ncell][COEF_STRIDE]
+    int64_t ncell, ncell_pad, ntile;
+    const double *cdf;              // [ns][ncell_pad] tile-local inclusive scan
+    const double *tilebase;         // [ns][ntile+1]
+    const double *total;            // [ns]
+    const DeviceSpecies *species;
+    int ns;
+    int64_t nev, ev_begin;
+    const int64_t *off_work;        // [ns*nev+1]
+    const int64_t *off_out;         // [nev*ns+1]
+    int64_t nwork;
+    MomentumTable mt[6];
+    ModeFlags mode;
+    int hydro_mode, lcc;
+    double y_LB, y_RB;
+    uint64_t seed;
+    iss_hadron *out;
+    unsigned long long *counters;   // [0] work cursor, [1] tries, [2] redraws, [3] range errors
+};
+
+constexpr int SAMPLER_THREADS = 128;
+constexpr int WORK_CHUNK = 512;         // hadrons a warp grabs at a time
+constexpr int REFILL_THRESHOLD = 16;    // refill when this many lanes are idle
+constexpr int MAX_IMPATIENCE = 5000;    // FSSW.cpp:1872
+
+struct LaneState {
+    // identity
+    int64_t out_slot;
+    int s;
+    // RNG
+    Stream rng;
+    // cell
+    int64_t cell;
+    // |p| sampler set-up (MomentumSamplerBase::Sample_a_momentum)
+    double T, mu, m_tilde, mu_tilde, w0, m_term, cdf_max, a_min;
+    int tab, idx_min;
+    // accept set-up
+    double dsigma_fac;
+    int tries;
+    int phase;      // 0 primary, 1 charge-conservation partner
+    int qsign;      // +1 primary, -1 partner (flips B,S,Q)
+};
+
+__device__ __forceinline__ double table_F(const double *__restrict__ tb, int i, double w1,
+                                          double w0, double m_term) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(tb + 4*i));       // Et, C0
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(tb + 4*i + 2));   // C1, C2
+    return b.y + w1*b.x + w0*a.y - m_term;
+}
+
+// sets up the |p| sampler for (species, cell); returns false if out of table range
+__device__ __forceinline__ bool setup_momentum(const SamplerArgs &A, LaneState &L, double mass,
+                                               int sign, double T_in, double mu) {
+    const double T = fmax(1e-16, T_in);
+    const double m_tilde = mass/T;
+    const double mu_tilde = mu/T;
+    const double a = m_tilde - mu_tilde;
+    const double m0tilde = mass/T - mu/T;
+    const int regime = (m0tilde < 30.) ? 0 : (m0tilde < 50. ? 1 : 2);
+    const bool fermion = (sign != -1);          // sign 0 -> fermion tables
+    const int tab = (fermion ? 3 : 0) + regime;
+    const MomentumTable &mt = A.mt[tab];
+    double c0, c1, c2;
+    if (fermion) {
+        cdf_012<true>(a, mt.m0, mt.trunc, c0, c1, c2);
+    } else {
+        cdf_012<false>(a, mt.m0, mt.trunc, c0, c1, c2);
+    }
+    const double w1 = 2.*mu_tilde;
+    const double w0 = mu_tilde*mu_tilde - m_tilde*m_tilde/2.;
+    const double m_term = c2 + w1*c1 + w0*c0;
+    const int idx_max = mt.n - 1;
+    const double cdf_max = table_F(mt.data, idx_max, w1, w0, m_term);
+    const int idx_min = static_cast<int>((a - mt.e0)/mt.de);
+    L.T = T;
+    L.mu = mu;
+    L.m_tilde = m_tilde;
+    L.mu_tilde = mu_tilde;
+    L.w0 = w0;
+    L.m_term = m_term;
+    L.cdf_max = cdf_max;
+    L.a_min = a;
+    L.tab = tab;
+    L.idx_min = idx_min;
+    return !(idx_min < 0 || idx_min >= idx_max);
+}
+
+// MomentumSamplerBase::inverse_CDF (MomentumSamplerBase.cpp:61-93)
+__device__ __forceinline__ double inverse_cdf(const MomentumTable &mt, const LaneState &L,
+                                              double r) {
+    const double w1 = 2.*L.mu_tilde;
+    int lo = L.idx_min;
+    int hi = mt.n - 1;
+    double r_min = table_F(mt.data, lo, w1, L.w0, L.m_term);
+    double r_max = L.cdf_max;
+    while (hi - lo > 1) {
+        const int mid = (hi + lo)/2;
+        const double r_mid = table_F(mt.data, mid, w1, L.w0, L.m_term);
+        if (r < r_mid) {
+            hi = mid;
+            r_max = r_mid;
+        } else {
+            lo = mid;
+            r_min = r_mid;
+        }
+    }
+    double E0 = __ldg(mt.data + 4*lo);
+    if (E0 < L.a_min) {
+        E0 = L.a_min;
+        r_min = 0.;
+    }
+    const double Ehi = __ldg(mt.data + 4*hi);
+    return E0 + (Ehi - E0)/fmax(1e-16, (r_max - r_min))*(r - r_min);
+}
+
+// RandomVariable1DArray::rand (two-level: tile prefix, then tile-local inclusive scan)
+__device__ __forceinline__ int64_t pick_cell(const SamplerArgs &A, int s, double u) {
+    const double total = __ldg(&A.total[s]);
+    const double v = (total - 1e-15)*u;
+    const double *__restrict__ tb = A.tilebase + static_cast<int64_t>(s)*(A.ntile + 1);
+    // largest t with tb[t] < v  (tb[0] = 0)
+    int64_t lo = 0, hi = A.ntile;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(&tb[mid]) < v) lo = mid; else hi = mid;
+    }
+    const double vt = v - __ldg(&tb[lo]);
+    const double *__restrict__ c = A.cdf + static_cast<int64_t>(s)*A.ncell_pad + lo*TILE;
+    // smallest j in [0, TILE) with c[j] >= vt
+    int l = -1, r = TILE - 1;
+    while (r - l > 1) {
+        const int mid = (l + r) >> 1;
+        if (__ldg(&c[mid]) < vt) l = mid; else r = mid;
+    }
+    int64_t cell = lo*TILE + r;
+    if (cell >= A.ncell) cell = A.ncell - 1;
+    return cell;
+}
+
+__global__ void __launch_bounds__(SAMPLER_THREADS)
+sampler_kernel(const SamplerArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
+    int64_t *sp_off = reinterpret_cast<int64_t *>(sp + A.ns);     // off_work[s*nev], s = 0..ns
+    for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
+    for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
+        sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
+    __syncthreads();
+
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    LaneState L;
+    bool busy = false;          // lane owns a hadron that still needs an accepted momentum
+    bool pending = false;       // lane holds an accepted momentum waiting for boost+emit
+    double acc_p0 = 0., acc_px = 0., acc_py = 0., acc_pz = 0.;
+    int64_t chunk_next = 0, chunk_end = 0;
+    bool more_work = true;
+    unsigned long long my_tries = 0, my_redraws = 0, my_range = 0;
+    const ModeFlags mode = A.mode;
+
+    for (;;) {
+        // -------------------------------------------------------------- refill / emit phase
+        const unsigned idle_mask = __ballot_sync(full, !busy);
+        const int nidle = __popc(idle_mask);
+        const bool any_busy = (nidle < 32);
+        if (nidle >= REFILL_THRESHOLD || !any_busy) {
+            // (a) boost + emit accepted momenta (FSSW.cpp:1946-1960 and 1969-1996)
+            if (pending) {
+                const DeviceSpecies p = sp[L.s];
+                const float4 *cr = reinterpret_cast<const float4 *>(A.cells + L.cell*CELL_STRIDE);
+                const float4 pos = __ldg(cr + 0);       // tau, x, y, eta
+                const float4 u4 = __ldg(cr + 2);        // ut, ux, uy, uz
+                const float pl0 = static_cast<float>(acc_p0), pl1 = static_cast<float>(acc_px),
+                            pl2 = static_cast<float>(acc_py), pl3 = static_cast<float>(acc_pz);
+                double p_dot_u = 0.;
+                p_dot_u += __fmul_rn(pl1, u4.y);
+                p_dot_u += __fmul_rn(pl2, u4.z);
+                p_dot_u += __fmul_rn(pl3, u4.w);
+                const float up1 = __fadd_rn(u4.x, 1.f);
+                const double fac = p_dot_u/up1 + pl0;
+                const float lab1 = static_cast<float>(pl1 + fac*u4.y);
+                const float lab2 = static_cast<float>(pl2 + fac*u4.z);
+                const float lab3 = static_cast<float>(pl3 + fac*u4.w);
+                const double mass = p.mass;
+                iss_hadron hd;
+                hd.pid = (L.qsign > 0) ? p.pid : -p.pid;
+                hd.mass = static_cast<float>(mass);
+                hd.x = pos.y;
+                hd.y = pos.z;
+                const double pT = sqrt(static_cast<double>(__fadd_rn(__fmul_rn(lab1, lab1),
+                                                                     __fmul_rn(lab2, lab2))));
+                const double mT = sqrt(pT*pT + mass*mass);
+                if (A.hydro_mode == 2) {
+                    // eta_s = cell eta: y = asinh(pz/mT) - eta + eta, p_z = mT sinh(y) = pLab[3],
+                    // px = pT cos(atan2(py,px)) = pLab[1] up to FP64 rounding; t,z precomputed.
+                    const float4 tz = __ldg(cr + 7);    // t, z, spare, spare
+                    const double pz = lab3;
+                    hd.px = lab1;
+                    hd.py = lab2;
+                    hd.pz = lab3;
+                    hd.E = static_cast<float>(sqrt(mT*mT + pz*pz));
+                    hd.t = tz.x;
+                    hd.z = tz.y;
+                } else {
+                    // boost-invariant: y ~ U(y_LB, y_RB), eta_s = y - (y - eta_s) (FSSW.cpp:1024-1029)
+                    const double y_minus_eta = asinh(lab3/mT) - pos.w;
+                    const double rap = A.y_LB + (A.y_RB - A.y_LB)*L.rng.next();
+                    const double eta_s = rap - y_minus_eta;
+                    const double rapidity_y = y_minus_eta + eta_s;
+                    hd.px = lab1;
+                    hd.py = lab2;
+                    hd.pz = static_cast<float>(mT*sinh(rapidity_y));
+                    hd.E = static_cast<float>(mT*cosh(rapidity_y));
+                    hd.z = static_cast<float>(pos.x*sinh(eta_s));
+                    hd.t = static_cast<float>(pos.x*cosh(eta_s));
+                }
+                // 40-byte record as five 8-byte stores (slots are 8-byte aligned)
+                float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
+                dst[0] = make_float2(__int_as_float(hd.pid), hd.mass);
+                dst[1] = make_float2(hd.E, hd.px);
+                dst[2] = make_float2(hd.py, hd.pz);
+                dst[3] = make_float2(hd.t, hd.x);
+                dst[4] = make_float2(hd.y, hd.z);
+                pending = false;
+                if (A.lcc == 1 && L.phase == 0 && p.charge > 0) {
+                    // partner with opposite quantum numbers from the SAME cell (FSSW.cpp:1035-1048)
+                    L.phase = 1;
+                    L.qsign = -1;
+                    L.out_slot += 1;
+                    L.tries = 1;
+                    const float4 th = __ldg(cr + 4);    // muB, muS, muQ, bulkPi
+                    const float4 th0 = __ldg(cr + 3);   // E, T, P, nB
+                    const float muf = __fadd_rn(
+                        __fadd_rn(__fmul_rn(static_cast<float>(-p.baryon), th.x),
+                                  __fmul_rn(static_cast<float>(-p.strange), th.y)),
+                        __fmul_rn(static_cast<float>(-p.charge), th.z));
+                    const double mu = fmin(mass, static_cast<double>(muf));
+                    if (setup_momentum(A, L, mass, p.sign, th0.y, mu)) {
+                        busy = true;
+                    } else {
+                        my_range++;
+                    }
+                }
+            }
+            // (b) hand new hadrons to idle lanes
+            const unsigned need_mask = __ballot_sync(full, !busy);
+            int nneed = __popc(need_mask);
+            const int rank = __popc(need_mask & lt_mask);
+            int given = 0;      // lanes served so far in this refill
+            while (given < nneed && more_work) {
+                if (chunk_next >= chunk_end) {
+                    unsigned long long c = 0;
+                    if (lane == 0) c = atomicAdd(&A.counters[0], (unsigned long long)WORK_CHUNK);
+                    c = __shfl_sync(full, c, 0);
+                    chunk_next = static_cast<int64_t>(c);
+                    chunk_end = min(chunk_next + WORK_CHUNK, A.nwork);
+                    if (chunk_next >= A.nwork) {
+                        more_work = false;
+                        break;
+                    }
+                }
+                const int64_t avail = chunk_end - chunk_next;
+                const int take = static_cast<int>(avail < (int64_t)(nneed - given) ? avail : (int64_t)(nneed - given));
+                if (!busy && rank >= given && rank < given + take) {
+                    const int64_t w = chunk_next + (rank - given);
+                    // (s, ev, k) from the species-major work offsets: species via smem, event via gmem
+                    int slo = 0, shi = A.ns;
+                    while (shi - slo > 1) {
+                        const int mid = (slo + shi) >> 1;
+                        if (sp_off[mid] <= w) slo = mid; else shi = mid;
+                    }
+                    const int s = slo;
+                    const int64_t *__restrict__ ow = A.off_work + static_cast<int64_t>(s)*A.nev;
+                    int64_t elo = 0, ehi = A.nev;
+                    while (ehi - elo > 1) {
+                        const int64_t mid = (elo + ehi) >> 1;
+                        if (__ldg(&ow[mid]) <= w) elo = mid; else ehi = mid;
+                    }
+                    const int64_t ev = elo;
+                    const int64_t k = w - __ldg(&ow[ev]);
+                    const DeviceSpecies p = sp[s];
+                    const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
+                    L.s = s;
+                    L.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k*mult;
+                    L.rng.init(A.seed, STREAM_SAMPLE, s, static_cast<uint32_t>(A.ev_begin + ev),
+                               static_cast<uint32_t>(k));
+                    L.phase = 0;
+                    L.qsign = 1;
+                    L.cell = -1;
+                    L.tries = MAX_IMPATIENCE;   // forces a cell draw below
+                    busy = true;
+                }
+                chunk_next += take;
+                given += take;
+            }
+            if (!more_work && !__any_sync(full, busy)) break;
+        }
+
+        // -------------------------------------------------------------- proposal phase
+        if (busy) {
+            const DeviceSpecies p = sp[L.s];
+            const double mass = p.mass;
+            if (L.tries >= MAX_IMPATIENCE) {
+                // (re)draw the cell: first visit, or the reference's "impatience" re-pick
+                // (FSSW.cpp:1017-1018 with status == 0)
+                if (L.cell >= 0) my_redraws++;
+                L.cell = pick_cell(A, L.s, L.rng.next());
+                L.tries = 1;
+                const float4 *cr = reinterpret_cast<const float4 *>(A.cells + L.cell*CELL_STRIDE);
+                const float4 da = __ldg(cr + 1);
+                const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
+                const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
+                const float muf = __fadd_rn(
+                    __fadd_rn(__fmul_rn(static_cast<float>(p.baryon), th.x),
+                              __fmul_rn(static_cast<float>(p.strange), th.y)),
+                    __fmul_rn(static_cast<float>(p.charge), th.z));
+                const double mu = fmin(mass, static_cast<double>(muf));
+                // float arithmetic inside the sqrt as in FSSW.cpp:1867-1870
+                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
+                                           __fmul_rn(da.w, da.w));
+                L.dsigma_fac = fabs(static_cast<double>(da.x)) + sqrt(static_cast<double>(d2));
+                if (!setup_momentum(A, L, mass, p.sign, th0.y, mu)) {
+                    // reference: exit(1) (MomentumSamplerBase.cpp:35-43); here flagged, lane dropped
+                    my_range++;
+                    busy = false;
+                }
+            }
+        }
+        if (busy) {
+            const DeviceSpecies p = sp[L.s];
+            const double mass = p.mass;
+            const int sign = p.sign;
+            const MomentumTable &mt = A.mt[L.tab];
+            // |p| proposal (MomentumSamplerBase.cpp:48-56); an inner rejection restarts the try
+            const double r = L.rng.next()*L.cdf_max;
+            const double Et = inverse_cdf(mt, L, r);
+            const double E_sample = L.T*Et + L.mu;
+            const double p_mag = sqrt(E_sample*E_sample - mass*mass);
+            const double accept_ratio = (p_mag/E_sample)/(1. - mass*mass/(2.*E_sample*E_sample));
+            const double u_inner = L.rng.next();
+            if (!(u_inner > accept_ratio)) {
+                my_tries++;
+                // FSSW.cpp:1880-1945
+                const double phi = 2*M_PI*L.rng.next();
+                const double cos_theta = 2.*L.rng.next() - 1.;
+                const double sin_theta = sqrt(1. - cos_theta*cos_theta);
+                const double pT = p_mag*sin_theta;
+                double sphi, cphi;
+                sincos(phi, &sphi, &cphi);
+                const double px = pT*cphi;
+                const double py = pT*sphi;
+                const double p0 = sqrt(mass*mass + p_mag*p_mag);
+                const double pz = p_mag*cos_theta;
+                const float4 *cr = reinterpret_cast<const float4 *>(A.cells + L.cell*CELL_STRIDE);
+                const float4 da = __ldg(cr + 1);
+                const double pdsigma = p0*da.x + px*da.y + py*da.z + pz*da.w;
+                const double f0 = 1./(exp((p0 - L.mu)/L.T) + sign);
+                const double stat = 1. - sign*f0;
+                double delta_f = 0.;
+                if (mode.include_shear | mode.include_bulk | mode.include_diff) {
+                    const float4 th0 = __ldg(cr + 3);   // E, T, P, nB
+                    const float4 th = __ldg(cr + 4);    // muB, muS, muQ, bulkPi
+                    const double *__restrict__ co = A.cellcoef + L.cell*COEF_STRIDE;
+                    const int B = L.qsign*p.baryon, S = L.qsign*p.strange, Q = L.qsign*p.charge;
+                    if (mode.include_shear == 1) {
+                        const float4 pa = __ldg(cr + 5);    // pixx, pixy, pixz, piyy
+                        const float4 pb = __ldg(cr + 6);    // piyz, qx, qy, qz
+                        const double Wfactor = (px*px*pa.x + 2.*px*py*pa.y + 2.*px*pz*pa.z
+                                                + py*py*pa.w + 2.*py*pz*pb.x
+                                                + pz*pz*(-pa.x - pa.w));
+                        if (mode.neos == 1) {
+                            delta_f += stat*Wfactor/(2.*__ldg(&co[2]))/(p0*L.T);
+                        } else if (mode.neos == 0) {
+                            delta_f += stat*Wfactor*__ldg(&co[0]);
+                        } else {
+                            const double Tdec = th0.y;
+                            const double pref = 1.0/(2.0*Tdec*Tdec
+                                                     *(static_cast<double>(__fadd_rn(th0.x, th0.z))));
+                            delta_f += stat*Wfactor*pref;
+                        }
+                    }
+                    if (mode.include_bulk == 1) {
+                        // FSSW::get_deltaf_bulk (FSSW.cpp:1795-1849); kinds 0,2,3,4: bulkPi = 0
+                        const double Tdec = th0.y;
+                        if (mode.kind == 21 || mode.kind == 1) {
+                            const double bulkPi = (mode.kind == 21)
+                                                      ? static_cast<double>(th.w)
+                                                      : static_cast<double>(th.w)/HBARC;
+                            const double E_over_T = p0/Tdec;
+                            const double mass_over_T = mass/Tdec;
+                            delta_f += (-1.0*stat*__ldg(&co[0])
+                                        *(mass_over_T*mass_over_T/(3.*E_over_T)
+                                          - __ldg(&co[1])*E_over_T)*bulkPi);
+                        } else if (mode.kind == 11) {
+                            const double bulkPi = th.w;
+                            delta_f += stat*bulkPi*(__ldg(&co[0])*mass*mass + __ldg(&co[1])*B*p0
+                                                    + __ldg(&co[2])*p0*p0);
+                        } else if (mode.kind == 20) {
+                            const double bulkPi = th.w;
+                            delta_f += stat*bulkPi*(mass*mass*__ldg(&co[2])
+                                                    + p0*(B*__ldg(&co[3]) + S*__ldg(&co[4])
+                                                          + Q*__ldg(&co[5]))
+                                                    + p0*p0*(__ldg(&co[1]) - __ldg(&co[2])));
+                        }
+                    }
+                    if (mode.include_diff == 1) {
+                        const float4 pb = __ldg(cr + 6);    // piyz, qx, qy, qz
+                        // float division as in FSSW.cpp:1866
+                        const double prefactor_qmu = __fdiv_rn(th0.w, __fadd_rn(th0.x, th0.z));
+                        const double qmufactor = -px*pb.y - py*pb.z - pz*pb.w;
+                        delta_f += stat*(prefactor_qmu - B/p0)*qmufactor/__ldg(&co[6]);
+                    }
+                }
+                double fact1 = pdsigma/p0/L.dsigma_fac;
+                double fact2 = (1. + delta_f)/2.;
+                fact1 = fmax(0., fmin(1., fact1));
+                fact2 = fmax(0., fmin(1., fact2));
+                const double accept_prob = fact1*fact2;
+                if (L.rng.next() < accept_prob) {
+                    acc_p0 = p0;
+                    acc_px = px;
+                    acc_py = py;
+                    acc_pz = pz;
+                    pending = true;
+                    busy = false;
+                } else {
+                    L.tries++;
+                    // partner sampling never re-picks the cell (do-while at FSSW.cpp:1039-1044)
+                    if (L.phase == 1 && L.tries >= MAX_IMPATIENCE) L.tries = 1;
+                }
+            }
+        }
+    }
+    // warp-aggregated counters
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        my_tries += __shfl_down_sync(full, my_tries, d);
+        my_redraws += __shfl_down_sync(full, my_redraws, d);
+        my_range += __shfl_down_sync(full, my_range, d);
+    }
+    if (lane == 0) {
+        if (my_tries) atomicAdd(&A.counters[1], my_tries);
+        if (my_redraws) atomicAdd(&A.counters[2], my_redraws);
+        if (my_range) atomicAdd(&A.counters[3], my_range);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev) {
+    const int ns = h->nspecies;
+    const int64_t n = nev*ns;
+    int rc;
+    if (n + 1 > h->mult_cap || !h->d_mult) {
+        if (h->d_mult) cudaFree(h->d_mult);
+        if (h->d_off_out) cudaFree(h->d_off_out);
+        if (h->d_off_work) cudaFree(h->d_off_work);
+        h->d_mult = h->d_off_out = h->d_off_work = nullptr;
+        h->mult_cap = n + 1 + n/8;
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_mult, sizeof(int64_t)*h->mult_cap));
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_off_out, sizeof(int64_t)*h->mult_cap));
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_off_work, sizeof(int64_t)*h->mult_cap));
+    }
+    rc = ensure_capacity(h, &h->d_event_off, &h->event_off_cap, nev + 1);
+    if (rc) return rc;
+
+    // Poisson parameters per species (host, once per yields computation)
+    const iss_options &o = h->opt;
+    h->h_lambda.resize(ns);
+    h->h_pmode.resize(ns);
+    for (int s = 0; s < ns; s++) {
+        double dN = h->h_total[s];
+        if (o.hydro_mode != 2) dN = (o.y_RB - o.y_LB)*dN;     // FSSW.cpp:953-958
+        h->h_lambda[s] = dN;
+        double pm = 1.0;
+        if (dN >= 1e-15) {
+            const double m = floor(dN);
+            pm = exp(m*log(dN) - dN - lgamma(m + 1.0));
+        }
+        h->h_pmode[s] = pm;
+    }
+    if (!h->d_lambda) {
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_lambda, sizeof(double)*MAX_SPECIES));
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_pmode, sizeof(double)*MAX_SPECIES));
+    }
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_lambda, h->h_lambda.data(), sizeof(double)*ns,
+                                    cudaMemcpyHostToDevice, h->stream));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_pmode, h->h_pmode.data(), sizeof(double)*ns,
+                                    cudaMemcpyHostToDevice, h->stream));
+
+    ScopedTimer t(h, ISS_T_MULT, 1);
+    // out_count -> d_off_out (scanned in place), work_count -> d_off_work (in place)
+    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_off_out + n, 0, sizeof(int64_t), h->stream));
+    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_off_work + n, 0, sizeof(int64_t), h->stream));
+    multiplicity_kernel<<<static_cast<unsigned>((n + 255)/256), 256, 0, h->stream>>>(
+        h->d_lambda, h->d_pmode, h->d_species, ns, nev, h->ev_begin, seed,
+        o.dN_dy_sampling_model, o.local_charge_conservation, h->d_mult, h->d_off_out,
+        h->d_off_work);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    return ISS_OK;
+}
+
+int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
+    const int ns = h->nspecies;
+    const int64_t n = nev*ns;
+    int rc = ensure_momentum_tables(h);
+    if (rc) return rc;
+    int64_t total_out = 0, total_work = 0;
+    {
+        ScopedTimer t(h, ISS_T_MULT, 0);
+        rc = device_exclusive_scan_i64(h, h->d_off_out, h->d_off_out, n, &total_out);
+        if (rc) return rc;
+        rc = device_exclusive_scan_i64(h, h->d_off_work, h->d_off_work, n, &total_work);
+        if (rc) return rc;
+        event_offset_kernel<<<static_cast<unsigned>((nev + 1 + 255)/256), 256, 0, h->stream>>>(
+            h->d_off_out, ns, nev, h->d_event_off);
+        ISS_CUDA_TRY(h, cudaGetLastError());
+    }
+    rc = ensure_capacity(h, &h->d_hadrons, &h->hadron_cap, total_out);
+    if (rc) return rc;
+    if (!h->d_counters) ISS_CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned long long)*8));
+    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long)*8, h->stream));
+    h->n_hadrons = total_out;
+    if (total_work == 0) return ISS_OK;
+
+    const iss_options &o = h->opt;
+    SamplerArgs A;
+    A.cells = h->d_cells;
+    A.cellcoef = h->d_cellcoef;
+    A.ncell = h->ncell;
+    A.ncell_pad = h->ncell_pad;
+    A.ntile = h->ntile;
+    A.cdf = h->d_cdf;
+    A.tilebase = h->d_tilebase;
+    A.total = h->d_total;
+    A.species = h->d_species;
+    A.ns = ns;
+    A.nev = nev;
+    A.ev_begin = h->ev_begin;
+    A.off_work = h->d_off_work;
+    A.off_out = h->d_off_out;
+    A.nwork = total_work;
+    for (int r = 0; r < 6; r++) A.mt[r] = h->momtab[r];
+    A.mode.include_shear = o.include_deltaf_shear;
+    A.mode.include_bulk = o.include_deltaf_bulk;
+    A.mode.include_diff = o.include_deltaf_diffusion;
+    A.mode.kind = o.bulk_deltaf_kind;
+    A.mode.neos = (o.bulk_deltaf_kind == 21) ? 1 : (o.bulk_deltaf_kind == 20 ? 0 : -1);
+    A.hydro_mode = o.hydro_mode;
+    A.lcc = o.local_charge_conservation;
+    A.y_LB = o.y_LB;
+    A.y_RB = o.y_RB;
+    A.seed = seed;
+    A.out = h->d_hadrons;
+    A.counters = h->d_counters;
+
+    const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
+    int dev = 0, nsm = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sampler_kernel, SAMPLER_THREADS, smem);
+    if (occ < 1) occ = 1;
+    int64_t grid = static_cast<int64_t>(nsm)*occ;
+    const int64_t max_useful = (total_work + 31)/32/(SAMPLER_THREADS/32) + 1;
+    if (grid > max_useful) grid = max_useful;
+    {
+        ScopedTimer t(h, ISS_T_SAMPLE, 1);
+        sampler_kernel<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(A);
+    }
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    return ISS_OK;
+}
+
+}  // namespace iss

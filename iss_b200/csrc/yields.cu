@@ -1,0 +1,398 @@
+// yields.cu -- per-cell x per-species thermal yields and their cell CDF.
+//
+// Replaces FSSW::calculate_dN_dxtdy_for_one_particle_species (FSSW.cpp:565-715),
+// FSSW::calculate_dN_analytic (FSSW.cpp:719-848) and the RandomVariable1DArray
+// constructor (RandomVariable1DArray.cpp:25-52) for ALL species in one pass:
+//   K3a yields_kernel   : one thread per cell, loop over a chunk of species; the
+//                         species-independent delta-f coefficients are computed
+//                         once per cell (the reference recomputes them per species).
+//   K3b tile_scan_kernel: inclusive scan of the yields inside tiles of 1024 cells
+//                         (warp-shuffle scan) + per-tile sums.
+//   K3c tile_base_kernel: one warp per species, fixed-order exclusive prefix over
+//                         the tile sums -> tile bases and species totals.
+// All reductions have a fixed order, so totals are bit-reproducible run to run
+// and identical on every GPU that holds the same surface.
+#include "coefficients.cuh"
+
+namespace iss {
+
+struct YieldArgs {
+    const float *surf;      // [ISS_NFIELD][ncell_pad]
+    int64_t ncell, ncell_pad;
+    const DeviceSpecies *species;
+    int ns;
+    int species_per_block;
+    CoefTables tab;
+    ModeFlags mode;
+    double *yields;         // [ns][ncell_pad]
+    double *cellcoef;       // [ncell][COEF_STRIDE] by-product for the sampler
+};
+
+constexpr int YIELD_THREADS = 128;
+constexpr int YIELD_SPECIES_SMEM = 512;
+
+__device__ __forceinline__ double lerp_tab(const double *__restrict__ tb, int stride, int col,
+                                           int idx, double frac) {
+    return (1. - frac)*__ldg(&tb[static_cast<size_t>(idx)*stride + col])
+           + frac*__ldg(&tb[static_cast<size_t>(idx + 1)*stride + col]);
+}
+
+__global__ void __launch_bounds__(YIELD_THREADS)
+yields_kernel(const YieldArgs a) {
+    __shared__ DeviceSpecies sp[YIELD_SPECIES_SMEM];
+    const int s_begin = blockIdx.y*a.species_per_block;
+    const int s_end = min(a.ns, s_begin + a.species_per_block);
+    for (int i = threadIdx.x; i < s_end - s_begin; i += blockDim.x) sp[i] = a.species[s_begin + i];
+    __syncthreads();
+
+    const int64_t cell = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (cell >= a.ncell) return;
+    const float *__restrict__ S = a.surf;
+    const int64_t np = a.ncell_pad;
+#define FLD(k) __ldg(&S[static_cast<int64_t>(k)*np + cell])
+    const float Tf = FLD(ISS_F_T);
+    const float muBf = FLD(ISS_F_MUB), muSf = FLD(ISS_F_MUS), muQf = FLD(ISS_F_MUQ);
+    const double temp = Tf;
+    const double mu_B = muBf;
+    const double dsigma_dot_u = FLD(ISS_F_DA0);
+    const double Edec = FLD(ISS_F_E), Pdec = FLD(ISS_F_P), rho_B = FLD(ISS_F_NB);
+    const float bulkPif = FLD(ISS_F_BULKPI);
+
+    const ModeFlags &m = a.mode;
+    CellCoef cc;
+    cell_coefficients(a.tab, m, Edec, rho_B, temp, mu_B, cc);
+    if (blockIdx.y == 0) {
+        double *co = a.cellcoef + cell*COEF_STRIDE;
+#pragma unroll
+        for (int i = 0; i < 6; i++) co[i] = cc.c[i];
+        co[6] = cc.kappa;
+        co[7] = 0.0;
+    }
+
+    double bulkPi = 0.0;
+    if (m.include_bulk == 1) {
+        if (m.kind == 21 || m.kind == 20 || m.kind == 11 || m.kind == 0) {
+            bulkPi = bulkPif;                       // GeV/fm^3
+        } else {
+            bulkPi = static_cast<double>(bulkPif)/HBARC;   // fm^-4
+        }
+    }
+
+    double dsigma_dot_q = 0.0, prefactor_qmu = 0.0;
+    if (m.include_diff == 1) {
+        // float arithmetic as in FSSW.cpp:627-629
+        const float q = __fadd_rn(__fadd_rn(__fmul_rn(FLD(ISS_F_QX), FLD(ISS_F_DA1)),
+                                            __fmul_rn(FLD(ISS_F_QY), FLD(ISS_F_DA2))),
+                                  __fmul_rn(FLD(ISS_F_QZ), FLD(ISS_F_DA3)));
+        dsigma_dot_q = q;
+        prefactor_qmu = rho_B/(Edec + Pdec);
+    }
+#undef FLD
+
+    const double beta = 1./temp;
+    const double unit_factor = 1.0/(HBARC*HBARC*HBARC);
+    const bool hot = temp > 0.05;
+    const bool bulk_ce = (m.include_bulk == 1) && (m.kind == 1 || m.kind == 21);
+    const bool bulk_mom = (m.include_bulk == 1) && (m.kind == 11 || m.kind == 20);
+    const SfGrid sf = a.tab.sf;
+
+    for (int is = 0; is < s_end - s_begin; is++) {
+        const DeviceSpecies p = sp[is];
+        const double mass = p.mass;
+        // mu: float arithmetic, FSSW.cpp:650
+        const float muf = __fadd_rn(__fadd_rn(__fmul_rn(static_cast<float>(p.baryon), muBf),
+                                              __fmul_rn(static_cast<float>(p.strange), muSf)),
+                                    __fmul_rn(static_cast<float>(p.charge), muQf));
+        const double mu = muf;
+        const double lambda = exp(beta*mu);
+        const int truncate_order = (p.trunc10_mass && hot) ? 10 : 1;
+        const double mbeta = mass*beta;
+
+        double N_eq = 0., b1 = 0., b2 = 0., b3 = 0., q1 = 0., q2 = 0.;
+        double theta = 1.0, fugacity = 1.0;
+        for (int n = 1; n <= truncate_order; n++) {
+            const double arg = n*mass*beta;
+            if (n > 1) theta *= -static_cast<double>(p.sign);
+            fugacity *= lambda;
+            double K_1 = 0., K_2, K_3 = 0.;
+            const bool in_tab = sf_in_table(sf, arg);
+            int idx = 0;
+            double frac = 0.;
+            if (in_tab) {
+                sf_index(sf, arg, idx, frac);
+                K_2 = lerp_tab(a.tab.bessel, 3, 1, idx, frac);
+                if (m.include_bulk == 1) {
+                    K_1 = lerp_tab(a.tab.bessel, 3, 0, idx, frac);
+                    if (bulk_mom) K_3 = lerp_tab(a.tab.bessel, 3, 2, idx, frac);
+                }
+            } else {
+                bessel_k123(arg, K_1, K_2, K_3);
+            }
+            N_eq += theta/n*fugacity*K_2;
+            if (bulk_ce) {
+                b1 += theta*fugacity*(mbeta*K_1 + 3*K_2/n);
+                b2 += theta*fugacity*K_1;
+            } else if (bulk_mom) {
+                b1 += theta*fugacity*K_2;
+                b2 += theta*fugacity*(mbeta*K_1 + 3*K_2/n);
+                b3 += theta*fugacity*(mbeta*K_2 + 3*K_3/n);
+            }
+            if (m.include_diff == 1) {
+                q1 += theta/n*fugacity*K_2;
+                // FSSW.cpp:784-808
+                double En[9];
+                if (in_tab) {
+#pragma unroll
+                    for (int i = 0; i < 9; i++) En[i] = lerp_tab(a.tab.expint, 9, i, idx, frac);
+                } else {
+#pragma unroll 1
+                    for (int i = 0; i < 9; i++) En[i] = expint_en(2*i + 2, arg);
+                }
+                double I_1_n = exp(-arg)/arg*(2./(arg*arg) + 2./arg - 1./2.) + 3./8.*En[0];
+                double double_factorial = 1., factorial = 2., two_k = 4.;
+#pragma unroll
+                for (int k = 3; k <= 10; k++) {
+                    double_factorial *= (2*k - 5);
+                    factorial *= k;
+                    two_k *= 2;
+                    I_1_n += 3.*double_factorial/two_k/factorial*En[k - 2];
+                }
+                I_1_n = -(mbeta*mbeta*mbeta)*I_1_n;
+                q2 += n*theta*fugacity*I_1_n;
+            }
+        }
+        // FSSW.cpp:812-847
+        N_eq = mass*mass*temp*N_eq;
+        if (bulk_ce) {
+            b1 = mass*mass/beta*b1;
+            b2 = mass*mass*mass/3.*b2;
+            b3 = 0.0;
+        } else if (bulk_mom) {
+            b1 = mass*mass/beta*b1;
+            b2 = mass*mass/(beta*beta)*b2;
+            b3 = mass*mass*mass/(beta*beta)*b3;
+        }
+        if (m.include_diff == 1) {
+            q1 = mass*mass/(beta*beta)*q1;
+            q2 = 1./(3.*beta*beta*beta)*q2;
+        }
+
+        // FSSW.cpp:656-706
+        const double prefactor = p.gspin/(2.*M_PI*M_PI);
+        const double Neq = unit_factor*prefactor*dsigma_dot_u*N_eq;
+        double dN_bulk = 0.0;
+        if (m.include_bulk == 1) {
+            if (m.kind == 1 || m.kind == 21) {
+                dN_bulk = unit_factor*prefactor*dsigma_dot_u*(-bulkPi*cc.c[0])
+                          *(-cc.c[1]*b1 + b2);
+            } else if (m.kind == 11) {
+                dN_bulk = unit_factor*prefactor*dsigma_dot_u*bulkPi
+                          *(b1*mass*mass*cc.c[0] + b2*p.baryon*cc.c[1] + b3*cc.c[2]);
+            } else if (m.kind == 20) {
+                dN_bulk = unit_factor*prefactor*dsigma_dot_u*bulkPi
+                          *(b1*mass*mass*cc.c[2]
+                            + b2*(p.baryon*cc.c[3] + p.strange*cc.c[4] + p.charge*cc.c[5])
+                            + b3*(cc.c[1] - cc.c[2]));
+            }
+        }
+        double dN_q = 0.0;
+        if (m.include_diff == 1) {
+            dN_q = unit_factor*prefactor*dsigma_dot_q/cc.kappa
+                   *(-prefactor_qmu*q1 - p.baryon*q2);
+        }
+        const double total = Neq + dN_bulk + dN_q;
+        a.yields[static_cast<int64_t>(s_begin + is)*np + cell] = fmax(0., total);
+    }
+}
+
+// K3b: inclusive scan inside each tile of TILE cells + tile sum.  One CTA of 256
+// threads per (tile, species); each thread owns 4 consecutive cells.
+__global__ void __launch_bounds__(256)
+tile_scan_kernel(const double *__restrict__ yields, double *__restrict__ cdf,
+                 double *__restrict__ tilesum, int64_t ncell, int64_t ncell_pad, int64_t ntile) {
+    __shared__ double warp_tot[8];
+    const int64_t tile = blockIdx.x;
+    const int s = blockIdx.y;
+    const int64_t base = static_cast<int64_t>(s)*ncell_pad + tile*TILE + threadIdx.x*4;
+    const int64_t c0 = tile*TILE + threadIdx.x*4;
+    double v[4];
+    // ncell_pad is a multiple of TILE and 32-byte aligned rows: vector load
+    const double2 a = *reinterpret_cast<const double2 *>(yields + base);
+    const double2 b = *reinterpret_cast<const double2 *>(yields + base + 2);
+    v[0] = (c0 + 0 < ncell) ? a.x : 0.0;
+    v[1] = (c0 + 1 < ncell) ? a.y : 0.0;
+    v[2] = (c0 + 2 < ncell) ? b.x : 0.0;
+    v[3] = (c0 + 3 < ncell) ? b.y : 0.0;
+    v[1] += v[0];
+    v[2] += v[1];
+    v[3] += v[2];
+    double incl = v[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    double offset = incl - v[3];   // exclusive within the warp
+    double wbase = 0.0;
+    for (int w = 0; w < warp; w++) wbase += warp_tot[w];
+    offset += wbase;
+    double2 o0, o1;
+    o0.x = v[0] + offset; o0.y = v[1] + offset;
+    o1.x = v[2] + offset; o1.y = v[3] + offset;
+    *reinterpret_cast<double2 *>(cdf + base) = o0;
+    *reinterpret_cast<double2 *>(cdf + base + 2) = o1;
+    if (threadIdx.x == 255) tilesum[static_cast<int64_t>(s)*ntile + tile] = o1.y;
+}
+
+// K3c: one warp per species; exclusive prefix over tile sums in a fixed order.
+__global__ void tile_base_kernel(const double *__restrict__ tilesum, double *__restrict__ tilebase,
+                                 double *__restrict__ total, int64_t ntile) {
+    const int s = blockIdx.x;
+    const int lane = threadIdx.x;
+    double carry = 0.0;
+    for (int64_t t0 = 0; t0 < ntile; t0 += 32) {
+        const int64_t t = t0 + lane;
+        const double v = (t < ntile) ? tilesum[static_cast<int64_t>(s)*ntile + t] : 0.0;
+        double incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const double x = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += x;
+        }
+        if (t < ntile) tilebase[static_cast<int64_t>(s)*(ntile + 1) + t] = carry + (incl - v);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+        tilebase[static_cast<int64_t>(s)*(ntile + 1) + ntile] = carry;
+        total[s] = carry;
+    }
+}
+
+// fills the K_n / E_n grids on the device (FSSW::initialize_special_function_arrays)
+__global__ void build_sf_tables_kernel(double *bessel, double *expint, SfGrid g, int with_bulk,
+                                       int with_diff) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const double x = g.x_min + i*g.dx;
+    double k1, k2, k3;
+    bessel_k123(x, k1, k2, k3);
+    bessel[i*3 + 0] = with_bulk ? k1 : 0.0;
+    bessel[i*3 + 1] = k2;
+    bessel[i*3 + 2] = with_bulk ? k3 : 0.0;
+    if (with_diff) {
+        for (int k = 0; k < 9; k++) expint[i*9 + k] = expint_en(2*k + 2, x);
+    }
+}
+
+static int ensure_sf_tables(iss_handle *h) {
+    const bool need_diff = h->opt.include_deltaf_diffusion == 1;
+    if (h->d_bessel && (!need_diff || h->d_expint)) return ISS_OK;
+    // FSSW.cpp:1611-1615
+    const double sf_x_min = 0.5, sf_x_max = 400, sf_dx = 0.05;
+    SfGrid g;
+    g.x_min = sf_x_min;
+    g.dx = sf_dx;
+    g.x_max_minus_dx = sf_x_max - sf_dx;
+    g.n = static_cast<int>((sf_x_max - sf_x_min)/sf_dx) + 1;
+    if (!h->d_bessel) ISS_CUDA_TRY(h, cudaMalloc(&h->d_bessel, sizeof(double)*3*g.n));
+    if (need_diff && !h->d_expint)
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_expint, sizeof(double)*9*g.n));
+    h->sf = g;
+    build_sf_tables_kernel<<<(g.n + 127)/128, 128, 0, h->stream>>>(
+        h->d_bessel, h->d_expint, g, 1, need_diff ? 1 : 0);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    return ISS_OK;
+}
+
+int run_yields(iss_handle *h) {
+    if (h->ncell <= 0 || !h->d_surf) ISS_FAIL(h, ISS_ERR_STATE, "no surface uploaded");
+    if (h->nspecies <= 0) ISS_FAIL(h, ISS_ERR_STATE, "no species uploaded");
+    if (!h->have_opt) ISS_FAIL(h, ISS_ERR_STATE, "options not set");
+    const iss_options &o = h->opt;
+    ModeFlags mode;
+    mode.include_shear = o.include_deltaf_shear;
+    mode.include_bulk = o.include_deltaf_bulk;
+    mode.include_diff = o.include_deltaf_diffusion;
+    mode.kind = o.bulk_deltaf_kind;
+    mode.neos = (o.bulk_deltaf_kind == 21) ? 1 : (o.bulk_deltaf_kind == 20 ? 0 : -1);
+    if (mode.neos == 1 && !h->d_ce) ISS_FAIL(h, ISS_ERR_STATE, "CE delta-f table not uploaded");
+    if (mode.neos == 0 && !h->d_mom22)
+        ISS_FAIL(h, ISS_ERR_STATE, "22-moment delta-f table not uploaded");
+    if (mode.include_bulk == 1 && mode.kind == 11 && !h->d_mom14)
+        ISS_FAIL(h, ISS_ERR_STATE, "14-moment bulk table not uploaded");
+    if (mode.include_diff == 1 && !h->d_kappa)
+        ISS_FAIL(h, ISS_ERR_STATE, "kappa_B table not uploaded");
+    int rc = ensure_sf_tables(h);
+    if (rc) return rc;
+
+    const int64_t ns = h->nspecies;
+    const size_t nval = static_cast<size_t>(ns)*h->ncell_pad;
+    if (!h->d_yields) {
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_yields, sizeof(double)*nval));
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_cdf, sizeof(double)*nval));
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_tilesum, sizeof(double)*ns*h->ntile));
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_tilebase, sizeof(double)*ns*(h->ntile + 1)));
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_total, sizeof(double)*ns));
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_cellcoef, sizeof(double)*COEF_STRIDE*h->ncell));
+        // padding cells must read as zero yield
+        ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_yields, 0, sizeof(double)*nval, h->stream));
+    }
+
+    YieldArgs a;
+    a.surf = h->d_surf;
+    a.ncell = h->ncell;
+    a.ncell_pad = h->ncell_pad;
+    a.species = h->d_species;
+    a.ns = h->nspecies;
+    a.tab.bessel = h->d_bessel;
+    a.tab.expint = h->d_expint;
+    a.tab.sf = h->sf;
+    a.tab.ce = h->d_ce;
+    a.tab.mom22 = h->d_mom22;
+    a.tab.ce_n = h->ce_ne;
+    a.tab.mom14 = h->d_mom14;
+    a.tab.g14 = h->g14;
+    a.tab.kappa = h->d_kappa;
+    a.tab.gk = h->gk;
+    a.mode = mode;
+    a.yields = h->d_yields;
+    a.cellcoef = h->d_cellcoef;
+
+    const int64_t nblk_x = (h->ncell + YIELD_THREADS - 1)/YIELD_THREADS;
+    // enough CTAs to fill 148 SMs several times over, without recomputing the
+    // per-cell coefficients more often than needed
+    int chunks = 1;
+    const int64_t want = 148*16;
+    if (nblk_x < want) chunks = static_cast<int>((want + nblk_x - 1)/nblk_x);
+    if (chunks > ns) chunks = static_cast<int>(ns);
+    int spb = static_cast<int>((ns + chunks - 1)/chunks);
+    if (spb > YIELD_SPECIES_SMEM) spb = YIELD_SPECIES_SMEM;
+    chunks = static_cast<int>((ns + spb - 1)/spb);
+    a.species_per_block = spb;
+    {
+        ScopedTimer t(h, ISS_T_YIELDS);
+        dim3 grid(static_cast<unsigned>(nblk_x), chunks);
+        yields_kernel<<<grid, YIELD_THREADS, 0, h->stream>>>(a);
+    }
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    {
+        ScopedTimer t(h, ISS_T_SCAN, 2);
+        dim3 grid(static_cast<unsigned>(h->ntile), static_cast<unsigned>(ns));
+        tile_scan_kernel<<<grid, 256, 0, h->stream>>>(h->d_yields, h->d_cdf, h->d_tilesum,
+                                                      h->ncell, h->ncell_pad, h->ntile);
+        tile_base_kernel<<<static_cast<unsigned>(ns), 32, 0, h->stream>>>(
+            h->d_tilesum, h->d_tilebase, h->d_total, h->ntile);
+    }
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    h->h_total.resize(ns);
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->h_total.data(), h->d_total, sizeof(double)*ns,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->have_yields = true;
+    return ISS_OK;
+}
+
+}  // namespace iss

@@ -1,0 +1,607 @@
+// gpu_fssw.cpp -- see gpu_fssw.h.  Citations are to the reference's src/FSSW.cpp.
+#include "gpu_fssw.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+#include "logger.h"
+
+using iss_host::info;
+
+namespace {
+
+double seconds_since(const std::chrono::steady_clock::time_point &t0) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// numbers of a whitespace separated text file after `skip_lines` header lines
+std::vector<double> read_numbers(const std::string &file, int skip_lines) {
+    std::vector<double> out;
+    FILE *f = fopen(file.c_str(), "r");
+    if (!f) {
+        iss_host::error("Can not found file: " + file);
+        exit(1);
+    }
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf(n + 1);
+    const size_t got = fread(buf.data(), 1, n, f);
+    fclose(f);
+    buf[got] = '\0';
+    char *p = buf.data();
+    for (int i = 0; i < skip_lines && p; i++) {
+        p = strchr(p, '\n');
+        if (p) p++;
+    }
+    if (!p) return out;
+    out.reserve(got/12);
+    for (;;) {
+        char *e;
+        const double v = strtod(p, &e);
+        if (e == p) break;
+        out.push_back(v);
+        p = e;
+    }
+    return out;
+}
+
+}  // namespace
+
+void GpuFSSW::check_(int rc, const char *what) {
+    if (rc == ISS_OK) return;
+    std::ostringstream os;
+    os << what << " failed (status " << rc << "): " << (h_ ? iss_cuda_last_error(h_) : "no handle");
+    iss_host::error(os.str());
+    exit(rc == ISS_ERR_RANGE ? 1 : -1);
+}
+
+GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
+                 const std::vector<particle_info> &particles,
+                 const std::vector<FO_surf_LRF> &FOsurf_LRF, int flag_PCE,
+                 ParameterReader *paraRdr, std::string path, std::string table_path,
+                 AfterburnerType afterburner_type)
+    : paraRdr_(paraRdr), path_(path), table_path_(table_path),
+      afterburner_type_(afterburner_type), particles_(particles), surf_(FOsurf_LRF), seed_(seed) {
+    if (flag_PCE != 0) {
+        iss_host::error("partial chemical equilibrium EoS is not supported by the B200 engine");
+        exit(1);
+    }
+    // keys consumed on the FSSW path (FSSW.cpp:67-103)
+    hydro_mode_ = static_cast<int>(paraRdr_->getVal("hydro_mode"));
+    use_oscar_ = static_cast<int>(paraRdr_->getVal("use_OSCAR_format"));
+    use_gzip_ = static_cast<int>(paraRdr_->getVal("use_gzip_format"));
+    use_binary_ = static_cast<int>(paraRdr_->getVal("use_binary_format"));
+    include_shear_ = static_cast<int>(paraRdr_->getVal("include_deltaf_shear"));
+    include_bulk_ = static_cast<int>(paraRdr_->getVal("include_deltaf_bulk"));
+    bulk_kind_ = static_cast<int>(paraRdr_->getVal("bulk_deltaf_kind"));
+    include_diff_ = static_cast<int>(paraRdr_->getVal("include_deltaf_diffusion"));
+    number_of_repeated_sampling_ =
+        static_cast<int>(paraRdr_->getVal("number_of_repeated_sampling"));
+    (void)paraRdr_->getVal("maximum_sampling_events");
+    (void)paraRdr_->getVal("output_samples_into_files");
+    flag_perform_decays_ = (paraRdr_->getVal("perform_decays") == 1) ? 1 : 0;
+    const int spectator_mode = static_cast<int>(paraRdr_->getVal("include_spectators", 0));
+    flag_spectators_ = (spectator_mode != 0) ? 1 : 0;
+    if (flag_spectators_) read_spectators_(path_ + "/spectators.dat");
+
+    int device = 0;
+    if (const char *lr = getenv("LOCAL_RANK")) device = atoi(lr);
+    if (const char *dv = getenv("ISS_CUDA_DEVICE")) device = atoi(dv);
+    const int rc = iss_cuda_create(device, &h_);
+    if (rc != ISS_OK) {
+        iss_host::error("iss_cuda_create: no usable CUDA device (the B200 engine has no CPU "
+                        "fallback)");
+        exit(-1);
+    }
+    select_species_(chosen_monvals);
+    upload_surface_();
+    upload_tables_();
+    upload_decay_table_();
+
+    iss_options opt;
+    memset(&opt, 0, sizeof(opt));
+    opt.hydro_mode = hydro_mode_;
+    opt.include_deltaf_shear = include_shear_;
+    opt.include_deltaf_bulk = include_bulk_;
+    opt.include_deltaf_diffusion = include_diff_;
+    opt.bulk_deltaf_kind = bulk_kind_;
+    opt.dN_dy_sampling_model = static_cast<int>(paraRdr_->getVal("dN_dy_sampling_model"));
+    opt.dN_dy_sampling_para1 = paraRdr_->getVal("dN_dy_sampling_para1");
+    opt.local_charge_conservation =
+        static_cast<int>(paraRdr_->getVal("local_charge_conservation"));
+    opt.y_LB = paraRdr_->getVal("y_LB");
+    opt.y_RB = paraRdr_->getVal("y_RB");
+    if (opt.dN_dy_sampling_model > 100) {
+        std::cout << "FSSW::sample_using_dN_dxtdy_4all_particles error: sampling model "
+                  << opt.dN_dy_sampling_model << " is not supported." << std::endl;
+        exit(-1);
+    }
+    check_(iss_cuda_set_options(h_, &opt), "iss_cuda_set_options");
+}
+
+GpuFSSW::~GpuFSSW() {
+    if (h_) {
+        if (hadrons_) iss_cuda_host_free(h_, hadrons_);
+        iss_cuda_destroy(h_);
+    }
+}
+
+// chosen list -> indices into the pdg table, unknown ids dropped with a warning, then a stable
+// ascending sort by mass (the reference's bubble sort only swaps on strict >, FSSW.cpp:115-162)
+void GpuFSSW::select_species_(const std::vector<int> &chosen_monvals) {
+    std::vector<int> missing;
+    for (int monval : chosen_monvals) {
+        int found = -1;
+        for (size_t n = 0; n < particles_.size(); n++)
+            if (particles_[n].monval == monval) {
+                found = static_cast<int>(n);
+                break;
+            }
+        if (found >= 0) species_table_idx_.push_back(found);
+        else missing.push_back(monval);
+    }
+    if (!missing.empty()) {
+        iss_host::warning("not all chosen particles are in the pdg particle list!");
+        std::ostringstream os;
+        os << "There are " << missing.size() << " particles can not be found in the pdg particle list!";
+        iss_host::warning(os.str());
+        iss_host::warning("Their monte carlo numbers are:");
+        for (int m : missing) iss_host::warning(std::to_string(m));
+    }
+    std::stable_sort(species_table_idx_.begin(), species_table_idx_.end(),
+                     [&](int a, int b) { return particles_[a].mass < particles_[b].mass; });
+    for (int idx : species_table_idx_) {
+        const particle_info &p = particles_[idx];
+        iss_species s;
+        memset(&s, 0, sizeof(s));
+        s.pid = p.monval;
+        s.gspin = p.gspin;
+        s.baryon = p.baryon;
+        s.strange = p.strange;
+        s.charge = p.charge;
+        s.sign = p.sign;
+        s.decay_idx = idx;      // the decay table is uploaded in pdg-table order
+        s.mass = p.mass;
+        species_.push_back(s);
+    }
+    check_(iss_cuda_upload_species(h_, species_.data(), static_cast<int>(species_.size())),
+           "iss_cuda_upload_species");
+}
+
+void GpuFSSW::upload_surface_() {
+    const int64_t n = static_cast<int64_t>(surf_.size());
+    std::vector<float> soa(static_cast<size_t>(ISS_NFIELD)*n);
+    const float *ptrs[ISS_NFIELD];
+    for (int k = 0; k < ISS_NFIELD; k++) ptrs[k] = soa.data() + static_cast<size_t>(k)*n;
+    for (int64_t c = 0; c < n; c++) {
+        const FO_surf_LRF &s = surf_[c];
+        const float rec[ISS_NFIELD] = {
+            s.tau, s.xpt, s.ypt, s.eta,
+            s.da_mu_LRF[0], s.da_mu_LRF[1], s.da_mu_LRF[2], s.da_mu_LRF[3],
+            s.u_tz[0], s.u_tz[1], s.u_tz[2], s.u_tz[3],
+            s.Edec, s.Tdec, s.Pdec, s.Bn, s.muB, s.muS, s.muQ, s.bulkPi,
+            s.piLRF_xx, s.piLRF_xy, s.piLRF_xz, s.piLRF_yy, s.piLRF_yz,
+            s.qmuLRF_x, s.qmuLRF_y, s.qmuLRF_z};
+        for (int k = 0; k < ISS_NFIELD; k++) soa[static_cast<size_t>(k)*n + c] = rec[k];
+    }
+    check_(iss_cuda_upload_surface(h_, ptrs, n), "iss_cuda_upload_surface");
+}
+
+// delta-f coefficient tables, file formats of FSSW.cpp:1215-1376 and 1546-1568
+void GpuFSSW::upload_tables_() {
+    const bool smash = (afterburner_type_ == AfterburnerType::SMASH);
+    const std::string dir = table_path_ + "/deltaf_tables";
+    if (include_bulk_ == 1 && bulk_kind_ == 11) {
+        // c0.dat, c1.dat, c2.dat: "101", "81", one text header, then rows "T muB value" with T
+        // running fastest.  All three files have THREE header lines; the reference skips only two
+        // for c0 and ends up with an unfilled c0 table -- parsed correctly here.
+        const std::string folder = dir + (smash ? "/smash_box" : "/urqmd");
+        std::vector<double> tab;
+        double grid[4] = {0, 0, 0, 0};
+        int nT = 0, nmu = 0;
+        for (int c = 0; c < 3; c++) {
+            const std::string file = folder + "/c" + std::to_string(c) + ".dat";
+            std::vector<double> head = read_numbers(file, 0);
+            if (head.size() < 2) {
+                iss_host::error("Can not found file: " + file);
+                exit(1);
+            }
+            nT = static_cast<int>(head[0]);
+            nmu = static_cast<int>(head[1]);
+            std::vector<double> v = read_numbers(file, 3);
+            if (static_cast<long>(v.size()) < 3L*nT*nmu) {
+                iss_host::error("short 14-moment table: " + file);
+                exit(1);
+            }
+            if (c == 0) {
+                tab.assign(static_cast<size_t>(3)*nT*nmu, 0.);
+                grid[0] = v[0];                 // T0
+                grid[1] = v[3] - v[0];          // dT   (second row, FSSW.cpp:1285-1288)
+                grid[2] = v[1];                 // mu0
+                grid[3] = v[3*nT + 1] - v[1];   // dmu  (first row of the second mu block)
+            }
+            for (int j = 0; j < nmu; j++)
+                for (int i = 0; i < nT; i++)
+                    tab[(static_cast<size_t>(c)*nT + i)*nmu + j] = v[3*(static_cast<size_t>(j)*nT + i) + 2];
+        }
+        check_(iss_cuda_upload_table(h_, ISS_TABLE_MOM14, tab.data(), nT, nmu, grid),
+               "iss_cuda_upload_table(14-moment)");
+    }
+    if (bulk_kind_ == 21) {
+        const std::string file = dir + (smash ? "/smash" : "/urqmd") + "/NEoSBQS_CE_deltafCoeff.dat";
+        std::vector<double> v = read_numbers(file, 1);
+        if (v.size() < 200u*200u*5u) {
+            iss_host::error("short CE table: " + file);
+            exit(1);
+        }
+        check_(iss_cuda_upload_table(h_, ISS_TABLE_CE, v.data(), 200, 200, nullptr),
+               "iss_cuda_upload_table(CE)");
+    } else if (bulk_kind_ == 20) {
+        const std::string file =
+            dir + (smash ? "/smash" : "/urqmd") + "/NEoSBQS_22mom_deltafCoeff.dat";
+        std::vector<double> v = read_numbers(file, 1);
+        if (v.size() < 200u*200u*8u) {
+            iss_host::error("short 22-moment table: " + file);
+            exit(1);
+        }
+        check_(iss_cuda_upload_table(h_, ISS_TABLE_MOM22, v.data(), 200, 200, nullptr),
+               "iss_cuda_upload_table(22-moment)");
+    }
+    if (include_diff_ == 1) {
+        // 100 (mu_B) x 150 (T) rows "T muB kappa", T fastest; the grid is hard-coded in the
+        // reference (FSSW.cpp:1548-1553)
+        const std::string file = dir + "/Coefficients_RTA_diffusion.dat";
+        std::vector<double> v = read_numbers(file, 0);
+        const int nT = 150, nmu = 100;
+        if (static_cast<long>(v.size()) < 3L*nT*nmu) {
+            iss_host::error("short kappa_B table: " + file);
+            exit(1);
+        }
+        std::vector<double> tab(static_cast<size_t>(nT)*nmu);
+        for (int j = 0; j < nmu; j++)
+            for (int i = 0; i < nT; i++)
+                tab[static_cast<size_t>(i)*nmu + j] = v[3*(static_cast<size_t>(j)*nT + i) + 2];
+        const double grid[4] = {0.05, 0.001, 0.0, 0.007892};
+        check_(iss_cuda_upload_table(h_, ISS_TABLE_KAPPA_B, tab.data(), nT, nmu, grid),
+               "iss_cuda_upload_table(kappa_B)");
+    }
+}
+
+// the decay table is the whole pdg list (particle_decay.cpp:33-172 re-reads the same file);
+// it is uploaded always because the QA kernel takes quantum numbers from it.
+void GpuFSSW::upload_decay_table_() {
+    std::vector<iss_decay_species> sp(particles_.size());
+    std::vector<iss_decay_channel> ch;
+    for (size_t i = 0; i < particles_.size(); i++) {
+        const particle_info &p = particles_[i];
+        iss_decay_species &d = sp[i];
+        memset(&d, 0, sizeof(d));
+        d.pid = p.monval;
+        d.stable = p.stable;
+        d.n_channels = p.decays;
+        d.first_channel = static_cast<int>(ch.size());
+        d.baryon = p.baryon;
+        d.strange = p.strange;
+        d.charge = p.charge;
+        d.mass = p.mass;
+        d.width = p.width;
+        for (int j = 0; j < p.decays; j++) {
+            iss_decay_channel c;
+            memset(&c, 0, sizeof(c));
+            c.n_part = p.decay_channels[j]->decay_Npart;
+            c.branching_ratio = p.decay_channels[j]->branching_ratio;
+            for (int k = 0; k < 5; k++) {
+                c.daughter[k] = -1;
+                const int monval = p.decay_channels[j]->decay_part[k];
+                if (monval == 0) continue;
+                for (size_t n = 0; n < particles_.size(); n++)
+                    if (particles_[n].monval == monval) {
+                        c.daughter[k] = static_cast<int>(n);
+                        break;
+                    }
+            }
+            ch.push_back(c);
+        }
+    }
+    check_(iss_cuda_upload_decay_table(h_, sp.data(), static_cast<int>(sp.size()), ch.data(),
+                                       static_cast<int>(ch.size())),
+           "iss_cuda_upload_decay_table");
+}
+
+// spectators.dat: one comment line, rows "t x y z mass px py rapidity charge" (Spectators.cpp:17-52)
+void GpuFSSW::read_spectators_(const std::string &file) {
+    std::ifstream in(file.c_str());
+    if (!in.good()) {
+        std::cout << "[Error]: Spectator file : " << file << " not found!" << std::endl;
+        exit(1);
+    }
+    std::string line;
+    std::getline(in, line);
+    while (std::getline(in, line)) {
+        if (in.eof()) break;    // an unterminated last line is not used by the reference
+        std::stringstream ss(line);
+        double t, x, y, z, mass, px, py, rap;
+        int e_charge = 0;
+        if (!(ss >> t >> x >> y >> z >> mass >> px >> py >> rap >> e_charge)) continue;
+        iSS_Hadron hd;
+        hd.pid = (e_charge == 0) ? 2112 : 2212;
+        hd.mass = static_cast<float>(mass);
+        hd.t = static_cast<float>(t);
+        hd.x = static_cast<float>(x);
+        hd.y = static_cast<float>(y);
+        hd.z = static_cast<float>(z);
+        const double mT = std::sqrt(mass*mass + px*px + py*py);
+        hd.E = static_cast<float>(mT*std::cosh(rap));
+        hd.px = static_cast<float>(px);
+        hd.py = static_cast<float>(py);
+        hd.pz = static_cast<float>(mT*std::sinh(rap));
+        spectators_.push_back(hd);
+    }
+}
+
+void GpuFSSW::reserve_hadrons_(int64_t need) {
+    if (need <= hadron_cap_) return;
+    int64_t cap = std::max<int64_t>(need, hadron_cap_ + hadron_cap_/2);
+    cap = std::max<int64_t>(cap, 1024);
+    void *p = nullptr;
+    check_(iss_cuda_host_alloc(h_, &p, cap*static_cast<int64_t>(sizeof(iSS_Hadron))),
+           "iss_cuda_host_alloc");
+    if (hadrons_) {
+        memcpy(p, hadrons_, sizeof(iSS_Hadron)*event_off_.back());
+        iss_cuda_host_free(h_, hadrons_);
+    }
+    hadrons_ = static_cast<iSS_Hadron *>(p);
+    hadron_cap_ = cap;
+}
+
+void GpuFSSW::compute_yields() {
+    dN_species_.assign(species_.size(), 0.);
+    check_(iss_cuda_compute_yields(h_, dN_species_.data(), nullptr), "iss_cuda_compute_yields");
+}
+
+// FSSW::compute_number_of_sampling_needed (FSSW.cpp:851-869): uses pdg-table entry 1 as "pi+"
+int GpuFSSW::compute_number_of_sampling_needed_(int number_of_particles_needed) {
+    double dNdy_thermal_pion = 0.;
+    for (size_t n = 0; n < species_table_idx_.size(); n++)
+        if (species_table_idx_[n] == 1) dNdy_thermal_pion = dN_species_[n];
+    int nev = static_cast<int>(number_of_particles_needed/(6.*dNdy_thermal_pion));
+    if (hydro_mode_ == 2) nev *= 10;
+    const int max_ev = static_cast<int>(paraRdr_->getVal("maximum_sampling_events"));
+    return std::max(1, std::min(max_ev, nev));
+}
+
+void GpuFSSW::sample_events() {
+    const auto t0 = std::chrono::steady_clock::now();
+    info(" Function sample_using_dN_dxtdy_4all_particles started...");
+    if (dN_species_.empty()) compute_yields();
+    if (static_cast<int>(paraRdr_->getVal("sample_upto_desired_particle_number")) == 1) {
+        number_of_repeated_sampling_ = compute_number_of_sampling_needed_(
+            static_cast<int>(paraRdr_->getVal("number_of_particles_needed")));
+    }
+    info("Sampling using dN/dy with sample_using_dN_dxtdy_4all_particles function.");
+    info("number of repeated sampling = " + std::to_string(number_of_repeated_sampling_));
+    const double y_LB = paraRdr_->getVal("y_LB"), y_RB = paraRdr_->getVal("y_RB");
+    double dN_event = 0.;
+    for (size_t n = 0; n < species_.size(); n++) {
+        const particle_info &p = particles_[species_table_idx_[n]];
+        const double dN_dy = dN_species_[n];
+        const double dN = (hydro_mode_ != 2) ? (y_RB - y_LB)*dN_dy : dN_dy;
+        dN_event += dN;
+        std::ostringstream os;
+        os << "Index: " << n << ", Name: " << p.name << ", Monte-carlo index: " << p.monval;
+        info(os.str());
+        std::ostringstream os2;
+        os2 << " -- Sampling using dN_dy=" << dN_dy << ", dN=" << dN << "...";
+        info(os2.str());
+    }
+
+    nev_ = number_of_repeated_sampling_;
+    event_off_.assign(1, 0);
+    event_cache_.clear();
+    event_cache_.resize(nev_);
+
+    // events per batch from the free device memory: 40 B per hadron, x2.5 head-room for decays
+    int64_t free_b = 0, total_b = 0;
+    check_(iss_cuda_mem_info(h_, &free_b, &total_b), "iss_cuda_mem_info");
+    const double per_event = std::max(1.0, dN_event)*40.0*(flag_perform_decays_ ? 4.0 : 1.5)
+                             + 16.0*species_.size()*3;
+    int64_t batch = static_cast<int64_t>(0.5*static_cast<double>(free_b)/per_event);
+    batch = std::max<int64_t>(1, std::min<int64_t>(batch, nev_));
+    const bool decays_on = flag_perform_decays_ && afterburner_type_ != AfterburnerType::SMASH;
+    if (decays_on) std::cout << "perform resonance decays... " << std::endl;
+    const int32_t qa_pids[2] = {211, 2212};
+    reserve_hadrons_(static_cast<int64_t>(dN_event*nev_*(decays_on ? 2.0 : 1.05)) + 1024);
+
+    for (int64_t ev0 = 0; ev0 < nev_; ev0 += batch) {
+        const int64_t ev1 = std::min<int64_t>(nev_, ev0 + batch);
+        iss_counts cnt;
+        check_(iss_cuda_sample(h_, static_cast<uint64_t>(seed_), ev0, ev1, &cnt), "iss_cuda_sample");
+        if (decays_on) {
+            // FSSW::shell skips the feed-down for SMASH (FSSW.cpp:346)
+            check_(iss_cuda_decay(h_, static_cast<uint64_t>(seed_), &cnt), "iss_cuda_decay");
+        }
+        check_(iss_cuda_histograms(h_, qa_pids, 2, ev0 > 0 ? 1 : 0), "iss_cuda_histograms");
+        std::vector<int64_t> off(ev1 - ev0 + 1);
+        check_(iss_cuda_event_offsets(h_, off.data()), "iss_cuda_event_offsets");
+        const int64_t base = event_off_.back();
+        const int64_t nsp = static_cast<int64_t>(spectators_.size());
+        if (nsp == 0) {
+            reserve_hadrons_(base + cnt.n_hadrons);
+            int64_t got = 0;
+            check_(iss_cuda_fetch_all(h_, reinterpret_cast<iss_hadron *>(hadrons_ + base),
+                                      hadron_cap_ - base, &got),
+                   "iss_cuda_fetch_all");
+            for (int64_t i = 1; i <= ev1 - ev0; i++) event_off_.push_back(base + off[i]);
+        } else {
+            // spectators are appended to every event (FSSW::addSpectatorsToHadronList)
+            reserve_hadrons_(base + cnt.n_hadrons + nsp*(ev1 - ev0));
+            int64_t pos = base;
+            for (int64_t i = 0; i < ev1 - ev0; i++) {
+                int64_t got = 0;
+                check_(iss_cuda_fetch_event(h_, i, reinterpret_cast<iss_hadron *>(hadrons_ + pos),
+                                            hadron_cap_ - pos, &got),
+                       "iss_cuda_fetch_event");
+                pos += got;
+                memcpy(hadrons_ + pos, spectators_.data(), sizeof(iSS_Hadron)*nsp);
+                pos += nsp;
+                event_off_.push_back(pos);
+            }
+        }
+    }
+    if (flag_spectators_) std::cout << "Add spectators to the hadron list... " << std::endl;
+    qa_.assign(iss_cuda_qa_size(), 0.);
+    check_(iss_cuda_qa_fetch(h_, qa_.data()), "iss_cuda_qa_fetch");
+    std::cout << std::endl
+              << "sample_using_dN_dxtdy_4all_particles finished in " << seconds_since(t0)
+              << " seconds." << std::endl;
+}
+
+void GpuFSSW::shell() {
+    compute_yields();
+    sample_events();
+    computeAvgTotalEnergyMomentum();
+    // priority OSCAR > gzip > binary (FSSW.cpp:354-360)
+    if (use_oscar_) combine_samples_to_OSCAR();
+    else if (use_gzip_) combine_samples_to_gzip_file();
+    else if (use_binary_) combine_samples_to_binary_file();
+}
+
+std::vector<iSS_Hadron> *GpuFSSW::get_hadron_list_iev(const int iev) {
+    if (iev < 0 || iev >= nev_) {
+        iss_host::error("get_hadron_list_iev: event index out of range");
+        exit(-1);
+    }
+    if (!event_cache_[iev]) {
+        event_cache_[iev].reset(new std::vector<iSS_Hadron>(hadrons_ + event_off_[iev],
+                                                            hadrons_ + event_off_[iev + 1]));
+    }
+    return event_cache_[iev].get();
+}
+
+// FSSW::computeAvgTotalEnergyMomentum (FSSW.cpp:2028-2059)
+void GpuFSSW::computeAvgTotalEnergyMomentum() {
+    double avg[4] = {0, 0, 0, 0}, err[4] = {0, 0, 0, 0};
+    for (int64_t ev = 0; ev < nev_; ev++) {
+        double P[4] = {0, 0, 0, 0};
+        for (int64_t i = event_off_[ev]; i < event_off_[ev + 1]; i++) {
+            P[0] += hadrons_[i].E;
+            P[1] += hadrons_[i].px;
+            P[2] += hadrons_[i].py;
+            P[3] += hadrons_[i].pz;
+        }
+        for (int j = 0; j < 4; j++) {
+            avg[j] += P[j];
+            err[j] += P[j]*P[j];
+        }
+    }
+    info("Averaged total energy and momentum:");
+    for (int i = 0; i < 4; i++) {
+        avg[i] /= nev_;
+        err[i] = std::sqrt((err[i]/nev_ - avg[i]*avg[i])/nev_);
+        std::ostringstream os;
+        os << "<P[" << i << "]> = " << avg[i] << " +/- " << err[i] << " GeV.";
+        info(os.str());
+    }
+}
+
+// OSCAR1997A text (FSSW.cpp:365-494): header file verbatim, per non-empty event a line
+// "iev(0-based) N 0 0", per hadron "index pid" + px py pz E m x y z t in %24.16e
+void GpuFSSW::combine_samples_to_OSCAR() {
+    const auto t0 = std::chrono::steady_clock::now();
+    info(" -- Now combine sample files to OSCAR file...");
+    const std::string header_file = table_path_ + "/OSCAR_header.txt";
+    remove("OSCAR.DAT");
+    std::ofstream oscar("OSCAR.DAT");
+    std::ifstream header(header_file.c_str());
+    if (!header.is_open()) {
+        std::cout << std::endl
+                  << "combine_samples_to_OSCAR error: OSCAR header file " << header_file
+                  << " not found." << std::endl;
+        exit(-1);
+    }
+    std::string line;
+    while (std::getline(header, line)) {
+        if (header.eof()) break;    // the reference drops an unterminated last line
+        oscar << line << std::endl;
+    }
+    char buf[512];
+    for (int64_t ev = 0; ev < nev_; ev++) {
+        const int64_t n = event_off_[ev + 1] - event_off_[ev];
+        if (n <= 0) continue;
+        oscar << std::setw(10) << ev << "  " << std::setw(10) << n << "  " << std::setw(8) << 0.0
+              << "  " << std::setw(8) << 0.0 << std::endl;
+        for (int64_t i = 0; i < n; i++) {
+            const iSS_Hadron &hd = hadrons_[event_off_[ev] + i];
+            oscar << std::setw(10) << i + 1 << "  " << std::setw(10) << hd.pid << "  ";
+            snprintf(buf, sizeof(buf),
+                     "%24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e",
+                     hd.px, hd.py, hd.pz, hd.E, hd.mass, hd.x, hd.y, hd.z, hd.t);
+            oscar << buf << std::endl;
+        }
+    }
+    std::cout << std::endl
+              << " -- combine_samples_to_OSCAR samples finishes " << seconds_since(t0)
+              << " seconds." << std::endl;
+}
+
+// particle_samples.gz (FSSW.cpp:497-526)
+void GpuFSSW::combine_samples_to_gzip_file() {
+    const auto t0 = std::chrono::steady_clock::now();
+    info(" -- Now combine sample files to a gzip file...");
+    remove("particle_samples.gz");
+    gzFile fp = gzopen("particle_samples.gz", "wb");
+    for (int64_t ev = 0; ev < nev_; ev++) {
+        const int n = static_cast<int>(event_off_[ev + 1] - event_off_[ev]);
+        gzprintf(fp, "%d \n", n);
+        for (int64_t i = event_off_[ev]; i < event_off_[ev + 1]; i++) {
+            const iSS_Hadron &hd = hadrons_[i];
+            gzprintf(fp, "%d ", hd.pid);
+            gzprintf(fp, "%.7e %.7e %.7e %.7e %.7e %.7e %.7e %.7e %.7e\n", hd.mass, hd.t, hd.x,
+                     hd.y, hd.z, hd.E, hd.px, hd.py, hd.pz);
+        }
+    }
+    gzclose(fp);
+    std::cout << std::endl
+              << " -- combine_samples_to_gzip_file finishes " << seconds_since(t0) << " seconds."
+              << std::endl;
+}
+
+// particle_samples.bin (FSSW.cpp:529-561): int N, then per hadron int pid + 9 floats
+// {mass, t, x, y, z, E, px, py, pz}
+void GpuFSSW::combine_samples_to_binary_file() {
+    const auto t0 = std::chrono::steady_clock::now();
+    info(" -- Now combine sample files to a binary file...");
+    remove("particle_samples.bin");
+    FILE *out = fopen("particle_samples.bin", "wb");
+    std::vector<char> rec;
+    for (int64_t ev = 0; ev < nev_; ev++) {
+        const int n = static_cast<int>(event_off_[ev + 1] - event_off_[ev]);
+        rec.resize(sizeof(int) + static_cast<size_t>(n)*40);
+        char *p = rec.data();
+        memcpy(p, &n, sizeof(int));
+        p += sizeof(int);
+        for (int64_t i = event_off_[ev]; i < event_off_[ev + 1]; i++) {
+            const iSS_Hadron &hd = hadrons_[i];
+            const float a[9] = {hd.mass, hd.t, hd.x, hd.y, hd.z, hd.E, hd.px, hd.py, hd.pz};
+            memcpy(p, &hd.pid, sizeof(int));
+            memcpy(p + sizeof(int), a, sizeof(a));
+            p += 40;
+        }
+        fwrite(rec.data(), 1, rec.size(), out);
+    }
+    fclose(out);
+    std::cout << std::endl
+              << " -- combine_samples_to_binary_file finishes " << seconds_since(t0) << " seconds."
+              << std::endl;
+}

@@ -1,0 +1,167 @@
+// oracle/ref_driver.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Drives the UNMODIFIED reference sources (compiled where they lie under
+// /root/reference/src by oracle/Makefile, objects only into oracle/_ref/) and
+// dumps intermediate results of the hot path so that the CUDA product and the
+// numpy restatement (oracle/iss_oracle.py) can be pinned against the reference
+// itself.  Nothing in the product links or executes this file.
+//
+//   ref_driver yields  <param_file> <work_path> <surface_file> <out_prefix> [key=value ...]
+//       -> <out_prefix>.lrf.bin      int64 ncell, then ncell x 28 float32 (FO_surf_LRF order below)
+//          <out_prefix>.species.txt  one line per chosen species in sampling order:
+//                                    monval mass gspin baryon strange charge sign stable
+//          <out_prefix>.yields.bin   int64 nspecies, int64 ncell, then nspecies x ncell float64
+//                                    = FSSW::dN_dxtdy_for_one_particle_species (FSSW.cpp:565-715)
+//   ref_driver momentum <m> <T> <mu> <sign> <n> <seed> <out.bin>
+//       -> n float64 |p| samples of MomentumSamplerShell::Sample_a_momentum (MomentumSamplerShell.cpp:24)
+//   ref_driver decay <table_path> <afterburner 1|2> <pid> <n> <seed> <out.bin>
+//       -> n mothers at rest-ish (fixed momentum) decayed once with particle_decay::perform_decays
+//          (particle_decay.cpp:265); records: int32 ndaughters then ndaughters x iSS_Hadron (40 B)
+#include <string>
+#include <vector>
+#include <memory>
+#include <array>
+#include <sstream>
+#include <iostream>
+#include <fstream>
+#include <random>
+#include <cmath>
+#include <iomanip>
+#include <cstdio>
+#include <cstdint>
+#include <cstring>
+#include <gsl/gsl_rng.h>
+#include <gsl/gsl_randist.h>
+
+#define private public
+#include "iSS.h"
+#undef private
+
+static void write_lrf(const std::vector<FO_surf_LRF> &surf, const std::string &fn) {
+    FILE *f = fopen(fn.c_str(), "wb");
+    int64_t n = surf.size();
+    fwrite(&n, sizeof(n), 1, f);
+    for (auto const &s : surf) {
+        float rec[28] = {
+            s.tau, s.xpt, s.ypt, s.eta,
+            s.da_mu_LRF[0], s.da_mu_LRF[1], s.da_mu_LRF[2], s.da_mu_LRF[3],
+            s.u_tz[0], s.u_tz[1], s.u_tz[2], s.u_tz[3],
+            s.Edec, s.Tdec, s.Pdec, s.Bn, s.muB, s.muS, s.muQ, s.bulkPi,
+            s.piLRF_xx, s.piLRF_xy, s.piLRF_xz, s.piLRF_yy, s.piLRF_yz,
+            s.qmuLRF_x, s.qmuLRF_y, s.qmuLRF_z};
+        fwrite(rec, sizeof(float), 28, f);
+    }
+    fclose(f);
+}
+
+static int run_yields(int argc, char **argv) {
+    if (argc < 6) { std::cerr << "usage: yields param path surface out_prefix [k=v]\n"; return 2; }
+    std::string param = argv[2], path = argv[3], surface = argv[4], out = argv[5];
+    iSS sampler(path, "iSS_tables", "iSS_tables", param, surface);
+    for (int i = 6; i < argc; i++) sampler.paraRdr_ptr->phraseOneLine(argv[i]);
+    sampler.read_in_FO_surface();
+    sampler.set_random_seed(1);
+    write_lrf(sampler.FOsurf_LRF_array_, out + ".lrf.bin");
+
+    // same construction as iSS::generate_samples (iSS.cpp:130-149)
+    Table chosen_particles;
+    if (sampler.afterburner_type_ == AfterburnerType::SMASH) {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_SMASH.dat");
+    } else if (sampler.afterburner_type_ == AfterburnerType::UrQMD) {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_urqmd_v3.3+.dat");
+    } else {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_s95p-v1.dat");
+    }
+    FSSW fssw(sampler.ran_gen_ptr_, &chosen_particles, sampler.particle_,
+              sampler.FOsurf_LRF_array_, sampler.flag_PCE_, sampler.paraRdr_ptr,
+              path, "iSS_tables", sampler.afterburner_type_);
+
+    int fix_c0 = static_cast<int>(sampler.paraRdr_ptr->getVal("oracle_fix_14mom_c0", 0));
+    if (fix_c0 == 1 && fssw.INCLUDE_BULK_DELTAF == 1 && fssw.bulk_deltaf_kind_ == 11) {
+        // FSSW::load_bulk_deltaf_14mom_table (FSSW.cpp:1246-1256) leaves the
+        // c0 table uninitialised; overwrite it with the correctly parsed file so that
+        // kind 11 has a well-defined oracle (documented deviation).
+        std::string folder = (sampler.afterburner_type_ == AfterburnerType::SMASH)
+                                 ? "/smash_box" : "/urqmd";
+        std::ifstream c0("iSS_tables/deltaf_tables" + folder + "/c0.dat");
+        std::string dummy;
+        for (int i = 0; i < 3; i++) std::getline(c0, dummy);
+        double t1, t2;
+        for (int j = 0; j < fssw.deltaf_bulk_coeff_14mom_table_length_mu_; j++)
+            for (int i = 0; i < fssw.deltaf_bulk_coeff_14mom_table_length_T_; i++)
+                c0 >> t1 >> t2 >> fssw.deltaf_bulk_coeff_14mom_c0_tb_[i][j];
+    }
+
+    int ns = fssw.number_of_chosen_particles;
+    int64_t ncell = sampler.FOsurf_LRF_array_.size();
+    std::ofstream sp(out + ".species.txt");
+    sp << std::setprecision(17);
+    FILE *f = fopen((out + ".yields.bin").c_str(), "wb");
+    int64_t ns64 = ns;
+    fwrite(&ns64, sizeof(ns64), 1, f);
+    fwrite(&ncell, sizeof(ncell), 1, f);
+    for (int n = 0; n < ns; n++) {
+        int idx = fssw.chosen_particles_sampling_table[n];
+        const particle_info &p = fssw.particles[idx];
+        sp << p.monval << " " << p.mass << " " << p.gspin << " " << p.baryon << " "
+           << p.strange << " " << p.charge << " " << p.sign << " " << p.stable << "\n";
+        fssw.calculate_dN_dxtdy_for_one_particle_species(idx);
+        fwrite(fssw.dN_dxtdy_for_one_particle_species.data(), sizeof(double), ncell, f);
+    }
+    fclose(f);
+    return 0;
+}
+
+static int run_momentum(int argc, char **argv) {
+    if (argc < 9) { std::cerr << "usage: momentum m T mu sign n seed out\n"; return 2; }
+    double m = atof(argv[2]), T = atof(argv[3]), mu = atof(argv[4]);
+    int sign = atoi(argv[5]);
+    long n = atol(argv[6]);
+    long seed = atol(argv[7]);
+    auto ran = std::make_shared<RandomUtil::Random>(seed);
+    MomentumSamplerShell shell(ran);
+    std::vector<double> out(n);
+    for (long i = 0; i < n; i++) out[i] = shell.Sample_a_momentum(m, T, mu, sign);
+    FILE *f = fopen(argv[8], "wb");
+    fwrite(out.data(), sizeof(double), n, f);
+    fclose(f);
+    return 0;
+}
+
+static int run_decay(int argc, char **argv) {
+    if (argc < 8) { std::cerr << "usage: decay table_path afterburner pid n seed out\n"; return 2; }
+    std::string table_path = argv[2];
+    AfterburnerType ab = (atoi(argv[3]) == 2) ? AfterburnerType::SMASH : AfterburnerType::UrQMD;
+    int pid = atoi(argv[4]);
+    long n = atol(argv[5]);
+    long seed = atol(argv[6]);
+    auto ran = std::make_shared<RandomUtil::Random>(seed);
+    particle_decay decayer(ran, ab, table_path);
+    FILE *f = fopen(argv[7], "wb");
+    for (long i = 0; i < n; i++) {
+        iSS_Hadron mother;
+        mother.pid = pid;
+        mother.mass = decayer.get_particle_mass(pid);
+        mother.px = 0.3f; mother.py = -0.2f; mother.pz = 0.5f;
+        mother.E = std::sqrt(mother.mass*mother.mass + mother.px*mother.px
+                             + mother.py*mother.py + mother.pz*mother.pz);
+        mother.t = 1.f; mother.x = 0.5f; mother.y = -0.5f; mother.z = 0.25f;
+        std::vector<iSS_Hadron> daughters;
+        decayer.perform_decays(&mother, &daughters);
+        int32_t nd = daughters.size();
+        fwrite(&nd, sizeof(nd), 1, f);
+        fwrite(daughters.data(), sizeof(iSS_Hadron), nd, f);
+    }
+    fclose(f);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    if (argc < 2) { std::cerr << "usage: ref_driver yields|momentum|decay ...\n"; return 2; }
+    std::string mode = argv[1];
+    if (mode == "yields") return run_yields(argc, argv);
+    if (mode == "momentum") return run_momentum(argc, argv);
+    if (mode == "decay") return run_decay(argc, argv);
+    std::cerr << "unknown mode " << mode << "\n";
+    return 2;
+}
