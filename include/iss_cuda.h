@@ -23,6 +23,14 @@
 extern "C" {
 #endif
 
+/* entry points are the only symbols libiss_cuda.so exports (it is built with
+ * -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define ISS_API __attribute__((visibility("default")))
+#else
+#define ISS_API
+#endif
+
 typedef struct iss_handle iss_handle;
 
 enum {
@@ -155,71 +163,78 @@ typedef struct {
 #define ISS_QA_PER (3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + 2*ISS_QA_NV2 + 2)
 
 /* ---- lifetime ---------------------------------------------------------- */
-int iss_cuda_create(int device, iss_handle **out);
-int iss_cuda_destroy(iss_handle *h);
-const char *iss_cuda_last_error(const iss_handle *h);
+ISS_API int iss_cuda_create(int device, iss_handle **out);
+ISS_API int iss_cuda_destroy(iss_handle *h);
+ISS_API const char *iss_cuda_last_error(const iss_handle *h);
 /* Run all work of this handle on an existing CUDA stream (cudaStream_t passed as void*). */
-int iss_cuda_set_stream(iss_handle *h, void *cuda_stream);
-int iss_cuda_synchronize(iss_handle *h);
+ISS_API int iss_cuda_set_stream(iss_handle *h, void *cuda_stream);
+ISS_API int iss_cuda_synchronize(iss_handle *h);
 
 /* ---- inputs (replace the std::vector<FO_surf_LRF>/particle tables FSSW's ctor takes,
  *      FSSW.cpp:43-201) -------------------------------------------------- */
-int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], int64_t ncell);
-int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t nspecies);
-int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data,
+ISS_API int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], int64_t ncell);
+ISS_API int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t nspecies);
+ISS_API int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data,
                           int64_t n0, int64_t n1, const double *grid4);
-int iss_cuda_upload_decay_table(iss_handle *h, const iss_decay_species *sp, int32_t nsp,
+ISS_API int iss_cuda_upload_decay_table(iss_handle *h, const iss_decay_species *sp, int32_t nsp,
                                 const iss_decay_channel *ch, int32_t nch);
-int iss_cuda_set_options(iss_handle *h, const iss_options *opt);
+ISS_API int iss_cuda_set_options(iss_handle *h, const iss_options *opt);
 
 /* ---- yields: FSSW::calculate_dN_dxtdy_for_one_particle_species for every species
  *      (FSSW.cpp:565-715, 719-848) + RandomVariable1DArray ctor (RandomVariable1DArray.cpp:25-52).
  *      dN_species_host[ns]  <- sum over cells (NOT yet multiplied by y_RB - y_LB);
  *      yields_host (may be NULL) <- [ns][ncell] FP64 per-cell yields.                */
-int iss_cuda_compute_yields(iss_handle *h, double *dN_species_host, double *yields_host);
+ISS_API int iss_cuda_compute_yields(iss_handle *h, double *dN_species_host, double *yields_host);
 
 /* ---- sampling: FSSW::sample_using_dN_dxtdy_4all_particles_conventional (FSSW.cpp:873-1071)
  *      for events [ev_begin, ev_end): multiplicities, offsets, momenta, boost, emit. */
-int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_end,
+ISS_API int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_end,
                     iss_counts *out);
 /* multiplicity table of the last batch: counts_host[(ev-ev_begin)*ns + s]              */
-int iss_cuda_get_multiplicities(iss_handle *h, int64_t *counts_host);
+ISS_API int iss_cuda_get_multiplicities(iss_handle *h, int64_t *counts_host);
 /* Poisson parameters the draws used: lambda[s], mode pmf pm[s] (for bit-exact CPU checks) */
-int iss_cuda_get_poisson_params(iss_handle *h, double *lambda_host, double *pmode_host);
+ISS_API int iss_cuda_get_poisson_params(iss_handle *h, double *lambda_host, double *pmode_host);
+
+/* ---- trace (test instrumentation): when enabled, the sampler also records for every output
+ *      slot of the batch the cell it was emitted from and the number of accept/reject
+ *      proposals it took; cell_host / tries_host receive n_hadrons int32 each (primaries,
+ *      before iss_cuda_decay).                                                          */
+ISS_API int iss_cuda_set_trace(iss_handle *h, int enable);
+ISS_API int iss_cuda_get_trace(iss_handle *h, int32_t *cell_host, int32_t *tries_host);
 
 /* ---- decays: FSSW::perform_resonance_feed_down + particle_decay (FSSW.cpp:1746-1779,
  *      particle_decay.cpp:265-546) on the batch held by the handle.                    */
-int iss_cuda_decay(iss_handle *h, uint64_t seed, iss_counts *out);
+ISS_API int iss_cuda_decay(iss_handle *h, uint64_t seed, iss_counts *out);
 
 /* ---- outputs (replace Hadron_list accessors, FSSW.h:166-184) ------------------- */
 /* event_offsets_host[n_events+1]: exclusive prefix of hadrons per event of the batch.  */
-int iss_cuda_event_offsets(iss_handle *h, int64_t *event_offsets_host);
-int iss_cuda_fetch_event(iss_handle *h, int64_t iev_in_batch, iss_hadron *dst, int64_t cap,
+ISS_API int iss_cuda_event_offsets(iss_handle *h, int64_t *event_offsets_host);
+ISS_API int iss_cuda_fetch_event(iss_handle *h, int64_t iev_in_batch, iss_hadron *dst, int64_t cap,
                          int64_t *n);
 /* whole batch, event-major; dst may be pinned memory. */
-int iss_cuda_fetch_all(iss_handle *h, iss_hadron *dst, int64_t cap, int64_t *n);
+ISS_API int iss_cuda_fetch_all(iss_handle *h, iss_hadron *dst, int64_t cap, int64_t *n);
 /* device pointer of the batch (for callers that keep the list on the GPU). */
-int iss_cuda_device_hadrons(iss_handle *h, const void **dptr, int64_t *n);
+ISS_API int iss_cuda_device_hadrons(iss_handle *h, const void **dptr, int64_t *n);
 
 /* ---- QA: iSS::perform_checks + Histogram (iSS.cpp:59-83, 296-363): fills a block of
  *      doubles on the DEVICE (so that NCCL can reduce it in place) and optionally copies it. */
-int64_t iss_cuda_qa_size(void);                   /* number of doubles in the QA block */
-int iss_cuda_histograms(iss_handle *h, const int32_t *pids, int32_t npid, int accumulate);
-int iss_cuda_qa_device_ptr(iss_handle *h, void **dptr);
-int iss_cuda_qa_fetch(iss_handle *h, double *dst_host);
+ISS_API int64_t iss_cuda_qa_size(void);                   /* number of doubles in the QA block */
+ISS_API int iss_cuda_histograms(iss_handle *h, const int32_t *pids, int32_t npid, int accumulate);
+ISS_API int iss_cuda_qa_device_ptr(iss_handle *h, void **dptr);
+ISS_API int iss_cuda_qa_fetch(iss_handle *h, double *dst_host);
 
 /* ---- timing: accumulated device time (CUDA events on the handle's stream) per kernel family */
 enum { ISS_T_YIELDS = 0, ISS_T_SCAN, ISS_T_MULT, ISS_T_SAMPLE, ISS_T_DECAY, ISS_T_QA, ISS_T_NKIND };
-int iss_cuda_timing(iss_handle *h, int enable, double *ms_host /*[ISS_T_NKIND]*/,
+ISS_API int iss_cuda_timing(iss_handle *h, int enable, double *ms_host /*[ISS_T_NKIND]*/,
                     int64_t *launches_host /*[ISS_T_NKIND]*/, int reset);
 
 /* ---- memory helpers for the host facade (pinned staging buffers, batch sizing) */
-int iss_cuda_mem_info(iss_handle *h, int64_t *free_bytes, int64_t *total_bytes);
-int iss_cuda_host_alloc(iss_handle *h, void **ptr, int64_t bytes);   /* cudaHostAlloc */
-int iss_cuda_host_free(iss_handle *h, void *ptr);
+ISS_API int iss_cuda_mem_info(iss_handle *h, int64_t *free_bytes, int64_t *total_bytes);
+ISS_API int iss_cuda_host_alloc(iss_handle *h, void **ptr, int64_t bytes);   /* cudaHostAlloc */
+ISS_API int iss_cuda_host_free(iss_handle *h, void *ptr);
 
 /* ---- FP64 pipe probe: dependent-free DFMA loop, returns achieved TFLOP/s (2 flop per FMA). */
-int iss_cuda_fp64_peak(iss_handle *h, double *tflops);
+ISS_API int iss_cuda_fp64_peak(iss_handle *h, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -107,7 +107,7 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_mult); cudaFree(h->d_off_out); cudaFree(h->d_off_work);
     cudaFree(h->d_hadrons); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
-    cudaFree(h->d_qa);
+    cudaFree(h->d_qa); cudaFree(h->d_trace);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -378,6 +378,24 @@ int iss_cuda_get_poisson_params(iss_handle *h, double *lambda_host, double *pmod
     if (h->h_lambda.empty()) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
     if (lambda_host) memcpy(lambda_host, h->h_lambda.data(), sizeof(double)*h->nspecies);
     if (pmode_host) memcpy(pmode_host, h->h_pmode.data(), sizeof(double)*h->nspecies);
+    return ISS_OK;
+}
+
+int iss_cuda_set_trace(iss_handle *h, int enable) {
+    if (!h) return ISS_ERR_ARG;
+    h->trace = (enable != 0);
+    return ISS_OK;
+}
+
+int iss_cuda_get_trace(iss_handle *h, int32_t *cell_host, int32_t *tries_host) {
+    if (!h || !cell_host || !tries_host) return ISS_ERR_ARG;
+    if (!h->have_batch || !h->trace || !h->d_trace)
+        ISS_FAIL(h, ISS_ERR_STATE, "no traced batch (iss_cuda_set_trace before iss_cuda_sample)");
+    const size_t nb = sizeof(int32_t)*h->n_primaries;
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(cell_host, h->d_trace, nb, cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(tries_host, h->d_trace + h->trace_cap, nb,
+                                    cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return ISS_OK;
 }
 

@@ -116,6 +116,10 @@ struct iss_handle {
     int64_t event_off_cap = 0;
     unsigned long long *d_counters = nullptr;   // [8] tries, redraws, error flags...
     bool have_batch = false;
+    bool trace = false;
+    int32_t *d_trace = nullptr;         // [2][trace_cap]: cell, tries per output slot
+    int64_t trace_cap = 0;
+    int64_t n_primaries = 0;
     bool decayed = false;
     iss_hadron *d_hadrons2 = nullptr;   // decay output
     int64_t hadron2_cap = 0;

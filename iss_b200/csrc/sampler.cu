@@ -190,6 +190,8 @@ struct SamplerArgs {
     uint64_t seed;
     iss_hadron *out;
     unsigned long long *counters;   // [0] work cursor, [1] tries, [2] redraws, [3] range errors
+    int32_t *trace_cell;            // optional [n_out]
+    int32_t *trace_tries;           // optional [n_out]
 };
 
 constexpr int SAMPLER_THREADS = 128;
@@ -211,6 +213,7 @@ struct LaneState {
     // accept set-up
     double dsigma_fac;
     int tries;
+    int total_tries;
     int phase;      // 0 primary, 1 charge-conservation partner
     int qsign;      // +1 primary, -1 partner (flips B,S,Q)
 };
@@ -397,6 +400,10 @@ sampler_kernel(const SamplerArgs A) {
                 dst[2] = make_float2(hd.py, hd.pz);
                 dst[3] = make_float2(hd.t, hd.x);
                 dst[4] = make_float2(hd.y, hd.z);
+                if (A.trace_cell) {
+                    A.trace_cell[L.out_slot] = static_cast<int32_t>(L.cell);
+                    A.trace_tries[L.out_slot] = L.total_tries;
+                }
                 pending = false;
                 if (A.lcc == 1 && L.phase == 0 && p.charge > 0) {
                     // partner with opposite quantum numbers from the SAME cell (FSSW.cpp:1035-1048)
@@ -404,6 +411,7 @@ sampler_kernel(const SamplerArgs A) {
                     L.qsign = -1;
                     L.out_slot += 1;
                     L.tries = 1;
+                    L.total_tries = 0;
                     const float4 th = __ldg(cr + 4);    // muB, muS, muQ, bulkPi
                     const float4 th0 = __ldg(cr + 3);   // E, T, P, nB
                     const float muf = __fadd_rn(
@@ -464,6 +472,7 @@ sampler_kernel(const SamplerArgs A) {
                     L.qsign = 1;
                     L.cell = -1;
                     L.tries = MAX_IMPATIENCE;   // forces a cell draw below
+                    L.total_tries = 0;
                     busy = true;
                 }
                 chunk_next += take;
@@ -516,6 +525,7 @@ sampler_kernel(const SamplerArgs A) {
             const double u_inner = L.rng.next();
             if (!(u_inner > accept_ratio)) {
                 my_tries++;
+                L.total_tries++;
                 // FSSW.cpp:1880-1945
                 const double phi = 2*M_PI*L.rng.next();
                 const double cos_theta = 2.*L.rng.next() - 1.;
@@ -730,6 +740,19 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.seed = seed;
     A.out = h->d_hadrons;
     A.counters = h->d_counters;
+    A.trace_cell = nullptr;
+    A.trace_tries = nullptr;
+    h->n_primaries = total_out;
+    if (h->trace) {
+        if (total_out > h->trace_cap || !h->d_trace) {
+            if (h->d_trace) cudaFree(h->d_trace);
+            h->d_trace = nullptr;
+            h->trace_cap = total_out + 1024;
+            ISS_CUDA_TRY(h, cudaMalloc(&h->d_trace, sizeof(int32_t)*2*h->trace_cap));
+        }
+        A.trace_cell = h->d_trace;
+        A.trace_tries = h->d_trace + h->trace_cap;
+    }
 
     const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
     int dev = 0, nsm = 148, occ = 1;

@@ -139,16 +139,17 @@ GpuFSSW::~GpuFSSW() {
 
 // chosen list -> indices into the pdg table, unknown ids dropped with a warning, then a stable
 // ascending sort by mass (the reference's bubble sort only swaps on strict >, FSSW.cpp:115-162)
-void GpuFSSW::select_species_(const std::vector<int> &chosen_monvals) {
-    std::vector<int> missing;
+std::vector<int> GpuFSSW::order_species(const std::vector<int> &chosen_monvals,
+                                        const std::vector<particle_info> &particles) {
+    std::vector<int> order, missing;
     for (int monval : chosen_monvals) {
         int found = -1;
-        for (size_t n = 0; n < particles_.size(); n++)
-            if (particles_[n].monval == monval) {
+        for (size_t n = 0; n < particles.size(); n++)
+            if (particles[n].monval == monval) {
                 found = static_cast<int>(n);
                 break;
             }
-        if (found >= 0) species_table_idx_.push_back(found);
+        if (found >= 0) order.push_back(found);
         else missing.push_back(monval);
     }
     if (!missing.empty()) {
@@ -159,8 +160,13 @@ void GpuFSSW::select_species_(const std::vector<int> &chosen_monvals) {
         iss_host::warning("Their monte carlo numbers are:");
         for (int m : missing) iss_host::warning(std::to_string(m));
     }
-    std::stable_sort(species_table_idx_.begin(), species_table_idx_.end(),
-                     [&](int a, int b) { return particles_[a].mass < particles_[b].mass; });
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int a, int b) { return particles[a].mass < particles[b].mass; });
+    return order;
+}
+
+void GpuFSSW::select_species_(const std::vector<int> &chosen_monvals) {
+    species_table_idx_ = order_species(chosen_monvals, particles_);
     for (int idx : species_table_idx_) {
         const particle_info &p = particles_[idx];
         iss_species s;

@@ -24,6 +24,11 @@ class GpuFSSW {
             std::string path, std::string table_path, AfterburnerType afterburner_type);
     ~GpuFSSW();
 
+    // chosen list -> indices into the pdg table in sampling order: unknown ids dropped with a
+    // warning, stable ascending sort by mass (FSSW.cpp:115-162).  Needs no GPU.
+    static std::vector<int> order_species(const std::vector<int> &chosen_monvals,
+                                          const std::vector<particle_info> &particles);
+
     void shell();       // it all starts here, as in FSSW::shell (FSSW.cpp:344-361)
 
     // pieces of shell(), public so that hosts/tests can drive them separately

@@ -76,6 +76,10 @@ class iSS {
     void getParticleQuantumNumbers(long monval, std::array<int, 3> &Qarr);
 
     // additions of the B200 engine (not in the reference API)
+    std::vector<int> read_chosen_particles() const;
+    // builds the device sampler (uploads surface, species and tables) without sampling, so that
+    // hosts can drive the C ABI (include/iss_cuda.h) on get_sampler()->cuda_handle() themselves
+    int prepare_sampler();
     GpuFSSW *get_sampler() { return spectra_sampler_.get(); }
     const std::vector<FO_surf_LRF> &get_LRF_surface() const { return FOsurf_LRF_array_; }
     const std::vector<particle_info> &get_particle_table() const { return particle_; }

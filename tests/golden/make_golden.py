@@ -1,0 +1,243 @@
+#!/usr/bin/env python3
+"""Generates the golden fixtures under tests/golden/ by running the UNMODIFIED reference
+(compiled by oracle/Makefile into oracle/_ref/) in THIS container.  The fixtures travel to the
+GPU box; /root/reference does not.
+
+    python tests/golden/make_golden.py [yields] [stats] [momentum] [decay]
+
+yields   : per-cell x per-species yields (FSSW::calculate_dN_dxtdy_for_one_particle_species)
+           + the reference's local-rest-frame surface + species order, for the six runnable
+           one-cell CI fixtures and for small synthetic surfaces in every delta-f mode.
+stats    : histograms (tests/obs.py) of particle_samples.bin written by the reference's own
+           sampler (iSS.e) with fixed seeds, >= 10^4 events each.
+momentum : |p| samples of MomentumSamplerShell::Sample_a_momentum reduced to histograms.
+decay    : daughters of particle_decay::perform_decays for a few resonances.
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.dirname(HERE))
+from iss_b200 import synthetic  # noqa: E402
+import obs  # noqa: E402
+
+REF = os.path.join(REPO, "oracle", "_ref")
+FIX = os.path.join(REPO, "tests", "fixtures")
+REF_TABLES = "/root/reference/iSS_tables"
+
+# name -> (music_input suffix, parameter file, surface fixture, overrides)
+ONE_CELL = {
+    "ideal1": ("91", "iSS_parameters_ideal.dat", "testIdealOneFluidCell1.dat", ["bulk_deltaf_kind=21"]),
+    "ideal2": ("9", "iSS_parameters_ideal.dat", "testIdealOneFluidCell2.dat", ["bulk_deltaf_kind=21"]),
+    "ideal3": ("12", "iSS_parameters_ideal.dat", "testIdealOneFluidCell3.dat", ["bulk_deltaf_kind=21"]),
+    "ideal4": ("14", "iSS_parameters_ideal.dat", "testIdealOneFluidCell4.dat", ["bulk_deltaf_kind=21"]),
+    "viscous1": ("91", "iSS_parameters_CEdeltaf.dat", "testViscousOneFluidCell1.dat", []),
+    "viscous2": ("9", "iSS_parameters_CEdeltaf.dat", "testViscousOneFluidCell2.dat", []),
+}
+
+# name -> dict(generator kwargs, parameter file, overrides)
+SYNTH = {
+    "s3d_ce": dict(gen=dict(ncell=240, seed=12345, eos=9), param="iSS_parameters_CEdeltaf.dat", over=[]),
+    "s3d_ce_diff": dict(gen=dict(ncell=240, seed=2024, eos=14, rhob=1, diffusion=1, binary=1),
+                        param="iSS_parameters_CEdeltaf.dat", over=["include_deltaf_diffusion=1"]),
+    "s3d_14mom": dict(gen=dict(ncell=240, seed=12345, eos=14, rhob=1),
+                      param="iSS_parameters.dat",
+                      over=["bulk_deltaf_kind=11", "include_deltaf_bulk=1", "oracle_fix_14mom_c0=1"]),
+    "s2d_smash_ce": dict(gen=dict(ncell=240, seed=12345, eos=91, boost_invariant=True),
+                         param="iSS_parameters_CEdeltaf.dat", over=["hydro_mode=1"]),
+    "s3d_ideal_b": dict(gen=dict(ncell=240, seed=777, eos=12, rhob=1),
+                        param="iSS_parameters_ideal.dat", over=["bulk_deltaf_kind=21"]),
+    "s3d_bulk1": dict(gen=dict(ncell=240, seed=99, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                      over=["bulk_deltaf_kind=1"]),
+    "s3d_boltzmann": dict(gen=dict(ncell=120, seed=5, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                          over=["quantum_statistics=0"]),
+}
+
+
+def workdir():
+    d = tempfile.mkdtemp(prefix="iss_golden_")
+    os.symlink(REF_TABLES, os.path.join(d, "iSS_tables"))
+    return d
+
+
+def run(cmd, cwd, log):
+    with open(log, "w") as f:
+        subprocess.run(cmd, cwd=cwd, stdout=f, stderr=subprocess.STDOUT, check=True)
+
+
+def read_dump(prefix):
+    with open(prefix + ".lrf.bin", "rb") as f:
+        n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+        lrf = np.fromfile(f, dtype=np.float32).reshape(n, 28)
+    sp = np.loadtxt(prefix + ".species.txt", ndmin=2)
+    with open(prefix + ".yields.bin", "rb") as f:
+        ns, nc = np.fromfile(f, dtype=np.int64, count=2)
+        y = np.fromfile(f, dtype=np.float64).reshape(int(ns), int(nc))
+    return lrf, sp, y
+
+
+def golden_yields():
+    for name, (mi, param, surf, over) in ONE_CELL.items():
+        d = workdir()
+        case = os.path.join(d, "case")
+        os.makedirs(case)
+        shutil.copy(os.path.join(FIX, "music_input_" + mi), os.path.join(case, "music_input"))
+        shutil.copy(os.path.join(FIX, surf), os.path.join(case, surf))
+        run([os.path.join(REF, "ref_driver"), "yields", os.path.join(FIX, param), "case", surf,
+             os.path.join(d, "out")] + over, d, os.path.join(d, "log"))
+        lrf, sp, y = read_dump(os.path.join(d, "out"))
+        np.savez_compressed(os.path.join(HERE, "yields_%s.npz" % name), lrf=lrf, species=sp, yields=y,
+                            music_input=mi, param=param, surface=surf, overrides=np.array(over))
+        print(name, lrf.shape, y.shape, "sum=%.17g" % y.sum())
+        shutil.rmtree(d)
+    for name, spec in SYNTH.items():
+        d = workdir()
+        g = dict(spec["gen"])
+        cells = synthetic.make_case(os.path.join(d, "case"), **g)
+        run([os.path.join(REF, "ref_driver"), "yields", os.path.join(FIX, spec["param"]), "case",
+             "surface.dat", os.path.join(d, "out")] + spec["over"], d, os.path.join(d, "log"))
+        lrf, sp, y = read_dump(os.path.join(d, "out"))
+        np.savez_compressed(os.path.join(HERE, "yields_%s.npz" % name), lrf=lrf, species=sp, yields=y,
+                            cells=cells, gen=np.array(sorted(g.items()), dtype=object).astype(str),
+                            param=spec["param"], overrides=np.array(spec["over"]))
+        print(name, lrf.shape, y.shape, "sum=%.17g" % y.sum())
+        shutil.rmtree(d)
+
+
+# statistical goldens: the reference's own sampler, fixed seed
+STATS = {
+    # one moving cell with shear stress, UrQMD list, CE delta-f (Viscous2 fixture scaled to a
+    # smaller volume so that 10^4 events are cheap): cell line written below
+    "cell_shear_ce": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=20000, seed=1,
+                          cell="viscous2_small", over=[]),
+    "cell_bulk_ce_smash": dict(music="91", param="iSS_parameters_CEdeltaf.dat", nev=20000, seed=2,
+                               cell="viscous1_small", over=[]),
+    "cell_ideal_muB": dict(music="14", param="iSS_parameters_ideal.dat", nev=20000, seed=3,
+                           cell="ideal4_small", over=["bulk_deltaf_kind=21"]),
+    "surf3d_ce_diff": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=4,
+                           gen=dict(ncell=2000, seed=2024, eos=14, rhob=1, diffusion=1, binary=1),
+                           over=["include_deltaf_diffusion=1"]),
+    "surf2d_ce_decay": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=5,
+                            gen=dict(ncell=500, seed=12345, eos=9, boost_invariant=True),
+                            over=["hydro_mode=1", "perform_decays=1", "y_LB=-2", "y_RB=2"]),
+}
+
+
+def small_cell(fixture, scale):
+    """one-cell fixture with da0 scaled (volume = tau*da0)."""
+    v = np.loadtxt(os.path.join(FIX, fixture)).ravel()
+    v[4] *= scale
+    return v
+
+
+def golden_stats():
+    for name, spec in STATS.items():
+        d = workdir()
+        case = os.path.join(d, "case")
+        os.makedirs(case)
+        extra = {}
+        if spec["music"] is not None:
+            shutil.copy(os.path.join(FIX, "music_input_" + spec["music"]),
+                        os.path.join(case, "music_input"))
+            fixture = {"viscous2_small": "testViscousOneFluidCell2.dat",
+                       "viscous1_small": "testViscousOneFluidCell1.dat",
+                       "ideal4_small": "testIdealOneFluidCell4.dat"}[spec["cell"]]
+            v = small_cell(fixture, 0.01)
+            np.savetxt(os.path.join(case, "surface.dat"), v[None, :], fmt="%.16e")
+            extra["cell_line"] = v
+        else:
+            extra["cells"] = synthetic.make_case(case, **spec["gen"])
+            extra["gen"] = np.array(sorted(spec["gen"].items()), dtype=object).astype(str)
+        over = ["number_of_repeated_sampling=%d" % spec["nev"], "randomSeed=%d" % spec["seed"],
+                "use_OSCAR_format=0", "use_gzip_format=0", "use_binary_format=1", "perform_checks=0",
+                "output_samples_into_files=0"] + spec["over"]
+        run([os.path.join(REF, "iSS.e"), os.path.join(FIX, spec["param"]), "case", "surface.dat"] + over,
+            d, os.path.join(d, "log"))
+        rec, off = obs.read_reference_bin(os.path.join(d, "particle_samples.bin"))
+        s = obs.summarize(rec, off)
+        np.savez_compressed(os.path.join(HERE, "stats_%s.npz" % name), param=spec["param"],
+                            overrides=np.array(spec["over"]), music=str(spec["music"]), **extra, **s)
+        print(name, "events", len(off) - 1, "hadrons", len(rec))
+        shutil.rmtree(d)
+
+
+MOMENTUM = [  # (mass, T, mu, sign)
+    (0.13957, 0.15, 0.0, -1), (0.13957, 0.12, 0.05, -1), (0.49367, 0.155, 0.02, -1),
+    (0.93827, 0.15, 0.3, 1), (0.93827, 0.15, -0.3, 1), (1.232, 0.14, 0.0, 1),
+    (2.25, 0.16, 0.1, 1), (0.5479, 0.15, 0.0, 0), (5.0, 0.15, 0.0, -1), (8.0, 0.15, 0.0, 1),
+]
+P_EDGES = np.linspace(0.0, 5.0, 101)
+
+
+def golden_momentum():
+    d = workdir()
+    hists = []
+    n = 2000000
+    for i, (m, T, mu, sign) in enumerate(MOMENTUM):
+        out = os.path.join(d, "p%d.bin" % i)
+        run([os.path.join(REF, "ref_driver"), "momentum", repr(m), repr(T), repr(mu), str(sign), str(n),
+             str(100 + i), out], d, os.path.join(d, "log"))
+        p = np.fromfile(out, dtype=np.float64)
+        hists.append(np.histogram(p, P_EDGES)[0])
+    np.savez_compressed(os.path.join(HERE, "momentum_sampler.npz"), cases=np.array(MOMENTUM),
+                        edges=P_EDGES, hist=np.array(hists), n=n)
+    print("momentum", np.array(hists).sum(axis=1))
+    shutil.rmtree(d)
+
+
+DECAY_PIDS = [113, 213, 223, 313, 2214, 3114, 221, 331, 333, 10213, 20223]
+
+
+def golden_decay():
+    d = workdir()
+    res = {}
+    n = 200000
+    for pid in DECAY_PIDS:
+        out = os.path.join(d, "d%d.bin" % pid)
+        run([os.path.join(REF, "ref_driver"), "decay", "iSS_tables", "1", str(pid), str(n), "7", out],
+            d, os.path.join(d, "log"))
+        raw = np.fromfile(out, dtype=np.uint8)
+        pos = 0
+        nd_hist = np.zeros(8, dtype=np.int64)
+        pids = {}
+        esum = np.zeros(4)
+        e_hist = np.zeros(50, dtype=np.int64)
+        while pos < len(raw):
+            nd = int(raw[pos:pos + 4].view("<i4")[0])
+            pos += 4
+            nd_hist[nd] += 1
+            rec = raw[pos:pos + 40*nd].view(np.dtype([("pid", "<i4"), ("f", "<f4", 9)]))
+            pos += 40*nd
+            key = tuple(sorted(int(x) for x in rec["pid"]))
+            pids[key] = pids.get(key, 0) + 1
+            for r in rec:
+                esum += r["f"][1:5]     # E px py pz  (iSS_Hadron: mass,E,px,py,pz,t,x,y,z)
+                e_hist[min(49, int(r["f"][1]/0.05))] += 1
+        res["nd_%d" % pid] = nd_hist
+        keys = sorted(pids)
+        res["chan_%d" % pid] = np.array([list(k) + [0]*(5 - len(k)) for k in keys], dtype=np.int64)
+        res["chan_count_%d" % pid] = np.array([pids[k] for k in keys], dtype=np.int64)
+        res["p4sum_%d" % pid] = esum
+        res["ehist_%d" % pid] = e_hist
+        print("decay", pid, nd_hist[:5], len(keys), "channels")
+    np.savez_compressed(os.path.join(HERE, "decay.npz"), pids=np.array(DECAY_PIDS), n=n, **res)
+    shutil.rmtree(d)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["yields", "stats", "momentum", "decay"]
+    if "yields" in what:
+        golden_yields()
+    if "momentum" in what:
+        golden_momentum()
+    if "decay" in what:
+        golden_decay()
+    if "stats" in what:
+        golden_stats()

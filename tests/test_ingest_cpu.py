@@ -1,0 +1,54 @@
+"""CPU tests of the host ingest: music_input / surface parsing, HRG regulation, particle table,
+local-rest-frame transform and species order, against dumps of the unmodified reference
+(tests/golden/yields_*.npz: `lrf`, `species`).  Bit-exact float32 records are required because
+Sigma_LRF and T feed every yield at 1e-6 (reference iSS.cpp:170-293, readindata.cpp:626-842)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+from iss_b200 import capi
+
+
+@pytest.mark.parametrize("name", cases.ONE_CELL + cases.SYNTH)
+def test_ingest_bit_exact(name, built, tmp_path):
+    g = cases.load(name)
+    case = tmp_path/"case"
+    param, surf, over = cases.materialise(g, str(case))
+    os.symlink(capi.TABLES, tmp_path/"iSS_tables")
+    exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iss_host_dump")
+    args = [exe, param, "case", surf, "out"] + ["%s=%r" % kv for kv in over.items()]
+    r = subprocess.run(args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    with open(tmp_path/"out.lrf.bin", "rb") as f:
+        n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+        lrf = np.fromfile(f, dtype=np.float32).reshape(n, 28)
+    assert lrf.shape == g["lrf"].shape
+    assert np.array_equal(lrf.view(np.uint32), g["lrf"].view(np.uint32))
+    sp = np.loadtxt(tmp_path/"out.species.txt", ndmin=2)
+    assert np.array_equal(sp, g["species"])
+
+
+def test_libraries_export_declared_symbols(built):
+    L = capi.cuda_lib()
+    H = capi.host_lib()
+    import re
+    inc = os.path.join(capi.REPO, "include")
+    declared = set(re.findall(r"\b(iss_cuda_\w+)\s*\(", open(os.path.join(inc, "iss_cuda.h")).read()))
+    assert declared == set(capi.CUDA_SYMBOLS)
+    for sname in declared:
+        assert hasattr(L, sname), sname
+    declared_h = set(re.findall(r"\b(iss_host_\w+)\s*\(", open(os.path.join(inc, "iss_host.h")).read()))
+    assert declared_h == set(capi.HOST_SYMBOLS)
+    for sname in declared_h:
+        assert hasattr(H, sname), sname
+
+
+def test_no_gpu_fails_loudly(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.IssError):
+        capi.Engine()
