@@ -1,0 +1,412 @@
+#!/usr/bin/env python3
+"""Benchmark of the Cooper-Frye particlization hot path (BASELINE.json metric: sampled hadrons/s
+and cell x species yields/s) on N B200s of one node, next to the reference's CPU sampler.
+
+    python bench.py --gpus N --steps K --warmup W            # this engine
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path
+
+Workload (config.workload): BASELINE.json configs[3], "C4": synthetic 3+1D MUSIC-format surface,
+10^6 cells (binary, 34 float32 per cell), EOS 14 with net baryon density and baryon diffusion,
+Chapman-Enskog delta-f (kind 21) for shear, bulk and diffusion, urqmd_v3.3+ list (321 species).
+A "step" is one pass of the hot path over one batch: yields for all cells x species, cell CDFs,
+multiplicities, offsets, momentum sampling fused with boost/emit for EVENTS_PER_STEP events, QA
+histograms (reduced over ranks with NCCL when N > 1).  The real job computes the yields once per
+10^4 events; recomputing them every 1000 events makes the step a conservative 1/10 of C4.
+
+Event sharding: every rank holds the whole surface and samples its own
+events, no data-path collective; per-GPU work is fixed -> "scaling": "weak".
+
+Timing: CUDA events on the stream the kernels run on (the handle is bound to torch's current
+stream), W >= 3 warm-up steps, barrier + synchronize on both sides, max over ranks.  The per-step
+working set (2 x 2.6 GB of yields/CDF + 2.3 GB of hadrons) is far larger than the 126 MB L2.
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+PARAM = os.path.join(REPO, "tests", "fixtures", "iSS_parameters_CEdeltaf.dat")
+OVERRIDES = dict(afterburner_type=1, include_deltaf_diffusion=1, include_deltaf_shear=1,
+                 include_deltaf_bulk=1, bulk_deltaf_kind=21, hydro_mode=2, perform_decays=0,
+                 use_OSCAR_format=0, use_gzip_format=0, use_binary_format=0, perform_checks=0,
+                 MC_sampling=4, local_charge_conservation=0, sample_upto_desired_particle_number=0)
+SURFACE_SEED = 2024          # C4 seed
+# algorithmic work per unit (restated in DESIGN.md)
+BYTES_PER_HADRON = 152.0     # 40 B record out + 112 B cell record in
+FLOP_PER_HADRON = 1.0e3
+BYTES_PER_YIELD = 8.2        # 8 B FP64 yield out + 64 B of cell fields / 321 species
+FLOP_PER_YIELD = 175.0       # CE bulk + diffusion series
+
+
+def load_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def make_case(folder, ncell):
+    from iss_b200 import synthetic
+    synthetic.make_case(folder, ncell=ncell, seed=SURFACE_SEED, eos=14, rhob=1, diffusion=1, binary=1)
+
+
+def workload_name(ncell, events):
+    return ("C4 (BASELINE.json configs[3]): synthetic 3+1D MUSIC-format surface, %d cells, EOS 14 + "
+            "rho_B + baryon diffusion, CE delta-f shear+bulk+diffusion, urqmd_v3.3+ list (321 "
+            "species); step = yields of all cells x species + CDF + multiplicities + %d sampled "
+            "events (+ QA histograms)" % (ncell, events))
+
+
+# ------------------------------------------------------------------------------------ engine arm
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from iss_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    os.environ["ISS_CUDA_DEVICE"] = str(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    E = args.events_per_step
+    work = tempfile.mkdtemp(prefix="iss_bench_r%d_" % rank)
+    make_case(work, args.cells)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved_stdout = os.dup(1)
+    os.dup2(devnull, 1)          # the facade logs like the reference; keep stdout for the JSON line
+    try:
+        over = dict(OVERRIDES, number_of_repeated_sampling=E)
+        s = capi.Sampler(work, PARAM, "surface.dat", **over)
+        s.read_in_FO_surface()
+        s.set_random_seed(args.seed)
+        s.prepare_sampler()
+        e = s.engine()
+        stream = torch.cuda.current_stream()
+        e.set_stream(stream.cuda_stream)
+        ncell, ns = e.ncell, e.nspecies
+        qa_pids = [211, -211, 321, -321, 2212, -2212, 3122, 111]
+
+        def qa_tensor():
+            class _Ext:
+                pass
+            o = _Ext()
+            n = int(capi.cuda_lib().iss_cuda_qa_size())
+            o.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8",
+                                          "data": (e.qa_device_ptr(), False), "version": 2}
+            return torch.as_tensor(o, device="cuda")
+
+        step_counter = [0]
+
+        def step():
+            k = step_counter[0]
+            step_counter[0] += 1
+            e.compute_yields()
+            ev0 = (k*world + rank)*E
+            c = e.sample(args.seed, ev0, ev0 + E)
+            e.L.iss_cuda_histograms(e.h, capi._ptr(np.asarray(qa_pids, dtype=np.int32)),
+                                    len(qa_pids), 0)
+            if world > 1:
+                dist.all_reduce(qa_tensor())        # NCCL: QA histograms only
+            return c.n_hadrons, c.n_tries
+
+        for _ in range(args.warmup):
+            step()
+        e.timing(enable=True, reset=True)
+        clocks = ClockSampler(local)
+        clocks.start()
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        hadrons = tries = 0
+        for _ in range(args.steps):
+            h, t = step()
+            hadrons += h
+            tries += t
+        t1.record(stream)
+        barrier()
+        ms = t0.elapsed_time(t1)
+        fam_ms, fam_n = e.timing(enable=False)
+        clk = clocks.summary()
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        th = torch.tensor([float(hadrons)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            dist.all_reduce(th, op=dist.ReduceOp.SUM)
+        ms_max, hadrons_all = float(tm.item()), float(th.item())
+
+        # ---- end to end through the reference-facing call: class iSS::generate_samples() with the
+        # surface in host memory (std::vector<FO_surf_LRF>): H2D of surface and tables, yields,
+        # sampling of E events, D2H of the hadron lists into the pinned host buffer.
+        s.set_param("number_of_repeated_sampling", E)
+        e2e_steps = max(1, min(args.steps, 3))
+        s.set_random_seed(args.seed + 1000*rank)
+        s.generate_samples()                         # warm-up (allocations, pinned buffer)
+        barrier()
+        w0 = time.perf_counter()
+        e2e_hadrons = 0
+        for _ in range(e2e_steps):
+            s.generate_samples()
+            h_all, off = s.hadrons()
+            e2e_hadrons += len(h_all)
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        barrier()
+        te = torch.tensor([w1 - w0], dtype=torch.float64, device="cuda")
+        the = torch.tensor([float(e2e_hadrons)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            dist.all_reduce(the, op=dist.ReduceOp.SUM)
+        e2e_value = float(the.item())/float(te.item())
+        table_bytes = 200*200*5*8 + 150*100*8 + 7991*12*8
+        h2d = ncell*28*4 + table_bytes
+        d2h = int(e2e_hadrons/e2e_steps)*40 + (E + 1)*8
+        fp64_peak = e.fp64_peak()
+        s.close()
+    finally:
+        os.dup2(saved_stdout, 1)
+        os.close(devnull)
+        shutil.rmtree(work, ignore_errors=True)
+
+    peaks, peak_src = load_peaks()
+    launches = int(sum(fam_n.values()))
+    dom = max(fam_ms, key=fam_ms.get)
+    sample_s = fam_ms["sample"]*1e-3
+    yields_s = fam_ms["yields"]*1e-3
+    n_launch_sample = max(1, int(fam_n["sample"]))
+    roof = {
+        "kernel": "sampler_kernel (persistent momentum sampler + boost/emit)",
+        "bound": "hbm",
+        "achieved": BYTES_PER_HADRON*hadrons/sample_s/1e9 if sample_s > 0 else None,
+        "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": (BYTES_PER_HADRON*hadrons/sample_s/1e9/peaks["hbm_gbs"]) if sample_s > 0 else None,
+        "traffic": None,
+        "peak_source": peak_src,
+        "avg_launch_ms": fam_ms["sample"]/n_launch_sample,
+        "share_of_step": fam_ms["sample"]/ms if ms > 0 else None,
+        "note": "the sampler is FP64/transcendental and divergence bound, not HBM bound "
+                "(SURVEY.md 8(d)); see fp64",
+        "fp64": {"achieved_tflops": FLOP_PER_HADRON*hadrons/sample_s/1e12 if sample_s > 0 else None,
+                 "peak_tflops": fp64_peak, "peak_source": "DFMA microbenchmark run in this process "
+                 "(iss_cuda_fp64_peak)",
+                 "frac": FLOP_PER_HADRON*hadrons/sample_s/1e12/fp64_peak if sample_s > 0 else None,
+                 "tries_per_hadron": tries/max(1, hadrons)},
+    }
+    ycs = float(ncell)*ns*args.steps
+    roof_y = {
+        "kernel": "yields_kernel", "bound": "hbm",
+        "achieved": BYTES_PER_YIELD*ycs/yields_s/1e9 if yields_s > 0 else None,
+        "peak": peaks["hbm_gbs"], "unit": "GB/s",
+        "frac": BYTES_PER_YIELD*ycs/yields_s/1e9/peaks["hbm_gbs"] if yields_s > 0 else None,
+        "avg_launch_ms": fam_ms["yields"]/max(1, args.steps),
+        "fp64": {"achieved_tflops": FLOP_PER_YIELD*ycs/yields_s/1e12 if yields_s > 0 else None,
+                 "peak_tflops": fp64_peak,
+                 "frac": FLOP_PER_YIELD*ycs/yields_s/1e12/fp64_peak if yields_s > 0 else None},
+    }
+    line = {
+        "metric": "sampled_hadrons_per_sec", "value": hadrons_all/(ms_max*1e-3),
+        "unit": "hadrons/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max/args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.cells, E), "cells": ncell, "species": ns,
+                   "events_per_step_per_gpu": E, "sharding": "events (weak), surface replicated",
+                   "l2": "inputs_larger_than_L2", "seed": args.seed},
+        "yields_per_sec": ycs/yields_s if yields_s > 0 else None,
+        "sampler_hadrons_per_sec_kernel": hadrons/sample_s if sample_s > 0 else None,
+        "kernel_ms": {k: v/args.steps for k, v in fam_ms.items()},
+        "dominant_kernel": dom,
+        "roofline": roof, "roofline_yields": roof_y,
+        "e2e": {"value": e2e_value, "unit": "hadrons/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                "call": "iSS::generate_samples() (class iSS facade, host surface -> host hadron lists)"},
+        "gpu_launches": launches,
+        "clocks": clk,
+    }
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(args, quick=True)
+        line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------- reference arm
+def ref_binary():
+    p = os.path.join(REPO, "oracle", "_ref", "iSS.e")
+    return p if os.path.exists(p) else None
+
+
+def cpu_reference(args, quick):
+    """Times the UNMODIFIED reference binary (oracle/_ref/iSS.e, compiled from /root/reference by
+    oracle/Makefile) on a bounded sample of the bench workload: a surface of args.cells/50 cells
+    generated with the same generator and seed, and the same events-per-step, so that the ratio
+    of yield work to sampling work per hadron is that of the GPU step.  The reference is serial:
+    `cores` independent processes run side by side with distinct seeds.  Throughput of one
+    process = hadrons / the reference's own timer line "sample_using_dN_dxtdy_4all_particles
+    finished in X seconds" (FSSW.cpp:1067-1070, CPU clock(): yields + sampling, no file I/O)."""
+    exe = ref_binary()
+    if exe is None:
+        return {"unavailable": "oracle/_ref/iSS.e not built (needs /root/reference at build time)"}
+    cores = os.cpu_count() or 1
+    ncell = max(1000, args.cells//50)
+    events = args.events_per_step
+    root = tempfile.mkdtemp(prefix="iss_ref_")
+    try:
+        make_case(os.path.join(root, "case"), ncell)
+        os.symlink(os.path.join(REPO, "iSS_tables"), os.path.join(root, "iSS_tables"))
+        over = dict(OVERRIDES, number_of_repeated_sampling=events, use_binary_format=0)
+        procs = []
+        t0 = time.perf_counter()
+        for c in range(cores):
+            d = os.path.join(root, "p%d" % c)
+            os.makedirs(d)
+            os.symlink(os.path.join(root, "iSS_tables"), os.path.join(d, "iSS_tables"))
+            os.symlink(os.path.join(root, "case"), os.path.join(d, "case"))
+            cmd = [exe, PARAM, "case", "surface.dat"] + ["%s=%s" % kv for kv in over.items()]
+            cmd.append("randomSeed=%d" % (c + 1))
+            procs.append(subprocess.Popen(cmd, cwd=d, stdout=open(os.path.join(d, "log"), "w"),
+                                          stderr=subprocess.STDOUT))
+        for p in procs:
+            p.wait()
+        wall = time.perf_counter() - t0
+        rate = 0.0
+        hadrons = 0.0
+        secs = []
+        for c in range(cores):
+            txt = open(os.path.join(root, "p%d" % c, "log")).read()
+            sec = None
+            dN = 0.0
+            for ln in txt.splitlines():
+                if "finished in" in ln and "sample_using_dN_dxtdy_4all_particles" in ln:
+                    sec = float(ln.split("finished in")[1].split()[0])
+                if "Sampling using dN_dy=" in ln:
+                    dN += float(ln.split("dN=")[1].split("...")[0])
+            if sec is None or sec <= 0:
+                return {"unavailable": "reference run failed: " + txt[-300:].replace("\n", " | ")}
+            n = dN*events        # expected hadrons (Poisson mean); the reference does not print counts
+            rate += n/sec
+            hadrons += n
+            secs.append(sec)
+        return {"value": rate, "unit": "hadrons/s", "cores": cores, "kind": "reference",
+                "sample": "%d-cell surface (1/%d of the workload, same generator and seed), %d events, "
+                          "%d independent single-thread processes of oracle/_ref/iSS.e; hadrons = "
+                          "events x sum of species dN; time = reference timer line (yields + sampling)"
+                          % (ncell, args.cells//ncell, events, cores),
+                "per_core": rate/cores, "cpu_seconds_per_process": float(np.mean(secs)),
+                "wall_seconds": wall}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_reference(args, quick=True)
+        if "unavailable" in cb:
+            print(json.dumps({"impl": "reference", "unavailable": cb["unavailable"]}), flush=True)
+            return
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {"impl": "reference", "metric": "sampled_hadrons_per_sec", "value": v, "unit": "hadrons/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.cells, args.events_per_step)},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "hadrons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--cells", type=int, default=1000000)
+    ap.add_argument("--events-per-step", type=int, default=1000)
+    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        # a reference "step" is a full multi-process run of the binary: keep the count small
+        args.steps = max(1, min(args.steps, 2))
+        args.warmup = min(args.warmup, 0)
+        run_reference(args)
+    else:
+        args.warmup = max(3, args.warmup)
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

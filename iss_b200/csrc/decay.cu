@@ -289,21 +289,21 @@ int run_decay(iss_handle *h, uint64_t seed) {
     const unsigned grid = static_cast<unsigned>((n_in + 127)/128);
     int64_t total = 0;
     {
-        ScopedTimer t(h, ISS_T_DECAY, 2);
+        ScopedTimer t(h, ISS_T_DECAY);
         ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_decay_cnt + n_in, 0, sizeof(int64_t), h->stream));
-        decay_kernel<false><<<grid, 128, 0, h->stream>>>(A);
+        decay_kernel<false><<<grid, 128, 0, h->stream>>>(A); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
         rc = device_exclusive_scan_i64(h, h->d_decay_cnt, h->d_decay_cnt, n_in, &total);
         if (rc) return rc;
         rc = ensure_capacity(h, &h->d_hadrons2, &h->hadron2_cap, total);
         if (rc) return rc;
         A.out = h->d_hadrons2;
-        decay_kernel<true><<<grid, 128, 0, h->stream>>>(A);
+        decay_kernel<true><<<grid, 128, 0, h->stream>>>(A); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
         // new per-event offsets (into a scratch area behind the counts, then copied over)
         int64_t *tmp = h->d_decay_cnt + n_in + 1;
         gather_event_offsets_kernel<<<static_cast<unsigned>((nev + 1 + 255)/256), 256, 0,
-                                      h->stream>>>(h->d_decay_cnt, h->d_event_off, nev, tmp);
+                                      h->stream>>>(h->d_decay_cnt, h->d_event_off, nev, tmp); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
         ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_event_off, tmp, sizeof(int64_t)*(nev + 1),
                                         cudaMemcpyDeviceToDevice, h->stream));

@@ -87,8 +87,6 @@ int iss_cuda_create(int device, iss_handle **out) {
         return ISS_ERR_CUDA;
     }
     h->own_stream = true;
-    cudaEventCreate(&h->ev0);
-    cudaEventCreate(&h->ev1);
     *out = h;
     return ISS_OK;
 }
@@ -108,8 +106,8 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_hadrons); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
     cudaFree(h->d_qa); cudaFree(h->d_trace);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return ISS_OK;
@@ -153,7 +151,7 @@ int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], i
     }
     ISS_CUDA_TRY(h, cudaMalloc(&h->d_cells, sizeof(float)*CELL_STRIDE*ncell));
     build_cells_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(
-        h->d_surf, ncell, h->ncell_pad, h->d_cells);
+        h->d_surf, ncell, h->ncell_pad, h->d_cells); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return ISS_OK;
@@ -495,6 +493,17 @@ int iss_cuda_qa_fetch(iss_handle *h, double *dst_host) {
 int iss_cuda_timing(iss_handle *h, int enable, double *ms_host, int64_t *launches_host,
                     int reset) {
     if (!h) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (!h->spans.empty()) {
+        ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (auto &sp : h->spans) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) h->t_ms[sp.kind] += ms;
+            h->ev_pool.push_back(sp.a);
+            h->ev_pool.push_back(sp.b);
+        }
+        h->spans.clear();
+    }
     if (ms_host) memcpy(ms_host, h->t_ms, sizeof(h->t_ms));
     if (launches_host) memcpy(launches_host, h->t_launch, sizeof(h->t_launch));
     if (reset) {
@@ -537,14 +546,14 @@ int iss_cuda_fp64_peak(iss_handle *h, double *tflops) {
     const int blocks = nsm*8, threads = 256, iters = 1 << 16;
     double *d_out = nullptr;
     ISS_CUDA_TRY(h, cudaMalloc(&d_out, sizeof(double)*blocks*threads));
-    fp64_fma_kernel<<<blocks, threads, 0, h->stream>>>(d_out, 1024);   // warm-up
+    fp64_fma_kernel<<<blocks, threads, 0, h->stream>>>(d_out, 1024); ISS_LAUNCHED(h);   // warm-up
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     float best = 1e30f;
     for (int rep = 0; rep < 5; rep++) {
         cudaEventRecord(e0, h->stream);
-        fp64_fma_kernel<<<blocks, threads, 0, h->stream>>>(d_out, iters);
+        fp64_fma_kernel<<<blocks, threads, 0, h->stream>>>(d_out, iters); ISS_LAUNCHED(h);
         cudaEventRecord(e1, h->stream);
         cudaEventSynchronize(e1);
         float ms = 0.f;

@@ -130,12 +130,20 @@ struct iss_handle {
     // QA
     double *d_qa = nullptr;
 
-    // timing
+    // timing: event pairs are recorded on the stream without synchronising and resolved in
+    // iss_cuda_timing(); t_launch counts every kernel launch of the library
     bool timing = false;
     double t_ms[ISS_T_NKIND] = {0};
     int64_t t_launch[ISS_T_NKIND] = {0};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> ev_pool;
+    int cur_kind = ISS_T_YIELDS;
 };
+
+// every <<< >>> of the library is followed by ISS_LAUNCHED(h): counts the launch in the family
+// of the enclosing ScopedTimer
+#define ISS_LAUNCHED(h) ((h)->t_launch[(h)->cur_kind]++)
 
 #define ISS_CUDA_TRY(h, expr)                                                        \
     do {                                                                             \
@@ -156,20 +164,31 @@ namespace iss {
 
 struct ScopedTimer {
     iss_handle *h;
-    int kind;
-    int launches;
-    ScopedTimer(iss_handle *h_, int kind_, int launches_ = 1)
-        : h(h_), kind(kind_), launches(launches_) {
-        if (h->timing) cudaEventRecord(h->ev0, h->stream);
+    int kind, prev_kind;
+    cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(iss_handle *h) {
+        cudaEvent_t e = nullptr;
+        if (!h->ev_pool.empty()) {
+            e = h->ev_pool.back();
+            h->ev_pool.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
+    }
+    ScopedTimer(iss_handle *h_, int kind_) : h(h_), kind(kind_), prev_kind(h_->cur_kind) {
+        h->cur_kind = kind;
+        if (h->timing) {
+            a = get(h);
+            b = get(h);
+            cudaEventRecord(a, h->stream);
+        }
     }
     ~ScopedTimer() {
-        h->t_launch[kind] += launches;
-        if (h->timing) {
-            cudaEventRecord(h->ev1, h->stream);
-            cudaEventSynchronize(h->ev1);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
-            h->t_ms[kind] += ms;
+        h->cur_kind = prev_kind;
+        if (a) {
+            cudaEventRecord(b, h->stream);
+            h->spans.push_back({kind, a, b});
         }
     }
 };

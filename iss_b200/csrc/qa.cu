@@ -178,8 +178,8 @@ int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate) {
     int64_t grid = std::min<int64_t>(A.nev, static_cast<int64_t>(nsm)*8);
     if (grid < 1) grid = 1;
     {
-        ScopedTimer t(h, ISS_T_QA, 1);
-        qa_kernel<<<static_cast<unsigned>(grid), QA_THREADS, 0, h->stream>>>(A);
+        ScopedTimer t(h, ISS_T_QA);
+        qa_kernel<<<static_cast<unsigned>(grid), QA_THREADS, 0, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));

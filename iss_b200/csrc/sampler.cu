@@ -107,7 +107,7 @@ static int ensure_momentum_tables(iss_handle *h) {
         const int npoints = (E_max - E_min)/dE + 1;
         ISS_CUDA_TRY(h, cudaMalloc(&h->d_momtab[r], sizeof(double)*4*npoints));
         build_momentum_table_kernel<<<(npoints + 127)/128, 128, 0, h->stream>>>(
-            h->d_momtab[r], npoints, E_min, dE, m0, trunc[r % 3], fermion ? 1 : 0);
+            h->d_momtab[r], npoints, E_min, dE, m0, trunc[r % 3], fermion ? 1 : 0); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
         MomentumTable &t = h->momtab[r];
         t.data = h->d_momtab[r];
@@ -680,14 +680,14 @@ int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev) {
     ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_pmode, h->h_pmode.data(), sizeof(double)*ns,
                                     cudaMemcpyHostToDevice, h->stream));
 
-    ScopedTimer t(h, ISS_T_MULT, 1);
+    ScopedTimer t(h, ISS_T_MULT);
     // out_count -> d_off_out (scanned in place), work_count -> d_off_work (in place)
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_off_out + n, 0, sizeof(int64_t), h->stream));
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_off_work + n, 0, sizeof(int64_t), h->stream));
     multiplicity_kernel<<<static_cast<unsigned>((n + 255)/256), 256, 0, h->stream>>>(
         h->d_lambda, h->d_pmode, h->d_species, ns, nev, h->ev_begin, seed,
         o.dN_dy_sampling_model, o.local_charge_conservation, h->d_mult, h->d_off_out,
-        h->d_off_work);
+        h->d_off_work); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
     return ISS_OK;
 }
@@ -699,13 +699,13 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     if (rc) return rc;
     int64_t total_out = 0, total_work = 0;
     {
-        ScopedTimer t(h, ISS_T_MULT, 0);
+        ScopedTimer t(h, ISS_T_MULT);
         rc = device_exclusive_scan_i64(h, h->d_off_out, h->d_off_out, n, &total_out);
         if (rc) return rc;
         rc = device_exclusive_scan_i64(h, h->d_off_work, h->d_off_work, n, &total_work);
         if (rc) return rc;
         event_offset_kernel<<<static_cast<unsigned>((nev + 1 + 255)/256), 256, 0, h->stream>>>(
-            h->d_off_out, ns, nev, h->d_event_off);
+            h->d_off_out, ns, nev, h->d_event_off); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
     }
     rc = ensure_capacity(h, &h->d_hadrons, &h->hadron_cap, total_out);
@@ -769,8 +769,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     const int64_t max_useful = (total_work + 31)/32/(SAMPLER_THREADS/32) + 1;
     if (grid > max_useful) grid = max_useful;
     {
-        ScopedTimer t(h, ISS_T_SAMPLE, 1);
-        sampler_kernel<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(A);
+        ScopedTimer t(h, ISS_T_SAMPLE);
+        sampler_kernel<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     return ISS_OK;

@@ -71,12 +71,12 @@ static int scan_rec(iss_handle *h, const int64_t *d_in, int64_t *d_out, int64_t 
     if (nblk > tmp_elems) ISS_FAIL(h, ISS_ERR_NOMEM, "scan scratch too small");
     int64_t *sums = d_tmp;
     scan_local_kernel<<<static_cast<unsigned>(nblk), SCAN_THREADS, 0, h->stream>>>(d_in, d_out,
-                                                                                   sums, n);
+                                                                                   sums, n); ISS_LAUNCHED(h);
     if (nblk > 1) {
         int rc = scan_rec(h, sums, sums, nblk, d_tmp + nblk, tmp_elems - nblk);
         if (rc) return rc;
         scan_add_kernel<<<static_cast<unsigned>(nblk), SCAN_THREADS, 0, h->stream>>>(d_out, sums,
-                                                                                     n);
+                                                                                     n); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     return ISS_OK;

@@ -302,7 +302,7 @@ static int ensure_sf_tables(iss_handle *h) {
         ISS_CUDA_TRY(h, cudaMalloc(&h->d_expint, sizeof(double)*9*g.n));
     h->sf = g;
     build_sf_tables_kernel<<<(g.n + 127)/128, 128, 0, h->stream>>>(
-        h->d_bessel, h->d_expint, g, 1, need_diff ? 1 : 0);
+        h->d_bessel, h->d_expint, g, 1, need_diff ? 1 : 0); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
     return ISS_OK;
 }
@@ -375,16 +375,16 @@ int run_yields(iss_handle *h) {
     {
         ScopedTimer t(h, ISS_T_YIELDS);
         dim3 grid(static_cast<unsigned>(nblk_x), chunks);
-        yields_kernel<<<grid, YIELD_THREADS, 0, h->stream>>>(a);
+        yields_kernel<<<grid, YIELD_THREADS, 0, h->stream>>>(a); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     {
-        ScopedTimer t(h, ISS_T_SCAN, 2);
+        ScopedTimer t(h, ISS_T_SCAN);
         dim3 grid(static_cast<unsigned>(h->ntile), static_cast<unsigned>(ns));
         tile_scan_kernel<<<grid, 256, 0, h->stream>>>(h->d_yields, h->d_cdf, h->d_tilesum,
-                                                      h->ncell, h->ncell_pad, h->ntile);
+                                                      h->ncell, h->ncell_pad, h->ntile); ISS_LAUNCHED(h);
         tile_base_kernel<<<static_cast<unsigned>(ns), 32, 0, h->stream>>>(
-            h->d_tilesum, h->d_tilebase, h->d_total, h->ntile);
+            h->d_tilesum, h->d_tilebase, h->d_total, h->ntile); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     h->h_total.resize(ns);
