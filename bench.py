@@ -195,6 +195,9 @@ def run_engine(args):
             dist.all_reduce(th, op=dist.ReduceOp.SUM)
         ms_max, hadrons_all = float(tm.item()), float(th.item())
 
+        fp64_peak = e.fp64_peak()
+        # (generate_samples() below builds a new device sampler: `e` must not be used after it)
+
         # ---- end to end through the reference-facing call: class iSS::generate_samples() with the
         # surface in host memory (std::vector<FO_surf_LRF>): H2D of surface and tables, yields,
         # sampling of E events, D2H of the hadron lists into the pinned host buffer.
@@ -221,7 +224,6 @@ def run_engine(args):
         table_bytes = 200*200*5*8 + 150*100*8 + 7991*12*8
         h2d = ncell*28*4 + table_bytes
         d2h = int(e2e_hadrons/e2e_steps)*40 + (E + 1)*8
-        fp64_peak = e.fp64_peak()
         s.close()
     finally:
         os.dup2(saved_stdout, 1)
