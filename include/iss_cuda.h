@@ -173,6 +173,10 @@ ISS_API int iss_cuda_synchronize(iss_handle *h);
 /* ---- inputs (replace the std::vector<FO_surf_LRF>/particle tables FSSW's ctor takes,
  *      FSSW.cpp:43-201) -------------------------------------------------- */
 ISS_API int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], int64_t ncell);
+/* the same records as one array-of-structures block [ncell][ISS_NFIELD] (the memory order of
+ * std::vector<FO_surf_LRF> minus its PCE vector): one host->device copy, transposed on the device.
+ * `cells` may be pinned memory; it can be reused when the call returns.                  */
+ISS_API int iss_cuda_upload_surface_aos(iss_handle *h, const float *cells, int64_t ncell);
 ISS_API int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t nspecies);
 ISS_API int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data,
                           int64_t n0, int64_t n1, const double *grid4);
@@ -213,6 +217,12 @@ ISS_API int iss_cuda_fetch_event(iss_handle *h, int64_t iev_in_batch, iss_hadron
                          int64_t *n);
 /* whole batch, event-major; dst may be pinned memory. */
 ISS_API int iss_cuda_fetch_all(iss_handle *h, iss_hadron *dst, int64_t cap, int64_t *n);
+/* same, asynchronous on the handle's copy stream: returns once the copy is queued behind the
+ * batch; the next iss_cuda_sample may run while it is in flight (the library alternates between
+ * two device output buffers).  dst must stay valid (and should be pinned) until
+ * iss_cuda_fetch_wait returns.                                                            */
+ISS_API int iss_cuda_fetch_all_async(iss_handle *h, iss_hadron *dst, int64_t cap, int64_t *n);
+ISS_API int iss_cuda_fetch_wait(iss_handle *h);
 /* device pointer of the batch (for callers that keep the list on the GPU). */
 ISS_API int iss_cuda_device_hadrons(iss_handle *h, const void **dptr, int64_t *n);
 

@@ -79,7 +79,8 @@ CUDA_SYMBOLS = [
     "iss_cuda_fetch_event", "iss_cuda_fetch_all", "iss_cuda_device_hadrons", "iss_cuda_qa_size",
     "iss_cuda_histograms", "iss_cuda_qa_device_ptr", "iss_cuda_qa_fetch", "iss_cuda_timing",
     "iss_cuda_mem_info", "iss_cuda_host_alloc", "iss_cuda_host_free", "iss_cuda_fp64_peak",
-    "iss_cuda_set_trace", "iss_cuda_get_trace",
+    "iss_cuda_set_trace", "iss_cuda_get_trace", "iss_cuda_upload_surface_aos",
+    "iss_cuda_fetch_all_async", "iss_cuda_fetch_wait",
 ]
 HOST_SYMBOLS = [
     "iss_host_create", "iss_host_destroy", "iss_host_set_param", "iss_host_get_param",
@@ -140,6 +141,9 @@ def cuda_lib():
         "iss_cuda_host_alloc": (C.c_int, [vp, C.POINTER(vp), i64]),
         "iss_cuda_host_free": (C.c_int, [vp, vp]),
         "iss_cuda_fp64_peak": (C.c_int, [vp, dp]),
+        "iss_cuda_upload_surface_aos": (C.c_int, [vp, vp, i64]),
+        "iss_cuda_fetch_all_async": (C.c_int, [vp, vp, i64, i64p]),
+        "iss_cuda_fetch_wait": (C.c_int, [vp]),
         "iss_cuda_set_trace": (C.c_int, [vp, C.c_int]),
         "iss_cuda_get_trace": (C.c_int, [vp, vp, vp]),
     }

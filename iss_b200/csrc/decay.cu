@@ -295,6 +295,10 @@ int run_decay(iss_handle *h, uint64_t seed) {
         ISS_CUDA_TRY(h, cudaGetLastError());
         rc = device_exclusive_scan_i64(h, h->d_decay_cnt, h->d_decay_cnt, n_in, &total);
         if (rc) return rc;
+        if (h->copy_pending2) {
+            ISS_CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->copy_done2, 0));
+            h->copy_pending2 = false;
+        }
         rc = ensure_capacity(h, &h->d_hadrons2, &h->hadron2_cap, total);
         if (rc) return rc;
         A.out = h->d_hadrons2;

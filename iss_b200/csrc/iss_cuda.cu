@@ -46,16 +46,56 @@ __global__ void fp64_fma_kernel(double *out, int iters) {
 }
 
 void free_surface(iss_handle *h) {
-    cudaFree(h->d_surf); h->d_surf = nullptr;
-    cudaFree(h->d_cells); h->d_cells = nullptr;
-    cudaFree(h->d_cellcoef); h->d_cellcoef = nullptr;
-    cudaFree(h->d_yields); h->d_yields = nullptr;
-    cudaFree(h->d_cdf); h->d_cdf = nullptr;
-    cudaFree(h->d_tilesum); h->d_tilesum = nullptr;
-    cudaFree(h->d_tilebase); h->d_tilebase = nullptr;
-    cudaFree(h->d_total); h->d_total = nullptr;
+    cudaFree(h->d_surf); h->d_surf = nullptr; h->surf_bytes = 0;
+    cudaFree(h->d_cells); h->d_cells = nullptr; h->cells_bytes = 0;
+    cudaFree(h->d_cellcoef); h->d_cellcoef = nullptr; h->coef_bytes = 0;
+    cudaFree(h->d_stage); h->d_stage = nullptr; h->stage_bytes = 0;
+    cudaFree(h->d_yields); h->d_yields = nullptr; h->yields_bytes = 0;
+    cudaFree(h->d_cdf); h->d_cdf = nullptr; h->cdf_bytes = 0;
+    cudaFree(h->d_tilesum); h->d_tilesum = nullptr; h->tilesum_bytes = 0;
+    cudaFree(h->d_tilebase); h->d_tilebase = nullptr; h->tilebase_bytes = 0;
+    cudaFree(h->d_total); h->d_total = nullptr; h->total_bytes = 0;
     h->have_yields = false;
     h->have_batch = false;
+}
+
+// [ncell][28] staging -> SoA [28][ncell_pad] and the sampler's AoS [ncell][32]; one thread per
+// cell reads its 112-byte record with 16-byte loads
+__global__ void unpack_cells_kernel(const float *__restrict__ stage, int64_t ncell,
+                                    int64_t ncell_pad, float *__restrict__ soa,
+                                    float *__restrict__ cells) {
+    const int64_t c = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    float rec[CELL_STRIDE];
+    const float4 *src = reinterpret_cast<const float4 *>(stage + c*ISS_NFIELD);
+#pragma unroll
+    for (int k = 0; k < ISS_NFIELD/4; k++) {
+        const float4 v = __ldg(src + k);
+        rec[4*k] = v.x; rec[4*k + 1] = v.y; rec[4*k + 2] = v.z; rec[4*k + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < ISS_NFIELD; k++) soa[static_cast<int64_t>(k)*ncell_pad + c] = rec[k];
+    const double tau = rec[ISS_F_TAU], eta = rec[ISS_F_ETA];
+    rec[CELL_T] = static_cast<float>(tau*cosh(eta));
+    rec[CELL_Z] = static_cast<float>(tau*sinh(eta));
+    rec[30] = 0.f;
+    rec[31] = 0.f;
+    float4 *dst = reinterpret_cast<float4 *>(cells + c*CELL_STRIDE);
+#pragma unroll
+    for (int k = 0; k < CELL_STRIDE/4; k++)
+        dst[k] = make_float4(rec[4*k], rec[4*k + 1], rec[4*k + 2], rec[4*k + 3]);
+}
+
+int prepare_surface_buffers(iss_handle *h, int64_t ncell) {
+    if (ncell >= (int64_t(1) << 31)) ISS_FAIL(h, ISS_ERR_ARG, "ncell must be < 2^31");
+    h->ncell = ncell;
+    h->ntile = (ncell + TILE - 1)/TILE;
+    h->ncell_pad = h->ntile*TILE;
+    h->have_yields = false;
+    h->have_batch = false;
+    ISS_ENSURE(h, h->d_surf, h->surf_bytes, sizeof(float)*ISS_NFIELD*h->ncell_pad);
+    ISS_ENSURE(h, h->d_cells, h->cells_bytes, sizeof(float)*CELL_STRIDE*ncell);
+    return ISS_OK;
 }
 
 int upload_doubles(iss_handle *h, double **dptr, const double *src, size_t n) {
@@ -87,6 +127,11 @@ int iss_cuda_create(int device, iss_handle **out) {
         return ISS_ERR_CUDA;
     }
     h->own_stream = true;
+    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&h->batch_ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->copy_done[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->copy_done[1], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->copy_done2, cudaEventDisableTiming);
     *out = h;
     return ISS_OK;
 }
@@ -95,6 +140,10 @@ int iss_cuda_destroy(iss_handle *h) {
     if (!h) return ISS_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->batch_ready) cudaEventDestroy(h->batch_ready);
+    for (int b = 0; b < 2; b++) if (h->copy_done[b]) cudaEventDestroy(h->copy_done[b]);
+    if (h->copy_done2) cudaEventDestroy(h->copy_done2);
     free_surface(h);
     cudaFree(h->d_species);
     cudaFree(h->d_bessel); cudaFree(h->d_expint); cudaFree(h->d_ce); cudaFree(h->d_mom22);
@@ -103,7 +152,7 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_dsp); cudaFree(h->d_dch); cudaFree(h->d_sorted_pid); cudaFree(h->d_sorted_idx);
     cudaFree(h->d_lambda); cudaFree(h->d_pmode);
     cudaFree(h->d_mult); cudaFree(h->d_off_out); cudaFree(h->d_off_work);
-    cudaFree(h->d_hadrons); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
+    cudaFree(h->d_hadbuf[0]); cudaFree(h->d_hadbuf[1]); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
     cudaFree(h->d_qa); cudaFree(h->d_trace);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -135,13 +184,9 @@ int iss_cuda_synchronize(iss_handle *h) {
 
 int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], int64_t ncell) {
     if (!h || !soa || ncell <= 0) return ISS_ERR_ARG;
-    if (ncell >= (int64_t(1) << 31)) ISS_FAIL(h, ISS_ERR_ARG, "ncell must be < 2^31");
     cudaSetDevice(h->device);
-    free_surface(h);
-    h->ncell = ncell;
-    h->ntile = (ncell + TILE - 1)/TILE;
-    h->ncell_pad = h->ntile*TILE;
-    ISS_CUDA_TRY(h, cudaMalloc(&h->d_surf, sizeof(float)*ISS_NFIELD*h->ncell_pad));
+    int rc = prepare_surface_buffers(h, ncell);
+    if (rc) return rc;
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_surf, 0, sizeof(float)*ISS_NFIELD*h->ncell_pad,
                                     h->stream));
     for (int k = 0; k < ISS_NFIELD; k++) {
@@ -149,10 +194,29 @@ int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], i
         ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_surf + static_cast<int64_t>(k)*h->ncell_pad, soa[k],
                                         sizeof(float)*ncell, cudaMemcpyHostToDevice, h->stream));
     }
-    ISS_CUDA_TRY(h, cudaMalloc(&h->d_cells, sizeof(float)*CELL_STRIDE*ncell));
     build_cells_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(
         h->d_surf, ncell, h->ncell_pad, h->d_cells); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_upload_surface_aos(iss_handle *h, const float *cells, int64_t ncell) {
+    if (!h || !cells || ncell <= 0) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    int rc = prepare_surface_buffers(h, ncell);
+    if (rc) return rc;
+    ISS_ENSURE(h, h->d_stage, h->stage_bytes, sizeof(float)*ISS_NFIELD*ncell);
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_stage, cells, sizeof(float)*ISS_NFIELD*ncell,
+                                    cudaMemcpyHostToDevice, h->stream));
+    if (h->ncell_pad > ncell)   // padding cells read as zeros
+        for (int k = 0; k < ISS_NFIELD; k++)
+            ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_surf + static_cast<int64_t>(k)*h->ncell_pad + ncell,
+                                            0, sizeof(float)*(h->ncell_pad - ncell), h->stream));
+    unpack_cells_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(
+        h->d_stage, ncell, h->ncell_pad, h->d_surf, h->d_cells); ISS_LAUNCHED(h);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    // the caller's buffer may be reused as soon as this returns
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return ISS_OK;
 }
@@ -182,15 +246,6 @@ int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t n
     ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_species, ds.data(), sizeof(DeviceSpecies)*nspecies,
                                     cudaMemcpyHostToDevice, h->stream));
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    if (h->nspecies != nspecies && h->d_yields) {
-        // yield buffers are sized by species count
-        cudaFree(h->d_yields); h->d_yields = nullptr;
-        cudaFree(h->d_cdf); h->d_cdf = nullptr;
-        cudaFree(h->d_tilesum); h->d_tilesum = nullptr;
-        cudaFree(h->d_tilebase); h->d_tilebase = nullptr;
-        cudaFree(h->d_total); h->d_total = nullptr;
-        cudaFree(h->d_cellcoef); h->d_cellcoef = nullptr;
-    }
     h->nspecies = nspecies;
     h->have_yields = false;
     return ISS_OK;
@@ -454,6 +509,34 @@ int iss_cuda_fetch_all(iss_handle *h, iss_hadron *dst, int64_t cap, int64_t *n) 
     ISS_CUDA_TRY(h, cudaMemcpyAsync(dst, batch_ptr(h), sizeof(iss_hadron)*(*n),
                                     cudaMemcpyDeviceToHost, h->stream));
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_fetch_all_async(iss_handle *h, iss_hadron *dst, int64_t cap, int64_t *n) {
+    if (!h || !n || !dst) return ISS_ERR_ARG;
+    if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
+    *n = h->n_hadrons;
+    if (*n > cap) ISS_FAIL(h, ISS_ERR_ARG, "destination too small");
+    ISS_CUDA_TRY(h, cudaEventRecord(h->batch_ready, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->batch_ready, 0));
+    if (*n > 0)
+        ISS_CUDA_TRY(h, cudaMemcpyAsync(dst, batch_ptr(h), sizeof(iss_hadron)*(*n),
+                                        cudaMemcpyDeviceToHost, h->copy_stream));
+    if (h->decayed) {
+        ISS_CUDA_TRY(h, cudaEventRecord(h->copy_done2, h->copy_stream));
+        h->copy_pending2 = true;
+    }
+    // the primaries' buffer stays untouched until its copy (or the copy of the decayed batch made
+    // from it) is done; the next iss_cuda_sample writes into the other buffer
+    ISS_CUDA_TRY(h, cudaEventRecord(h->copy_done[h->cur_buf], h->copy_stream));
+    h->copy_pending[h->cur_buf] = true;
+    h->cur_buf ^= 1;
+    return ISS_OK;
+}
+
+int iss_cuda_fetch_wait(iss_handle *h) {
+    if (!h) return ISS_ERR_ARG;
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
     return ISS_OK;
 }
 

@@ -66,6 +66,8 @@ struct iss_handle {
     int64_t ntile = 0;
     float *d_cells = nullptr;           // [ncell][32] AoS copy for the sampler's random access
     double *d_cellcoef = nullptr;       // [ncell][8] delta-f coefficients c0..c5, kappa, spare
+    float *d_stage = nullptr;           // [ncell][28] staging of an AoS upload
+    size_t surf_bytes = 0, cells_bytes = 0, coef_bytes = 0, stage_bytes = 0;   // capacities
 
     // species
     int nspecies = 0;
@@ -98,6 +100,7 @@ struct iss_handle {
     double *d_tilesum = nullptr;        // [ns][ntile]
     double *d_tilebase = nullptr;       // [ns][ntile+1]    exclusive prefix over tiles
     double *d_total = nullptr;          // [ns]
+    size_t yields_bytes = 0, cdf_bytes = 0, tilesum_bytes = 0, tilebase_bytes = 0, total_bytes = 0;
     bool have_yields = false;
     std::vector<double> h_total;        // dN per species (3+1D sum)
     std::vector<double> h_lambda, h_pmode;
@@ -109,8 +112,19 @@ struct iss_handle {
     int64_t *d_off_out = nullptr;       // [nev*ns + 1] event-major exclusive prefix
     int64_t *d_off_work = nullptr;      // [ns*nev + 1] species-major exclusive prefix
     int64_t mult_cap = 0;
-    iss_hadron *d_hadrons = nullptr;
+    iss_hadron *d_hadrons = nullptr;    // = d_hadbuf[cur_buf]
     int64_t hadron_cap = 0;
+    // two output buffers so that the device->host copy of one batch (copy_stream) overlaps the
+    // sampling of the next (iss_cuda_fetch_all_async)
+    iss_hadron *d_hadbuf[2] = {nullptr, nullptr};
+    int64_t hadbuf_cap[2] = {0, 0};
+    int cur_buf = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t batch_ready = nullptr;          // recorded on stream when a batch is complete
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    cudaEvent_t copy_done2 = nullptr;           // copies out of d_hadrons2 (decayed batches)
+    bool copy_pending2 = false;
     int64_t n_hadrons = 0;
     int64_t *d_event_off = nullptr;     // [nev+1]
     int64_t event_off_cap = 0;
@@ -202,6 +216,26 @@ int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev);
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t total);
 int run_decay(iss_handle *h, uint64_t seed);
 int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate);
+
+// grows *ptr to at least `need` bytes (contents are not preserved)
+inline int ensure_bytes(iss_handle *h, void **ptr, size_t *cap, size_t need) {
+    if (*ptr && need <= *cap) return ISS_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    cudaError_t e = cudaMalloc(ptr, need);
+    if (e != cudaSuccess) {
+        h->err = std::string("cudaMalloc failed: ") + cudaGetErrorString(e);
+        return ISS_ERR_NOMEM;
+    }
+    *cap = need;
+    return ISS_OK;
+}
+#define ISS_ENSURE(h, ptr, cap, need)                                                    \
+    do {                                                                                 \
+        int rc__ = iss::ensure_bytes((h), reinterpret_cast<void **>(&(ptr)), &(cap), (need)); \
+        if (rc__) return rc__;                                                           \
+    } while (0)
 
 template <typename T>
 int ensure_capacity(iss_handle *h, T **ptr, int64_t *cap, int64_t need) {

@@ -40,118 +40,186 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     return t;   // valid on thread 0
 }
 
+// shared-memory image of the per-species histograms of one CTA (flushed once at the end)
+struct QaShared {
+    int pt_evt[ISS_QA_NSPEC][ISS_QA_NPT];       // current event only (for the per-event squares)
+    int n_evt[ISS_QA_NSPEC];
+    unsigned long long pt_cnt[ISS_QA_NSPEC][ISS_QA_NPT];
+    unsigned long long pt_sq[ISS_QA_NSPEC][ISS_QA_NPT];
+    unsigned long long n_tot[ISS_QA_NSPEC], n_sq[ISS_QA_NSPEC];
+    unsigned int y_cnt[ISS_QA_NSPEC][ISS_QA_NY];
+    unsigned int phi_cnt[ISS_QA_NSPEC][ISS_QA_NPHI];
+    unsigned int v2_den[ISS_QA_NSPEC][ISS_QA_NV2];
+    double pt_sum[ISS_QA_NSPEC][ISS_QA_NPT];
+    double v2_num[ISS_QA_NSPEC][ISS_QA_NV2];
+    double red[QA_THREADS/32];
+};
+
 __global__ void __launch_bounds__(QA_THREADS)
 qa_kernel(const QaArgs A) {
-    __shared__ int pt_cnt[ISS_QA_NSPEC][ISS_QA_NPT];
-    __shared__ int n_cnt[ISS_QA_NSPEC];
-    __shared__ double red[QA_THREADS/32];
+    extern __shared__ __align__(16) unsigned char qa_smem[];
+    QaShared &S = *reinterpret_cast<QaShared *>(qa_smem);
     double *qa = A.qa;
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(QaShared)/4); i += blockDim.x)
+        reinterpret_cast<unsigned int *>(qa_smem)[i] = 0u;
+    __syncthreads();
+
+    // plain sums over all hadrons this thread sees (reduced once, at the end)
+    double T[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) T[i] = 0.;
+    double net[3] = {0., 0., 0.};
+    double P1[4] = {0., 0., 0., 0.}, P2[4] = {0., 0., 0., 0.};   // thread 0: sum_ev P, sum_ev P^2
+    long long n_had = 0, n_evt_done = 0;
+    int last_pid = 0, last_k = -1;
+    double last_q[3] = {0., 0., 0.};
+
     for (int64_t ev = blockIdx.x; ev < A.nev; ev += gridDim.x) {
-        for (int i = threadIdx.x; i < ISS_QA_NSPEC*ISS_QA_NPT; i += blockDim.x)
-            (&pt_cnt[0][0])[i] = 0;
-        if (threadIdx.x < ISS_QA_NSPEC) n_cnt[threadIdx.x] = 0;
-        __syncthreads();
         const int64_t b = A.event_off[ev], e = A.event_off[ev + 1];
         double P[4] = {0., 0., 0., 0.};
-        double T[16];
-#pragma unroll
-        for (int i = 0; i < 16; i++) T[i] = 0.;
-        double net[3] = {0., 0., 0.};
         for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
             const iss_hadron hd = A.hadrons[i];
             const double p[4] = {hd.E, hd.px, hd.py, hd.pz};
+            const double inv_e = 1.0/p[0];
 #pragma unroll
             for (int a = 0; a < 4; a++) {
                 P[a] += p[a];
 #pragma unroll
-                for (int c = 0; c < 4; c++) T[4*a + c] += p[a]*p[c]/p[0];
+                for (int c = a; c < 4; c++) T[4*a + c] += p[a]*p[c]*inv_e;
             }
-            if (A.dsp) {
-                int lo = 0, hi = A.ndsp - 1;
-                while (lo <= hi) {
-                    const int mid = (lo + hi) >> 1;
-                    const int v = __ldg(&A.sorted_pid[mid]);
-                    if (v == hd.pid) {
-                        const iss_decay_species &s = A.dsp[__ldg(&A.sorted_idx[mid])];
-                        net[0] += s.baryon;
-                        net[1] += s.strange;
-                        net[2] += s.charge;
-                        break;
+            if (hd.pid != last_pid) {
+                // hadrons are species-ordered inside an event: the look-ups below are rare
+                last_pid = hd.pid;
+                last_k = -1;
+                for (int j = 0; j < A.npid; j++)
+                    if (A.pids[j] == hd.pid) last_k = j;
+                last_q[0] = last_q[1] = last_q[2] = 0.;
+                if (A.dsp) {
+                    int lo = 0, hi = A.ndsp - 1;
+                    while (lo <= hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const int v = __ldg(&A.sorted_pid[mid]);
+                        if (v == hd.pid) {
+                            const iss_decay_species &s = A.dsp[__ldg(&A.sorted_idx[mid])];
+                            last_q[0] = s.baryon;
+                            last_q[1] = s.strange;
+                            last_q[2] = s.charge;
+                            break;
+                        }
+                        if (v < hd.pid) lo = mid + 1; else hi = mid - 1;
                     }
-                    if (v < hd.pid) lo = mid + 1; else hi = mid - 1;
                 }
             }
-            int k = -1;
-            for (int j = 0; j < A.npid; j++)
-                if (A.pids[j] == hd.pid) k = j;
+            net[0] += last_q[0];
+            net[1] += last_q[1];
+            net[2] += last_q[2];
+            const int k = last_k;
             if (k >= 0) {
-                double *blk = qa + ISS_QA_HEAD + static_cast<int64_t>(k)*ISS_QA_PER;
                 const double pT = sqrt(static_cast<double>(hd.px)*hd.px
                                        + static_cast<double>(hd.py)*hd.py);
                 // Histogram::fill with bin_width = (5-0)/(100-1) (Histogram.cpp:12, 27-36)
                 const double bw = 5.0/(ISS_QA_NPT - 1);
                 const int ib = static_cast<int>(pT/bw);
                 if (ib >= 0 && ib < ISS_QA_NPT) {
-                    atomicAdd(&pt_cnt[k][ib], 1);
-                    atomicAdd(&blk[ISS_QA_NPT + ib], pT);
+                    atomicAdd(&S.pt_evt[k][ib], 1);
+                    atomicAdd(&S.pt_sum[k][ib], pT);
                 }
                 const double mT2 = static_cast<double>(hd.mass)*hd.mass + pT*pT;
                 const double y = asinh(hd.pz/sqrt(mT2));
                 const int iy = static_cast<int>(floor((y + 5.0)/(10.0/ISS_QA_NY)));
-                if (iy >= 0 && iy < ISS_QA_NY) atomicAdd(&blk[3*ISS_QA_NPT + iy], 1.0);
+                if (iy >= 0 && iy < ISS_QA_NY) atomicAdd(&S.y_cnt[k][iy], 1u);
                 const double phi = atan2(static_cast<double>(hd.py), static_cast<double>(hd.px));
                 int iphi = static_cast<int>(floor((phi + M_PI)/(2.*M_PI/ISS_QA_NPHI)));
                 iphi = min(ISS_QA_NPHI - 1, max(0, iphi));
-                atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + iphi], 1.0);
+                atomicAdd(&S.phi_cnt[k][iphi], 1u);
                 const int iv = static_cast<int>(pT/(3.0/ISS_QA_NV2));
                 if (iv < ISS_QA_NV2) {
                     const double c2 = (pT > 0.) ? (static_cast<double>(hd.px)*hd.px
                                                    - static_cast<double>(hd.py)*hd.py)/(pT*pT)
                                                 : 0.;
-                    atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + iv], c2);
-                    atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + ISS_QA_NV2 + iv], 1.0);
+                    atomicAdd(&S.v2_num[k][iv], c2);
+                    atomicAdd(&S.v2_den[k][iv], 1u);
                 }
-                atomicAdd(&n_cnt[k], 1);
+                atomicAdd(&S.n_evt[k], 1);
+            }
+        }
+        // per-event quantities: total four-momentum and the per-event bin contents
+        for (int a = 0; a < 4; a++) {
+            const double t = block_sum(P[a], S.red);
+            if (threadIdx.x == 0) {
+                P1[a] += t;
+                P2[a] += t*t;
             }
         }
         __syncthreads();
-        // per-event quantities
-        for (int a = 0; a < 4; a++) {
-            const double t = block_sum(P[a], red);
-            if (threadIdx.x == 0) {
-                atomicAdd(&qa[1 + a], t);
-                atomicAdd(&qa[5 + a], t*t);
-            }
-        }
-        for (int a = 0; a < 16; a++) {
-            const double t = block_sum(T[a], red);
-            if (threadIdx.x == 0) atomicAdd(&qa[9 + a], t);
-        }
-        for (int a = 0; a < 3; a++) {
-            const double t = block_sum(net[a], red);
-            if (threadIdx.x == 0) atomicAdd(&qa[26 + a], t);
-        }
-        if (threadIdx.x == 0) {
-            atomicAdd(&qa[0], 1.0);
-            atomicAdd(&qa[25], static_cast<double>(e - b));
-        }
         for (int i = threadIdx.x; i < A.npid*ISS_QA_NPT; i += blockDim.x) {
             const int k = i/ISS_QA_NPT, ib = i - k*ISS_QA_NPT;
-            const int c = pt_cnt[k][ib];
+            const unsigned long long c = S.pt_evt[k][ib];
             if (c) {
-                double *blk = qa + ISS_QA_HEAD + static_cast<int64_t>(k)*ISS_QA_PER;
-                atomicAdd(&blk[ib], static_cast<double>(c));
-                atomicAdd(&blk[2*ISS_QA_NPT + ib], static_cast<double>(c)*c);
+                S.pt_cnt[k][ib] += c;
+                S.pt_sq[k][ib] += c*c;
+                S.pt_evt[k][ib] = 0;
             }
         }
         if (threadIdx.x < A.npid) {
-            const int k = threadIdx.x;
-            const double c = n_cnt[k];
-            double *blk = qa + ISS_QA_HEAD + static_cast<int64_t>(k)*ISS_QA_PER;
-            atomicAdd(&blk[ISS_QA_PER - 2], c);
-            atomicAdd(&blk[ISS_QA_PER - 1], c*c);
+            const unsigned long long c = S.n_evt[threadIdx.x];
+            S.n_tot[threadIdx.x] += c;
+            S.n_sq[threadIdx.x] += c*c;
+            S.n_evt[threadIdx.x] = 0;
+        }
+        if (threadIdx.x == 0) {
+            n_had += e - b;
+            n_evt_done++;
         }
         __syncthreads();
+    }
+
+    // flush: one global atomic per non-empty entry and CTA
+    for (int a = 0; a < 4; a++)
+        for (int c = a; c < 4; c++) {
+            const double t = block_sum(T[4*a + c], S.red);
+            if (threadIdx.x == 0 && t != 0.) {
+                atomicAdd(&qa[9 + 4*a + c], t);
+                if (c != a) atomicAdd(&qa[9 + 4*c + a], t);
+            }
+        }
+    for (int a = 0; a < 3; a++) {
+        const double t = block_sum(net[a], S.red);
+        if (threadIdx.x == 0 && t != 0.) atomicAdd(&qa[26 + a], t);
+    }
+    if (threadIdx.x == 0 && n_evt_done > 0) {
+        for (int a = 0; a < 4; a++) {
+            atomicAdd(&qa[1 + a], P1[a]);
+            atomicAdd(&qa[5 + a], P2[a]);
+        }
+        atomicAdd(&qa[0], static_cast<double>(n_evt_done));
+        atomicAdd(&qa[25], static_cast<double>(n_had));
+    }
+    __syncthreads();
+    for (int k = 0; k < A.npid; k++) {
+        double *blk = qa + ISS_QA_HEAD + static_cast<int64_t>(k)*ISS_QA_PER;
+        for (int i = threadIdx.x; i < ISS_QA_NPT; i += blockDim.x) {
+            if (S.pt_cnt[k][i]) {
+                atomicAdd(&blk[i], static_cast<double>(S.pt_cnt[k][i]));
+                atomicAdd(&blk[ISS_QA_NPT + i], S.pt_sum[k][i]);
+                atomicAdd(&blk[2*ISS_QA_NPT + i], static_cast<double>(S.pt_sq[k][i]));
+            }
+        }
+        for (int i = threadIdx.x; i < ISS_QA_NY; i += blockDim.x)
+            if (S.y_cnt[k][i]) atomicAdd(&blk[3*ISS_QA_NPT + i], static_cast<double>(S.y_cnt[k][i]));
+        for (int i = threadIdx.x; i < ISS_QA_NPHI; i += blockDim.x)
+            if (S.phi_cnt[k][i])
+                atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + i], static_cast<double>(S.phi_cnt[k][i]));
+        for (int i = threadIdx.x; i < ISS_QA_NV2; i += blockDim.x)
+            if (S.v2_den[k][i]) {
+                atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + i], S.v2_num[k][i]);
+                atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + ISS_QA_NV2 + i],
+                          static_cast<double>(S.v2_den[k][i]));
+            }
+        if (threadIdx.x == 0 && S.n_tot[k]) {
+            atomicAdd(&blk[ISS_QA_PER - 2], static_cast<double>(S.n_tot[k]));
+            atomicAdd(&blk[ISS_QA_PER - 1], static_cast<double>(S.n_sq[k]));
+        }
     }
 }
 
@@ -175,15 +243,21 @@ int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate) {
     A.qa = h->d_qa;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-    int64_t grid = std::min<int64_t>(A.nev, static_cast<int64_t>(nsm)*8);
+    const size_t smem = sizeof(QaShared);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(qa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem));
+        attr_set = true;
+    }
+    int64_t grid = std::min<int64_t>(A.nev, static_cast<int64_t>(nsm)*2);
     if (grid < 1) grid = 1;
     {
         ScopedTimer t(h, ISS_T_QA);
-        qa_kernel<<<static_cast<unsigned>(grid), QA_THREADS, 0, h->stream>>>(A); ISS_LAUNCHED(h);
+        qa_kernel<<<static_cast<unsigned>(grid), QA_THREADS, smem, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
-    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    return ISS_OK;
+    return ISS_OK;      // asynchronous: iss_cuda_qa_fetch synchronises
 }
 
 }  // namespace iss

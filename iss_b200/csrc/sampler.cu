@@ -708,8 +708,19 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
             h->d_off_out, ns, nev, h->d_event_off); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
     }
-    rc = ensure_capacity(h, &h->d_hadrons, &h->hadron_cap, total_out);
-    if (rc) return rc;
+    {
+        // output buffer of this batch: the one whose previous device->host copy (if any) is
+        // ordered before this kernel
+        const int b = h->cur_buf;
+        if (h->copy_pending[b]) {
+            ISS_CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->copy_done[b], 0));
+            h->copy_pending[b] = false;
+        }
+        rc = ensure_capacity(h, &h->d_hadbuf[b], &h->hadbuf_cap[b], total_out);
+        if (rc) return rc;
+        h->d_hadrons = h->d_hadbuf[b];
+        h->hadron_cap = h->hadbuf_cap[b];
+    }
     if (!h->d_counters) ISS_CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned long long)*8));
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long)*8, h->stream));
     h->n_hadrons = total_out;

@@ -330,16 +330,12 @@ int run_yields(iss_handle *h) {
 
     const int64_t ns = h->nspecies;
     const size_t nval = static_cast<size_t>(ns)*h->ncell_pad;
-    if (!h->d_yields) {
-        ISS_CUDA_TRY(h, cudaMalloc(&h->d_yields, sizeof(double)*nval));
-        ISS_CUDA_TRY(h, cudaMalloc(&h->d_cdf, sizeof(double)*nval));
-        ISS_CUDA_TRY(h, cudaMalloc(&h->d_tilesum, sizeof(double)*ns*h->ntile));
-        ISS_CUDA_TRY(h, cudaMalloc(&h->d_tilebase, sizeof(double)*ns*(h->ntile + 1)));
-        ISS_CUDA_TRY(h, cudaMalloc(&h->d_total, sizeof(double)*ns));
-        ISS_CUDA_TRY(h, cudaMalloc(&h->d_cellcoef, sizeof(double)*COEF_STRIDE*h->ncell));
-        // padding cells must read as zero yield
-        ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_yields, 0, sizeof(double)*nval, h->stream));
-    }
+    ISS_ENSURE(h, h->d_yields, h->yields_bytes, sizeof(double)*nval);
+    ISS_ENSURE(h, h->d_cdf, h->cdf_bytes, sizeof(double)*nval);
+    ISS_ENSURE(h, h->d_tilesum, h->tilesum_bytes, sizeof(double)*ns*h->ntile);
+    ISS_ENSURE(h, h->d_tilebase, h->tilebase_bytes, sizeof(double)*ns*(h->ntile + 1));
+    ISS_ENSURE(h, h->d_total, h->total_bytes, sizeof(double)*ns);
+    ISS_ENSURE(h, h->d_cellcoef, h->coef_bytes, sizeof(double)*COEF_STRIDE*h->ncell);
 
     YieldArgs a;
     a.surf = h->d_surf;

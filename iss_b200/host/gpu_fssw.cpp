@@ -12,7 +12,11 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <map>
+#include <mutex>
 #include <sstream>
+#include <thread>
+#include <unordered_map>
 
 #include "logger.h"
 
@@ -54,6 +58,82 @@ std::vector<double> read_numbers(const std::string &file, int skip_lines) {
         p = e;
     }
     return out;
+}
+
+// Process-wide caches.  MUSIC/JETSCAPE-style hosts call iSS::generate_samples() once per
+// hydro event and the reference builds a fresh FSSW every time (iSS.cpp:145-149); rebuilding
+// the CUDA context objects, re-pinning gigabytes of host memory and re-parsing the coefficient
+// tables on every call would dominate the run, so they are kept for the life of the process.
+struct HandlePool {
+    std::mutex mu;
+    std::map<int, std::vector<iss_handle *>> idle;     // by device
+    ~HandlePool() {
+        for (auto &kv : idle)
+            for (iss_handle *h : kv.second) iss_cuda_destroy(h);
+    }
+};
+HandlePool &handle_pool() {
+    static HandlePool p;
+    return p;
+}
+
+struct PinnedBlock {
+    void *ptr = nullptr;
+    int64_t bytes = 0;
+};
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<PinnedBlock> idle;
+};
+PinnedPool &pinned_pool() {
+    static PinnedPool p;      // blocks are left to the driver at process exit
+    return p;
+}
+
+// a pinned block of at least `bytes` (the largest idle one if it fits, else a new allocation)
+PinnedBlock pinned_acquire(iss_handle *h, int64_t bytes) {
+    PinnedPool &P = pinned_pool();
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        for (size_t i = 0; i < P.idle.size(); i++)
+            if (P.idle[i].bytes >= bytes) {
+                PinnedBlock b = P.idle[i];
+                P.idle.erase(P.idle.begin() + i);
+                return b;
+            }
+    }
+    PinnedBlock b;
+    if (iss_cuda_host_alloc(h, &b.ptr, bytes) != ISS_OK) {
+        iss_host::error(std::string("iss_cuda_host_alloc failed: ") + iss_cuda_last_error(h));
+        exit(-1);
+    }
+    b.bytes = bytes;
+    return b;
+}
+
+void pinned_release(iss_handle *h, PinnedBlock b) {
+    if (!b.ptr) return;
+    PinnedPool &P = pinned_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    // keep at most two idle blocks (hadron list + surface staging): drop the smallest
+    P.idle.push_back(b);
+    while (P.idle.size() > 2) {
+        size_t k = 0;
+        for (size_t i = 1; i < P.idle.size(); i++)
+            if (P.idle[i].bytes < P.idle[k].bytes) k = i;
+        iss_cuda_host_free(h, P.idle[k].ptr);
+        P.idle.erase(P.idle.begin() + k);
+    }
+}
+
+const std::vector<double> &cached_numbers(const std::string &file, int skip_lines) {
+    static std::mutex mu;
+    static std::map<std::string, std::vector<double>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    const std::string key = file + "#" + std::to_string(skip_lines);
+    auto it = cache.find(key);
+    if (it == cache.end()) it = cache.emplace(key, read_numbers(file, skip_lines)).first;
+    return it->second;
 }
 
 }  // namespace
@@ -98,8 +178,17 @@ GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
     int device = 0;
     if (const char *lr = getenv("LOCAL_RANK")) device = atoi(lr);
     if (const char *dv = getenv("ISS_CUDA_DEVICE")) device = atoi(dv);
-    const int rc = iss_cuda_create(device, &h_);
-    if (rc != ISS_OK) {
+    device_ = device;
+    {
+        HandlePool &P = handle_pool();
+        std::lock_guard<std::mutex> lk(P.mu);
+        auto &v = P.idle[device];
+        if (!v.empty()) {
+            h_ = v.back();
+            v.pop_back();
+        }
+    }
+    if (!h_ && iss_cuda_create(device, &h_) != ISS_OK) {
         iss_host::error("iss_cuda_create: no usable CUDA device (the B200 engine has no CPU "
                         "fallback)");
         exit(-1);
@@ -131,10 +220,16 @@ GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
 }
 
 GpuFSSW::~GpuFSSW() {
-    if (h_) {
-        if (hadrons_) iss_cuda_host_free(h_, hadrons_);
-        iss_cuda_destroy(h_);
-    }
+    if (!h_) return;
+    iss_cuda_fetch_wait(h_);
+    iss_cuda_synchronize(h_);
+    PinnedBlock b;
+    b.ptr = hadrons_;
+    b.bytes = hadron_cap_*static_cast<int64_t>(sizeof(iSS_Hadron));
+    pinned_release(h_, b);
+    HandlePool &P = handle_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.idle[device_].push_back(h_);
 }
 
 // chosen list -> indices into the pdg table, unknown ids dropped with a warning, then a stable
@@ -187,21 +282,35 @@ void GpuFSSW::select_species_(const std::vector<int> &chosen_monvals) {
 
 void GpuFSSW::upload_surface_() {
     const int64_t n = static_cast<int64_t>(surf_.size());
-    std::vector<float> soa(static_cast<size_t>(ISS_NFIELD)*n);
-    const float *ptrs[ISS_NFIELD];
-    for (int k = 0; k < ISS_NFIELD; k++) ptrs[k] = soa.data() + static_cast<size_t>(k)*n;
-    for (int64_t c = 0; c < n; c++) {
-        const FO_surf_LRF &s = surf_[c];
-        const float rec[ISS_NFIELD] = {
-            s.tau, s.xpt, s.ypt, s.eta,
-            s.da_mu_LRF[0], s.da_mu_LRF[1], s.da_mu_LRF[2], s.da_mu_LRF[3],
-            s.u_tz[0], s.u_tz[1], s.u_tz[2], s.u_tz[3],
-            s.Edec, s.Tdec, s.Pdec, s.Bn, s.muB, s.muS, s.muQ, s.bulkPi,
-            s.piLRF_xx, s.piLRF_xy, s.piLRF_xz, s.piLRF_yy, s.piLRF_yz,
-            s.qmuLRF_x, s.qmuLRF_y, s.qmuLRF_z};
-        for (int k = 0; k < ISS_NFIELD; k++) soa[static_cast<size_t>(k)*n + c] = rec[k];
+    PinnedBlock stage = pinned_acquire(h_, n*ISS_NFIELD*static_cast<int64_t>(sizeof(float)));
+    float *dst = static_cast<float *>(stage.ptr);
+    auto pack = [&](int64_t c0, int64_t c1) {
+        for (int64_t c = c0; c < c1; c++) {
+            const FO_surf_LRF &s = surf_[c];
+            float *r = dst + c*ISS_NFIELD;
+            r[0] = s.tau; r[1] = s.xpt; r[2] = s.ypt; r[3] = s.eta;
+            for (int k = 0; k < 4; k++) {
+                r[4 + k] = s.da_mu_LRF[k];
+                r[8 + k] = s.u_tz[k];
+            }
+            r[12] = s.Edec; r[13] = s.Tdec; r[14] = s.Pdec; r[15] = s.Bn;
+            r[16] = s.muB; r[17] = s.muS; r[18] = s.muQ; r[19] = s.bulkPi;
+            r[20] = s.piLRF_xx; r[21] = s.piLRF_xy; r[22] = s.piLRF_xz; r[23] = s.piLRF_yy;
+            r[24] = s.piLRF_yz; r[25] = s.qmuLRF_x; r[26] = s.qmuLRF_y; r[27] = s.qmuLRF_z;
+        }
+    };
+    const int nthread = static_cast<int>(std::max<int64_t>(
+        1, std::min<int64_t>(8, std::min<int64_t>(std::thread::hardware_concurrency(), n/65536))));
+    if (nthread <= 1) {
+        pack(0, n);
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthread; t++)
+            pool.emplace_back(pack, n*t/nthread, n*(t + 1)/nthread);
+        for (auto &t : pool) t.join();
     }
-    check_(iss_cuda_upload_surface(h_, ptrs, n), "iss_cuda_upload_surface");
+    check_(iss_cuda_upload_surface_aos(h_, dst, n), "iss_cuda_upload_surface_aos");
+    pinned_release(h_, stage);
 }
 
 // delta-f coefficient tables, file formats of FSSW.cpp:1215-1376 and 1546-1568
@@ -218,14 +327,14 @@ void GpuFSSW::upload_tables_() {
         int nT = 0, nmu = 0;
         for (int c = 0; c < 3; c++) {
             const std::string file = folder + "/c" + std::to_string(c) + ".dat";
-            std::vector<double> head = read_numbers(file, 0);
+            const std::vector<double> &head = cached_numbers(file, 0);
             if (head.size() < 2) {
                 iss_host::error("Can not found file: " + file);
                 exit(1);
             }
             nT = static_cast<int>(head[0]);
             nmu = static_cast<int>(head[1]);
-            std::vector<double> v = read_numbers(file, 3);
+            const std::vector<double> &v = cached_numbers(file, 3);
             if (static_cast<long>(v.size()) < 3L*nT*nmu) {
                 iss_host::error("short 14-moment table: " + file);
                 exit(1);
@@ -246,7 +355,7 @@ void GpuFSSW::upload_tables_() {
     }
     if (bulk_kind_ == 21) {
         const std::string file = dir + (smash ? "/smash" : "/urqmd") + "/NEoSBQS_CE_deltafCoeff.dat";
-        std::vector<double> v = read_numbers(file, 1);
+        const std::vector<double> &v = cached_numbers(file, 1);
         if (v.size() < 200u*200u*5u) {
             iss_host::error("short CE table: " + file);
             exit(1);
@@ -256,7 +365,7 @@ void GpuFSSW::upload_tables_() {
     } else if (bulk_kind_ == 20) {
         const std::string file =
             dir + (smash ? "/smash" : "/urqmd") + "/NEoSBQS_22mom_deltafCoeff.dat";
-        std::vector<double> v = read_numbers(file, 1);
+        const std::vector<double> &v = cached_numbers(file, 1);
         if (v.size() < 200u*200u*8u) {
             iss_host::error("short 22-moment table: " + file);
             exit(1);
@@ -268,7 +377,7 @@ void GpuFSSW::upload_tables_() {
         // 100 (mu_B) x 150 (T) rows "T muB kappa", T fastest; the grid is hard-coded in the
         // reference (FSSW.cpp:1548-1553)
         const std::string file = dir + "/Coefficients_RTA_diffusion.dat";
-        std::vector<double> v = read_numbers(file, 0);
+        const std::vector<double> &v = cached_numbers(file, 0);
         const int nT = 150, nmu = 100;
         if (static_cast<long>(v.size()) < 3L*nT*nmu) {
             iss_host::error("short kappa_B table: " + file);
@@ -289,6 +398,8 @@ void GpuFSSW::upload_tables_() {
 void GpuFSSW::upload_decay_table_() {
     std::vector<iss_decay_species> sp(particles_.size());
     std::vector<iss_decay_channel> ch;
+    std::unordered_map<int, int> row_of;    // first row with a given Monte-Carlo id
+    for (size_t i = 0; i < particles_.size(); i++) row_of.emplace(particles_[i].monval, static_cast<int>(i));
     for (size_t i = 0; i < particles_.size(); i++) {
         const particle_info &p = particles_[i];
         iss_decay_species &d = sp[i];
@@ -311,11 +422,8 @@ void GpuFSSW::upload_decay_table_() {
                 c.daughter[k] = -1;
                 const int monval = p.decay_channels[j]->decay_part[k];
                 if (monval == 0) continue;
-                for (size_t n = 0; n < particles_.size(); n++)
-                    if (particles_[n].monval == monval) {
-                        c.daughter[k] = static_cast<int>(n);
-                        break;
-                    }
+                const auto it = row_of.find(monval);
+                if (it != row_of.end()) c.daughter[k] = it->second;
             }
             ch.push_back(c);
         }
@@ -360,15 +468,17 @@ void GpuFSSW::reserve_hadrons_(int64_t need) {
     if (need <= hadron_cap_) return;
     int64_t cap = std::max<int64_t>(need, hadron_cap_ + hadron_cap_/2);
     cap = std::max<int64_t>(cap, 1024);
-    void *p = nullptr;
-    check_(iss_cuda_host_alloc(h_, &p, cap*static_cast<int64_t>(sizeof(iSS_Hadron))),
-           "iss_cuda_host_alloc");
+    PinnedBlock b = pinned_acquire(h_, cap*static_cast<int64_t>(sizeof(iSS_Hadron)));
     if (hadrons_) {
-        memcpy(p, hadrons_, sizeof(iSS_Hadron)*event_off_.back());
-        iss_cuda_host_free(h_, hadrons_);
+        check_(iss_cuda_fetch_wait(h_), "iss_cuda_fetch_wait");     // copies into the old block
+        memcpy(b.ptr, hadrons_, sizeof(iSS_Hadron)*event_off_.back());
+        PinnedBlock old;
+        old.ptr = hadrons_;
+        old.bytes = hadron_cap_*static_cast<int64_t>(sizeof(iSS_Hadron));
+        pinned_release(h_, old);
     }
-    hadrons_ = static_cast<iSS_Hadron *>(p);
-    hadron_cap_ = cap;
+    hadrons_ = static_cast<iSS_Hadron *>(b.ptr);
+    hadron_cap_ = b.bytes/static_cast<int64_t>(sizeof(iSS_Hadron));
 }
 
 void GpuFSSW::compute_yields() {
@@ -417,17 +527,24 @@ void GpuFSSW::sample_events() {
     event_cache_.clear();
     event_cache_.resize(nev_);
 
-    // events per batch from the free device memory: 40 B per hadron, x2.5 head-room for decays
+    // events per batch: bounded by the free device memory (40 B per hadron in two output buffers,
+    // x4 head-room for decays) and small enough that the device->host copy of one batch overlaps
+    // the sampling of the next (at least 8 batches for large runs)
     int64_t free_b = 0, total_b = 0;
     check_(iss_cuda_mem_info(h_, &free_b, &total_b), "iss_cuda_mem_info");
-    const double per_event = std::max(1.0, dN_event)*40.0*(flag_perform_decays_ ? 4.0 : 1.5)
-                             + 16.0*species_.size()*3;
+    const double per_event = std::max(1.0, dN_event)*40.0*(flag_perform_decays_ ? 6.0 : 2.5)
+                             + 24.0*species_.size();
     int64_t batch = static_cast<int64_t>(0.5*static_cast<double>(free_b)/per_event);
+    const double hadrons_total = dN_event*static_cast<double>(nev_);
+    if (hadrons_total > 4e6) batch = std::min<int64_t>(batch, (nev_ + 7)/8);
     batch = std::max<int64_t>(1, std::min<int64_t>(batch, nev_));
     const bool decays_on = flag_perform_decays_ && afterburner_type_ != AfterburnerType::SMASH;
     if (decays_on) std::cout << "perform resonance decays... " << std::endl;
     const int32_t qa_pids[2] = {211, 2212};
-    reserve_hadrons_(static_cast<int64_t>(dN_event*nev_*(decays_on ? 2.0 : 1.05)) + 1024);
+    const int64_t nsp = static_cast<int64_t>(spectators_.size());
+    reserve_hadrons_(static_cast<int64_t>(dN_event*nev_*(decays_on ? 2.0 : 1.02)
+                                         + 6.0*std::sqrt(dN_event*nev_ + 1.0))
+                     + nsp*nev_ + 1024);
 
     for (int64_t ev0 = 0; ev0 < nev_; ev0 += batch) {
         const int64_t ev1 = std::min<int64_t>(nev_, ev0 + batch);
@@ -441,13 +558,12 @@ void GpuFSSW::sample_events() {
         std::vector<int64_t> off(ev1 - ev0 + 1);
         check_(iss_cuda_event_offsets(h_, off.data()), "iss_cuda_event_offsets");
         const int64_t base = event_off_.back();
-        const int64_t nsp = static_cast<int64_t>(spectators_.size());
         if (nsp == 0) {
             reserve_hadrons_(base + cnt.n_hadrons);
             int64_t got = 0;
-            check_(iss_cuda_fetch_all(h_, reinterpret_cast<iss_hadron *>(hadrons_ + base),
-                                      hadron_cap_ - base, &got),
-                   "iss_cuda_fetch_all");
+            check_(iss_cuda_fetch_all_async(h_, reinterpret_cast<iss_hadron *>(hadrons_ + base),
+                                            hadron_cap_ - base, &got),
+                   "iss_cuda_fetch_all_async");
             for (int64_t i = 1; i <= ev1 - ev0; i++) event_off_.push_back(base + off[i]);
         } else {
             // spectators are appended to every event (FSSW::addSpectatorsToHadronList)
@@ -465,6 +581,7 @@ void GpuFSSW::sample_events() {
             }
         }
     }
+    check_(iss_cuda_fetch_wait(h_), "iss_cuda_fetch_wait");
     if (flag_spectators_) std::cout << "Add spectators to the hadron list... " << std::endl;
     qa_.assign(iss_cuda_qa_size(), 0.);
     check_(iss_cuda_qa_fetch(h_, qa_.data()), "iss_cuda_qa_fetch");
@@ -495,28 +612,23 @@ std::vector<iSS_Hadron> *GpuFSSW::get_hadron_list_iev(const int iev) {
     return event_cache_[iev].get();
 }
 
-// FSSW::computeAvgTotalEnergyMomentum (FSSW.cpp:2028-2059)
+// FSSW::computeAvgTotalEnergyMomentum (FSSW.cpp:2028-2059).  The per-event sums of P^mu and
+// their squares were accumulated on the device with the other QA quantities (QA block [1..8]);
+// spectators, which are appended on the host, are added here.
 void GpuFSSW::computeAvgTotalEnergyMomentum() {
-    double avg[4] = {0, 0, 0, 0}, err[4] = {0, 0, 0, 0};
-    for (int64_t ev = 0; ev < nev_; ev++) {
-        double P[4] = {0, 0, 0, 0};
-        for (int64_t i = event_off_[ev]; i < event_off_[ev + 1]; i++) {
-            P[0] += hadrons_[i].E;
-            P[1] += hadrons_[i].px;
-            P[2] += hadrons_[i].py;
-            P[3] += hadrons_[i].pz;
-        }
-        for (int j = 0; j < 4; j++) {
-            avg[j] += P[j];
-            err[j] += P[j]*P[j];
-        }
+    double sp[4] = {0, 0, 0, 0};
+    for (const iSS_Hadron &hd : spectators_) {
+        sp[0] += hd.E; sp[1] += hd.px; sp[2] += hd.py; sp[3] += hd.pz;
     }
     info("Averaged total energy and momentum:");
     for (int i = 0; i < 4; i++) {
-        avg[i] /= nev_;
-        err[i] = std::sqrt((err[i]/nev_ - avg[i]*avg[i])/nev_);
+        // sum (P + s) = S1 + n s ;  sum (P + s)^2 = S2 + 2 s S1 + n s^2
+        const double S1 = qa_[1 + i], S2 = qa_[5 + i], n = static_cast<double>(nev_);
+        const double avg = (S1 + n*sp[i])/n;
+        const double sq = (S2 + 2.*sp[i]*S1 + n*sp[i]*sp[i])/n;
+        const double err = std::sqrt(std::max(0., sq - avg*avg)/n);
         std::ostringstream os;
-        os << "<P[" << i << "]> = " << avg[i] << " +/- " << err[i] << " GeV.";
+        os << "<P[" << i << "]> = " << avg << " +/- " << err << " GeV.";
         info(os.str());
     }
 }

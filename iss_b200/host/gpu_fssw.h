@@ -69,6 +69,7 @@ class GpuFSSW {
     int use_oscar_, use_gzip_, use_binary_;
 
     iss_handle *h_ = nullptr;
+    int device_ = 0;
     std::vector<iss_species> species_;
     std::vector<int> species_table_idx_;    // index into particles_ (chosen_particles_sampling_table)
     std::vector<double> dN_species_;

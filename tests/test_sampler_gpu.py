@@ -160,3 +160,54 @@ def test_decays_match_oracle(name, nev, extra, built, tmp_path):
         assert set(np.unique(fin["pid"])) <= stable
     finally:
         s.close()
+
+
+def test_qa_block_matches_numpy(built, tmp_path):
+    """iss_cuda_histograms (QA kernel, the block NCCL reduces) against numpy on the same hadrons:
+    counts exact, floating sums to 1e-9 (atomic order)."""
+    capi = built
+    g, s = prepare(capi, "s3d_ce", tmp_path, {})
+    try:
+        e = s.engine()
+        e.compute_yields()
+        nev = 3000
+        e.sample(5, 0, nev)
+        had = e.fetch_all()
+        off = e.event_offsets(nev)
+        pids = [211, -211, 2212, 321, 111]
+        qa = e.histograms(pids)
+        E, px, py, pz = (had[k].astype(np.float64) for k in ("E", "px", "py", "pz"))
+        assert qa[0] == nev and qa[25] == len(had)
+        ev = np.repeat(np.arange(nev), np.diff(off))
+        for i, a in enumerate((E, px, py, pz)):
+            P = np.bincount(ev, weights=a, minlength=nev)
+            assert np.isclose(qa[1 + i], P.sum(), rtol=1e-9)
+            assert np.isclose(qa[5 + i], (P**2).sum(), rtol=1e-9)
+        p4 = np.stack([E, px, py, pz])
+        T = np.einsum("in,jn->ij", p4, p4/E)
+        assert np.allclose(qa[9:25].reshape(4, 4), T, rtol=1e-9, atol=1e-9)
+        sp = s.species()
+        Bof = dict(zip(sp["pid"], sp["baryon"]))
+        assert np.isclose(qa[26], sum(Bof.get(p, 0) for p in had["pid"]))
+        pT = np.hypot(px, py)
+        for k, pid in enumerate(pids):
+            blk = qa[capi.QA_HEAD + k*capi.QA_PER: capi.QA_HEAD + (k + 1)*capi.QA_PER]
+            m = had["pid"] == pid
+            ib = (pT[m]/(5.0/99)).astype(int)
+            ok = ib < 100
+            cnt = np.bincount(ib[ok], minlength=100)
+            assert np.array_equal(blk[:100], cnt)
+            assert np.allclose(blk[100:200], np.bincount(ib[ok], weights=pT[m][ok], minlength=100), rtol=1e-9)
+            per_ev = np.zeros((nev, 100))
+            np.add.at(per_ev, (ev[m][ok], ib[ok]), 1)
+            assert np.array_equal(blk[200:300], (per_ev**2).sum(axis=0))
+            nper = np.bincount(ev[m], minlength=nev)
+            assert blk[-2] == nper.sum() and blk[-1] == (nper**2).sum()
+            assert blk[300:400].sum() <= m.sum() and blk[400:464].sum() == m.sum()
+            iv = (pT[m]/(3.0/20)).astype(int)
+            okv = iv < 20
+            assert np.array_equal(blk[484:504], np.bincount(iv[okv], minlength=20))
+            c2 = (px[m]**2 - py[m]**2)/pT[m]**2
+            assert np.allclose(blk[464:484], np.bincount(iv[okv], weights=c2[okv], minlength=20), rtol=1e-8, atol=1e-9)
+    finally:
+        s.close()
