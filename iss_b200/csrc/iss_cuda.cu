@@ -146,7 +146,7 @@ int iss_cuda_destroy(iss_handle *h) {
     if (h->copy_done2) cudaEventDestroy(h->copy_done2);
     free_surface(h);
     cudaFree(h->d_species);
-    cudaFree(h->d_bessel); cudaFree(h->d_expint); cudaFree(h->d_ce); cudaFree(h->d_mom22);
+    cudaFree(h->d_bessel); cudaFree(h->d_expint); cudaFree(h->d_sf4); cudaFree(h->d_combos); cudaFree(h->d_ce); cudaFree(h->d_mom22);
     cudaFree(h->d_mom14); cudaFree(h->d_kappa);
     for (int r = 0; r < 6; r++) cudaFree(h->d_momtab[r]);
     cudaFree(h->d_dsp); cudaFree(h->d_dch); cudaFree(h->d_sorted_pid); cudaFree(h->d_sorted_idx);
@@ -226,6 +226,7 @@ int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t n
     cudaSetDevice(h->device);
     h->h_species.assign(species, species + nspecies);
     std::vector<DeviceSpecies> ds(nspecies);
+    std::vector<int4> combos;
     for (int i = 0; i < nspecies; i++) {
         const iss_species &p = species[i];
         DeviceSpecies &d = ds[i];
@@ -238,8 +239,19 @@ int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t n
         d.sign = static_cast<int16_t>(p.sign);
         d.trunc10_mass = (p.mass < 0.7) ? 1 : 0;    // FSSW.cpp:741
         d.decay_idx = p.decay_idx;
-        d.pad = 0;
+        int c = 0;
+        for (; c < static_cast<int>(combos.size()); c++)
+            if (combos[c].x == p.baryon && combos[c].y == p.strange && combos[c].z == p.charge) break;
+        if (c == static_cast<int>(combos.size())) combos.push_back(make_int4(p.baryon, p.strange, p.charge, 0));
+        d.combo = c;
     }
+    if (combos.size() > 200) ISS_FAIL(h, ISS_ERR_ARG, "more than 200 distinct (B,S,Q) combinations");
+    if (h->d_combos) cudaFree(h->d_combos);
+    h->d_combos = nullptr;
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_combos, sizeof(int4)*combos.size()));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_combos, combos.data(), sizeof(int4)*combos.size(),
+                                    cudaMemcpyHostToDevice, h->stream));
+    h->ncombo = static_cast<int>(combos.size());
     if (h->d_species) cudaFree(h->d_species);
     h->d_species = nullptr;
     ISS_CUDA_TRY(h, cudaMalloc(&h->d_species, sizeof(DeviceSpecies)*nspecies));
@@ -266,6 +278,7 @@ int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data, int64
         g.n = static_cast<int>(n0);
         g.x_max_minus_dx = grid4[2];    // = sf_x_max - sf_dx of the caller
         h->sf = g;
+        if (h->d_sf4) { cudaFree(h->d_sf4); h->d_sf4 = nullptr; }
         if (kind == ISS_TABLE_BESSEL_K) return upload_doubles(h, &h->d_bessel, data, n0*3);
         return upload_doubles(h, &h->d_expint, data, n0*9);
     }

@@ -35,6 +35,10 @@ struct MomentumTable {      // one Boson/FermionMomentumSampler instance
     int trunc;              // trunc_order_
     double m0;              // regime base (m0_)
     double e0, de;          // Etilde_[0], Etilde_[1] - Etilde_[0]
+    // constants of the series evaluated per (cell, species) at Etilde = (m - mu)/T
+    double exp_m0;          // exp(m0)
+    double denom0;          // 1 -/+ exp(-m0) (boson / fermion closed form of CDF_0)
+    double a[10];           // exp(-m0 n), n = 0..9
 };
 
 constexpr int CELL_STRIDE = 32;   // floats per AoS cell record (28 fields + t, z + 2 spare)
@@ -48,7 +52,7 @@ struct DeviceSpecies {      // what the kernels read per species (smem-friendly,
     int16_t gspin, baryon, strange, charge, sign;
     int16_t trunc10_mass;   // 1 if mass < 0.7 (series of 10 terms when also T > 0.05)
     int32_t decay_idx;
-    int32_t pad;
+    int32_t combo;          // index of (B,S,Q) among the distinct combinations of the list
 };
 
 }  // namespace iss
@@ -81,6 +85,8 @@ struct iss_handle {
     // tables
     double *d_bessel = nullptr; iss::SfGrid sf{};
     double *d_expint = nullptr;
+    double *d_sf4 = nullptr; bool sf4_with_diff = false;
+    int4 *d_combos = nullptr; int ncombo = 0;
     double *d_ce = nullptr; int ce_ne = 0, ce_nb = 0;
     double *d_mom22 = nullptr;
     double *d_mom14 = nullptr; iss::Grid2D g14{};

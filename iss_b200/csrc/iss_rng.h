@@ -79,13 +79,19 @@ ISS_HD double u53(uint32_t hi, uint32_t lo) {
     return static_cast<double>(v)*(1.0/9007199254740992.0);
 }
 
-// A per-object random stream: key = seed, counter = (block, draw_lo, event, species|stream<<24).
-// Each Philox block yields two 53-bit uniforms; next() hands them out in order.
+// 32-bit uniform in (0,1): (x + 1/2) 2^-32.
+ISS_HD double u32(uint32_t x) {
+    return (static_cast<double>(x) + 0.5)*(1.0/4294967296.0);
+}
+
+// A per-object random stream: key = seed, counter = (block, draw, event, species|stream<<24).
+// Each Philox block yields four 32-bit words that are handed out in order; next() consumes two
+// words for a 53-bit uniform in [0,1), next32() one word for a 32-bit uniform in (0,1).
 struct Stream {
     uint32_t ctr[4];
     uint32_t key[2];
     uint32_t buf[4];
-    int have;   // uniforms left in buf (0..2)
+    int pos;    // next unused word of buf (4: empty)
 
     ISS_HD void init(uint64_t seed, uint32_t stream, uint32_t species, uint32_t event,
                      uint32_t draw, uint32_t block0 = 0) {
@@ -95,19 +101,57 @@ struct Stream {
         ctr[1] = draw;
         ctr[2] = event;
         ctr[3] = (stream << 24) | (species & 0xFFFFFFu);
-        have = 0;
+        pos = 4;
     }
-    ISS_HD double next() {
-        if (have == 0) {
+    ISS_HD uint32_t word() {
+        if (pos == 4) {
             philox4x32_10(ctr, key, buf);
             ctr[0]++;
-            have = 2;
+            pos = 0;
         }
-        double u = (have == 2) ? u53(buf[0], buf[1]) : u53(buf[2], buf[3]);
-        have--;
-        return u;
+        const uint32_t w = (pos == 0) ? buf[0] : (pos == 1) ? buf[1] : (pos == 2) ? buf[2] : buf[3];
+        pos++;
+        return w;
+    }
+    ISS_HD double next() {
+        const uint32_t hi = word();
+        const uint32_t lo = word();
+        return u53(hi, lo);
+    }
+    ISS_HD double next32() { return u32(word()); }
+};
+
+// Block-granular view of the same streams, used by the sampler kernel: every random decision
+// point consumes one whole Philox block (four words) and the only state is the block counter.
+//   cell choice        block: (w0,w1) -> 53-bit uniform
+//   |p| proposal       block: (w0,w1) -> r (53 bit), w2 -> inner accept (32 bit), w3 -> phi (32 bit)
+//   direction/accept   block: w0 -> cos(theta) (32 bit), w1 -> accept (32 bit)   [only if the inner
+//                      accept passed]
+//   rapidity           block: w0 -> y (32 bit)                                   [boost-invariant]
+struct BlockStream {
+    uint32_t block;     // next block of the stream
+    uint32_t draw;      // hadron index inside (event, species)
+    uint32_t event;
+    ISS_HD void init(uint32_t event_, uint32_t draw_) {
+        block = 0;
+        draw = draw_;
+        event = event_;
     }
 };
+
+#if defined(__CUDACC__)
+static __device__ __noinline__
+#else
+inline
+#endif
+void philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                  uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
+    const uint32_t ctr[4] = {c0, c1, c2, c3};
+    const uint32_t key[2] = {k0, k1};
+    uint32_t out[4];
+    philox4x32_10(ctr, key, out);
+    w0 = out[0]; w1 = out[1]; w2 = out[2]; w3 = out[3];
+}
 
 // Exact Poisson draw by inversion from the mode ("chop-down" outward from
 // m = floor(lambda)).  pmode = Poisson pmf at m, computed once per species on the

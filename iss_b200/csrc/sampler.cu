@@ -67,6 +67,46 @@ __host__ __device__ inline void cdf_012(double Et, double m0, int trunc, double 
     }
 }
 
+// The same three series at Etilde = a for the per-(cell, species) set-up
+// (MomentumSamplerBase::update_cache), with the table constants exp(-m0 n) precomputed and
+// exp((m0 - a)(n+1)) formed as powers of exp(m0 - a): 2 exp + 1 log instead of 22 exp + 1 log.
+// Differs from the literal series only by FP64 rounding (~1e-16 relative).
+template <bool FERMION>
+__device__ __forceinline__ void cdf_012_lane(const MomentumTable &mt, double Et, double &c0,
+                                             double &c1, double &c2) {
+    const double m0 = mt.m0;
+    const double e1 = exp(m0 - Et);
+    double b = 1.;
+    double s0 = 0.;
+    c1 = 0.;
+    c2 = 0.;
+    double sign = 1.;
+#pragma unroll 1
+    for (int n = 0; n < mt.trunc; n++) {
+        const double n1 = n + 1;
+        b *= e1;
+        const double a = mt.a[n];
+        const double inv = 1./n1;
+        if (FERMION) {
+            if (n == 0) s0 += a*(1. - b);
+        } else {
+            s0 += inv*a*(1. - b);
+        }
+        c1 += ((FERMION ? sign : 1.)*inv*inv*a*((m0*n1 + 1) - b*(Et*n1 + 1)));
+        c2 += (inv*inv*inv*a*((m0*n1*(m0*n1 + 2) + 2) - b*(Et*n1*(Et*n1 + 2) + 2)));
+        sign = -sign;
+    }
+    if (mt.trunc > 5) {
+        if (FERMION) {
+            c0 = -mt.exp_m0*log((1. + exp(-Et))/mt.denom0);
+        } else {
+            c0 = mt.exp_m0*log((1. - exp(-Et))/mt.denom0);
+        }
+    } else {
+        c0 = s0;
+    }
+}
+
 __global__ void build_momentum_table_kernel(double *tab, int n, double e0, double de, double m0,
                                             int trunc, int fermion) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -116,6 +156,9 @@ static int ensure_momentum_tables(iss_handle *h) {
         t.m0 = m0;
         t.e0 = E_min;
         t.de = (E_min + dE) - E_min;    // Etilde_[1] - Etilde_[0]
+        t.exp_m0 = exp(m0);
+        t.denom0 = fermion ? (1. + exp(-m0)) : (1. - exp(-m0));
+        for (int n = 0; n < 10; n++) t.a[n] = exp(-m0*n);
     }
     return ISS_OK;
 }
@@ -204,7 +247,7 @@ struct LaneState {
     int64_t out_slot;
     int s;
     // RNG
-    Stream rng;
+    BlockStream rng;
     // cell
     int64_t cell;
     // |p| sampler set-up (MomentumSamplerBase::Sample_a_momentum)
@@ -240,9 +283,9 @@ __device__ __forceinline__ bool setup_momentum(const SamplerArgs &A, LaneState &
     const MomentumTable &mt = A.mt[tab];
     double c0, c1, c2;
     if (fermion) {
-        cdf_012<true>(a, mt.m0, mt.trunc, c0, c1, c2);
+        cdf_012_lane<true>(mt, a, c0, c1, c2);
     } else {
-        cdf_012<false>(a, mt.m0, mt.trunc, c0, c1, c2);
+        cdf_012_lane<false>(mt, a, c0, c1, c2);
     }
     const double w1 = 2.*mu_tilde;
     const double w0 = mu_tilde*mu_tilde - m_tilde*m_tilde/2.;
@@ -315,8 +358,40 @@ __device__ __forceinline__ int64_t pick_cell(const SamplerArgs &A, int s, double
     return cell;
 }
 
-__global__ void __launch_bounds__(SAMPLER_THREADS)
+// SPEC selects a compile-time specialisation of the run-time mode flags (smaller and faster
+// code for the common configurations); SPEC 0 is the generic kernel that handles every mode.
+//   1: 3+1D, Chapman-Enskog (kind 21) shear + bulk + baryon diffusion, no charge pairing
+//   2: 3+1D, Chapman-Enskog (kind 21) shear + bulk, no diffusion, no charge pairing
+//   3: 3+1D, no delta f, no charge pairing
+template <int SPEC>
+struct SpecMode {
+    static constexpr bool generic = (SPEC == 0);
+    static constexpr int shear = (SPEC == 1 || SPEC == 2) ? 1 : 0;
+    static constexpr int bulk = (SPEC == 1 || SPEC == 2) ? 1 : 0;
+    static constexpr int diff = (SPEC == 1) ? 1 : 0;
+    static constexpr int kind = 21;
+    static constexpr int neos = (SPEC == 3) ? -1 : 1;
+    static constexpr int hydro_mode = 2;
+    static constexpr int lcc = 0;
+};
+
+template <int MIN_BLOCKS, int SPEC>
+__global__ void __launch_bounds__(SAMPLER_THREADS, MIN_BLOCKS)
 sampler_kernel(const SamplerArgs A) {
+    using SM = SpecMode<SPEC>;
+    ModeFlags mode;
+    mode.include_shear = SM::generic ? A.mode.include_shear : SM::shear;
+    mode.include_bulk = SM::generic ? A.mode.include_bulk : SM::bulk;
+    mode.include_diff = SM::generic ? A.mode.include_diff : SM::diff;
+    mode.kind = SM::generic ? A.mode.kind : SM::kind;
+    mode.neos = SM::generic ? A.mode.neos : SM::neos;
+    const int hydro_mode = SM::generic ? A.hydro_mode : SM::hydro_mode;
+    const int lcc = SM::generic ? A.lcc : SM::lcc;
+    const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
+#define ISS_NEXT_BLOCK(L_, w0, w1, w2, w3)                                                     \
+    philox_block((L_).rng.block++, (L_).rng.draw, (L_).rng.event,                              \
+                 (static_cast<uint32_t>(STREAM_SAMPLE) << 24) | static_cast<uint32_t>((L_).s), \
+                 key0, key1, w0, w1, w2, w3)
     extern __shared__ unsigned char smem_raw[];
     DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
     int64_t *sp_off = reinterpret_cast<int64_t *>(sp + A.ns);     // off_work[s*nev], s = 0..ns
@@ -336,7 +411,6 @@ sampler_kernel(const SamplerArgs A) {
     int64_t chunk_next = 0, chunk_end = 0;
     bool more_work = true;
     unsigned long long my_tries = 0, my_redraws = 0, my_range = 0;
-    const ModeFlags mode = A.mode;
 
     for (;;) {
         // -------------------------------------------------------------- refill / emit phase
@@ -370,7 +444,7 @@ sampler_kernel(const SamplerArgs A) {
                 const double pT = sqrt(static_cast<double>(__fadd_rn(__fmul_rn(lab1, lab1),
                                                                      __fmul_rn(lab2, lab2))));
                 const double mT = sqrt(pT*pT + mass*mass);
-                if (A.hydro_mode == 2) {
+                if (hydro_mode == 2) {
                     // eta_s = cell eta: y = asinh(pz/mT) - eta + eta, p_z = mT sinh(y) = pLab[3],
                     // px = pT cos(atan2(py,px)) = pLab[1] up to FP64 rounding; t,z precomputed.
                     const float4 tz = __ldg(cr + 7);    // t, z, spare, spare
@@ -386,7 +460,9 @@ sampler_kernel(const SamplerArgs A) {
                     const double y_minus_eta = asinh(lab3/mT) - pos.w;
                     // the charge-conservation partner keeps the primary's eta_s (FSSW.cpp:1045-1047)
                     if (L.phase == 0) {
-                        const double rap = A.y_LB + (A.y_RB - A.y_LB)*L.rng.next();
+                        uint32_t w0, w1, w2, w3;
+                    ISS_NEXT_BLOCK(L, w0, w1, w2, w3);
+                    const double rap = A.y_LB + (A.y_RB - A.y_LB)*u32(w0);
                         L.eta_s = rap - y_minus_eta;
                     }
                     const double eta_s = L.eta_s;
@@ -410,7 +486,7 @@ sampler_kernel(const SamplerArgs A) {
                     A.trace_tries[L.out_slot] = L.total_tries;
                 }
                 pending = false;
-                if (A.lcc == 1 && L.phase == 0 && p.charge > 0) {
+                if (lcc == 1 && L.phase == 0 && p.charge > 0) {
                     // partner with opposite quantum numbers from the SAME cell (FSSW.cpp:1035-1048)
                     L.phase = 1;
                     L.qsign = -1;
@@ -468,11 +544,10 @@ sampler_kernel(const SamplerArgs A) {
                     const int64_t ev = elo;
                     const int64_t k = w - __ldg(&ow[ev]);
                     const DeviceSpecies p = sp[s];
-                    const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
+                    const int mult = (lcc == 1 && p.charge > 0) ? 2 : 1;
                     L.s = s;
                     L.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k*mult;
-                    L.rng.init(A.seed, STREAM_SAMPLE, s, static_cast<uint32_t>(A.ev_begin + ev),
-                               static_cast<uint32_t>(k));
+                    L.rng.init(static_cast<uint32_t>(A.ev_begin + ev), static_cast<uint32_t>(k));
                     L.phase = 0;
                     L.qsign = 1;
                     L.cell = -1;
@@ -494,7 +569,11 @@ sampler_kernel(const SamplerArgs A) {
                 // (re)draw the cell: first visit, or the reference's "impatience" re-pick
                 // (FSSW.cpp:1017-1018 with status == 0)
                 if (L.cell >= 0) my_redraws++;
-                L.cell = pick_cell(A, L.s, L.rng.next());
+                {
+                    uint32_t w0, w1, w2, w3;
+                    ISS_NEXT_BLOCK(L, w0, w1, w2, w3);
+                    L.cell = pick_cell(A, L.s, u53(w0, w1));
+                }
                 L.tries = 1;
                 const float4 *cr = reinterpret_cast<const float4 *>(A.cells + L.cell*CELL_STRIDE);
                 const float4 da = __ldg(cr + 1);
@@ -522,22 +601,27 @@ sampler_kernel(const SamplerArgs A) {
             const int sign = p.sign;
             const MomentumTable &mt = A.mt[L.tab];
             // |p| proposal (MomentumSamplerBase.cpp:48-56); an inner rejection restarts the try
-            const double r = L.rng.next()*L.cdf_max;
+            uint32_t pw0, pw1, pw2, pw3;
+            ISS_NEXT_BLOCK(L, pw0, pw1, pw2, pw3);
+            const double r = u53(pw0, pw1)*L.cdf_max;
             const double Et = inverse_cdf(mt, L, r);
             const double E_sample = L.T*Et + L.mu;
             const double p_mag = sqrt(E_sample*E_sample - mass*mass);
             const double accept_ratio = (p_mag/E_sample)/(1. - mass*mass/(2.*E_sample*E_sample));
-            const double u_inner = L.rng.next();
+            const double u_inner = u32(pw2);
             if (!(u_inner > accept_ratio)) {
                 my_tries++;
                 L.total_tries++;
                 // FSSW.cpp:1880-1945
-                const double phi = 2*M_PI*L.rng.next();
-                const double cos_theta = 2.*L.rng.next() - 1.;
+                // phi = 2 pi u: sin/cos through sincospi(2u) (no large-argument reduction path)
+                uint32_t qw0, qw1, qw2, qw3;
+                ISS_NEXT_BLOCK(L, qw0, qw1, qw2, qw3);
+                const double u_phi = u32(pw3);
+                const double cos_theta = 2.*u32(qw0) - 1.;
                 const double sin_theta = sqrt(1. - cos_theta*cos_theta);
                 const double pT = p_mag*sin_theta;
                 double sphi, cphi;
-                sincos(phi, &sphi, &cphi);
+                sincospi(2.*u_phi, &sphi, &cphi);
                 const double px = pT*cphi;
                 const double py = pT*sphi;
                 const double p0 = sqrt(mass*mass + p_mag*p_mag);
@@ -545,69 +629,76 @@ sampler_kernel(const SamplerArgs A) {
                 const float4 *cr = reinterpret_cast<const float4 *>(A.cells + L.cell*CELL_STRIDE);
                 const float4 da = __ldg(cr + 1);
                 const double pdsigma = p0*da.x + px*da.y + py*da.z + pz*da.w;
-                const double f0 = 1./(exp((p0 - L.mu)/L.T) + sign);
-                const double stat = 1. - sign*f0;
-                double delta_f = 0.;
-                if (mode.include_shear | mode.include_bulk | mode.include_diff) {
-                    const float4 th0 = __ldg(cr + 3);   // E, T, P, nB
-                    const float4 th = __ldg(cr + 4);    // muB, muS, muQ, bulkPi
-                    const double *__restrict__ co = A.cellcoef + L.cell*COEF_STRIDE;
-                    const int B = L.qsign*p.baryon, S = L.qsign*p.strange, Q = L.qsign*p.charge;
-                    if (mode.include_shear == 1) {
-                        const float4 pa = __ldg(cr + 5);    // pixx, pixy, pixz, piyy
-                        const float4 pb = __ldg(cr + 6);    // piyz, qx, qy, qz
-                        const double Wfactor = (px*px*pa.x + 2.*px*py*pa.y + 2.*px*pz*pa.z
-                                                + py*py*pa.w + 2.*py*pz*pb.x
-                                                + pz*pz*(-pa.x - pa.w));
-                        if (mode.neos == 1) {
-                            delta_f += stat*Wfactor/(2.*__ldg(&co[2]))/(p0*L.T);
-                        } else if (mode.neos == 0) {
-                            delta_f += stat*Wfactor*__ldg(&co[0]);
-                        } else {
-                            const double Tdec = th0.y;
-                            const double pref = 1.0/(2.0*Tdec*Tdec
-                                                     *(static_cast<double>(__fadd_rn(th0.x, th0.z))));
-                            delta_f += stat*Wfactor*pref;
-                        }
-                    }
-                    if (mode.include_bulk == 1) {
-                        // FSSW::get_deltaf_bulk (FSSW.cpp:1795-1849); kinds 0,2,3,4: bulkPi = 0
-                        const double Tdec = th0.y;
-                        if (mode.kind == 21 || mode.kind == 1) {
-                            const double bulkPi = (mode.kind == 21)
-                                                      ? static_cast<double>(th.w)
-                                                      : static_cast<double>(th.w)/HBARC;
-                            const double E_over_T = p0/Tdec;
-                            const double mass_over_T = mass/Tdec;
-                            delta_f += (-1.0*stat*__ldg(&co[0])
-                                        *(mass_over_T*mass_over_T/(3.*E_over_T)
-                                          - __ldg(&co[1])*E_over_T)*bulkPi);
-                        } else if (mode.kind == 11) {
-                            const double bulkPi = th.w;
-                            delta_f += stat*bulkPi*(__ldg(&co[0])*mass*mass + __ldg(&co[1])*B*p0
-                                                    + __ldg(&co[2])*p0*p0);
-                        } else if (mode.kind == 20) {
-                            const double bulkPi = th.w;
-                            delta_f += stat*bulkPi*(mass*mass*__ldg(&co[2])
-                                                    + p0*(B*__ldg(&co[3]) + S*__ldg(&co[4])
-                                                          + Q*__ldg(&co[5]))
-                                                    + p0*p0*(__ldg(&co[1]) - __ldg(&co[2])));
-                        }
-                    }
-                    if (mode.include_diff == 1) {
-                        const float4 pb = __ldg(cr + 6);    // piyz, qx, qy, qz
-                        // float division as in FSSW.cpp:1866
-                        const double prefactor_qmu = __fdiv_rn(th0.w, __fadd_rn(th0.x, th0.z));
-                        const double qmufactor = -px*pb.y - py*pb.z - pz*pb.w;
-                        delta_f += stat*(prefactor_qmu - B/p0)*qmufactor/__ldg(&co[6]);
-                    }
-                }
                 double fact1 = pdsigma/p0/L.dsigma_fac;
-                double fact2 = (1. + delta_f)/2.;
                 fact1 = fmax(0., fmin(1., fact1));
-                fact2 = fmax(0., fmin(1., fact2));
-                const double accept_prob = fact1*fact2;
-                if (L.rng.next() < accept_prob) {
+                // the accept uniform is the next draw of the stream whatever delta f is; since
+                // fact2 <= 1, u >= fact1 already decides "reject" and the delta-f evaluation
+                // (exp, W, coefficients) is skipped
+                const double u_acc = u32(qw1);
+                double accept_prob = 0.;
+                if (u_acc < fact1) {
+                    const double f0 = 1./(exp((p0 - L.mu)/L.T) + sign);
+                    const double stat = 1. - sign*f0;
+                    double delta_f = 0.;
+                    if (mode.include_shear | mode.include_bulk | mode.include_diff) {
+                        const float4 th0 = __ldg(cr + 3);   // E, T, P, nB
+                        const float4 th = __ldg(cr + 4);    // muB, muS, muQ, bulkPi
+                        const double *__restrict__ co = A.cellcoef + L.cell*COEF_STRIDE;
+                        const int B = L.qsign*p.baryon, S = L.qsign*p.strange, Q = L.qsign*p.charge;
+                        if (mode.include_shear == 1) {
+                            const float4 pa = __ldg(cr + 5);    // pixx, pixy, pixz, piyy
+                            const float4 pb = __ldg(cr + 6);    // piyz, qx, qy, qz
+                            const double Wfactor = (px*px*pa.x + 2.*px*py*pa.y + 2.*px*pz*pa.z
+                                                    + py*py*pa.w + 2.*py*pz*pb.x
+                                                    + pz*pz*(-pa.x - pa.w));
+                            if (mode.neos == 1) {
+                                delta_f += stat*Wfactor/(2.*__ldg(&co[2]))/(p0*L.T);
+                            } else if (mode.neos == 0) {
+                                delta_f += stat*Wfactor*__ldg(&co[0]);
+                            } else {
+                                const double Tdec = th0.y;
+                                const double pref = 1.0/(2.0*Tdec*Tdec
+                                                         *(static_cast<double>(__fadd_rn(th0.x, th0.z))));
+                                delta_f += stat*Wfactor*pref;
+                            }
+                        }
+                        if (mode.include_bulk == 1) {
+                            // FSSW::get_deltaf_bulk (FSSW.cpp:1795-1849); kinds 0,2,3,4: bulkPi = 0
+                            const double Tdec = th0.y;
+                            if (mode.kind == 21 || mode.kind == 1) {
+                                const double bulkPi = (mode.kind == 21)
+                                                          ? static_cast<double>(th.w)
+                                                          : static_cast<double>(th.w)/HBARC;
+                                const double E_over_T = p0/Tdec;
+                                const double mass_over_T = mass/Tdec;
+                                delta_f += (-1.0*stat*__ldg(&co[0])
+                                            *(mass_over_T*mass_over_T/(3.*E_over_T)
+                                              - __ldg(&co[1])*E_over_T)*bulkPi);
+                            } else if (mode.kind == 11) {
+                                const double bulkPi = th.w;
+                                delta_f += stat*bulkPi*(__ldg(&co[0])*mass*mass + __ldg(&co[1])*B*p0
+                                                        + __ldg(&co[2])*p0*p0);
+                            } else if (mode.kind == 20) {
+                                const double bulkPi = th.w;
+                                delta_f += stat*bulkPi*(mass*mass*__ldg(&co[2])
+                                                        + p0*(B*__ldg(&co[3]) + S*__ldg(&co[4])
+                                                              + Q*__ldg(&co[5]))
+                                                        + p0*p0*(__ldg(&co[1]) - __ldg(&co[2])));
+                            }
+                        }
+                        if (mode.include_diff == 1) {
+                            const float4 pb = __ldg(cr + 6);    // piyz, qx, qy, qz
+                            // float division as in FSSW.cpp:1866
+                            const double prefactor_qmu = __fdiv_rn(th0.w, __fadd_rn(th0.x, th0.z));
+                            const double qmufactor = -px*pb.y - py*pb.z - pz*pb.w;
+                            delta_f += stat*(prefactor_qmu - B/p0)*qmufactor/__ldg(&co[6]);
+                        }
+                    }
+                    double fact2 = (1. + delta_f)/2.;
+                    fact2 = fmax(0., fmin(1., fact2));
+                    accept_prob = fact1*fact2;
+                }
+                if (u_acc < accept_prob) {
                     acc_p0 = p0;
                     acc_px = px;
                     acc_py = py;
@@ -774,14 +865,46 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     int dev = 0, nsm = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sampler_kernel, SAMPLER_THREADS, smem);
+    // register budget of the persistent kernel: MIN_BLOCKS CTAs of 4 warps per SM
+    // (ISS_SAMPLER_MINB = 4, 5, 6 or 8 selects the variant; for tuning)
+    static int minb = -1;
+    if (minb < 0) {
+        const char *e = getenv("ISS_SAMPLER_MINB");
+        minb = e ? atoi(e) : 6;
+    }
+    int spec = 0;
+    if (A.hydro_mode == 2 && A.lcc != 1) {
+        const bool ce = (A.mode.kind == 21 && A.mode.include_shear == 1 && A.mode.include_bulk == 1);
+        if (ce && A.mode.include_diff == 1) spec = 1;
+        else if (ce && A.mode.include_diff != 1) spec = 2;
+        else if (A.mode.include_shear != 1 && A.mode.include_bulk != 1 && A.mode.include_diff != 1
+                 && A.mode.kind != 20 && A.mode.kind != 21) spec = 3;
+    }
+    static int force_generic = -1;
+    if (force_generic < 0) {
+        const char *e = getenv("ISS_SAMPLER_GENERIC");
+        force_generic = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    if (force_generic) spec = 0;
+    void (*kern)(const SamplerArgs) = sampler_kernel<4, 0>;
+    if (minb == 5) {
+        kern = spec == 1 ? sampler_kernel<5, 1> : spec == 2 ? sampler_kernel<5, 2>
+             : spec == 3 ? sampler_kernel<5, 3> : sampler_kernel<5, 0>;
+    } else if (minb == 6) {
+        kern = spec == 1 ? sampler_kernel<6, 1> : spec == 2 ? sampler_kernel<6, 2>
+             : spec == 3 ? sampler_kernel<6, 3> : sampler_kernel<6, 0>;
+    } else {
+        kern = spec == 1 ? sampler_kernel<4, 1> : spec == 2 ? sampler_kernel<4, 2>
+             : spec == 3 ? sampler_kernel<4, 3> : sampler_kernel<4, 0>;
+    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SAMPLER_THREADS, smem);
     if (occ < 1) occ = 1;
     int64_t grid = static_cast<int64_t>(nsm)*occ;
     const int64_t max_useful = (total_work + 31)/32/(SAMPLER_THREADS/32) + 1;
     if (grid > max_useful) grid = max_useful;
     {
         ScopedTimer t(h, ISS_T_SAMPLE);
-        sampler_kernel<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(A); ISS_LAUNCHED(h);
+        kern<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     return ISS_OK;

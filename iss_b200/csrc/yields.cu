@@ -26,20 +26,36 @@ struct YieldArgs {
     ModeFlags mode;
     double *yields;         // [ns][ncell_pad]
     double *cellcoef;       // [ncell][COEF_STRIDE] by-product for the sampler
+    const double *sf4;      // [n][4] K1, K2, K3, weighted sum of E_2..E_18
+    const int4 *combos;     // [ncombo] distinct (B, S, Q) of the species list
+    int ncombo;
 };
 
 constexpr int YIELD_THREADS = 128;
 constexpr int YIELD_SPECIES_SMEM = 512;
 
-__device__ __forceinline__ double lerp_tab(const double *__restrict__ tb, int stride, int col,
-                                           int idx, double frac) {
-    return (1. - frac)*__ldg(&tb[static_cast<size_t>(idx)*stride + col])
-           + frac*__ldg(&tb[static_cast<size_t>(idx + 1)*stride + col]);
+// I_1 weights of E_2, E_4, ..., E_18 (FSSW.cpp:787-806): 3/8, then 3 (2k-5)!!/(2^k k!), k = 3..10
+__host__ __device__ inline void expint_weights(double w[9]) {
+    w[0] = 3./8.;
+    double double_factorial = 1., factorial = 2., two_k = 4.;
+    for (int k = 3; k <= 10; k++) {
+        double_factorial *= (2*k - 5);
+        factorial *= k;
+        two_k *= 2;
+        w[k - 2] = 3.*double_factorial/two_k/factorial;
+    }
 }
 
+// One thread per cell, species loop.  Per cell (hoisted out of the species loop, the reference
+// recomputes them per species): delta-f coefficients and the fugacities exp(mu/T) of the distinct
+// (B,S,Q) combinations of the list (~30 instead of one exp per species), kept in shared memory.
+// Per term of the series one pair of 32-byte table records {K1,K2,K3,I} is read: the nine E_2k
+// look-ups of the diffusion term are one look-up of their pre-combined weighted sum (a lerp is
+// linear, so lerp-then-combine == combine-then-lerp up to rounding).
 __global__ void __launch_bounds__(YIELD_THREADS)
 yields_kernel(const YieldArgs a) {
     __shared__ DeviceSpecies sp[YIELD_SPECIES_SMEM];
+    extern __shared__ double lam_smem[];        // [ncombo][YIELD_THREADS]
     const int s_begin = blockIdx.y*a.species_per_block;
     const int s_end = min(a.ns, s_begin + a.species_per_block);
     for (int i = threadIdx.x; i < s_end - s_begin; i += blockDim.x) sp[i] = a.species[s_begin + i];
@@ -90,117 +106,114 @@ yields_kernel(const YieldArgs a) {
 #undef FLD
 
     const double beta = 1./temp;
+    // fugacity of every distinct (B,S,Q): mu in float arithmetic as FSSW.cpp:650
+    for (int c = 0; c < a.ncombo; c++) {
+        const int4 q = a.combos[c];
+        const float muf = __fadd_rn(__fadd_rn(__fmul_rn(static_cast<float>(q.x), muBf),
+                                              __fmul_rn(static_cast<float>(q.y), muSf)),
+                                    __fmul_rn(static_cast<float>(q.z), muQf));
+        lam_smem[c*YIELD_THREADS + threadIdx.x] = exp(beta*static_cast<double>(muf));
+    }
+
     const double unit_factor = 1.0/(HBARC*HBARC*HBARC);
     const bool hot = temp > 0.05;
     const bool bulk_ce = (m.include_bulk == 1) && (m.kind == 1 || m.kind == 21);
     const bool bulk_mom = (m.include_bulk == 1) && (m.kind == 11 || m.kind == 20);
+    const bool with_diff = (m.include_diff == 1);
     const SfGrid sf = a.tab.sf;
+    const double inv_dx = 1.0/sf.dx;
+    const double2 *__restrict__ sf2 = reinterpret_cast<const double2 *>(a.sf4);
+    const double common = unit_factor/(2.*M_PI*M_PI);
 
     for (int is = 0; is < s_end - s_begin; is++) {
         const DeviceSpecies p = sp[is];
         const double mass = p.mass;
-        // mu: float arithmetic, FSSW.cpp:650
-        const float muf = __fadd_rn(__fadd_rn(__fmul_rn(static_cast<float>(p.baryon), muBf),
-                                              __fmul_rn(static_cast<float>(p.strange), muSf)),
-                                    __fmul_rn(static_cast<float>(p.charge), muQf));
-        const double mu = muf;
-        const double lambda = exp(beta*mu);
+        const double lambda = lam_smem[p.combo*YIELD_THREADS + threadIdx.x];
         const int truncate_order = (p.trunc10_mass && hot) ? 10 : 1;
         const double mbeta = mass*beta;
 
-        double N_eq = 0., b1 = 0., b2 = 0., b3 = 0., q1 = 0., q2 = 0.;
+        double N_eq = 0., b1 = 0., b2 = 0., b3 = 0., q2 = 0.;
         double theta = 1.0, fugacity = 1.0;
         for (int n = 1; n <= truncate_order; n++) {
             const double arg = n*mass*beta;
             if (n > 1) theta *= -static_cast<double>(p.sign);
             fugacity *= lambda;
-            double K_1 = 0., K_2, K_3 = 0.;
-            const bool in_tab = sf_in_table(sf, arg);
-            int idx = 0;
-            double frac = 0.;
-            if (in_tab) {
-                sf_index(sf, arg, idx, frac);
-                K_2 = lerp_tab(a.tab.bessel, 3, 1, idx, frac);
-                if (m.include_bulk == 1) {
-                    K_1 = lerp_tab(a.tab.bessel, 3, 0, idx, frac);
-                    if (bulk_mom) K_3 = lerp_tab(a.tab.bessel, 3, 2, idx, frac);
-                }
+            double K_1, K_2, K_3, I_tab;
+            if (sf_in_table(sf, arg)) {
+                // idx = int((arg - x_min)/dx), frac = remainder/dx (FSSW.cpp:1666-1683); the
+                // division by dx is a multiplication here: the lerp is continuous in arg, so a
+                // last-bit difference of idx/frac changes the result by ~1e-15 relative
+                const double t = (arg - sf.x_min)*inv_dx;
+                const int idx = static_cast<int>(t);
+                const double frac = t - idx;
+                // records idx and idx+1 are adjacent: four 16-byte loads of one 64-byte span
+                const double2 k12a = __ldg(sf2 + 2*idx), k3ia = __ldg(sf2 + 2*idx + 1);
+                const double2 k12b = __ldg(sf2 + 2*idx + 2), k3ib = __ldg(sf2 + 2*idx + 3);
+                const double omf = 1. - frac;
+                K_1 = omf*k12a.x + frac*k12b.x;
+                K_2 = omf*k12a.y + frac*k12b.y;
+                K_3 = omf*k3ia.x + frac*k3ib.x;
+                I_tab = omf*k3ia.y + frac*k3ib.y;
             } else {
                 bessel_k123(arg, K_1, K_2, K_3);
-            }
-            N_eq += theta/n*fugacity*K_2;
-            if (bulk_ce) {
-                b1 += theta*fugacity*(mbeta*K_1 + 3*K_2/n);
-                b2 += theta*fugacity*K_1;
-            } else if (bulk_mom) {
-                b1 += theta*fugacity*K_2;
-                b2 += theta*fugacity*(mbeta*K_1 + 3*K_2/n);
-                b3 += theta*fugacity*(mbeta*K_2 + 3*K_3/n);
-            }
-            if (m.include_diff == 1) {
-                q1 += theta/n*fugacity*K_2;
-                // FSSW.cpp:784-808
-                double En[9];
-                if (in_tab) {
-#pragma unroll
-                    for (int i = 0; i < 9; i++) En[i] = lerp_tab(a.tab.expint, 9, i, idx, frac);
-                } else {
+                I_tab = 0.;
+                if (with_diff) {
+                    double w[9];
+                    expint_weights(w);
 #pragma unroll 1
-                    for (int i = 0; i < 9; i++) En[i] = expint_en(2*i + 2, arg);
+                    for (int i = 0; i < 9; i++) I_tab += w[i]*expint_en(2*i + 2, arg);
                 }
-                double I_1_n = exp(-arg)/arg*(2./(arg*arg) + 2./arg - 1./2.) + 3./8.*En[0];
-                double double_factorial = 1., factorial = 2., two_k = 4.;
-#pragma unroll
-                for (int k = 3; k <= 10; k++) {
-                    double_factorial *= (2*k - 5);
-                    factorial *= k;
-                    two_k *= 2;
-                    I_1_n += 3.*double_factorial/two_k/factorial*En[k - 2];
-                }
-                I_1_n = -(mbeta*mbeta*mbeta)*I_1_n;
-                q2 += n*theta*fugacity*I_1_n;
+            }
+            const double tf = theta*fugacity;
+            const double inv_n = 1.0/n;
+            N_eq += tf*inv_n*K_2;
+            if (bulk_ce) {
+                b1 += tf*(mbeta*K_1 + 3*K_2*inv_n);
+                b2 += tf*K_1;
+            } else if (bulk_mom) {
+                b1 += tf*K_2;
+                b2 += tf*(mbeta*K_1 + 3*K_2*inv_n);
+                b3 += tf*(mbeta*K_2 + 3*K_3*inv_n);
+            }
+            if (with_diff) {
+                // FSSW.cpp:784-808
+                const double ra = 1.0/arg;
+                const double I_1_n = exp(-arg)*ra*(2.*ra*ra + 2.*ra - 0.5) + I_tab;
+                q2 += n*tf*(-(mbeta*mbeta*mbeta)*I_1_n);
             }
         }
-        // FSSW.cpp:812-847
+        // FSSW.cpp:812-847; the equilibrium series doubles as the first diffusion term
+        const double q1 = mass*mass/(beta*beta)*N_eq;
         N_eq = mass*mass*temp*N_eq;
         if (bulk_ce) {
             b1 = mass*mass/beta*b1;
             b2 = mass*mass*mass/3.*b2;
-            b3 = 0.0;
         } else if (bulk_mom) {
             b1 = mass*mass/beta*b1;
             b2 = mass*mass/(beta*beta)*b2;
             b3 = mass*mass*mass/(beta*beta)*b3;
         }
-        if (m.include_diff == 1) {
-            q1 = mass*mass/(beta*beta)*q1;
-            q2 = 1./(3.*beta*beta*beta)*q2;
-        }
 
         // FSSW.cpp:656-706
-        const double prefactor = p.gspin/(2.*M_PI*M_PI);
-        const double Neq = unit_factor*prefactor*dsigma_dot_u*N_eq;
-        double dN_bulk = 0.0;
+        const double pref = common*p.gspin;
+        double total = pref*dsigma_dot_u*N_eq;
         if (m.include_bulk == 1) {
-            if (m.kind == 1 || m.kind == 21) {
-                dN_bulk = unit_factor*prefactor*dsigma_dot_u*(-bulkPi*cc.c[0])
-                          *(-cc.c[1]*b1 + b2);
+            if (bulk_ce) {
+                total += pref*dsigma_dot_u*(-bulkPi*cc.c[0])*(-cc.c[1]*b1 + b2);
             } else if (m.kind == 11) {
-                dN_bulk = unit_factor*prefactor*dsigma_dot_u*bulkPi
-                          *(b1*mass*mass*cc.c[0] + b2*p.baryon*cc.c[1] + b3*cc.c[2]);
+                total += pref*dsigma_dot_u*bulkPi
+                         *(b1*mass*mass*cc.c[0] + b2*p.baryon*cc.c[1] + b3*cc.c[2]);
             } else if (m.kind == 20) {
-                dN_bulk = unit_factor*prefactor*dsigma_dot_u*bulkPi
-                          *(b1*mass*mass*cc.c[2]
-                            + b2*(p.baryon*cc.c[3] + p.strange*cc.c[4] + p.charge*cc.c[5])
-                            + b3*(cc.c[1] - cc.c[2]));
+                total += pref*dsigma_dot_u*bulkPi
+                         *(b1*mass*mass*cc.c[2]
+                           + b2*(p.baryon*cc.c[3] + p.strange*cc.c[4] + p.charge*cc.c[5])
+                           + b3*(cc.c[1] - cc.c[2]));
             }
         }
-        double dN_q = 0.0;
-        if (m.include_diff == 1) {
-            dN_q = unit_factor*prefactor*dsigma_dot_q/cc.kappa
-                   *(-prefactor_qmu*q1 - p.baryon*q2);
+        if (with_diff) {
+            total += pref*dsigma_dot_q/cc.kappa
+                     *(-prefactor_qmu*q1 - p.baryon*(1./(3.*beta*beta*beta)*q2));
         }
-        const double total = Neq + dN_bulk + dN_q;
         a.yields[static_cast<int64_t>(s_begin + is)*np + cell] = fmax(0., total);
     }
 }
@@ -287,23 +300,49 @@ __global__ void build_sf_tables_kernel(double *bessel, double *expint, SfGrid g,
     }
 }
 
+// {K1, K2, K3, sum_k w_k E_2k} records the yield kernel reads
+__global__ void pack_sf4_kernel(const double *__restrict__ bessel, const double *__restrict__ expint,
+                                int n, double *__restrict__ sf4) {
+    const int i = blockIdx.x*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double w[9];
+    expint_weights(w);
+    double acc = 0.;
+    if (expint)
+        for (int k = 0; k < 9; k++) acc += w[k]*expint[i*9 + k];
+    sf4[i*4 + 0] = bessel[i*3 + 0];
+    sf4[i*4 + 1] = bessel[i*3 + 1];
+    sf4[i*4 + 2] = bessel[i*3 + 2];
+    sf4[i*4 + 3] = acc;
+}
+
 static int ensure_sf_tables(iss_handle *h) {
     const bool need_diff = h->opt.include_deltaf_diffusion == 1;
-    if (h->d_bessel && (!need_diff || h->d_expint)) return ISS_OK;
-    // FSSW.cpp:1611-1615
-    const double sf_x_min = 0.5, sf_x_max = 400, sf_dx = 0.05;
-    SfGrid g;
-    g.x_min = sf_x_min;
-    g.dx = sf_dx;
-    g.x_max_minus_dx = sf_x_max - sf_dx;
-    g.n = static_cast<int>((sf_x_max - sf_x_min)/sf_dx) + 1;
-    if (!h->d_bessel) ISS_CUDA_TRY(h, cudaMalloc(&h->d_bessel, sizeof(double)*3*g.n));
-    if (need_diff && !h->d_expint)
-        ISS_CUDA_TRY(h, cudaMalloc(&h->d_expint, sizeof(double)*9*g.n));
-    h->sf = g;
-    build_sf_tables_kernel<<<(g.n + 127)/128, 128, 0, h->stream>>>(
-        h->d_bessel, h->d_expint, g, 1, need_diff ? 1 : 0); ISS_LAUNCHED(h);
+    if (h->d_bessel && (!need_diff || h->d_expint) && h->d_sf4 && h->sf4_with_diff == need_diff)
+        return ISS_OK;
+    if (!h->d_bessel || (need_diff && !h->d_expint)) {
+        // FSSW.cpp:1611-1615
+        const double sf_x_min = 0.5, sf_x_max = 400, sf_dx = 0.05;
+        SfGrid g;
+        g.x_min = sf_x_min;
+        g.dx = sf_dx;
+        g.x_max_minus_dx = sf_x_max - sf_dx;
+        g.n = static_cast<int>((sf_x_max - sf_x_min)/sf_dx) + 1;
+        if (!h->d_bessel) ISS_CUDA_TRY(h, cudaMalloc(&h->d_bessel, sizeof(double)*3*g.n));
+        if (need_diff && !h->d_expint)
+            ISS_CUDA_TRY(h, cudaMalloc(&h->d_expint, sizeof(double)*9*g.n));
+        h->sf = g;
+        build_sf_tables_kernel<<<(g.n + 127)/128, 128, 0, h->stream>>>(
+            h->d_bessel, h->d_expint, g, 1, need_diff ? 1 : 0); ISS_LAUNCHED(h);
+        ISS_CUDA_TRY(h, cudaGetLastError());
+    }
+    if (h->d_sf4) cudaFree(h->d_sf4);
+    h->d_sf4 = nullptr;
+    ISS_CUDA_TRY(h, cudaMalloc(&h->d_sf4, sizeof(double)*4*(h->sf.n + 1)));
+    pack_sf4_kernel<<<(h->sf.n + 127)/128, 128, 0, h->stream>>>(
+        h->d_bessel, need_diff ? h->d_expint : nullptr, h->sf.n, h->d_sf4); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
+    h->sf4_with_diff = need_diff;
     return ISS_OK;
 }
 
@@ -356,6 +395,9 @@ int run_yields(iss_handle *h) {
     a.mode = mode;
     a.yields = h->d_yields;
     a.cellcoef = h->d_cellcoef;
+    a.sf4 = h->d_sf4;
+    a.combos = h->d_combos;
+    a.ncombo = h->ncombo;
 
     const int64_t nblk_x = (h->ncell + YIELD_THREADS - 1)/YIELD_THREADS;
     // enough CTAs to fill 148 SMs several times over, without recomputing the
@@ -371,7 +413,11 @@ int run_yields(iss_handle *h) {
     {
         ScopedTimer t(h, ISS_T_YIELDS);
         dim3 grid(static_cast<unsigned>(nblk_x), chunks);
-        yields_kernel<<<grid, YIELD_THREADS, 0, h->stream>>>(a); ISS_LAUNCHED(h);
+        const size_t smem = sizeof(double)*YIELD_THREADS*h->ncombo;
+        if (smem + sizeof(DeviceSpecies)*YIELD_SPECIES_SMEM > 48*1024)
+            cudaFuncSetAttribute(yields_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem));
+        yields_kernel<<<grid, YIELD_THREADS, smem, h->stream>>>(a); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     {

@@ -80,7 +80,7 @@ static void philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
 
 typedef struct {
     uint32_t ctr[4], key[2], buf[4];
-    int have;
+    int pos;
 } o_stream;
 
 enum { STREAM_MULT = 1, STREAM_SAMPLE = 2, STREAM_DECAY = 3 };
@@ -93,22 +93,42 @@ static void stream_init(o_stream *s, uint64_t seed, uint32_t stream, uint32_t sp
     s->ctr[1] = draw;
     s->ctr[2] = event;
     s->ctr[3] = (stream << 24) | (species & 0xFFFFFFu);
-    s->have = 0;
+    s->pos = 4;
 }
 
-/* 53-bit uniform in [0,1): 27 high bits of word a, 26 high bits of word b */
-static double stream_next(o_stream *s) {
-    if (s->have == 0) {
+/* the four words of each Philox block are consumed in order */
+static uint32_t stream_word(o_stream *s) {
+    if (s->pos == 4) {
         philox(s->ctr, s->key, s->buf);
         s->ctr[0]++;
-        s->have = 2;
+        s->pos = 0;
     }
-    const uint32_t a = (s->have == 2) ? s->buf[0] : s->buf[2];
-    const uint32_t b = (s->have == 2) ? s->buf[1] : s->buf[3];
-    s->have--;
+    return s->buf[s->pos++];
+}
+
+/* 53-bit uniform in [0,1) from two words: 27 high bits of the first, 26 high bits of the second */
+static double stream_next(o_stream *s) {
+    const uint32_t a = stream_word(s);
+    const uint32_t b = stream_word(s);
     const uint64_t v = ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6);
     return (double)v*(1.0/9007199254740992.0);
 }
+
+/* Block-granular use of the sampling streams (engine design, DESIGN.md "Random numbers"): every
+ * decision point consumes one whole Philox block; unused words are discarded.
+ *   cell choice       (w0,w1) -> 53-bit uniform
+ *   |p| proposal      (w0,w1) -> r (53 bit), w2 -> inner accept (32 bit), w3 -> phi (32 bit)
+ *   direction/accept  w0 -> cos(theta) (32 bit), w1 -> accept (32 bit)   [after the inner accept]
+ *   rapidity          w0 -> y (32 bit)                                   [boost-invariant]      */
+static void stream_block(o_stream *s, uint32_t w[4]) {
+    philox(s->ctr, s->key, w);
+    s->ctr[0]++;
+}
+static double w53(uint32_t a, uint32_t b) {
+    const uint64_t v = ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6);
+    return (double)v*(1.0/9007199254740992.0);
+}
+static double w32(uint32_t x) { return ((double)x + 0.5)*(1.0/4294967296.0); }
 
 void oracle_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { philox(ctr, key, out); }
 
@@ -306,16 +326,20 @@ static double inverse_cdf(const o_psetup *q, double r) {
     return E0 + (q->t->E[hi] - E0)/fmax(1e-16, r_max - r_min)*(r - r_min);
 }
 
-/* MomentumSamplerBase::Sample_a_momentum's do-while, uniforms from the stream */
-static double sample_p(const o_psetup *q, double m, o_stream *rng) {
+/* MomentumSamplerBase::Sample_a_momentum's do-while; one block per iteration.  The last word of
+ * the accepted iteration's block is returned for the azimuth. */
+static double sample_p(const o_psetup *q, double m, o_stream *rng, uint32_t *phi_word) {
     double p, E, ratio;
+    uint32_t w[4];
     do {
-        const double r = stream_next(rng)*q->cdf_max;
+        stream_block(rng, w);
+        const double r = w53(w[0], w[1])*q->cdf_max;
         const double Et = inverse_cdf(q, r);
         E = q->T*Et + q->mu;
         p = sqrt(E*E - m*m);
         ratio = (p/E)/(1. - m*m/(2.*E*E));
-    } while (stream_next(rng) > ratio);
+    } while (w32(w[2]) > ratio);
+    *phi_word = w[3];
     return p;
 }
 
@@ -328,7 +352,8 @@ int oracle_sample_momentum(double m, double T, double mu, int sign, int64_t n, u
     for (int64_t i = 0; i < n; i++) {
         o_stream rng;
         stream_init(&rng, seed, STREAM_SAMPLE, 0, (uint32_t)(i >> 20), (uint32_t)(i & 0xFFFFF));
-        out[i] = sample_p(&q, m, &rng);
+        uint32_t unused;
+        out[i] = sample_p(&q, m, &rng, &unused);
     }
     return 0;
 }
@@ -364,10 +389,12 @@ static int sample_in_cell(const float *c, const double *coef, const o_options *o
     if (!psetup(&q, mass, Tdec, mu, sign)) { *range_error = 1; return 0; }
     int tries = 1;
     while (tries < 5000) {
-        const double p_mag = sample_p(&q, mass, rng);
+        uint32_t phi_word, w[4];
+        const double p_mag = sample_p(&q, mass, rng, &phi_word);
         (*ntries)++;
-        const double phi_c = 2*M_PI*stream_next(rng);
-        const double cos_theta = 2.*stream_next(rng) - 1.;
+        stream_block(rng, w);
+        const double phi_c = 2*M_PI*w32(phi_word);
+        const double cos_theta = 2.*w32(w[0]) - 1.;
         const double sin_theta = sqrt(1. - cos_theta*cos_theta);
         const double pT_c = p_mag*sin_theta;
         const double px = pT_c*cos(phi_c), py = pT_c*sin(phi_c);
@@ -409,7 +436,7 @@ static int sample_in_cell(const float *c, const double *coef, const o_options *o
         }
         const double fact1 = clip01(pdsigma/p0/dsigma_fac);
         const double fact2 = clip01((1. + d_shear + d_bulk + d_q)/2.);
-        if (stream_next(rng) < fact1*fact2) {
+        if (w32(w[1]) < fact1*fact2) {
             const float pl[4] = {(float)p0, (float)px, (float)py, (float)pz};
             const float *u = c + F_UT;
             double pdu = 0.;
@@ -448,8 +475,10 @@ static void emit(o_hadron *h, int pid, double mass, const float *c, double pT, d
 /*
  * The event/species/particle loops of FSSW::sample_using_dN_dxtdy_4all_particles_conventional
  * (src/FSSW.cpp:920-1050) with the engine's stream keying: hadron k of species s in event ev draws
- * from stream (seed; SAMPLE, s, ev, k) in the order
- *    cell | per try: (r, inner accept)+ , phi, cos(theta), accept | after 4999 rejections: new cell
+ * from stream (seed; SAMPLE, s, ev, k) in the order (53 = 53-bit uniform from two Philox words,
+ * 32 = 32-bit uniform from one word)
+ *    cell | per try: (proposal block)+ , direction/accept block | after 4999 rejections: new cell
+ *    (one Philox block per decision point, see stream_block above)
  *    | boost-invariant: rapidity | charge-conservation partner: tries in the same cell, same eta_s.
  * Output: event-major, species in sampling order inside an event (as Hadron_list), draw order.
  * yields: [ns][ncell] (cell CDF = sequential exclusive prefix, RandomVariable1DArray.cpp:38-50).
@@ -480,7 +509,9 @@ int64_t oracle_sample(const float *cells, int64_t ncell, const double *coef /*[n
                 double pT, phi, yme;
                 int64_t cell;
                 for (;;) {
-                    cell = pick_cell(cdf + (size_t)s*(ncell + 1), ncell, stream_next(&rng));
+                    uint32_t w[4];
+                    stream_block(&rng, w);
+                    cell = pick_cell(cdf + (size_t)s*(ncell + 1), ncell, w53(w[0], w[1]));
                     if (sample_in_cell(cells + cell*NFIELD, coef + cell*7, o, p->mass, p->sign,
                                        p->baryon, p->strange, p->charge, &rng, &ntries, &pT, &phi,
                                        &yme, &range_error))
@@ -491,7 +522,9 @@ int64_t oracle_sample(const float *cells, int64_t ncell, const double *coef /*[n
                 const float *c = cells + cell*NFIELD;
                 double eta_s = c[F_ETA];
                 if (o->hydro_mode != 2) {
-                    const double rap = o->y_LB + (o->y_RB - o->y_LB)*stream_next(&rng);
+                    uint32_t w[4];
+                    stream_block(&rng, w);
+                    const double rap = o->y_LB + (o->y_RB - o->y_LB)*w32(w[0]);
                     eta_s = rap - yme;
                 }
                 if (n >= cap) { free(cdf); return -1; }
