@@ -252,9 +252,14 @@ decay_kernel(const DecayArgs A) {
 
 __global__ void gather_event_offsets_kernel(const int64_t *__restrict__ off_primary,
                                             const int64_t *__restrict__ event_off_in, int64_t nev,
-                                            int64_t *__restrict__ event_off_out) {
+                                            int64_t *__restrict__ event_off_out,
+                                            int64_t *__restrict__ event_off_host /* mapped */) {
     const int64_t ev = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
-    if (ev <= nev) event_off_out[ev] = off_primary[event_off_in[ev]];
+    if (ev <= nev) {
+        const int64_t v = off_primary[event_off_in[ev]];
+        event_off_out[ev] = v;
+        event_off_host[ev] = v;
+    }
 }
 
 int run_decay(iss_handle *h, uint64_t seed) {
@@ -307,15 +312,18 @@ int run_decay(iss_handle *h, uint64_t seed) {
         // new per-event offsets (into a scratch area behind the counts, then copied over)
         int64_t *tmp = h->d_decay_cnt + n_in + 1;
         gather_event_offsets_kernel<<<static_cast<unsigned>((nev + 1 + 255)/256), 256, 0,
-                                      h->stream>>>(h->d_decay_cnt, h->d_event_off, nev, tmp); ISS_LAUNCHED(h);
+                                      h->stream>>>(h->d_decay_cnt, h->d_event_off, nev, tmp,
+                                                    h->d_evoff_mapped); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
         ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_event_off, tmp, sizeof(int64_t)*(nev + 1),
                                         cudaMemcpyDeviceToDevice, h->stream));
     }
     unsigned long long err[2] = {0, 0};
-    ISS_CUDA_TRY(h, cudaMemcpyAsync(err, h->d_counters + 4, sizeof(err), cudaMemcpyDeviceToHost,
-                                    h->stream));
+    rc = mail_post(h, h->d_counters + 4, 2, 16);
+    if (rc) return rc;
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    err[0] = *reinterpret_cast<volatile unsigned long long *>(h->h_mail + 16);
+    err[1] = *reinterpret_cast<volatile unsigned long long *>(h->h_mail + 17);
     h->n_hadrons = total;
     h->decayed = true;
     if (err[0] || err[1]) {

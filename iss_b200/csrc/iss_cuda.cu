@@ -155,6 +155,8 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_hadbuf[0]); cudaFree(h->d_hadbuf[1]); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
     cudaFree(h->d_qa); cudaFree(h->d_trace);
+    if (h->h_mail) cudaFreeHost(h->h_mail);
+    if (h->h_evoff) cudaFreeHost(h->h_evoff);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : h->ev_pool) cudaEventDestroy(e);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -370,6 +372,7 @@ int iss_cuda_set_options(iss_handle *h, const iss_options *opt) {
     const bool changed = !h->have_opt || memcmp(&h->opt, opt, sizeof(*opt)) != 0;
     h->opt = *opt;
     h->have_opt = true;
+    h->lambda_on_device = false;
     if (changed) {
         h->have_yields = false;
         // K/E tables depend on include_deltaf_diffusion: rebuild lazily
@@ -409,9 +412,10 @@ int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_e
     rc = run_sampler(h, seed, nev, 0);
     if (rc) return rc;
     unsigned long long cnt[8] = {0};
-    ISS_CUDA_TRY(h, cudaMemcpyAsync(cnt, h->d_counters, sizeof(cnt), cudaMemcpyDeviceToHost,
-                                    h->stream));
+    rc = mail_post(h, h->d_counters, 8, 0);
+    if (rc) return rc;
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 8; i++) cnt[i] = *reinterpret_cast<volatile unsigned long long *>(h->h_mail + i);
     h->have_batch = true;
     if (out) {
         out->n_events = nev;
@@ -485,9 +489,9 @@ int iss_cuda_event_offsets(iss_handle *h, int64_t *event_offsets_host) {
     if (!h || !event_offsets_host) return ISS_ERR_ARG;
     if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
     const int64_t nev = h->ev_end - h->ev_begin;
-    ISS_CUDA_TRY(h, cudaMemcpyAsync(event_offsets_host, h->d_event_off, sizeof(int64_t)*(nev + 1),
-                                    cudaMemcpyDeviceToHost, h->stream));
-    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    // the kernels that produce the offsets also wrote them to mapped pinned memory, and the
+    // batch was synchronised when iss_cuda_sample / iss_cuda_decay returned
+    memcpy(event_offsets_host, h->h_evoff, sizeof(int64_t)*(nev + 1));
     return ISS_OK;
 }
 

@@ -16,6 +16,7 @@ namespace iss {
 constexpr double HBARC = 0.197327053;     // reference data_struct.h:9
 constexpr int TILE = 1024;                // cells per CDF tile (scan granularity)
 constexpr int MAX_SPECIES = 1024;
+constexpr int MAIL_WORDS = 64;          // [0..7] sampler counters, [8] scan total, [16..] spare
 
 // special-function table grid (FSSW.cpp:1611-1615)
 struct SfGrid {
@@ -111,6 +112,7 @@ struct iss_handle {
     std::vector<double> h_total;        // dN per species (3+1D sum)
     std::vector<double> h_lambda, h_pmode;
     double *d_lambda = nullptr, *d_pmode = nullptr;
+    bool lambda_on_device = false;      // reset whenever yields or options change
 
     // sampling batch
     int64_t ev_begin = 0, ev_end = 0;
@@ -146,6 +148,14 @@ struct iss_handle {
     int64_t *d_decay_cnt = nullptr;     // per-primary final multiplicity / offsets
     int64_t decay_cnt_cap = 0;
     void *d_scan_tmp = nullptr; size_t scan_tmp_bytes = 0;
+
+    // mailbox: a page of mapped pinned host memory that tiny kernels write scalars into (scan
+    // totals, counters), so that no small device->host copy has to queue on the copy engine
+    // behind a multi-hundred-MB hadron transfer
+    unsigned long long *h_mail = nullptr;       // host view  [ISS_MAIL_WORDS]
+    unsigned long long *d_mail = nullptr;       // device view of the same page
+    int64_t *h_evoff = nullptr, *d_evoff_mapped = nullptr;   // mapped copy of the event offsets
+    int64_t evoff_mapped_cap = 0;
 
     // QA
     double *d_qa = nullptr;
@@ -212,6 +222,10 @@ struct ScopedTimer {
         }
     }
 };
+
+// copies n 64-bit words device -> mailbox[slot..] with a one-warp kernel (no copy engine)
+int mail_post(iss_handle *h, const void *d_src, int n, int slot);
+int ensure_mapped_event_offsets(iss_handle *h, int64_t n);
 
 // exclusive scan of int64 on the handle's stream (own kernels, see scan.cu)
 int device_exclusive_scan_i64(iss_handle *h, const int64_t *d_in, int64_t *d_out, int64_t n,

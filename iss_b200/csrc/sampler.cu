@@ -205,9 +205,14 @@ __global__ void multiplicity_kernel(const double *__restrict__ lambda,
 
 // per-event offsets = off_out[ev*ns]
 __global__ void event_offset_kernel(const int64_t *__restrict__ off_out, int ns, int64_t nev,
-                                    int64_t *__restrict__ event_off) {
+                                    int64_t *__restrict__ event_off,
+                                    int64_t *__restrict__ event_off_host /* mapped pinned */) {
     const int64_t ev = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
-    if (ev <= nev) event_off[ev] = off_out[ev*ns];
+    if (ev <= nev) {
+        const int64_t v = off_out[ev*ns];
+        event_off[ev] = v;
+        event_off_host[ev] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -766,10 +771,14 @@ int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev) {
         ISS_CUDA_TRY(h, cudaMalloc(&h->d_lambda, sizeof(double)*MAX_SPECIES));
         ISS_CUDA_TRY(h, cudaMalloc(&h->d_pmode, sizeof(double)*MAX_SPECIES));
     }
-    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_lambda, h->h_lambda.data(), sizeof(double)*ns,
-                                    cudaMemcpyHostToDevice, h->stream));
-    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_pmode, h->h_pmode.data(), sizeof(double)*ns,
-                                    cudaMemcpyHostToDevice, h->stream));
+    if (!h->lambda_on_device) {
+        ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_lambda, h->h_lambda.data(), sizeof(double)*ns,
+                                        cudaMemcpyHostToDevice, h->stream));
+        ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_pmode, h->h_pmode.data(), sizeof(double)*ns,
+                                        cudaMemcpyHostToDevice, h->stream));
+        // the host vectors are pageable: the copies are complete when the calls return
+        h->lambda_on_device = true;
+    }
 
     ScopedTimer t(h, ISS_T_MULT);
     // out_count -> d_off_out (scanned in place), work_count -> d_off_work (in place)
@@ -795,8 +804,10 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         if (rc) return rc;
         rc = device_exclusive_scan_i64(h, h->d_off_work, h->d_off_work, n, &total_work);
         if (rc) return rc;
+        rc = ensure_mapped_event_offsets(h, nev + 1);
+        if (rc) return rc;
         event_offset_kernel<<<static_cast<unsigned>((nev + 1 + 255)/256), 256, 0, h->stream>>>(
-            h->d_off_out, ns, nev, h->d_event_off); ISS_LAUNCHED(h);
+            h->d_off_out, ns, nev, h->d_event_off, h->d_evoff_mapped); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
     }
     {

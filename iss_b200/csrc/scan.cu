@@ -65,6 +65,41 @@ scan_add_kernel(int64_t *__restrict__ out, const int64_t *__restrict__ sums_scan
         if (base + i < n) out[base + i] += add;
 }
 
+__global__ void mail_post_kernel(const unsigned long long *__restrict__ src,
+                                 unsigned long long *__restrict__ mail, int n) {
+    if (threadIdx.x < n) mail[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
+int mail_post(iss_handle *h, const void *d_src, int n, int slot) {
+    if (!h->h_mail) {
+        void *p = nullptr;
+        ISS_CUDA_TRY(h, cudaHostAlloc(&p, sizeof(unsigned long long)*MAIL_WORDS, cudaHostAllocMapped));
+        h->h_mail = static_cast<unsigned long long *>(p);
+        void *d = nullptr;
+        ISS_CUDA_TRY(h, cudaHostGetDevicePointer(&d, p, 0));
+        h->d_mail = static_cast<unsigned long long *>(d);
+    }
+    mail_post_kernel<<<1, 32, 0, h->stream>>>(static_cast<const unsigned long long *>(d_src),
+                                               h->d_mail + slot, n); ISS_LAUNCHED(h);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    return ISS_OK;
+}
+
+int ensure_mapped_event_offsets(iss_handle *h, int64_t n) {
+    if (h->h_evoff && n <= h->evoff_mapped_cap) return ISS_OK;
+    if (h->h_evoff) cudaFreeHost(h->h_evoff);
+    h->h_evoff = nullptr;
+    h->evoff_mapped_cap = n + n/2 + 1024;
+    void *p = nullptr;
+    ISS_CUDA_TRY(h, cudaHostAlloc(&p, sizeof(int64_t)*h->evoff_mapped_cap, cudaHostAllocMapped));
+    h->h_evoff = static_cast<int64_t *>(p);
+    void *d = nullptr;
+    ISS_CUDA_TRY(h, cudaHostGetDevicePointer(&d, p, 0));
+    h->d_evoff_mapped = static_cast<int64_t *>(d);
+    return ISS_OK;
+}
+
 static int scan_rec(iss_handle *h, const int64_t *d_in, int64_t *d_out, int64_t n,
                     int64_t *d_tmp, int64_t tmp_elems) {
     const int64_t nblk = (n + SCAN_BLOCK - 1)/SCAN_BLOCK;
@@ -105,9 +140,10 @@ int device_exclusive_scan_i64(iss_handle *h, const int64_t *d_in, int64_t *d_out
                       static_cast<int64_t>(h->scan_tmp_bytes/sizeof(int64_t)));
     if (rc) return rc;
     if (h_total) {
-        ISS_CUDA_TRY(h, cudaMemcpyAsync(h_total, d_out + n, sizeof(int64_t),
-                                        cudaMemcpyDeviceToHost, h->stream));
+        rc = mail_post(h, d_out + n, 1, 8);
+        if (rc) return rc;
         ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        *h_total = static_cast<int64_t>(*reinterpret_cast<volatile unsigned long long *>(h->h_mail + 8));
     }
     return ISS_OK;
 }

@@ -434,6 +434,7 @@ int run_yields(iss_handle *h) {
                                     cudaMemcpyDeviceToHost, h->stream));
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_yields = true;
+    h->lambda_on_device = false;
     return ISS_OK;
 }
 

@@ -28,6 +28,24 @@ double seconds_since(const std::chrono::steady_clock::time_point &t0) {
     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
+// ISS_PROFILE=1: wall-clock of the host-side phases on stderr
+struct PhaseTimer {
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    static bool on() {
+        static int v = -1;
+        if (v < 0) {
+            const char *e = getenv("ISS_PROFILE");
+            v = (e && atoi(e) == 1) ? 1 : 0;
+        }
+        return v == 1;
+    }
+    explicit PhaseTimer(const char *n) : name(n), t0(std::chrono::steady_clock::now()) {}
+    ~PhaseTimer() {
+        if (on()) fprintf(stderr, "[iss profile] %-28s %8.3f ms\n", name, 1e3*seconds_since(t0));
+    }
+};
+
 // numbers of a whitespace separated text file after `skip_lines` header lines
 std::vector<double> read_numbers(const std::string &file, int skip_lines) {
     std::vector<double> out;
@@ -193,10 +211,10 @@ GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
                         "fallback)");
         exit(-1);
     }
-    select_species_(chosen_monvals);
-    upload_surface_();
-    upload_tables_();
-    upload_decay_table_();
+    { PhaseTimer t("select_species"); select_species_(chosen_monvals); }
+    { PhaseTimer t("upload_surface"); upload_surface_(); }
+    { PhaseTimer t("upload_tables"); upload_tables_(); }
+    { PhaseTimer t("upload_decay_table"); upload_decay_table_(); }
 
     iss_options opt;
     memset(&opt, 0, sizeof(opt));
@@ -482,6 +500,7 @@ void GpuFSSW::reserve_hadrons_(int64_t need) {
 }
 
 void GpuFSSW::compute_yields() {
+    PhaseTimer t("compute_yields");
     dN_species_.assign(species_.size(), 0.);
     check_(iss_cuda_compute_yields(h_, dN_species_.data(), nullptr), "iss_cuda_compute_yields");
 }
@@ -546,6 +565,7 @@ void GpuFSSW::sample_events() {
                                          + 6.0*std::sqrt(dN_event*nev_ + 1.0))
                      + nsp*nev_ + 1024);
 
+    PhaseTimer tb("batches (sample+copy)");
     for (int64_t ev0 = 0; ev0 < nev_; ev0 += batch) {
         const int64_t ev1 = std::min<int64_t>(nev_, ev0 + batch);
         iss_counts cnt;
@@ -581,7 +601,7 @@ void GpuFSSW::sample_events() {
             }
         }
     }
-    check_(iss_cuda_fetch_wait(h_), "iss_cuda_fetch_wait");
+    { PhaseTimer tw("final fetch_wait"); check_(iss_cuda_fetch_wait(h_), "iss_cuda_fetch_wait"); }
     if (flag_spectators_) std::cout << "Add spectators to the hadron list... " << std::endl;
     qa_.assign(iss_cuda_qa_size(), 0.);
     check_(iss_cuda_qa_fetch(h_, qa_.data()), "iss_cuda_qa_fetch");
@@ -591,8 +611,9 @@ void GpuFSSW::sample_events() {
 }
 
 void GpuFSSW::shell() {
+    PhaseTimer t("shell total");
     compute_yields();
-    sample_events();
+    { PhaseTimer t2("sample_events"); sample_events(); }
     computeAvgTotalEnergyMomentum();
     // priority OSCAR > gzip > binary (FSSW.cpp:354-360)
     if (use_oscar_) combine_samples_to_OSCAR();

@@ -2,6 +2,7 @@
 // Citations are to the reference's src/iSS.cpp.
 #include "iSS.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -160,6 +161,16 @@ std::vector<int> iSS::read_chosen_particles() const {
 }
 
 int iSS::prepare_sampler() {
+    const auto t0 = std::chrono::steady_clock::now();
+    struct Report {
+        std::chrono::steady_clock::time_point t0;
+        ~Report() {
+            const char *e = getenv("ISS_PROFILE");
+            if (e && atoi(e) == 1)
+                fprintf(stderr, "[iss profile] %-28s %8.3f ms\n", "prepare_sampler total",
+                        1e3*std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
+    } report{t0};
     require_fssw_();
     if (!seed_set_) set_random_seed();
     const std::vector<int> chosen = read_chosen_particles();
