@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -132,9 +132,10 @@ def run_engine(args):
     E = args.events_per_step
     work = tempfile.mkdtemp(prefix="iss_bench_r%d_" % rank)
     make_case(work, args.cells)
-    devnull = os.open(os.devnull, os.O_WRONLY)
     saved_stdout = os.dup(1)
-    os.dup2(devnull, 1)          # the facade logs like the reference; keep stdout for the JSON line
+    sys.stdout.flush()
+    os.dup2(2, 1)                # the facade logs to stdout like the reference: send that to stderr
+                                 # and keep the real stdout for the JSON line
     try:
         over = dict(OVERRIDES, number_of_repeated_sampling=E)
         s = capi.Sampler(work, PARAM, "surface.dat", **over)
@@ -147,14 +148,8 @@ def run_engine(args):
         ncell, ns = e.ncell, e.nspecies
         qa_pids = [211, -211, 321, -321, 2212, -2212, 3122, 111]
 
-        def qa_tensor():
-            class _Ext:
-                pass
-            o = _Ext()
-            n = int(capi.cuda_lib().iss_cuda_qa_size())
-            o.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8",
-                                          "data": (e.qa_device_ptr(), False), "version": 2}
-            return torch.as_tensor(o, device="cuda")
+        from iss_b200 import sharding
+        qa_n = int(capi.cuda_lib().iss_cuda_qa_size())
 
         step_counter = [0]
 
@@ -162,19 +157,19 @@ def run_engine(args):
             k = step_counter[0]
             step_counter[0] += 1
             e.compute_yields()
-            ev0 = (k*world + rank)*E
-            c = e.sample(args.seed, ev0, ev0 + E)
+            ev0, ev1 = sharding.weak_event_range(k, rank, world, E)
+            c = e.sample(args.seed, ev0, ev1)
             e.L.iss_cuda_histograms(e.h, capi._ptr(np.asarray(qa_pids, dtype=np.int32)),
                                     len(qa_pids), 0)
-            if world > 1:
-                dist.all_reduce(qa_tensor())        # NCCL: QA histograms only
+            if world > 1:       # NCCL: QA histograms only
+                sharding.allreduce_sum_(sharding.device_block_as_tensor(e.qa_device_ptr(), qa_n, "cuda"))
             return c.n_hadrons, c.n_tries
 
+        clocks = ClockSampler(local)    # sampled from the warm-up steps (same load) to the end
+        clocks.start()
         for _ in range(args.warmup):
             step()
         e.timing(enable=True, reset=True)
-        clocks = ClockSampler(local)
-        clocks.start()
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record(stream)
@@ -226,8 +221,8 @@ def run_engine(args):
         d2h = int(e2e_hadrons/e2e_steps)*40 + (E + 1)*8
         s.close()
     finally:
+        sys.stdout.flush()
         os.dup2(saved_stdout, 1)
-        os.close(devnull)
         shutil.rmtree(work, ignore_errors=True)
 
     peaks, peak_src = load_peaks()

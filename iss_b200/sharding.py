@@ -1,0 +1,42 @@
+"""Event sharding across the GPUs of one node.
+
+Events are independent given the yields and every random stream is keyed by the global event index,
+so rank r of N simply samples its own event range with the same seed: no data-path collective, and
+the union of the ranks' outputs is bit-identical to a single-GPU run.  Only the QA block (plain
+sums, include/iss_cuda.h) is reduced, with one all-reduce (NCCL on GPUs; gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def split_events(nev_total, world):
+    """Contiguous, disjoint ranges covering [0, nev_total): rank r gets [b[r], b[r+1])."""
+    base, rem = divmod(int(nev_total), int(world))
+    bounds = [0]
+    for r in range(world):
+        bounds.append(bounds[-1] + base + (1 if r < rem else 0))
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def weak_event_range(step, rank, world, events_per_rank):
+    """Weak-scaling benchmark layout: every rank samples `events_per_rank` new events per step."""
+    begin = (int(step)*int(world) + int(rank))*int(events_per_rank)
+    return begin, begin + int(events_per_rank)
+
+
+def allreduce_sum_(t):
+    """In-place sum over ranks of a tensor (QA block, counters); no-op without a process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t
+
+
+def device_block_as_tensor(device_ptr, n_doubles, device):
+    """Wraps a device pointer of the engine (e.g. iss_cuda_qa_device_ptr) as a torch tensor so that
+    NCCL can reduce it in place."""
+    class _Ext:
+        pass
+    o = _Ext()
+    o.__cuda_array_interface__ = {"shape": (int(n_doubles),), "typestr": "<f8",
+                                  "data": (int(device_ptr), False), "version": 2}
+    return torch.as_tensor(o, device=device)
