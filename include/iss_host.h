@@ -56,6 +56,13 @@ ISS_API int32_t iss_host_species_dN(iss_host *s, double *dst);
 /* QA block (layout: iss_cuda.h), iss_cuda_qa_size() doubles */
 ISS_API int iss_host_qa_block(iss_host *s, double *dst);
 
+/* the reference's sample-file writers (FSSW::combine_samples_to_OSCAR / _gzip_file / _binary_file,
+ * FSSW.cpp:365-561) on a caller-supplied hadron list; files go to the current directory like the
+ * reference's.  format: 0 OSCAR.DAT, 1 particle_samples.gz, 2 particle_samples.bin             */
+ISS_API int iss_host_write_samples(int format, const iss_hadron *hadrons,
+                                   const int64_t *event_offsets, int64_t nev,
+                                   const char *table_path);
+
 #ifdef __cplusplus
 }
 #endif

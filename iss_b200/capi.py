@@ -89,7 +89,7 @@ HOST_SYMBOLS = [
     "iss_host_get_number_of_sampled_events", "iss_host_get_number_of_particles",
     "iss_host_get_hadron_list_iev", "iss_host_clear", "iss_host_prepare_sampler",
     "iss_host_cuda_handle", "iss_host_lrf_surface", "iss_host_species", "iss_host_hadron_buffer",
-    "iss_host_species_dN", "iss_host_qa_block",
+    "iss_host_species_dN", "iss_host_qa_block", "iss_host_write_samples",
 ]
 
 _cuda = None
@@ -186,6 +186,7 @@ def host_lib():
         "iss_host_hadron_buffer": (vp, [vp, C.POINTER(vp), i64p]),
         "iss_host_species_dN": (C.c_int32, [vp, vp]),
         "iss_host_qa_block": (C.c_int, [vp, vp]),
+        "iss_host_write_samples": (C.c_int, [C.c_int, vp, vp, C.c_int64, cs]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -193,6 +194,18 @@ def host_lib():
         fn.argtypes = args
     _host = L
     return L
+
+
+def write_samples(fmt, hadrons, event_offsets, table_path=TABLES):
+    """reference-format sample files in the current directory; fmt: "oscar", "gzip", "binary"."""
+    h = np.ascontiguousarray(hadrons, dtype=HADRON_DTYPE)
+    off = np.ascontiguousarray(event_offsets, dtype=np.int64)
+    code = {"oscar": 0, "gzip": 1, "binary": 2}[fmt]
+    rc = host_lib().iss_host_write_samples(code, h.ctypes.data_as(C.c_void_p),
+                                           off.ctypes.data_as(C.c_void_p), len(off) - 1,
+                                           table_path.encode())
+    if rc != 0:
+        raise IssError("iss_host_write_samples failed")
 
 
 class IssError(RuntimeError):

@@ -5,6 +5,7 @@
 #include "../../include/iss_host.h"
 #include "gpu_fssw.h"
 #include "iSS.h"
+#include "writers.h"
 
 struct iss_host {
     iSS *obj;
@@ -109,6 +110,22 @@ int iss_host_qa_block(iss_host *s, double *dst) {
     GpuFSSW *g = s->obj->get_sampler();
     if (!g || g->qa_block().empty()) return 1;
     memcpy(dst, g->qa_block().data(), sizeof(double)*g->qa_block().size());
+    return 0;
+}
+
+int iss_host_write_samples(int format, const iss_hadron *hadrons, const int64_t *event_offsets,
+                           int64_t nev, const char *table_path) {
+    const iSS_Hadron *h = reinterpret_cast<const iSS_Hadron *>(hadrons);
+    if (format == 0) {
+        iss_writers::write_oscar("OSCAR.DAT", std::string(table_path ? table_path : "iSS_tables")
+                                                  + "/OSCAR_header.txt", h, event_offsets, nev);
+    } else if (format == 1) {
+        iss_writers::write_gzip("particle_samples.gz", h, event_offsets, nev);
+    } else if (format == 2) {
+        iss_writers::write_binary("particle_samples.bin", h, event_offsets, nev);
+    } else {
+        return 1;
+    }
     return 0;
 }
 

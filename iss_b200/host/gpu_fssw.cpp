@@ -1,8 +1,6 @@
 // gpu_fssw.cpp -- see gpu_fssw.h.  Citations are to the reference's src/FSSW.cpp.
 #include "gpu_fssw.h"
 
-#include <zlib.h>
-
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -19,6 +17,7 @@
 #include <unordered_map>
 
 #include "logger.h"
+#include "writers.h"
 
 using iss_host::info;
 
@@ -654,93 +653,15 @@ void GpuFSSW::computeAvgTotalEnergyMomentum() {
     }
 }
 
-// OSCAR1997A text (FSSW.cpp:365-494): header file verbatim, per non-empty event a line
-// "iev(0-based) N 0 0", per hadron "index pid" + px py pz E m x y z t in %24.16e
 void GpuFSSW::combine_samples_to_OSCAR() {
-    const auto t0 = std::chrono::steady_clock::now();
-    info(" -- Now combine sample files to OSCAR file...");
-    const std::string header_file = table_path_ + "/OSCAR_header.txt";
-    remove("OSCAR.DAT");
-    std::ofstream oscar("OSCAR.DAT");
-    std::ifstream header(header_file.c_str());
-    if (!header.is_open()) {
-        std::cout << std::endl
-                  << "combine_samples_to_OSCAR error: OSCAR header file " << header_file
-                  << " not found." << std::endl;
-        exit(-1);
-    }
-    std::string line;
-    while (std::getline(header, line)) {
-        if (header.eof()) break;    // the reference drops an unterminated last line
-        oscar << line << std::endl;
-    }
-    char buf[512];
-    for (int64_t ev = 0; ev < nev_; ev++) {
-        const int64_t n = event_off_[ev + 1] - event_off_[ev];
-        if (n <= 0) continue;
-        oscar << std::setw(10) << ev << "  " << std::setw(10) << n << "  " << std::setw(8) << 0.0
-              << "  " << std::setw(8) << 0.0 << std::endl;
-        for (int64_t i = 0; i < n; i++) {
-            const iSS_Hadron &hd = hadrons_[event_off_[ev] + i];
-            oscar << std::setw(10) << i + 1 << "  " << std::setw(10) << hd.pid << "  ";
-            snprintf(buf, sizeof(buf),
-                     "%24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e",
-                     hd.px, hd.py, hd.pz, hd.E, hd.mass, hd.x, hd.y, hd.z, hd.t);
-            oscar << buf << std::endl;
-        }
-    }
-    std::cout << std::endl
-              << " -- combine_samples_to_OSCAR samples finishes " << seconds_since(t0)
-              << " seconds." << std::endl;
+    iss_writers::write_oscar("OSCAR.DAT", table_path_ + "/OSCAR_header.txt", hadrons_,
+                             event_off_.data(), nev_);
 }
 
-// particle_samples.gz (FSSW.cpp:497-526)
 void GpuFSSW::combine_samples_to_gzip_file() {
-    const auto t0 = std::chrono::steady_clock::now();
-    info(" -- Now combine sample files to a gzip file...");
-    remove("particle_samples.gz");
-    gzFile fp = gzopen("particle_samples.gz", "wb");
-    for (int64_t ev = 0; ev < nev_; ev++) {
-        const int n = static_cast<int>(event_off_[ev + 1] - event_off_[ev]);
-        gzprintf(fp, "%d \n", n);
-        for (int64_t i = event_off_[ev]; i < event_off_[ev + 1]; i++) {
-            const iSS_Hadron &hd = hadrons_[i];
-            gzprintf(fp, "%d ", hd.pid);
-            gzprintf(fp, "%.7e %.7e %.7e %.7e %.7e %.7e %.7e %.7e %.7e\n", hd.mass, hd.t, hd.x,
-                     hd.y, hd.z, hd.E, hd.px, hd.py, hd.pz);
-        }
-    }
-    gzclose(fp);
-    std::cout << std::endl
-              << " -- combine_samples_to_gzip_file finishes " << seconds_since(t0) << " seconds."
-              << std::endl;
+    iss_writers::write_gzip("particle_samples.gz", hadrons_, event_off_.data(), nev_);
 }
 
-// particle_samples.bin (FSSW.cpp:529-561): int N, then per hadron int pid + 9 floats
-// {mass, t, x, y, z, E, px, py, pz}
 void GpuFSSW::combine_samples_to_binary_file() {
-    const auto t0 = std::chrono::steady_clock::now();
-    info(" -- Now combine sample files to a binary file...");
-    remove("particle_samples.bin");
-    FILE *out = fopen("particle_samples.bin", "wb");
-    std::vector<char> rec;
-    for (int64_t ev = 0; ev < nev_; ev++) {
-        const int n = static_cast<int>(event_off_[ev + 1] - event_off_[ev]);
-        rec.resize(sizeof(int) + static_cast<size_t>(n)*40);
-        char *p = rec.data();
-        memcpy(p, &n, sizeof(int));
-        p += sizeof(int);
-        for (int64_t i = event_off_[ev]; i < event_off_[ev + 1]; i++) {
-            const iSS_Hadron &hd = hadrons_[i];
-            const float a[9] = {hd.mass, hd.t, hd.x, hd.y, hd.z, hd.E, hd.px, hd.py, hd.pz};
-            memcpy(p, &hd.pid, sizeof(int));
-            memcpy(p + sizeof(int), a, sizeof(a));
-            p += 40;
-        }
-        fwrite(rec.data(), 1, rec.size(), out);
-    }
-    fclose(out);
-    std::cout << std::endl
-              << " -- combine_samples_to_binary_file finishes " << seconds_since(t0) << " seconds."
-              << std::endl;
+    iss_writers::write_binary("particle_samples.bin", hadrons_, event_off_.data(), nev_);
 }

@@ -156,12 +156,46 @@ static int run_decay(int argc, char **argv) {
     return 0;
 }
 
+// ref_driver writers <param_file> <work_path> <surface_file> <hadrons.bin>
+//   hadrons.bin: int64 nev, int64 offsets[nev+1], then iSS_Hadron records (40 B).  The list is put
+//   into FSSW::Hadron_list and the reference's three writers are called; OSCAR.DAT,
+//   particle_samples.gz and particle_samples.bin appear in the current directory.
+static int run_writers(int argc, char **argv) {
+    if (argc < 6) { std::cerr << "usage: writers param path surface hadrons.bin\n"; return 2; }
+    std::string param = argv[2], path = argv[3], surface = argv[4];
+    iSS sampler(path, "iSS_tables", "iSS_tables", param, surface);
+    for (int i = 6; i < argc; i++) sampler.paraRdr_ptr->phraseOneLine(argv[i]);
+    sampler.read_in_FO_surface();
+    sampler.set_random_seed(1);
+    Table chosen_particles;
+    chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_urqmd_v3.3+.dat");
+    FSSW fssw(sampler.ran_gen_ptr_, &chosen_particles, sampler.particle_,
+              sampler.FOsurf_LRF_array_, sampler.flag_PCE_, sampler.paraRdr_ptr,
+              path, "iSS_tables", sampler.afterburner_type_);
+    FILE *f = fopen(argv[5], "rb");
+    int64_t nev = 0;
+    if (fread(&nev, sizeof(nev), 1, f) != 1) return 1;
+    std::vector<int64_t> off(nev + 1);
+    if (fread(off.data(), sizeof(int64_t), nev + 1, f) != static_cast<size_t>(nev + 1)) return 1;
+    for (int64_t ev = 0; ev < nev; ev++) {
+        auto *v = new std::vector<iSS_Hadron>(off[ev + 1] - off[ev]);
+        if (!v->empty() && fread(v->data(), sizeof(iSS_Hadron), v->size(), f) != v->size()) return 1;
+        fssw.Hadron_list->push_back(v);
+    }
+    fclose(f);
+    fssw.combine_samples_to_OSCAR();
+    fssw.combine_samples_to_gzip_file();
+    fssw.combine_samples_to_binary_file();
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { std::cerr << "usage: ref_driver yields|momentum|decay ...\n"; return 2; }
     std::string mode = argv[1];
     if (mode == "yields") return run_yields(argc, argv);
     if (mode == "momentum") return run_momentum(argc, argv);
     if (mode == "decay") return run_decay(argc, argv);
+    if (mode == "writers") return run_writers(argc, argv);
     std::cerr << "unknown mode " << mode << "\n";
     return 2;
 }

@@ -231,8 +231,55 @@ def golden_decay():
     shutil.rmtree(d)
 
 
+def writer_hadrons():
+    """a small fixed hadron list: 5 events (one of them empty), odd values to exercise the formats"""
+    rng = np.random.default_rng(31415)
+    counts = [7, 0, 3, 12, 1]
+    n = sum(counts)
+    dt = np.dtype([("pid", "<i4"), ("mass", "<f4"), ("E", "<f4"), ("px", "<f4"), ("py", "<f4"),
+                   ("pz", "<f4"), ("t", "<f4"), ("x", "<f4"), ("y", "<f4"), ("z", "<f4")])
+    h = np.zeros(n, dtype=dt)
+    h["pid"] = rng.choice([211, -211, 2212, -2212, 3122, 111, 9000221, -3334], n)
+    h["mass"] = rng.choice([0.13957, 0.93827, 1.11568, 0.13498], n)
+    for k in ("px", "py", "pz"):
+        h[k] = rng.normal(0, 0.7, n)
+    h["E"] = np.sqrt(h["mass"].astype(np.float64)**2 + h["px"].astype(np.float64)**2
+                     + h["py"].astype(np.float64)**2 + h["pz"].astype(np.float64)**2)
+    h["t"] = rng.uniform(0.6, 15, n)
+    h["x"], h["y"] = rng.uniform(-10, 10, n), rng.uniform(-10, 10, n)
+    h["z"] = rng.normal(0, 5, n)
+    h["t"][0] = 1e10            # stable-particle "life time" of the decay code
+    h["px"][1] = 0.0
+    h["pz"][2] = -1.2345678e-7
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    return h, off
+
+
+def golden_writers():
+    d = workdir()
+    case = os.path.join(d, "case")
+    os.makedirs(case)
+    shutil.copy(os.path.join(FIX, "music_input_9"), os.path.join(case, "music_input"))
+    shutil.copy(os.path.join(FIX, "testIdealOneFluidCell2.dat"), case)
+    h, off = writer_hadrons()
+    with open(os.path.join(d, "hadrons.bin"), "wb") as f:
+        np.int64(len(off) - 1).tofile(f)
+        off.tofile(f)
+        h.tofile(f)
+    run([os.path.join(REF, "ref_driver"), "writers", os.path.join(FIX, "iSS_parameters_ideal.dat"),
+         "case", "testIdealOneFluidCell2.dat", "hadrons.bin", "bulk_deltaf_kind=21"], d,
+        os.path.join(d, "log"))
+    import gzip
+    np.savez_compressed(os.path.join(HERE, "writers.npz"), hadrons=h, offsets=off,
+                        oscar=np.frombuffer(open(os.path.join(d, "OSCAR.DAT"), "rb").read(), dtype=np.uint8),
+                        binary=np.frombuffer(open(os.path.join(d, "particle_samples.bin"), "rb").read(), dtype=np.uint8),
+                        gz_text=np.frombuffer(gzip.open(os.path.join(d, "particle_samples.gz"), "rb").read(), dtype=np.uint8))
+    print("writers", len(h), "hadrons")
+    shutil.rmtree(d)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["yields", "stats", "momentum", "decay"]
+    what = sys.argv[1:] or ["yields", "stats", "momentum", "decay", "writers"]
     if "yields" in what:
         golden_yields()
     if "momentum" in what:
@@ -241,3 +288,5 @@ if __name__ == "__main__":
         golden_decay()
     if "stats" in what:
         golden_stats()
+    if "writers" in what:
+        golden_writers()
