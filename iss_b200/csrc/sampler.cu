@@ -216,8 +216,22 @@ __global__ void event_offset_kernel(const int64_t *__restrict__ off_out, int ns,
 }
 
 // ---------------------------------------------------------------------------------
-// K5: persistent sampler
+// K5: sampler = set-up kernel (one thread per hadron) + persistent proposal kernel
 // ---------------------------------------------------------------------------------
+// One hadron to sample, produced by setup_kernel and consumed by propose_kernel (48 bytes).
+struct __align__(16) Task {
+    int64_t out_slot;       // index of the output record
+    double m_term;          // CDF(a) term of MomentumSamplerBase::Sample_a_momentum
+    double cdf_max;
+    int32_t cell;
+    int32_t s;              // species (sampling order)
+    uint32_t event;         // global event index
+    uint32_t draw;          // index of the hadron inside (event, species)
+    int32_t tab_idx;        // momentum table (bits 0..2) | idx_min << 3; < 0: table range error
+    int32_t pad;
+};
+static_assert(sizeof(Task) == 48, "Task must stay 48 bytes");
+
 struct SamplerArgs {
     const float *cells;             // [ncell][CELL_STRIDE]
     const double *cellcoef;         // [ncell][COEF_STRIDE]
@@ -236,35 +250,22 @@ struct SamplerArgs {
     int hydro_mode, lcc;
     double y_LB, y_RB;
     uint64_t seed;
+    Task *tasks;                    // [nwork]
     iss_hadron *out;
-    unsigned long long *counters;   // [0] work cursor, [1] tries, [2] redraws, [3] range errors
+    unsigned long long *counters;   // [0] task cursor, [1] tries, [2] redraws, [3] range errors
     int32_t *trace_cell;            // optional [n_out]
     int32_t *trace_tries;           // optional [n_out]
 };
 
+constexpr int SETUP_THREADS = 256;
 constexpr int SAMPLER_THREADS = 128;
-constexpr int WORK_CHUNK = 512;         // hadrons a warp grabs at a time
-constexpr int REFILL_THRESHOLD = 16;    // refill when this many lanes are idle
+constexpr int TASK_CHUNK = 128;         // tasks a warp reserves at a time
 constexpr int MAX_IMPATIENCE = 5000;    // FSSW.cpp:1872
 
-struct LaneState {
-    // identity
-    int64_t out_slot;
-    int s;
-    // RNG
-    BlockStream rng;
-    // cell
-    int64_t cell;
-    // |p| sampler set-up (MomentumSamplerBase::Sample_a_momentum)
-    double T, mu, m_tilde, mu_tilde, w0, m_term, cdf_max, a_min;
+// per-(cell, species) constants of the |p| sampler (MomentumSamplerBase::Sample_a_momentum)
+struct MomSetup {
+    double T, mu, mu_tilde, w0, m_term, cdf_max, a_min;
     int tab, idx_min;
-    // accept set-up
-    double dsigma_fac;
-    int tries;
-    int total_tries;
-    int phase;      // 0 primary, 1 charge-conservation partner
-    int qsign;      // +1 primary, -1 partner (flips B,S,Q)
-    double eta_s;   // boost-invariant mode: eta_s of the primary, reused by its partner
 };
 
 __device__ __forceinline__ double table_F(const double *__restrict__ tb, int i, double w1,
@@ -274,9 +275,27 @@ __device__ __forceinline__ double table_F(const double *__restrict__ tb, int i, 
     return b.y + w1*b.x + w0*a.y - m_term;
 }
 
-// sets up the |p| sampler for (species, cell); returns false if out of table range
-__device__ __forceinline__ bool setup_momentum(const SamplerArgs &A, LaneState &L, double mass,
-                                               int sign, double T_in, double mu) {
+// the cheap part: everything but the two series values, which travel in the Task
+__device__ __forceinline__ void momentum_restore(double mass, double T_in, double mu, double m_term,
+                                                 double cdf_max, int tab, int idx_min, MomSetup &M) {
+    const double T = fmax(1e-16, T_in);
+    const double m_tilde = mass/T;
+    const double mu_tilde = mu/T;
+    M.T = T;
+    M.mu = mu;
+    M.mu_tilde = mu_tilde;
+    M.w0 = mu_tilde*mu_tilde - m_tilde*m_tilde/2.;
+    M.m_term = m_term;
+    M.cdf_max = cdf_max;
+    M.a_min = m_tilde - mu_tilde;
+    M.tab = tab;
+    M.idx_min = idx_min;
+}
+
+// full set-up for (species, cell); returns false if (m - mu)/T is outside the table
+// (reference: exit(1), MomentumSamplerBase.cpp:35-43)
+__device__ __forceinline__ bool momentum_setup(const MomentumTable *__restrict__ mts, double mass,
+                                               int sign, double T_in, double mu, MomSetup &M) {
     const double T = fmax(1e-16, T_in);
     const double m_tilde = mass/T;
     const double mu_tilde = mu/T;
@@ -285,7 +304,7 @@ __device__ __forceinline__ bool setup_momentum(const SamplerArgs &A, LaneState &
     const int regime = (m0tilde < 30.) ? 0 : (m0tilde < 50. ? 1 : 2);
     const bool fermion = (sign != -1);          // sign 0 -> fermion tables
     const int tab = (fermion ? 3 : 0) + regime;
-    const MomentumTable &mt = A.mt[tab];
+    const MomentumTable &mt = mts[tab];
     double c0, c1, c2;
     if (fermion) {
         cdf_012_lane<true>(mt, a, c0, c1, c2);
@@ -296,32 +315,28 @@ __device__ __forceinline__ bool setup_momentum(const SamplerArgs &A, LaneState &
     const double w0 = mu_tilde*mu_tilde - m_tilde*m_tilde/2.;
     const double m_term = c2 + w1*c1 + w0*c0;
     const int idx_max = mt.n - 1;
-    const double cdf_max = table_F(mt.data, idx_max, w1, w0, m_term);
-    const int idx_min = static_cast<int>((a - mt.e0)/mt.de);
-    L.T = T;
-    L.mu = mu;
-    L.m_tilde = m_tilde;
-    L.mu_tilde = mu_tilde;
-    L.w0 = w0;
-    L.m_term = m_term;
-    L.cdf_max = cdf_max;
-    L.a_min = a;
-    L.tab = tab;
-    L.idx_min = idx_min;
-    return !(idx_min < 0 || idx_min >= idx_max);
+    M.T = T;
+    M.mu = mu;
+    M.mu_tilde = mu_tilde;
+    M.w0 = w0;
+    M.m_term = m_term;
+    M.cdf_max = table_F(mt.data, idx_max, w1, w0, m_term);
+    M.a_min = a;
+    M.tab = tab;
+    M.idx_min = static_cast<int>((a - mt.e0)/mt.de);
+    return !(M.idx_min < 0 || M.idx_min >= idx_max);
 }
 
 // MomentumSamplerBase::inverse_CDF (MomentumSamplerBase.cpp:61-93)
-__device__ __forceinline__ double inverse_cdf(const MomentumTable &mt, const LaneState &L,
-                                              double r) {
-    const double w1 = 2.*L.mu_tilde;
-    int lo = L.idx_min;
+__device__ __forceinline__ double inverse_cdf(const MomentumTable &mt, const MomSetup &M, double r) {
+    const double w1 = 2.*M.mu_tilde;
+    int lo = M.idx_min;
     int hi = mt.n - 1;
-    double r_min = table_F(mt.data, lo, w1, L.w0, L.m_term);
-    double r_max = L.cdf_max;
+    double r_min = table_F(mt.data, lo, w1, M.w0, M.m_term);
+    double r_max = M.cdf_max;
     while (hi - lo > 1) {
         const int mid = (hi + lo)/2;
-        const double r_mid = table_F(mt.data, mid, w1, L.w0, L.m_term);
+        const double r_mid = table_F(mt.data, mid, w1, M.w0, M.m_term);
         if (r < r_mid) {
             hi = mid;
             r_max = r_mid;
@@ -331,8 +346,8 @@ __device__ __forceinline__ double inverse_cdf(const MomentumTable &mt, const Lan
         }
     }
     double E0 = __ldg(mt.data + 4*lo);
-    if (E0 < L.a_min) {
-        E0 = L.a_min;
+    if (E0 < M.a_min) {
+        E0 = M.a_min;
         r_min = 0.;
     }
     const double Ehi = __ldg(mt.data + 4*hi);
@@ -363,6 +378,117 @@ __device__ __forceinline__ int64_t pick_cell(const SamplerArgs &A, int s, double
     return cell;
 }
 
+// chemical potential of a species in a cell: float arithmetic and min(m, mu) as FSSW.cpp:1861-1863
+__device__ __forceinline__ double species_mu(const DeviceSpecies &p, int qsign, const float4 th,
+                                             double mass) {
+    const float muf = __fadd_rn(
+        __fadd_rn(__fmul_rn(static_cast<float>(qsign*p.baryon), th.x),
+                  __fmul_rn(static_cast<float>(qsign*p.strange), th.y)),
+        __fmul_rn(static_cast<float>(qsign*p.charge), th.z));
+    return fmin(mass, static_cast<double>(muf));
+}
+
+__device__ __forceinline__ uint32_t sample_stream_word3(int s) {
+    return (static_cast<uint32_t>(STREAM_SAMPLE) << 24) | static_cast<uint32_t>(s);
+}
+
+// K5a: one thread per hadron of the batch: identity (species, event, draw) from the species-major
+// work offsets, output slot, cell choice (first block of the hadron's stream) and the two series
+// values of the |p| sampler.  Massively parallel, so the dependent loads of the two binary
+// searches are hidden by occupancy instead of stalling the proposal loop.
+__global__ void __launch_bounds__(SETUP_THREADS)
+setup_kernel(const SamplerArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
+    int64_t *sp_off = reinterpret_cast<int64_t *>(sp + A.ns);     // off_work[s*nev], s = 0..ns
+    for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
+    for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
+        sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
+    __syncthreads();
+    const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
+    unsigned long long my_range = 0;
+    for (int64_t w = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x; w < A.nwork;
+         w += static_cast<int64_t>(gridDim.x)*blockDim.x) {
+        int slo = 0, shi = A.ns;
+        while (shi - slo > 1) {
+            const int mid = (slo + shi) >> 1;
+            if (sp_off[mid] <= w) slo = mid; else shi = mid;
+        }
+        const int s = slo;
+        const int64_t *__restrict__ ow = A.off_work + static_cast<int64_t>(s)*A.nev;
+        int64_t elo = 0, ehi = A.nev;
+        while (ehi - elo > 1) {
+            const int64_t mid = (elo + ehi) >> 1;
+            if (__ldg(&ow[mid]) <= w) elo = mid; else ehi = mid;
+        }
+        const int64_t ev = elo;
+        const int64_t k = w - __ldg(&ow[ev]);
+        const DeviceSpecies p = sp[s];
+        const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
+        Task t;
+        t.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k*mult;
+        t.s = s;
+        t.event = static_cast<uint32_t>(A.ev_begin + ev);
+        t.draw = static_cast<uint32_t>(k);
+        uint32_t w0, w1, w2, w3;
+        philox_block(0u, t.draw, t.event, sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
+        const int64_t cell = pick_cell(A, s, u53(w0, w1));
+        t.cell = static_cast<int32_t>(cell);
+        const float4 *cr = reinterpret_cast<const float4 *>(A.cells + cell*CELL_STRIDE);
+        const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
+        const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
+        MomSetup M;
+        const bool ok = momentum_setup(A.mt, p.mass, p.sign, th0.y, species_mu(p, 1, th, p.mass), M);
+        t.m_term = M.m_term;
+        t.cdf_max = M.cdf_max;
+        t.tab_idx = ok ? (M.tab | (M.idx_min << 3)) : -1;
+        t.pad = 0;
+        if (!ok) my_range++;
+        A.tasks[w] = t;
+    }
+    if (my_range) atomicAdd(&A.counters[3], my_range);
+}
+
+// what a lane of the proposal kernel carries
+struct LaneState {
+    int64_t out_slot;
+    int s;
+    int cell;
+    BlockStream rng;
+    MomSetup M;
+    double dsigma_fac;
+    int tries;
+    int total_tries;
+    int qsign;      // +1 primary, -1 charge-conservation partner (flips B,S,Q)
+    double eta_s;   // boost-invariant mode: eta_s of the primary, reused by its partner
+};
+
+// Rare paths of the proposal kernel, kept out of line so that the hot loop stays small.
+// (a) the reference's "impatience": after 4999 rejected tries a NEW cell is drawn (FSSW.cpp:1017-1018)
+// (b) local charge conservation: the partner is sampled from the same cell with conjugate
+//     quantum numbers (FSSW.cpp:1035-1048)
+__device__ __noinline__ bool lane_new_setup(const SamplerArgs *Ag, LaneState &L, const DeviceSpecies &p,
+                                            bool redraw_cell, uint32_t key0, uint32_t key1) {
+    // Ag: copy of the kernel arguments in global memory (taking the address of the by-value
+    // kernel parameter would force a 1.2 KB per-thread stack copy)
+    const SamplerArgs &A = *Ag;
+    if (redraw_cell) {
+        uint32_t w0, w1, w2, w3;
+        philox_block(L.rng.block++, L.rng.draw, L.rng.event, sample_stream_word3(L.s), key0, key1,
+                     w0, w1, w2, w3);
+        L.cell = static_cast<int>(pick_cell(A, L.s, u53(w0, w1)));
+    }
+    const float4 *cr = reinterpret_cast<const float4 *>(A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
+    const float4 da = __ldg(cr + 1);
+    const float4 th0 = __ldg(cr + 3);
+    const float4 th = __ldg(cr + 4);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
+                               __fmul_rn(da.w, da.w));
+    L.dsigma_fac = fabs(static_cast<double>(da.x)) + sqrt(static_cast<double>(d2));
+    L.tries = 1;
+    return momentum_setup(A.mt, p.mass, p.sign, th0.y, species_mu(p, L.qsign, th, p.mass), L.M);
+}
+
 // SPEC selects a compile-time specialisation of the run-time mode flags (smaller and faster
 // code for the common configurations); SPEC 0 is the generic kernel that handles every mode.
 //   1: 3+1D, Chapman-Enskog (kind 21) shear + bulk + baryon diffusion, no charge pairing
@@ -380,9 +506,12 @@ struct SpecMode {
     static constexpr int lcc = 0;
 };
 
+// K5b: persistent proposal kernel.  Every lane owns one hadron and repeats the reference's try
+// (|p| proposal, direction, accept test) until it is accepted, then boosts, emits the record and
+// immediately takes the next task: all 32 lanes of a warp stay busy whatever the acceptance rate.
 template <int MIN_BLOCKS, int SPEC>
 __global__ void __launch_bounds__(SAMPLER_THREADS, MIN_BLOCKS)
-sampler_kernel(const SamplerArgs A) {
+propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     using SM = SpecMode<SPEC>;
     ModeFlags mode;
     mode.include_shear = SM::generic ? A.mode.include_shear : SM::shear;
@@ -393,16 +522,10 @@ sampler_kernel(const SamplerArgs A) {
     const int hydro_mode = SM::generic ? A.hydro_mode : SM::hydro_mode;
     const int lcc = SM::generic ? A.lcc : SM::lcc;
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
-#define ISS_NEXT_BLOCK(L_, w0, w1, w2, w3)                                                     \
-    philox_block((L_).rng.block++, (L_).rng.draw, (L_).rng.event,                              \
-                 (static_cast<uint32_t>(STREAM_SAMPLE) << 24) | static_cast<uint32_t>((L_).s), \
-                 key0, key1, w0, w1, w2, w3)
+
     extern __shared__ unsigned char smem_raw[];
     DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
-    int64_t *sp_off = reinterpret_cast<int64_t *>(sp + A.ns);     // off_work[s*nev], s = 0..ns
     for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
-    for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
-        sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
     __syncthreads();
 
     const unsigned full = 0xffffffffu;
@@ -410,207 +533,86 @@ sampler_kernel(const SamplerArgs A) {
     const unsigned lt_mask = (1u << lane) - 1u;
 
     LaneState L;
-    bool busy = false;          // lane owns a hadron that still needs an accepted momentum
-    bool pending = false;       // lane holds an accepted momentum waiting for boost+emit
-    double acc_p0 = 0., acc_px = 0., acc_py = 0., acc_pz = 0.;
-    int64_t chunk_next = 0, chunk_end = 0;
+    L.qsign = 1;
+    bool busy = false;
+    int64_t chunk_next = 0, chunk_end = 0;      // tasks reserved by this warp
     bool more_work = true;
     unsigned long long my_tries = 0, my_redraws = 0, my_range = 0;
 
     for (;;) {
-        // -------------------------------------------------------------- refill / emit phase
-        const unsigned idle_mask = __ballot_sync(full, !busy);
-        const int nidle = __popc(idle_mask);
-        const bool any_busy = (nidle < 32);
-        if (nidle >= REFILL_THRESHOLD || !any_busy) {
-            // (a) boost + emit accepted momenta (FSSW.cpp:1946-1960 and 1969-1996)
-            if (pending) {
-                const DeviceSpecies p = sp[L.s];
-                const float4 *cr = reinterpret_cast<const float4 *>(A.cells + L.cell*CELL_STRIDE);
-                const float4 pos = __ldg(cr + 0);       // tau, x, y, eta
-                const float4 u4 = __ldg(cr + 2);        // ut, ux, uy, uz
-                const float pl0 = static_cast<float>(acc_p0), pl1 = static_cast<float>(acc_px),
-                            pl2 = static_cast<float>(acc_py), pl3 = static_cast<float>(acc_pz);
-                double p_dot_u = 0.;
-                p_dot_u += __fmul_rn(pl1, u4.y);
-                p_dot_u += __fmul_rn(pl2, u4.z);
-                p_dot_u += __fmul_rn(pl3, u4.w);
-                const float up1 = __fadd_rn(u4.x, 1.f);
-                const double fac = p_dot_u/up1 + pl0;
-                const float lab1 = static_cast<float>(pl1 + fac*u4.y);
-                const float lab2 = static_cast<float>(pl2 + fac*u4.z);
-                const float lab3 = static_cast<float>(pl3 + fac*u4.w);
-                const double mass = p.mass;
-                iss_hadron hd;
-                hd.pid = (L.qsign > 0) ? p.pid : -p.pid;
-                hd.mass = static_cast<float>(mass);
-                hd.x = pos.y;
-                hd.y = pos.z;
-                const double pT = sqrt(static_cast<double>(__fadd_rn(__fmul_rn(lab1, lab1),
-                                                                     __fmul_rn(lab2, lab2))));
-                const double mT = sqrt(pT*pT + mass*mass);
-                if (hydro_mode == 2) {
-                    // eta_s = cell eta: y = asinh(pz/mT) - eta + eta, p_z = mT sinh(y) = pLab[3],
-                    // px = pT cos(atan2(py,px)) = pLab[1] up to FP64 rounding; t,z precomputed.
-                    const float4 tz = __ldg(cr + 7);    // t, z, spare, spare
-                    const double pz = lab3;
-                    hd.px = lab1;
-                    hd.py = lab2;
-                    hd.pz = lab3;
-                    hd.E = static_cast<float>(sqrt(mT*mT + pz*pz));
-                    hd.t = tz.x;
-                    hd.z = tz.y;
-                } else {
-                    // boost-invariant: y ~ U(y_LB, y_RB), eta_s = y - (y - eta_s) (FSSW.cpp:1024-1029)
-                    const double y_minus_eta = asinh(lab3/mT) - pos.w;
-                    // the charge-conservation partner keeps the primary's eta_s (FSSW.cpp:1045-1047)
-                    if (L.phase == 0) {
-                        uint32_t w0, w1, w2, w3;
-                    ISS_NEXT_BLOCK(L, w0, w1, w2, w3);
-                    const double rap = A.y_LB + (A.y_RB - A.y_LB)*u32(w0);
-                        L.eta_s = rap - y_minus_eta;
-                    }
-                    const double eta_s = L.eta_s;
-                    const double rapidity_y = y_minus_eta + eta_s;
-                    hd.px = lab1;
-                    hd.py = lab2;
-                    hd.pz = static_cast<float>(mT*sinh(rapidity_y));
-                    hd.E = static_cast<float>(mT*cosh(rapidity_y));
-                    hd.z = static_cast<float>(pos.x*sinh(eta_s));
-                    hd.t = static_cast<float>(pos.x*cosh(eta_s));
-                }
-                // 40-byte record as five 8-byte stores (slots are 8-byte aligned)
-                float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
-                dst[0] = make_float2(__int_as_float(hd.pid), hd.mass);
-                dst[1] = make_float2(hd.E, hd.px);
-                dst[2] = make_float2(hd.py, hd.pz);
-                dst[3] = make_float2(hd.t, hd.x);
-                dst[4] = make_float2(hd.y, hd.z);
-                if (A.trace_cell) {
-                    A.trace_cell[L.out_slot] = static_cast<int32_t>(L.cell);
-                    A.trace_tries[L.out_slot] = L.total_tries;
-                }
-                pending = false;
-                if (lcc == 1 && L.phase == 0 && p.charge > 0) {
-                    // partner with opposite quantum numbers from the SAME cell (FSSW.cpp:1035-1048)
-                    L.phase = 1;
-                    L.qsign = -1;
-                    L.out_slot += 1;
-                    L.tries = 1;
-                    L.total_tries = 0;
-                    const float4 th = __ldg(cr + 4);    // muB, muS, muQ, bulkPi
-                    const float4 th0 = __ldg(cr + 3);   // E, T, P, nB
-                    const float muf = __fadd_rn(
-                        __fadd_rn(__fmul_rn(static_cast<float>(-p.baryon), th.x),
-                                  __fmul_rn(static_cast<float>(-p.strange), th.y)),
-                        __fmul_rn(static_cast<float>(-p.charge), th.z));
-                    const double mu = fmin(mass, static_cast<double>(muf));
-                    if (setup_momentum(A, L, mass, p.sign, th0.y, mu)) {
-                        busy = true;
-                    } else {
-                        my_range++;
-                    }
+        // ------------------------------------------------------------ hand tasks to idle lanes
+        unsigned need_mask = __ballot_sync(full, !busy);
+        while (need_mask != 0u && more_work) {
+            if (chunk_next >= chunk_end) {
+                unsigned long long c = 0;
+                if (lane == 0) c = atomicAdd(&A.counters[0], (unsigned long long)TASK_CHUNK);
+                c = __shfl_sync(full, c, 0);
+                chunk_next = static_cast<int64_t>(c);
+                chunk_end = min(chunk_next + TASK_CHUNK, A.nwork);
+                if (chunk_next >= A.nwork) {
+                    more_work = false;
+                    break;
                 }
             }
-            // (b) hand new hadrons to idle lanes
-            const unsigned need_mask = __ballot_sync(full, !busy);
-            int nneed = __popc(need_mask);
+            const int nneed = __popc(need_mask);
+            const int64_t avail = chunk_end - chunk_next;
+            const int take = static_cast<int>(avail < (int64_t)nneed ? avail : (int64_t)nneed);
             const int rank = __popc(need_mask & lt_mask);
-            int given = 0;      // lanes served so far in this refill
-            while (given < nneed && more_work) {
-                if (chunk_next >= chunk_end) {
-                    unsigned long long c = 0;
-                    if (lane == 0) c = atomicAdd(&A.counters[0], (unsigned long long)WORK_CHUNK);
-                    c = __shfl_sync(full, c, 0);
-                    chunk_next = static_cast<int64_t>(c);
-                    chunk_end = min(chunk_next + WORK_CHUNK, A.nwork);
-                    if (chunk_next >= A.nwork) {
-                        more_work = false;
-                        break;
-                    }
-                }
-                const int64_t avail = chunk_end - chunk_next;
-                const int take = static_cast<int>(avail < (int64_t)(nneed - given) ? avail : (int64_t)(nneed - given));
-                if (!busy && rank >= given && rank < given + take) {
-                    const int64_t w = chunk_next + (rank - given);
-                    // (s, ev, k) from the species-major work offsets: species via smem, event via gmem
-                    int slo = 0, shi = A.ns;
-                    while (shi - slo > 1) {
-                        const int mid = (slo + shi) >> 1;
-                        if (sp_off[mid] <= w) slo = mid; else shi = mid;
-                    }
-                    const int s = slo;
-                    const int64_t *__restrict__ ow = A.off_work + static_cast<int64_t>(s)*A.nev;
-                    int64_t elo = 0, ehi = A.nev;
-                    while (ehi - elo > 1) {
-                        const int64_t mid = (elo + ehi) >> 1;
-                        if (__ldg(&ow[mid]) <= w) elo = mid; else ehi = mid;
-                    }
-                    const int64_t ev = elo;
-                    const int64_t k = w - __ldg(&ow[ev]);
-                    const DeviceSpecies p = sp[s];
-                    const int mult = (lcc == 1 && p.charge > 0) ? 2 : 1;
-                    L.s = s;
-                    L.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k*mult;
-                    L.rng.init(static_cast<uint32_t>(A.ev_begin + ev), static_cast<uint32_t>(k));
-                    L.phase = 0;
-                    L.qsign = 1;
-                    L.cell = -1;
-                    L.tries = MAX_IMPATIENCE;   // forces a cell draw below
-                    L.total_tries = 0;
+            if (!busy && rank < take) {
+                const float4 *tp = reinterpret_cast<const float4 *>(A.tasks + chunk_next + rank);
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                L.out_slot = (static_cast<int64_t>(__float_as_uint(t0.y)) << 32)
+                             | static_cast<int64_t>(__float_as_uint(t0.x));
+                const double m_term = __hiloint2double(__float_as_int(t0.w), __float_as_int(t0.z));
+                const double cdf_max = __hiloint2double(__float_as_int(t1.y), __float_as_int(t1.x));
+                L.cell = __float_as_int(t1.z);
+                L.s = __float_as_int(t1.w);
+                L.rng.event = __float_as_uint(t2.x);
+                L.rng.draw = __float_as_uint(t2.y);
+                L.rng.block = 1u;               // block 0 chose the cell (setup_kernel)
+                const int tab_idx = __float_as_int(t2.z);
+                L.qsign = 1;
+                L.tries = 1;
+                L.total_tries = 0;
+                if (tab_idx >= 0) {
+                    const DeviceSpecies p = sp[L.s];
+                    const float4 *cr = reinterpret_cast<const float4 *>(
+                        A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
+                    const float4 da = __ldg(cr + 1);
+                    const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
+                    const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
+                    // float arithmetic inside the sqrt as in FSSW.cpp:1867-1870
+                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
+                                               __fmul_rn(da.w, da.w));
+                    L.dsigma_fac = fabs(static_cast<double>(da.x)) + sqrt(static_cast<double>(d2));
+                    momentum_restore(p.mass, th0.y, species_mu(p, 1, th, p.mass), m_term, cdf_max,
+                                     tab_idx & 7, tab_idx >> 3, L.M);
                     busy = true;
                 }
-                chunk_next += take;
-                given += take;
+                // tab_idx < 0: momentum table range error, counted by setup_kernel; no record
             }
-            if (!more_work && !__any_sync(full, busy)) break;
+            chunk_next += take;
+            need_mask = __ballot_sync(full, !busy);
+            if (take == 0) break;
+        }
+        if (!__any_sync(full, busy)) {
+            if (!more_work) break;
+            continue;
         }
 
-        // -------------------------------------------------------------- proposal phase
-        if (busy) {
-            const DeviceSpecies p = sp[L.s];
-            const double mass = p.mass;
-            if (L.tries >= MAX_IMPATIENCE) {
-                // (re)draw the cell: first visit, or the reference's "impatience" re-pick
-                // (FSSW.cpp:1017-1018 with status == 0)
-                if (L.cell >= 0) my_redraws++;
-                {
-                    uint32_t w0, w1, w2, w3;
-                    ISS_NEXT_BLOCK(L, w0, w1, w2, w3);
-                    L.cell = pick_cell(A, L.s, u53(w0, w1));
-                }
-                L.tries = 1;
-                const float4 *cr = reinterpret_cast<const float4 *>(A.cells + L.cell*CELL_STRIDE);
-                const float4 da = __ldg(cr + 1);
-                const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
-                const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
-                const float muf = __fadd_rn(
-                    __fadd_rn(__fmul_rn(static_cast<float>(p.baryon), th.x),
-                              __fmul_rn(static_cast<float>(p.strange), th.y)),
-                    __fmul_rn(static_cast<float>(p.charge), th.z));
-                const double mu = fmin(mass, static_cast<double>(muf));
-                // float arithmetic inside the sqrt as in FSSW.cpp:1867-1870
-                const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
-                                           __fmul_rn(da.w, da.w));
-                L.dsigma_fac = fabs(static_cast<double>(da.x)) + sqrt(static_cast<double>(d2));
-                if (!setup_momentum(A, L, mass, p.sign, th0.y, mu)) {
-                    // reference: exit(1) (MomentumSamplerBase.cpp:35-43); here flagged, lane dropped
-                    my_range++;
-                    busy = false;
-                }
-            }
-        }
+        // ------------------------------------------------------------ one try per busy lane
         if (busy) {
             const DeviceSpecies p = sp[L.s];
             const double mass = p.mass;
             const int sign = p.sign;
-            const MomentumTable &mt = A.mt[L.tab];
+            const MomentumTable &mt = A.mt[L.M.tab];
             // |p| proposal (MomentumSamplerBase.cpp:48-56); an inner rejection restarts the try
             uint32_t pw0, pw1, pw2, pw3;
-            ISS_NEXT_BLOCK(L, pw0, pw1, pw2, pw3);
-            const double r = u53(pw0, pw1)*L.cdf_max;
-            const double Et = inverse_cdf(mt, L, r);
-            const double E_sample = L.T*Et + L.mu;
+            philox_block(L.rng.block++, L.rng.draw, L.rng.event, sample_stream_word3(L.s), key0, key1,
+                         pw0, pw1, pw2, pw3);
+            const double r = u53(pw0, pw1)*L.M.cdf_max;
+            const double Et = inverse_cdf(mt, L.M, r);
+            const double E_sample = L.M.T*Et + L.M.mu;
             const double p_mag = sqrt(E_sample*E_sample - mass*mass);
             const double accept_ratio = (p_mag/E_sample)/(1. - mass*mass/(2.*E_sample*E_sample));
             const double u_inner = u32(pw2);
@@ -618,9 +620,10 @@ sampler_kernel(const SamplerArgs A) {
                 my_tries++;
                 L.total_tries++;
                 // FSSW.cpp:1880-1945
-                // phi = 2 pi u: sin/cos through sincospi(2u) (no large-argument reduction path)
                 uint32_t qw0, qw1, qw2, qw3;
-                ISS_NEXT_BLOCK(L, qw0, qw1, qw2, qw3);
+                philox_block(L.rng.block++, L.rng.draw, L.rng.event, sample_stream_word3(L.s), key0,
+                             key1, qw0, qw1, qw2, qw3);
+                // phi = 2 pi u: sin/cos through sincospi(2u) (no large-argument reduction path)
                 const double u_phi = u32(pw3);
                 const double cos_theta = 2.*u32(qw0) - 1.;
                 const double sin_theta = sqrt(1. - cos_theta*cos_theta);
@@ -631,24 +634,24 @@ sampler_kernel(const SamplerArgs A) {
                 const double py = pT*sphi;
                 const double p0 = sqrt(mass*mass + p_mag*p_mag);
                 const double pz = p_mag*cos_theta;
-                const float4 *cr = reinterpret_cast<const float4 *>(A.cells + L.cell*CELL_STRIDE);
+                const float4 *cr = reinterpret_cast<const float4 *>(
+                    A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
                 const float4 da = __ldg(cr + 1);
                 const double pdsigma = p0*da.x + px*da.y + py*da.z + pz*da.w;
                 double fact1 = pdsigma/p0/L.dsigma_fac;
                 fact1 = fmax(0., fmin(1., fact1));
-                // the accept uniform is the next draw of the stream whatever delta f is; since
-                // fact2 <= 1, u >= fact1 already decides "reject" and the delta-f evaluation
-                // (exp, W, coefficients) is skipped
+                // the accept uniform is drawn whatever delta f is; since fact2 <= 1, u >= fact1
+                // already decides "reject" and the delta-f evaluation is skipped
                 const double u_acc = u32(qw1);
                 double accept_prob = 0.;
                 if (u_acc < fact1) {
-                    const double f0 = 1./(exp((p0 - L.mu)/L.T) + sign);
+                    const double f0 = 1./(exp((p0 - L.M.mu)/L.M.T) + sign);
                     const double stat = 1. - sign*f0;
                     double delta_f = 0.;
                     if (mode.include_shear | mode.include_bulk | mode.include_diff) {
                         const float4 th0 = __ldg(cr + 3);   // E, T, P, nB
                         const float4 th = __ldg(cr + 4);    // muB, muS, muQ, bulkPi
-                        const double *__restrict__ co = A.cellcoef + L.cell*COEF_STRIDE;
+                        const double *__restrict__ co = A.cellcoef + static_cast<int64_t>(L.cell)*COEF_STRIDE;
                         const int B = L.qsign*p.baryon, S = L.qsign*p.strange, Q = L.qsign*p.charge;
                         if (mode.include_shear == 1) {
                             const float4 pa = __ldg(cr + 5);    // pixx, pixy, pixz, piyy
@@ -657,7 +660,7 @@ sampler_kernel(const SamplerArgs A) {
                                                     + py*py*pa.w + 2.*py*pz*pb.x
                                                     + pz*pz*(-pa.x - pa.w));
                             if (mode.neos == 1) {
-                                delta_f += stat*Wfactor/(2.*__ldg(&co[2]))/(p0*L.T);
+                                delta_f += stat*Wfactor/(2.*__ldg(&co[2]))/(p0*L.M.T);
                             } else if (mode.neos == 0) {
                                 delta_f += stat*Wfactor*__ldg(&co[0]);
                             } else {
@@ -704,16 +707,92 @@ sampler_kernel(const SamplerArgs A) {
                     accept_prob = fact1*fact2;
                 }
                 if (u_acc < accept_prob) {
-                    acc_p0 = p0;
-                    acc_px = px;
-                    acc_py = py;
-                    acc_pz = pz;
-                    pending = true;
+                    // ---- accepted: boost to the lab frame and emit (FSSW.cpp:1946-1960, 1969-1996)
+                    const float4 pos = __ldg(cr + 0);       // tau, x, y, eta
+                    const float4 u4 = __ldg(cr + 2);        // ut, ux, uy, uz
+                    const float pl0 = static_cast<float>(p0), pl1 = static_cast<float>(px),
+                                pl2 = static_cast<float>(py), pl3 = static_cast<float>(pz);
+                    double p_dot_u = 0.;
+                    p_dot_u += __fmul_rn(pl1, u4.y);
+                    p_dot_u += __fmul_rn(pl2, u4.z);
+                    p_dot_u += __fmul_rn(pl3, u4.w);
+                    const float up1 = __fadd_rn(u4.x, 1.f);
+                    const double fac = p_dot_u/up1 + pl0;
+                    const float lab1 = static_cast<float>(pl1 + fac*u4.y);
+                    const float lab2 = static_cast<float>(pl2 + fac*u4.z);
+                    const float lab3 = static_cast<float>(pl3 + fac*u4.w);
+                    iss_hadron hd;
+                    hd.pid = (L.qsign > 0) ? p.pid : -p.pid;
+                    hd.mass = static_cast<float>(mass);
+                    hd.x = pos.y;
+                    hd.y = pos.z;
+                    const double pT_lab = sqrt(static_cast<double>(__fadd_rn(__fmul_rn(lab1, lab1),
+                                                                             __fmul_rn(lab2, lab2))));
+                    const double mT = sqrt(pT_lab*pT_lab + mass*mass);
+                    hd.px = lab1;
+                    hd.py = lab2;
+                    if (hydro_mode == 2) {
+                        // eta_s = cell eta: y = asinh(pz/mT) - eta + eta, p_z = mT sinh(y) = pLab[3],
+                        // px = pT cos(atan2(py,px)) = pLab[1] up to FP64 rounding; t,z precomputed.
+                        const float4 tz = __ldg(cr + 7);    // t, z, spare, spare
+                        const double pzl = lab3;
+                        hd.pz = lab3;
+                        hd.E = static_cast<float>(sqrt(mT*mT + pzl*pzl));
+                        hd.t = tz.x;
+                        hd.z = tz.y;
+                    } else {
+                        // boost-invariant: y ~ U(y_LB, y_RB), eta_s = y - (y - eta_s) (FSSW.cpp:1024-1029);
+                        // the charge-conservation partner keeps the primary's eta_s (FSSW.cpp:1045-1047)
+                        const double y_minus_eta = asinh(lab3/mT) - pos.w;
+                        if (L.qsign > 0) {
+                            uint32_t w0, w1, w2, w3;
+                            philox_block(L.rng.block++, L.rng.draw, L.rng.event,
+                                         sample_stream_word3(L.s), key0, key1, w0, w1, w2, w3);
+                            const double rap = A.y_LB + (A.y_RB - A.y_LB)*u32(w0);
+                            L.eta_s = rap - y_minus_eta;
+                        }
+                        const double eta_s = L.eta_s;
+                        const double rapidity_y = y_minus_eta + eta_s;
+                        hd.pz = static_cast<float>(mT*sinh(rapidity_y));
+                        hd.E = static_cast<float>(mT*cosh(rapidity_y));
+                        hd.z = static_cast<float>(pos.x*sinh(eta_s));
+                        hd.t = static_cast<float>(pos.x*cosh(eta_s));
+                    }
+                    // 40-byte record as five 8-byte stores (slots are 8-byte aligned)
+                    float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
+                    dst[0] = make_float2(__int_as_float(hd.pid), hd.mass);
+                    dst[1] = make_float2(hd.E, hd.px);
+                    dst[2] = make_float2(hd.py, hd.pz);
+                    dst[3] = make_float2(hd.t, hd.x);
+                    dst[4] = make_float2(hd.y, hd.z);
+                    if (A.trace_cell) {
+                        A.trace_cell[L.out_slot] = L.cell;
+                        A.trace_tries[L.out_slot] = L.total_tries;
+                    }
                     busy = false;
+                    if (lcc == 1 && L.qsign > 0 && p.charge > 0) {
+                        // partner with conjugate quantum numbers from the SAME cell
+                        L.qsign = -1;
+                        L.out_slot += 1;
+                        L.total_tries = 0;
+                        if (lane_new_setup(Ag, L, p, false, key0, key1)) busy = true;
+                        else my_range++;
+                    }
                 } else {
                     L.tries++;
-                    // partner sampling never re-picks the cell (do-while at FSSW.cpp:1039-1044)
-                    if (L.phase == 1 && L.tries >= MAX_IMPATIENCE) L.tries = 1;
+                    if (L.tries >= MAX_IMPATIENCE) {
+                        if (L.qsign > 0) {
+                            // the reference's "impatience" (FSSW.cpp:1017-1018 with status == 0)
+                            my_redraws++;
+                            if (!lane_new_setup(Ag, L, p, true, key0, key1)) {
+                                my_range++;
+                                busy = false;
+                            }
+                        } else {
+                            // partner sampling never re-picks the cell (do-while at FSSW.cpp:1039-1044)
+                            L.tries = 1;
+                        }
+                    }
                 }
             }
         }
@@ -872,10 +951,32 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         A.trace_tries = h->d_trace + h->trace_cap;
     }
 
-    const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
+    // task list of the batch
+    {
+        const size_t need = sizeof(Task)*static_cast<size_t>(total_work);
+        if (need > h->tasks_bytes || !h->d_tasks) {
+            if (h->d_tasks) cudaFree(h->d_tasks);
+            h->d_tasks = nullptr;
+            h->tasks_bytes = need + need/8 + 4096;
+            ISS_CUDA_TRY(h, cudaMalloc(&h->d_tasks, h->tasks_bytes));
+        }
+        A.tasks = static_cast<Task *>(h->d_tasks);
+    }
+    if (!h->d_sampler_args) ISS_CUDA_TRY(h, cudaMalloc(&h->d_sampler_args, sizeof(SamplerArgs)));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_sampler_args, &A, sizeof(SamplerArgs), cudaMemcpyHostToDevice,
+                                    h->stream));
     int dev = 0, nsm = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    {
+        ScopedTimer t(h, ISS_T_SAMPLE);
+        const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
+        int64_t grid = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
+        if (grid > static_cast<int64_t>(nsm)*32) grid = static_cast<int64_t>(nsm)*32;
+        setup_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
+    }
+    ISS_CUDA_TRY(h, cudaGetLastError());
+
     // register budget of the persistent kernel: MIN_BLOCKS CTAs of 4 warps per SM
     // (ISS_SAMPLER_MINB = 4, 5, 6 or 8 selects the variant; for tuning)
     static int minb = -1;
@@ -897,17 +998,18 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         force_generic = (e && atoi(e) == 1) ? 1 : 0;
     }
     if (force_generic) spec = 0;
-    void (*kern)(const SamplerArgs) = sampler_kernel<4, 0>;
-    if (minb == 5) {
-        kern = spec == 1 ? sampler_kernel<5, 1> : spec == 2 ? sampler_kernel<5, 2>
-             : spec == 3 ? sampler_kernel<5, 3> : sampler_kernel<5, 0>;
+    void (*kern)(const SamplerArgs, const SamplerArgs *) = propose_kernel<4, 0>;
+    if (minb == 8) {
+        kern = spec == 1 ? propose_kernel<8, 1> : spec == 2 ? propose_kernel<8, 2>
+             : spec == 3 ? propose_kernel<8, 3> : propose_kernel<8, 0>;
     } else if (minb == 6) {
-        kern = spec == 1 ? sampler_kernel<6, 1> : spec == 2 ? sampler_kernel<6, 2>
-             : spec == 3 ? sampler_kernel<6, 3> : sampler_kernel<6, 0>;
+        kern = spec == 1 ? propose_kernel<6, 1> : spec == 2 ? propose_kernel<6, 2>
+             : spec == 3 ? propose_kernel<6, 3> : propose_kernel<6, 0>;
     } else {
-        kern = spec == 1 ? sampler_kernel<4, 1> : spec == 2 ? sampler_kernel<4, 2>
-             : spec == 3 ? sampler_kernel<4, 3> : sampler_kernel<4, 0>;
+        kern = spec == 1 ? propose_kernel<4, 1> : spec == 2 ? propose_kernel<4, 2>
+             : spec == 3 ? propose_kernel<4, 3> : propose_kernel<4, 0>;
     }
+    const size_t smem = sizeof(DeviceSpecies)*ns;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SAMPLER_THREADS, smem);
     if (occ < 1) occ = 1;
     int64_t grid = static_cast<int64_t>(nsm)*occ;
@@ -915,7 +1017,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     if (grid > max_useful) grid = max_useful;
     {
         ScopedTimer t(h, ISS_T_SAMPLE);
-        kern<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(A); ISS_LAUNCHED(h);
+        kern<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(
+            A, static_cast<const SamplerArgs *>(h->d_sampler_args)); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     return ISS_OK;
