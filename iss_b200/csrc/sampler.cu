@@ -258,7 +258,7 @@ struct SamplerArgs {
 };
 
 constexpr int SETUP_THREADS = 256;
-constexpr int SAMPLER_THREADS = 128;
+constexpr int SAMPLER_THREADS = 768;     // one CTA of 24 warps per SM (96 KB of tables in smem)
 constexpr int TASK_CHUNK = 128;         // tasks a warp reserves at a time
 constexpr int MAX_IMPATIENCE = 5000;    // FSSW.cpp:1872
 
@@ -268,10 +268,19 @@ struct MomSetup {
     int tab, idx_min;
 };
 
+// F(i) = CDF_2[i] + w1 CDF_1[i] + w0 CDF_0[i] - m_term of one table point; SMEM: the table is the
+// CTA's shared-memory copy (regime-0 tables), otherwise global memory through the read-only path
+template <bool SMEM>
 __device__ __forceinline__ double table_F(const double *__restrict__ tb, int i, double w1,
                                           double w0, double m_term) {
-    const double2 a = __ldg(reinterpret_cast<const double2 *>(tb + 4*i));       // Et, C0
-    const double2 b = __ldg(reinterpret_cast<const double2 *>(tb + 4*i + 2));   // C1, C2
+    double2 a, b;
+    if (SMEM) {
+        a = *reinterpret_cast<const double2 *>(tb + 4*i);
+        b = *reinterpret_cast<const double2 *>(tb + 4*i + 2);
+    } else {
+        a = __ldg(reinterpret_cast<const double2 *>(tb + 4*i));       // Et, C0
+        b = __ldg(reinterpret_cast<const double2 *>(tb + 4*i + 2));   // C1, C2
+    }
     return b.y + w1*b.x + w0*a.y - m_term;
 }
 
@@ -320,7 +329,7 @@ __device__ __forceinline__ bool momentum_setup(const MomentumTable *__restrict__
     M.mu_tilde = mu_tilde;
     M.w0 = w0;
     M.m_term = m_term;
-    M.cdf_max = table_F(mt.data, idx_max, w1, w0, m_term);
+    M.cdf_max = table_F<false>(mt.data, idx_max, w1, w0, m_term);
     M.a_min = a;
     M.tab = tab;
     M.idx_min = static_cast<int>((a - mt.e0)/mt.de);
@@ -328,15 +337,17 @@ __device__ __forceinline__ bool momentum_setup(const MomentumTable *__restrict__
 }
 
 // MomentumSamplerBase::inverse_CDF (MomentumSamplerBase.cpp:61-93)
-__device__ __forceinline__ double inverse_cdf(const MomentumTable &mt, const MomSetup &M, double r) {
+template <bool SMEM>
+__device__ __forceinline__ double inverse_cdf(const double *__restrict__ tb, int n, const MomSetup &M,
+                                              double r) {
     const double w1 = 2.*M.mu_tilde;
     int lo = M.idx_min;
-    int hi = mt.n - 1;
-    double r_min = table_F(mt.data, lo, w1, M.w0, M.m_term);
+    int hi = n - 1;
+    double r_min = table_F<SMEM>(tb, lo, w1, M.w0, M.m_term);
     double r_max = M.cdf_max;
     while (hi - lo > 1) {
         const int mid = (hi + lo)/2;
-        const double r_mid = table_F(mt.data, mid, w1, M.w0, M.m_term);
+        const double r_mid = table_F<SMEM>(tb, mid, w1, M.w0, M.m_term);
         if (r < r_mid) {
             hi = mid;
             r_max = r_mid;
@@ -345,12 +356,12 @@ __device__ __forceinline__ double inverse_cdf(const MomentumTable &mt, const Mom
             r_min = r_mid;
         }
     }
-    double E0 = __ldg(mt.data + 4*lo);
+    double E0 = SMEM ? tb[4*lo] : __ldg(tb + 4*lo);
     if (E0 < M.a_min) {
         E0 = M.a_min;
         r_min = 0.;
     }
-    const double Ehi = __ldg(mt.data + 4*hi);
+    const double Ehi = SMEM ? tb[4*hi] : __ldg(tb + 4*hi);
     return E0 + (Ehi - E0)/fmax(1e-16, (r_max - r_min))*(r - r_min);
 }
 
@@ -523,9 +534,18 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     const int lcc = SM::generic ? A.lcc : SM::lcc;
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
 
-    extern __shared__ unsigned char smem_raw[];
+    // shared memory: species table, then the two regime-0 momentum tables (boson 32 KB, fermion
+    // 64 KB): they serve every species with (m - mu)/T < 30 and take the 11-step bisection of each
+    // proposal off the L1/LSU gather path
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
+    double *sm_boson = reinterpret_cast<double *>(sp + A.ns);
+    double *sm_fermion = sm_boson + 4*A.mt[0].n;
     for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
+    for (int i = threadIdx.x; i < 2*A.mt[0].n; i += blockDim.x)
+        reinterpret_cast<double2 *>(sm_boson)[i] = __ldg(reinterpret_cast<const double2 *>(A.mt[0].data) + i);
+    for (int i = threadIdx.x; i < 2*A.mt[3].n; i += blockDim.x)
+        reinterpret_cast<double2 *>(sm_fermion)[i] = __ldg(reinterpret_cast<const double2 *>(A.mt[3].data) + i);
     __syncthreads();
 
     const unsigned full = 0xffffffffu;
@@ -611,7 +631,10 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
             philox_block(L.rng.block++, L.rng.draw, L.rng.event, sample_stream_word3(L.s), key0, key1,
                          pw0, pw1, pw2, pw3);
             const double r = u53(pw0, pw1)*L.M.cdf_max;
-            const double Et = inverse_cdf(mt, L.M, r);
+            double Et;
+            if (L.M.tab == 0) Et = inverse_cdf<true>(sm_boson, mt.n, L.M, r);
+            else if (L.M.tab == 3) Et = inverse_cdf<true>(sm_fermion, mt.n, L.M, r);
+            else Et = inverse_cdf<false>(mt.data, mt.n, L.M, r);
             const double E_sample = L.M.T*Et + L.M.mu;
             const double p_mag = sqrt(E_sample*E_sample - mass*mass);
             const double accept_ratio = (p_mag/E_sample)/(1. - mass*mass/(2.*E_sample*E_sample));
@@ -977,13 +1000,6 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
 
-    // register budget of the persistent kernel: MIN_BLOCKS CTAs of 4 warps per SM
-    // (ISS_SAMPLER_MINB = 4, 5, 6 or 8 selects the variant; for tuning)
-    static int minb = -1;
-    if (minb < 0) {
-        const char *e = getenv("ISS_SAMPLER_MINB");
-        minb = e ? atoi(e) : 6;
-    }
     int spec = 0;
     if (A.hydro_mode == 2 && A.lcc != 1) {
         const bool ce = (A.mode.kind == 21 && A.mode.include_shear == 1 && A.mode.include_bulk == 1);
@@ -998,23 +1014,16 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         force_generic = (e && atoi(e) == 1) ? 1 : 0;
     }
     if (force_generic) spec = 0;
-    void (*kern)(const SamplerArgs, const SamplerArgs *) = propose_kernel<4, 0>;
-    if (minb == 8) {
-        kern = spec == 1 ? propose_kernel<8, 1> : spec == 2 ? propose_kernel<8, 2>
-             : spec == 3 ? propose_kernel<8, 3> : propose_kernel<8, 0>;
-    } else if (minb == 6) {
-        kern = spec == 1 ? propose_kernel<6, 1> : spec == 2 ? propose_kernel<6, 2>
-             : spec == 3 ? propose_kernel<6, 3> : propose_kernel<6, 0>;
-    } else {
-        kern = spec == 1 ? propose_kernel<4, 1> : spec == 2 ? propose_kernel<4, 2>
-             : spec == 3 ? propose_kernel<4, 3> : propose_kernel<4, 0>;
-    }
-    const size_t smem = sizeof(DeviceSpecies)*ns;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SAMPLER_THREADS, smem);
-    if (occ < 1) occ = 1;
-    int64_t grid = static_cast<int64_t>(nsm)*occ;
-    const int64_t max_useful = (total_work + 31)/32/(SAMPLER_THREADS/32) + 1;
+    void (*kern)(const SamplerArgs, const SamplerArgs *) =
+        spec == 1 ? propose_kernel<1, 1> : spec == 2 ? propose_kernel<1, 2>
+        : spec == 3 ? propose_kernel<1, 3> : propose_kernel<1, 0>;
+    const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(double)*4*(A.mt[0].n + A.mt[3].n);
+    ISS_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
+    int64_t grid = nsm;         // persistent: one CTA per SM
+    const int64_t max_useful = (total_work + SAMPLER_THREADS - 1)/SAMPLER_THREADS;
     if (grid > max_useful) grid = max_useful;
+    (void)occ;
     {
         ScopedTimer t(h, ISS_T_SAMPLE);
         kern<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(
