@@ -541,6 +541,30 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
     double *sm_boson = reinterpret_cast<double *>(sp + A.ns);
     double *sm_fermion = sm_boson + 4*A.mt[0].n;
+    // per-lane copy of the cell fields every try reads (dsigma, thermodynamics, pi, q, delta-f
+    // coefficients): written once per hadron at task hand-over, so that the tries do not depend
+    // on the (small, table-squeezed) L1 keeping 768 scattered 128-byte cell records resident
+    float4 *lc_da = reinterpret_cast<float4 *>(sm_fermion + 4*A.mt[3].n);
+    float4 *lc_th0 = lc_da + SAMPLER_THREADS;
+    float4 *lc_th = lc_th0 + SAMPLER_THREADS;
+    float4 *lc_pa = lc_th + SAMPLER_THREADS;
+    float4 *lc_pb = lc_pa + SAMPLER_THREADS;
+    double2 *lc_c01 = reinterpret_cast<double2 *>(lc_pb + SAMPLER_THREADS);
+    double2 *lc_c2k = lc_c01 + SAMPLER_THREADS;
+    const int tid = threadIdx.x;
+    LaneState L;
+    L.qsign = 1;
+    auto fill_lane_cache = [&](const float4 *cr, const float4 &da, const float4 &th0, const float4 &th) {
+        const double2 *cop = reinterpret_cast<const double2 *>(
+            A.cellcoef + static_cast<int64_t>(L.cell)*COEF_STRIDE);
+        lc_da[tid] = da;
+        lc_th0[tid] = th0;
+        lc_th[tid] = th;
+        lc_pa[tid] = __ldg(cr + 5);             // pixx, pixy, pixz, piyy
+        lc_pb[tid] = __ldg(cr + 6);             // piyz, qx, qy, qz
+        lc_c01[tid] = __ldg(cop);               // c0, c1
+        lc_c2k[tid] = make_double2(__ldg(&cop[1].x), __ldg(&cop[3].x));   // c2, kappa
+    };
     for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
     for (int i = threadIdx.x; i < 2*A.mt[0].n; i += blockDim.x)
         reinterpret_cast<double2 *>(sm_boson)[i] = __ldg(reinterpret_cast<const double2 *>(A.mt[0].data) + i);
@@ -552,8 +576,6 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    LaneState L;
-    L.qsign = 1;
     bool busy = false;
     int64_t chunk_next = 0, chunk_end = 0;      // tasks reserved by this warp
     bool more_work = true;
@@ -601,6 +623,7 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                     const float4 da = __ldg(cr + 1);
                     const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
                     const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
+                    fill_lane_cache(cr, da, th0, th);
                     // float arithmetic inside the sqrt as in FSSW.cpp:1867-1870
                     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
                                                __fmul_rn(da.w, da.w));
@@ -659,7 +682,7 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 const double pz = p_mag*cos_theta;
                 const float4 *cr = reinterpret_cast<const float4 *>(
                     A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
-                const float4 da = __ldg(cr + 1);
+                const float4 da = lc_da[tid];
                 const double pdsigma = p0*da.x + px*da.y + py*da.z + pz*da.w;
                 double fact1 = pdsigma/p0/L.dsigma_fac;
                 fact1 = fmax(0., fmin(1., fact1));
@@ -672,20 +695,21 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                     const double stat = 1. - sign*f0;
                     double delta_f = 0.;
                     if (mode.include_shear | mode.include_bulk | mode.include_diff) {
-                        const float4 th0 = __ldg(cr + 3);   // E, T, P, nB
-                        const float4 th = __ldg(cr + 4);    // muB, muS, muQ, bulkPi
+                        const float4 th0 = lc_th0[tid];     // E, T, P, nB
+                        const float4 th = lc_th[tid];       // muB, muS, muQ, bulkPi
                         const double *__restrict__ co = A.cellcoef + static_cast<int64_t>(L.cell)*COEF_STRIDE;
+                        const double2 c01 = lc_c01[tid], c2k = lc_c2k[tid];
                         const int B = L.qsign*p.baryon, S = L.qsign*p.strange, Q = L.qsign*p.charge;
                         if (mode.include_shear == 1) {
-                            const float4 pa = __ldg(cr + 5);    // pixx, pixy, pixz, piyy
-                            const float4 pb = __ldg(cr + 6);    // piyz, qx, qy, qz
+                            const float4 pa = lc_pa[tid];       // pixx, pixy, pixz, piyy
+                            const float4 pb = lc_pb[tid];       // piyz, qx, qy, qz
                             const double Wfactor = (px*px*pa.x + 2.*px*py*pa.y + 2.*px*pz*pa.z
                                                     + py*py*pa.w + 2.*py*pz*pb.x
                                                     + pz*pz*(-pa.x - pa.w));
                             if (mode.neos == 1) {
-                                delta_f += stat*Wfactor/(2.*__ldg(&co[2]))/(p0*L.M.T);
+                                delta_f += stat*Wfactor/(2.*c2k.x)/(p0*L.M.T);
                             } else if (mode.neos == 0) {
-                                delta_f += stat*Wfactor*__ldg(&co[0]);
+                                delta_f += stat*Wfactor*c01.x;
                             } else {
                                 const double Tdec = th0.y;
                                 const double pref = 1.0/(2.0*Tdec*Tdec
@@ -702,27 +726,26 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                                                           : static_cast<double>(th.w)/HBARC;
                                 const double E_over_T = p0/Tdec;
                                 const double mass_over_T = mass/Tdec;
-                                delta_f += (-1.0*stat*__ldg(&co[0])
+                                delta_f += (-1.0*stat*c01.x
                                             *(mass_over_T*mass_over_T/(3.*E_over_T)
-                                              - __ldg(&co[1])*E_over_T)*bulkPi);
+                                              - c01.y*E_over_T)*bulkPi);
                             } else if (mode.kind == 11) {
                                 const double bulkPi = th.w;
-                                delta_f += stat*bulkPi*(__ldg(&co[0])*mass*mass + __ldg(&co[1])*B*p0
-                                                        + __ldg(&co[2])*p0*p0);
+                                delta_f += stat*bulkPi*(c01.x*mass*mass + c01.y*B*p0 + c2k.x*p0*p0);
                             } else if (mode.kind == 20) {
                                 const double bulkPi = th.w;
-                                delta_f += stat*bulkPi*(mass*mass*__ldg(&co[2])
+                                delta_f += stat*bulkPi*(mass*mass*c2k.x
                                                         + p0*(B*__ldg(&co[3]) + S*__ldg(&co[4])
                                                               + Q*__ldg(&co[5]))
-                                                        + p0*p0*(__ldg(&co[1]) - __ldg(&co[2])));
+                                                        + p0*p0*(c01.y - c2k.x));
                             }
                         }
                         if (mode.include_diff == 1) {
-                            const float4 pb = __ldg(cr + 6);    // piyz, qx, qy, qz
+                            const float4 pb = lc_pb[tid];       // piyz, qx, qy, qz
                             // float division as in FSSW.cpp:1866
                             const double prefactor_qmu = __fdiv_rn(th0.w, __fadd_rn(th0.x, th0.z));
                             const double qmufactor = -px*pb.y - py*pb.z - pz*pb.w;
-                            delta_f += stat*(prefactor_qmu - B/p0)*qmufactor/__ldg(&co[6]);
+                            delta_f += stat*(prefactor_qmu - B/p0)*qmufactor/c2k.y;
                         }
                     }
                     double fact2 = (1. + delta_f)/2.;
@@ -810,6 +833,10 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                             if (!lane_new_setup(Ag, L, p, true, key0, key1)) {
                                 my_range++;
                                 busy = false;
+                            } else {
+                                const float4 *cr2 = reinterpret_cast<const float4 *>(
+                                    A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
+                                fill_lane_cache(cr2, __ldg(cr2 + 1), __ldg(cr2 + 3), __ldg(cr2 + 4));
                             }
                         } else {
                             // partner sampling never re-picks the cell (do-while at FSSW.cpp:1039-1044)
@@ -1017,7 +1044,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     void (*kern)(const SamplerArgs, const SamplerArgs *) =
         spec == 1 ? propose_kernel<1, 1> : spec == 2 ? propose_kernel<1, 2>
         : spec == 3 ? propose_kernel<1, 3> : propose_kernel<1, 0>;
-    const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(double)*4*(A.mt[0].n + A.mt[3].n);
+    const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(double)*4*(A.mt[0].n + A.mt[3].n)
+                        + (5*sizeof(float4) + 2*sizeof(double2))*SAMPLER_THREADS;
     ISS_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     int64_t grid = nsm;         // persistent: one CTA per SM
