@@ -46,6 +46,7 @@ BYTES_PER_HADRON = 152.0     # 40 B record out + 112 B cell record in
 FLOP_PER_HADRON = 1.0e3
 BYTES_PER_YIELD = 8.2        # 8 B FP64 yield out + 64 B of cell fields / 321 species
 FLOP_PER_YIELD = 175.0       # CE bulk + diffusion series
+NCU_PROPOSE_TRAFFIC_BYTES = None   # filled from the committed ncu capture (see profiles/)
 
 
 def load_peaks():
@@ -232,12 +233,17 @@ def run_engine(args):
     yields_s = fam_ms["yields"]*1e-3
     n_launch_sample = max(1, int(fam_n["sample"]))
     roof = {
-        "kernel": "sampler_kernel (persistent momentum sampler + boost/emit)",
+        "kernel": "propose_kernel (persistent momentum sampler fused with boost/emit); the set-up "
+                  "kernel that feeds it is timed separately (kernel_ms.setup)",
         "bound": "hbm",
         "achieved": BYTES_PER_HADRON*hadrons/sample_s/1e9 if sample_s > 0 else None,
         "peak": peaks["hbm_gbs"], "unit": "GB/s",
         "frac": (BYTES_PER_HADRON*hadrons/sample_s/1e9/peaks["hbm_gbs"]) if sample_s > 0 else None,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, from the
+        # ncu --set full capture summarised in profiles/ (static evidence, not measured here)
+        "traffic": NCU_PROPOSE_TRAFFIC_BYTES if (args.cells == 1000000 and E == 1000) else None,
+        "traffic_source": "profiles/r1_ncu_final.csv",
+        "algorithmic_bytes_per_launch": BYTES_PER_HADRON*hadrons/max(1, n_launch_sample),
         "peak_source": peak_src,
         "avg_launch_ms": fam_ms["sample"]/n_launch_sample,
         "share_of_step": fam_ms["sample"]/ms if ms > 0 else None,

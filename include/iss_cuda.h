@@ -234,7 +234,8 @@ ISS_API int iss_cuda_qa_device_ptr(iss_handle *h, void **dptr);
 ISS_API int iss_cuda_qa_fetch(iss_handle *h, double *dst_host);
 
 /* ---- timing: accumulated device time (CUDA events on the handle's stream) per kernel family */
-enum { ISS_T_YIELDS = 0, ISS_T_SCAN, ISS_T_MULT, ISS_T_SAMPLE, ISS_T_DECAY, ISS_T_QA, ISS_T_NKIND };
+enum { ISS_T_YIELDS = 0, ISS_T_SCAN, ISS_T_MULT, ISS_T_SAMPLE /* proposal kernel */, ISS_T_DECAY,
+       ISS_T_QA, ISS_T_SETUP /* sampler set-up kernel */, ISS_T_NKIND };
 ISS_API int iss_cuda_timing(iss_handle *h, int enable, double *ms_host /*[ISS_T_NKIND]*/,
                     int64_t *launches_host /*[ISS_T_NKIND]*/, int reset);
 

@@ -55,6 +55,7 @@ void free_surface(iss_handle *h) {
     cudaFree(h->d_tilesum); h->d_tilesum = nullptr; h->tilesum_bytes = 0;
     cudaFree(h->d_tilebase); h->d_tilebase = nullptr; h->tilebase_bytes = 0;
     cudaFree(h->d_total); h->d_total = nullptr; h->total_bytes = 0;
+    cudaFree(h->d_cdflev); h->d_cdflev = nullptr; h->cdflev_bytes = 0;
     h->have_yields = false;
     h->have_batch = false;
 }

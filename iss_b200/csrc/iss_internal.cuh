@@ -107,6 +107,11 @@ struct iss_handle {
     double *d_tilesum = nullptr;        // [ns][ntile]
     double *d_tilebase = nullptr;       // [ns][ntile+1]    exclusive prefix over tiles
     double *d_total = nullptr;          // [ns]
+    // 16-ary search levels over the global inclusive prefix d_cdf: level k (k >= 1) holds every
+    // 16^k-th prefix value; all levels of one species are contiguous, padded to multiples of 16
+    double *d_cdflev = nullptr; size_t cdflev_bytes = 0;
+    int nlev = 0;                       // number of levels above the prefix itself
+    int64_t lev_n[8] = {0}, lev_off[8] = {0}, lev_stride = 0;
     size_t yields_bytes = 0, cdf_bytes = 0, tilesum_bytes = 0, tilebase_bytes = 0, total_bytes = 0;
     bool have_yields = false;
     std::vector<double> h_total;        // dN per species (3+1D sum)

@@ -236,8 +236,11 @@ struct SamplerArgs {
     const float *cells;             // [ncell][CELL_STRIDE]
     const double *cellcoef;         // [ncell][COEF_STRIDE]
     int64_t ncell, ncell_pad, ntile;
-    const double *cdf;              // [ns][ncell_pad] tile-local inclusive scan
+    const double *cdf;              // [ns][ncell_pad] global inclusive prefix of the yields
     const double *tilebase;         // [ns][ntile+1]
+    const double *cdflev;           // [ns][lev_stride] 16-ary search levels over cdf
+    int nlev;
+    int64_t lev_off[8], lev_stride;
     const double *total;            // [ns]
     const DeviceSpecies *species;
     int ns;
@@ -365,26 +368,30 @@ __device__ __forceinline__ double inverse_cdf(const double *__restrict__ tb, int
     return E0 + (Ehi - E0)/fmax(1e-16, (r_max - r_min))*(r - r_min);
 }
 
-// RandomVariable1DArray::rand (two-level: tile prefix, then tile-local inclusive scan)
+// number of entries < v among the 16 sorted doubles of one 128-byte node whose last entry is
+// known to be >= v: four dependent loads inside one cache line
+__device__ __forceinline__ int count_below_16(const double *__restrict__ node, double v) {
+    int c = 0;
+    c += (__ldg(&node[c + 7]) < v) ? 8 : 0;
+    c += (__ldg(&node[c + 3]) < v) ? 4 : 0;
+    c += (__ldg(&node[c + 1]) < v) ? 2 : 0;
+    c += (__ldg(&node[c]) < v) ? 1 : 0;
+    return c;
+}
+
+// RandomVariable1DArray::rand (RandomVariable1DArray.cpp:63-67): v = (sum - 1e-15) u, cell =
+// largest i with CDF[i] < v where CDF is the exclusive prefix, i.e. the number of inclusive-prefix
+// entries below v.  The reference bisects the whole array (arsenal.cpp:644-678); here the same
+// count is obtained by descending a 16-ary tree of sampled prefix values: one 128-byte node per
+// level, five levels for 10^6 cells.
 __device__ __forceinline__ int64_t pick_cell(const SamplerArgs &A, int s, double u) {
     const double total = __ldg(&A.total[s]);
     const double v = (total - 1e-15)*u;
-    const double *__restrict__ tb = A.tilebase + static_cast<int64_t>(s)*(A.ntile + 1);
-    // largest t with tb[t] < v  (tb[0] = 0)
-    int64_t lo = 0, hi = A.ntile;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(&tb[mid]) < v) lo = mid; else hi = mid;
-    }
-    const double vt = v - __ldg(&tb[lo]);
-    const double *__restrict__ c = A.cdf + static_cast<int64_t>(s)*A.ncell_pad + lo*TILE;
-    // smallest j in [0, TILE) with c[j] >= vt
-    int l = -1, r = TILE - 1;
-    while (r - l > 1) {
-        const int mid = (l + r) >> 1;
-        if (__ldg(&c[mid]) < vt) l = mid; else r = mid;
-    }
-    int64_t cell = lo*TILE + r;
+    const double *__restrict__ lev = A.cdflev + static_cast<int64_t>(s)*A.lev_stride;
+    int64_t q = 0;
+    for (int k = A.nlev; k >= 1; k--) q = 16*q + count_below_16(lev + A.lev_off[k] + 16*q, v);
+    const double *__restrict__ P = A.cdf + static_cast<int64_t>(s)*A.ncell_pad;
+    int64_t cell = 16*q + count_below_16(P + 16*q, v);
     if (cell >= A.ncell) cell = A.ncell - 1;
     return cell;
 }
@@ -966,6 +973,10 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.ntile = h->ntile;
     A.cdf = h->d_cdf;
     A.tilebase = h->d_tilebase;
+    A.cdflev = h->d_cdflev;
+    A.nlev = h->nlev;
+    for (int k = 0; k < 8; k++) A.lev_off[k] = h->lev_off[k];
+    A.lev_stride = h->lev_stride;
     A.total = h->d_total;
     A.species = h->d_species;
     A.ns = ns;
@@ -1019,7 +1030,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     {
-        ScopedTimer t(h, ISS_T_SAMPLE);
+        ScopedTimer t(h, ISS_T_SETUP);
         const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
         int64_t grid = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
         if (grid > static_cast<int64_t>(nsm)*32) grid = static_cast<int64_t>(nsm)*32;

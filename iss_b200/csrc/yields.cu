@@ -284,6 +284,44 @@ __global__ void tile_base_kernel(const double *__restrict__ tilesum, double *__r
     }
 }
 
+// K3d: tile-local inclusive scan + tile base -> global inclusive prefix P (in place), and level 1
+// of the 16-ary search tree: L1[j] = P[16 j + 15].  One thread per pair of cells.
+__global__ void __launch_bounds__(256)
+cdf_finalize_kernel(double *__restrict__ cdf, const double *__restrict__ tilebase,
+                    double *__restrict__ lev, int64_t ncell_pad, int64_t ntile, int64_t lev_stride) {
+    const int s = blockIdx.y;
+    const int64_t t = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;    // pair index
+    if (2*t >= ncell_pad) return;
+    const int64_t tile = (2*t)/TILE;
+    const double base = __ldg(&tilebase[static_cast<int64_t>(s)*(ntile + 1) + tile]);
+    double2 *p = reinterpret_cast<double2 *>(cdf + static_cast<int64_t>(s)*ncell_pad) + t;
+    double2 v = *p;
+    v.x += base;
+    v.y += base;
+    *p = v;
+    if ((t & 7) == 7) lev[static_cast<int64_t>(s)*lev_stride + (t >> 3)] = v.y;
+}
+
+// K3e: level k >= 2 from level k-1 (every 16th entry); entries past the end read as the total
+__global__ void cdf_level_kernel(double *__restrict__ lev, const double *__restrict__ total,
+                                 int64_t lev_stride, int64_t off_prev, int64_t n_prev,
+                                 int64_t off_cur, int64_t n_cur_padded) {
+    const int s = blockIdx.y;
+    const int64_t j = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (j >= n_cur_padded) return;
+    double *L = lev + static_cast<int64_t>(s)*lev_stride;
+    const int64_t src = 16*j + 15;
+    L[off_cur + j] = (src < n_prev) ? L[off_prev + src] : __ldg(&total[s]);
+}
+
+// pads level 1 beyond its last real entry
+__global__ void cdf_level_pad_kernel(double *__restrict__ lev, const double *__restrict__ total,
+                                     int64_t lev_stride, int64_t off, int64_t n, int64_t n_padded) {
+    const int s = blockIdx.x;
+    for (int64_t j = n + threadIdx.x; j < n_padded; j += blockDim.x)
+        lev[static_cast<int64_t>(s)*lev_stride + off + j] = __ldg(&total[s]);
+}
+
 // fills the K_n / E_n grids on the device (FSSW::initialize_special_function_arrays)
 __global__ void build_sf_tables_kernel(double *bessel, double *expint, SfGrid g, int with_bulk,
                                        int with_diff) {
@@ -374,6 +412,22 @@ int run_yields(iss_handle *h) {
     ISS_ENSURE(h, h->d_tilesum, h->tilesum_bytes, sizeof(double)*ns*h->ntile);
     ISS_ENSURE(h, h->d_tilebase, h->tilebase_bytes, sizeof(double)*ns*(h->ntile + 1));
     ISS_ENSURE(h, h->d_total, h->total_bytes, sizeof(double)*ns);
+    {
+        // geometry of the 16-ary search levels (level 0 = the prefix itself, ncell_pad entries)
+        int64_t n_prev = h->ncell_pad, off = 0;
+        h->nlev = 0;
+        while (n_prev > 16 && h->nlev < 7) {
+            const int64_t n = (n_prev + 15)/16;
+            const int64_t n_padded = (n + 15)/16*16;
+            const int k = ++h->nlev;
+            h->lev_n[k] = n;
+            h->lev_off[k] = off;
+            off += n_padded;
+            n_prev = n;
+        }
+        h->lev_stride = off > 0 ? off : 16;
+        ISS_ENSURE(h, h->d_cdflev, h->cdflev_bytes, sizeof(double)*ns*h->lev_stride);
+    }
     ISS_ENSURE(h, h->d_cellcoef, h->coef_bytes, sizeof(double)*COEF_STRIDE*h->ncell);
 
     YieldArgs a;
@@ -427,6 +481,26 @@ int run_yields(iss_handle *h) {
                                                       h->ncell, h->ncell_pad, h->ntile); ISS_LAUNCHED(h);
         tile_base_kernel<<<static_cast<unsigned>(ns), 32, 0, h->stream>>>(
             h->d_tilesum, h->d_tilebase, h->d_total, h->ntile); ISS_LAUNCHED(h);
+        {
+            const int64_t npair = h->ncell_pad/2;
+            dim3 g2(static_cast<unsigned>((npair + 255)/256), static_cast<unsigned>(ns));
+            cdf_finalize_kernel<<<g2, 256, 0, h->stream>>>(h->d_cdf, h->d_tilebase, h->d_cdflev,
+                                                           h->ncell_pad, h->ntile, h->lev_stride); ISS_LAUNCHED(h);
+        }
+        if (h->nlev >= 1) {
+            const int64_t n1p = (h->lev_n[1] + 15)/16*16;
+            if (n1p > h->lev_n[1]) {
+                cdf_level_pad_kernel<<<static_cast<unsigned>(ns), 32, 0, h->stream>>>(
+                    h->d_cdflev, h->d_total, h->lev_stride, h->lev_off[1], h->lev_n[1], n1p); ISS_LAUNCHED(h);
+            }
+        }
+        for (int k = 2; k <= h->nlev; k++) {
+            const int64_t np_ = (h->lev_n[k] + 15)/16*16;
+            dim3 g3(static_cast<unsigned>((np_ + 127)/128), static_cast<unsigned>(ns));
+            cdf_level_kernel<<<g3, 128, 0, h->stream>>>(h->d_cdflev, h->d_total, h->lev_stride,
+                                                        h->lev_off[k - 1], h->lev_n[k - 1],
+                                                        h->lev_off[k], np_); ISS_LAUNCHED(h);
+        }
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     h->h_total.resize(ns);
