@@ -119,6 +119,11 @@ def run_engine(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    # Everything below that writes to file descriptor 1 (the facade logs like the reference, NCCL
+    # prints its version) goes to stderr; the real stdout is kept for the single JSON line.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     os.environ["ISS_CUDA_DEVICE"] = str(local)
     if world > 1:
@@ -133,10 +138,6 @@ def run_engine(args):
     E = args.events_per_step
     work = tempfile.mkdtemp(prefix="iss_bench_r%d_" % rank)
     make_case(work, args.cells)
-    saved_stdout = os.dup(1)
-    sys.stdout.flush()
-    os.dup2(2, 1)                # the facade logs to stdout like the reference: send that to stderr
-                                 # and keep the real stdout for the JSON line
     try:
         over = dict(OVERRIDES, number_of_repeated_sampling=E)
         s = capi.Sampler(work, PARAM, "surface.dat", **over)
