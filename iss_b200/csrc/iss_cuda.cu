@@ -235,6 +235,8 @@ int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t n
         const iss_species &p = species[i];
         DeviceSpecies &d = ds[i];
         d.mass = p.mass;
+        d.mass2 = p.mass*p.mass;
+        d.inv_mass = 1.0/p.mass;
         d.pid = p.pid;
         d.gspin = static_cast<int16_t>(p.gspin);
         d.baryon = static_cast<int16_t>(p.baryon);

@@ -47,8 +47,10 @@ constexpr int CELL_T = 28;        // tau*cosh(eta)
 constexpr int CELL_Z = 29;        // tau*sinh(eta)
 constexpr int COEF_STRIDE = 8;
 
-struct DeviceSpecies {      // what the kernels read per species (smem-friendly, 32 B)
+struct DeviceSpecies {      // what the kernels read per species (smem-friendly, 48 B)
     double mass;
+    double mass2;           // mass*mass
+    double inv_mass;        // 1/mass
     int32_t pid;
     int16_t gspin, baryon, strange, charge, sign;
     int16_t trunc10_mass;   // 1 if mass < 0.7 (series of 10 terms when also T > 0.05)

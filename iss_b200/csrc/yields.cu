@@ -124,17 +124,27 @@ yields_kernel(const YieldArgs a) {
     const double inv_dx = 1.0/sf.dx;
     const double2 *__restrict__ sf2 = reinterpret_cast<const double2 *>(a.sf4);
     const double common = unit_factor/(2.*M_PI*M_PI);
+    // per-cell powers of T: the reference divides by beta = 1/T (FSSW.cpp:812-847); multiplying by
+    // T instead differs by one rounding (~1e-16 relative) and removes every division from the
+    // species loop
+    const double T2 = temp*temp;
+    const double T3_over_3 = T2*temp/3.;
+    const double sigma = common*dsigma_dot_u;
+    const double q_pref = with_diff ? common*dsigma_dot_q/cc.kappa : 0.;
 
+#pragma unroll 2
     for (int is = 0; is < s_end - s_begin; is++) {
         const DeviceSpecies p = sp[is];
         const double mass = p.mass;
         const double lambda = lam_smem[p.combo*YIELD_THREADS + threadIdx.x];
         const int truncate_order = (p.trunc10_mass && hot) ? 10 : 1;
         const double mbeta = mass*beta;
+        const double T_over_m = temp*p.inv_mass;
 
         double N_eq = 0., b1 = 0., b2 = 0., b3 = 0., q2 = 0.;
         double theta = 1.0, fugacity = 1.0;
         for (int n = 1; n <= truncate_order; n++) {
+            const double inv_n = (n == 1) ? 1.0 : 1.0/n;
             const double arg = n*mass*beta;
             if (n > 1) theta *= -static_cast<double>(p.sign);
             fugacity *= lambda;
@@ -165,7 +175,6 @@ yields_kernel(const YieldArgs a) {
                 }
             }
             const double tf = theta*fugacity;
-            const double inv_n = 1.0/n;
             N_eq += tf*inv_n*K_2;
             if (bulk_ce) {
                 b1 += tf*(mbeta*K_1 + 3*K_2*inv_n);
@@ -176,45 +185,33 @@ yields_kernel(const YieldArgs a) {
                 b3 += tf*(mbeta*K_2 + 3*K_3*inv_n);
             }
             if (with_diff) {
-                // FSSW.cpp:784-808
-                const double ra = 1.0/arg;
+                // FSSW.cpp:784-808 with 1/arg = T/(n m)
+                const double ra = T_over_m*inv_n;
                 const double I_1_n = exp(-arg)*ra*(2.*ra*ra + 2.*ra - 0.5) + I_tab;
                 q2 += n*tf*(-(mbeta*mbeta*mbeta)*I_1_n);
             }
         }
-        // FSSW.cpp:812-847; the equilibrium series doubles as the first diffusion term
-        const double q1 = mass*mass/(beta*beta)*N_eq;
-        N_eq = mass*mass*temp*N_eq;
-        if (bulk_ce) {
-            b1 = mass*mass/beta*b1;
-            b2 = mass*mass*mass/3.*b2;
-        } else if (bulk_mom) {
-            b1 = mass*mass/beta*b1;
-            b2 = mass*mass/(beta*beta)*b2;
-            b3 = mass*mass*mass/(beta*beta)*b3;
-        }
-
-        // FSSW.cpp:656-706
-        const double pref = common*p.gspin;
-        double total = pref*dsigma_dot_u*N_eq;
+        // FSSW.cpp:812-847 and 656-706; the equilibrium series doubles as the first diffusion term
+        const double m2 = p.mass2;
+        const double pref = p.gspin;
+        double total = sigma*m2*temp*N_eq;
         if (m.include_bulk == 1) {
             if (bulk_ce) {
-                total += pref*dsigma_dot_u*(-bulkPi*cc.c[0])*(-cc.c[1]*b1 + b2);
+                total += sigma*(-bulkPi*cc.c[0])*(-cc.c[1]*(m2*temp*b1) + m2*mass*(1./3.)*b2);
             } else if (m.kind == 11) {
-                total += pref*dsigma_dot_u*bulkPi
-                         *(b1*mass*mass*cc.c[0] + b2*p.baryon*cc.c[1] + b3*cc.c[2]);
+                total += sigma*bulkPi*((m2*temp*b1)*m2*cc.c[0] + (m2*T2*b2)*p.baryon*cc.c[1]
+                                       + (m2*mass*T2*b3)*cc.c[2]);
             } else if (m.kind == 20) {
-                total += pref*dsigma_dot_u*bulkPi
-                         *(b1*mass*mass*cc.c[2]
-                           + b2*(p.baryon*cc.c[3] + p.strange*cc.c[4] + p.charge*cc.c[5])
-                           + b3*(cc.c[1] - cc.c[2]));
+                total += sigma*bulkPi*((m2*temp*b1)*m2*cc.c[2]
+                                       + (m2*T2*b2)*(p.baryon*cc.c[3] + p.strange*cc.c[4]
+                                                     + p.charge*cc.c[5])
+                                       + (m2*mass*T2*b3)*(cc.c[1] - cc.c[2]));
             }
         }
         if (with_diff) {
-            total += pref*dsigma_dot_q/cc.kappa
-                     *(-prefactor_qmu*q1 - p.baryon*(1./(3.*beta*beta*beta)*q2));
+            total += q_pref*(-prefactor_qmu*(m2*T2*N_eq) - p.baryon*(T3_over_3*q2));
         }
-        a.yields[static_cast<int64_t>(s_begin + is)*np + cell] = fmax(0., total);
+        a.yields[static_cast<int64_t>(s_begin + is)*np + cell] = fmax(0., pref*total);
     }
 }
 
