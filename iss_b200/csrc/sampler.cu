@@ -552,25 +552,41 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     // coefficients): written once per hadron at task hand-over, so that the tries do not depend
     // on the (small, table-squeezed) L1 keeping 768 scattered 128-byte cell records resident
     float4 *lc_da = reinterpret_cast<float4 *>(sm_fermion + 4*A.mt[3].n);
-    float4 *lc_th0 = lc_da + SAMPLER_THREADS;
-    float4 *lc_th = lc_th0 + SAMPLER_THREADS;
-    float4 *lc_pa = lc_th + SAMPLER_THREADS;
+    float4 *lc_pa = lc_da + SAMPLER_THREADS;
     float4 *lc_pb = lc_pa + SAMPLER_THREADS;
-    double2 *lc_c01 = reinterpret_cast<double2 *>(lc_pb + SAMPLER_THREADS);
-    double2 *lc_c2k = lc_c01 + SAMPLER_THREADS;
+    // derived per-(cell, species) doubles, [k][lane]: every division of the accept test that does
+    // not depend on the proposed momentum is done once per hadron here
+    double *lc_d = reinterpret_cast<double *>(lc_pb + SAMPLER_THREADS);
+    enum { D_INV_T = 0, D_INV_DSIG, D_SHEAR, D_CB, D_C1, D_INV_KAPPA, D_PREFQ, D_COUNT };
     const int tid = threadIdx.x;
     LaneState L;
     L.qsign = 1;
     auto fill_lane_cache = [&](const float4 *cr, const float4 &da, const float4 &th0, const float4 &th) {
         const double2 *cop = reinterpret_cast<const double2 *>(
             A.cellcoef + static_cast<int64_t>(L.cell)*COEF_STRIDE);
+        const double2 c01 = __ldg(cop);                     // c0, c1
+        const double c2 = __ldg(&cop[1].x), kappa = __ldg(&cop[3].x);
         lc_da[tid] = da;
-        lc_th0[tid] = th0;
-        lc_th[tid] = th;
         lc_pa[tid] = __ldg(cr + 5);             // pixx, pixy, pixz, piyy
         lc_pb[tid] = __ldg(cr + 6);             // piyz, qx, qy, qz
-        lc_c01[tid] = __ldg(cop);               // c0, c1
-        lc_c2k[tid] = make_double2(__ldg(&cop[1].x), __ldg(&cop[3].x));   // c2, kappa
+        const double Tdec = th0.y;
+        lc_d[D_INV_T*SAMPLER_THREADS + tid] = 1.0/L.M.T;
+        lc_d[D_INV_DSIG*SAMPLER_THREADS + tid] = 1.0/L.dsigma_fac;
+        // shear delta f prefactor (FSSW.cpp:1898-1913): CE W/(2 eta_hat p0 T), 22-moment W c0,
+        // otherwise W/(2 T^2 (e+P))
+        double sh;
+        if (mode.neos == 1) sh = 1.0/(2.*c2);
+        else if (mode.neos == 0) sh = c01.x;
+        else sh = 1.0/(2.0*Tdec*Tdec*(static_cast<double>(__fadd_rn(th0.x, th0.z))));
+        lc_d[D_SHEAR*SAMPLER_THREADS + tid] = sh;
+        // CE bulk delta f (kinds 1, 21): c0 * Pi with Pi in GeV/fm^3 (21) or fm^-4 (1)
+        const double bulkPi = (mode.kind == 21) ? static_cast<double>(th.w)
+                                                : static_cast<double>(th.w)/HBARC;
+        lc_d[D_CB*SAMPLER_THREADS + tid] = c01.x*bulkPi;
+        lc_d[D_C1*SAMPLER_THREADS + tid] = c01.y;
+        lc_d[D_INV_KAPPA*SAMPLER_THREADS + tid] = 1.0/kappa;
+        // float division as in FSSW.cpp:1866
+        lc_d[D_PREFQ*SAMPLER_THREADS + tid] = __fdiv_rn(th0.w, __fadd_rn(th0.x, th0.z));
     };
     for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
     for (int i = threadIdx.x; i < 2*A.mt[0].n; i += blockDim.x)
@@ -582,7 +598,6 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
-
     bool busy = false;
     int64_t chunk_next = 0, chunk_end = 0;      // tasks reserved by this warp
     bool more_work = true;
@@ -630,13 +645,13 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                     const float4 da = __ldg(cr + 1);
                     const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
                     const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
-                    fill_lane_cache(cr, da, th0, th);
                     // float arithmetic inside the sqrt as in FSSW.cpp:1867-1870
                     const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
                                                __fmul_rn(da.w, da.w));
                     L.dsigma_fac = fabs(static_cast<double>(da.x)) + sqrt(static_cast<double>(d2));
                     momentum_restore(p.mass, th0.y, species_mu(p, 1, th, p.mass), m_term, cdf_max,
                                      tab_idx & 7, tab_idx >> 3, L.M);
+                    fill_lane_cache(cr, da, th0, th);
                     busy = true;
                 }
                 // tab_idx < 0: momentum table range error, counted by setup_kernel; no record
@@ -666,8 +681,9 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
             else if (L.M.tab == 3) Et = inverse_cdf<true>(sm_fermion, mt.n, L.M, r);
             else Et = inverse_cdf<false>(mt.data, mt.n, L.M, r);
             const double E_sample = L.M.T*Et + L.M.mu;
-            const double p_mag = sqrt(E_sample*E_sample - mass*mass);
-            const double accept_ratio = (p_mag/E_sample)/(1. - mass*mass/(2.*E_sample*E_sample));
+            const double p_mag = sqrt(E_sample*E_sample - p.mass2);
+            // (p/E)/(1 - m^2/(2E^2)) = 2 p E/(2 E^2 - m^2): one division instead of three
+            const double accept_ratio = 2.*p_mag*E_sample/(2.*E_sample*E_sample - p.mass2);
             const double u_inner = u32(pw2);
             if (!(u_inner > accept_ratio)) {
                 my_tries++;
@@ -685,27 +701,26 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 sincospi(2.*u_phi, &sphi, &cphi);
                 const double px = pT*cphi;
                 const double py = pT*sphi;
-                const double p0 = sqrt(mass*mass + p_mag*p_mag);
+                const double p0 = sqrt(p.mass2 + p_mag*p_mag);
                 const double pz = p_mag*cos_theta;
                 const float4 *cr = reinterpret_cast<const float4 *>(
                     A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
                 const float4 da = lc_da[tid];
                 const double pdsigma = p0*da.x + px*da.y + py*da.z + pz*da.w;
-                double fact1 = pdsigma/p0/L.dsigma_fac;
+                const double inv_p0 = 1.0/p0;
+                // p.dsigma/(p0 (|dsigma0| + |dsigma_vec|)), FSSW.cpp:1939
+                double fact1 = pdsigma*inv_p0*lc_d[D_INV_DSIG*SAMPLER_THREADS + tid];
                 fact1 = fmax(0., fmin(1., fact1));
                 // the accept uniform is drawn whatever delta f is; since fact2 <= 1, u >= fact1
                 // already decides "reject" and the delta-f evaluation is skipped
                 const double u_acc = u32(qw1);
                 double accept_prob = 0.;
                 if (u_acc < fact1) {
-                    const double f0 = 1./(exp((p0 - L.M.mu)/L.M.T) + sign);
+                    const double inv_T = lc_d[D_INV_T*SAMPLER_THREADS + tid];
+                    const double f0 = 1./(exp((p0 - L.M.mu)*inv_T) + sign);
                     const double stat = 1. - sign*f0;
                     double delta_f = 0.;
                     if (mode.include_shear | mode.include_bulk | mode.include_diff) {
-                        const float4 th0 = lc_th0[tid];     // E, T, P, nB
-                        const float4 th = lc_th[tid];       // muB, muS, muQ, bulkPi
-                        const double *__restrict__ co = A.cellcoef + static_cast<int64_t>(L.cell)*COEF_STRIDE;
-                        const double2 c01 = lc_c01[tid], c2k = lc_c2k[tid];
                         const int B = L.qsign*p.baryon, S = L.qsign*p.strange, Q = L.qsign*p.charge;
                         if (mode.include_shear == 1) {
                             const float4 pa = lc_pa[tid];       // pixx, pixy, pixz, piyy
@@ -713,46 +728,37 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                             const double Wfactor = (px*px*pa.x + 2.*px*py*pa.y + 2.*px*pz*pa.z
                                                     + py*py*pa.w + 2.*py*pz*pb.x
                                                     + pz*pz*(-pa.x - pa.w));
-                            if (mode.neos == 1) {
-                                delta_f += stat*Wfactor/(2.*c2k.x)/(p0*L.M.T);
-                            } else if (mode.neos == 0) {
-                                delta_f += stat*Wfactor*c01.x;
-                            } else {
-                                const double Tdec = th0.y;
-                                const double pref = 1.0/(2.0*Tdec*Tdec
-                                                         *(static_cast<double>(__fadd_rn(th0.x, th0.z))));
-                                delta_f += stat*Wfactor*pref;
-                            }
+                            const double sh = lc_d[D_SHEAR*SAMPLER_THREADS + tid];
+                            if (mode.neos == 1) delta_f += stat*Wfactor*sh*inv_p0*inv_T;
+                            else delta_f += stat*Wfactor*sh;
                         }
                         if (mode.include_bulk == 1) {
                             // FSSW::get_deltaf_bulk (FSSW.cpp:1795-1849); kinds 0,2,3,4: bulkPi = 0
-                            const double Tdec = th0.y;
                             if (mode.kind == 21 || mode.kind == 1) {
-                                const double bulkPi = (mode.kind == 21)
-                                                          ? static_cast<double>(th.w)
-                                                          : static_cast<double>(th.w)/HBARC;
-                                const double E_over_T = p0/Tdec;
-                                const double mass_over_T = mass/Tdec;
-                                delta_f += (-1.0*stat*c01.x
-                                            *(mass_over_T*mass_over_T/(3.*E_over_T)
-                                              - c01.y*E_over_T)*bulkPi);
-                            } else if (mode.kind == 11) {
-                                const double bulkPi = th.w;
-                                delta_f += stat*bulkPi*(c01.x*mass*mass + c01.y*B*p0 + c2k.x*p0*p0);
-                            } else if (mode.kind == 20) {
-                                const double bulkPi = th.w;
-                                delta_f += stat*bulkPi*(mass*mass*c2k.x
-                                                        + p0*(B*__ldg(&co[3]) + S*__ldg(&co[4])
-                                                              + Q*__ldg(&co[5]))
-                                                        + p0*p0*(c01.y - c2k.x));
+                                // -(1 -/+ f0) c0 (m^2/(3 T p0) - c1 p0/T) Pi
+                                delta_f += (-stat*lc_d[D_CB*SAMPLER_THREADS + tid]*inv_T
+                                            *(p.mass2*(1./3.)*inv_p0
+                                              - lc_d[D_C1*SAMPLER_THREADS + tid]*p0));
+                            } else if (mode.kind == 11 || mode.kind == 20) {
+                                const double *__restrict__ co =
+                                    A.cellcoef + static_cast<int64_t>(L.cell)*COEF_STRIDE;
+                                const double bulkPi = __ldg(cr + 4).w;
+                                if (mode.kind == 11) {
+                                    delta_f += stat*bulkPi*(__ldg(&co[0])*p.mass2 + __ldg(&co[1])*B*p0
+                                                            + __ldg(&co[2])*p0*p0);
+                                } else {
+                                    delta_f += stat*bulkPi*(p.mass2*__ldg(&co[2])
+                                                            + p0*(B*__ldg(&co[3]) + S*__ldg(&co[4])
+                                                                  + Q*__ldg(&co[5]))
+                                                            + p0*p0*(__ldg(&co[1]) - __ldg(&co[2])));
+                                }
                             }
                         }
                         if (mode.include_diff == 1) {
                             const float4 pb = lc_pb[tid];       // piyz, qx, qy, qz
-                            // float division as in FSSW.cpp:1866
-                            const double prefactor_qmu = __fdiv_rn(th0.w, __fadd_rn(th0.x, th0.z));
                             const double qmufactor = -px*pb.y - py*pb.z - pz*pb.w;
-                            delta_f += stat*(prefactor_qmu - B/p0)*qmufactor/c2k.y;
+                            delta_f += stat*(lc_d[D_PREFQ*SAMPLER_THREADS + tid] - B*inv_p0)*qmufactor
+                                       *lc_d[D_INV_KAPPA*SAMPLER_THREADS + tid];
                         }
                     }
                     double fact2 = (1. + delta_f)/2.;
@@ -1056,7 +1062,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         spec == 1 ? propose_kernel<1, 1> : spec == 2 ? propose_kernel<1, 2>
         : spec == 3 ? propose_kernel<1, 3> : propose_kernel<1, 0>;
     const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(double)*4*(A.mt[0].n + A.mt[3].n)
-                        + (5*sizeof(float4) + 2*sizeof(double2))*SAMPLER_THREADS;
+                        + (3*sizeof(float4) + 7*sizeof(double))*SAMPLER_THREADS;
     ISS_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     int64_t grid = nsm;         // persistent: one CTA per SM
