@@ -325,6 +325,17 @@ int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data, int64
             t.trunc = static_cast<int>(grid4[1]);
             t.e0 = data[0];
             t.de = data[1] - data[0];
+            t.exp_m0 = exp(t.m0);
+            {
+                const bool fermion = (r >= 3);
+                t.denom0 = fermion ? (1. + exp(-t.m0)) : (1. - exp(-t.m0));
+                t.inv_denom0 = 1.0/t.denom0;
+                t.inv_de = 1.0/t.de;
+                for (int n = 0; n < 10; n++) {
+                    t.a[n] = exp(-t.m0*n);
+                    t.inv_n1[n] = 1.0/(n + 1);
+                }
+            }
             return ISS_OK;
         }
         ISS_FAIL(h, ISS_ERR_ARG, "unknown table kind");

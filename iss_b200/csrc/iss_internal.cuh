@@ -40,6 +40,8 @@ struct MomentumTable {      // one Boson/FermionMomentumSampler instance
     double exp_m0;          // exp(m0)
     double denom0;          // 1 -/+ exp(-m0) (boson / fermion closed form of CDF_0)
     double a[10];           // exp(-m0 n), n = 0..9
+    double inv_n1[10];      // 1/(n+1)
+    double inv_denom0, inv_de;
 };
 
 constexpr int CELL_STRIDE = 32;   // floats per AoS cell record (28 fields + t, z + 2 spare)

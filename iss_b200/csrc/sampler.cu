@@ -86,7 +86,7 @@ __device__ __forceinline__ void cdf_012_lane(const MomentumTable &mt, double Et,
         const double n1 = n + 1;
         b *= e1;
         const double a = mt.a[n];
-        const double inv = 1./n1;
+        const double inv = mt.inv_n1[n];        // 1/(n+1)
         if (FERMION) {
             if (n == 0) s0 += a*(1. - b);
         } else {
@@ -97,10 +97,12 @@ __device__ __forceinline__ void cdf_012_lane(const MomentumTable &mt, double Et,
         sign = -sign;
     }
     if (mt.trunc > 5) {
+        // exp(-Et) = exp(m0 - Et) exp(-m0); log(x/denom) with 1/denom precomputed
+        const double emE = e1*mt.a[1];
         if (FERMION) {
-            c0 = -mt.exp_m0*log((1. + exp(-Et))/mt.denom0);
+            c0 = -mt.exp_m0*log((1. + emE)*mt.inv_denom0);
         } else {
-            c0 = mt.exp_m0*log((1. - exp(-Et))/mt.denom0);
+            c0 = mt.exp_m0*log((1. - emE)*mt.inv_denom0);
         }
     } else {
         c0 = s0;
@@ -158,7 +160,12 @@ static int ensure_momentum_tables(iss_handle *h) {
         t.de = (E_min + dE) - E_min;    // Etilde_[1] - Etilde_[0]
         t.exp_m0 = exp(m0);
         t.denom0 = fermion ? (1. + exp(-m0)) : (1. - exp(-m0));
-        for (int n = 0; n < 10; n++) t.a[n] = exp(-m0*n);
+        t.inv_denom0 = 1.0/t.denom0;
+        t.inv_de = 1.0/t.de;
+        for (int n = 0; n < 10; n++) {
+            t.a[n] = exp(-m0*n);
+            t.inv_n1[n] = 1.0/(n + 1);
+        }
     }
     return ISS_OK;
 }
@@ -335,7 +342,14 @@ __device__ __forceinline__ bool momentum_setup(const MomentumTable *__restrict__
     M.cdf_max = table_F<false>(mt.data, idx_max, w1, w0, m_term);
     M.a_min = a;
     M.tab = tab;
-    M.idx_min = static_cast<int>((a - mt.e0)/mt.de);
+    // int((a - Etilde_0)/dEtilde) (MomentumSamplerBase.cpp:33-34) with the reciprocal spacing; when
+    // the product lands within rounding of an integer the exact quotient decides
+    {
+        const double t = (a - mt.e0)*mt.inv_de;
+        int idx = static_cast<int>(t);
+        if (fabs(t - rint(t)) < 1e-9) idx = static_cast<int>((a - mt.e0)/mt.de);
+        M.idx_min = idx;
+    }
     return !(M.idx_min < 0 || M.idx_min >= idx_max);
 }
 

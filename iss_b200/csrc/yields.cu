@@ -215,11 +215,17 @@ yields_kernel(const YieldArgs a) {
     }
 }
 
-// K3b: inclusive scan inside each tile of TILE cells + tile sum.  One CTA of 256
-// threads per (tile, species); each thread owns 4 consecutive cells.
+// K3b: one CTA of 256 threads per (tile of 1024 cells, species); each thread owns 4 consecutive
+// cells.  PASS 1 only reduces the tile (tile sums -> K3c); PASS 2 repeats the same fixed-order
+// scan, adds the tile base and writes the global inclusive prefix together with level 1 of the
+// 16-ary search tree (L1[j] = P[16 j + 15]).  Two reads of the yields instead of read + write +
+// read + write of a scan-then-fix-up scheme.
+template <int PASS>
 __global__ void __launch_bounds__(256)
 tile_scan_kernel(const double *__restrict__ yields, double *__restrict__ cdf,
-                 double *__restrict__ tilesum, int64_t ncell, int64_t ncell_pad, int64_t ntile) {
+                 double *__restrict__ tilesum, const double *__restrict__ tilebase,
+                 double *__restrict__ lev, int64_t lev_stride, int64_t ncell, int64_t ncell_pad,
+                 int64_t ntile) {
     __shared__ double warp_tot[8];
     const int64_t tile = blockIdx.x;
     const int s = blockIdx.y;
@@ -249,12 +255,19 @@ tile_scan_kernel(const double *__restrict__ yields, double *__restrict__ cdf,
     double wbase = 0.0;
     for (int w = 0; w < warp; w++) wbase += warp_tot[w];
     offset += wbase;
+    if (PASS == 1) {
+        if (threadIdx.x == 255) tilesum[static_cast<int64_t>(s)*ntile + tile] = v[3] + offset;
+        return;
+    }
+    // the same association as the tile-local scan followed by "+ tile base"
+    const double tb = __ldg(&tilebase[static_cast<int64_t>(s)*(ntile + 1) + tile]);
     double2 o0, o1;
-    o0.x = v[0] + offset; o0.y = v[1] + offset;
-    o1.x = v[2] + offset; o1.y = v[3] + offset;
+    o0.x = (v[0] + offset) + tb; o0.y = (v[1] + offset) + tb;
+    o1.x = (v[2] + offset) + tb; o1.y = (v[3] + offset) + tb;
     *reinterpret_cast<double2 *>(cdf + base) = o0;
     *reinterpret_cast<double2 *>(cdf + base + 2) = o1;
-    if (threadIdx.x == 255) tilesum[static_cast<int64_t>(s)*ntile + tile] = o1.y;
+    if ((threadIdx.x & 3) == 3)
+        lev[static_cast<int64_t>(s)*lev_stride + ((tile*TILE + threadIdx.x*4) >> 4)] = o1.y;
 }
 
 // K3c: one warp per species; exclusive prefix over tile sums in a fixed order.
@@ -279,24 +292,6 @@ __global__ void tile_base_kernel(const double *__restrict__ tilesum, double *__r
         tilebase[static_cast<int64_t>(s)*(ntile + 1) + ntile] = carry;
         total[s] = carry;
     }
-}
-
-// K3d: tile-local inclusive scan + tile base -> global inclusive prefix P (in place), and level 1
-// of the 16-ary search tree: L1[j] = P[16 j + 15].  One thread per pair of cells.
-__global__ void __launch_bounds__(256)
-cdf_finalize_kernel(double *__restrict__ cdf, const double *__restrict__ tilebase,
-                    double *__restrict__ lev, int64_t ncell_pad, int64_t ntile, int64_t lev_stride) {
-    const int s = blockIdx.y;
-    const int64_t t = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;    // pair index
-    if (2*t >= ncell_pad) return;
-    const int64_t tile = (2*t)/TILE;
-    const double base = __ldg(&tilebase[static_cast<int64_t>(s)*(ntile + 1) + tile]);
-    double2 *p = reinterpret_cast<double2 *>(cdf + static_cast<int64_t>(s)*ncell_pad) + t;
-    double2 v = *p;
-    v.x += base;
-    v.y += base;
-    *p = v;
-    if ((t & 7) == 7) lev[static_cast<int64_t>(s)*lev_stride + (t >> 3)] = v.y;
 }
 
 // K3e: level k >= 2 from level k-1 (every 16th entry); entries past the end read as the total
@@ -474,16 +469,13 @@ int run_yields(iss_handle *h) {
     {
         ScopedTimer t(h, ISS_T_SCAN);
         dim3 grid(static_cast<unsigned>(h->ntile), static_cast<unsigned>(ns));
-        tile_scan_kernel<<<grid, 256, 0, h->stream>>>(h->d_yields, h->d_cdf, h->d_tilesum,
-                                                      h->ncell, h->ncell_pad, h->ntile); ISS_LAUNCHED(h);
+        tile_scan_kernel<1><<<grid, 256, 0, h->stream>>>(h->d_yields, h->d_cdf, h->d_tilesum, nullptr,
+                                                         nullptr, 0, h->ncell, h->ncell_pad, h->ntile); ISS_LAUNCHED(h);
         tile_base_kernel<<<static_cast<unsigned>(ns), 32, 0, h->stream>>>(
             h->d_tilesum, h->d_tilebase, h->d_total, h->ntile); ISS_LAUNCHED(h);
-        {
-            const int64_t npair = h->ncell_pad/2;
-            dim3 g2(static_cast<unsigned>((npair + 255)/256), static_cast<unsigned>(ns));
-            cdf_finalize_kernel<<<g2, 256, 0, h->stream>>>(h->d_cdf, h->d_tilebase, h->d_cdflev,
-                                                           h->ncell_pad, h->ntile, h->lev_stride); ISS_LAUNCHED(h);
-        }
+        tile_scan_kernel<2><<<grid, 256, 0, h->stream>>>(h->d_yields, h->d_cdf, h->d_tilesum,
+                                                         h->d_tilebase, h->d_cdflev, h->lev_stride,
+                                                         h->ncell, h->ncell_pad, h->ntile); ISS_LAUNCHED(h);
         if (h->nlev >= 1) {
             const int64_t n1p = (h->lev_n[1] + 15)/16*16;
             if (n1p > h->lev_n[1]) {
