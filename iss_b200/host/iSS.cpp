@@ -13,6 +13,7 @@
 
 #include "gpu_fssw.h"
 #include "logger.h"
+#include "parallel.h"
 #include "readindata.h"
 
 using iSS_data::Vec4;
@@ -107,20 +108,83 @@ int iSS::shell() {
 // iSS.cpp:86-113
 int iSS::read_in_FO_surface() {
     require_fssw_();
+    const char *prof_env = getenv("ISS_PROFILE");
+    const bool prof = prof_env && atoi(prof_env) == 1;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        const auto t1 = std::chrono::steady_clock::now();
+        if (prof)
+            fprintf(stderr, "[iss profile] %-28s %8.3f ms\n", what,
+                    1e3*std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    };
     std::vector<FO_surf> cells;
     read_FOdata reader(paraRdr_ptr, path_, table_path_, particle_table_path_);
-    reader.read_in_freeze_out_data(cells, surface_filename_);
-    info("total number of cells: " + std::to_string(cells.size()));
-    if (cells.empty()) {
-        iss_host::warning("No freeze-out fluid cell, exit now ...");
-        exit(1);
-    }
-    afterburner_type_ = reader.get_afterburner_type();
-    reader.read_in_chemical_potentials(cells, particle_);
-    flag_PCE_ = reader.get_flag_PCE();
-    computeFOSurfTmunu(cells);
+    lap("reader ctor (EOS table)");
     FOsurf_LRF_array_.clear();
-    transform_to_local_rest_frame(cells, FOsurf_LRF_array_);
+    const int64_t nbin = reader.open_binary_surface(surface_filename_);
+    if (nbin >= 0) {
+        // binary surface: parse -> regulate -> T^{mu nu} -> LRF transform over blocks that stay in
+        // cache; per-cell arithmetic and cell order are those of the whole-surface path
+        std::cout << " -- Read spatial positions of freeze out surface from MUSIC...";
+        FOsurf_Tmunu_.assign(16, 0.f);
+        FOsurf_Q_.assign(3, 0.f);
+        FOsurf_LRF_array_.reserve(nbin);
+        const int64_t BLOCK = 1 << 17;
+        int64_t ntotal = 0;
+        double tp[4] = {0, 0, 0, 0};
+        auto now = [] { return std::chrono::steady_clock::now(); };
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return 1e3*std::chrono::duration<double>(b - a).count();
+        };
+        lap("open (slurp)");
+        for (int64_t c0 = 0; c0 < nbin; c0 += BLOCK) {
+            auto a0 = now();
+            reader.read_binary_block(cells, c0, std::min<int64_t>(BLOCK, nbin - c0));
+            auto a1 = now();
+            reader.regulate_surface_cells(cells, c0 == 0);
+            auto a2 = now();
+            ntotal += static_cast<int64_t>(cells.size());
+            accumulate_Tmunu_(cells);
+            auto a3 = now();
+            transform_to_local_rest_frame(cells, FOsurf_LRF_array_);
+            auto a4 = now();
+            tp[0] += ms(a0, a1); tp[1] += ms(a1, a2); tp[2] += ms(a2, a3); tp[3] += ms(a3, a4);
+        }
+        if (prof)
+            fprintf(stderr, "[iss profile]   parse %.1f regulate %.1f tmunu %.1f lrf %.1f ms\n", tp[0],
+                    tp[1], tp[2], tp[3]);
+        reader.close_surface();
+        std::cout << "done" << std::endl;
+        lap("binary surface pipeline");
+        info("total number of cells: " + std::to_string(ntotal));
+        if (ntotal == 0) {
+            iss_host::warning("No freeze-out fluid cell, exit now ...");
+            exit(1);
+        }
+        cells.clear();
+        afterburner_type_ = reader.get_afterburner_type();
+        reader.read_in_chemical_potentials(cells, particle_);
+        flag_PCE_ = reader.get_flag_PCE();
+        report_Tmunu_();
+        lap("particle table");
+    } else {
+        reader.read_in_freeze_out_data(cells, surface_filename_);
+        lap("read + regulate surface");
+        info("total number of cells: " + std::to_string(cells.size()));
+        if (cells.empty()) {
+            iss_host::warning("No freeze-out fluid cell, exit now ...");
+            exit(1);
+        }
+        afterburner_type_ = reader.get_afterburner_type();
+        reader.read_in_chemical_potentials(cells, particle_);
+        flag_PCE_ = reader.get_flag_PCE();
+        lap("particle table");
+        computeFOSurfTmunu(cells);
+        lap("computeFOSurfTmunu");
+        transform_to_local_rest_frame(cells, FOsurf_LRF_array_);
+        lap("transform_to_local_rest_frame");
+    }
     info(" -- Read in data finished!");
     return 0;
 }
@@ -204,52 +268,87 @@ std::vector<iSS_Hadron> *iSS::get_hadron_list_iev(const int iev) {
 // compared with the reference at 1e-6 and Sigma_LRF = da_mu_LRF[0] multiplies every yield.
 void iSS::transform_to_local_rest_frame(std::vector<FO_surf> &FOsurf_ptr,
                                         std::vector<FO_surf_LRF> &FOsurf_LRF_ptr) {
-    info("Transforming fluid cells to their local rest frame ...");
-    FOsurf_LRF_ptr.reserve(FOsurf_LRF_ptr.size() + FOsurf_ptr.size());
-    for (const FO_surf &c : FOsurf_ptr) {
-        const EtaRotation rot(c.eta);
-        const float ut = rot.time_like(c.u0, c.u3);
-        const float uz = rot.z_like(c.u0, c.u3);
+    const int64_t ncell = static_cast<int64_t>(FOsurf_ptr.size());
+    const int nthread = iss_host::ingest_threads(ncell);
+    // pass 1: which cells survive u.dsigma >= 0 (iSS.cpp:226), counted per thread range;
+    // pass 2: full transform written straight to the final position (file order is kept)
+    auto boost_of = [](const FO_surf &c, const EtaRotation &rot, double L[4][4], float &ut, float &uz) {
+        ut = rot.time_like(c.u0, c.u3);
+        uz = rot.z_like(c.u0, c.u3);
         const float ux = c.u1, uy = c.u2;
         const double g = ut + 1.;
-        const double L[4][4] = {{ut, -ux, -uy, -uz},
+        const double M[4][4] = {{ut, -ux, -uy, -uz},
                                 {-ux, 1. + ux*ux/g, ux*uy/g, ux*uz/g},
                                 {-uy, ux*uy/g, 1. + uy*uy/g, uy*uz/g},
                                 {-uz, ux*uz/g, uy*uz/g, 1. + uz*uz/g}};
+        for (int i = 0; i < 4; i++)
+            for (int j = 0; j < 4; j++) L[i][j] = M[i][j];
+    };
+    auto normal_of = [](const FO_surf &c, const EtaRotation &rot) {
         // contravariant surface normal in (t,x,y,z) from the Milne covariant components
         const Vec4 dsigma = {c.tau*c.da0*rot.ch - c.da3*rot.sh, -c.tau*c.da1, -c.tau*c.da2,
                              -c.da3*rot.ch + c.tau*c.da0*rot.sh};
-        const Vec4 ds = boost_apply(L, dsigma);
-        if (ds[0] < 0) continue;    // u.dsigma < 0: cell dropped (iSS.cpp:226)
+        return dsigma;
+    };
+    std::vector<unsigned char> keep(static_cast<size_t>(ncell));
+    std::vector<int64_t> count(nthread + 1, 0);
+    iss_host::parallel_ranges(ncell, nthread, [&](int64_t c0, int64_t c1, int t) {
+        int64_t n = 0;
+        for (int64_t ic = c0; ic < c1; ic++) {
+            const FO_surf &c = FOsurf_ptr[ic];
+            const EtaRotation rot(c.eta);
+            double L[4][4];
+            float ut, uz;
+            boost_of(c, rot, L, ut, uz);
+            const Vec4 ds = boost_apply(L, normal_of(c, rot));
+            keep[ic] = !(ds[0] < 0);
+            n += keep[ic];
+        }
+        count[t + 1] = n;
+    });
+    for (int t = 0; t < nthread; t++) count[t + 1] += count[t];
+    const size_t base = FOsurf_LRF_ptr.size();
+    FOsurf_LRF_ptr.resize(base + count[nthread]);
+    iss_host::parallel_ranges(ncell, nthread, [&](int64_t c0, int64_t c1, int t) {
+        size_t w = base + count[t];
+        for (int64_t ic = c0; ic < c1; ic++) {
+            if (!keep[ic]) continue;
+            const FO_surf &c = FOsurf_ptr[ic];
+            const EtaRotation rot(c.eta);
+            double L[4][4];
+            float ut, uz;
+            boost_of(c, rot, L, ut, uz);
+            const float ux = c.u1, uy = c.u2;
+            const Vec4 ds = boost_apply(L, normal_of(c, rot));
 
-        FO_surf_LRF o;
-        o.tau = c.tau; o.xpt = c.xpt; o.ypt = c.ypt; o.eta = c.eta;
-        o.Edec = c.Edec; o.Tdec = c.Tdec; o.Pdec = c.Pdec;
-        o.Bn = c.Bn; o.muB = c.muB; o.muS = c.muS; o.muQ = c.muQ;
-        o.bulkPi = c.bulkPi;
-        o.particle_mu_PCE = c.particle_mu_PCE;
-        o.u_tz = {ut, ux, uy, uz};
-        o.da_mu_LRF = {ds[0], -ds[1], -ds[2], -ds[3]};
+            FO_surf_LRF &o = FOsurf_LRF_ptr[w++];
+            o.tau = c.tau; o.xpt = c.xpt; o.ypt = c.ypt; o.eta = c.eta;
+            o.Edec = c.Edec; o.Tdec = c.Tdec; o.Pdec = c.Pdec;
+            o.Bn = c.Bn; o.muB = c.muB; o.muS = c.muS; o.muQ = c.muQ;
+            o.bulkPi = c.bulkPi;
+            o.particle_mu_PCE = c.particle_mu_PCE;
+            o.u_tz = {ut, ux, uy, uz};
+            o.da_mu_LRF = {ds[0], -ds[1], -ds[2], -ds[3]};
 
-        const Vec4 q_tz = {rot.time_like(c.qmu0, c.qmu3), c.qmu1, c.qmu2,
-                           rot.z_like(c.qmu0, c.qmu3)};
-        const Vec4 q = boost_apply(L, q_tz);
-        o.qmuLRF_x = q[1]; o.qmuLRF_y = q[2]; o.qmuLRF_z = q[3];
+            const Vec4 q_tz = {rot.time_like(c.qmu0, c.qmu3), c.qmu1, c.qmu2,
+                               rot.z_like(c.qmu0, c.qmu3)};
+            const Vec4 q = boost_apply(L, q_tz);
+            o.qmuLRF_x = q[1]; o.qmuLRF_y = q[2]; o.qmuLRF_z = q[3];
 
-        float pi_tz[4][4];
-        shear_to_tz(c, rot, pi_tz);
-        float pi_lrf[4][4];
-        for (int i = 1; i < 3; i++)         // only xx, xy, xz, yy, yz are kept
-            for (int j = i; j < 4; j++) {
-                float acc = 0.;
-                for (int a = 0; a < 4; a++)
-                    for (int b = 0; b < 4; b++) acc += (L[i][a]*pi_tz[a][b]*L[b][j]);
-                pi_lrf[i][j] = acc;
-            }
-        o.piLRF_xx = pi_lrf[1][1]; o.piLRF_xy = pi_lrf[1][2]; o.piLRF_xz = pi_lrf[1][3];
-        o.piLRF_yy = pi_lrf[2][2]; o.piLRF_yz = pi_lrf[2][3];
-        FOsurf_LRF_ptr.push_back(o);
-    }
+            float pi_tz[4][4];
+            shear_to_tz(c, rot, pi_tz);
+            float pi_lrf[4][4];
+            for (int i = 1; i < 3; i++)         // only xx, xy, xz, yy, yz are kept
+                for (int j = i; j < 4; j++) {
+                    float acc = 0.;
+                    for (int a = 0; a < 4; a++)
+                        for (int b = 0; b < 4; b++) acc += (L[i][a]*pi_tz[a][b]*L[b][j]);
+                    pi_lrf[i][j] = acc;
+                }
+            o.piLRF_xx = pi_lrf[1][1]; o.piLRF_xy = pi_lrf[1][2]; o.piLRF_xz = pi_lrf[1][3];
+            o.piLRF_yy = pi_lrf[2][2]; o.piLRF_yz = pi_lrf[2][3];
+        }
+    });
 }
 
 // iSS.cpp:378-445: unweighted sum of the cells' T^{mu nu}; meaningful for one-cell inputs
@@ -257,21 +356,48 @@ void iSS::transform_to_local_rest_frame(std::vector<FO_surf> &FOsurf_ptr,
 void iSS::computeFOSurfTmunu(std::vector<FO_surf> &FOsurf_ptr) {
     FOsurf_Tmunu_.assign(16, 0.f);
     FOsurf_Q_.assign(3, 0.f);
-    for (const FO_surf &c : FOsurf_ptr) {
-        const EtaRotation rot(c.eta);
-        const float u[4] = {rot.time_like(c.u0, c.u3), c.u1, c.u2, rot.z_like(c.u0, c.u3)};
-        float pi_tz[4][4];
-        shear_to_tz(c, rot, pi_tz);
-        for (int i = 0; i < 4; i++)
-            for (int j = 0; j < 4; j++) {
-                const float gij = (i != j) ? 0.f : (i == 0 ? 1.f : -1.f);
-                const float Tij = (c.Edec*u[i]*u[j] - (c.Pdec + c.bulkPi)*(gij - u[i]*u[j])
-                                   + pi_tz[i][j]);
-                FOsurf_Tmunu_[4*i + j] += Tij;
+    accumulate_Tmunu_(FOsurf_ptr);
+    report_Tmunu_();
+}
+
+void iSS::accumulate_Tmunu_(const std::vector<FO_surf> &FOsurf_ptr) {
+    // the per-cell tensors are computed by several threads, block by block; the accumulation
+    // stays a sequential float sum in file order like the reference's
+    const int64_t ncell = static_cast<int64_t>(FOsurf_ptr.size());
+    const int64_t BLOCK = 1 << 17;
+    std::vector<float> tmp(static_cast<size_t>(std::min<int64_t>(BLOCK, std::max<int64_t>(ncell, 1)))*16);
+    for (int64_t b0 = 0; b0 < ncell; b0 += BLOCK) {
+        const int64_t nb = std::min<int64_t>(BLOCK, ncell - b0);
+        iss_host::parallel_ranges(nb, iss_host::ingest_threads(nb), [&](int64_t c0, int64_t c1, int) {
+            for (int64_t ic = c0; ic < c1; ic++) {
+                const FO_surf &c = FOsurf_ptr[b0 + ic];
+                const EtaRotation rot(c.eta);
+                const float u[4] = {rot.time_like(c.u0, c.u3), c.u1, c.u2, rot.z_like(c.u0, c.u3)};
+                float pi_tz[4][4];
+                shear_to_tz(c, rot, pi_tz);
+                for (int i = 0; i < 4; i++)
+                    for (int j = 0; j < 4; j++) {
+                        const float gij = (i != j) ? 0.f : (i == 0 ? 1.f : -1.f);
+                        tmp[ic*16 + 4*i + j] = (c.Edec*u[i]*u[j]
+                                                - (c.Pdec + c.bulkPi)*(gij - u[i]*u[j]) + pi_tz[i][j]);
+                    }
             }
+        });
+        float acc[16];
+        for (int k = 0; k < 16; k++) acc[k] = FOsurf_Tmunu_[k];
+        const float *t = tmp.data();
+        for (int64_t ic = 0; ic < nb; ic++)
+            for (int k = 0; k < 16; k++) acc[k] += t[ic*16 + k];    // 16 independent running sums
+        for (int k = 0; k < 16; k++) FOsurf_Tmunu_[k] = acc[k];
+    }
+    if (ncell > 0) {
+        const FO_surf &c = FOsurf_ptr[ncell - 1];
         FOsurf_Q_[0] = c.Bn;
         FOsurf_Q_[2] = 0.4*c.Bn;
     }
+}
+
+void iSS::report_Tmunu_() const {
     info("The total energy-momentum tensor from the surface:");
     for (int i = 0; i < 4; i++)
         for (int j = 0; j < 4; j++) {

@@ -42,6 +42,8 @@ class iSS {
     std::unique_ptr<GpuFSSW> spectra_sampler_;
 
     void require_fssw_() const;
+    void accumulate_Tmunu_(const std::vector<FO_surf> &cells);
+    void report_Tmunu_() const;
 
  public:
     iSS(std::string path, std::string table_path = "iSS_tables",

@@ -9,7 +9,13 @@
 #include <iostream>
 #include <sstream>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "logger.h"
+#include "parallel.h"
 
 using iSS_data::hbarC;
 using iss_host::info;
@@ -191,34 +197,86 @@ void read_FOdata::read_binary_surface_(std::vector<FO_surf> &surf, const std::st
         exit(1);
     }
     const size_t ncell = (buf.size() - 1)/(34*sizeof(float));
-    surf.reserve(surf.size() + ncell);
-    const float *a = reinterpret_cast<const float *>(buf.data());
-    for (size_t c = 0; c < ncell; c++, a += 34) {
-        FO_surf s;
-        s.tau = a[0]; s.xpt = a[1]; s.ypt = a[2];
-        s.eta = boost_inv ? 0.0f : a[3];
-        s.da0 = a[4]; s.da1 = a[5]; s.da2 = a[6];
-        s.da3 = boost_inv ? 0.0f : a[7];
-        s.u0 = a[8]; s.u1 = a[9]; s.u2 = a[10]; s.u3 = a[11];
-        s.Edec = static_cast<float>(a[12]*hbarC);
-        s.Tdec = static_cast<float>(a[13]*hbarC);
-        s.muB = static_cast<float>(a[14]*hbarC);
-        s.muS = static_cast<float>(a[15]*hbarC);
-        s.muQ = static_cast<float>(a[16]*hbarC);
-        s.Pdec = a[17]*s.Tdec - s.Edec;         // float arithmetic (readindata.cpp:670)
-        float *pi = &s.pi00;
-        for (int i = 0; i < 10; i++) pi[i] = static_cast<float>(a[18 + i]*hbarC);
-        s.bulkPi = static_cast<float>(a[28]*hbarC);
-        s.Bn = a[29];
-        s.qmu0 = a[30]; s.qmu1 = a[31]; s.qmu2 = a[32]; s.qmu3 = a[33];
+    parse_binary_cells_(reinterpret_cast<const float *>(buf.data()), static_cast<int64_t>(ncell),
+                        boost_inv, surf, surf.size());
+}
+
+int64_t read_FOdata::open_binary_surface(const std::string &surface_filename) {
+    if (!surface_in_binary_) return -1;
+    const std::string file = path_ + "/" + surface_filename;
+    close_surface();
+    const int fd = open(file.c_str(), O_RDONLY);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0) {
+        std::cout << "[Error] Surface file is not found! " << file << std::endl;
+        exit(1);
+    }
+    surface_map_bytes_ = static_cast<size_t>(st.st_size);
+    if (surface_map_bytes_ > 0) {
+        surface_map_ = mmap(nullptr, surface_map_bytes_, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (surface_map_ == MAP_FAILED) {
+            surface_map_ = nullptr;
+            std::cout << "[Error] can not map surface file " << file << std::endl;
+            exit(1);
+        }
+        madvise(surface_map_, surface_map_bytes_, MADV_SEQUENTIAL);
+    }
+    close(fd);
+    return static_cast<int64_t>(surface_map_bytes_/(34*sizeof(float)));
+}
+
+void read_FOdata::read_binary_block(std::vector<FO_surf> &surf, int64_t c0, int64_t n) {
+    const float *all = static_cast<const float *>(surface_map_) + 34*c0;
+    // the records are overwritten in place: no per-block construction of 160-byte elements
+    parse_binary_cells_(all, n, mode_ == 1, surf, 0);
+}
+
+void read_FOdata::close_surface() {
+    if (surface_map_) munmap(surface_map_, surface_map_bytes_);
+    surface_map_ = nullptr;
+    surface_map_bytes_ = 0;
+}
+
+void read_FOdata::parse_binary_cells_(const float *all, int64_t ncell, bool boost_inv,
+                                      std::vector<FO_surf> &surf, size_t first) {
+    surf.resize(first + ncell);
+    iss_host::parallel_ranges(static_cast<int64_t>(ncell), iss_host::ingest_threads(ncell),
+                              [&](int64_t c0, int64_t c1, int) {
+        for (int64_t c = c0; c < c1; c++) {
+            const float *a = all + 34*c;
+            FO_surf &s = surf[first + c];
+            s.tau = a[0]; s.xpt = a[1]; s.ypt = a[2];
+            s.eta = boost_inv ? 0.0f : a[3];
+            s.da0 = a[4]; s.da1 = a[5]; s.da2 = a[6];
+            s.da3 = boost_inv ? 0.0f : a[7];
+            s.u0 = a[8]; s.u1 = a[9]; s.u2 = a[10]; s.u3 = a[11];
+            s.Edec = static_cast<float>(a[12]*hbarC);
+            s.Tdec = static_cast<float>(a[13]*hbarC);
+            s.muB = static_cast<float>(a[14]*hbarC);
+            s.muS = static_cast<float>(a[15]*hbarC);
+            s.muQ = static_cast<float>(a[16]*hbarC);
+            s.Pdec = a[17]*s.Tdec - s.Edec;         // float arithmetic (readindata.cpp:670)
+            float *pi = &s.pi00;
+            for (int i = 0; i < 10; i++) pi[i] = static_cast<float>(a[18 + i]*hbarC);
+            s.bulkPi = static_cast<float>(a[28]*hbarC);
+            s.Bn = a[29];
+            s.qmu0 = a[30]; s.qmu1 = a[31]; s.qmu2 = a[32]; s.qmu3 = a[33];
+        }
+    });
+    // cells with T <= 0.01 GeV are discarded, in file order (readindata.cpp:752)
+    size_t w = first;
+    for (size_t c = first; c < first + static_cast<size_t>(ncell); c++) {
+        const FO_surf &s = surf[c];
         if (s.Tdec > 0.01) {
-            surf.push_back(s);
+            if (w != c) surf[w] = s;
+            w++;
         } else {
             std::cout << "Discard surf elem: T = " << s.Tdec << " GeV, Edec = " << s.Edec
                       << " GeV/fm^3, rhoB = " << s.Bn << " 1/fm^3, muB = " << s.muB << " GeV. "
                       << std::endl;
         }
     }
+    surf.resize(w);
 }
 
 // whitespace separated numbers, cells need not be aligned with lines (readindata.cpp:692-749)
@@ -301,38 +359,42 @@ void read_FOdata::read_text_surface_boost_invariant_(std::vector<FO_surf> &surf,
 }
 
 // readindata.cpp:768-842
-void read_FOdata::regulate_surface_cells(std::vector<FO_surf> &surf) {
+void read_FOdata::regulate_surface_cells(std::vector<FO_surf> &surf, bool announce) {
     const bool regulateTemperature =
         (iEOS_MUSIC_ == 9 || iEOS_MUSIC_ == 91 || iEOS_MUSIC_ == 12 || iEOS_MUSIC_ == 14);
-    if (regulateTemperature)
+    if (regulateTemperature && announce)
         std::cout << "Regulate local temperature with pure HRG EoS." << std::endl;
-    std::vector<double> eos;
-    for (auto &s : surf) {
-        if (regulateTemperature) {
-            if (getValuesFromHRGEOS(s.Edec, s.Bn, eos) == 0) {
-                s.Tdec = static_cast<float>(eos[1]);
-                s.muB = static_cast<float>(eos[2]);
-                s.muS = static_cast<float>(eos[3]);
-                s.muQ = static_cast<float>(eos[4]);
-                s.Pdec = static_cast<float>(eos[0]);
+    const int64_t n = static_cast<int64_t>(surf.size());
+    iss_host::parallel_ranges(n, iss_host::ingest_threads(n), [&](int64_t c0, int64_t c1, int) {
+        std::vector<double> eos;
+        for (int64_t c = c0; c < c1; c++) {
+            FO_surf &s = surf[c];
+            if (regulateTemperature) {
+                if (getValuesFromHRGEOS(s.Edec, s.Bn, eos) == 0) {
+                    s.Tdec = static_cast<float>(eos[1]);
+                    s.muB = static_cast<float>(eos[2]);
+                    s.muS = static_cast<float>(eos[3]);
+                    s.muQ = static_cast<float>(eos[4]);
+                    s.Pdec = static_cast<float>(eos[0]);
+                }
             }
+            // 1. is a double literal, the products are float (readindata.cpp:796-798)
+            s.u0 = static_cast<float>(std::sqrt(1. + s.u1*s.u1 + s.u2*s.u2 + s.u3*s.u3));
+            s.qmu0 = (s.u1*s.qmu1 + s.u2*s.qmu2 + s.u3*s.qmu3)/s.u0;
+            double u[4] = {s.u0, s.u1, s.u2, s.u3};
+            double W[4][4] = {{s.pi00, s.pi01, s.pi02, s.pi03},
+                              {s.pi01, s.pi11, s.pi12, s.pi13},
+                              {s.pi02, s.pi12, s.pi22, s.pi23},
+                              {s.pi03, s.pi13, s.pi23, s.pi33}};
+            double R[4][4];
+            regulate_Wmunu(u, W, R);
+            s.pi00 = static_cast<float>(R[0][0]); s.pi01 = static_cast<float>(R[0][1]);
+            s.pi02 = static_cast<float>(R[0][2]); s.pi03 = static_cast<float>(R[0][3]);
+            s.pi11 = static_cast<float>(R[1][1]); s.pi12 = static_cast<float>(R[1][2]);
+            s.pi13 = static_cast<float>(R[1][3]); s.pi22 = static_cast<float>(R[2][2]);
+            s.pi23 = static_cast<float>(R[2][3]); s.pi33 = static_cast<float>(R[3][3]);
         }
-        // 1. is a double literal, the products are float (readindata.cpp:796-798)
-        s.u0 = static_cast<float>(std::sqrt(1. + s.u1*s.u1 + s.u2*s.u2 + s.u3*s.u3));
-        s.qmu0 = (s.u1*s.qmu1 + s.u2*s.qmu2 + s.u3*s.qmu3)/s.u0;
-        double u[4] = {s.u0, s.u1, s.u2, s.u3};
-        double W[4][4] = {{s.pi00, s.pi01, s.pi02, s.pi03},
-                          {s.pi01, s.pi11, s.pi12, s.pi13},
-                          {s.pi02, s.pi12, s.pi22, s.pi23},
-                          {s.pi03, s.pi13, s.pi23, s.pi33}};
-        double R[4][4];
-        regulate_Wmunu(u, W, R);
-        s.pi00 = static_cast<float>(R[0][0]); s.pi01 = static_cast<float>(R[0][1]);
-        s.pi02 = static_cast<float>(R[0][2]); s.pi03 = static_cast<float>(R[0][3]);
-        s.pi11 = static_cast<float>(R[1][1]); s.pi12 = static_cast<float>(R[1][2]);
-        s.pi13 = static_cast<float>(R[1][3]); s.pi22 = static_cast<float>(R[2][2]);
-        s.pi23 = static_cast<float>(R[2][3]); s.pi33 = static_cast<float>(R[3][3]);
-    }
+    });
 }
 
 // transverse, traceless projection (readindata.cpp:1216-1246)

@@ -15,6 +15,7 @@
 #ifndef ISS_B200_READINDATA_H_
 #define ISS_B200_READINDATA_H_
 
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -25,7 +26,7 @@ class read_FOdata {
  public:
     read_FOdata(ParameterReader *paraRdr_in, std::string path, std::string table_path,
                 std::string particle_table_path);
-    ~read_FOdata() = default;
+    ~read_FOdata() { close_surface(); }
 
     int get_IEOS_music() const { return iEOS_MUSIC_; }
     AfterburnerType get_afterburner_type() const { return afterburner_type_; }
@@ -33,10 +34,17 @@ class read_FOdata {
     bool get_surface_in_binary() const { return surface_in_binary_; }
 
     void read_in_freeze_out_data(std::vector<FO_surf> &surf, std::string surface_filename);
+    // Block-wise access to a binary surface (engine addition): the file is loaded once, cells
+    // [c0, c0+n) are parsed into `surf` (replacing its content; cells with T <= 0.01 GeV dropped).
+    // Lets the facade pipeline parse -> regulate -> LRF transform over cache-sized blocks instead
+    // of materialising 160-byte FO_surf records for the whole surface.
+    int64_t open_binary_surface(const std::string &surface_filename);   // cells in the file, -1 if text
+    void read_binary_block(std::vector<FO_surf> &surf, int64_t c0, int64_t n);
+    void close_surface();
     void read_in_chemical_potentials(std::vector<FO_surf> &surf,
                                      std::vector<particle_info> &particles);
     int read_resonances_list(std::vector<particle_info> &particles);
-    void regulate_surface_cells(std::vector<FO_surf> &surf);
+    void regulate_surface_cells(std::vector<FO_surf> &surf, bool announce = true);
     void regulate_Wmunu(double u[4], double Wmunu[4][4], double Wmunu_regulated[4][4]);
     int getValuesFromHRGEOS(double ed, double nB, std::vector<double> &eos);
 
@@ -51,11 +59,15 @@ class read_FOdata {
     int iEOS_MUSIC_;
     AfterburnerType afterburner_type_;
     std::vector<double> hrg_;       // rows of 7: ed, nB, P, T, muB, muS, muQ
+    void *surface_map_ = nullptr;       // read-only mapping of the binary surface file
+    size_t surface_map_bytes_ = 0;
     long hrg_rows_;
 
     void read_music_input_();
     void read_in_HRG_EOS_();
     void read_binary_surface_(std::vector<FO_surf> &surf, const std::string &file, bool boost_inv);
+    void parse_binary_cells_(const float *all, int64_t ncell, bool boost_inv, std::vector<FO_surf> &surf,
+                             size_t first);
     void read_text_surface_3d_(std::vector<FO_surf> &surf, const std::string &file);
     void read_text_surface_boost_invariant_(std::vector<FO_surf> &surf, const std::string &file);
 };
