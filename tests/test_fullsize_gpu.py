@@ -117,3 +117,52 @@ def test_command_line_end_to_end(built, tmp_path):
     assert int(lines[3].split()[0]) == 0 and n0 > 10000
     assert len(lines[4].split()) == 11
     assert os.path.exists(tmp_path/"check_211_spectra.dat")
+
+
+def test_decays_at_scale_conserve_four_momentum(built, tmp_path):
+    """BASELINE.json configs[2]-like: boost-invariant 10^5-cell surface, CE delta-f, resonance
+    decays (UrQMD table, since the reference skips decays for SMASH, FSSW.cpp:346).  Pole-mass
+    decays conserve four-momentum: per event, sum p^mu of the final hadrons equals that of the
+    primaries whose decay chain was kept (chains through 4-body / Npart<0 channels drop the
+    mother, particle_decay.cpp:291-327), so the totals can only decrease, and by little."""
+    from iss_b200 import synthetic
+    capi = built
+    work = str(tmp_path)
+    synthetic.make_case(work, ncell=100000, seed=12345, eos=9, boost_invariant=True)
+    over = dict(bench.OVERRIDES, hydro_mode=1, include_deltaf_diffusion=0, perform_decays=1,
+                number_of_repeated_sampling=20, y_LB=-2.0, y_RB=2.0)
+    s = capi.Sampler(work, bench.PARAM, "surface.dat", **over)
+    try:
+        s.read_in_FO_surface()
+        s.set_random_seed(3)
+        s.prepare_sampler()
+        e = s.engine()
+        e.compute_yields()
+        nev = 20
+        e.timing(enable=True, reset=True)
+        e.sample(3, 0, nev)
+        prim = e.fetch_all().copy()
+        off = e.event_offsets(nev).copy()
+        e.decay(3)
+        fin = e.fetch_all()
+        foff = e.event_offsets(nev)
+        ms, _ = e.timing(enable=False)
+        print("primaries %d finals %d  decay kernels %.3f ms  proposal %.3f ms" %
+              (len(prim), len(fin), ms["decay"], ms["sample"]))
+        assert len(fin) > 1.2*len(prim)
+        dsp = {int(p): (int(st)) for p, st in []}
+        for ev in range(nev):
+            a, b = prim[off[ev]:off[ev + 1]], fin[foff[ev]:foff[ev + 1]]
+            Ea, Eb = a["E"].astype(np.float64).sum(), b["E"].astype(np.float64).sum()
+            assert Eb <= Ea*(1 + 1e-6)
+            assert Eb >= 0.93*Ea
+            for k in ("px", "py", "pz"):
+                pa, pb = a[k].astype(np.float64).sum(), b[k].astype(np.float64).sum()
+                assert abs(pa - pb) < 0.05*Ea
+        # rapidity window of the boost-invariant mode for primaries
+        mT = np.sqrt(prim["mass"].astype(np.float64)**2 + prim["px"].astype(np.float64)**2
+                     + prim["py"].astype(np.float64)**2)
+        y = np.arcsinh(prim["pz"]/mT)
+        assert y.min() > -2.0 - 1e-4 and y.max() < 2.0 + 1e-4
+    finally:
+        s.close()
