@@ -78,7 +78,8 @@ typedef struct {
     int32_t include_deltaf_bulk;
     int32_t include_deltaf_diffusion;
     int32_t bulk_deltaf_kind;           /* 1, 11, 20, 21 active; 0,2,3,4 no-ops as in FSSW */
-    int32_t dN_dy_sampling_model;       /* 30 Poisson (default), 1 floor+Bernoulli      */
+    int32_t dN_dy_sampling_model;       /* 30 Poisson (default), 1 floor+Bernoulli,
+                                           10 / 20 negative binomial (para1)            */
     int32_t local_charge_conservation;
     int32_t reserved;
     double dN_dy_sampling_para1;

@@ -380,10 +380,11 @@ int iss_cuda_upload_decay_table(iss_handle *h, const iss_decay_species *sp, int3
 
 int iss_cuda_set_options(iss_handle *h, const iss_options *opt) {
     if (!h || !opt) return ISS_ERR_ARG;
-    if (opt->dN_dy_sampling_model != 30 && opt->dN_dy_sampling_model != 1)
+    const int model = opt->dN_dy_sampling_model;
+    if (model != 30 && model != 1 && model != 10 && model != 20)
         ISS_FAIL(h, ISS_ERR_ARG,
-                 "dN_dy_sampling_model must be 30 (Poisson) or 1 (floor+Bernoulli); "
-                 "NBD models 10/20 are not implemented");
+                 "dN_dy_sampling_model must be 1 (floor+Bernoulli), 10 or 20 (negative binomial) "
+                 "or 30 (Poisson) (FSSW.cpp:250-309)");
     const bool changed = !h->have_opt || memcmp(&h->opt, opt, sizeof(*opt)) != 0;
     h->opt = *opt;
     h->have_opt = true;

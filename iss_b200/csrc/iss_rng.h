@@ -10,6 +10,7 @@
 #ifndef ISS_RNG_H_
 #define ISS_RNG_H_
 
+#include <math.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -186,6 +187,56 @@ ISS_HD int64_t floor_plus_bernoulli(double dN, double u) {
     double frac = ISS_SUB(dN, static_cast<double>(n));
     if (u < frac) n++;
     return n;
+}
+
+// dN_dy_sampling_model 10 / 20 (FSSW.cpp:275-292): gsl_ran_negative_binomial(p, k) with
+// p = 1/(1 + para1), i.e. X ~ Poisson(Y), Y ~ Gamma(shape k, scale (1-p)/p = para1) (GSL's
+// definition; GSL itself is not part of the reference tree).  Gamma by Marsaglia & Tsang (2000),
+// with the U^(1/k) boost for k < 1; normals by Box-Muller; the Poisson draw is the inversion
+// from the mode used everywhere else.  Uses libm transcendentals, so host and device agree
+// statistically, not bit for bit.
+template <typename RNG>
+ISS_HD double gamma_draw(RNG &rng, double shape) {
+    double boost = 1.0;
+    if (shape < 1.0) {
+        boost = pow(rng.next(), 1.0/shape);
+        shape += 1.0;
+    }
+    const double d = shape - 1.0/3.0;
+    const double c = 1.0/sqrt(9.0*d);
+    for (int it = 0; it < 1000; it++) {
+        const double u1 = rng.next(), u2 = rng.next();
+        const double x = sqrt(-2.0*log(u1 > 0.0 ? u1 : 1e-300))*cos(6.283185307179586*u2);
+        const double t = 1.0 + c*x;
+        if (t <= 0.0) continue;
+        const double v = t*t*t;
+        const double u = rng.next();
+        if (log(u > 0.0 ? u : 1e-300) < 0.5*x*x + d - d*v + d*log(v)) return boost*d*v;
+    }
+    return boost*d;
+}
+
+template <typename RNG>
+ISS_HD int64_t negative_binomial_draw(RNG &rng, double k, double scale) {
+    const double y = scale*gamma_draw(rng, k);
+    if (y < 1e-15) return 0;
+    const double m = floor(y);
+    const double pmode = exp(m*log(y) - y - lgamma(m + 1.0));
+    return poisson_from_mode(y, pmode, rng.next());
+}
+
+// FSSW::determine_number_to_sample (FSSW.cpp:250-309) for every model
+template <typename RNG>
+ISS_HD int64_t number_to_sample(RNG &rng, int model, double para1, double dN, double pmode) {
+    if (model == 1) return floor_plus_bernoulli(dN, rng.next());
+    if (model == 10 || model == 20) {
+        const int64_t dN_int = static_cast<int64_t>(dN);
+        const double k = (model == 10) ? para1*(dN - static_cast<double>(dN_int)) : para1*dN;
+        if (k < 1e-15) return dN_int;
+        const int64_t x = negative_binomial_draw(rng, k, para1);
+        return (model == 10) ? dN_int + x : x;
+    }
+    return poisson_from_mode(dN, pmode, rng.next());
 }
 
 }  // namespace iss

@@ -176,7 +176,7 @@ static int ensure_momentum_tables(iss_handle *h) {
 __global__ void multiplicity_kernel(const double *__restrict__ lambda,
                                     const double *__restrict__ pmode,
                                     const DeviceSpecies *__restrict__ species, int ns, int64_t nev,
-                                    int64_t ev_begin, uint64_t seed, int model, int lcc,
+                                    int64_t ev_begin, uint64_t seed, int model, double para1, int lcc,
                                     int64_t *__restrict__ mult,       // [nev][ns] draws
                                     int64_t *__restrict__ out_count,  // [nev*ns] hadrons written
                                     int64_t *__restrict__ work_count  // [ns*nev] draws
@@ -187,13 +187,7 @@ __global__ void multiplicity_kernel(const double *__restrict__ lambda,
     const int s = static_cast<int>(i - ev*ns);
     Stream rng;
     rng.init(seed, STREAM_MULT, s, static_cast<uint32_t>(ev_begin + ev), 0);
-    const double u = rng.next();
-    int64_t n;
-    if (model == 1) {
-        n = floor_plus_bernoulli(lambda[s], u);
-    } else {
-        n = poisson_from_mode(lambda[s], pmode[s], u);
-    }
+    int64_t n = number_to_sample(rng, model, para1, lambda[s], pmode[s]);
     int64_t nout = n;
     if (lcc == 1) {
         // FSSW.cpp:931-938, 1035-1048: negative species skipped, positive ones paired
@@ -942,7 +936,8 @@ int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev) {
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_off_work + n, 0, sizeof(int64_t), h->stream));
     multiplicity_kernel<<<static_cast<unsigned>((n + 255)/256), 256, 0, h->stream>>>(
         h->d_lambda, h->d_pmode, h->d_species, ns, nev, h->ev_begin, seed,
-        o.dN_dy_sampling_model, o.local_charge_conservation, h->d_mult, h->d_off_out,
+        o.dN_dy_sampling_model, o.dN_dy_sampling_para1, o.local_charge_conservation, h->d_mult,
+        h->d_off_out,
         h->d_off_work); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
     return ISS_OK;

@@ -166,20 +166,56 @@ static int64_t poisson_mode(double lambda, double pmode, double u) {
     }
 }
 
+/* Models 10 / 20 (src/FSSW.cpp:275-292): gsl_ran_negative_binomial(p = 1/(1+para1), k), i.e.
+ * X ~ Poisson(Y) with Y ~ Gamma(shape k, scale para1) (GSL's published definition; GSL is not in
+ * the reference tree).  Gamma by Marsaglia & Tsang (2000) + U^(1/k) boost, Box-Muller normals,
+ * Poisson by the inversion above; uniforms taken from the stream in this order. */
+static double gamma_draw(o_stream *r, double shape) {
+    double boost = 1.0;
+    if (shape < 1.0) {
+        boost = pow(stream_next(r), 1.0/shape);
+        shape += 1.0;
+    }
+    const double d = shape - 1.0/3.0, c = 1.0/sqrt(9.0*d);
+    for (int it = 0; it < 1000; it++) {
+        const double u1 = stream_next(r), u2 = stream_next(r);
+        const double x = sqrt(-2.0*log(u1 > 0.0 ? u1 : 1e-300))*cos(6.283185307179586*u2);
+        const double t = 1.0 + c*x;
+        if (t <= 0.0) continue;
+        const double v = t*t*t;
+        const double u = stream_next(r);
+        if (log(u > 0.0 ? u : 1e-300) < 0.5*x*x + d - d*v + d*log(v)) return boost*d*v;
+    }
+    return boost*d;
+}
+
+static int64_t nbd_draw(o_stream *r, double k, double scale) {
+    const double y = scale*gamma_draw(r, k);
+    if (y < 1e-15) return 0;
+    const double m = floor(y);
+    const double pm = exp(m*log(y) - y - lgamma(m + 1.0));
+    return poisson_mode(y, pm, stream_next(r));
+}
+
 void oracle_multiplicities(const double *lambda, const double *pmode, const o_species *sp, int ns,
-                           int64_t nev, int64_t ev_begin, uint64_t seed, int model, int lcc,
-                           int64_t *mult /*[nev][ns]*/, int64_t *out_count /*[nev][ns]*/) {
+                           int64_t nev, int64_t ev_begin, uint64_t seed, int model, double para1,
+                           int lcc, int64_t *mult /*[nev][ns]*/, int64_t *out_count /*[nev][ns]*/) {
     for (int64_t ev = 0; ev < nev; ev++)
         for (int s = 0; s < ns; s++) {
             o_stream r;
             stream_init(&r, seed, STREAM_MULT, (uint32_t)s, (uint32_t)(ev_begin + ev), 0);
-            const double u = stream_next(&r);
             int64_t n;
             if (model == 1) {
+                const double u = stream_next(&r);
                 n = (int64_t)lambda[s];
                 if (u < lambda[s] - (double)n) n++;
+            } else if (model == 10 || model == 20) {
+                const int64_t dN_int = (int64_t)lambda[s];
+                const double k = (model == 10) ? para1*(lambda[s] - (double)dN_int) : para1*lambda[s];
+                if (k < 1e-15) n = dN_int;
+                else n = ((model == 10) ? dN_int : 0) + nbd_draw(&r, k, para1);
             } else {
-                n = poisson_mode(lambda[s], pmode[s], u);
+                n = poisson_mode(lambda[s], pmode[s], stream_next(&r));
             }
             int64_t nout = n;
             if (lcc == 1) { /* src/FSSW.cpp:931-938, 1035-1048 */

@@ -354,7 +354,7 @@ def philox(ctr, key):
     return out
 
 
-def multiplicities(lam, pmode, species, nev, ev_begin, seed, model=30, lcc=0):
+def multiplicities(lam, pmode, species, nev, ev_begin, seed, model=30, lcc=0, para1=0.16):
     lam = np.ascontiguousarray(lam, dtype=np.float64)
     pmode = np.ascontiguousarray(pmode, dtype=np.float64)
     sp = np.ascontiguousarray(species)
@@ -363,7 +363,7 @@ def multiplicities(lam, pmode, species, nev, ev_begin, seed, model=30, lcc=0):
     outc = np.zeros((nev, ns), dtype=np.int64)
     clib().oracle_multiplicities(_p(lam), _p(pmode), _p(sp), C.c_int(ns), C.c_int64(nev),
                                  C.c_int64(ev_begin), C.c_uint64(seed), C.c_int(model),
-                                 C.c_int(lcc), _p(mult), _p(outc))
+                                 C.c_double(para1), C.c_int(lcc), _p(mult), _p(outc))
     return mult, outc
 
 

@@ -93,9 +93,9 @@ def test_c_abi_error_conventions(built, tmp_path):
         assert L.iss_cuda_upload_surface(e.h, None, 10) == 2
         assert L.iss_cuda_upload_table(e.h, 99, capi._ptr(np.zeros(4)), 2, 2, None) == 2
         o = capi.Options()
-        o.dN_dy_sampling_model = 10         # negative binomial: not implemented, rejected loudly
+        o.dN_dy_sampling_model = 7          # not a model of FSSW::determine_number_to_sample
         assert L.iss_cuda_set_options(e.h, C.byref(o)) == 2
-        assert b"not implemented" in L.iss_cuda_last_error(e.h)
+        assert b"dN_dy_sampling_model" in L.iss_cuda_last_error(e.h)
         assert L.iss_cuda_destroy(None) == 0
     finally:
         e.close()

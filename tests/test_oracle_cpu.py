@@ -111,6 +111,36 @@ def test_poisson_inversion_is_poisson():
     assert abs(m1[:, 3].mean() - 4.5) < 0.02
 
 
+def test_negative_binomial_models():
+    """models 10 and 20 (FSSW.cpp:275-292): X ~ NB(n = k, p = 1/(1+para1)); mean k para1,
+    variance k para1 (1 + para1); model 10 adds the draw to the integer part."""
+    para1 = 0.16
+    lam = np.array([0.37, 4.5, 167.2, 2251.25])
+    sp = np.zeros(len(lam), dtype=orc.OSpecies)
+    pm = orc.poisson_pmode(lam)
+    nev = 40000
+    m20, _ = orc.multiplicities(lam, pm, sp, nev, 0, 7, model=20, para1=para1)
+    for j, dN in enumerate(lam):
+        k = para1*dN
+        mean, var = k*para1, k*para1*(1 + para1)
+        x = m20[:, j].astype(float)
+        assert abs(x.mean() - mean) < 5*np.sqrt(var/nev) + 1e-12
+        assert abs(x.var() - var) < 0.06*var + 5*var*np.sqrt(2.0/nev)
+    # pmf of one case against scipy
+    k = para1*lam[2]
+    cnt = np.bincount(m20[:, 2], minlength=30)[:30]
+    exp = stats.nbinom.pmf(np.arange(30), k, 1.0/(1 + para1))*nev
+    msk = exp > 10
+    chi2 = ((cnt[msk] - exp[msk])**2/exp[msk]).sum()
+    assert stats.chi2.sf(chi2, msk.sum() - 1) > 1e-3
+    m10, _ = orc.multiplicities(lam, pm, sp, nev, 0, 8, model=10, para1=para1)
+    for j, dN in enumerate(lam):
+        frac = dN - np.floor(dN)
+        x = m10[:, j].astype(float) - np.floor(dN)
+        assert x.min() >= 0
+        assert abs(x.mean() - para1*frac*para1) < 5*np.sqrt(para1*frac*para1*(1 + para1)/nev) + 1e-12
+
+
 def test_momentum_sampler_matches_reference():
     """|p| spectra of MomentumSamplerShell::Sample_a_momentum (2e6 samples per case from the
     compiled reference) against the C restatement; two-sample chi2, p > 1e-3 per case (ten cases)

@@ -105,6 +105,38 @@ def test_hadrons_match_oracle(name, nev, extra, built, tmp_path):
         s.close()
 
 
+@pytest.mark.parametrize("model", [10, 20])
+def test_negative_binomial_multiplicities(model, built, tmp_path):
+    """dN_dy_sampling_model 10 / 20 on the device against the analytic negative-binomial moments
+    (and the oracle's restatement, statistically: these models go through libm transcendentals, so
+    CPU and GPU agree in distribution, not bit for bit)."""
+    capi = built
+    para1 = 0.16
+    g, s = prepare(capi, "viscous2", tmp_path, {"dN_dy_sampling_model": model,
+                                                "dN_dy_sampling_para1": para1})
+    try:
+        e = s.engine()
+        dN = e.compute_yields()
+        nev = 1500
+        e.sample(11, 0, nev)
+        mult = e.multiplicities(nev).astype(float)
+        sel = np.argsort(dN)[-40:]                 # the 40 most abundant species
+        for j in sel:
+            if model == 20:
+                k, base = para1*dN[j], 0.0
+            else:
+                k, base = para1*(dN[j] - np.floor(dN[j])), np.floor(dN[j])
+            mean, var = base + k*para1, k*para1*(1 + para1)
+            assert abs(mult[:, j].mean() - mean) < 5*np.sqrt(var/nev) + 1e-9, (j, dN[j])
+        lam, pm = e.poisson_params()
+        om, _ = orc.multiplicities(lam, pm, s.species(), nev, 0, 11, model=model, para1=para1)
+        j = sel[-1]
+        assert abs(om[:, j].mean() - mult[:, j].mean()) < 6*np.sqrt(2*para1*dN[j]*para1*(1 + para1)/nev) + 1e-9
+        assert e.fetch_all().shape[0] == int(mult.sum())
+    finally:
+        s.close()
+
+
 def test_event_sharding_is_bit_reproducible(built, tmp_path):
     """Philox keyed by (event, species, draw): any split of the event range gives the same bytes
     (the property the 1/2/4/8-GPU event sharding relies on)."""
