@@ -234,7 +234,10 @@ ISS_API int iss_cuda_histograms(iss_handle *h, const int32_t *pids, int32_t npid
 ISS_API int iss_cuda_qa_device_ptr(iss_handle *h, void **dptr);
 ISS_API int iss_cuda_qa_fetch(iss_handle *h, double *dst_host);
 
-/* ---- timing: accumulated device time (CUDA events on the handle's stream) per kernel family */
+/* ---- timing: accumulated device time per kernel family.  While enabled, every family span is
+ *      bracketed by a pair of CUDA events recorded on the handle's stream WITHOUT synchronising;
+ *      the pairs are resolved (one stream synchronisation) by the next call of this function.
+ *      launches_host counts every kernel launch of the library, enabled or not.              */
 enum { ISS_T_YIELDS = 0, ISS_T_SCAN, ISS_T_MULT, ISS_T_SAMPLE /* proposal kernel */, ISS_T_DECAY,
        ISS_T_QA, ISS_T_SETUP /* sampler set-up kernel */, ISS_T_NKIND };
 ISS_API int iss_cuda_timing(iss_handle *h, int enable, double *ms_host /*[ISS_T_NKIND]*/,

@@ -146,6 +146,7 @@ struct iss_handle {
     int64_t *d_event_off = nullptr;     // [nev+1]
     int64_t event_off_cap = 0;
     void *d_sampler_args = nullptr;
+    void *d_hints = nullptr; size_t hints_bytes = 0;
     void *d_tasks = nullptr; size_t tasks_bytes = 0;     // sampler task list of the batch
     unsigned long long *d_counters = nullptr;   // [8] tries, redraws, error flags...
     bool have_batch = false;

@@ -255,6 +255,7 @@ struct SamplerArgs {
     double y_LB, y_RB;
     uint64_t seed;
     Task *tasks;                    // [nwork]
+    const int2 *hints;              // [ceil(nwork/SETUP_THREADS)] (species, event) of item b*SETUP_THREADS
     iss_hadron *out;
     unsigned long long *counters;   // [0] task cursor, [1] tries, [2] redraws, [3] range errors
     int32_t *trace_cell;            // optional [n_out]
@@ -418,6 +419,27 @@ __device__ __forceinline__ uint32_t sample_stream_word3(int s) {
     return (static_cast<uint32_t>(STREAM_SAMPLE) << 24) | static_cast<uint32_t>(s);
 }
 
+// (species, event) of every SETUP_THREADS-th work item by full binary searches; setup_kernel's
+// threads start from these hints
+__global__ void work_hint_kernel(const int64_t *__restrict__ off_work, int ns, int64_t nev,
+                                 int64_t nwork, int2 *__restrict__ hints, int64_t nhint) {
+    const int64_t b = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (b >= nhint) return;
+    const int64_t w = min(b*SETUP_THREADS, nwork - 1);
+    int slo = 0, shi = ns;
+    while (shi - slo > 1) {
+        const int mid = (slo + shi) >> 1;
+        if (__ldg(&off_work[static_cast<int64_t>(mid)*nev]) <= w) slo = mid; else shi = mid;
+    }
+    const int64_t *__restrict__ ow = off_work + static_cast<int64_t>(slo)*nev;
+    int64_t elo = 0, ehi = nev;
+    while (ehi - elo > 1) {
+        const int64_t mid = (elo + ehi) >> 1;
+        if (__ldg(&ow[mid]) <= w) elo = mid; else ehi = mid;
+    }
+    hints[b] = make_int2(slo, static_cast<int>(elo));
+}
+
 // K5a: one thread per hadron of the batch: identity (species, event, draw) from the species-major
 // work offsets, output slot, cell choice (first block of the hadron's stream) and the two series
 // values of the |p| sampler.  Massively parallel, so the dependent loads of the two binary
@@ -435,14 +457,19 @@ setup_kernel(const SamplerArgs A) {
     unsigned long long my_range = 0;
     for (int64_t w = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x; w < A.nwork;
          w += static_cast<int64_t>(gridDim.x)*blockDim.x) {
-        int slo = 0, shi = A.ns;
-        while (shi - slo > 1) {
-            const int mid = (slo + shi) >> 1;
-            if (sp_off[mid] <= w) slo = mid; else shi = mid;
-        }
-        const int s = slo;
+        // (species, event) of work item w: start from the hint stored for the first item of this
+        // group of SETUP_THREADS consecutive items and move forward (work items are species-major,
+        // event-minor, so the answer is at or after the hint)
+        const int2 hint = __ldg(&A.hints[w/SETUP_THREADS]);
+        int s = hint.x;
+        while (sp_off[s + 1] <= w) s++;
         const int64_t *__restrict__ ow = A.off_work + static_cast<int64_t>(s)*A.nev;
-        int64_t elo = 0, ehi = A.nev;
+        int64_t elo = (s == hint.x) ? hint.y : 0, step = 1;
+        while (elo + step < A.nev && __ldg(&ow[elo + step]) <= w) {
+            elo += step;
+            step <<= 1;
+        }
+        int64_t ehi = min(elo + step, A.nev);
         while (ehi - elo > 1) {
             const int64_t mid = (elo + ehi) >> 1;
             if (__ldg(&ow[mid]) <= w) elo = mid; else ehi = mid;
@@ -1038,6 +1065,17 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         }
         A.tasks = static_cast<Task *>(h->d_tasks);
     }
+    const int64_t nhint = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
+    {
+        const size_t need = sizeof(int2)*static_cast<size_t>(nhint);
+        if (need > h->hints_bytes || !h->d_hints) {
+            if (h->d_hints) cudaFree(h->d_hints);
+            h->d_hints = nullptr;
+            h->hints_bytes = need + need/8 + 4096;
+            ISS_CUDA_TRY(h, cudaMalloc(&h->d_hints, h->hints_bytes));
+        }
+        A.hints = static_cast<const int2 *>(h->d_hints);
+    }
     if (!h->d_sampler_args) ISS_CUDA_TRY(h, cudaMalloc(&h->d_sampler_args, sizeof(SamplerArgs)));
     ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_sampler_args, &A, sizeof(SamplerArgs), cudaMemcpyHostToDevice,
                                     h->stream));
@@ -1049,6 +1087,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
         int64_t grid = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
         if (grid > static_cast<int64_t>(nsm)*32) grid = static_cast<int64_t>(nsm)*32;
+        work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
+            h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
         setup_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());

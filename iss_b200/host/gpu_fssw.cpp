@@ -550,7 +550,9 @@ void GpuFSSW::sample_events() {
     // the sampling of the next (at least 8 batches for large runs)
     int64_t free_b = 0, total_b = 0;
     check_(iss_cuda_mem_info(h_, &free_b, &total_b), "iss_cuda_mem_info");
-    const double per_event = std::max(1.0, dN_event)*40.0*(flag_perform_decays_ ? 6.0 : 2.5)
+    // device bytes per primary hadron: two 40-B output buffers + 48-B task (+ decays: counts,
+    // decayed list ~1.6x longer) with head-room for Poisson fluctuations
+    const double per_event = std::max(1.0, dN_event)*(flag_perform_decays_ ? 320.0 : 150.0)
                              + 24.0*species_.size();
     int64_t batch = static_cast<int64_t>(0.5*static_cast<double>(free_b)/per_event);
     const double hadrons_total = dN_event*static_cast<double>(nev_);
