@@ -244,12 +244,9 @@ int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate) {
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
     const size_t smem = sizeof(QaShared);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(qa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem));
-        attr_set = true;
-    }
+    // per device and cheap: set on every call (a process may drive several devices)
+    ISS_CUDA_TRY(h, cudaFuncSetAttribute(qa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem)));
     int64_t grid = std::min<int64_t>(A.nev, static_cast<int64_t>(nsm)*2);
     if (grid < 1) grid = 1;
     {
