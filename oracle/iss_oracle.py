@@ -328,6 +328,9 @@ def clib():
     global _lib
     if _lib is None:
         path = os.path.join(HERE, "_build", "libiss_oracle.so")
+        if not os.path.exists(path):
+            import subprocess
+            subprocess.run(["make", "-C", HERE, "port"], check=True, stdout=subprocess.DEVNULL)
         _lib = C.CDLL(path)
         _lib.oracle_sample.restype = C.c_int64
         _lib.oracle_decay.restype = C.c_int64
