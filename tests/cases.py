@@ -13,7 +13,7 @@ FIX = os.path.join(HERE, "fixtures")
 
 ONE_CELL = ["ideal1", "ideal2", "ideal3", "ideal4", "viscous1", "viscous2"]
 SYNTH = ["s3d_ce", "s3d_ce_diff", "s3d_14mom", "s2d_smash_ce", "s3d_ideal_b", "s3d_bulk1",
-         "s3d_boltzmann"]
+         "s3d_boltzmann", "s2d_urqmd_bin"]
 
 
 def load(name, kind="yields"):

@@ -56,6 +56,8 @@ SYNTH = {
                         param="iSS_parameters_ideal.dat", over=["bulk_deltaf_kind=21"]),
     "s3d_bulk1": dict(gen=dict(ncell=240, seed=99, eos=9), param="iSS_parameters_CEdeltaf.dat",
                       over=["bulk_deltaf_kind=1"]),
+    "s2d_urqmd_bin": dict(gen=dict(ncell=240, seed=4242, eos=9, boost_invariant=True, binary=1),
+                          param="iSS_parameters_CEdeltaf.dat", over=["hydro_mode=1"]),
     "s3d_boltzmann": dict(gen=dict(ncell=120, seed=5, eos=9), param="iSS_parameters_CEdeltaf.dat",
                           over=["quantum_statistics=0"]),
 }
@@ -83,8 +85,10 @@ def read_dump(prefix):
     return lrf, sp, y
 
 
-def golden_yields():
+def golden_yields(only=None):
     for name, (mi, param, surf, over) in ONE_CELL.items():
+        if only and name not in only:
+            continue
         d = workdir()
         case = os.path.join(d, "case")
         os.makedirs(case)
@@ -98,6 +102,8 @@ def golden_yields():
         print(name, lrf.shape, y.shape, "sum=%.17g" % y.sum())
         shutil.rmtree(d)
     for name, spec in SYNTH.items():
+        if only and name not in only:
+            continue
         d = workdir()
         g = dict(spec["gen"])
         cells = synthetic.make_case(os.path.join(d, "case"), **g)
@@ -281,7 +287,7 @@ def golden_writers():
 if __name__ == "__main__":
     what = sys.argv[1:] or ["yields", "stats", "momentum", "decay", "writers"]
     if "yields" in what:
-        golden_yields()
+        golden_yields([w for w in what if w in ONE_CELL or w in SYNTH] or None)
     if "momentum" in what:
         golden_momentum()
     if "decay" in what:
