@@ -127,6 +127,15 @@ STATS = {
                                cell="viscous1_small", over=[]),
     "cell_ideal_muB": dict(music="14", param="iSS_parameters_ideal.dat", nev=20000, seed=3,
                            cell="ideal4_small", over=["bulk_deltaf_kind=21"]),
+    # Grad (14-moment) shear delta f with mu_B, mu_S, mu_Q != 0 (bulk off: the reference's kind-11
+    # bulk table is uninitialised)
+    "cell_shear_grad_muB": dict(music="14", param="iSS_parameters.dat", nev=20000, seed=6,
+                                cell="viscous4_small",
+                                over=["bulk_deltaf_kind=11", "include_deltaf_bulk=0",
+                                      "include_deltaf_shear=1"]),
+    # local charge conservation: positive species paired with their conjugates from the same cell
+    "cell_lcc": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=20000, seed=7,
+                     cell="viscous2_small", over=["local_charge_conservation=1"]),
     "surf3d_ce_diff": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=4,
                            gen=dict(ncell=2000, seed=2024, eos=14, rhob=1, diffusion=1, binary=1),
                            over=["include_deltaf_diffusion=1"]),
@@ -143,8 +152,10 @@ def small_cell(fixture, scale):
     return v
 
 
-def golden_stats():
+def golden_stats(only=None):
     for name, spec in STATS.items():
+        if only and name not in only:
+            continue
         d = workdir()
         case = os.path.join(d, "case")
         os.makedirs(case)
@@ -154,7 +165,8 @@ def golden_stats():
                         os.path.join(case, "music_input"))
             fixture = {"viscous2_small": "testViscousOneFluidCell2.dat",
                        "viscous1_small": "testViscousOneFluidCell1.dat",
-                       "ideal4_small": "testIdealOneFluidCell4.dat"}[spec["cell"]]
+                       "ideal4_small": "testIdealOneFluidCell4.dat",
+                       "viscous4_small": "testViscousOneFluidCell4.dat"}[spec["cell"]]
             v = small_cell(fixture, 0.01)
             np.savetxt(os.path.join(case, "surface.dat"), v[None, :], fmt="%.16e")
             extra["cell_line"] = v
@@ -293,6 +305,6 @@ if __name__ == "__main__":
     if "decay" in what:
         golden_decay()
     if "stats" in what:
-        golden_stats()
+        golden_stats([w for w in what if w in STATS] or None)
     if "writers" in what:
         golden_writers()
