@@ -96,6 +96,30 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pins this rank (and the threads/pinned buffers it creates later) to the NUMA node of its GPU:
+    with one process per GPU, the 2.2 GB/step device->host hadron stream otherwise crosses the
+    socket interconnect for half of the ranks.  Returns a short description for the JSON line."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return "numa node unknown for %s" % bdf
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no allowed cpus on node %d" % node
+        os.sched_setaffinity(0, cpus)
+        return "gpu %s -> numa node %d (%d cpus)" % (bdf, node, len(cpus))
+    except Exception as exc:        # placement is an optimisation, never a failure
+        return "not bound (%s)" % type(exc).__name__
+
+
 def make_case(folder, ncell):
     from iss_b200 import synthetic
     synthetic.make_case(folder, ncell=ncell, seed=SURFACE_SEED, eos=14, rhob=1, diffusion=1, binary=1)
@@ -126,6 +150,7 @@ def run_engine(args):
     os.dup2(2, 1)
     torch.cuda.set_device(local)
     os.environ["ISS_CUDA_DEVICE"] = str(local)
+    numa = bind_to_gpu_numa_node(local) if os.environ.get("ISS_BENCH_NUMA", "1") == "1" else "off"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -274,7 +299,7 @@ def run_engine(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.cells, E), "cells": ncell, "species": ns,
                    "events_per_step_per_gpu": E, "sharding": "events (weak), surface replicated",
-                   "l2": "inputs_larger_than_L2", "seed": args.seed},
+                   "l2": "inputs_larger_than_L2", "seed": args.seed, "host_placement": numa},
         "yields_per_sec": ycs/yields_s if yields_s > 0 else None,
         "sampler_hadrons_per_sec_kernel": hadrons/sample_s if sample_s > 0 else None,
         "kernel_ms": {k: v/args.steps for k, v in fam_ms.items()},
