@@ -236,9 +236,8 @@ static_assert(sizeof(Task) == 48, "Task must stay 48 bytes");
 struct SamplerArgs {
     const float *cells;             // [ncell][CELL_STRIDE]
     const double *cellcoef;         // [ncell][COEF_STRIDE]
-    int64_t ncell, ncell_pad, ntile;
+    int64_t ncell, ncell_pad;
     const double *cdf;              // [ns][ncell_pad] global inclusive prefix of the yields
-    const double *tilebase;         // [ns][ntile+1]
     const double *cdflev;           // [ns][lev_stride] 16-ary search levels over cdf
     int nlev;
     int64_t lev_off[8], lev_stride;
@@ -1012,9 +1011,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.cellcoef = h->d_cellcoef;
     A.ncell = h->ncell;
     A.ncell_pad = h->ncell_pad;
-    A.ntile = h->ntile;
     A.cdf = h->d_cdf;
-    A.tilebase = h->d_tilebase;
     A.cdflev = h->d_cdflev;
     A.nlev = h->nlev;
     for (int k = 0; k < 8; k++) A.lev_off[k] = h->lev_off[k];
@@ -1079,7 +1076,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     if (!h->d_sampler_args) ISS_CUDA_TRY(h, cudaMalloc(&h->d_sampler_args, sizeof(SamplerArgs)));
     ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_sampler_args, &A, sizeof(SamplerArgs), cudaMemcpyHostToDevice,
                                     h->stream));
-    int dev = 0, nsm = 148, occ = 1;
+    int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     {
@@ -1117,7 +1114,6 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     int64_t grid = nsm;         // persistent: one CTA per SM
     const int64_t max_useful = (total_work + SAMPLER_THREADS - 1)/SAMPLER_THREADS;
     if (grid > max_useful) grid = max_useful;
-    (void)occ;
     {
         ScopedTimer t(h, ISS_T_SAMPLE);
         kern<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(

@@ -21,6 +21,6 @@ for k in range(3):
     c = e.sample(1, (k+1)*E, (k+2)*E); n += c.n_hadrons
 ms, cnt = e.timing(enable=False)
 os.dup2(fd, 1)
-print("MINB=%s cells=%d ev=%d hadrons/step=%d tries/hadron=%.3f  ms/step: %s  sampler %.3e hadrons/s" % (
-    os.environ.get("ISS_SAMPLER_MINB", "4"), ncell, E, n//3, c.n_tries/c.n_hadrons,
+print("cells=%d ev=%d hadrons/step=%d tries/hadron=%.3f  ms/step: %s  sampler %.3e hadrons/s" % (
+    ncell, E, n//3, c.n_tries/c.n_hadrons,
     {k: round(v/3, 3) for k, v in ms.items()}, n/(ms["sample"]*1e-3)))
