@@ -200,6 +200,12 @@ ISS_API int iss_cuda_get_multiplicities(iss_handle *h, int64_t *counts_host);
 /* Poisson parameters the draws used: lambda[s], mode pmf pm[s] (for bit-exact CPU checks) */
 ISS_API int iss_cuda_get_poisson_params(iss_handle *h, double *lambda_host, double *pmode_host);
 
+/* ---- unit-level access to the |p| sampler (MomentumSamplerShell::Sample_a_momentum,
+ *      MomentumSamplerShell.cpp:24-48; the reference's Boson/FermionMomentumSampler_IntegratedTests
+ *      exercise exactly this call): n momentum magnitudes for fixed (mass, T, mu, sign).       */
+ISS_API int iss_cuda_sample_momentum(iss_handle *h, double mass, double T, double mu, int32_t sign,
+                                     int64_t n, uint64_t seed, double *p_host);
+
 /* ---- trace (test instrumentation): when enabled, the sampler also records for every output
  *      slot of the batch the cell it was emitted from and the number of accept/reject
  *      proposals it took; cell_host / tries_host receive n_hadrons int32 each (primaries,

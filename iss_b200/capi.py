@@ -80,7 +80,7 @@ CUDA_SYMBOLS = [
     "iss_cuda_histograms", "iss_cuda_qa_device_ptr", "iss_cuda_qa_fetch", "iss_cuda_timing",
     "iss_cuda_mem_info", "iss_cuda_host_alloc", "iss_cuda_host_free", "iss_cuda_fp64_peak",
     "iss_cuda_set_trace", "iss_cuda_get_trace", "iss_cuda_upload_surface_aos",
-    "iss_cuda_fetch_all_async", "iss_cuda_fetch_wait",
+    "iss_cuda_fetch_all_async", "iss_cuda_fetch_wait", "iss_cuda_sample_momentum",
 ]
 HOST_SYMBOLS = [
     "iss_host_create", "iss_host_destroy", "iss_host_set_param", "iss_host_get_param",
@@ -144,6 +144,7 @@ def cuda_lib():
         "iss_cuda_upload_surface_aos": (C.c_int, [vp, vp, i64]),
         "iss_cuda_fetch_all_async": (C.c_int, [vp, vp, i64, i64p]),
         "iss_cuda_fetch_wait": (C.c_int, [vp]),
+        "iss_cuda_sample_momentum": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, i32, i64, u64, vp]),
         "iss_cuda_set_trace": (C.c_int, [vp, C.c_int]),
         "iss_cuda_get_trace": (C.c_int, [vp, vp, vp]),
     }
@@ -317,6 +318,12 @@ class Engine:
         if n.value:
             self.check(self.L.iss_cuda_fetch_all(self.h, _ptr(out), n.value, C.byref(n)),
                        "fetch_all")
+        return out
+
+    def sample_momentum(self, mass, T, mu, sign, n, seed):
+        out = np.zeros(n)
+        self.check(self.L.iss_cuda_sample_momentum(self.h, mass, T, mu, sign, n, seed, _ptr(out)),
+                   "sample_momentum")
         return out
 
     def set_trace(self, enable):

@@ -467,6 +467,13 @@ int iss_cuda_get_poisson_params(iss_handle *h, double *lambda_host, double *pmod
     return ISS_OK;
 }
 
+int iss_cuda_sample_momentum(iss_handle *h, double mass, double T, double mu, int32_t sign,
+                             int64_t n, uint64_t seed, double *p_host) {
+    if (!h || !p_host || n <= 0) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    return run_momentum_unit(h, mass, T, mu, sign, n, seed, p_host);
+}
+
 int iss_cuda_set_trace(iss_handle *h, int enable) {
     if (!h) return ISS_ERR_ARG;
     h->trace = (enable != 0);

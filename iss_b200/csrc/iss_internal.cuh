@@ -248,6 +248,8 @@ int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev);
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t total);
 int run_decay(iss_handle *h, uint64_t seed);
 int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate);
+int run_momentum_unit(iss_handle *h, double m, double T, double mu, int sign, int64_t n,
+                      uint64_t seed, double *out_host);
 
 // grows *ptr to at least `need` bytes (contents are not preserved)
 inline int ensure_bytes(iss_handle *h, void **ptr, size_t *cap, size_t need) {

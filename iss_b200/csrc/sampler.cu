@@ -908,6 +908,63 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     }
 }
 
+// Unit-level entry for the |p| sampler alone (rows M of SURVEY.md section 8(a)): n draws of
+// MomentumSamplerShell::Sample_a_momentum(m, T, mu, sign) (MomentumSamplerShell.cpp:24-48), draw i
+// from stream (seed; SAMPLE, species 0, event i >> 20, draw i & 0xFFFFF), one proposal block per
+// iteration of the inner accept loop -- the protocol of the proposal kernel.
+__global__ void momentum_unit_kernel(const MomentumTable *__restrict__ mts, double m, double T,
+                                     double mu, int sign, int64_t n, uint64_t seed,
+                                     double *__restrict__ out, int *__restrict__ range_error) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    MomSetup M;
+    if (!momentum_setup(mts, m, sign, T, mu, M)) {
+        *range_error = 1;
+        return;
+    }
+    const MomentumTable &mt = mts[M.tab];
+    const uint32_t key0 = static_cast<uint32_t>(seed), key1 = static_cast<uint32_t>(seed >> 32);
+    uint32_t block = 0;
+    double p_mag, ratio;
+    uint32_t w0, w1, w2, w3;
+    do {
+        philox_block(block++, static_cast<uint32_t>(i & 0xFFFFF), static_cast<uint32_t>(i >> 20),
+                     sample_stream_word3(0), key0, key1, w0, w1, w2, w3);
+        const double r = u53(w0, w1)*M.cdf_max;
+        const double Et = inverse_cdf<false>(mt.data, mt.n, M, r);
+        const double E = M.T*Et + M.mu;
+        p_mag = sqrt(E*E - m*m);
+        ratio = (p_mag/E)/(1. - m*m/(2.*E*E));
+    } while (u32(w2) > ratio);
+    out[i] = p_mag;
+}
+
+int run_momentum_unit(iss_handle *h, double m, double T, double mu, int sign, int64_t n,
+                      uint64_t seed, double *out_host) {
+    int rc = ensure_momentum_tables(h);
+    if (rc) return rc;
+    MomentumTable *d_mt = nullptr;
+    double *d_out = nullptr;
+    int *d_err = nullptr;
+    ISS_CUDA_TRY(h, cudaMalloc(&d_mt, sizeof(MomentumTable)*6));
+    ISS_CUDA_TRY(h, cudaMalloc(&d_out, sizeof(double)*n));
+    ISS_CUDA_TRY(h, cudaMalloc(&d_err, sizeof(int)));
+    ISS_CUDA_TRY(h, cudaMemsetAsync(d_err, 0, sizeof(int), h->stream));
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(d_mt, h->momtab, sizeof(MomentumTable)*6, cudaMemcpyHostToDevice,
+                                    h->stream));
+    momentum_unit_kernel<<<static_cast<unsigned>((n + 127)/128), 128, 0, h->stream>>>(
+        d_mt, m, T, mu, sign, n, seed, d_out, d_err); ISS_LAUNCHED(h);
+    int err = 0;
+    cudaError_t e1 = cudaMemcpyAsync(out_host, d_out, sizeof(double)*n, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e2 = cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e3 = cudaStreamSynchronize(h->stream);
+    cudaFree(d_mt); cudaFree(d_out); cudaFree(d_err);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        ISS_FAIL(h, ISS_ERR_CUDA, "momentum unit kernel failed");
+    if (err) ISS_FAIL(h, ISS_ERR_RANGE, "[MomentumSampler] out of range (m/T - mu/T outside the tables)");
+    return ISS_OK;
+}
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------

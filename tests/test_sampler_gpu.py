@@ -137,6 +137,42 @@ def test_negative_binomial_multiplicities(model, built, tmp_path):
         s.close()
 
 
+def test_momentum_sampler_unit(built):
+    """Row M at the unit level, like the reference's Boson/FermionMomentumSampler_IntegratedTests:
+    |p| draws for fixed (m, T, mu, sign) on the device against (a) 2x10^6 draws per case of the
+    compiled reference (tests/golden/momentum_sampler.npz, two-sample chi2) and (b) the C
+    restatement driven by the same streams, draw by draw.  The reference's algorithm subtracts the
+    O(1) term CDF(a) from O(1) table values to get differences as small as e^-(m-mu)/T, so the 1e-16
+    differences between glibc and CUDA exp/log are amplified: observed median 1e-16..7e-11, maximum
+    2e-7 (m = 2.25 GeV); required: 1e-7 relative for >= 99.9 % of the draws, 1e-5 for all."""
+    from scipy import stats
+    import obs
+    capi = built
+    g = np.load(os.path.join(cases.GOLDEN, "momentum_sampler.npz"))
+    e = capi.Engine()
+    try:
+        n = 1000000
+        tot_chi2, tot_ndf = 0.0, 0
+        for i, (m, T, mu, sign) in enumerate(g["cases"]):
+            p = e.sample_momentum(float(m), float(T), float(mu), int(sign), n, 1000 + i)
+            assert np.all(np.isfinite(p)) and p.min() >= 0
+            h = np.histogram(p, g["edges"])[0]
+            chi2, ndf = obs.chi2_two_hist(h, g["hist"][i], n, int(g["n"]))
+            assert stats.chi2.sf(chi2, ndf) > 1e-3, (i, chi2, ndf)
+            tot_chi2 += chi2
+            tot_ndf += ndf
+            po = orc.sample_momentum(float(m), float(T), float(mu), int(sign), 20000, 1000 + i)
+            rel = np.abs(p[:20000] - po)/np.maximum(po, 1e-3)
+            assert (rel <= 1e-7).mean() >= 0.999, (i, (rel <= 1e-7).mean())
+            assert rel.max() < 1e-5, (i, rel.max())
+        assert stats.chi2.sf(tot_chi2, tot_ndf) > 0.01
+        # (m - mu)/T beyond the last table: reported, like the reference's exit(1)
+        with pytest.raises(capi.IssError, match="status 4"):
+            e.sample_momentum(20.0, 0.15, 0.0, 1, 10, 1)
+    finally:
+        e.close()
+
+
 def test_event_sharding_is_bit_reproducible(built, tmp_path):
     """Philox keyed by (event, species, draw): any split of the event range gives the same bytes
     (the property the 1/2/4/8-GPU event sharding relies on)."""
