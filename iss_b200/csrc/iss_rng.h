@@ -141,18 +141,32 @@ struct BlockStream {
 };
 
 #if defined(__CUDACC__)
-static __device__ __noinline__
+// Out of line on purpose (one copy of the ten unrolled rounds keeps the sampler's hot loop small);
+// the four words come back by value, i.e. in registers, not through the local-memory stack.
+static __device__ __noinline__ uint4 philox_block4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                   uint32_t k0, uint32_t k1) {
+    const uint32_t ctr[4] = {c0, c1, c2, c3};
+    const uint32_t key[2] = {k0, k1};
+    uint32_t out[4];
+    philox4x32_10(ctr, key, out);
+    return make_uint4(out[0], out[1], out[2], out[3]);
+}
+static __device__ __forceinline__ void philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                    uint32_t k0, uint32_t k1, uint32_t &w0,
+                                                    uint32_t &w1, uint32_t &w2, uint32_t &w3) {
+    const uint4 w = philox_block4(c0, c1, c2, c3, k0, k1);
+    w0 = w.x; w1 = w.y; w2 = w.z; w3 = w.w;
+}
 #else
-inline
-#endif
-void philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                  uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
+inline void philox_block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                         uint32_t &w0, uint32_t &w1, uint32_t &w2, uint32_t &w3) {
     const uint32_t ctr[4] = {c0, c1, c2, c3};
     const uint32_t key[2] = {k0, k1};
     uint32_t out[4];
     philox4x32_10(ctr, key, out);
     w0 = out[0]; w1 = out[1]; w2 = out[2]; w3 = out[3];
 }
+#endif
 
 // Exact Poisson draw by inversion from the mode ("chop-down" outward from
 // m = floor(lambda)).  pmode = Poisson pmf at m, computed once per species on the
