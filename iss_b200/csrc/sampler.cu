@@ -588,9 +588,12 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     float4 *lc_da = reinterpret_cast<float4 *>(sm_fermion + 4*A.mt[3].n);
     float4 *lc_pa = lc_da + SAMPLER_THREADS;
     float4 *lc_pb = lc_pa + SAMPLER_THREADS;
+    float4 *lc_u4 = lc_pb + SAMPLER_THREADS;        // ut, ux, uy, uz      (emit)
+    float4 *lc_pos = lc_u4 + SAMPLER_THREADS;       // tau, x, y, eta      (emit)
+    float2 *lc_tz = reinterpret_cast<float2 *>(lc_pos + SAMPLER_THREADS);   // t, z of the cell
     // derived per-(cell, species) doubles, [k][lane]: every division of the accept test that does
     // not depend on the proposed momentum is done once per hadron here
-    double *lc_d = reinterpret_cast<double *>(lc_pb + SAMPLER_THREADS);
+    double *lc_d = reinterpret_cast<double *>(lc_tz + SAMPLER_THREADS);
     enum { D_INV_T = 0, D_INV_DSIG, D_SHEAR, D_CB, D_C1, D_INV_KAPPA, D_PREFQ, D_COUNT };
     const int tid = threadIdx.x;
     LaneState L;
@@ -603,6 +606,12 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
         lc_da[tid] = da;
         lc_pa[tid] = __ldg(cr + 5);             // pixx, pixy, pixz, piyy
         lc_pb[tid] = __ldg(cr + 6);             // piyz, qx, qy, qz
+        lc_u4[tid] = __ldg(cr + 2);
+        lc_pos[tid] = __ldg(cr + 0);
+        {
+            const float4 tz = __ldg(cr + 7);    // t, z, spare, spare
+            lc_tz[tid] = make_float2(tz.x, tz.y);
+        }
         const double Tdec = th0.y;
         lc_d[D_INV_T*SAMPLER_THREADS + tid] = 1.0/L.M.T;
         lc_d[D_INV_DSIG*SAMPLER_THREADS + tid] = 1.0/L.dsigma_fac;
@@ -801,8 +810,8 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 }
                 if (u_acc < accept_prob) {
                     // ---- accepted: boost to the lab frame and emit (FSSW.cpp:1946-1960, 1969-1996)
-                    const float4 pos = __ldg(cr + 0);       // tau, x, y, eta
-                    const float4 u4 = __ldg(cr + 2);        // ut, ux, uy, uz
+                    const float4 pos = lc_pos[tid];         // tau, x, y, eta
+                    const float4 u4 = lc_u4[tid];           // ut, ux, uy, uz
                     const float pl0 = static_cast<float>(p0), pl1 = static_cast<float>(px),
                                 pl2 = static_cast<float>(py), pl3 = static_cast<float>(pz);
                     double p_dot_u = 0.;
@@ -827,7 +836,7 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                     if (hydro_mode == 2) {
                         // eta_s = cell eta: y = asinh(pz/mT) - eta + eta, p_z = mT sinh(y) = pLab[3],
                         // px = pT cos(atan2(py,px)) = pLab[1] up to FP64 rounding; t,z precomputed.
-                        const float4 tz = __ldg(cr + 7);    // t, z, spare, spare
+                        const float2 tz = lc_tz[tid];       // t, z of the cell
                         const double pzl = lab3;
                         hd.pz = lab3;
                         hd.E = static_cast<float>(sqrt(mT*mT + pzl*pzl));
@@ -1165,7 +1174,13 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         spec == 1 ? propose_kernel<1, 1> : spec == 2 ? propose_kernel<1, 2>
         : spec == 3 ? propose_kernel<1, 3> : propose_kernel<1, 0>;
     const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(double)*4*(A.mt[0].n + A.mt[3].n)
-                        + (3*sizeof(float4) + 7*sizeof(double))*SAMPLER_THREADS;
+                        + (5*sizeof(float4) + sizeof(float2) + 7*sizeof(double))*SAMPLER_THREADS;
+    {
+        int smem_max = 0;
+        cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (static_cast<int>(smem) > smem_max)
+            ISS_FAIL(h, ISS_ERR_ARG, "too many species for the proposal kernel's shared-memory species table");
+    }
     ISS_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     int64_t grid = nsm;         // persistent: one CTA per SM
