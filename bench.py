@@ -46,7 +46,7 @@ BYTES_PER_HADRON = 152.0     # 40 B record out + 112 B cell record in
 FLOP_PER_HADRON = 1.0e3
 BYTES_PER_YIELD = 8.2        # 8 B FP64 yield out + 64 B of cell fields / 321 species
 FLOP_PER_YIELD = 175.0       # CE bulk + diffusion series
-NCU_PROPOSE_TRAFFIC_BYTES = 15.61e9   # 12.78 GB read + 2.82 GB written per launch (profiles/r1_ncu_final.csv)
+NCU_PROPOSE_TRAFFIC_BYTES = 14.29e9   # 11.71 GB read + 2.58 GB written per launch (profiles/r1_ncu_final.csv)
 
 
 def load_peaks():
