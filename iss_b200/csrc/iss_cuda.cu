@@ -439,6 +439,13 @@ int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_e
         out->n_tries = static_cast<int64_t>(cnt[1]);
         out->n_cell_redraws = static_cast<int64_t>(cnt[2]);
     }
+    if (cnt[6] != 0) {
+        char buf[200];
+        snprintf(buf, sizeof(buf),
+                 "sampler gave up on %llu hadrons after %d rejected tries each (zero acceptance in "
+                 "every cell drawn); their records are null (pid 0)", cnt[6], 2000000);
+        ISS_FAIL(h, ISS_ERR_RANGE, buf);
+    }
     if (cnt[3] != 0) {
         char buf[160];
         snprintf(buf, sizeof(buf),

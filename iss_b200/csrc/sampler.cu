@@ -256,7 +256,8 @@ struct SamplerArgs {
     Task *tasks;                    // [nwork]
     const int2 *hints;              // [ceil(nwork/SETUP_THREADS)] (species, event) of item b*SETUP_THREADS
     iss_hadron *out;
-    unsigned long long *counters;   // [0] task cursor, [1] tries, [2] redraws, [3] range errors
+    unsigned long long *counters;   // [0] task cursor, [1] tries, [2] redraws, [3] range errors,
+                                    // [4],[5] decay errors, [6] hadrons given up
     int32_t *trace_cell;            // optional [n_out]
     int32_t *trace_tries;           // optional [n_out]
 };
@@ -265,6 +266,7 @@ constexpr int SETUP_THREADS = 256;
 constexpr int SAMPLER_THREADS = 768;     // one CTA of 24 warps per SM (640: 16.8 ms, 1024: 16.2 ms, 768: 15.5 ms on C4) (96 KB of tables in smem)
 constexpr int TASK_CHUNK = 128;         // tasks a warp reserves at a time
 constexpr int MAX_IMPATIENCE = 5000;    // FSSW.cpp:1872
+constexpr int MAX_TRIES_PER_HADRON = 2000000;   // safety valve, see propose_kernel
 
 // per-(cell, species) constants of the |p| sampler (MomentumSamplerBase::Sample_a_momentum)
 struct MomSetup {
@@ -644,7 +646,7 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     bool busy = false;
     int64_t chunk_next = 0, chunk_end = 0;      // tasks reserved by this warp
     bool more_work = true;
-    unsigned long long my_tries = 0, my_redraws = 0, my_range = 0;
+    unsigned long long my_tries = 0, my_redraws = 0, my_range = 0, my_giveup = 0;
 
     for (;;) {
         // ------------------------------------------------------------ hand tasks to idle lanes
@@ -883,7 +885,16 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 } else {
                     L.tries++;
                     if (L.tries >= MAX_IMPATIENCE) {
-                        if (L.qsign > 0) {
+                        if (L.total_tries > MAX_TRIES_PER_HADRON) {
+                            // The reference would loop forever on a (cell, species) pair that can
+                            // never be accepted (FSSW.cpp:977-1018); a kernel must not.  The slot
+                            // gets a null record (pid 0) and the call reports ISS_ERR_RANGE.
+                            float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
+#pragma unroll
+                            for (int q = 0; q < 5; q++) dst[q] = make_float2(0.f, 0.f);
+                            my_giveup++;
+                            busy = false;
+                        } else if (L.qsign > 0) {
                             // the reference's "impatience" (FSSW.cpp:1017-1018 with status == 0)
                             my_redraws++;
                             if (!lane_new_setup(Ag, L, p, true, key0, key1)) {
@@ -909,8 +920,10 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
         my_tries += __shfl_down_sync(full, my_tries, d);
         my_redraws += __shfl_down_sync(full, my_redraws, d);
         my_range += __shfl_down_sync(full, my_range, d);
+        my_giveup += __shfl_down_sync(full, my_giveup, d);
     }
     if (lane == 0) {
+        if (my_giveup) atomicAdd(&A.counters[6], my_giveup);
         if (my_tries) atomicAdd(&A.counters[1], my_tries);
         if (my_redraws) atomicAdd(&A.counters[2], my_redraws);
         if (my_range) atomicAdd(&A.counters[3], my_range);
