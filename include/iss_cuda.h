@@ -11,7 +11,8 @@
  *
  * Conventions: plain C types, opaque handle, one handle per GPU, caller-owned
  * host buffers, `int` status (0 = ok, !=0 = error; text via iss_cuda_last_error).
- * No exceptions cross this boundary.  There is NO CPU fallback: every call
+ * No exceptions cross this boundary.  A handle is not thread-safe: use it from one
+ * thread at a time (different handles may be used concurrently).  There is NO CPU fallback: every call
  * fails with ISS_ERR_CUDA when no sm_100-class device is usable.
  */
 #ifndef ISS_CUDA_H_

@@ -534,10 +534,8 @@ int iss_cuda_fetch_event(iss_handle *h, int64_t iev, iss_hadron *dst, int64_t ca
     if (!h->have_batch) ISS_FAIL(h, ISS_ERR_STATE, "no sampled batch");
     const int64_t nev = h->ev_end - h->ev_begin;
     if (iev < 0 || iev >= nev) ISS_FAIL(h, ISS_ERR_ARG, "event index out of range");
-    int64_t off[2];
-    ISS_CUDA_TRY(h, cudaMemcpyAsync(off, h->d_event_off + iev, sizeof(off), cudaMemcpyDeviceToHost,
-                                    h->stream));
-    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    // offsets were mirrored into mapped pinned memory when the batch was produced
+    const int64_t off[2] = {h->h_evoff[iev], h->h_evoff[iev + 1]};
     *n = off[1] - off[0];
     if (!dst) return ISS_OK;
     if (*n > cap) ISS_FAIL(h, ISS_ERR_ARG, "destination too small");
