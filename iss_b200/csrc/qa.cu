@@ -19,13 +19,12 @@ struct QaArgs {
     int32_t pids[ISS_QA_NSPEC];
     int npid;
     const iss_decay_species *dsp;
-    const int32_t *sorted_pid;
-    const int32_t *sorted_idx;
     int ndsp;
     double *qa;
 };
 
 constexpr int QA_THREADS = 256;
+constexpr int QA_HASH_BITS = 11, QA_HASH = 1 << QA_HASH_BITS;
 
 __device__ __forceinline__ double block_sum(double v, double *red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -53,7 +52,41 @@ struct QaShared {
     double pt_sum[ISS_QA_NSPEC][ISS_QA_NPT];
     double v2_num[ISS_QA_NSPEC][ISS_QA_NV2];
     double red[QA_THREADS/32];
+    // pid -> (tracked slot, B, S, Q): open-addressing hash, built once per CTA.  Hadrons are
+    // species-ordered inside an event, but most of the ~300 species have fewer hadrons per event
+    // than the CTA has threads, so nearly every record a thread reads has a new pid.
+    int hash_key[QA_HASH];
+    int hash_val[QA_HASH];
 };
+
+// (k + 1) | B << 8 | S << 16 | Q << 24 with signed 8-bit charges; k = -1: not tracked
+__device__ __forceinline__ int qa_pack(int k, int b, int sq, int q) {
+    return ((k + 1) & 0xff) | ((b & 0xff) << 8) | ((sq & 0xff) << 16) | ((q & 0xff) << 24);
+}
+__device__ __forceinline__ unsigned qa_hash(int pid) {
+    return (static_cast<unsigned>(pid)*2654435761u) >> (32 - QA_HASH_BITS);
+}
+__device__ __forceinline__ void qa_hash_insert(QaShared &S, int pid, int val) {
+    unsigned slot = qa_hash(pid);
+    for (;;) {
+        const int old = atomicCAS(&S.hash_key[slot], 0, pid);
+        if (old == 0 || old == pid) {
+            S.hash_val[slot] = val;
+            return;
+        }
+        slot = (slot + 1) & (QA_HASH - 1);
+    }
+}
+// val of pid, or qa_pack(-1, 0, 0, 0) = 0 when the pid is unknown
+__device__ __forceinline__ int qa_hash_find(const QaShared &S, int pid) {
+    unsigned slot = qa_hash(pid);
+    for (;;) {
+        const int key = S.hash_key[slot];
+        if (key == pid) return S.hash_val[slot];
+        if (key == 0) return 0;
+        slot = (slot + 1) & (QA_HASH - 1);
+    }
+}
 
 __global__ void __launch_bounds__(QA_THREADS)
 qa_kernel(const QaArgs A) {
@@ -62,6 +95,20 @@ qa_kernel(const QaArgs A) {
     double *qa = A.qa;
     for (int i = threadIdx.x; i < static_cast<int>(sizeof(QaShared)/4); i += blockDim.x)
         reinterpret_cast<unsigned int *>(qa_smem)[i] = 0u;
+    __syncthreads();
+    // tracked pids first (charges 0), then the particle table (overwrites with the charges)
+    if (threadIdx.x < A.npid && A.pids[threadIdx.x] != 0)
+        qa_hash_insert(S, A.pids[threadIdx.x], qa_pack(threadIdx.x, 0, 0, 0));
+    __syncthreads();
+    if (A.dsp) {
+        for (int j = threadIdx.x; j < A.ndsp; j += blockDim.x) {
+            const iss_decay_species &d = A.dsp[j];
+            int k = -1;
+            for (int q = 0; q < A.npid; q++)
+                if (A.pids[q] == d.pid) k = q;
+            if (d.pid != 0) qa_hash_insert(S, d.pid, qa_pack(k, d.baryon, d.strange, d.charge));
+        }
+    }
     __syncthreads();
 
     // plain sums over all hadrons this thread sees (reduced once, at the end)
@@ -77,8 +124,25 @@ qa_kernel(const QaArgs A) {
     for (int64_t ev = blockIdx.x; ev < A.nev; ev += gridDim.x) {
         const int64_t b = A.event_off[ev], e = A.event_off[ev + 1];
         double P[4] = {0., 0., 0., 0.};
-        for (int64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
-            const iss_hadron hd = A.hadrons[i];
+        // 40-byte records as five 8-byte loads, the next record in flight while this one is binned
+        const float2 *rec = reinterpret_cast<const float2 *>(A.hadrons);
+        float2 nx[5];
+        int64_t i = b + threadIdx.x;
+        if (i < e) {
+#pragma unroll
+            for (int q = 0; q < 5; q++) nx[q] = __ldg(rec + 5*i + q);
+        }
+        for (; i < e; i += blockDim.x) {
+            iss_hadron hd;
+            hd.pid = __float_as_int(nx[0].x); hd.mass = nx[0].y;
+            hd.E = nx[1].x; hd.px = nx[1].y;
+            hd.py = nx[2].x; hd.pz = nx[2].y;
+            hd.t = nx[3].x; hd.x = nx[3].y;
+            hd.y = nx[4].x; hd.z = nx[4].y;
+            if (i + blockDim.x < e) {
+#pragma unroll
+                for (int q = 0; q < 5; q++) nx[q] = __ldg(rec + 5*(i + blockDim.x) + q);
+            }
             const double p[4] = {hd.E, hd.px, hd.py, hd.pz};
             const double inv_e = 1.0/p[0];
 #pragma unroll
@@ -88,27 +152,12 @@ qa_kernel(const QaArgs A) {
                 for (int c = a; c < 4; c++) T[4*a + c] += p[a]*p[c]*inv_e;
             }
             if (hd.pid != last_pid) {
-                // hadrons are species-ordered inside an event: the look-ups below are rare
                 last_pid = hd.pid;
-                last_k = -1;
-                for (int j = 0; j < A.npid; j++)
-                    if (A.pids[j] == hd.pid) last_k = j;
-                last_q[0] = last_q[1] = last_q[2] = 0.;
-                if (A.dsp) {
-                    int lo = 0, hi = A.ndsp - 1;
-                    while (lo <= hi) {
-                        const int mid = (lo + hi) >> 1;
-                        const int v = __ldg(&A.sorted_pid[mid]);
-                        if (v == hd.pid) {
-                            const iss_decay_species &s = A.dsp[__ldg(&A.sorted_idx[mid])];
-                            last_q[0] = s.baryon;
-                            last_q[1] = s.strange;
-                            last_q[2] = s.charge;
-                            break;
-                        }
-                        if (v < hd.pid) lo = mid + 1; else hi = mid - 1;
-                    }
-                }
+                const int v = qa_hash_find(S, hd.pid);
+                last_k = (v & 0xff) - 1;
+                last_q[0] = static_cast<double>(static_cast<signed char>((v >> 8) & 0xff));
+                last_q[1] = static_cast<double>(static_cast<signed char>((v >> 16) & 0xff));
+                last_q[2] = static_cast<double>(static_cast<signed char>((v >> 24) & 0xff));
             }
             net[0] += last_q[0];
             net[1] += last_q[1];
@@ -230,6 +279,8 @@ int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate) {
         accumulate = 0;
     }
     if (!accumulate) ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_qa, 0, sizeof(double)*nq, h->stream));
+    if (h->ndsp + npid > QA_HASH*3/4)
+        ISS_FAIL(h, ISS_ERR_ARG, "particle table too large for the QA kernel's pid hash");
     QaArgs A;
     A.hadrons = h->decayed ? h->d_hadrons2 : h->d_hadrons;
     A.event_off = h->d_event_off;
@@ -237,8 +288,6 @@ int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate) {
     for (int i = 0; i < ISS_QA_NSPEC; i++) A.pids[i] = (i < npid) ? pids[i] : 0;
     A.npid = npid;
     A.dsp = h->d_dsp;
-    A.sorted_pid = h->d_sorted_pid;
-    A.sorted_idx = h->d_sorted_idx;
     A.ndsp = h->ndsp;
     A.qa = h->d_qa;
     int nsm = 148;

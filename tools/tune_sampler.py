@@ -19,6 +19,7 @@ n = 0
 for k in range(3):
     e.compute_yields()
     c = e.sample(1, (k+1)*E, (k+2)*E); n += c.n_hadrons
+    e.L.iss_cuda_histograms(e.h, capi._ptr(np.asarray([211, 2212], dtype=np.int32)), 2, 0)
 ms, cnt = e.timing(enable=False)
 os.dup2(fd, 1)
 print("cells=%d ev=%d hadrons/step=%d tries/hadron=%.3f  ms/step: %s  sampler %.3e hadrons/s" % (
