@@ -556,7 +556,9 @@ void GpuFSSW::sample_events() {
                              + 24.0*species_.size();
     int64_t batch = static_cast<int64_t>(0.5*static_cast<double>(free_b)/per_event);
     const double hadrons_total = dN_event*static_cast<double>(nev_);
-    if (hadrons_total > 4e6) batch = std::min<int64_t>(batch, (nev_ + 7)/8);
+    int64_t min_batches = 8;
+    if (const char *e = getenv("ISS_BATCHES")) min_batches = std::max(1, atoi(e));
+    if (hadrons_total > 4e6) batch = std::min<int64_t>(batch, (nev_ + min_batches - 1)/min_batches);
     batch = std::max<int64_t>(1, std::min<int64_t>(batch, nev_));
     const bool decays_on = flag_perform_decays_ && afterburner_type_ != AfterburnerType::SMASH;
     if (decays_on) std::cout << "perform resonance decays... " << std::endl;

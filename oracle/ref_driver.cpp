@@ -189,6 +189,96 @@ static int run_writers(int argc, char **argv) {
     return 0;
 }
 
+// ref_driver spectra <param_file> <work_path> <surface_file> <out_prefix> species=<monval,...> [key=value ...]
+//   MC_sampling is forced to 0 so that iSS::read_in_FO_surface keeps the lab-frame (Milne) cells
+//   (iSS.cpp:105-109).  For every requested species EmissionFunctionArray::calculate_dN_pTdpTdphidy
+//   (emissionfunction.cpp:624-829) and calculate_flows (:875-1016) are called.
+//   -> <out_prefix>.lab.bin    int64 ncell, then ncell x 32 float32 in the ISS_L_* order of
+//                              include/iss_cuda.h (tau, u0-3, da0-3, T, P, e, muB, muS, muQ,
+//                              pi00 01 02 03 11 12 13 22 23 33, bulkPi, Bn, q0-3, 0)
+//      <out_prefix>.dN.bin     int64 ns, npT, nphi, then per species [npT][nphi] float64 dN and the
+//                              same for dN_max
+//      <out_prefix>.species.txt  monval mass gspin baryon strange charge sign
+//      <out_prefix>.vndiff.<monval>.dat / .vninte.<monval>.dat  the reference's flow files
+static int run_spectra(int argc, char **argv) {
+    if (argc < 7) { std::cerr << "usage: spectra param path surface out_prefix species=.. [k=v]\n"; return 2; }
+    std::string param = argv[2], path = argv[3], surface = argv[4], out = argv[5];
+    iSS sampler(path, "iSS_tables", "iSS_tables", param, surface);
+    std::vector<int> wanted;
+    for (int i = 6; i < argc; i++) {
+        std::string a = argv[i];
+        if (a.rfind("species=", 0) == 0) {
+            std::stringstream ss(a.substr(8));
+            std::string tok;
+            while (std::getline(ss, tok, ',')) wanted.push_back(atoi(tok.c_str()));
+        } else {
+            sampler.paraRdr_ptr->phraseOneLine(argv[i]);
+        }
+    }
+    sampler.paraRdr_ptr->setVal("MC_sampling", 0);
+    sampler.read_in_FO_surface();
+    sampler.set_random_seed(1);
+    {
+        FILE *f = fopen((out + ".lab.bin").c_str(), "wb");
+        int64_t n = sampler.FOsurf_array_.size();
+        fwrite(&n, sizeof(n), 1, f);
+        for (auto const &c : sampler.FOsurf_array_) {
+            float rec[32] = {c.tau, c.u0, c.u1, c.u2, c.u3, c.da0, c.da1, c.da2, c.da3,
+                             c.Tdec, c.Pdec, c.Edec, c.muB, c.muS, c.muQ,
+                             c.pi00, c.pi01, c.pi02, c.pi03, c.pi11, c.pi12, c.pi13, c.pi22, c.pi23,
+                             c.pi33, c.bulkPi, c.Bn, c.qmu0, c.qmu1, c.qmu2, c.qmu3, 0.f};
+            fwrite(rec, sizeof(float), 32, f);
+        }
+        fclose(f);
+    }
+    // same construction as iSS::generate_samples (iSS.cpp:150-163)
+    Table chosen_particles;
+    if (sampler.afterburner_type_ == AfterburnerType::SMASH) {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_SMASH.dat");
+    } else if (sampler.afterburner_type_ == AfterburnerType::UrQMD) {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_urqmd_v3.3+.dat");
+    } else {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_s95p-v1.dat");
+    }
+    Table pT_tab("iSS_tables/bin_tables/pT_gauss_table.dat");
+    Table phi_tab("iSS_tables/bin_tables/phi_gauss_table.dat");
+    Table eta_tab("iSS_tables/bin_tables/eta_uni_table.dat");
+    EmissionFunctionArray efa(sampler.ran_gen_ptr_, &chosen_particles, &pT_tab, &phi_tab, &eta_tab,
+                              sampler.particle_, sampler.FOsurf_array_, sampler.flag_PCE_,
+                              sampler.paraRdr_ptr, path, "iSS_tables", sampler.afterburner_type_);
+    const int to_order = sampler.paraRdr_ptr->getVal("calculate_vn_to_order");
+    const int npT = efa.pT_tab_length, nphi = efa.phi_tab_length;
+    std::ofstream sp(out + ".species.txt");
+    sp << std::setprecision(17);
+    FILE *f = fopen((out + ".dN.bin").c_str(), "wb");
+    int64_t hdr[3] = {static_cast<int64_t>(wanted.size()), npT, nphi};
+    fwrite(hdr, sizeof(int64_t), 3, f);
+    for (int monval : wanted) {
+        int idx = -1;
+        for (int n = 0; n < efa.Nparticles; n++)
+            if (efa.particles[n].monval == monval) idx = n;
+        if (idx < 0) { std::cerr << "unknown species " << monval << "\n"; return 1; }
+        const particle_info &p = efa.particles[idx];
+        sp << p.monval << " " << p.mass << " " << p.gspin << " " << p.baryon << " "
+           << p.strange << " " << p.charge << " " << p.sign << "\n";
+        efa.calculate_dN_pTdpTdphidy(idx);
+        std::vector<double> buf(2*npT*nphi);
+        for (int i = 0; i < npT; i++)
+            for (int j = 0; j < nphi; j++) {
+                buf[i*nphi + j] = efa.dN_pTdpTdphidy->get(i + 1, j + 1);
+                buf[npT*nphi + i*nphi + j] = efa.dN_pTdpTdphidy_max->get(i + 1, j + 1);
+            }
+        fwrite(buf.data(), sizeof(double), buf.size(), f);
+        std::string fd = out + ".vndiff." + std::to_string(monval) + ".dat";
+        std::string fi = out + ".vninte." + std::to_string(monval) + ".dat";
+        remove(fd.c_str());
+        remove(fi.c_str());
+        efa.calculate_flows(to_order, fd, fi);
+    }
+    fclose(f);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { std::cerr << "usage: ref_driver yields|momentum|decay ...\n"; return 2; }
     std::string mode = argv[1];
@@ -196,6 +286,7 @@ int main(int argc, char **argv) {
     if (mode == "momentum") return run_momentum(argc, argv);
     if (mode == "decay") return run_decay(argc, argv);
     if (mode == "writers") return run_writers(argc, argv);
+    if (mode == "spectra") return run_spectra(argc, argv);
     std::cerr << "unknown mode " << mode << "\n";
     return 2;
 }

@@ -3,7 +3,7 @@
 (compiled by oracle/Makefile into oracle/_ref/) in THIS container.  The fixtures travel to the
 GPU box; /root/reference does not.
 
-    python tests/golden/make_golden.py [yields] [stats] [momentum] [decay]
+    python tests/golden/make_golden.py [yields] [stats] [momentum] [decay] [writers] [spectra]
 
 yields   : per-cell x per-species yields (FSSW::calculate_dN_dxtdy_for_one_particle_species)
            + the reference's local-rest-frame surface + species order, for the six runnable
@@ -12,6 +12,9 @@ stats    : histograms (tests/obs.py) of particle_samples.bin written by the refe
            sampler (iSS.e) with fixed seeds, >= 10^4 events each.
 momentum : |p| samples of MomentumSamplerShell::Sample_a_momentum reduced to histograms.
 decay    : daughters of particle_decay::perform_decays for a few resonances.
+spectra  : dN/(pT dpT dphi dy) tables of EmissionFunctionArray::calculate_dN_pTdpTdphidy and the
+           flow tables of calculate_flows for a few species on small synthetic surfaces, with the
+           lab-frame cells the reference used.
 """
 import os
 import shutil
@@ -296,8 +299,63 @@ def golden_writers():
     shutil.rmtree(d)
 
 
+# smooth Cooper-Frye spectra of the legacy EmissionFunctionArray:
+# name -> generator kwargs, parameter file, overrides, species (Monte-Carlo ids)
+SPECTRA_SPECIES = [211, 321, 2212, -2212, 3122, 113, 2224]
+SPECTRA = {
+    "sp3d_shear": dict(gen=dict(ncell=150, seed=31, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                       over=["include_deltaf_bulk=0"]),
+    "sp3d_bulk1_diff": dict(gen=dict(ncell=150, seed=32, eos=14, rhob=1, diffusion=1, binary=1),
+                            param="iSS_parameters_CEdeltaf.dat",
+                            over=["bulk_deltaf_kind=1", "include_deltaf_diffusion=1"]),
+    "sp3d_bulk2_norestrict": dict(gen=dict(ncell=100, seed=33, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                                  over=["bulk_deltaf_kind=2", "restrict_deltaf=0"]),
+    "sp3d_bulk3_pos": dict(gen=dict(ncell=100, seed=34, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                           over=["bulk_deltaf_kind=3", "use_pos_dN_only=1", "deltaf_max_ratio=0.5"]),
+    "sp3d_bulk4": dict(gen=dict(ncell=100, seed=35, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                       over=["bulk_deltaf_kind=4"]),
+    "sp3d_bulk0_quirk": dict(gen=dict(ncell=60, seed=36, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                             over=["bulk_deltaf_kind=0"]),
+    "sp2d_ideal_boltzmann": dict(gen=dict(ncell=100, seed=37, eos=9, boost_invariant=True),
+                                 param="iSS_parameters_ideal.dat",
+                                 over=["hydro_mode=1", "quantum_statistics=0", "bulk_deltaf_kind=21"]),
+}
+
+
+def golden_spectra(only=None):
+    for name, spec in SPECTRA.items():
+        if only and name not in only:
+            continue
+        d = workdir()
+        g = dict(spec["gen"])
+        cells = synthetic.make_case(os.path.join(d, "case"), **g)
+        out = os.path.join(d, "out")
+        run([os.path.join(REF, "ref_driver"), "spectra", os.path.join(FIX, spec["param"]), "case",
+             "surface.dat", out, "species=" + ",".join(str(m) for m in SPECTRA_SPECIES)] + spec["over"],
+            d, os.path.join(d, "log"))
+        with open(out + ".lab.bin", "rb") as f:
+            n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+            lab = np.fromfile(f, dtype=np.float32).reshape(n, 32)
+        sp = np.loadtxt(out + ".species.txt", ndmin=2)
+        with open(out + ".dN.bin", "rb") as f:
+            ns, npt, nphi = (int(v) for v in np.fromfile(f, dtype=np.int64, count=3))
+            dn = np.fromfile(f, dtype=np.float64).reshape(ns, 2, npt, nphi)
+        vndiff = np.array([np.loadtxt(out + ".vndiff.%d.dat" % m) for m in SPECTRA_SPECIES])
+        vninte = np.array([np.loadtxt(out + ".vninte.%d.dat" % m) for m in SPECTRA_SPECIES])
+        text = open(out + ".vndiff.%d.dat" % SPECTRA_SPECIES[0], "rb").read()
+        np.savez_compressed(os.path.join(HERE, "spectra_%s.npz" % name), lab=lab, species=sp,
+                            dN=dn[:, 0], dN_max=dn[:, 1], vndiff=vndiff, vninte=vninte,
+                            vndiff_text0=np.frombuffer(text, dtype=np.uint8), cells=cells,
+                            gen=np.array(sorted(g.items()), dtype=object).astype(str),
+                            param=spec["param"], overrides=np.array(spec["over"]))
+        print(name, lab.shape, dn.shape, "sum=%.17g" % dn[:, 0].sum())
+        shutil.rmtree(d)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["yields", "stats", "momentum", "decay", "writers"]
+    what = sys.argv[1:] or ["yields", "stats", "momentum", "decay", "writers", "spectra"]
+    if "spectra" in what:
+        golden_spectra([w for w in what if w in SPECTRA] or None)
     if "yields" in what:
         golden_yields([w for w in what if w in ONE_CELL or w in SYNTH] or None)
     if "momentum" in what:
