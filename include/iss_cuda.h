@@ -258,6 +258,49 @@ ISS_API int iss_cuda_host_free(iss_handle *h, void *ptr);
 /* ---- FP64 pipe probe: dependent-free DFMA loop, returns achieved TFLOP/s (2 flop per FMA). */
 ISS_API int iss_cuda_fp64_peak(iss_handle *h, double *tflops);
 
+/* ---- smooth Cooper-Frye spectra -------------------------
+ * Replaces EmissionFunctionArray::calculate_dN_pTdpTdphidy (reference
+ * src/emissionfunction.cpp:624-829): dN/(pT dpT dphi dy) on a (pT, phi) grid, summed over all
+ * cells and over a table of y - eta_s points, for a list of species.  The cells are the
+ * LAB-frame (Milne) records `FO_surf` (src/data_struct.h:53-63) that iSS::read_in_FO_surface
+ * keeps when MC_sampling != 4 (src/iSS.cpp:105-109), one array-of-structures block of
+ * ISS_LAB_NFIELD floats per cell in this order: */
+enum {
+    ISS_L_TAU = 0, ISS_L_U0, ISS_L_U1, ISS_L_U2, ISS_L_U3,
+    ISS_L_DA0, ISS_L_DA1, ISS_L_DA2, ISS_L_DA3,
+    ISS_L_T, ISS_L_P, ISS_L_E, ISS_L_MUB, ISS_L_MUS, ISS_L_MUQ,
+    ISS_L_PI00, ISS_L_PI01, ISS_L_PI02, ISS_L_PI03, ISS_L_PI11, ISS_L_PI12, ISS_L_PI13,
+    ISS_L_PI22, ISS_L_PI23, ISS_L_PI33,
+    ISS_L_BULKPI, ISS_L_BN, ISS_L_Q0, ISS_L_Q1, ISS_L_Q2, ISS_L_Q3, ISS_L_SPARE,
+    ISS_LAB_NFIELD = 32
+};
+
+/* Parameters read by the legacy class (src/emissionfunction.cpp:88-100, 632). */
+typedef struct {
+    int32_t include_deltaf_shear;
+    int32_t include_deltaf_bulk;
+    int32_t bulk_deltaf_kind;       /* 1..4 polynomial coefficients; 0: coefficients stay 0 (the
+                                       reference never fills them on this path); others: no bulk */
+    int32_t include_deltaf_diffusion;   /* needs ISS_TABLE_KAPPA_B */
+    int32_t restrict_deltaf;
+    int32_t use_pos_dN_only;
+    double deltaf_max_ratio;
+} iss_spectra_options;
+
+ISS_API int iss_cuda_upload_surface_lab(iss_handle *h, const float *cells, int64_t ncell);
+/* dN and dN_max: host arrays [nspecies][npT][nphi] (dN_max may be NULL).  y_minus_eta / y_weight
+ * are the two columns of the reference's eta table (bin_tables/eta_uni_table.dat).  Uses
+ * iss_species.{mass, gspin, baryon, strange, charge, sign}.  The sum over cells runs in chunks
+ * whose size depends on ncell only, so the result is bit-identical from run to run and
+ * independent of how species are spread over GPUs. */
+ISS_API int iss_cuda_spectra(iss_handle *h, const iss_spectra_options *opt,
+                             const iss_species *species, int32_t nspecies,
+                             const double *pT, int32_t npT, const double *phi, int32_t nphi,
+                             const double *y_minus_eta, const double *y_weight, int32_t ny,
+                             double *dN, double *dN_max);
+/* evaluations (cell x y-eta point x pT x phi x species) and kernel milliseconds of the last call */
+ISS_API int iss_cuda_spectra_stats(iss_handle *h, double *evaluations, double *kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

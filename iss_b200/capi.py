@@ -54,6 +54,13 @@ class DecayChannel(C.Structure):
                 ("branching_ratio", C.c_double)]
 
 
+class SpectraOptions(C.Structure):
+    _fields_ = [("include_deltaf_shear", C.c_int32), ("include_deltaf_bulk", C.c_int32),
+                ("bulk_deltaf_kind", C.c_int32), ("include_deltaf_diffusion", C.c_int32),
+                ("restrict_deltaf", C.c_int32), ("use_pos_dN_only", C.c_int32),
+                ("deltaf_max_ratio", C.c_double)]
+
+
 class Counts(C.Structure):
     _fields_ = [("n_events", C.c_int64), ("n_hadrons", C.c_int64), ("n_tries", C.c_int64),
                 ("n_cell_redraws", C.c_int64)]
@@ -81,6 +88,7 @@ CUDA_SYMBOLS = [
     "iss_cuda_mem_info", "iss_cuda_host_alloc", "iss_cuda_host_free", "iss_cuda_fp64_peak",
     "iss_cuda_set_trace", "iss_cuda_get_trace", "iss_cuda_upload_surface_aos",
     "iss_cuda_fetch_all_async", "iss_cuda_fetch_wait", "iss_cuda_sample_momentum",
+    "iss_cuda_upload_surface_lab", "iss_cuda_spectra", "iss_cuda_spectra_stats",
 ]
 HOST_SYMBOLS = [
     "iss_host_create", "iss_host_destroy", "iss_host_set_param", "iss_host_get_param",
@@ -147,6 +155,10 @@ def cuda_lib():
         "iss_cuda_sample_momentum": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, i32, i64, u64, vp]),
         "iss_cuda_set_trace": (C.c_int, [vp, C.c_int]),
         "iss_cuda_get_trace": (C.c_int, [vp, vp, vp]),
+        "iss_cuda_upload_surface_lab": (C.c_int, [vp, vp, i64]),
+        "iss_cuda_spectra": (C.c_int, [vp, C.POINTER(SpectraOptions), vp, i32, vp, i32, vp, i32, vp, vp,
+                                       i32, vp, vp]),
+        "iss_cuda_spectra_stats": (C.c_int, [vp, dp, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -354,6 +366,41 @@ class Engine:
         self.check(self.L.iss_cuda_timing(self.h, int(enable), _ptr(ms), _ptr(n), int(reset)),
                    "timing")
         return dict(zip(T_KINDS, ms)), dict(zip(T_KINDS, n))
+
+    # ---- smooth Cooper-Frye spectra (EmissionFunctionArray::calculate_dN_pTdpTdphidy)
+    def upload_surface_lab(self, cells):
+        """cells: float32 [ncell, 32] lab-frame records in ISS_L_* order."""
+        cells = np.ascontiguousarray(cells, dtype=np.float32)
+        assert cells.ndim == 2 and cells.shape[1] == 32
+        self.check(self.L.iss_cuda_upload_surface_lab(self.h, _ptr(cells), cells.shape[0]),
+                   "upload_surface_lab")
+
+    def spectra(self, species, pT, phi, y_minus_eta, y_weight, **opt):
+        """Returns (dN, dN_max), each [nspecies, npT, nphi]."""
+        species = np.ascontiguousarray(species, dtype=SPECIES_DTYPE)
+        pT = np.ascontiguousarray(pT, dtype=np.float64)
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        y = np.ascontiguousarray(y_minus_eta, dtype=np.float64)
+        w = np.ascontiguousarray(y_weight, dtype=np.float64)
+        o = SpectraOptions()
+        o.include_deltaf_shear = 1
+        o.restrict_deltaf = 1
+        o.deltaf_max_ratio = 1.0
+        o.bulk_deltaf_kind = 1
+        for k, v in opt.items():
+            setattr(o, k, v)
+        dN = np.zeros((len(species), len(pT), len(phi)))
+        dN_max = np.zeros_like(dN)
+        self.check(self.L.iss_cuda_spectra(self.h, C.byref(o), _ptr(species), len(species), _ptr(pT),
+                                           len(pT), _ptr(phi), len(phi), _ptr(y), _ptr(w), len(y),
+                                           _ptr(dN), _ptr(dN_max)), "spectra")
+        return dN, dN_max
+
+    def spectra_stats(self):
+        """(evaluations, kernel milliseconds) of the last spectra() call."""
+        n, ms = C.c_double(), C.c_double()
+        self.check(self.L.iss_cuda_spectra_stats(self.h, C.byref(n), C.byref(ms)), "spectra_stats")
+        return n.value, ms.value
 
     def fp64_peak(self):
         t = C.c_double()

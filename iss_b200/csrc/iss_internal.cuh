@@ -96,6 +96,13 @@ struct iss_handle {
     double *d_mom22 = nullptr;
     double *d_mom14 = nullptr; iss::Grid2D g14{};
     double *d_kappa = nullptr; iss::Grid2D gk{};
+    // smooth spectra (spectra.cu)
+    float *d_lab = nullptr; size_t lab_bytes = 0; int64_t nlab = 0;     // [nlab][ISS_LAB_NFIELD]
+    double *d_labrec = nullptr; size_t labrec_bytes = 0;                // per-cell double records
+    double *d_spec_part = nullptr; size_t spec_part_bytes = 0;          // chunk partial sums
+    double *d_spec_out = nullptr; size_t spec_out_bytes = 0;
+    double *d_spec_tab = nullptr; size_t spec_tab_bytes = 0;            // momentum / eta tables
+    double spec_evals = 0., spec_ms = 0.;
     double *d_momtab[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     iss::MomentumTable momtab[6]{};     // 0..2 boson regimes, 3..5 fermion regimes
 
