@@ -56,6 +56,14 @@ ISS_API int32_t iss_host_species_dN(iss_host *s, double *dst);
 /* QA block (layout: iss_cuda.h), iss_cuda_qa_size() doubles */
 ISS_API int iss_host_qa_block(iss_host *s, double *dst);
 
+/* smooth spectra (MC_sampling = 0, calculate_vn = 1): the dN/(pT dpT dphi dy) table of one species
+ * after generate_samples, [npT][nphi] doubles (EmissionFunctionArray::dN_pTdpTdphidy,
+ * emissionfunction.h:64).  dst may be NULL to query the sizes.  Returns 0, or 1 when the species
+ * was not calculated.  kernel_ms / evaluations (may be NULL): device time and integrand
+ * evaluations of the run. */
+ISS_API int iss_host_spectra_table(iss_host *s, int32_t monval, double *dst, int32_t *npT,
+                                   int32_t *nphi, double *kernel_ms, double *evaluations);
+
 /* the reference's sample-file writers (FSSW::combine_samples_to_OSCAR / _gzip_file / _binary_file,
  * FSSW.cpp:365-561) on a caller-supplied hadron list; files go to the current directory like the
  * reference's.  format: 0 OSCAR.DAT, 1 particle_samples.gz, 2 particle_samples.bin             */

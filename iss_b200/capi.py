@@ -97,7 +97,7 @@ HOST_SYMBOLS = [
     "iss_host_get_number_of_sampled_events", "iss_host_get_number_of_particles",
     "iss_host_get_hadron_list_iev", "iss_host_clear", "iss_host_prepare_sampler",
     "iss_host_cuda_handle", "iss_host_lrf_surface", "iss_host_species", "iss_host_hadron_buffer",
-    "iss_host_species_dN", "iss_host_qa_block", "iss_host_write_samples",
+    "iss_host_species_dN", "iss_host_qa_block", "iss_host_write_samples", "iss_host_spectra_table",
 ]
 
 _cuda = None
@@ -200,6 +200,8 @@ def host_lib():
         "iss_host_species_dN": (C.c_int32, [vp, vp]),
         "iss_host_qa_block": (C.c_int, [vp, vp]),
         "iss_host_write_samples": (C.c_int, [C.c_int, vp, vp, C.c_int64, cs]),
+        "iss_host_spectra_table": (C.c_int, [vp, C.c_int32, vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                             C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -510,6 +512,17 @@ class Sampler:
             return np.zeros(0, dtype=HADRON_DTYPE), off
         buf = (C.c_char*(40*n)).from_address(p)
         return np.frombuffer(buf, dtype=HADRON_DTYPE), off
+
+    def spectra_table(self, monval):
+        """dN/(pT dpT dphi dy) [npT, nphi] of one species after generate_samples() with
+        MC_sampling = 0, calculate_vn = 1; also returns (kernel_ms, evaluations) of the run."""
+        npt, nphi, ms, ev = C.c_int32(), C.c_int32(), C.c_double(), C.c_double()
+        if self.L.iss_host_spectra_table(self.s, monval, None, C.byref(npt), C.byref(nphi),
+                                         C.byref(ms), C.byref(ev)) != 0:
+            raise IssError("no spectra table for species %d" % monval)
+        a = np.zeros((npt.value, nphi.value))
+        self.L.iss_host_spectra_table(self.s, monval, _ptr(a), None, None, None, None)
+        return a, ms.value, ev.value
 
     def qa_block(self):
         qa = np.zeros(cuda_lib().iss_cuda_qa_size())

@@ -4,6 +4,7 @@
 
 #include "../../include/iss_host.h"
 #include "gpu_fssw.h"
+#include "gpu_spectra.h"
 #include "iSS.h"
 #include "writers.h"
 
@@ -111,6 +112,25 @@ int iss_host_qa_block(iss_host *s, double *dst) {
     if (!g || g->qa_block().empty()) return 1;
     memcpy(dst, g->qa_block().data(), sizeof(double)*g->qa_block().size());
     return 0;
+}
+
+int iss_host_spectra_table(iss_host *s, int32_t monval, double *dst, int32_t *npT, int32_t *nphi,
+                           double *kernel_ms, double *evaluations) {
+    GpuSpectra *g = s->obj->get_spectra();
+    if (!g) return 1;
+    if (npT) *npT = g->pT_tab_length();
+    if (nphi) *nphi = g->phi_tab_length();
+    if (kernel_ms) *kernel_ms = g->last_kernel_ms();
+    if (evaluations) *evaluations = g->last_evaluations();
+    const auto &pt = s->obj->get_particle_table();
+    for (size_t n = 0; n < pt.size(); n++)
+        if (pt[n].monval == monval) {
+            const std::vector<double> &t = g->dN_pTdpTdphidy(static_cast<int>(n));
+            if (t.empty()) return 1;
+            if (dst) memcpy(dst, t.data(), sizeof(double)*t.size());
+            return 0;
+        }
+    return 1;
 }
 
 int iss_host_write_samples(int format, const iss_hadron *hadrons, const int64_t *event_offsets,

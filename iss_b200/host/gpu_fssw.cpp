@@ -16,6 +16,7 @@
 #include <thread>
 #include <unordered_map>
 
+#include "engine_pool.h"
 #include "logger.h"
 #include "writers.h"
 
@@ -143,7 +144,7 @@ void pinned_release(iss_handle *h, PinnedBlock b) {
     }
 }
 
-const std::vector<double> &cached_numbers(const std::string &file, int skip_lines) {
+const std::vector<double> &cached_numbers_impl(const std::string &file, int skip_lines) {
     static std::mutex mu;
     static std::map<std::string, std::vector<double>> cache;
     std::lock_guard<std::mutex> lk(mu);
@@ -153,7 +154,52 @@ const std::vector<double> &cached_numbers(const std::string &file, int skip_line
     return it->second;
 }
 
+const std::vector<double> &cached_numbers(const std::string &file, int skip_lines) {
+    return cached_numbers_impl(file, skip_lines);
+}
+
 }  // namespace
+
+namespace iss_pool {
+
+int default_device() {
+    int device = 0;
+    if (const char *lr = getenv("LOCAL_RANK")) device = atoi(lr);
+    if (const char *dv = getenv("ISS_CUDA_DEVICE")) device = atoi(dv);
+    return device;
+}
+
+iss_handle *acquire_handle(int device) {
+    iss_handle *h = nullptr;
+    {
+        HandlePool &P = handle_pool();
+        std::lock_guard<std::mutex> lk(P.mu);
+        auto &v = P.idle[device];
+        if (!v.empty()) {
+            h = v.back();
+            v.pop_back();
+        }
+    }
+    if (!h && iss_cuda_create(device, &h) != ISS_OK) {
+        iss_host::error("iss_cuda_create: no usable CUDA device (the B200 engine has no CPU "
+                        "fallback)");
+        exit(-1);
+    }
+    return h;
+}
+
+void release_handle(int device, iss_handle *h) {
+    if (!h) return;
+    HandlePool &P = handle_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    P.idle[device].push_back(h);
+}
+
+const std::vector<double> &cached_numbers(const std::string &file, int skip_lines) {
+    return cached_numbers_impl(file, skip_lines);
+}
+
+}  // namespace iss_pool
 
 void GpuFSSW::check_(int rc, const char *what) {
     if (rc == ISS_OK) return;
@@ -192,24 +238,8 @@ GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
     flag_spectators_ = (spectator_mode != 0) ? 1 : 0;
     if (flag_spectators_) read_spectators_(path_ + "/spectators.dat");
 
-    int device = 0;
-    if (const char *lr = getenv("LOCAL_RANK")) device = atoi(lr);
-    if (const char *dv = getenv("ISS_CUDA_DEVICE")) device = atoi(dv);
-    device_ = device;
-    {
-        HandlePool &P = handle_pool();
-        std::lock_guard<std::mutex> lk(P.mu);
-        auto &v = P.idle[device];
-        if (!v.empty()) {
-            h_ = v.back();
-            v.pop_back();
-        }
-    }
-    if (!h_ && iss_cuda_create(device, &h_) != ISS_OK) {
-        iss_host::error("iss_cuda_create: no usable CUDA device (the B200 engine has no CPU "
-                        "fallback)");
-        exit(-1);
-    }
+    device_ = iss_pool::default_device();
+    h_ = iss_pool::acquire_handle(device_);
     { PhaseTimer t("select_species"); select_species_(chosen_monvals); }
     { PhaseTimer t("upload_surface"); upload_surface_(); }
     { PhaseTimer t("upload_tables"); upload_tables_(); }
@@ -244,9 +274,7 @@ GpuFSSW::~GpuFSSW() {
     b.ptr = hadrons_;
     b.bytes = hadron_cap_*static_cast<int64_t>(sizeof(iSS_Hadron));
     pinned_release(h_, b);
-    HandlePool &P = handle_pool();
-    std::lock_guard<std::mutex> lk(P.mu);
-    P.idle[device_].push_back(h_);
+    iss_pool::release_handle(device_, h_);
 }
 
 // chosen list -> indices into the pdg table, unknown ids dropped with a warning, then a stable

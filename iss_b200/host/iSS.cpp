@@ -12,6 +12,7 @@
 #include <sstream>
 
 #include "gpu_fssw.h"
+#include "gpu_spectra.h"
 #include "logger.h"
 #include "parallel.h"
 #include "readindata.h"
@@ -72,11 +73,13 @@ iSS::iSS(std::string path, std::string table_path, std::string particle_table_pa
 
 iSS::~iSS() {
     spectra_sampler_.reset();
+    efa_.reset();
     clear();
     delete paraRdr_ptr;
 }
 
 void iSS::clear() {
+    FOsurf_array_.clear();
     FOsurf_LRF_array_.clear();
     FOsurf_Tmunu_.clear();
     for (auto &p : particle_)
@@ -86,8 +89,20 @@ void iSS::clear() {
 
 void iSS::require_fssw_() const {
     if (paraRdr_ptr->getVal("MC_sampling") != 4) {
-        iss_host::error("the B200 engine implements the FSSW sampler only: set MC_sampling = 4 "
+        iss_host::error("the B200 engine samples with FSSW only: set MC_sampling = 4 "
                         "(the legacy EmissionFunctionArray samplers MC_sampling = 1/2/3 are out of scope)");
+        exit(-1);
+    }
+}
+
+// MC_sampling = 4: FSSW sampler; MC_sampling = 0: smooth spectra and flows of the legacy class
+// (calculate_vn = 1) without sampling.
+void iSS::require_supported_mode_() const {
+    const double mode = paraRdr_ptr->getVal("MC_sampling");
+    if (mode != 4 && mode != 0) {
+        iss_host::error("the B200 engine implements MC_sampling = 4 (FSSW) and MC_sampling = 0 "
+                        "(smooth spectra and flows); the legacy EmissionFunctionArray samplers "
+                        "MC_sampling = 1/2/3 are out of scope");
         exit(-1);
     }
 }
@@ -107,7 +122,8 @@ int iSS::shell() {
 
 // iSS.cpp:86-113
 int iSS::read_in_FO_surface() {
-    require_fssw_();
+    require_supported_mode_();
+    const bool fssw = paraRdr_ptr->getVal("MC_sampling") == 4;
     const char *prof_env = getenv("ISS_PROFILE");
     const bool prof = prof_env && atoi(prof_env) == 1;
     auto t0 = std::chrono::steady_clock::now();
@@ -122,7 +138,9 @@ int iSS::read_in_FO_surface() {
     read_FOdata reader(paraRdr_ptr, path_, table_path_, particle_table_path_);
     lap("reader ctor (EOS table)");
     FOsurf_LRF_array_.clear();
-    const int64_t nbin = reader.open_binary_surface(surface_filename_);
+    FOsurf_array_.clear();
+    // (the blocked binary pipeline feeds the LRF transform; the lab-frame path keeps whole cells)
+    const int64_t nbin = fssw ? reader.open_binary_surface(surface_filename_) : -1;
     if (nbin >= 0) {
         // binary surface: parse -> regulate -> T^{mu nu} -> LRF transform over blocks that stay in
         // cache; per-cell arithmetic and cell order are those of the whole-surface path
@@ -182,8 +200,12 @@ int iSS::read_in_FO_surface() {
         lap("particle table");
         computeFOSurfTmunu(cells);
         lap("computeFOSurfTmunu");
-        transform_to_local_rest_frame(cells, FOsurf_LRF_array_);
-        lap("transform_to_local_rest_frame");
+        if (fssw) {
+            transform_to_local_rest_frame(cells, FOsurf_LRF_array_);
+            lap("transform_to_local_rest_frame");
+        } else {
+            FOsurf_array_.swap(cells);      // iSS.cpp:105-109
+        }
     }
     info(" -- Read in data finished!");
     return 0;
@@ -247,8 +269,17 @@ int iSS::prepare_sampler() {
 // iSS.cpp:130-165
 int iSS::generate_samples() {
     info("Start computation and generating samples ...");
-    prepare_sampler();
-    spectra_sampler_->shell();
+    require_supported_mode_();
+    if (paraRdr_ptr->getVal("MC_sampling") == 4) {
+        prepare_sampler();
+        spectra_sampler_->shell();
+    } else {
+        const std::vector<int> chosen = read_chosen_particles();
+        efa_.reset();
+        efa_.reset(new GpuSpectra(chosen, particle_, FOsurf_array_, flag_PCE_, paraRdr_ptr, path_,
+                                  table_path_, afterburner_type_));
+        efa_->shell();
+    }
     return 0;
 }
 

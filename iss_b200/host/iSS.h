@@ -21,6 +21,7 @@
 #include "data_struct.h"
 
 class GpuFSSW;
+class GpuSpectra;
 
 class iSS {
  private:
@@ -29,6 +30,7 @@ class iSS {
     const std::string particle_table_path_;
     const std::string surface_filename_;
 
+    std::vector<FO_surf> FOsurf_array_;         // lab-frame cells, kept when MC_sampling != 4
     std::vector<FO_surf_LRF> FOsurf_LRF_array_;
     std::vector<float> FOsurf_Tmunu_;
     std::vector<float> FOsurf_Q_;
@@ -40,8 +42,10 @@ class iSS {
 
     std::vector<particle_info> particle_;
     std::unique_ptr<GpuFSSW> spectra_sampler_;
+    std::unique_ptr<GpuSpectra> efa_;           // smooth spectra / flows (MC_sampling = 0)
 
     void require_fssw_() const;
+    void require_supported_mode_() const;
     void accumulate_Tmunu_(const std::vector<FO_surf> &cells);
     void report_Tmunu_() const;
 
@@ -83,6 +87,8 @@ class iSS {
     // hosts can drive the C ABI (include/iss_cuda.h) on get_sampler()->cuda_handle() themselves
     int prepare_sampler();
     GpuFSSW *get_sampler() { return spectra_sampler_.get(); }
+    GpuSpectra *get_spectra() { return efa_.get(); }
+    const std::vector<FO_surf> &get_lab_surface() const { return FOsurf_array_; }
     const std::vector<FO_surf_LRF> &get_LRF_surface() const { return FOsurf_LRF_array_; }
     const std::vector<particle_info> &get_particle_table() const { return particle_; }
 };

@@ -352,10 +352,49 @@ def golden_spectra(only=None):
         shutil.rmtree(d)
 
 
+# whole-program golden of the spectra mode: the reference's iSS.e with MC_sampling = 0 and
+# calculate_vn = 1 on a short chosen-particle list (tables folder with only that file replaced)
+FLOW_CHOSEN = [211, -211, 111, 321, 2212, -2212, 2112, 3122, 113, 213, 223, 2224, 2214]
+FLOW_RUNS = {
+    "new": ["use_historic_flow_output_format=0", "calculate_dN_dphi=1"],
+    "old": ["use_historic_flow_output_format=1"],
+}
+
+
+def golden_flows():
+    for name, over in FLOW_RUNS.items():
+        d = tempfile.mkdtemp(prefix="iss_golden_")
+        os.makedirs(os.path.join(d, "iSS_tables"))
+        for f in os.listdir(REF_TABLES):
+            if f != "chosen_particles_SMASH.dat":
+                os.symlink(os.path.join(REF_TABLES, f), os.path.join(d, "iSS_tables", f))
+        # (EOS 14 with afterburner_type = 2 in the parameter file: the SMASH lists are used)
+        with open(os.path.join(d, "iSS_tables", "chosen_particles_SMASH.dat"), "w") as f:
+            f.write("".join("%d\n" % m for m in FLOW_CHOSEN))
+        g = dict(ncell=40, seed=41, eos=14, rhob=1, diffusion=1, binary=1)
+        cells = synthetic.make_case(os.path.join(d, "case"), **g)
+        over = ["MC_sampling=0", "calculate_vn=1", "bulk_deltaf_kind=1", "include_deltaf_diffusion=1",
+                "calculate_vn_to_order=4", "perform_checks=0"] + over
+        run([os.path.join(REF, "iSS.e"), os.path.join(FIX, "iSS_parameters_CEdeltaf.dat"), "case",
+             "surface.dat"] + over, d, os.path.join(d, "log"))
+        files = {}
+        for f in sorted(os.listdir(os.path.join(d, "case"))):
+            if f.startswith(("thermal_", "dN_", "v2data")):
+                files[f] = np.frombuffer(open(os.path.join(d, "case", f), "rb").read(), dtype=np.uint8)
+        np.savez_compressed(os.path.join(HERE, "flows_%s.npz" % name), cells=cells,
+                            gen=np.array(sorted(g.items()), dtype=object).astype(str),
+                            param="iSS_parameters_CEdeltaf.dat", overrides=np.array(over),
+                            chosen=np.array(FLOW_CHOSEN), names=np.array(sorted(files)),
+                            **{"file_%d" % i: files[k] for i, k in enumerate(sorted(files))})
+        print("flows", name, sorted(files)[:4], "...", len(files), "files")
+        shutil.rmtree(d)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["yields", "stats", "momentum", "decay", "writers", "spectra"]
     if "spectra" in what:
         golden_spectra([w for w in what if w in SPECTRA] or None)
+        golden_flows()
     if "yields" in what:
         golden_yields([w for w in what if w in ONE_CELL or w in SYNTH] or None)
     if "momentum" in what:

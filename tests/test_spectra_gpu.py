@@ -104,3 +104,80 @@ def test_spectra_errors():
             e.spectra(sp, pT[:, 0], phi[:, 0], np.zeros(200), np.zeros(200))
     finally:
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# whole program: class iSS with MC_sampling = 0, calculate_vn = 1 against the files written by the
+# reference's iSS.e on the same surface (tests/golden/flows_*.npz)
+def _tables_with_chosen(tmp, chosen):
+    d = os.path.join(tmp, "tables")
+    os.makedirs(d)
+    for f in os.listdir(sc.TABLES):
+        if f != "chosen_particles_SMASH.dat":
+            os.symlink(os.path.join(sc.TABLES, f), os.path.join(d, f))
+    with open(os.path.join(d, "chosen_particles_SMASH.dat"), "w") as f:
+        f.write("".join("%d\n" % m for m in chosen))
+    return d
+
+
+def _compare_text(name, got, want):
+    gl, wl = got.split("\n"), want.split("\n")
+    assert len(gl) == len(wl), name
+    assert [len(x) for x in gl] == [len(x) for x in wl], name       # same layout, column for column
+    gt, wt = got.split(), want.split()
+    same = 0
+    for a, b in zip(gt, wt):
+        if a == b:
+            same += 1
+            continue
+        if a.startswith("#") or b.startswith("#"):
+            assert a == b, name
+        try:
+            fa, fb = float(a), float(b)
+        except ValueError:
+            assert a == b, (name, a, b)       # names in the comment lines of the historic format
+            continue
+        # 9 significant digits in the files; flows are ratios of sums that cancel
+        assert abs(fa - fb) <= 3e-8*max(abs(fa), abs(fb)) + 1e-13, (name, a, b)
+    # v_n are ratios of cancelling sums: a 1e-13 difference in dN can flip the ninth printed digit
+    assert same >= 0.90*len(wt), (name, same, len(wt))
+
+
+@pytest.mark.parametrize("which", ["new", "old"])
+def test_facade_spectra_and_flows_match_reference_files(which, tmp_path):
+    import cases
+    g = np.load(os.path.join(sc.GOLDEN, "flows_%s.npz" % which), allow_pickle=False)
+    folder = str(tmp_path/"case")
+    param, surf, over = cases.materialise(g, folder)
+    tables = _tables_with_chosen(str(tmp_path), [int(m) for m in g["chosen"]])
+    s = capi.Sampler(folder, param, surf, table_path=tables, **over)
+    try:
+        assert s.read_in_FO_surface() == 0
+        assert s.generate_samples() == 0
+        tab, ms, ev = s.spectra_table(211)
+        assert tab.shape == (15, 48) and ev > 0 and ms > 0
+    finally:
+        s.close()
+    names = [str(n) for n in g["names"]]
+    for i, n in enumerate(names):
+        want = bytes(g["file_%d" % i]).decode()
+        got = open(os.path.join(folder, n)).read()
+        _compare_text(n, got, want)
+    produced = sorted(f for f in os.listdir(folder) if f.startswith(("thermal_", "dN_", "v2data")))
+    assert produced == sorted(names)
+
+
+def test_facade_rejects_legacy_samplers(tmp_path):
+    """MC_sampling = 1/2/3 (legacy EmissionFunctionArray samplers) exit with an error, they do
+    not fall back to anything"""
+    import subprocess
+    import cases
+    g = np.load(os.path.join(sc.GOLDEN, "flows_new.npz"), allow_pickle=False)
+    folder = str(tmp_path/"case")
+    param, surf, over = cases.materialise(g, folder)
+    code = ("import sys; sys.path.insert(0, %r); from iss_b200 import capi; "
+            "s = capi.Sampler(%r, %r, %r, MC_sampling=2); s.read_in_FO_surface()" %
+            (REPO, folder, param, surf))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "out of scope" in r.stdout
