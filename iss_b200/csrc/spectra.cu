@@ -71,6 +71,44 @@ __constant__ double c_bulk_poly[4][2][11] = {
       -6737468792456.4, 7730102407679.65, -6058276038129.83, 3103990764357.81, -938850005883.612,
       127305171097.249}}};
 
+// exp() and reciprocal of the occupation number, written out so that every constant is a
+// constant-bank operand of the DFMA that uses it (the library exp() re-materialises its 64-bit
+// coefficients through uniform-register moves on every call: ~24 extra issue slots per point)
+// and without special-case branches: [0] log2(e), [1] 1.5 * 2^52, [2] -ln2 (high part),
+// [3] -ln2 (low part), [4..17] 1/13! ... 1/0!
+__constant__ double c_exp[18] = {
+    1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
+    -1.90821492927058770002e-10,
+    1.0/6227020800.0, 1.0/479001600.0, 1.0/39916800.0, 1.0/3628800.0, 1.0/362880.0, 1.0/40320.0,
+    1.0/5040.0, 1.0/720.0, 1.0/120.0, 1.0/24.0, 1.0/6.0, 0.5, 1.0, 1.0};
+
+// 1/d for a normal, finite d: hardware seed (20+ bits) and two Newton steps, no slow path
+__device__ __forceinline__ double fast_rcp(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+
+// f0 = 1/(exp(x) + sign).  x is clamped to [-700, 700]: beyond, the reference's value is below
+// 1e-304 of the table's scale (exp overflows to inf and f0 becomes 0 there).  exp: x = n ln2 + r,
+// |r| <= ln2/2, Taylor polynomial of degree 13 (remainder < 1e-17), 2^n through the exponent field.
+__device__ __forceinline__ double occupation(double x, double sign) {
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double t = fma(x, c_exp[0], c_exp[1]);
+    const int n = __double2loint(t);
+    const double tn = t - c_exp[1];
+    double r = fma(tn, c_exp[2], x);
+    r = fma(tn, c_exp[3], r);
+    double p = c_exp[4];
+#pragma unroll
+    for (int i = 5; i < 18; i++) p = fma(p, r, c_exp[i]);
+    const double scale = __hiloint2double((n + 1023) << 20, 0);
+    return fast_rcp(fma(p, scale, sign));
+}
+
 struct SpectraArgs {
     const float *lab;           // [ncell][ISS_LAB_NFIELD]
     double *rec;                // [ncell][REC]
@@ -210,7 +248,7 @@ spectra_kernel(const SpectraArgs A) {
             const float mu = __fadd_rn(__fadd_rn(__fmul_rn(static_cast<float>(sp.baryon), muB),
                                                  __fmul_rn(static_cast<float>(sp.strange), muS)),
                                        __fmul_rn(static_cast<float>(sp.charge), muQ));
-            o[S_MU] = mu;
+            o[S_MU] = static_cast<double>(mu)*r[R_INVT];       // mu/T
             o[S_INVT] = r[R_INVT];
             o[S_T] = r[R_T];
             o[S_SHEAR] = r[R_SHEAR];
@@ -225,7 +263,7 @@ spectra_kernel(const SpectraArgs A) {
             const double ch = s_ch[k], sh = s_sh[k];
             double2 ac, eq;
             ac.x = ch*r[R_U0] - sh*r[R_U3];
-            ac.y = ch*r[R_DA0] + sh*r[R_DA3T];
+            ac.y = pref*r[R_TAU]*(ch*r[R_DA0] + sh*r[R_DA3T]);    // with prefactor * g * tau
             eq.x = ch*ch*r[R_PI00] - 2.0*ch*sh*r[R_PI03] + sh*sh*r[R_PI33];
             eq.y = ch*r[R_Q0] - sh*r[R_Q3];
             s_ac[q][k] = ac;
@@ -236,14 +274,15 @@ spectra_kernel(const SpectraArgs A) {
         for (int q = 0; q < nc; q++) {
             const double *o = s_sc[q];
             const double Bv = px*o[S_U1] + py*o[S_U2];
-            const double Dv = px*o[S_DA1] + py*o[S_DA2];
+            const double taufac = o[S_TAUFAC];
+            const double Dv = taufac*(px*o[S_DA1] + py*o[S_DA2]);
             const double F = px*o[S_PI01] + py*o[S_PI02];
             const double G = px*o[S_PI13] + py*o[S_PI23];
             const double H = pxx*o[S_PI11] + pxy2*o[S_PI12] + pyy*o[S_PI22];
             const double Rq = px*o[S_Q1] + py*o[S_Q2];
-            const double mu = o[S_MU], invT = o[S_INVT], shear = o[S_SHEAR];
+            const double mu_T = o[S_MU], invT = o[S_INVT], shear = o[S_SHEAR];
             const double bulkPi = o[S_BULKPI], bc0 = o[S_C0], bc1 = o[S_C1];
-            const double inv_kappa = o[S_INVKAPPA], pref_q = o[S_PREFQ], taufac = o[S_TAUFAC];
+            const double inv_kappa = o[S_INVKAPPA], pref_q = o[S_PREFQ];
             const double Tc = o[S_T];
             const double m2_3T = mass2*invT*(1.0/3.0);      // (m/T)^2/(3 E/T) = m^2/(3 T) / p.u
 #pragma unroll 3
@@ -251,16 +290,16 @@ spectra_kernel(const SpectraArgs A) {
                 const double2 ac = s_ac[q][k];
                 const double2 eq = s_eq[q][k];
                 const double ch = s_ch[k], sh = s_sh[k];
-                const double pdotu = mT*ac.x - Bv;
-                const double f0 = 1.0/(exp((pdotu - mu)*invT) + sign);
-                const double pdsigma = mT*ac.y + Dv;
-                const double one_m = 1.0 - sign*f0;
-                const double W = mT2*eq.x + mT*(ch*F + sh*G) + H;
+                const double pdotu = fma(mT, ac.x, -Bv);
+                const double f0 = occupation(fma(pdotu, invT, -mu_T), sign);
+                const double pdsigma = fma(mT, ac.y, Dv);           // x prefactor * g * tau
+                const double one_m = fma(-sign, f0, 1.0);
+                const double W = fma(mT2, eq.x, fma(mT, fma(ch, F, sh*G), H));
                 double df = one_m*W*shear;
                 if (BULK != 0 || DIFF) {
                     const double EoT = pdotu*invT;
                     double inv_pdotu = 0.;
-                    if (BULK == 1 || BULK == 4 || DIFF) inv_pdotu = 1.0/pdotu;
+                    if (BULK == 1 || BULK == 4 || DIFF) inv_pdotu = fast_rcp(pdotu);
                     if (BULK == 1) {
                         df += -one_m*bc0*(m2_3T*inv_pdotu - bc1*EoT)*bulkPi;
                     } else if (BULK == 2) {
@@ -275,11 +314,11 @@ spectra_kernel(const SpectraArgs A) {
                 if (restrict_df) {
                     // resize = min(1, ratio/(|df| + 1e-10)): the division only when it bites
                     const double size = fabs(df) + 1e-10;
-                    if (size > ratio_max) df *= ratio_max/size;
+                    if (size > ratio_max) df *= ratio_max*fast_rcp(size);
                 }
-                const double result = taufac*f0*pdsigma*(1.0 + df);
+                const double result = f0*pdsigma*(1.0 + df);
                 if (!(pos_only && result < 0.)) {
-                    sum += result*s_wy[k];
+                    sum = fma(result, s_wy[k], sum);
                     vmax = fmax(vmax, result);
                 }
             }
