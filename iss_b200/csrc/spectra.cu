@@ -22,6 +22,7 @@
 #include "coefficients.cuh"
 
 #include <cmath>
+#include <type_traits>
 
 namespace iss {
 
@@ -74,13 +75,12 @@ __constant__ double c_bulk_poly[4][2][11] = {
 // exp() and reciprocal of the occupation number, written out so that every constant is a
 // constant-bank operand of the DFMA that uses it (the library exp() re-materialises its 64-bit
 // coefficients through uniform-register moves on every call: ~24 extra issue slots per point)
-// and without special-case branches: [0] log2(e), [1] 1.5 * 2^52, [2] -ln2 (high part),
-// [3] -ln2 (low part), [4..17] 1/13! ... 1/0!
-__constant__ double c_exp[18] = {
-    1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
-    -1.90821492927058770002e-10,
-    1.0/6227020800.0, 1.0/479001600.0, 1.0/39916800.0, 1.0/3628800.0, 1.0/362880.0, 1.0/40320.0,
-    1.0/5040.0, 1.0/720.0, 1.0/120.0, 1.0/24.0, 1.0/6.0, 0.5, 1.0, 1.0};
+// and without special-case branches.  [0] 16/ln2, [1] 1.5 * 2^52, [2] -(ln2/16) high part,
+// [3] -(ln2/16) low part, [4..10] 1/6! ... 1/0!
+__constant__ double c_exp[11] = {
+    23.083120654223414519, 6755399441055744.0, -4.33216987730702385306e-02,
+    -1.19263433079411731251e-11,
+    1.0/720.0, 1.0/120.0, 1.0/24.0, 1.0/6.0, 0.5, 1.0, 1.0};
 
 // 1/d for a normal, finite d: hardware seed (20+ bits) and two Newton steps, no slow path
 __device__ __forceinline__ double fast_rcp(double d) {
@@ -92,21 +92,23 @@ __device__ __forceinline__ double fast_rcp(double d) {
     return fma(y, e, y);
 }
 
-// f0 = 1/(exp(x) + sign).  x is clamped to [-700, 700]: beyond, the reference's value is below
-// 1e-304 of the table's scale (exp overflows to inf and f0 becomes 0 there).  exp: x = n ln2 + r,
-// |r| <= ln2/2, Taylor polynomial of degree 13 (remainder < 1e-17), 2^n through the exponent field.
-__device__ __forceinline__ double occupation(double x, double sign) {
-    x = fmin(fmax(x, -700.0), 700.0);
+// f0 = 1/(exp(x) + sign) and exp(x) f0 = 1 - sign f0.  exp: x = (16 n + j) ln2/16 + r,
+// |r| <= ln2/32, exp(x) = 2^n 2^(j/16) p(r) with a degree-6 Taylor polynomial (remainder
+// < 5e-16) and a 16-entry table of 2^(j/16) in shared memory.  2^n goes through the exponent
+// field with n clamped to [-1022, 1010]: beyond +-700 the reference's f0 is below 1e-304 of the
+// table's scale (its exp overflows to inf and f0 becomes 0 there).
+__device__ __forceinline__ double occupation(double x, double sign, const double *s_pow2) {
     const double t = fma(x, c_exp[0], c_exp[1]);
-    const int n = __double2loint(t);
+    const int n16 = __double2loint(t);
     const double tn = t - c_exp[1];
     double r = fma(tn, c_exp[2], x);
     r = fma(tn, c_exp[3], r);
     double p = c_exp[4];
 #pragma unroll
-    for (int i = 5; i < 18; i++) p = fma(p, r, c_exp[i]);
+    for (int i = 5; i < 11; i++) p = fma(p, r, c_exp[i]);
+    const int n = min(max(n16 >> 4, -1022), 1010);
     const double scale = __hiloint2double((n + 1023) << 20, 0);
-    return fast_rcp(fma(p, scale, sign));
+    return fast_rcp(fma(p*s_pow2[n16 & 15], scale, sign));
 }
 
 struct SpectraArgs {
@@ -186,11 +188,13 @@ spectra_cell_kernel(const SpectraArgs A) {
     r[R_SPARE] = 0.;
 }
 
-// BULK: 0 none/kind 0 (zero coefficients), 1..4 the reference's kinds; DIFF: diffusion delta f
-template <int BULK, bool DIFF>
+// BULK: 0 none/kind 0 (zero coefficients), 1..4 the reference's kinds; DIFF: diffusion delta f;
+// WANT_MAX: also the maximum over (cell, y - eta_s) the reference keeps for its MC_sampling = 3
+template <int BULK, bool DIFF, bool WANT_MAX>
 __global__ void __launch_bounds__(SPEC_THREADS, 2)
 spectra_kernel(const SpectraArgs A) {
     __shared__ double s_ch[MAX_NY], s_sh[MAX_NY], s_wy[MAX_NY];
+    __shared__ double s_pow2[16];
     __shared__ double2 s_ac[CELL_TILE][MAX_NY];     // A, C
     __shared__ double2 s_eq[CELL_TILE][MAX_NY];     // E, Q
     __shared__ double s_sc[CELL_TILE][S_COUNT];
@@ -203,6 +207,7 @@ spectra_kernel(const SpectraArgs A) {
     const double mass = sp.mass;
     const double sign = sp.sign;
     const int ny = A.ny;
+    if (threadIdx.x < 16) s_pow2[threadIdx.x] = exp2(threadIdx.x*(1.0/16.0));
     for (int k = threadIdx.x; k < ny; k += blockDim.x) {
         s_ch[k] = A.ch[k];
         s_sh[k] = A.sh[k];
@@ -264,7 +269,7 @@ spectra_kernel(const SpectraArgs A) {
             double2 ac, eq;
             ac.x = ch*r[R_U0] - sh*r[R_U3];
             ac.y = pref*r[R_TAU]*(ch*r[R_DA0] + sh*r[R_DA3T]);    // with prefactor * g * tau
-            eq.x = ch*ch*r[R_PI00] - 2.0*ch*sh*r[R_PI03] + sh*sh*r[R_PI33];
+            eq.x = r[R_SHEAR]*(ch*ch*r[R_PI00] - 2.0*ch*sh*r[R_PI03] + sh*sh*r[R_PI33]);   // x shear prefactor
             eq.y = ch*r[R_Q0] - sh*r[R_Q3];
             s_ac[q][k] = ac;
             s_eq[q][k] = eq;
@@ -276,52 +281,72 @@ spectra_kernel(const SpectraArgs A) {
             const double Bv = px*o[S_U1] + py*o[S_U2];
             const double taufac = o[S_TAUFAC];
             const double Dv = taufac*(px*o[S_DA1] + py*o[S_DA2]);
-            const double F = px*o[S_PI01] + py*o[S_PI02];
-            const double G = px*o[S_PI13] + py*o[S_PI23];
-            const double H = pxx*o[S_PI11] + pxy2*o[S_PI12] + pyy*o[S_PI22];
+            const double shear = o[S_SHEAR];
+            // W x shear prefactor = mT^2 E'[k] + ch F + sh G + H
+            const double F = shear*mT*(px*o[S_PI01] + py*o[S_PI02]);
+            const double G = shear*mT*(px*o[S_PI13] + py*o[S_PI23]);
+            const double H = shear*(pxx*o[S_PI11] + pxy2*o[S_PI12] + pyy*o[S_PI22]);
             const double Rq = px*o[S_Q1] + py*o[S_Q2];
-            const double mu_T = o[S_MU], invT = o[S_INVT], shear = o[S_SHEAR];
+            const double mu_T = o[S_MU], invT = o[S_INVT];
             const double bulkPi = o[S_BULKPI], bc0 = o[S_C0], bc1 = o[S_C1];
             const double inv_kappa = o[S_INVKAPPA], pref_q = o[S_PREFQ];
             const double Tc = o[S_T];
             const double m2_3T = mass2*invT*(1.0/3.0);      // (m/T)^2/(3 E/T) = m^2/(3 T) / p.u
+            // MODE 0: no restriction of delta f; 2: resize = min(1, ratio/(|df| + 1e-10)) at
+            // every point, branch-free (a data-dependent branch inside the loop keeps the
+            // scheduler from interleaving the unrolled points and costs more than the reciprocal;
+            // on viscous surfaces the restriction bites too often for a detect-and-redo scheme)
+            auto cell_loop = [&](auto mode_tag, double &csum, double &cmax) -> bool {
+                constexpr int MODE = decltype(mode_tag)::value;
+                bool exceed = false;
+                csum = 0.;
+                cmax = 0.;
 #pragma unroll 3
-            for (int k = 0; k < ny; k++) {
-                const double2 ac = s_ac[q][k];
-                const double2 eq = s_eq[q][k];
-                const double ch = s_ch[k], sh = s_sh[k];
-                const double pdotu = fma(mT, ac.x, -Bv);
-                const double f0 = occupation(fma(pdotu, invT, -mu_T), sign);
-                const double pdsigma = fma(mT, ac.y, Dv);           // x prefactor * g * tau
-                const double one_m = fma(-sign, f0, 1.0);
-                const double W = fma(mT2, eq.x, fma(mT, fma(ch, F, sh*G), H));
-                double df = one_m*W*shear;
-                if (BULK != 0 || DIFF) {
-                    const double EoT = pdotu*invT;
-                    double inv_pdotu = 0.;
-                    if (BULK == 1 || BULK == 4 || DIFF) inv_pdotu = fast_rcp(pdotu);
-                    if (BULK == 1) {
-                        df += -one_m*bc0*(m2_3T*inv_pdotu - bc1*EoT)*bulkPi;
-                    } else if (BULK == 2) {
-                        df += -one_m*bulkPi*(-bc0 + bc1*EoT);
-                    } else if (BULK == 3) {
-                        df += -one_m*bulkPi*rsqrt(EoT)*(-bc0 + bc1*EoT);
-                    } else if (BULK == 4) {
-                        df += -one_m*bulkPi*(bc0 - bc1*Tc*inv_pdotu);
+                for (int k = 0; k < ny; k++) {
+                    const double2 ac = s_ac[q][k];
+                    const double2 eq = s_eq[q][k];
+                    const double pdotu = fma(mT, ac.x, -Bv);
+                    const double f0 = occupation(fma(pdotu, invT, -mu_T), sign, s_pow2);
+                    const double pdsigma = fma(mT, ac.y, Dv);           // x prefactor * g * tau
+                    const double one_m = fma(-sign, f0, 1.0);
+                    double df = one_m*fma(mT2, eq.x, fma(s_ch[k], F, fma(s_sh[k], G, H)));
+                    if (BULK != 0 || DIFF) {
+                        const double EoT = pdotu*invT;
+                        double inv_pdotu = 0.;
+                        if (BULK == 1 || BULK == 4 || DIFF) inv_pdotu = fast_rcp(pdotu);
+                        if (BULK == 1) {
+                            df += -one_m*bc0*(m2_3T*inv_pdotu - bc1*EoT)*bulkPi;
+                        } else if (BULK == 2) {
+                            df += -one_m*bulkPi*(-bc0 + bc1*EoT);
+                        } else if (BULK == 3) {
+                            df += -one_m*bulkPi*rsqrt(EoT)*(-bc0 + bc1*EoT);
+                        } else if (BULK == 4) {
+                            df += -one_m*bulkPi*(bc0 - bc1*Tc*inv_pdotu);
+                        }
+                        if (DIFF) df += one_m*(pref_q - baryon*inv_pdotu)*(mT*eq.y - Rq)*inv_kappa;
                     }
-                    if (DIFF) df += one_m*(pref_q - baryon*inv_pdotu)*(mT*eq.y - Rq)*inv_kappa;
+                    if (MODE == 2) {
+                        const double size = fabs(df) + 1e-10;
+                        const double resized = df*(ratio_max*fast_rcp(size));
+                        df = size > ratio_max ? resized : df;
+                    }
+                    const double fp = f0*pdsigma;
+                    const double result = fma(fp, df, fp);
+                    if (!(pos_only && result < 0.)) {
+                        csum = fma(result, s_wy[k], csum);
+                        if (WANT_MAX) cmax = fmax(cmax, result);
+                    }
                 }
-                if (restrict_df) {
-                    // resize = min(1, ratio/(|df| + 1e-10)): the division only when it bites
-                    const double size = fabs(df) + 1e-10;
-                    if (size > ratio_max) df *= ratio_max*fast_rcp(size);
-                }
-                const double result = f0*pdsigma*(1.0 + df);
-                if (!(pos_only && result < 0.)) {
-                    sum = fma(result, s_wy[k], sum);
-                    vmax = fmax(vmax, result);
-                }
+                return exceed;
+            };
+            double csum, cmax;
+            if (restrict_df) {
+                cell_loop(std::integral_constant<int, 2>(), csum, cmax);
+            } else {
+                cell_loop(std::integral_constant<int, 0>(), csum, cmax);
             }
+            sum += csum;
+            if (WANT_MAX) vmax = fmax(vmax, cmax);
         }
     }
     if (live) {
@@ -349,9 +374,12 @@ spectra_reduce_kernel(const SpectraArgs A) {
 }
 
 template <int BULK>
-void launch_spectra(const SpectraArgs &A, dim3 grid, cudaStream_t st) {
-    if (A.opt.include_deltaf_diffusion == 1) spectra_kernel<BULK, true><<<grid, SPEC_THREADS, 0, st>>>(A);
-    else spectra_kernel<BULK, false><<<grid, SPEC_THREADS, 0, st>>>(A);
+void launch_spectra(const SpectraArgs &A, dim3 grid, cudaStream_t st, bool want_max) {
+    const bool diff = A.opt.include_deltaf_diffusion == 1;
+    if (diff && want_max) spectra_kernel<BULK, true, true><<<grid, SPEC_THREADS, 0, st>>>(A);
+    else if (diff) spectra_kernel<BULK, true, false><<<grid, SPEC_THREADS, 0, st>>>(A);
+    else if (want_max) spectra_kernel<BULK, false, true><<<grid, SPEC_THREADS, 0, st>>>(A);
+    else spectra_kernel<BULK, false, false><<<grid, SPEC_THREADS, 0, st>>>(A);
 }
 
 }  // namespace
@@ -455,11 +483,11 @@ int iss_cuda_spectra(iss_handle *h, const iss_spectra_options *opt, const iss_sp
     if (opt->include_deltaf_bulk == 1 && opt->bulk_deltaf_kind >= 1 && opt->bulk_deltaf_kind <= 4)
         bulk = opt->bulk_deltaf_kind;
     switch (bulk) {
-    case 1: launch_spectra<1>(A, grid, h->stream); break;
-    case 2: launch_spectra<2>(A, grid, h->stream); break;
-    case 3: launch_spectra<3>(A, grid, h->stream); break;
-    case 4: launch_spectra<4>(A, grid, h->stream); break;
-    default: launch_spectra<0>(A, grid, h->stream); break;
+    case 1: launch_spectra<1>(A, grid, h->stream, dN_max != nullptr); break;
+    case 2: launch_spectra<2>(A, grid, h->stream, dN_max != nullptr); break;
+    case 3: launch_spectra<3>(A, grid, h->stream, dN_max != nullptr); break;
+    case 4: launch_spectra<4>(A, grid, h->stream, dN_max != nullptr); break;
+    default: launch_spectra<0>(A, grid, h->stream, dN_max != nullptr); break;
     }
     ISS_LAUNCHED(h);
     spectra_reduce_kernel<<<static_cast<unsigned>((n_out + 255)/256), 256, 0, h->stream>>>(A);
