@@ -4,6 +4,10 @@ Events are independent given the yields and every random stream is keyed by the 
 so rank r of N simply samples its own event range with the same seed: no data-path collective, and
 the union of the ranks' outputs is bit-identical to a single-GPU run.  Only the QA block (plain
 sums, include/iss_cuda.h) is reduced, with one all-reduce (NCCL on GPUs; gloo in the CPU tests).
+
+The smooth-spectra integrator (iss_cuda_spectra) shards the other way: every rank holds the whole
+surface and integrates its own species; the [npT][nphi] tables are gathered, no reduction at all
+(the sum over cells stays on one GPU, in a chunk order that does not depend on the rank count).
 """
 import torch
 import torch.distributed as dist
@@ -22,6 +26,29 @@ def weak_event_range(step, rank, world, events_per_rank):
     """Weak-scaling benchmark layout: every rank samples `events_per_rank` new events per step."""
     begin = (int(step)*int(world) + int(rank))*int(events_per_rank)
     return begin, begin + int(events_per_rank)
+
+
+def split_species(nspecies, world):
+    """Round-robin species lists per rank (species are mass-sorted and the cost per species is
+    uniform, so round-robin balances any list length): rank r gets indices r, r + N, ..."""
+    return [list(range(r, int(nspecies), int(world))) for r in range(int(world))]
+
+
+def gather_species_tables(local, nspecies, world, rank):
+    """local: float64 tensor [len(split_species(...)[rank]), npT, nphi] -> [nspecies, npT, nphi] on
+    every rank (all_gather of equally padded blocks, then un-interleaved)."""
+    per = (int(nspecies) + world - 1)//world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    if world > 1:
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad)
+    else:
+        parts = [pad]
+    out = torch.zeros((int(nspecies),) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r, idx in enumerate(split_species(nspecies, world)):
+        out[idx] = parts[r][:len(idx)]
+    return out
 
 
 def allreduce_sum_(t):

@@ -66,3 +66,47 @@ def test_two_ranks_equal_one_rank(tmp_path):
     sp = np.zeros(len(LAM), dtype=orc.OSpecies)
     mult, _ = orc.multiplicities(LAM, orc.poisson_pmode(LAM), sp, NEV, 0, SEED)
     assert np.array_equal(got, qa_like_block(mult))
+
+
+# ---- species sharding of the smooth-spectra integrator (no reduction: a gather of tables)
+def _spectra_worker(rank, world, port, out):
+    import spectra_oracle as spo
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import spectra_cases as sc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = sc.load("sp3d_shear")
+    opt = sc.options_of(g)
+    species = sc.species_of(g)[:5]
+    pT, phi, eta = sc.bin_tables()
+    lab = g["lab"][:12]
+    mine = sharding.split_species(len(species), world)[rank]
+    local = np.array([spo.spectra(lab, species[k], opt, pT[:4], phi[:6], eta[::8])[0] for k in mine])
+    local = local.reshape(len(mine), 4, 6)
+    full = sharding.gather_species_tables(torch.from_numpy(local), len(species), world, rank)
+    if rank == 0:
+        np.save(out, full.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_split_species_round_robin():
+    for ns, world in [(5, 2), (321, 8), (3, 4), (7, 1)]:
+        parts = sharding.split_species(ns, world)
+        assert sorted(i for p in parts for i in p) == list(range(ns))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_species_sharded_spectra_equal_single_process(tmp_path):
+    import socket
+    outs = []
+    for world in (1, 2):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        out = str(tmp_path/("spectra_w%d.npy" % world))
+        mp.spawn(_spectra_worker, args=(world, port, out), nprocs=world, join=True)
+        outs.append(np.load(out))
+    assert outs[0].shape == (5, 4, 6)
+    assert np.array_equal(outs[0], outs[1])       # gathered tables are bit-identical

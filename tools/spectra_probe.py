@@ -34,3 +34,25 @@ for name, kw in (("shear only", dict(include_deltaf_bulk=0, include_deltaf_diffu
     n, ms = e.spectra_stats()
     print("%-20s cells=%d species=%d evals=%.3e kernel %.1f ms (wall %.1f ms) -> %.3e evals/s; "
           "FP64 DFMA peak %.1f TFLOP/s" % (name, ncell, ns, n, ms, 1e3*wall, n/(ms*1e-3), peak))
+
+# CPU reference beside it: the unmodified reference (oracle/_ref/ref_driver spectra, one core) on a
+# 300-cell sample of the same kind of surface, 7 species, bulk kind 1 + diffusion
+import json, shutil, subprocess, tempfile
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+drv = os.path.join(REPO, "oracle", "_ref", "ref_driver")
+if os.path.exists(drv) and os.environ.get("PROBE_CPU", "1") == "1":
+    from iss_b200 import synthetic
+    d = tempfile.mkdtemp()
+    os.symlink(os.path.join(REPO, "iSS_tables"), os.path.join(d, "iSS_tables"))
+    synthetic.make_case(os.path.join(d, "case"), ncell=300, seed=32, eos=14, rhob=1, diffusion=1, binary=1)
+    t0 = time.perf_counter()
+    subprocess.run([drv, "spectra", os.path.join(REPO, "tests", "fixtures", "iSS_parameters_CEdeltaf.dat"),
+                    "case", "surface.dat", os.path.join(d, "out"), "species=211,321,2212,-2212,3122,113,2224",
+                    "bulk_deltaf_kind=1", "include_deltaf_diffusion=1"], cwd=d, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    wall = time.perf_counter() - t0
+    log_evals = 300*81*15*48*7
+    print(json.dumps({"cpu_reference": "ref_driver spectra (EmissionFunctionArray::calculate_dN_pTdpTdphidy), 1 core, "
+                      "300 cells x 7 species, bulk kind 1 + diffusion", "evals": log_evals, "wall_s": round(wall, 3),
+                      "evals_per_s_per_core": log_evals/wall, "note": "wall includes reading the tables (~0.1 s)"}))
+    shutil.rmtree(d)
