@@ -191,7 +191,7 @@ spectra_cell_kernel(const SpectraArgs A) {
 // BULK: 0 none/kind 0 (zero coefficients), 1..4 the reference's kinds; DIFF: diffusion delta f;
 // WANT_MAX: also the maximum over (cell, y - eta_s) the reference keeps for its MC_sampling = 3
 template <int BULK, bool DIFF, bool WANT_MAX>
-__global__ void __launch_bounds__(SPEC_THREADS, 2)
+__global__ void __launch_bounds__(SPEC_THREADS, 3)
 spectra_kernel(const SpectraArgs A) {
     __shared__ double s_ch[MAX_NY], s_sh[MAX_NY], s_wy[MAX_NY];
     __shared__ double s_pow2[16];
