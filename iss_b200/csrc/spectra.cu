@@ -29,6 +29,10 @@ namespace iss {
 namespace {
 
 constexpr int SPEC_THREADS = 256;
+#ifndef SPEC_UNROLL
+#define SPEC_UNROLL 3
+#endif
+constexpr int K_UNROLL = SPEC_UNROLL;    // y - eta_s points interleaved per thread
 constexpr int CELL_TILE = 8;            // cells staged per shared-memory tile
 constexpr int MAX_NY = 128;             // y - eta_s points
 constexpr int REC = 36;                 // doubles per cell record (species independent)
@@ -191,7 +195,7 @@ spectra_cell_kernel(const SpectraArgs A) {
 // BULK: 0 none/kind 0 (zero coefficients), 1..4 the reference's kinds; DIFF: diffusion delta f;
 // WANT_MAX: also the maximum over (cell, y - eta_s) the reference keeps for its MC_sampling = 3
 template <int BULK, bool DIFF, bool WANT_MAX>
-__global__ void __launch_bounds__(SPEC_THREADS, 3)
+__global__ void __launch_bounds__(SPEC_THREADS, 2)
 spectra_kernel(const SpectraArgs A) {
     __shared__ double s_ch[MAX_NY], s_sh[MAX_NY], s_wy[MAX_NY];
     __shared__ double s_pow2[16];
@@ -301,7 +305,7 @@ spectra_kernel(const SpectraArgs A) {
                 bool exceed = false;
                 csum = 0.;
                 cmax = 0.;
-#pragma unroll 3
+#pragma unroll K_UNROLL
                 for (int k = 0; k < ny; k++) {
                     const double2 ac = s_ac[q][k];
                     const double2 eq = s_eq[q][k];
