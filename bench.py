@@ -132,6 +132,35 @@ def workload_name(ncell, events):
             "events (+ QA histograms)" % (ncell, events))
 
 
+def spectra_leg(cells=5000):
+    """Secondary measurement, N = 1 only: the smooth-spectra mode of
+    the facade (MC_sampling = 0, calculate_vn = 1) on a `cells`-cell surface of the same generator,
+    all species of the list, shear + bulk (kind 1) + diffusion delta f.  Not part of `value`."""
+    from iss_b200 import capi
+    work = tempfile.mkdtemp(prefix="iss_bench_spectra_")
+    try:
+        make_case(work, cells)
+        over = dict(OVERRIDES, MC_sampling=0, calculate_vn=1, bulk_deltaf_kind=1,
+                    calculate_vn_to_order=4)
+        s = capi.Sampler(work, PARAM, "surface.dat", **over)
+        s.read_in_FO_surface()
+        t0 = time.perf_counter()
+        s.generate_samples()
+        wall = time.perf_counter() - t0
+        _, kernel_ms, evals = s.spectra_table(211)
+        s.close()
+        return {"what": "iSS::generate_samples() with MC_sampling=0, calculate_vn=1: dN/(pT dpT dphi dy) "
+                        "and v_n of every species (EmissionFunctionArray::calculate_dN_pTdpTdphidy)",
+                "cells": cells, "points": evals, "kernel_ms": kernel_ms,
+                "points_per_sec": evals/(kernel_ms*1e-3) if kernel_ms > 0 else None,
+                "wall_ms_generate_samples": 1e3*wall, "bound": "fp64",
+                "note": "ncu of the shear-only variant (profiles/r1_ncu_spectra_qa.json): 37.3 FP64 "
+                        "instructions of 68.7 per point, FP64 pipe 67.6 % of peak; reference CPU "
+                        "5.2e7 points/s per core (profiles/r1_spectra_probe.txt)"}
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------------------ engine arm
 def run_engine(args):
     import torch
@@ -247,6 +276,12 @@ def run_engine(args):
         h2d = ncell*28*4 + table_bytes
         d2h = int(e2e_hadrons/e2e_steps)*40 + (E + 1)*8
         s.close()
+        spectra = None
+        if world == 1 and not args.no_spectra:
+            try:
+                spectra = spectra_leg()
+            except Exception as exc:        # secondary figure: never fails the headline line
+                spectra = {"error": "%s: %s" % (type(exc).__name__, exc)}
     finally:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
@@ -310,6 +345,7 @@ def run_engine(args):
                 "call": "iSS::generate_samples() (class iSS facade, host surface -> host hadron lists)"},
         "gpu_launches": launches,
         "clocks": clk,
+        "spectra": spectra,
     }
     if rank == 0:
         cb = None
@@ -426,6 +462,7 @@ def main():
     ap.add_argument("--events-per-step", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-spectra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         # a reference "step" is a full multi-process run of the binary: keep the count small
