@@ -301,6 +301,41 @@ ISS_API int iss_cuda_spectra(iss_handle *h, const iss_spectra_options *opt,
 /* evaluations (cell x y-eta point x pT x phi x species) and kernel milliseconds of the last call */
 ISS_API int iss_cuda_spectra_stats(iss_handle *h, double *evaluations, double *kernel_ms);
 
+/* ---- surface ingest on the device -------------------------
+ * Binary MUSIC surface records (34 float32 per cell, reference src/readindata.cpp:646-689) ->
+ * local-rest-frame records in ISS_F_* order, i.e. the per-cell work of
+ * read_FOdata::read_FOsurfdat_MUSIC(_boost_invariant) (readindata.cpp:395-546, 626-765),
+ * regulate_surface_cells / getValuesFromHRGEOS / regulate_Wmunu (:768-842, 1216-1309),
+ * iSS::computeFOSurfTmunu (src/iSS.cpp:378-445, per-cell tensors) and
+ * iSS::transform_to_local_rest_frame (src/iSS.cpp:170-293), with both filters applied in file
+ * order: cells with T <= 0.01 GeV (readindata.cpp:752) and cells with u.dsigma < 0 (iSS.cpp:226). */
+typedef struct {
+    int32_t boost_invariant;    /* hydro_mode 1: eta_s = 0, da3 = 0 (readindata.cpp:428-432)       */
+    int32_t regulate_eos;       /* EOS 9/91/12/14: T, mu_B, mu_S, mu_Q, P from the HRG table        */
+    int32_t hrg_nB;             /* n_B points per energy-density row: 1 (EOS 9/91) or 200 (12/14)   */
+    int32_t reserved;
+    int64_t hrg_rows;           /* rows of 7 doubles: ed, nB, P, T, muB, muS, muQ                   */
+} iss_ingest_options;
+
+typedef struct {
+    int64_t n_in;               /* records in the file                                             */
+    int64_t n_after_T;          /* cells that passed the T filter (tmunu_out rows)                  */
+    int64_t n_kept;             /* cells that also passed u.dsigma >= 0 (lrf_out rows)              */
+} iss_ingest_result;
+
+/* per-record status bits (status_out) */
+#define ISS_INGEST_DROPPED_T 1          /* T <= 0.01 GeV                                           */
+#define ISS_INGEST_EOS_RANGE 2          /* energy density outside the HRG table: T, mu, P kept       */
+#define ISS_INGEST_DROPPED_NORMAL 4     /* u.dsigma < 0                                             */
+
+/* All pointers are host memory.  lrf_out: room for ncell x ISS_NFIELD floats; tmunu_out (may be
+ * NULL): ncell x 16 floats, the per-cell T^{mu nu} of iSS::computeFOSurfTmunu for the cells that
+ * passed the T filter; status_out (may be NULL): ncell bytes. */
+ISS_API int iss_cuda_ingest_music_binary(iss_handle *h, const float *raw, int64_t ncell,
+                                         const iss_ingest_options *opt, const double *hrg,
+                                         float *lrf_out, float *tmunu_out, uint8_t *status_out,
+                                         iss_ingest_result *res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,15 @@ class SpectraOptions(C.Structure):
                 ("deltaf_max_ratio", C.c_double)]
 
 
+class IngestOptions(C.Structure):
+    _fields_ = [("boost_invariant", C.c_int32), ("regulate_eos", C.c_int32), ("hrg_nB", C.c_int32),
+                ("reserved", C.c_int32), ("hrg_rows", C.c_int64)]
+
+
+class IngestResult(C.Structure):
+    _fields_ = [("n_in", C.c_int64), ("n_after_T", C.c_int64), ("n_kept", C.c_int64)]
+
+
 class Counts(C.Structure):
     _fields_ = [("n_events", C.c_int64), ("n_hadrons", C.c_int64), ("n_tries", C.c_int64),
                 ("n_cell_redraws", C.c_int64)]
@@ -89,6 +98,7 @@ CUDA_SYMBOLS = [
     "iss_cuda_set_trace", "iss_cuda_get_trace", "iss_cuda_upload_surface_aos",
     "iss_cuda_fetch_all_async", "iss_cuda_fetch_wait", "iss_cuda_sample_momentum",
     "iss_cuda_upload_surface_lab", "iss_cuda_spectra", "iss_cuda_spectra_stats",
+    "iss_cuda_ingest_music_binary",
 ]
 HOST_SYMBOLS = [
     "iss_host_create", "iss_host_destroy", "iss_host_set_param", "iss_host_get_param",
@@ -159,6 +169,8 @@ def cuda_lib():
         "iss_cuda_spectra": (C.c_int, [vp, C.POINTER(SpectraOptions), vp, i32, vp, i32, vp, i32, vp, vp,
                                        i32, vp, vp]),
         "iss_cuda_spectra_stats": (C.c_int, [vp, dp, dp]),
+        "iss_cuda_ingest_music_binary": (C.c_int, [vp, vp, i64, C.POINTER(IngestOptions), vp, vp, vp, vp,
+                                                   C.POINTER(IngestResult)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -403,6 +415,30 @@ class Engine:
         n, ms = C.c_double(), C.c_double()
         self.check(self.L.iss_cuda_spectra_stats(self.h, C.byref(n), C.byref(ms)), "spectra_stats")
         return n.value, ms.value
+
+    # ---- surface ingest on the device (binary MUSIC records -> LRF records)
+    def ingest_music_binary(self, raw, hrg=None, hrg_nB=1, boost_invariant=False):
+        """raw: float32 [ncell, 34]; hrg: float64 [rows, 7] or None (no EOS regulation).
+        Returns (lrf [n_kept, 28], tmunu [n_after_T, 16], status [ncell])."""
+        raw = np.ascontiguousarray(raw, dtype=np.float32)
+        n = raw.shape[0]
+        o = IngestOptions()
+        o.boost_invariant = int(bool(boost_invariant))
+        o.regulate_eos = 0 if hrg is None else 1
+        o.hrg_nB = int(hrg_nB)
+        hp = None
+        if hrg is not None:
+            hrg = np.ascontiguousarray(hrg, dtype=np.float64)
+            o.hrg_rows = hrg.shape[0]
+            hp = _ptr(hrg)
+        lrf = np.zeros((n, NFIELD), dtype=np.float32)
+        tm = np.zeros((n, 16), dtype=np.float32)
+        st = np.zeros(n, dtype=np.uint8)
+        res = IngestResult()
+        self.check(self.L.iss_cuda_ingest_music_binary(self.h, _ptr(raw), n, C.byref(o), hp, _ptr(lrf),
+                                                       _ptr(tm), _ptr(st), C.byref(res)),
+                   "ingest_music_binary")
+        return lrf[:res.n_kept], tm[:res.n_after_T], st
 
     def fp64_peak(self):
         t = C.c_double()

@@ -150,7 +150,7 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_bessel); cudaFree(h->d_expint); cudaFree(h->d_sf4); cudaFree(h->d_combos); cudaFree(h->d_ce); cudaFree(h->d_mom22);
     cudaFree(h->d_mom14); cudaFree(h->d_kappa);
     cudaFree(h->d_lab); cudaFree(h->d_labrec); cudaFree(h->d_spec_part); cudaFree(h->d_spec_out);
-    cudaFree(h->d_spec_tab);
+    cudaFree(h->d_spec_tab); cudaFree(h->d_ingest);
     for (int r = 0; r < 6; r++) cudaFree(h->d_momtab[r]);
     cudaFree(h->d_dsp); cudaFree(h->d_dch); cudaFree(h->d_sorted_pid); cudaFree(h->d_sorted_idx);
     cudaFree(h->d_lambda); cudaFree(h->d_pmode);

@@ -103,6 +103,7 @@ struct iss_handle {
     double *d_spec_out = nullptr; size_t spec_out_bytes = 0;
     double *d_spec_tab = nullptr; size_t spec_tab_bytes = 0;            // momentum / eta tables
     double spec_evals = 0., spec_ms = 0.;
+    void *d_ingest = nullptr; size_t ingest_bytes = 0;                  // surface ingest arena (ingest.cu)
     double *d_momtab[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     iss::MomentumTable momtab[6]{};     // 0..2 boson regimes, 3..5 fermion regimes
 

@@ -95,10 +95,7 @@ HandlePool &handle_pool() {
     return p;
 }
 
-struct PinnedBlock {
-    void *ptr = nullptr;
-    int64_t bytes = 0;
-};
+using iss_pool::PinnedBlock;
 struct PinnedPool {
     std::mutex mu;
     std::vector<PinnedBlock> idle;
@@ -109,7 +106,7 @@ PinnedPool &pinned_pool() {
 }
 
 // a pinned block of at least `bytes` (the largest idle one if it fits, else a new allocation)
-PinnedBlock pinned_acquire(iss_handle *h, int64_t bytes) {
+PinnedBlock pool_acquire(iss_handle *h, int64_t bytes) {
     PinnedPool &P = pinned_pool();
     {
         std::lock_guard<std::mutex> lk(P.mu);
@@ -129,7 +126,7 @@ PinnedBlock pinned_acquire(iss_handle *h, int64_t bytes) {
     return b;
 }
 
-void pinned_release(iss_handle *h, PinnedBlock b) {
+void pool_release(iss_handle *h, PinnedBlock b) {
     if (!b.ptr) return;
     PinnedPool &P = pinned_pool();
     std::lock_guard<std::mutex> lk(P.mu);
@@ -198,6 +195,9 @@ void release_handle(int device, iss_handle *h) {
 const std::vector<double> &cached_numbers(const std::string &file, int skip_lines) {
     return cached_numbers_impl(file, skip_lines);
 }
+
+PinnedBlock pinned_acquire(iss_handle *h, int64_t bytes) { return pool_acquire(h, bytes); }
+void pinned_release(iss_handle *h, PinnedBlock b) { pool_release(h, b); }
 
 }  // namespace iss_pool
 
@@ -273,7 +273,7 @@ GpuFSSW::~GpuFSSW() {
     PinnedBlock b;
     b.ptr = hadrons_;
     b.bytes = hadron_cap_*static_cast<int64_t>(sizeof(iSS_Hadron));
-    pinned_release(h_, b);
+    pool_release(h_, b);
     iss_pool::release_handle(device_, h_);
 }
 
@@ -327,7 +327,7 @@ void GpuFSSW::select_species_(const std::vector<int> &chosen_monvals) {
 
 void GpuFSSW::upload_surface_() {
     const int64_t n = static_cast<int64_t>(surf_.size());
-    PinnedBlock stage = pinned_acquire(h_, n*ISS_NFIELD*static_cast<int64_t>(sizeof(float)));
+    PinnedBlock stage = pool_acquire(h_, n*ISS_NFIELD*static_cast<int64_t>(sizeof(float)));
     float *dst = static_cast<float *>(stage.ptr);
     auto pack = [&](int64_t c0, int64_t c1) {
         for (int64_t c = c0; c < c1; c++) {
@@ -355,7 +355,7 @@ void GpuFSSW::upload_surface_() {
         for (auto &t : pool) t.join();
     }
     check_(iss_cuda_upload_surface_aos(h_, dst, n), "iss_cuda_upload_surface_aos");
-    pinned_release(h_, stage);
+    pool_release(h_, stage);
 }
 
 // delta-f coefficient tables, file formats of FSSW.cpp:1215-1376 and 1546-1568
@@ -513,14 +513,14 @@ void GpuFSSW::reserve_hadrons_(int64_t need) {
     if (need <= hadron_cap_) return;
     int64_t cap = std::max<int64_t>(need, hadron_cap_ + hadron_cap_/2);
     cap = std::max<int64_t>(cap, 1024);
-    PinnedBlock b = pinned_acquire(h_, cap*static_cast<int64_t>(sizeof(iSS_Hadron)));
+    PinnedBlock b = pool_acquire(h_, cap*static_cast<int64_t>(sizeof(iSS_Hadron)));
     if (hadrons_) {
         check_(iss_cuda_fetch_wait(h_), "iss_cuda_fetch_wait");     // copies into the old block
         memcpy(b.ptr, hadrons_, sizeof(iSS_Hadron)*event_off_.back());
         PinnedBlock old;
         old.ptr = hadrons_;
         old.bytes = hadron_cap_*static_cast<int64_t>(sizeof(iSS_Hadron));
-        pinned_release(h_, old);
+        pool_release(h_, old);
     }
     hadrons_ = static_cast<iSS_Hadron *>(b.ptr);
     hadron_cap_ = b.bytes/static_cast<int64_t>(sizeof(iSS_Hadron));

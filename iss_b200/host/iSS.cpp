@@ -11,6 +11,7 @@
 #include <iostream>
 #include <sstream>
 
+#include "engine_pool.h"
 #include "gpu_fssw.h"
 #include "gpu_spectra.h"
 #include "logger.h"
@@ -141,7 +142,24 @@ int iSS::read_in_FO_surface() {
     FOsurf_array_.clear();
     // (the blocked binary pipeline feeds the LRF transform; the lab-frame path keeps whole cells)
     const int64_t nbin = fssw ? reader.open_binary_surface(surface_filename_) : -1;
-    if (nbin >= 0) {
+    // ISS_INGEST=host keeps the per-cell work on the host (tests without a GPU, debugging); the
+    // default for binary surfaces is the device (no silent fallback: without a CUDA device
+    // acquire_handle exits with a message)
+    const char *ingest_env = getenv("ISS_INGEST");
+    const bool device_ingest = !(ingest_env && std::string(ingest_env) == "host");
+    if (nbin >= 0 && device_ingest) {
+        std::cout << " -- Read spatial positions of freeze out surface from MUSIC...";
+        ingest_binary_on_device_(reader, nbin);
+        reader.close_surface();
+        std::cout << "done" << std::endl;
+        lap("binary surface, device ingest");
+        std::vector<FO_surf> none;
+        afterburner_type_ = reader.get_afterburner_type();
+        reader.read_in_chemical_potentials(none, particle_);
+        flag_PCE_ = reader.get_flag_PCE();
+        report_Tmunu_();
+        lap("particle table");
+    } else if (nbin >= 0) {
         // binary surface: parse -> regulate -> T^{mu nu} -> LRF transform over blocks that stay in
         // cache; per-cell arithmetic and cell order are those of the whole-surface path
         std::cout << " -- Read spatial positions of freeze out surface from MUSIC...";
@@ -209,6 +227,108 @@ int iSS::read_in_FO_surface() {
     }
     info(" -- Read in data finished!");
     return 0;
+}
+
+// Binary surface -> FOsurf_LRF_array_ with the per-cell work on the GPU
+// (iss_cuda_ingest_music_binary, include/iss_cuda.h): the file is sent in chunks, the compacted
+// local-rest-frame records and per-cell T^{mu nu} tensors come back; what stays on the host is
+// the sequential float sum of the tensors in file order (iSS.cpp:378-445) and the messages.
+void iSS::ingest_binary_on_device_(read_FOdata &reader, int64_t nbin) {
+    const int device = iss_pool::default_device();
+    iss_handle *h = iss_pool::acquire_handle(device);
+    iss_ingest_options opt;
+    opt.boost_invariant = reader.boost_invariant() ? 1 : 0;
+    opt.regulate_eos = reader.regulates_eos() ? 1 : 0;
+    opt.hrg_nB = reader.hrg_nB();
+    opt.reserved = 0;
+    opt.hrg_rows = static_cast<int64_t>(reader.hrg_table().size()/7);
+    FOsurf_Tmunu_.assign(16, 0.f);
+    FOsurf_Q_.assign(3, 0.f);
+    const int64_t CHUNK = 1 << 22;          // cells per call: bounds the device arena (~2 GB)
+    const int64_t cap = std::min<int64_t>(nbin, CHUNK);
+    iss_pool::PinnedBlock blk = iss_pool::pinned_acquire(
+        h, cap*static_cast<int64_t>((ISS_NFIELD + 16)*sizeof(float) + 1));
+    float *lrf = static_cast<float *>(blk.ptr);
+    float *tm = lrf + cap*ISS_NFIELD;
+    uint8_t *status = reinterpret_cast<uint8_t *>(tm + cap*16);
+    const float *raw = reader.binary_records();
+    const bool regulate = reader.regulates_eos();
+    if (regulate) std::cout << "Regulate local temperature with pure HRG EoS." << std::endl;
+    int64_t ntotal = 0;
+    float last_Bn = 0.f;
+    bool any_T = false;
+    for (int64_t c0 = 0; c0 < nbin; c0 += CHUNK) {
+        const int64_t n = std::min<int64_t>(CHUNK, nbin - c0);
+        iss_ingest_result res;
+        const int rc = iss_cuda_ingest_music_binary(h, raw + 34*c0, n, &opt, reader.hrg_table().data(),
+                                                    lrf, tm, status, &res);
+        if (rc != ISS_OK) {
+            iss_host::error(std::string("iss_cuda_ingest_music_binary failed: ") + iss_cuda_last_error(h));
+            exit(-1);
+        }
+        // the reference's per-cell messages (readindata.cpp:752-758, 1262-1266)
+        if (res.n_after_T != n || regulate) {
+            for (int64_t c = 0; c < n; c++) {
+                if (status[c] & ISS_INGEST_DROPPED_T) {
+                    const float *a = raw + 34*(c0 + c);
+                    std::cout << "Discard surf elem: T = " << static_cast<float>(a[13]*iSS_data::hbarC)
+                              << " GeV, Edec = " << static_cast<float>(a[12]*iSS_data::hbarC)
+                              << " GeV/fm^3, rhoB = " << a[29] << " 1/fm^3, muB = "
+                              << static_cast<float>(a[14]*iSS_data::hbarC) << " GeV. " << std::endl;
+                } else if (status[c] & ISS_INGEST_EOS_RANGE) {
+                    std::ostringstream os;
+                    os << "ed is out of range: ed = "
+                       << static_cast<double>(static_cast<float>(raw[34*(c0 + c) + 12]*iSS_data::hbarC))
+                       << " GeV/fm^3. Can not regulate this fluid cell!";
+                    iss_host::warning(os.str());
+                }
+            }
+        }
+        // sequential float sums of the per-cell tensors, file order
+        float acc[16];
+        for (int k = 0; k < 16; k++) acc[k] = FOsurf_Tmunu_[k];
+        for (int64_t ic = 0; ic < res.n_after_T; ic++)
+            for (int k = 0; k < 16; k++) acc[k] += tm[ic*16 + k];
+        for (int k = 0; k < 16; k++) FOsurf_Tmunu_[k] = acc[k];
+        ntotal += res.n_after_T;
+        // Bn of the last cell that passed the T filter (FOsurf_Q_, iSS.cpp:441-444)
+        for (int64_t c = n - 1; c >= 0; c--)
+            if (!(status[c] & ISS_INGEST_DROPPED_T)) {
+                last_Bn = raw[34*(c0 + c) + 29];
+                any_T = true;
+                break;
+            }
+        // records -> FO_surf_LRF
+        const size_t base = FOsurf_LRF_array_.size();
+        FOsurf_LRF_array_.resize(base + res.n_kept);
+        iss_host::parallel_ranges(res.n_kept, iss_host::ingest_threads(res.n_kept),
+                                  [&](int64_t b, int64_t e, int) {
+            for (int64_t i = b; i < e; i++) {
+                const float *r = lrf + i*ISS_NFIELD;
+                FO_surf_LRF &o = FOsurf_LRF_array_[base + i];
+                o.tau = r[ISS_F_TAU]; o.xpt = r[ISS_F_X]; o.ypt = r[ISS_F_Y]; o.eta = r[ISS_F_ETA];
+                o.da_mu_LRF = {r[ISS_F_DA0], r[ISS_F_DA1], r[ISS_F_DA2], r[ISS_F_DA3]};
+                o.u_tz = {r[ISS_F_UT], r[ISS_F_UX], r[ISS_F_UY], r[ISS_F_UZ]};
+                o.Edec = r[ISS_F_E]; o.Tdec = r[ISS_F_T]; o.Pdec = r[ISS_F_P]; o.Bn = r[ISS_F_NB];
+                o.muB = r[ISS_F_MUB]; o.muS = r[ISS_F_MUS]; o.muQ = r[ISS_F_MUQ];
+                o.bulkPi = r[ISS_F_BULKPI];
+                o.piLRF_xx = r[ISS_F_PIXX]; o.piLRF_xy = r[ISS_F_PIXY]; o.piLRF_xz = r[ISS_F_PIXZ];
+                o.piLRF_yy = r[ISS_F_PIYY]; o.piLRF_yz = r[ISS_F_PIYZ];
+                o.qmuLRF_x = r[ISS_F_QX]; o.qmuLRF_y = r[ISS_F_QY]; o.qmuLRF_z = r[ISS_F_QZ];
+            }
+        });
+    }
+    if (any_T) {
+        FOsurf_Q_[0] = last_Bn;
+        FOsurf_Q_[2] = 0.4*last_Bn;
+    }
+    iss_pool::pinned_release(h, blk);
+    iss_pool::release_handle(device, h);
+    info("total number of cells: " + std::to_string(ntotal));
+    if (ntotal == 0) {
+        iss_host::warning("No freeze-out fluid cell, exit now ...");
+        exit(1);
+    }
 }
 
 // Philox needs a definite key: a negative seed (reference: std::random_device, Random.cpp:7-14)

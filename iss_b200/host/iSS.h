@@ -48,6 +48,7 @@ class iSS {
     void require_supported_mode_() const;
     void accumulate_Tmunu_(const std::vector<FO_surf> &cells);
     void report_Tmunu_() const;
+    void ingest_binary_on_device_(class read_FOdata &reader, int64_t nbin);
 
  public:
     iSS(std::string path, std::string table_path = "iSS_tables",

@@ -41,6 +41,14 @@ class read_FOdata {
     int64_t open_binary_surface(const std::string &surface_filename);   // cells in the file, -1 if text
     void read_binary_block(std::vector<FO_surf> &surf, int64_t c0, int64_t n);
     void close_surface();
+    // what the device ingest (iss_cuda_ingest_music_binary) needs from the reader
+    const float *binary_records() const { return static_cast<const float *>(surface_map_); }
+    bool boost_invariant() const { return mode_ == 1; }
+    bool regulates_eos() const {
+        return iEOS_MUSIC_ == 9 || iEOS_MUSIC_ == 91 || iEOS_MUSIC_ == 12 || iEOS_MUSIC_ == 14;
+    }
+    int hrg_nB() const { return (iEOS_MUSIC_ == 12 || iEOS_MUSIC_ == 14) ? 200 : 1; }
+    const std::vector<double> &hrg_table() const { return hrg_; }
     void read_in_chemical_potentials(std::vector<FO_surf> &surf,
                                      std::vector<particle_info> &particles);
     int read_resonances_list(std::vector<particle_info> &particles);

@@ -20,7 +20,10 @@ def test_ingest_bit_exact(name, built, tmp_path):
     os.symlink(capi.TABLES, tmp_path/"iSS_tables")
     exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iss_host_dump")
     args = [exe, param, "case", surf, "out"] + ["%s=%r" % kv for kv in over.items()]
-    r = subprocess.run(args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    # the HOST reader is what this CPU test checks; binary surfaces go through the device by
+    # default (tests/test_ingest_gpu.py) and never fall back silently
+    r = subprocess.run(args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       env=dict(os.environ, ISS_INGEST="host"))
     assert r.returncode == 0, r.stdout.decode()[-2000:]
     with open(tmp_path/"out.lrf.bin", "rb") as f:
         n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
@@ -46,9 +49,20 @@ def test_libraries_export_declared_symbols(built):
         assert hasattr(H, sname), sname
 
 
-def test_no_gpu_fails_loudly(built):
+def test_no_gpu_fails_loudly(built, tmp_path):
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     with pytest.raises(capi.IssError):
         capi.Engine()
+    # a binary surface is ingested on the device: without one the facade exits with a message
+    # instead of quietly using the host reader
+    g = cases.load("s3d_ce_diff")
+    param, surf, over = cases.materialise(g, str(tmp_path/"case"))
+    os.symlink(capi.TABLES, tmp_path/"iSS_tables")
+    exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iss_host_dump")
+    env = {k: v for k, v in os.environ.items() if k != "ISS_INGEST"}
+    r = subprocess.run([exe, param, "case", surf, "out"] + ["%s=%r" % kv for kv in over.items()],
+                       cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
+    assert r.returncode != 0
+    assert b"no usable CUDA device" in r.stdout
