@@ -192,6 +192,37 @@ ISS_API int iss_cuda_set_options(iss_handle *h, const iss_options *opt);
  *      yields_host (may be NULL) <- [ns][ncell] FP64 per-cell yields.                */
 ISS_API int iss_cuda_compute_yields(iss_handle *h, double *dN_species_host, double *yields_host);
 
+/* ---- surface-chunk sharding: a surface too large, or too slow, for one
+ *      GPU is cut into contiguous cell ranges, one per rank; every rank samples ALL events but only
+ *      the hadrons whose cell (RandomVariable1DArray::rand over the WHOLE surface,
+ *      RandomVariable1DArray.cpp:63-67) lies in its range.  The reference has no counterpart (it is
+ *      serial); what is kept is its result: the union of the ranks' hadron lists equals, record for
+ *      record, the list of one GPU holding the whole surface, because
+ *        - the per-species sum over cells (RandomVariable1DArray.cpp:38-50) is evaluated as tile
+ *          sums (1024 cells) combined in one fixed order; ranks exchange the tile sums (one
+ *          all-gather of [nspecies][ntile] doubles, the only collective) and each evaluates the
+ *          same combination, so totals, Poisson draws and prefix values have the same bits;
+ *        - the cell search descends the same 16-ary tree: its upper levels (one entry per 4096
+ *          cells) are rebuilt on every rank from the gathered tile sums, the lower ones are local.
+ *      Call order per rank:  upload_surface(_aos)(cells of the chunk) -> set_surface_chunk ->
+ *      chunk_yields_local -> [all-gather] -> chunk_yields_finish -> sample / decay / histograms.
+ *      cell_begin must be a multiple of ISS_CHUNK_ALIGN; the chunk ends at a multiple of it or at
+ *      the end of the surface.  ncell_global <= 0 switches the mode off.
+ *      Limitation: the reference's re-draw of the cell after 4999 rejected tries
+ *      (FSSW.cpp:1017-1018) is only honoured when the new cell is in the same chunk; otherwise the
+ *      record is null and iss_cuda_sample returns ISS_ERR_RANGE.                              */
+#define ISS_CHUNK_ALIGN 4096
+ISS_API int iss_cuda_set_surface_chunk(iss_handle *h, int64_t cell_begin, int64_t ncell_global);
+/* yields of the local cells; *tilesum_dev <- device pointer of [nspecies][*ntile_local] doubles
+ * (valid until the next yields call), ready to be the send buffer of the all-gather              */
+ISS_API int iss_cuda_chunk_yields_local(iss_handle *h, void **tilesum_dev, int64_t *ntile_local);
+/* rank_tilesums[r]: the block rank r exported, [nspecies][rank_ntile[r]], in rank (= cell) order;
+ * device pointers if on_device != 0 (e.g. the output of an NCCL all-gather), else host memory.
+ * dN_species_host[ns] <- sums over the WHOLE surface (as iss_cuda_compute_yields).               */
+ISS_API int iss_cuda_chunk_yields_finish(iss_handle *h, const double *const *rank_tilesums,
+                                         const int64_t *rank_ntile, int32_t nranks, int on_device,
+                                         double *dN_species_host);
+
 /* ---- sampling: FSSW::sample_using_dN_dxtdy_4all_particles_conventional (FSSW.cpp:873-1071)
  *      for events [ev_begin, ev_end): multiplicities, offsets, momenta, boost, emit. */
 ISS_API int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_end,

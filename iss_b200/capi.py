@@ -98,7 +98,8 @@ CUDA_SYMBOLS = [
     "iss_cuda_set_trace", "iss_cuda_get_trace", "iss_cuda_upload_surface_aos",
     "iss_cuda_fetch_all_async", "iss_cuda_fetch_wait", "iss_cuda_sample_momentum",
     "iss_cuda_upload_surface_lab", "iss_cuda_spectra", "iss_cuda_spectra_stats",
-    "iss_cuda_ingest_music_binary",
+    "iss_cuda_ingest_music_binary", "iss_cuda_set_surface_chunk", "iss_cuda_chunk_yields_local",
+    "iss_cuda_chunk_yields_finish",
 ]
 HOST_SYMBOLS = [
     "iss_host_create", "iss_host_destroy", "iss_host_set_param", "iss_host_get_param",
@@ -142,6 +143,9 @@ def cuda_lib():
         "iss_cuda_upload_decay_table": (C.c_int, [vp, vp, i32, vp, i32]),
         "iss_cuda_set_options": (C.c_int, [vp, C.POINTER(Options)]),
         "iss_cuda_compute_yields": (C.c_int, [vp, vp, vp]),
+        "iss_cuda_set_surface_chunk": (C.c_int, [vp, i64, i64]),
+        "iss_cuda_chunk_yields_local": (C.c_int, [vp, C.POINTER(vp), i64p]),
+        "iss_cuda_chunk_yields_finish": (C.c_int, [vp, C.POINTER(vp), i64p, i32, C.c_int, vp]),
         "iss_cuda_sample": (C.c_int, [vp, u64, i64, i64, C.POINTER(Counts)]),
         "iss_cuda_get_multiplicities": (C.c_int, [vp, vp]),
         "iss_cuda_get_poisson_params": (C.c_int, [vp, vp, vp]),
@@ -309,6 +313,45 @@ class Engine:
         self.check(self.L.iss_cuda_compute_yields(self.h, _ptr(dN), _ptr(y) if want_cells else None),
                    "compute_yields")
         return (dN, y) if want_cells else dN
+
+    # ---- surface-chunk sharding (include/iss_cuda.h): this handle holds a contiguous cell range
+    def set_surface_chunk(self, cell_begin, ncell_global):
+        self.check(self.L.iss_cuda_set_surface_chunk(self.h, cell_begin, ncell_global),
+                   "set_surface_chunk")
+
+    def chunk_yields_local(self):
+        """-> (device pointer of the [nspecies][ntile_local] tile sums, ntile_local)"""
+        p = C.c_void_p()
+        n = C.c_int64()
+        self.check(self.L.iss_cuda_chunk_yields_local(self.h, C.byref(p), C.byref(n)),
+                   "chunk_yields_local")
+        return p.value, n.value
+
+    def chunk_tilesums_host(self):
+        """the same block copied to the host (tests; the multi-GPU path all-gathers on the device)"""
+        import torch
+        ptr, nt = self.chunk_yields_local()
+        from .sharding import device_block_as_tensor
+        t = device_block_as_tensor(ptr, self.nspecies*nt, torch.device("cuda", torch.cuda.current_device()))
+        return t.cpu().numpy().reshape(self.nspecies, nt).copy()
+
+    def chunk_yields_finish(self, blocks, ntiles, on_device):
+        """blocks: per rank, a device pointer (int) or a host float64 array [nspecies][ntiles[r]]"""
+        nr = len(blocks)
+        keep = []
+        ptrs = (C.c_void_p*nr)()
+        for r, b in enumerate(blocks):
+            if on_device:
+                ptrs[r] = int(b)
+            else:
+                a = np.ascontiguousarray(b, dtype=np.float64)
+                keep.append(a)
+                ptrs[r] = a.ctypes.data
+        nt = (C.c_int64*nr)(*[int(x) for x in ntiles])
+        dN = np.zeros(self.nspecies)
+        self.check(self.L.iss_cuda_chunk_yields_finish(self.h, ptrs, nt, nr, 1 if on_device else 0,
+                                                       _ptr(dN)), "chunk_yields_finish")
+        return dN
 
     def sample(self, seed, ev_begin, ev_end):
         c = Counts()

@@ -26,6 +26,7 @@ struct DecayArgs {
     int64_t n_in;
     const int64_t *event_off_in;    // [nev+1]
     int64_t nev, ev_begin;
+    uint32_t chunk_id;      // surface-chunk mode: first 4096-cell block of the rank (else 0)
     const iss_decay_species *dsp;
     int ndsp;
     const iss_decay_channel *dch;
@@ -79,7 +80,9 @@ decay_kernel(const DecayArgs A) {
     const int64_t ev = lo;
     const int64_t k = i - __ldg(&A.event_off_in[ev]);
     Stream rng;
-    rng.init(A.seed, STREAM_DECAY, 0, static_cast<uint32_t>(A.ev_begin + ev),
+    // (surface-chunk mode: k counts the rank's primaries of the event; the chunk id keeps the
+    //  streams of different ranks apart)
+    rng.init(A.seed, STREAM_DECAY, A.chunk_id, static_cast<uint32_t>(A.ev_begin + ev),
              static_cast<uint32_t>(k));
 
     const iss_hadron h0 = A.in[i];
@@ -281,6 +284,7 @@ int run_decay(iss_handle *h, uint64_t seed) {
     A.event_off_in = h->d_event_off;
     A.nev = nev;
     A.ev_begin = h->ev_begin;
+    A.chunk_id = h->chunk ? static_cast<uint32_t>(h->chunk_cell_begin/ISS_CHUNK_ALIGN) : 0u;
     A.dsp = h->d_dsp;
     A.ndsp = h->ndsp;
     A.dch = h->d_dch;

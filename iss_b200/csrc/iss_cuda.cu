@@ -56,7 +56,11 @@ void free_surface(iss_handle *h) {
     cudaFree(h->d_tilebase); h->d_tilebase = nullptr; h->tilebase_bytes = 0;
     cudaFree(h->d_total); h->d_total = nullptr; h->total_bytes = 0;
     cudaFree(h->d_cdflev); h->d_cdflev = nullptr; h->cdflev_bytes = 0;
+    cudaFree(h->d_tilesum_g); h->d_tilesum_g = nullptr; h->tilesum_g_bytes = 0;
+    cudaFree(h->d_tilebase_g); h->d_tilebase_g = nullptr; h->tilebase_g_bytes = 0;
+    cudaFree(h->d_cdflev_g); h->d_cdflev_g = nullptr; h->cdflev_g_bytes = 0;
     h->have_yields = false;
+    h->have_local_yields = false;
     h->have_batch = false;
 }
 
@@ -93,7 +97,9 @@ int prepare_surface_buffers(iss_handle *h, int64_t ncell) {
     h->ntile = (ncell + TILE - 1)/TILE;
     h->ncell_pad = h->ntile*TILE;
     h->have_yields = false;
+    h->have_local_yields = false;
     h->have_batch = false;
+    h->chunk = false;           // a new surface is a whole surface until declared a chunk
     ISS_ENSURE(h, h->d_surf, h->surf_bytes, sizeof(float)*ISS_NFIELD*h->ncell_pad);
     ISS_ENSURE(h, h->d_cells, h->cells_bytes, sizeof(float)*CELL_STRIDE*ncell);
     return ISS_OK;
@@ -159,6 +165,7 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_tasks); cudaFree(h->d_sampler_args); cudaFree(h->d_hints);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
     cudaFree(h->d_qa); cudaFree(h->d_trace);
+    cudaFree(h->d_own); cudaFree(h->d_wlist);
     if (h->h_mail) cudaFreeHost(h->h_mail);
     if (h->h_evoff) cudaFreeHost(h->h_evoff);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -393,6 +400,7 @@ int iss_cuda_set_options(iss_handle *h, const iss_options *opt) {
     h->lambda_on_device = false;
     if (changed) {
         h->have_yields = false;
+        h->have_local_yields = false;
         // K/E tables depend on include_deltaf_diffusion: rebuild lazily
     }
     return ISS_OK;
@@ -411,6 +419,80 @@ int iss_cuda_compute_yields(iss_handle *h, double *dN_species_host, double *yiel
                                           h->nspecies, cudaMemcpyDeviceToHost, h->stream));
         ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
+    return ISS_OK;
+}
+
+int iss_cuda_set_surface_chunk(iss_handle *h, int64_t cell_begin, int64_t ncell_global) {
+    if (!h) return ISS_ERR_ARG;
+    if (h->ncell <= 0 || !h->d_surf) ISS_FAIL(h, ISS_ERR_STATE, "upload the cells of the chunk first");
+    h->have_yields = false;
+    h->have_local_yields = false;
+    h->have_batch = false;
+    if (ncell_global <= 0) {
+        h->chunk = false;
+        return ISS_OK;
+    }
+    if (cell_begin < 0 || cell_begin % ISS_CHUNK_ALIGN != 0)
+        ISS_FAIL(h, ISS_ERR_ARG, "cell_begin must be a multiple of ISS_CHUNK_ALIGN (4096)");
+    const int64_t cell_end = cell_begin + h->ncell;
+    if (cell_end > ncell_global || (cell_end < ncell_global && cell_end % ISS_CHUNK_ALIGN != 0))
+        ISS_FAIL(h, ISS_ERR_ARG, "a chunk must end at a multiple of ISS_CHUNK_ALIGN or at the end of the surface");
+    if (ncell_global >= (int64_t(1) << 31)) ISS_FAIL(h, ISS_ERR_ARG, "ncell must be < 2^31");
+    if (ncell_global <= ISS_CHUNK_ALIGN)
+        ISS_FAIL(h, ISS_ERR_ARG, "surface-chunk mode needs a surface of more than 4096 cells");
+    h->chunk = true;
+    h->chunk_cell_begin = cell_begin;
+    h->chunk_tile_begin = cell_begin/TILE;
+    h->g_ncell = ncell_global;
+    h->g_ntile = (ncell_global + TILE - 1)/TILE;
+    return ISS_OK;
+}
+
+int iss_cuda_chunk_yields_local(iss_handle *h, void **tilesum_dev, int64_t *ntile_local) {
+    if (!h) return ISS_ERR_ARG;
+    if (!h->chunk) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_set_surface_chunk must run first");
+    cudaSetDevice(h->device);
+    int rc = run_yields_local(h);
+    if (rc) return rc;
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));   // the caller's collective may use another stream
+    if (tilesum_dev) *tilesum_dev = h->d_tilesum;
+    if (ntile_local) *ntile_local = h->ntile;
+    return ISS_OK;
+}
+
+int iss_cuda_chunk_yields_finish(iss_handle *h, const double *const *rank_tilesums,
+                                 const int64_t *rank_ntile, int32_t nranks, int on_device,
+                                 double *dN_species_host) {
+    if (!h || !rank_tilesums || !rank_ntile || nranks <= 0) return ISS_ERR_ARG;
+    if (!h->chunk) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_set_surface_chunk must run first");
+    if (!h->have_local_yields) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_chunk_yields_local must run first");
+    cudaSetDevice(h->device);
+    int64_t sum = 0;
+    bool mine = false;
+    for (int r = 0; r < nranks; r++) {
+        if (rank_ntile[r] < 0 || !rank_tilesums[r]) return ISS_ERR_ARG;
+        if (sum == h->chunk_tile_begin && rank_ntile[r] == h->ntile) mine = true;
+        sum += rank_ntile[r];
+    }
+    if (sum != h->g_ntile || !mine)
+        ISS_FAIL(h, ISS_ERR_ARG, "the ranks' tile counts do not add up to the surface declared by "
+                                 "iss_cuda_set_surface_chunk, or this handle's chunk is not among them");
+    const int64_t ns = h->nspecies;
+    ISS_ENSURE(h, h->d_tilesum_g, h->tilesum_g_bytes, sizeof(double)*ns*h->g_ntile);
+    int64_t t0 = 0;
+    for (int r = 0; r < nranks; r++) {
+        // [ns][rank_ntile[r]] -> columns [t0, t0 + rank_ntile[r]) of [ns][g_ntile]
+        if (rank_ntile[r] > 0)
+            ISS_CUDA_TRY(h, cudaMemcpy2DAsync(h->d_tilesum_g + t0, sizeof(double)*h->g_ntile,
+                                              rank_tilesums[r], sizeof(double)*rank_ntile[r],
+                                              sizeof(double)*rank_ntile[r], ns,
+                                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                              h->stream));
+        t0 += rank_ntile[r];
+    }
+    int rc = run_yields_finish(h);
+    if (rc) return rc;
+    if (dN_species_host) memcpy(dN_species_host, h->h_total.data(), sizeof(double)*h->nspecies);
     return ISS_OK;
 }
 
@@ -440,6 +522,13 @@ int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_e
         out->n_hadrons = h->n_hadrons;
         out->n_tries = static_cast<int64_t>(cnt[1]);
         out->n_cell_redraws = static_cast<int64_t>(cnt[2]);
+    }
+    if (cnt[7] != 0) {
+        char buf[240];
+        snprintf(buf, sizeof(buf),
+                 "surface-chunk mode: %llu hadrons needed a cell re-draw (4999 rejected tries, "
+                 "FSSW.cpp:1017-1018) that left this rank's chunk; their records are null (pid 0)", cnt[7]);
+        ISS_FAIL(h, ISS_ERR_RANGE, buf);
     }
     if (cnt[6] != 0) {
         char buf[200];
@@ -498,6 +587,9 @@ int iss_cuda_get_trace(iss_handle *h, int32_t *cell_host, int32_t *tries_host) {
     ISS_CUDA_TRY(h, cudaMemcpyAsync(tries_host, h->d_trace + h->trace_cap, nb,
                                     cudaMemcpyDeviceToHost, h->stream));
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->chunk)       // cells are reported with their index in the whole surface
+        for (int64_t i = 0; i < h->n_primaries; i++)
+            cell_host[i] += static_cast<int32_t>(h->chunk_cell_begin);
     return ISS_OK;
 }
 

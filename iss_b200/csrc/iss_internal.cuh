@@ -126,6 +126,21 @@ struct iss_handle {
     int64_t lev_n[8] = {0}, lev_off[8] = {0}, lev_stride = 0;
     size_t yields_bytes = 0, cdf_bytes = 0, tilesum_bytes = 0, tilebase_bytes = 0, total_bytes = 0;
     bool have_yields = false;
+    bool have_local_yields = false;     // yields + tile sums of the local cells (part 1 of run_yields)
+    // surface-chunk sharding (iss_cuda_set_surface_chunk): this handle holds cells
+    // [chunk_cell_begin, chunk_cell_begin + ncell) of a surface of g_ncell cells.  Tile sums,
+    // tile bases and search levels >= 3 exist for the WHOLE surface (small), everything per cell
+    // only for the local cells.
+    bool chunk = false;
+    int64_t chunk_cell_begin = 0, chunk_tile_begin = 0, g_ncell = 0, g_ntile = 0;
+    double *d_tilesum_g = nullptr;      // [ns][g_ntile]
+    double *d_tilebase_g = nullptr;     // [ns][g_ntile+1]
+    double *d_cdflev_g = nullptr;       // [ns][g_lev_stride]: levels 3..g_nlev of the global tree
+    size_t tilesum_g_bytes = 0, tilebase_g_bytes = 0, cdflev_g_bytes = 0;
+    int g_nlev = 0;
+    int64_t g_lev_n[8] = {0}, g_lev_off[8] = {0}, g_lev_stride = 0;
+    int64_t *d_own = nullptr; int64_t own_cap = 0;        // [nwork+1] ownership flags -> prefix
+    int64_t *d_wlist = nullptr; int64_t wlist_cap = 0;    // work items of the batch this rank owns
     std::vector<double> h_total;        // dN per species (3+1D sum)
     std::vector<double> h_lambda, h_pmode;
     double *d_lambda = nullptr, *d_pmode = nullptr;
@@ -252,6 +267,8 @@ int device_exclusive_scan_i64(iss_handle *h, const int64_t *d_in, int64_t *d_out
                               int64_t *h_total);
 
 int run_yields(iss_handle *h);
+int run_yields_local(iss_handle *h);
+int run_yields_finish(iss_handle *h);
 int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev);
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t total);
 int run_decay(iss_handle *h, uint64_t seed);

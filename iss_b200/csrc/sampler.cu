@@ -260,6 +260,16 @@ struct SamplerArgs {
                                     // [4],[5] decay errors, [6] hadrons given up
     int32_t *trace_cell;            // optional [n_out]
     int32_t *trace_tries;           // optional [n_out]
+    // surface-chunk mode (iss_cuda_set_surface_chunk): cells/cdf/cdflev above are those of the
+    // local cells; levels >= 3 of the search tree over the whole surface are in cdflev_g
+    int chunk;
+    int g_nlev;
+    const double *cdflev_g;         // [ns][g_lev_stride]
+    int64_t g_lev_off[8], g_lev_stride;
+    int64_t blk_begin, blk_end;     // 4096-cell blocks of the whole surface this rank owns
+    int64_t cell_begin, g_ncell;
+    const int64_t *own_pos;         // [nwork_global + 1] exclusive prefix of the ownership flags
+    const int64_t *wlist;           // [nwork] global work-item index of the rank's k-th hadron
 };
 
 constexpr int SETUP_THREADS = 256;
@@ -399,6 +409,21 @@ __device__ __forceinline__ int64_t pick_cell(const SamplerArgs &A, int s, double
     const double v = (total - 1e-15)*u;
     const double *__restrict__ lev = A.cdflev + static_cast<int64_t>(s)*A.lev_stride;
     int64_t q = 0;
+    if (A.chunk) {
+        // the same descent through the same numbers as on one GPU: levels >= 3 over the whole
+        // surface pick the 4096-cell block; a foreign block ends the search (-1), an owned one is
+        // continued in the local levels 2, 1 and the local prefix
+        const double *__restrict__ levg = A.cdflev_g + static_cast<int64_t>(s)*A.g_lev_stride;
+        for (int k = A.g_nlev; k >= 3; k--) q = 16*q + count_below_16(levg + A.g_lev_off[k] + 16*q, v);
+        if (q < A.blk_begin || q >= A.blk_end) return -1;
+        q -= A.blk_begin;
+        q = 16*q + count_below_16(lev + A.lev_off[2] + 16*q, v);
+        q = 16*q + count_below_16(lev + A.lev_off[1] + 16*q, v);
+        const double *__restrict__ Pl = A.cdf + static_cast<int64_t>(s)*A.ncell_pad;
+        int64_t cl = 16*q + count_below_16(Pl + 16*q, v);
+        if (cl + A.cell_begin >= A.g_ncell) cl = A.g_ncell - 1 - A.cell_begin;
+        return cl;
+    }
     for (int k = A.nlev; k >= 1; k--) q = 16*q + count_below_16(lev + A.lev_off[k] + 16*q, v);
     const double *__restrict__ P = A.cdf + static_cast<int64_t>(s)*A.ncell_pad;
     int64_t cell = 16*q + count_below_16(P + 16*q, v);
@@ -441,6 +466,84 @@ __global__ void work_hint_kernel(const int64_t *__restrict__ off_work, int ns, i
     hints[b] = make_int2(slo, static_cast<int>(elo));
 }
 
+// (species, event, draw) of work item w: start from the hint stored for the first item of its group
+// of SETUP_THREADS consecutive items and move forward (work items are species-major, event-minor,
+// so the answer is at or after the hint).  sp_off[s] = off_work[s*nev] (shared memory).
+__device__ __forceinline__ void work_identity(const SamplerArgs &A, const int64_t *sp_off, int64_t w,
+                                              int &s_out, int64_t &ev_out, int64_t &k_out) {
+    const int2 hint = __ldg(&A.hints[w/SETUP_THREADS]);
+    int s = hint.x;
+    while (sp_off[s + 1] <= w) s++;
+    const int64_t *__restrict__ ow = A.off_work + static_cast<int64_t>(s)*A.nev;
+    int64_t elo = (s == hint.x) ? hint.y : 0, step = 1;
+    while (elo + step < A.nev && __ldg(&ow[elo + step]) <= w) {
+        elo += step;
+        step <<= 1;
+    }
+    int64_t ehi = min(elo + step, A.nev);
+    while (ehi - elo > 1) {
+        const int64_t mid = (elo + ehi) >> 1;
+        if (__ldg(&ow[mid]) <= w) elo = mid; else ehi = mid;
+    }
+    s_out = s;
+    ev_out = elo;
+    k_out = w - __ldg(&ow[elo]);
+}
+
+// Surface-chunk mode, step 1: one thread per hadron of the WHOLE batch (all ranks run this over
+// the same work items): own[w] = 1 if the hadron's cell lies in this rank's cell range.  Only the
+// global levels of the search tree are read (a few KB per species, cache resident).
+__global__ void __launch_bounds__(SETUP_THREADS)
+owner_kernel(const SamplerArgs A, int64_t nwork_global, int64_t *__restrict__ own) {
+    extern __shared__ unsigned char smem_raw[];
+    int64_t *sp_off = reinterpret_cast<int64_t *>(smem_raw);
+    for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
+        sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
+    __syncthreads();
+    const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
+    for (int64_t w = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x; w < nwork_global;
+         w += static_cast<int64_t>(gridDim.x)*blockDim.x) {
+        int s;
+        int64_t ev, k;
+        work_identity(A, sp_off, w, s, ev, k);
+        uint32_t w0, w1, w2, w3;
+        philox_block(0u, static_cast<uint32_t>(k), static_cast<uint32_t>(A.ev_begin + ev),
+                     sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
+        const double v = (__ldg(&A.total[s]) - 1e-15)*u53(w0, w1);
+        const double *__restrict__ levg = A.cdflev_g + static_cast<int64_t>(s)*A.g_lev_stride;
+        int64_t q = 0;
+        for (int l = A.g_nlev; l >= 3; l--) q = 16*q + count_below_16(levg + A.g_lev_off[l] + 16*q, v);
+        own[w] = (q >= A.blk_begin && q < A.blk_end) ? 1 : 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) own[nwork_global] = 0;
+}
+
+// step 2 (after the prefix sum of the flags): hadrons this rank writes per (event, species) and
+// the list of the work items it owns, in work-item order
+__global__ void chunk_count_kernel(const int64_t *__restrict__ own_pos, const int64_t *__restrict__ off_work,
+                                   const DeviceSpecies *__restrict__ species, int ns, int64_t nev,
+                                   int lcc, int64_t *__restrict__ out_count) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (i > nev*ns) return;
+    if (i == nev*ns) {
+        out_count[i] = 0;
+        return;
+    }
+    const int64_t ev = i/ns;
+    const int s = static_cast<int>(i - ev*ns);
+    const int64_t j = static_cast<int64_t>(s)*nev + ev;
+    const int64_t n = own_pos[off_work[j + 1]] - own_pos[off_work[j]];
+    out_count[i] = (lcc == 1 && species[s].charge > 0) ? 2*n : n;
+}
+
+__global__ void chunk_compact_kernel(const int64_t *__restrict__ own_pos, int64_t nwork_global,
+                                     int64_t *__restrict__ wlist) {
+    const int64_t w = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (w >= nwork_global) return;
+    const int64_t p = own_pos[w];
+    if (own_pos[w + 1] != p) wlist[p] = w;
+}
+
 // K5a: one thread per hadron of the batch: identity (species, event, draw) from the species-major
 // work offsets, output slot, cell choice (first block of the hadron's stream) and the two series
 // values of the |p| sampler.  Massively parallel, so the dependent loads of the two binary
@@ -456,37 +559,25 @@ setup_kernel(const SamplerArgs A) {
     __syncthreads();
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
     unsigned long long my_range = 0;
-    for (int64_t w = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x; w < A.nwork;
-         w += static_cast<int64_t>(gridDim.x)*blockDim.x) {
-        // (species, event) of work item w: start from the hint stored for the first item of this
-        // group of SETUP_THREADS consecutive items and move forward (work items are species-major,
-        // event-minor, so the answer is at or after the hint)
-        const int2 hint = __ldg(&A.hints[w/SETUP_THREADS]);
-        int s = hint.x;
-        while (sp_off[s + 1] <= w) s++;
-        const int64_t *__restrict__ ow = A.off_work + static_cast<int64_t>(s)*A.nev;
-        int64_t elo = (s == hint.x) ? hint.y : 0, step = 1;
-        while (elo + step < A.nev && __ldg(&ow[elo + step]) <= w) {
-            elo += step;
-            step <<= 1;
-        }
-        int64_t ehi = min(elo + step, A.nev);
-        while (ehi - elo > 1) {
-            const int64_t mid = (elo + ehi) >> 1;
-            if (__ldg(&ow[mid]) <= w) elo = mid; else ehi = mid;
-        }
-        const int64_t ev = elo;
-        const int64_t k = w - __ldg(&ow[ev]);
+    for (int64_t j = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x; j < A.nwork;
+         j += static_cast<int64_t>(gridDim.x)*blockDim.x) {
+        // surface-chunk mode: the rank's j-th hadron is work item wlist[j] of the whole batch
+        const int64_t w = A.chunk ? __ldg(&A.wlist[j]) : j;
+        int s;
+        int64_t ev, k;
+        work_identity(A, sp_off, w, s, ev, k);
         const DeviceSpecies p = sp[s];
         const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
+        // position among the hadrons of (event, species) this rank writes
+        const int64_t k_out = A.chunk ? (__ldg(&A.own_pos[w]) - __ldg(&A.own_pos[w - k])) : k;
         Task t;
-        t.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k*mult;
+        t.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k_out*mult;
         t.s = s;
         t.event = static_cast<uint32_t>(A.ev_begin + ev);
         t.draw = static_cast<uint32_t>(k);
         uint32_t w0, w1, w2, w3;
         philox_block(0u, t.draw, t.event, sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
-        const int64_t cell = pick_cell(A, s, u53(w0, w1));
+        const int64_t cell = pick_cell(A, s, u53(w0, w1));    // chunk mode: owned, hence >= 0
         t.cell = static_cast<int32_t>(cell);
         const float4 *cr = reinterpret_cast<const float4 *>(A.cells + cell*CELL_STRIDE);
         const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
@@ -498,7 +589,7 @@ setup_kernel(const SamplerArgs A) {
         t.tab_idx = ok ? (M.tab | (M.idx_min << 3)) : -1;
         t.pad = 0;
         if (!ok) my_range++;
-        A.tasks[w] = t;
+        A.tasks[j] = t;
     }
     if (my_range) atomicAdd(&A.counters[3], my_range);
 }
@@ -530,7 +621,16 @@ __device__ __noinline__ bool lane_new_setup(const SamplerArgs *Ag, LaneState &L,
         uint32_t w0, w1, w2, w3;
         philox_block(L.rng.block++, L.rng.draw, L.rng.event, sample_stream_word3(L.s), key0, key1,
                      w0, w1, w2, w3);
-        L.cell = static_cast<int>(pick_cell(A, L.s, u53(w0, w1)));
+        const int64_t c = pick_cell(A, L.s, u53(w0, w1));
+        if (c < 0) {
+            // surface-chunk mode: the new cell belongs to another rank (include/iss_cuda.h)
+            atomicAdd(&A.counters[7], 1ull);
+            float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
+#pragma unroll
+            for (int q = 0; q < 5; q++) dst[q] = make_float2(0.f, 0.f);
+            return false;
+        }
+        L.cell = static_cast<int>(c);
     }
     const float4 *cr = reinterpret_cast<const float4 *>(A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
     const float4 da = __ldg(cr + 1);
@@ -1048,17 +1148,122 @@ int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev) {
     return ISS_OK;
 }
 
+// Surface-chunk mode: which hadrons of the batch are this rank's.  d_off_work holds the scanned
+// work offsets of the WHOLE batch (identical on every rank); on return d_own holds the exclusive
+// prefix of the ownership flags, d_wlist the owned work items, d_off_out the UNSCANNED per
+// (event, species) output counts of this rank and *n_owned their number.
+static int chunk_select_work(iss_handle *h, const SamplerArgs &A, int64_t nev, int64_t total_work,
+                             int64_t nhint, int nsm, int64_t *n_owned) {
+    const int ns = h->nspecies;
+    int rc = ensure_capacity(h, &h->d_own, &h->own_cap, total_work + 1);
+    if (rc) return rc;
+    work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
+        h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
+    int64_t grid = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
+    if (grid > static_cast<int64_t>(nsm)*32) grid = static_cast<int64_t>(nsm)*32;
+    owner_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, sizeof(int64_t)*(ns + 1), h->stream>>>(
+        A, total_work, h->d_own); ISS_LAUNCHED(h);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    rc = device_exclusive_scan_i64(h, h->d_own, h->d_own, total_work, n_owned);
+    if (rc) return rc;
+    const int64_t n = nev*ns;
+    chunk_count_kernel<<<static_cast<unsigned>((n + 1 + 255)/256), 256, 0, h->stream>>>(
+        h->d_own, h->d_off_work, h->d_species, ns, nev, h->opt.local_charge_conservation,
+        h->d_off_out); ISS_LAUNCHED(h);
+    rc = ensure_capacity(h, &h->d_wlist, &h->wlist_cap, *n_owned + 1);
+    if (rc) return rc;
+    chunk_compact_kernel<<<static_cast<unsigned>((total_work + 255)/256), 256, 0, h->stream>>>(
+        h->d_own, total_work, h->d_wlist); ISS_LAUNCHED(h);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    return ISS_OK;
+}
+
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     const int ns = h->nspecies;
     const int64_t n = nev*ns;
     int rc = ensure_momentum_tables(h);
     if (rc) return rc;
-    int64_t total_out = 0, total_work = 0;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+
+    const iss_options &o = h->opt;
+    SamplerArgs A;
+    A.cells = h->d_cells;
+    A.cellcoef = h->d_cellcoef;
+    A.ncell = h->ncell;
+    A.ncell_pad = h->ncell_pad;
+    A.cdf = h->d_cdf;
+    A.cdflev = h->d_cdflev;
+    A.nlev = h->nlev;
+    for (int k = 0; k < 8; k++) A.lev_off[k] = h->lev_off[k];
+    A.lev_stride = h->lev_stride;
+    A.total = h->d_total;
+    A.species = h->d_species;
+    A.ns = ns;
+    A.nev = nev;
+    A.ev_begin = h->ev_begin;
+    A.off_work = h->d_off_work;
+    A.off_out = h->d_off_out;
+    for (int r = 0; r < 6; r++) A.mt[r] = h->momtab[r];
+    A.mode.include_shear = o.include_deltaf_shear;
+    A.mode.include_bulk = o.include_deltaf_bulk;
+    A.mode.include_diff = o.include_deltaf_diffusion;
+    A.mode.kind = o.bulk_deltaf_kind;
+    A.mode.neos = (o.bulk_deltaf_kind == 21) ? 1 : (o.bulk_deltaf_kind == 20 ? 0 : -1);
+    A.hydro_mode = o.hydro_mode;
+    A.lcc = o.local_charge_conservation;
+    A.y_LB = o.y_LB;
+    A.y_RB = o.y_RB;
+    A.seed = seed;
+    A.trace_cell = nullptr;
+    A.trace_tries = nullptr;
+    A.chunk = h->chunk ? 1 : 0;
+    A.g_nlev = h->g_nlev;
+    A.cdflev_g = h->d_cdflev_g;
+    for (int k = 0; k < 8; k++) A.g_lev_off[k] = h->g_lev_off[k];
+    A.g_lev_stride = h->g_lev_stride;
+    A.cell_begin = h->chunk_cell_begin;
+    A.g_ncell = h->g_ncell;
+    A.blk_begin = h->chunk_cell_begin/ISS_CHUNK_ALIGN;
+    // the last chunk also owns the partly filled block at the end of the surface
+    A.blk_end = (h->chunk_cell_begin + h->ncell >= h->g_ncell)
+                    ? (int64_t(1) << 62) : (h->chunk_cell_begin + h->ncell)/ISS_CHUNK_ALIGN;
+    A.own_pos = nullptr;
+    A.wlist = nullptr;
+    A.hints = nullptr;
+    A.tasks = nullptr;
+    A.out = nullptr;
+    A.counters = nullptr;
+    A.nwork = 0;
+
+    int64_t total_out = 0, total_work = 0, nhint = 0;
     {
         ScopedTimer t(h, ISS_T_MULT);
-        rc = device_exclusive_scan_i64(h, h->d_off_out, h->d_off_out, n, &total_out);
-        if (rc) return rc;
         rc = device_exclusive_scan_i64(h, h->d_off_work, h->d_off_work, n, &total_work);
+        if (rc) return rc;
+        nhint = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
+        {
+            const size_t need = sizeof(int2)*static_cast<size_t>(nhint > 0 ? nhint : 1);
+            if (need > h->hints_bytes || !h->d_hints) {
+                if (h->d_hints) cudaFree(h->d_hints);
+                h->d_hints = nullptr;
+                h->hints_bytes = need + need/8 + 4096;
+                ISS_CUDA_TRY(h, cudaMalloc(&h->d_hints, h->hints_bytes));
+            }
+            A.hints = static_cast<const int2 *>(h->d_hints);
+        }
+        if (h->chunk && total_work > 0) {
+            int64_t n_owned = 0;
+            rc = chunk_select_work(h, A, nev, total_work, nhint, nsm, &n_owned);
+            if (rc) return rc;
+            A.own_pos = h->d_own;
+            A.wlist = h->d_wlist;
+            A.nwork = n_owned;
+        } else {
+            A.nwork = total_work;
+        }
+        rc = device_exclusive_scan_i64(h, h->d_off_out, h->d_off_out, n, &total_out);
         if (rc) return rc;
         rc = ensure_mapped_event_offsets(h, nev + 1);
         if (rc) return rc;
@@ -1082,43 +1287,11 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     if (!h->d_counters) ISS_CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned long long)*8));
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long)*8, h->stream));
     h->n_hadrons = total_out;
-    if (total_work == 0) return ISS_OK;
+    h->n_primaries = total_out;
+    if (A.nwork == 0) return ISS_OK;
 
-    const iss_options &o = h->opt;
-    SamplerArgs A;
-    A.cells = h->d_cells;
-    A.cellcoef = h->d_cellcoef;
-    A.ncell = h->ncell;
-    A.ncell_pad = h->ncell_pad;
-    A.cdf = h->d_cdf;
-    A.cdflev = h->d_cdflev;
-    A.nlev = h->nlev;
-    for (int k = 0; k < 8; k++) A.lev_off[k] = h->lev_off[k];
-    A.lev_stride = h->lev_stride;
-    A.total = h->d_total;
-    A.species = h->d_species;
-    A.ns = ns;
-    A.nev = nev;
-    A.ev_begin = h->ev_begin;
-    A.off_work = h->d_off_work;
-    A.off_out = h->d_off_out;
-    A.nwork = total_work;
-    for (int r = 0; r < 6; r++) A.mt[r] = h->momtab[r];
-    A.mode.include_shear = o.include_deltaf_shear;
-    A.mode.include_bulk = o.include_deltaf_bulk;
-    A.mode.include_diff = o.include_deltaf_diffusion;
-    A.mode.kind = o.bulk_deltaf_kind;
-    A.mode.neos = (o.bulk_deltaf_kind == 21) ? 1 : (o.bulk_deltaf_kind == 20 ? 0 : -1);
-    A.hydro_mode = o.hydro_mode;
-    A.lcc = o.local_charge_conservation;
-    A.y_LB = o.y_LB;
-    A.y_RB = o.y_RB;
-    A.seed = seed;
     A.out = h->d_hadrons;
     A.counters = h->d_counters;
-    A.trace_cell = nullptr;
-    A.trace_tries = nullptr;
-    h->n_primaries = total_out;
     if (h->trace) {
         if (total_out > h->trace_cap || !h->d_trace) {
             if (h->d_trace) cudaFree(h->d_trace);
@@ -1132,7 +1305,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
 
     // task list of the batch
     {
-        const size_t need = sizeof(Task)*static_cast<size_t>(total_work);
+        const size_t need = sizeof(Task)*static_cast<size_t>(A.nwork);
         if (need > h->tasks_bytes || !h->d_tasks) {
             if (h->d_tasks) cudaFree(h->d_tasks);
             h->d_tasks = nullptr;
@@ -1141,30 +1314,18 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         }
         A.tasks = static_cast<Task *>(h->d_tasks);
     }
-    const int64_t nhint = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
-    {
-        const size_t need = sizeof(int2)*static_cast<size_t>(nhint);
-        if (need > h->hints_bytes || !h->d_hints) {
-            if (h->d_hints) cudaFree(h->d_hints);
-            h->d_hints = nullptr;
-            h->hints_bytes = need + need/8 + 4096;
-            ISS_CUDA_TRY(h, cudaMalloc(&h->d_hints, h->hints_bytes));
-        }
-        A.hints = static_cast<const int2 *>(h->d_hints);
-    }
     if (!h->d_sampler_args) ISS_CUDA_TRY(h, cudaMalloc(&h->d_sampler_args, sizeof(SamplerArgs)));
     ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_sampler_args, &A, sizeof(SamplerArgs), cudaMemcpyHostToDevice,
                                     h->stream));
-    int dev = 0, nsm = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     {
         ScopedTimer t(h, ISS_T_SETUP);
         const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
-        int64_t grid = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
+        int64_t grid = (A.nwork + SETUP_THREADS - 1)/SETUP_THREADS;
         if (grid > static_cast<int64_t>(nsm)*32) grid = static_cast<int64_t>(nsm)*32;
-        work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
-            h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
+        if (!h->chunk) {    // (chunk mode: the hints exist already, chunk_select_work)
+            work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
+                h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
+        }
         setup_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
@@ -1197,7 +1358,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     ISS_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     int64_t grid = nsm;         // persistent: one CTA per SM
-    const int64_t max_useful = (total_work + SAMPLER_THREADS - 1)/SAMPLER_THREADS;
+    const int64_t max_useful = (A.nwork + SAMPLER_THREADS - 1)/SAMPLER_THREADS;
     if (grid > max_useful) grid = max_useful;
     {
         ScopedTimer t(h, ISS_T_SAMPLE);

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256)
 tile_scan_kernel(const double *__restrict__ yields, double *__restrict__ cdf,
                  double *__restrict__ tilesum, const double *__restrict__ tilebase,
                  double *__restrict__ lev, int64_t lev_stride, int64_t ncell, int64_t ncell_pad,
-                 int64_t ntile) {
+                 int64_t ntile, int64_t tb_stride, int64_t tb_off) {
     __shared__ double warp_tot[8];
     const int64_t tile = blockIdx.x;
     const int s = blockIdx.y;
@@ -260,7 +260,8 @@ tile_scan_kernel(const double *__restrict__ yields, double *__restrict__ cdf,
         return;
     }
     // the same association as the tile-local scan followed by "+ tile base"
-    const double tb = __ldg(&tilebase[static_cast<int64_t>(s)*(ntile + 1) + tile]);
+    // (surface-chunk mode: tilebase is the GLOBAL table, this handle's tiles start at tb_off)
+    const double tb = __ldg(&tilebase[static_cast<int64_t>(s)*tb_stride + tb_off + tile]);
     double2 o0, o1;
     o0.x = (v[0] + offset) + tb; o0.y = (v[1] + offset) + tb;
     o1.x = (v[2] + offset) + tb; o1.y = (v[3] + offset) + tb;
@@ -312,6 +313,25 @@ __global__ void cdf_level_pad_kernel(double *__restrict__ lev, const double *__r
     const int s = blockIdx.x;
     for (int64_t j = n + threadIdx.x; j < n_padded; j += blockDim.x)
         lev[static_cast<int64_t>(s)*lev_stride + off + j] = __ldg(&total[s]);
+}
+
+// Surface-chunk mode: level 3 of the GLOBAL search tree from the gathered tile sums.  Entry j is the
+// prefix value of the last cell of the 4096-cell block j, which is the last value tile 4j+3 writes in
+// pass 2: tilesum + tilebase, the same two operands in the same order, hence the same bits as the
+// single-GPU level 3 (a copy of that prefix value via levels 1 and 2).
+__global__ void chunk_level3_kernel(const double *__restrict__ tilesum, const double *__restrict__ tilebase,
+                                    const double *__restrict__ total, int64_t g_ntile, int64_t n1,
+                                    double *__restrict__ levg, int64_t levg_stride, int64_t n3_padded) {
+    const int s = blockIdx.y;
+    const int64_t j = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (j >= n3_padded) return;
+    double v = __ldg(&total[s]);
+    if (256*j + 255 < n1) {
+        const int64_t t = 4*j + 3;
+        v = tilesum[static_cast<int64_t>(s)*g_ntile + t]
+            + tilebase[static_cast<int64_t>(s)*(g_ntile + 1) + t];
+    }
+    levg[static_cast<int64_t>(s)*levg_stride + j] = v;
 }
 
 // fills the K_n / E_n grids on the device (FSSW::initialize_special_function_arrays)
@@ -376,7 +396,29 @@ static int ensure_sf_tables(iss_handle *h) {
     return ISS_OK;
 }
 
-int run_yields(iss_handle *h) {
+// geometry of the 16-ary search levels over a prefix array of n0 entries (level 0 = the prefix
+// itself): level k holds ceil(n_{k-1}/16) entries, stored padded to a multiple of 16
+static int level_geometry(int64_t n0, int max_levels, int64_t *lev_n, int64_t *lev_off,
+                          int64_t *stride) {
+    int64_t n_prev = n0, off = 0;
+    int nlev = 0;
+    while (n_prev > 16 && nlev < max_levels) {
+        const int64_t n = (n_prev + 15)/16;
+        const int64_t n_padded = (n + 15)/16*16;
+        const int k = ++nlev;
+        lev_n[k] = n;
+        lev_off[k] = off;
+        off += n_padded;
+        n_prev = n;
+    }
+    *stride = off > 0 ? off : 16;
+    return nlev;
+}
+
+// Part 1 of the yields: per cell x species yields of the cells this handle holds and the sums of
+// their 1024-cell tiles.  In surface-chunk mode the caller gathers the tile sums of all ranks
+// before part 2.
+int run_yields_local(iss_handle *h) {
     if (h->ncell <= 0 || !h->d_surf) ISS_FAIL(h, ISS_ERR_STATE, "no surface uploaded");
     if (h->nspecies <= 0) ISS_FAIL(h, ISS_ERR_STATE, "no species uploaded");
     if (!h->have_opt) ISS_FAIL(h, ISS_ERR_STATE, "options not set");
@@ -397,6 +439,8 @@ int run_yields(iss_handle *h) {
     int rc = ensure_sf_tables(h);
     if (rc) return rc;
 
+    h->have_yields = false;
+    h->have_local_yields = false;
     const int64_t ns = h->nspecies;
     const size_t nval = static_cast<size_t>(ns)*h->ncell_pad;
     ISS_ENSURE(h, h->d_yields, h->yields_bytes, sizeof(double)*nval);
@@ -404,22 +448,11 @@ int run_yields(iss_handle *h) {
     ISS_ENSURE(h, h->d_tilesum, h->tilesum_bytes, sizeof(double)*ns*h->ntile);
     ISS_ENSURE(h, h->d_tilebase, h->tilebase_bytes, sizeof(double)*ns*(h->ntile + 1));
     ISS_ENSURE(h, h->d_total, h->total_bytes, sizeof(double)*ns);
-    {
-        // geometry of the 16-ary search levels (level 0 = the prefix itself, ncell_pad entries)
-        int64_t n_prev = h->ncell_pad, off = 0;
-        h->nlev = 0;
-        while (n_prev > 16 && h->nlev < 7) {
-            const int64_t n = (n_prev + 15)/16;
-            const int64_t n_padded = (n + 15)/16*16;
-            const int k = ++h->nlev;
-            h->lev_n[k] = n;
-            h->lev_off[k] = off;
-            off += n_padded;
-            n_prev = n;
-        }
-        h->lev_stride = off > 0 ? off : 16;
-        ISS_ENSURE(h, h->d_cdflev, h->cdflev_bytes, sizeof(double)*ns*h->lev_stride);
-    }
+    // surface-chunk mode keeps exactly levels 1 and 2 locally (a 4096-cell block = one level-2
+    // node; ncell_pad is a multiple of 1024, so both always exist); the levels above them are
+    // global (run_yields_finish)
+    h->nlev = level_geometry(h->ncell_pad, h->chunk ? 2 : 7, h->lev_n, h->lev_off, &h->lev_stride);
+    ISS_ENSURE(h, h->d_cdflev, h->cdflev_bytes, sizeof(double)*ns*h->lev_stride);
     ISS_ENSURE(h, h->d_cellcoef, h->coef_bytes, sizeof(double)*COEF_STRIDE*h->ncell);
 
     YieldArgs a;
@@ -470,12 +503,39 @@ int run_yields(iss_handle *h) {
         ScopedTimer t(h, ISS_T_SCAN);
         dim3 grid(static_cast<unsigned>(h->ntile), static_cast<unsigned>(ns));
         tile_scan_kernel<1><<<grid, 256, 0, h->stream>>>(h->d_yields, h->d_cdf, h->d_tilesum, nullptr,
-                                                         nullptr, 0, h->ncell, h->ncell_pad, h->ntile); ISS_LAUNCHED(h);
-        tile_base_kernel<<<static_cast<unsigned>(ns), 32, 0, h->stream>>>(
-            h->d_tilesum, h->d_tilebase, h->d_total, h->ntile); ISS_LAUNCHED(h);
-        tile_scan_kernel<2><<<grid, 256, 0, h->stream>>>(h->d_yields, h->d_cdf, h->d_tilesum,
-                                                         h->d_tilebase, h->d_cdflev, h->lev_stride,
-                                                         h->ncell, h->ncell_pad, h->ntile); ISS_LAUNCHED(h);
+                                                         nullptr, 0, h->ncell, h->ncell_pad, h->ntile,
+                                                         0, 0); ISS_LAUNCHED(h);
+    }
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    h->have_local_yields = true;
+    return ISS_OK;
+}
+
+// Part 2: tile bases (fixed-order prefix over ALL tiles of the surface), global inclusive prefix of
+// this handle's cells, search levels, species totals.  Surface-chunk mode: the tile sums of the
+// whole surface are in h->d_tilesum_g ([ns][g_ntile], assembled by iss_cuda_chunk_yields_finish);
+// every rank runs the same tile_base_kernel on the same numbers, so bases, totals and upper search
+// levels are bit-identical to a single-GPU run and to each other.
+int run_yields_finish(iss_handle *h) {
+    if (!h->have_local_yields) ISS_FAIL(h, ISS_ERR_STATE, "yields of the local cells not computed");
+    const int64_t ns = h->nspecies;
+    {
+        ScopedTimer t(h, ISS_T_SCAN);
+        dim3 grid(static_cast<unsigned>(h->ntile), static_cast<unsigned>(ns));
+        if (h->chunk) {
+            ISS_ENSURE(h, h->d_tilebase_g, h->tilebase_g_bytes, sizeof(double)*ns*(h->g_ntile + 1));
+            tile_base_kernel<<<static_cast<unsigned>(ns), 32, 0, h->stream>>>(
+                h->d_tilesum_g, h->d_tilebase_g, h->d_total, h->g_ntile); ISS_LAUNCHED(h);
+            tile_scan_kernel<2><<<grid, 256, 0, h->stream>>>(
+                h->d_yields, h->d_cdf, h->d_tilesum, h->d_tilebase_g, h->d_cdflev, h->lev_stride,
+                h->ncell, h->ncell_pad, h->ntile, h->g_ntile + 1, h->chunk_tile_begin); ISS_LAUNCHED(h);
+        } else {
+            tile_base_kernel<<<static_cast<unsigned>(ns), 32, 0, h->stream>>>(
+                h->d_tilesum, h->d_tilebase, h->d_total, h->ntile); ISS_LAUNCHED(h);
+            tile_scan_kernel<2><<<grid, 256, 0, h->stream>>>(
+                h->d_yields, h->d_cdf, h->d_tilesum, h->d_tilebase, h->d_cdflev, h->lev_stride,
+                h->ncell, h->ncell_pad, h->ntile, h->ntile + 1, 0); ISS_LAUNCHED(h);
+        }
         if (h->nlev >= 1) {
             const int64_t n1p = (h->lev_n[1] + 15)/16*16;
             if (n1p > h->lev_n[1]) {
@@ -490,6 +550,31 @@ int run_yields(iss_handle *h) {
                                                         h->lev_off[k - 1], h->lev_n[k - 1],
                                                         h->lev_off[k], np_); ISS_LAUNCHED(h);
         }
+        if (h->chunk) {
+            // global levels 3..g_nlev in their own array (offsets relative to level 3)
+            int64_t gn[8] = {0}, goff[8] = {0}, gstride = 0;
+            h->g_nlev = level_geometry(h->g_ntile*TILE, 7, gn, goff, &gstride);
+            if (h->g_nlev < 3)
+                ISS_FAIL(h, ISS_ERR_ARG, "surface-chunk mode needs a surface of more than 4096 cells");
+            for (int k = 3; k <= h->g_nlev; k++) {
+                h->g_lev_n[k] = gn[k];
+                h->g_lev_off[k] = goff[k] - goff[3];
+            }
+            h->g_lev_stride = gstride - goff[3];
+            ISS_ENSURE(h, h->d_cdflev_g, h->cdflev_g_bytes, sizeof(double)*ns*h->g_lev_stride);
+            const int64_t n3p = (gn[3] + 15)/16*16;
+            dim3 g3(static_cast<unsigned>((n3p + 127)/128), static_cast<unsigned>(ns));
+            chunk_level3_kernel<<<g3, 128, 0, h->stream>>>(h->d_tilesum_g, h->d_tilebase_g, h->d_total,
+                                                           h->g_ntile, gn[1], h->d_cdflev_g,
+                                                           h->g_lev_stride, n3p); ISS_LAUNCHED(h);
+            for (int k = 4; k <= h->g_nlev; k++) {
+                const int64_t np_ = (gn[k] + 15)/16*16;
+                dim3 g4(static_cast<unsigned>((np_ + 127)/128), static_cast<unsigned>(ns));
+                cdf_level_kernel<<<g4, 128, 0, h->stream>>>(h->d_cdflev_g, h->d_total, h->g_lev_stride,
+                                                            h->g_lev_off[k - 1], gn[k - 1],
+                                                            h->g_lev_off[k], np_); ISS_LAUNCHED(h);
+            }
+        }
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
     h->h_total.resize(ns);
@@ -499,6 +584,14 @@ int run_yields(iss_handle *h) {
     h->have_yields = true;
     h->lambda_on_device = false;
     return ISS_OK;
+}
+
+int run_yields(iss_handle *h) {
+    if (h->chunk)
+        ISS_FAIL(h, ISS_ERR_STATE, "surface-chunk mode: use iss_cuda_chunk_yields_local/_finish");
+    int rc = run_yields_local(h);
+    if (rc) return rc;
+    return run_yields_finish(h);
 }
 
 }  // namespace iss

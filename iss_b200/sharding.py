@@ -8,9 +8,74 @@ sums, include/iss_cuda.h) is reduced, with one all-reduce (NCCL on GPUs; gloo in
 The smooth-spectra integrator (iss_cuda_spectra) shards the other way: every rank holds the whole
 surface and integrates its own species; the [npT][nphi] tables are gathered, no reduction at all
 (the sum over cells stays on one GPU, in a chunk order that does not depend on the rank count).
+
+Surface-chunk sharding (the alternative for surfaces like C5): every rank
+holds a contiguous cell range and samples, for ALL events, the hadrons whose cell lies in it.  The
+one collective is an all-gather of the per-tile (1024 cells) yield sums, [nspecies][ntile] doubles;
+every rank then combines them in the same fixed order (include/iss_cuda.h,
+iss_cuda_chunk_yields_finish), so totals, multiplicities and chosen cells are bit-identical to a
+single-GPU run and the union of the ranks' lists is that run's list.
 """
 import torch
 import torch.distributed as dist
+
+CHUNK_ALIGN = 4096      # ISS_CHUNK_ALIGN: one node of level 2 of the cell-search tree
+TILE = 1024             # cells per tile of the fixed-order yield sums
+
+
+def split_cells(ncell, world):
+    """Contiguous cell ranges [b, e) per rank, boundaries on multiples of CHUNK_ALIGN, sizes as
+    equal as the alignment allows; trailing ranks may be empty for small surfaces."""
+    ncell, world = int(ncell), int(world)
+    nblk = (ncell + CHUNK_ALIGN - 1)//CHUNK_ALIGN
+    base, rem = divmod(nblk, world)
+    out, b = [], 0
+    for r in range(world):
+        e = b + (base + (1 if r < rem else 0))*CHUNK_ALIGN
+        out.append((min(b, ncell), min(e, ncell)))
+        b = e
+    return out
+
+
+def ntiles_of(cell_range):
+    return (cell_range[1] - cell_range[0] + TILE - 1)//TILE
+
+
+def gather_tile_sums(local, ranges, nspecies):
+    """local: float64 tensor [nspecies, ntiles_of(ranges[rank])] (device of the backend: CUDA for
+    NCCL, CPU for gloo) -> list over ranks of contiguous [nspecies, ntiles_of(ranges[r])] tensors.
+    One all_gather of equally padded blocks."""
+    world = len(ranges)
+    nt = [ntiles_of(r) for r in ranges]
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        return [local.contiguous()]
+    width = max(nt)
+    pad = torch.zeros((int(nspecies), width), dtype=torch.float64, device=local.device)
+    pad[:, :local.shape[1]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    return [parts[r][:, :nt[r]].contiguous() for r in range(world)]
+
+
+def chunk_yields(engine, cells, rank, world, device=None):
+    """Surface-chunk yields of one rank: uploads cells[b:e] of the whole surface `cells`
+    (float32 [ncell, 28]), runs the local part, all-gathers the tile sums over the process group
+    (NCCL) and finishes.  Returns (dN per species over the whole surface, (b, e))."""
+    ranges = split_cells(len(cells), world)
+    b, e = ranges[rank]
+    if e <= b:
+        raise ValueError("rank %d has no cells: use fewer ranks for a surface of %d cells" %
+                         (rank, len(cells)))
+    engine.upload_surface(cells[b:e])
+    engine.set_surface_chunk(b, len(cells))
+    ptr, nt = engine.chunk_yields_local()
+    dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+    local = device_block_as_tensor(ptr, engine.nspecies*nt, dev).view(engine.nspecies, nt)
+    blocks = gather_tile_sums(local, ranges, engine.nspecies)
+    torch.cuda.synchronize()
+    dN = engine.chunk_yields_finish([t.data_ptr() for t in blocks], [t.shape[1] for t in blocks],
+                                    on_device=True)
+    return dN, (b, e)
 
 
 def split_events(nev_total, world):

@@ -287,6 +287,68 @@ def species_totals(y):
     return np.cumsum(np.maximum(y, 0.), axis=1)[:, -1]
 
 
+# ---- the engine's fixed-order evaluation of the same sums (engine design: the reference's
+# sequential sum cannot be parallelised; any fixed order is reproducible, and the tile structure is
+# what lets GPUs that hold different cell ranges obtain identical bits, iss_b200/csrc/yields.cu)
+ENGINE_TILE = 1024
+
+
+def _hillis_steele32(a):
+    """inclusive scan over the last axis (32 lanes) in the order of a warp shuffle-up scan"""
+    a = a.copy()
+    for d in (1, 2, 4, 8, 16):
+        a[..., d:] = a[..., d:] + a[..., :-d]
+    return a
+
+
+def engine_tile_scan(y):
+    """y: [ns, ncell] -> (local [ns, ntile, 1024] inclusive prefix inside each tile, tilesum
+    [ns, ntile]) in the association of tile_scan_kernel: 4 cells per thread sequentially, warp
+    scan of the thread sums, warp bases added sequentially."""
+    y = np.maximum(np.asarray(y, dtype=np.float64), 0.)     # the yield kernel already clamps
+    ns, ncell = y.shape
+    ntile = (ncell + ENGINE_TILE - 1)//ENGINE_TILE
+    v = np.zeros((ns, ntile*ENGINE_TILE))
+    v[:, :ncell] = y
+    v = v.reshape(ns, ntile, 8, 32, 4)                        # tile, warp, lane, item
+    v = v.copy()
+    for i in (1, 2, 3):
+        v[..., i] = v[..., i] + v[..., i - 1]
+    incl = _hillis_steele32(v[..., 3])                        # [ns, ntile, 8, 32]
+    warp_tot = incl[..., 31]                                  # [ns, ntile, 8]
+    wbase = np.zeros_like(warp_tot)
+    for w in range(1, 8):
+        wbase[..., w] = wbase[..., w - 1] + warp_tot[..., w - 1]
+    offset = (incl - v[..., 3]) + wbase[..., None]
+    local = v + offset[..., None]
+    tilesum = local[:, :, 7, 31, 3]
+    return local.reshape(ns, ntile, ENGINE_TILE), tilesum.copy()
+
+
+def engine_tile_bases(tilesum):
+    """[ns, ntile] -> (tilebase [ns, ntile], total [ns]) in the order of tile_base_kernel: groups of
+    32 tiles, shuffle scan inside a group, sequential carry between groups."""
+    ns, ntile = tilesum.shape
+    base = np.zeros((ns, ntile))
+    carry = np.zeros(ns)
+    for t0 in range(0, ntile, 32):
+        v = np.zeros((ns, 32))
+        n = min(32, ntile - t0)
+        v[:, :n] = tilesum[:, t0:t0 + n]
+        incl = _hillis_steele32(v)
+        base[:, t0:t0 + n] = (carry[:, None] + (incl - v))[:, :n]
+        carry = carry + incl[:, 31]
+    return base, carry
+
+
+def engine_prefix(y):
+    """global inclusive prefix [ns, ncell] and totals [ns] exactly as the device computes them"""
+    local, tilesum = engine_tile_scan(y)
+    base, total = engine_tile_bases(tilesum)
+    P = (local + base[:, :, None]).reshape(y.shape[0], -1)[:, :y.shape[1]]
+    return P, total
+
+
 def poisson_pmode(lam):
     """pmf of Poisson(lam) at its mode floor(lam) (engine design, see iss_oracle.c)."""
     lam = np.asarray(lam, dtype=np.float64)

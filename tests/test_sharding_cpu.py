@@ -110,3 +110,75 @@ def test_species_sharded_spectra_equal_single_process(tmp_path):
         outs.append(np.load(out))
     assert outs[0].shape == (5, 4, 6)
     assert np.array_equal(outs[0], outs[1])       # gathered tables are bit-identical
+
+
+# ---- surface-chunk sharding: all-gather of tile sums, then the same fixed-order combination
+def _chunk_case():
+    rng = np.random.default_rng(11)
+    ns, ncell = 4, 3*4096 + 1500
+    y = rng.random((ns, ncell))*np.where(rng.random((ns, ncell)) < 0.2, 0.0, 1.0)
+    y[1] *= 1e-7
+    return y
+
+
+def _chunk_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    y = _chunk_case()
+    ranges = sharding.split_cells(y.shape[1], world)
+    b, e = ranges[rank]
+    local, tilesum = orc.engine_tile_scan(y[:, b:e])            # what chunk_yields_local computes
+    blocks = sharding.gather_tile_sums(torch.from_numpy(tilesum), ranges, y.shape[0])
+    full = np.concatenate([t.numpy() for t in blocks], axis=1)  # what chunk_yields_finish assembles
+    base, total = orc.engine_tile_bases(full)
+    t0 = b//sharding.TILE
+    P = (local + base[:, t0:t0 + local.shape[1], None]).reshape(y.shape[0], -1)[:, :e - b]
+    np.savez(out % rank, P=P, total=total, b=b, e=e)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_split_cells_aligned_cover():
+    for ncell, world in [(20000, 2), (966924, 8), (10**7, 8), (5000, 2), (4097, 3), (4096, 1)]:
+        r = sharding.split_cells(ncell, world)
+        assert r[0][0] == 0 and r[-1][1] == ncell
+        assert all(r[i][1] == r[i + 1][0] for i in range(world - 1))
+        assert all(b % sharding.CHUNK_ALIGN == 0 for b, e in r if e > b)
+        assert all(e % sharding.CHUNK_ALIGN == 0 or e == ncell for b, e in r)
+        blocks = [-(-(e - b)//sharding.CHUNK_ALIGN) for b, e in r]
+        assert max(blocks) - min(blocks) <= 1
+        assert sum(sharding.ntiles_of(x) for x in r) == -(-ncell//sharding.TILE)
+
+
+def test_chunked_prefix_equals_single_process(tmp_path):
+    """Two ranks holding half the cells each obtain, after one all-gather of tile sums, the bits of
+    the single-process prefix and totals; every draw v is then claimed by exactly one rank and
+    resolves to the same cell."""
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path/"chunk_r%d.npz")
+    mp.spawn(_chunk_worker, args=(2, port, out), nprocs=2, join=True)
+    y = _chunk_case()
+    P, total = orc.engine_prefix(y)
+    # the engine's order differs from the reference's sequential sum only by rounding
+    assert np.allclose(total, orc.species_totals(y), rtol=1e-13)
+    parts = [np.load(out % r) for r in range(2)]
+    for p in parts:
+        assert np.array_equal(p["total"], total)
+        assert np.array_equal(p["P"], P[:, int(p["b"]):int(p["e"])])
+    rng = np.random.default_rng(3)
+    for s_ in range(y.shape[0]):
+        v = (total[s_] - 1e-15)*rng.random(2000)
+        cell = np.minimum((P[s_][None, :] < v[:, None]).sum(axis=1), y.shape[1] - 1)
+        claimed = np.zeros(len(v), dtype=int)
+        for p in parts:
+            b, e = int(p["b"]), int(p["e"])
+            lo = P[s_, b - 1] if b > 0 else -np.inf
+            mine = (v > lo) & ((v <= p["P"][s_, -1]) | (e == y.shape[1]))
+            local = (p["P"][s_][None, :] < v[mine, None]).sum(axis=1)
+            assert np.array_equal(np.minimum(local + b, y.shape[1] - 1), cell[mine])
+            claimed += mine
+        assert np.all(claimed == 1)
