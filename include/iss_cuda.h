@@ -179,6 +179,13 @@ ISS_API int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NF
  * std::vector<FO_surf_LRF> minus its PCE vector): one host->device copy, transposed on the device.
  * `cells` may be pinned memory; it can be reused when the call returns.                  */
 ISS_API int iss_cuda_upload_surface_aos(iss_handle *h, const float *cells, int64_t ncell);
+/* the same in parts, so that a host that has to assemble the records (e.g. out of a
+ * std::vector<FO_surf_LRF>) overlaps its packing with the copies: parts in ascending order,
+ * the first with first = 0, every call with the same ncell_total; cells_part points at record
+ * `first` and must stay valid (pinned) until the call of the last part returns, which also
+ * synchronises.                                                                          */
+ISS_API int iss_cuda_upload_surface_aos_part(iss_handle *h, const float *cells_part, int64_t first,
+                                             int64_t n, int64_t ncell_total);
 ISS_API int iss_cuda_upload_species(iss_handle *h, const iss_species *species, int32_t nspecies);
 ISS_API int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data,
                           int64_t n0, int64_t n1, const double *grid4);

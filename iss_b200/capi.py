@@ -99,7 +99,7 @@ CUDA_SYMBOLS = [
     "iss_cuda_fetch_all_async", "iss_cuda_fetch_wait", "iss_cuda_sample_momentum",
     "iss_cuda_upload_surface_lab", "iss_cuda_spectra", "iss_cuda_spectra_stats",
     "iss_cuda_ingest_music_binary", "iss_cuda_set_surface_chunk", "iss_cuda_chunk_yields_local",
-    "iss_cuda_chunk_yields_finish",
+    "iss_cuda_chunk_yields_finish", "iss_cuda_upload_surface_aos_part",
 ]
 HOST_SYMBOLS = [
     "iss_host_create", "iss_host_destroy", "iss_host_set_param", "iss_host_get_param",
@@ -164,6 +164,7 @@ def cuda_lib():
         "iss_cuda_host_free": (C.c_int, [vp, vp]),
         "iss_cuda_fp64_peak": (C.c_int, [vp, dp]),
         "iss_cuda_upload_surface_aos": (C.c_int, [vp, vp, i64]),
+        "iss_cuda_upload_surface_aos_part": (C.c_int, [vp, vp, i64, i64, i64]),
         "iss_cuda_fetch_all_async": (C.c_int, [vp, vp, i64, i64p]),
         "iss_cuda_fetch_wait": (C.c_int, [vp]),
         "iss_cuda_sample_momentum": (C.c_int, [vp, C.c_double, C.c_double, C.c_double, i32, i64, u64, vp]),

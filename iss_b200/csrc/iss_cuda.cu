@@ -66,11 +66,11 @@ void free_surface(iss_handle *h) {
 
 // [ncell][28] staging -> SoA [28][ncell_pad] and the sampler's AoS [ncell][32]; one thread per
 // cell reads its 112-byte record with 16-byte loads
-__global__ void unpack_cells_kernel(const float *__restrict__ stage, int64_t ncell,
+__global__ void unpack_cells_kernel(const float *__restrict__ stage, int64_t first, int64_t end,
                                     int64_t ncell_pad, float *__restrict__ soa,
                                     float *__restrict__ cells) {
-    const int64_t c = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
-    if (c >= ncell) return;
+    const int64_t c = first + static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (c >= end) return;
     float rec[CELL_STRIDE];
     const float4 *src = reinterpret_cast<const float4 *>(stage + c*ISS_NFIELD);
 #pragma unroll
@@ -227,10 +227,36 @@ int iss_cuda_upload_surface_aos(iss_handle *h, const float *cells, int64_t ncell
             ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_surf + static_cast<int64_t>(k)*h->ncell_pad + ncell,
                                             0, sizeof(float)*(h->ncell_pad - ncell), h->stream));
     unpack_cells_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(
-        h->d_stage, ncell, h->ncell_pad, h->d_surf, h->d_cells); ISS_LAUNCHED(h);
+        h->d_stage, 0, ncell, h->ncell_pad, h->d_surf, h->d_cells); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
     // the caller's buffer may be reused as soon as this returns
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return ISS_OK;
+}
+
+int iss_cuda_upload_surface_aos_part(iss_handle *h, const float *cells_part, int64_t first,
+                                     int64_t n, int64_t ncell_total) {
+    if (!h || !cells_part || first < 0 || n <= 0 || first + n > ncell_total) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    if (first == 0) {
+        int rc = prepare_surface_buffers(h, ncell_total);
+        if (rc) return rc;
+        ISS_ENSURE(h, h->d_stage, h->stage_bytes, sizeof(float)*ISS_NFIELD*ncell_total);
+        if (h->ncell_pad > ncell_total)   // padding cells read as zeros
+            for (int k = 0; k < ISS_NFIELD; k++)
+                ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_surf + static_cast<int64_t>(k)*h->ncell_pad + ncell_total,
+                                                0, sizeof(float)*(h->ncell_pad - ncell_total), h->stream));
+    } else if (h->ncell != ncell_total || !h->d_stage) {
+        ISS_FAIL(h, ISS_ERR_STATE, "surface parts must start with first = 0 and keep ncell_total");
+    }
+    // copy and transposition of this part queue behind each other on the stream; the host packs
+    // the next part meanwhile
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_stage + first*ISS_NFIELD, cells_part, sizeof(float)*ISS_NFIELD*n,
+                                    cudaMemcpyHostToDevice, h->stream));
+    unpack_cells_kernel<<<static_cast<unsigned>((n + 127)/128), 128, 0, h->stream>>>(
+        h->d_stage, first, first + n, h->ncell_pad, h->d_surf, h->d_cells); ISS_LAUNCHED(h);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    if (first + n == ncell_total) ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return ISS_OK;
 }
 

@@ -345,16 +345,22 @@ void GpuFSSW::upload_surface_() {
         }
     };
     const int nthread = static_cast<int>(std::max<int64_t>(
-        1, std::min<int64_t>(8, std::min<int64_t>(std::thread::hardware_concurrency(), n/65536))));
-    if (nthread <= 1) {
-        pack(0, n);
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < nthread; t++)
-            pool.emplace_back(pack, n*t/nthread, n*(t + 1)/nthread);
-        for (auto &t : pool) t.join();
+        1, std::min<int64_t>(16, std::min<int64_t>(std::thread::hardware_concurrency(), n/65536))));
+    // in parts: while one part travels to the device (and is transposed there) the next is packed
+    const int nparts = (n >= 262144) ? 4 : 1;
+    for (int part = 0; part < nparts; part++) {
+        const int64_t p0 = n*part/nparts, p1 = n*(part + 1)/nparts;
+        if (nthread <= 1) {
+            pack(p0, p1);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthread; t++)
+                pool.emplace_back(pack, p0 + (p1 - p0)*t/nthread, p0 + (p1 - p0)*(t + 1)/nthread);
+            for (auto &t : pool) t.join();
+        }
+        check_(iss_cuda_upload_surface_aos_part(h_, dst + p0*ISS_NFIELD, p0, p1 - p0, n),
+               "iss_cuda_upload_surface_aos_part");
     }
-    check_(iss_cuda_upload_surface_aos(h_, dst, n), "iss_cuda_upload_surface_aos");
     pool_release(h_, stage);
 }
 
