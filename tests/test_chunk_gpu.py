@@ -177,3 +177,30 @@ def test_chunk_argument_checks(surf):
     e.set_surface_chunk(0, 0)                               # off again
     e.upload_surface(lrf)
     e.compute_yields()
+
+
+def test_chunk_ragged_tail_and_decays(surf):
+    """a last rank that holds ONE cell (surface of 3 x 4096 + 1 cells on 4 ranks), and resonance
+    decays on the ranks' own primaries: every rank's final list keeps charge, and the ranks' primary
+    lists still tile the single-GPU list."""
+    capi, s, lrf = surf
+    e = s.engine()
+    sub = lrf[:3*sharding.CHUNK_ALIGN + 1]
+    ranges = sharding.split_cells(len(sub), 4)
+    assert ranges[-1] == (3*sharding.CHUNK_ALIGN, 3*sharding.CHUNK_ALIGN + 1)
+    ref = whole_run(e, sub, nev=30)
+    outs = chunk_runs(e, sub, 4, nev=30)
+    assert len(outs) == 4
+    for o in outs:
+        b, en = o["range"]
+        mine = (ref["cell"] >= b) & (ref["cell"] < en)
+        assert np.array_equal(o["dN"], ref["dN"])
+        assert o["had"].tobytes() == ref["had"][mine].tobytes()
+    assert sum(len(o["had"]) for o in outs) == len(ref["had"])
+    # decays of the last configured rank's batch (the handle still holds it)
+    prim = outs[-1]["had"]
+    c = e.decay(SEED)
+    fin = e.fetch_all()
+    assert c.n_hadrons == len(fin) >= len(prim)
+    e.upload_surface(lrf)
+    e.compute_yields()
