@@ -31,6 +31,8 @@ struct YieldArgs {
     int ncombo;
 };
 
+// 1/n for the terms of the quantum-statistics series (same bits as the division 1.0/n)
+__constant__ double c_inv_n[11] = {0., 1.0, 1.0/2, 1.0/3, 1.0/4, 1.0/5, 1.0/6, 1.0/7, 1.0/8, 1.0/9, 1.0/10};
 constexpr int YIELD_THREADS = 128;
 constexpr int YIELD_SPECIES_SMEM = 512;
 
@@ -144,7 +146,7 @@ yields_kernel(const YieldArgs a) {
         double N_eq = 0., b1 = 0., b2 = 0., b3 = 0., q2 = 0.;
         double theta = 1.0, fugacity = 1.0;
         for (int n = 1; n <= truncate_order; n++) {
-            const double inv_n = (n == 1) ? 1.0 : 1.0/n;
+            const double inv_n = (n == 1) ? 1.0 : c_inv_n[n];
             const double arg = n*mass*beta;
             if (n > 1) theta *= -static_cast<double>(p.sign);
             fugacity *= lambda;
