@@ -213,9 +213,10 @@ GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
                  const std::vector<particle_info> &particles,
                  const std::vector<FO_surf_LRF> &FOsurf_LRF, int flag_PCE,
                  ParameterReader *paraRdr, std::string path, std::string table_path,
-                 AfterburnerType afterburner_type)
+                 AfterburnerType afterburner_type, const float *packed_lrf)
     : paraRdr_(paraRdr), path_(path), table_path_(table_path),
-      afterburner_type_(afterburner_type), particles_(particles), surf_(FOsurf_LRF), seed_(seed) {
+      afterburner_type_(afterburner_type), particles_(particles), surf_(FOsurf_LRF),
+      packed_lrf_(packed_lrf), seed_(seed) {
     if (flag_PCE != 0) {
         iss_host::error("partial chemical equilibrium EoS is not supported by the B200 engine");
         exit(1);
@@ -325,13 +326,10 @@ void GpuFSSW::select_species_(const std::vector<int> &chosen_monvals) {
            "iss_cuda_upload_species");
 }
 
-void GpuFSSW::upload_surface_() {
-    const int64_t n = static_cast<int64_t>(surf_.size());
-    PinnedBlock stage = pool_acquire(h_, n*ISS_NFIELD*static_cast<int64_t>(sizeof(float)));
-    float *dst = static_cast<float *>(stage.ptr);
-    auto pack = [&](int64_t c0, int64_t c1) {
-        for (int64_t c = c0; c < c1; c++) {
-            const FO_surf_LRF &s = surf_[c];
+void GpuFSSW::pack_surface(const std::vector<FO_surf_LRF> &surf, float *dst, int64_t c0, int64_t c1) {
+    auto pack = [&](int64_t b, int64_t e) {
+        for (int64_t c = b; c < e; c++) {
+            const FO_surf_LRF &s = surf[c];
             float *r = dst + c*ISS_NFIELD;
             r[0] = s.tau; r[1] = s.xpt; r[2] = s.ypt; r[3] = s.eta;
             for (int k = 0; k < 4; k++) {
@@ -344,20 +342,32 @@ void GpuFSSW::upload_surface_() {
             r[24] = s.piLRF_yz; r[25] = s.qmuLRF_x; r[26] = s.qmuLRF_y; r[27] = s.qmuLRF_z;
         }
     };
+    const int64_t n = c1 - c0;
     const int nthread = static_cast<int>(std::max<int64_t>(
         1, std::min<int64_t>(16, std::min<int64_t>(std::thread::hardware_concurrency(), n/65536))));
+    if (nthread <= 1) {
+        pack(c0, c1);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthread; t++) pool.emplace_back(pack, c0 + n*t/nthread, c0 + n*(t + 1)/nthread);
+    for (auto &t : pool) t.join();
+}
+
+void GpuFSSW::upload_surface_() {
+    const int64_t n = static_cast<int64_t>(surf_.size());
+    if (packed_lrf_) {
+        // the caller holds the records in upload layout in pinned memory: one copy, no staging
+        check_(iss_cuda_upload_surface_aos(h_, packed_lrf_, n), "iss_cuda_upload_surface_aos");
+        return;
+    }
+    PinnedBlock stage = pool_acquire(h_, n*ISS_NFIELD*static_cast<int64_t>(sizeof(float)));
+    float *dst = static_cast<float *>(stage.ptr);
     // in parts: while one part travels to the device (and is transposed there) the next is packed
     const int nparts = (n >= 262144) ? 4 : 1;
     for (int part = 0; part < nparts; part++) {
         const int64_t p0 = n*part/nparts, p1 = n*(part + 1)/nparts;
-        if (nthread <= 1) {
-            pack(p0, p1);
-        } else {
-            std::vector<std::thread> pool;
-            for (int t = 0; t < nthread; t++)
-                pool.emplace_back(pack, p0 + (p1 - p0)*t/nthread, p0 + (p1 - p0)*(t + 1)/nthread);
-            for (auto &t : pool) t.join();
-        }
+        pack_surface(surf_, dst, p0, p1);
         check_(iss_cuda_upload_surface_aos_part(h_, dst + p0*ISS_NFIELD, p0, p1 - p0, n),
                "iss_cuda_upload_surface_aos_part");
     }

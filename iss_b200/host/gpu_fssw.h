@@ -21,11 +21,16 @@ class GpuFSSW {
     GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
             const std::vector<particle_info> &particles,
             const std::vector<FO_surf_LRF> &FOsurf_LRF, int flag_PCE, ParameterReader *paraRdr,
-            std::string path, std::string table_path, AfterburnerType afterburner_type);
+            std::string path, std::string table_path, AfterburnerType afterburner_type,
+            const float *packed_lrf = nullptr);
     ~GpuFSSW();
 
     // chosen list -> indices into the pdg table in sampling order: unknown ids dropped with a
     // warning, stable ascending sort by mass (FSSW.cpp:115-162).  Needs no GPU.
+    // FO_surf_LRF records -> [n][ISS_NFIELD] floats in ISS_F_* order (the upload layout), on
+    // several threads.  `class iSS` keeps such a block in pinned memory per surface, so that
+    // repeated generate_samples() calls copy it to the device without repacking.
+    static void pack_surface(const std::vector<FO_surf_LRF> &surf, float *dst, int64_t c0, int64_t c1);
     static std::vector<int> order_species(const std::vector<int> &chosen_monvals,
                                           const std::vector<particle_info> &particles);
 
@@ -61,6 +66,7 @@ class GpuFSSW {
     const AfterburnerType afterburner_type_;
     const std::vector<particle_info> &particles_;
     const std::vector<FO_surf_LRF> &surf_;
+    const float *packed_lrf_ = nullptr;     // optional: surf_ already packed in pinned memory
     long seed_;
     int hydro_mode_;
     int include_shear_, include_bulk_, include_diff_, bulk_kind_;

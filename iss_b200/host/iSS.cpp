@@ -79,7 +79,38 @@ iSS::~iSS() {
     delete paraRdr_ptr;
 }
 
+void iSS::drop_packed_lrf_() {
+    if (lrf_packed_) {
+        const int device = iss_pool::default_device();
+        iss_handle *h = iss_pool::acquire_handle(device);
+        iss_pool::PinnedBlock b;
+        b.ptr = lrf_packed_;
+        b.bytes = lrf_packed_bytes_;
+        iss_pool::pinned_release(h, b);
+        iss_pool::release_handle(device, h);
+    }
+    lrf_packed_ = nullptr;
+    lrf_packed_bytes_ = 0;
+    lrf_packed_n_ = -1;
+}
+
+void iSS::ensure_packed_lrf_() {
+    const int64_t n = static_cast<int64_t>(FOsurf_LRF_array_.size());
+    if (lrf_packed_ && lrf_packed_n_ == n) return;
+    drop_packed_lrf_();
+    if (n == 0) return;
+    const int device = iss_pool::default_device();
+    iss_handle *h = iss_pool::acquire_handle(device);
+    iss_pool::PinnedBlock b = iss_pool::pinned_acquire(h, n*ISS_NFIELD*static_cast<int64_t>(sizeof(float)));
+    iss_pool::release_handle(device, h);
+    lrf_packed_ = b.ptr;
+    lrf_packed_bytes_ = b.bytes;
+    lrf_packed_n_ = n;
+    GpuFSSW::pack_surface(FOsurf_LRF_array_, static_cast<float *>(lrf_packed_), 0, n);
+}
+
 void iSS::clear() {
+    drop_packed_lrf_();
     FOsurf_array_.clear();
     FOsurf_LRF_array_.clear();
     FOsurf_Tmunu_.clear();
@@ -138,6 +169,7 @@ int iSS::read_in_FO_surface() {
     std::vector<FO_surf> cells;
     read_FOdata reader(paraRdr_ptr, path_, table_path_, particle_table_path_);
     lap("reader ctor (EOS table)");
+    lrf_packed_n_ = -1;         // a new surface: the packed copy is rebuilt
     FOsurf_LRF_array_.clear();
     FOsurf_array_.clear();
     // (the blocked binary pipeline feeds the LRF transform; the lab-frame path keeps whole cells)
@@ -159,6 +191,8 @@ int iSS::read_in_FO_surface() {
         flag_PCE_ = reader.get_flag_PCE();
         report_Tmunu_();
         lap("particle table");
+        ensure_packed_lrf_();
+        lap("pack LRF surface (pinned)");
     } else if (nbin >= 0) {
         // binary surface: parse -> regulate -> T^{mu nu} -> LRF transform over blocks that stay in
         // cache; per-cell arithmetic and cell order are those of the whole-surface path
@@ -381,8 +415,10 @@ int iSS::prepare_sampler() {
     if (!seed_set_) set_random_seed();
     const std::vector<int> chosen = read_chosen_particles();
     spectra_sampler_.reset();   // frees the previous batch before the new one is allocated
+    ensure_packed_lrf_();
     spectra_sampler_.reset(new GpuFSSW(randomSeed_, chosen, particle_, FOsurf_LRF_array_, flag_PCE_,
-                                       paraRdr_ptr, path_, table_path_, afterburner_type_));
+                                       paraRdr_ptr, path_, table_path_, afterburner_type_,
+                                       static_cast<const float *>(lrf_packed_)));
     return 0;
 }
 

@@ -49,6 +49,12 @@ class iSS {
     void accumulate_Tmunu_(const std::vector<FO_surf> &cells);
     void report_Tmunu_() const;
     void ingest_binary_on_device_(class read_FOdata &reader, int64_t nbin);
+    // FOsurf_LRF_array_ in the upload layout ([n][28] floats) in pinned host memory, built once per
+    // surface (engine addition: every generate_samples() copies it to the device as it is)
+    void *lrf_packed_ = nullptr;
+    int64_t lrf_packed_bytes_ = 0, lrf_packed_n_ = -1;
+    void ensure_packed_lrf_();
+    void drop_packed_lrf_();
 
  public:
     iSS(std::string path, std::string table_path = "iSS_tables",
