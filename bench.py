@@ -254,7 +254,10 @@ def run_engine(args):
         # sampling of E events, D2H of the hadron lists into the pinned host buffer.
         s.set_param("number_of_repeated_sampling", E)
         e2e_steps = max(1, min(args.steps, 3))
-        s.set_random_seed(args.seed + 1000*rank)
+        # same seed on every rank, disjoint event indices: together the ranks produce the events
+        # one process would produce for the whole range
+        s.set_param("first_event_index", rank*E)
+        s.set_random_seed(args.seed)
         s.generate_samples()                         # warm-up (allocations, pinned buffer)
         barrier()
         w0 = time.perf_counter()

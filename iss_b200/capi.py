@@ -285,6 +285,17 @@ class Engine:
         self.check(self.L.iss_cuda_upload_surface(self.h, ptrs, cells.shape[0]), "upload_surface")
         self.ncell = cells.shape[0]
 
+    def upload_surface_parts(self, cells, nparts):
+        """the same records through iss_cuda_upload_surface_aos_part, in `nparts` pieces"""
+        cells = np.ascontiguousarray(cells, dtype=np.float32)
+        n = cells.shape[0]
+        for k in range(nparts):
+            b, e = n*k//nparts, n*(k + 1)//nparts
+            if e > b:
+                self.check(self.L.iss_cuda_upload_surface_aos_part(self.h, _ptr(cells[b:e]), b, e - b, n),
+                           "upload_surface_aos_part")
+        self.ncell = n
+
     def upload_species(self, species):
         """species: structured array of SPECIES_DTYPE."""
         species = np.ascontiguousarray(species, dtype=SPECIES_DTYPE)

@@ -612,11 +612,21 @@ void GpuFSSW::sample_events() {
                                          + 6.0*std::sqrt(dN_event*nev_ + 1.0))
                      + nsp*nev_ + 1024);
 
+    // engine addition: `first_event_index` (default 0) numbers this call's events
+    // first, first + 1, ...  Every random stream is keyed by (seed, event index, ...), so processes
+    // that share the seed and use disjoint index ranges (one per GPU) produce together exactly the
+    // events a single process would produce for the whole range.
+    const int64_t ev_base = static_cast<int64_t>(paraRdr_->getVal("first_event_index", 0));
+    if (ev_base < 0) {
+        iss_host::error("first_event_index must be >= 0");
+        exit(-1);
+    }
     PhaseTimer tb("batches (sample+copy)");
     for (int64_t ev0 = 0; ev0 < nev_; ev0 += batch) {
         const int64_t ev1 = std::min<int64_t>(nev_, ev0 + batch);
         iss_counts cnt;
-        check_(iss_cuda_sample(h_, static_cast<uint64_t>(seed_), ev0, ev1, &cnt), "iss_cuda_sample");
+        check_(iss_cuda_sample(h_, static_cast<uint64_t>(seed_), ev_base + ev0, ev_base + ev1, &cnt),
+               "iss_cuda_sample");
         if (decays_on) {
             // FSSW::shell skips the feed-down for SMASH (FSSW.cpp:346)
             check_(iss_cuda_decay(h_, static_cast<uint64_t>(seed_), &cnt), "iss_cuda_decay");

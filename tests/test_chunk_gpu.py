@@ -204,3 +204,26 @@ def test_chunk_ragged_tail_and_decays(surf):
     assert c.n_hadrons == len(fin) >= len(prim)
     e.upload_surface(lrf)
     e.compute_yields()
+
+
+def test_surface_upload_in_parts_equals_whole(surf):
+    """iss_cuda_upload_surface_aos_part (host packs the next part while one is copied): same
+    device surface, hence the same yields bit for bit and the same hadrons."""
+    capi, s, lrf = surf
+    e = s.engine()
+    e.upload_surface(lrf)
+    dN0, y0 = e.compute_yields(want_cells=True)
+    e.sample(SEED, 0, 5)
+    h0 = e.fetch_all().copy()
+    for nparts in (1, 3, 7):
+        e.upload_surface_parts(lrf, nparts)
+        dN1, y1 = e.compute_yields(want_cells=True)
+        assert np.array_equal(dN0, dN1) and np.array_equal(y0, y1)
+    e.sample(SEED, 0, 5)
+    assert e.fetch_all().tobytes() == h0.tobytes()
+    with pytest.raises(capi.IssError):
+        e.L.iss_cuda_upload_surface_aos_part.restype  # noqa: B018  (binding exists)
+        e.check(e.L.iss_cuda_upload_surface_aos_part(e.h, capi._ptr(lrf[10:20].copy()), 10, 10, 12345),
+                "part without a first part of that surface")
+    e.upload_surface(lrf)
+    e.compute_yields()

@@ -44,6 +44,32 @@ def test_facade_batches_equal_single_batch(built, tmp_path):
         s.close()
 
 
+def test_facade_event_ranges_tile_a_single_run(built, tmp_path):
+    """`first_event_index` (engine addition): two facade runs with the same seed over events
+    [0, 40) and [40, 100) give together, byte for byte, the run over [0, 100) -- how the C++ host
+    shards oversampled events over the GPUs of a box, one process each."""
+    capi = built
+    g = cases.load("viscous2")
+    param, surf, over = cases.materialise(g, str(tmp_path))
+    over.update(perform_decays=0)
+    got = []
+    for first, nev in [(0, 100), (0, 40), (40, 60)]:
+        s = capi.Sampler(str(tmp_path), param, surf,
+                         **dict(over, number_of_repeated_sampling=nev, first_event_index=first))
+        try:
+            s.read_in_FO_surface()
+            s.set_random_seed(23)
+            s.generate_samples()
+            h, off = s.hadrons()
+            got.append((h.copy(), off.copy()))
+        finally:
+            s.close()
+    whole, a, b = got
+    assert len(a[0]) + len(b[0]) == len(whole[0])
+    assert (a[0].tobytes() + b[0].tobytes()) == whole[0].tobytes()
+    assert np.array_equal(np.concatenate([a[1], a[1][-1] + b[1][1:]]), whole[1])
+
+
 def test_facade_decays_and_spectators(built, tmp_path):
     capi = built
     g = cases.load("s3d_ce")
