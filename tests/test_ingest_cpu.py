@@ -66,3 +66,57 @@ def test_no_gpu_fails_loudly(built, tmp_path):
                        cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, env=env)
     assert r.returncode != 0
     assert b"no usable CUDA device" in r.stdout
+
+
+def _dump_lrf(tmp_path, param, surf, over, threads, out):
+    exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iss_host_dump")
+    args = [exe, param, "case", surf, out] + ["%s=%r" % kv for kv in over.items()]
+    r = subprocess.run(args, cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       env=dict(os.environ, ISS_INGEST="host", ISS_HOST_THREADS=str(threads)))
+    assert r.returncode == 0, r.stdout.decode()[-2000:]
+    with open(tmp_path/(out + ".lrf.bin"), "rb") as f:
+        n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+        return np.fromfile(f, dtype=np.float32).reshape(n, 28), r.stdout.decode()
+
+
+@pytest.mark.parametrize("boost_invariant", [False, True])
+def test_text_surface_parallel_parse(boost_invariant, built, tmp_path):
+    """Text surfaces are cut at newlines and parsed on several threads with std::from_chars: the
+    records must not depend on the number of threads, a file whose cells straddle lines (allowed
+    by the reference's stream reader in 3+1D, readindata.cpp:692-749) must give the same records
+    through the single-piece fallback, and cold cells are reported and dropped in file order."""
+    import bench
+    from iss_b200 import synthetic
+    case = tmp_path/"case"
+    synthetic.make_case(str(case), ncell=30000, seed=99, eos=14, rhob=1, diffusion=1, binary=0,
+                        boost_invariant=boost_invariant)
+    os.symlink(capi.TABLES, tmp_path/"iSS_tables")
+    over = dict(bench.OVERRIDES, hydro_mode=1 if boost_invariant else 2)
+    text = open(case/"surface.dat").read()
+    lines = text.splitlines()
+    assert len(lines) == 30000 and os.path.getsize(case/"surface.dat") > 8*(1 << 20)
+    # two cells below the temperature cut, far apart (different pieces)
+    for k in (5, 29990):
+        cols = lines[k].split()
+        cols[13] = "1.0e-03"            # T in fm^-1: 2e-4 GeV
+        lines[k] = " ".join(cols)
+    open(case/"surface.dat", "w").write("\n".join(lines) + "\n")
+    one, log1 = _dump_lrf(tmp_path, bench.PARAM, "surface.dat", over, 1, "t1")
+    many, log8 = _dump_lrf(tmp_path, bench.PARAM, "surface.dat", over, 8, "t8")
+    assert len(one) > 20000
+    assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+    assert log1.count("Discard surf elem") == 2 == log8.count("Discard surf elem")
+    # a trailing line without newline is a cell in 3+1D (stream eof after the last number) but is
+    # dropped by the boost-invariant line reader (readindata.cpp:531-541)
+    open(case/"surface.dat", "w").write("\n".join(lines))
+    cut, _ = _dump_lrf(tmp_path, bench.PARAM, "surface.dat", over, 8, "t8b")
+    if boost_invariant:
+        assert len(cut) <= len(one) and np.array_equal(cut.view(np.uint32), one[:len(cut)].view(np.uint32))
+        return
+    assert np.array_equal(cut.view(np.uint32), one.view(np.uint32))
+    # same numbers, seven per line: cells straddle lines
+    nums = " ".join(lines).split()
+    reflow = "\n".join(" ".join(nums[i:i + 7]) for i in range(0, len(nums), 7)) + "\n"
+    open(case/"surface.dat", "w").write(reflow)
+    odd, _ = _dump_lrf(tmp_path, bench.PARAM, "surface.dat", over, 8, "t8c")
+    assert np.array_equal(odd.view(np.uint32), one.view(np.uint32))
