@@ -17,7 +17,7 @@ namespace {
 // precomputed in double from the float fields exactly as FSSW::add_one_sampled_particle does for
 // eta_s = cell eta (FSSW.cpp:1981-1982).
 __global__ void build_cells_kernel(const float *__restrict__ soa, int64_t ncell, int64_t ncell_pad,
-                                   float *__restrict__ cells) {
+                                   float *__restrict__ cells, float4 *__restrict__ thermo) {
     const int64_t c = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
     if (c >= ncell) return;
     float rec[CELL_STRIDE];
@@ -28,6 +28,7 @@ __global__ void build_cells_kernel(const float *__restrict__ soa, int64_t ncell,
     rec[CELL_Z] = static_cast<float>(tau*sinh(eta));
     rec[30] = 0.f;
     rec[31] = 0.f;
+    thermo[c] = make_float4(rec[ISS_F_T], rec[ISS_F_MUB], rec[ISS_F_MUS], rec[ISS_F_MUQ]);
     float4 *dst = reinterpret_cast<float4 *>(cells + c*CELL_STRIDE);
 #pragma unroll
     for (int k = 0; k < CELL_STRIDE/4; k++)
@@ -50,6 +51,7 @@ void free_surface(iss_handle *h) {
     cudaFree(h->d_cells); h->d_cells = nullptr; h->cells_bytes = 0;
     cudaFree(h->d_cellcoef); h->d_cellcoef = nullptr; h->coef_bytes = 0;
     cudaFree(h->d_stage); h->d_stage = nullptr; h->stage_bytes = 0;
+    cudaFree(h->d_thermo); h->d_thermo = nullptr; h->thermo_bytes = 0;
     cudaFree(h->d_yields); h->d_yields = nullptr; h->yields_bytes = 0;
     cudaFree(h->d_cdf); h->d_cdf = nullptr; h->cdf_bytes = 0;
     cudaFree(h->d_tilesum); h->d_tilesum = nullptr; h->tilesum_bytes = 0;
@@ -68,7 +70,7 @@ void free_surface(iss_handle *h) {
 // cell reads its 112-byte record with 16-byte loads
 __global__ void unpack_cells_kernel(const float *__restrict__ stage, int64_t first, int64_t end,
                                     int64_t ncell_pad, float *__restrict__ soa,
-                                    float *__restrict__ cells) {
+                                    float *__restrict__ cells, float4 *__restrict__ thermo) {
     const int64_t c = first + static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
     if (c >= end) return;
     float rec[CELL_STRIDE];
@@ -85,6 +87,7 @@ __global__ void unpack_cells_kernel(const float *__restrict__ stage, int64_t fir
     rec[CELL_Z] = static_cast<float>(tau*sinh(eta));
     rec[30] = 0.f;
     rec[31] = 0.f;
+    thermo[c] = make_float4(rec[ISS_F_T], rec[ISS_F_MUB], rec[ISS_F_MUS], rec[ISS_F_MUQ]);
     float4 *dst = reinterpret_cast<float4 *>(cells + c*CELL_STRIDE);
 #pragma unroll
     for (int k = 0; k < CELL_STRIDE/4; k++)
@@ -102,6 +105,7 @@ int prepare_surface_buffers(iss_handle *h, int64_t ncell) {
     h->chunk = false;           // a new surface is a whole surface until declared a chunk
     ISS_ENSURE(h, h->d_surf, h->surf_bytes, sizeof(float)*ISS_NFIELD*h->ncell_pad);
     ISS_ENSURE(h, h->d_cells, h->cells_bytes, sizeof(float)*CELL_STRIDE*ncell);
+    ISS_ENSURE(h, h->d_thermo, h->thermo_bytes, sizeof(float4)*ncell);
     return ISS_OK;
 }
 
@@ -208,7 +212,7 @@ int iss_cuda_upload_surface(iss_handle *h, const float *const soa[ISS_NFIELD], i
                                         sizeof(float)*ncell, cudaMemcpyHostToDevice, h->stream));
     }
     build_cells_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(
-        h->d_surf, ncell, h->ncell_pad, h->d_cells); ISS_LAUNCHED(h);
+        h->d_surf, ncell, h->ncell_pad, h->d_cells, h->d_thermo); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return ISS_OK;
@@ -227,7 +231,7 @@ int iss_cuda_upload_surface_aos(iss_handle *h, const float *cells, int64_t ncell
             ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_surf + static_cast<int64_t>(k)*h->ncell_pad + ncell,
                                             0, sizeof(float)*(h->ncell_pad - ncell), h->stream));
     unpack_cells_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(
-        h->d_stage, 0, ncell, h->ncell_pad, h->d_surf, h->d_cells); ISS_LAUNCHED(h);
+        h->d_stage, 0, ncell, h->ncell_pad, h->d_surf, h->d_cells, h->d_thermo); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
     // the caller's buffer may be reused as soon as this returns
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -254,7 +258,7 @@ int iss_cuda_upload_surface_aos_part(iss_handle *h, const float *cells_part, int
     ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_stage + first*ISS_NFIELD, cells_part, sizeof(float)*ISS_NFIELD*n,
                                     cudaMemcpyHostToDevice, h->stream));
     unpack_cells_kernel<<<static_cast<unsigned>((n + 127)/128), 128, 0, h->stream>>>(
-        h->d_stage, first, first + n, h->ncell_pad, h->d_surf, h->d_cells); ISS_LAUNCHED(h);
+        h->d_stage, first, first + n, h->ncell_pad, h->d_surf, h->d_cells, h->d_thermo); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
     if (first + n == ncell_total) ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return ISS_OK;

@@ -76,7 +76,9 @@ struct iss_handle {
     float *d_cells = nullptr;           // [ncell][32] AoS copy for the sampler's random access
     double *d_cellcoef = nullptr;       // [ncell][8] delta-f coefficients c0..c5, kappa, spare
     float *d_stage = nullptr;           // [ncell][28] staging of an AoS upload
-    size_t surf_bytes = 0, cells_bytes = 0, coef_bytes = 0, stage_bytes = 0;   // capacities
+    float4 *d_thermo = nullptr;         // [ncell] {T, muB, muS, muQ}: 16 B per cell, L2 resident, all the
+                                        // sampler's set-up kernel needs from a cell
+    size_t surf_bytes = 0, cells_bytes = 0, coef_bytes = 0, stage_bytes = 0, thermo_bytes = 0;   // capacities
 
     // species
     int nspecies = 0;

@@ -235,6 +235,7 @@ static_assert(sizeof(Task) == 48, "Task must stay 48 bytes");
 
 struct SamplerArgs {
     const float *cells;             // [ncell][CELL_STRIDE]
+    const float4 *thermo;           // [ncell] {T, muB, muS, muQ}
     const double *cellcoef;         // [ncell][COEF_STRIDE]
     int64_t ncell, ncell_pad;
     const double *cdf;              // [ns][ncell_pad] global inclusive prefix of the yields
@@ -579,11 +580,12 @@ setup_kernel(const SamplerArgs A) {
         philox_block(0u, t.draw, t.event, sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
         const int64_t cell = pick_cell(A, s, u53(w0, w1));    // chunk mode: owned, hence >= 0
         t.cell = static_cast<int32_t>(cell);
-        const float4 *cr = reinterpret_cast<const float4 *>(A.cells + cell*CELL_STRIDE);
-        const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
-        const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
+        // T and the chemical potentials come from the 16-byte-per-cell copy (15 MB at C4: it stays in
+        // L2), not from the 128-byte record the proposal kernel gathers from DRAM
+        const float4 tm = __ldg(A.thermo + cell);
+        const float4 th = make_float4(tm.y, tm.z, tm.w, 0.f);
         MomSetup M;
-        const bool ok = momentum_setup(A.mt, p.mass, p.sign, th0.y, species_mu(p, 1, th, p.mass), M);
+        const bool ok = momentum_setup(A.mt, p.mass, p.sign, tm.x, species_mu(p, 1, th, p.mass), M);
         t.m_term = M.m_term;
         t.cdf_max = M.cdf_max;
         t.tab_idx = ok ? (M.tab | (M.idx_min << 3)) : -1;
@@ -1190,6 +1192,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     const iss_options &o = h->opt;
     SamplerArgs A;
     A.cells = h->d_cells;
+    A.thermo = h->d_thermo;
     A.cellcoef = h->d_cellcoef;
     A.ncell = h->ncell;
     A.ncell_pad = h->ncell_pad;
