@@ -339,6 +339,45 @@ ISS_API int iss_cuda_spectra(iss_handle *h, const iss_spectra_options *opt,
 /* evaluations (cell x y-eta point x pT x phi x species) and kernel milliseconds of the last call */
 ISS_API int iss_cuda_spectra_stats(iss_handle *h, double *evaluations, double *kernel_ms);
 
+/* ---- legacy "conventional" sampler --------------------------
+ * Replaces EmissionFunctionArray::sample_using_dN_dxtdy_4all_particles_conventional, the
+ * MC_sampling = 2 path (reference src/emissionfunction.cpp:3273-3623): yields over the LAB-frame
+ * (Milne) cells (calculate_dN_dxtdy_for_one_particle_species, :2977-3208), cell choice
+ * (RandomVariable1DArray), estimate_maximum (:4006-4153, 4309-4421), uniform proposals in
+ * (pT^2, phi, y - eta_s) accepted against that maximum (sample_momemtum_from_a_fluid_cell,
+ * :4188-4306), add_one_sampled_particle (:4423-4475).
+ * Call order: upload_species / upload_table(BESSEL_K [, EXPINT, KAPPA_B]) / set_options (hydro_mode,
+ * y_LB, y_RB, multiplicity model; local_charge_conservation must be 0) as for the FSSW path, then
+ *   iss_cuda_upload_surface_lab(cells) -> iss_cuda_legacy_upload_positions ->
+ *   iss_cuda_legacy_upload_z_table -> iss_cuda_legacy_set_options -> iss_cuda_legacy_compute_yields
+ *   -> iss_cuda_sample / iss_cuda_decay / iss_cuda_histograms / fetch as usual.
+ * Not supported (rejected with ISS_ERR_ARG): bulk_deltaf_kind 0 (needs the s95p-PCE coefficient
+ * table), local charge conservation, PCE chemical potentials.                                  */
+typedef struct {
+    int32_t include_deltaf_shear;
+    int32_t include_deltaf_bulk;
+    int32_t bulk_deltaf_kind;           /* 1..4 (the yields carry a bulk term for kind 1 only,
+                                           emissionfunction.cpp:3143-3147); others: zero coefficients */
+    int32_t include_deltaf_diffusion;   /* needs ISS_TABLE_KAPPA_B and ISS_TABLE_EXPINT */
+    int32_t restrict_deltaf;
+    int32_t reserved;
+    double deltaf_max_ratio;
+    double sample_pT_up_to;             /* > 0: the host resolves the reference's "-1 = last row of
+                                           the pT table" (emissionfunction.cpp:3302-3305) */
+    double sample_y_minus_eta_s_range;
+} iss_legacy_options;
+
+/* pos: [ncell][4] floats = xpt, ypt, eta_s, 0 of the cells given to iss_cuda_upload_surface_lab */
+ISS_API int iss_cuda_legacy_upload_positions(iss_handle *h, const float *pos, int64_t ncell);
+/* the two columns of iSS_tables/z_exp_m_z.dat (TableFunction z_exp_m_z, emissionfunction.cpp:3284-3287) */
+ISS_API int iss_cuda_legacy_upload_z_table(iss_handle *h, const double *x, const double *y, int32_t n);
+ISS_API int iss_cuda_legacy_set_options(iss_handle *h, const iss_legacy_options *opt);
+/* dN_species_host[ns] <- sum over cells of max(yield, 0) (RandomVariable1DArray::return_sum);
+ * yields_host (may be NULL) <- [ns][ncell] raw yields (the reference does not clamp them);
+ * maximum_host (may be NULL) <- [ns][ncell] estimate_maximum values (test instrumentation).     */
+ISS_API int iss_cuda_legacy_compute_yields(iss_handle *h, double *dN_species_host,
+                                           double *yields_host, double *maximum_host);
+
 /* ---- surface ingest on the device -------------------------
  * Binary MUSIC surface records (34 float32 per cell, reference src/readindata.cpp:646-689) ->
  * local-rest-frame records in ISS_F_* order, i.e. the per-cell work of

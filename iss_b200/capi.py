@@ -61,6 +61,14 @@ class SpectraOptions(C.Structure):
                 ("deltaf_max_ratio", C.c_double)]
 
 
+class LegacyOptions(C.Structure):
+    _fields_ = [("include_deltaf_shear", C.c_int32), ("include_deltaf_bulk", C.c_int32),
+                ("bulk_deltaf_kind", C.c_int32), ("include_deltaf_diffusion", C.c_int32),
+                ("restrict_deltaf", C.c_int32), ("reserved", C.c_int32),
+                ("deltaf_max_ratio", C.c_double), ("sample_pT_up_to", C.c_double),
+                ("sample_y_minus_eta_s_range", C.c_double)]
+
+
 class IngestOptions(C.Structure):
     _fields_ = [("boost_invariant", C.c_int32), ("regulate_eos", C.c_int32), ("hrg_nB", C.c_int32),
                 ("reserved", C.c_int32), ("hrg_rows", C.c_int64)]
@@ -100,6 +108,8 @@ CUDA_SYMBOLS = [
     "iss_cuda_upload_surface_lab", "iss_cuda_spectra", "iss_cuda_spectra_stats",
     "iss_cuda_ingest_music_binary", "iss_cuda_set_surface_chunk", "iss_cuda_chunk_yields_local",
     "iss_cuda_chunk_yields_finish", "iss_cuda_upload_surface_aos_part",
+    "iss_cuda_legacy_upload_positions", "iss_cuda_legacy_upload_z_table",
+    "iss_cuda_legacy_set_options", "iss_cuda_legacy_compute_yields",
 ]
 HOST_SYMBOLS = [
     "iss_host_create", "iss_host_destroy", "iss_host_set_param", "iss_host_get_param",
@@ -174,6 +184,10 @@ def cuda_lib():
         "iss_cuda_spectra": (C.c_int, [vp, C.POINTER(SpectraOptions), vp, i32, vp, i32, vp, i32, vp, vp,
                                        i32, vp, vp]),
         "iss_cuda_spectra_stats": (C.c_int, [vp, dp, dp]),
+        "iss_cuda_legacy_upload_positions": (C.c_int, [vp, vp, i64]),
+        "iss_cuda_legacy_upload_z_table": (C.c_int, [vp, vp, vp, i32]),
+        "iss_cuda_legacy_set_options": (C.c_int, [vp, C.POINTER(LegacyOptions)]),
+        "iss_cuda_legacy_compute_yields": (C.c_int, [vp, vp, vp, vp]),
         "iss_cuda_ingest_music_binary": (C.c_int, [vp, vp, i64, C.POINTER(IngestOptions), vp, vp, vp, vp,
                                                    C.POINTER(IngestResult)]),
     }
@@ -464,6 +478,36 @@ class Engine:
                                            len(pT), _ptr(phi), len(phi), _ptr(y), _ptr(w), len(y),
                                            _ptr(dN), _ptr(dN_max)), "spectra")
         return dN, dN_max
+
+    # ---- legacy "conventional" sampler (MC_sampling = 2, EmissionFunctionArray)
+    def legacy_setup(self, lab, pos, ztab, **opt):
+        """lab: float32 [ncell, 32] (ISS_L_* order); pos: float32 [ncell, 4] x, y, eta_s, 0;
+        ztab: the two columns of iSS_tables/z_exp_m_z.dat; opt: fields of iss_legacy_options."""
+        self.upload_surface_lab(lab)
+        pos = np.ascontiguousarray(pos, dtype=np.float32)
+        assert pos.shape == (len(lab), 4)
+        self.check(self.L.iss_cuda_legacy_upload_positions(self.h, _ptr(pos), len(pos)),
+                   "legacy_upload_positions")
+        zx = np.ascontiguousarray(ztab[0], dtype=np.float64)
+        zy = np.ascontiguousarray(ztab[1], dtype=np.float64)
+        self.check(self.L.iss_cuda_legacy_upload_z_table(self.h, _ptr(zx), _ptr(zy), len(zx)),
+                   "legacy_upload_z_table")
+        o = LegacyOptions()
+        o.deltaf_max_ratio = 1.0
+        o.bulk_deltaf_kind = 1
+        for k, v in opt.items():
+            setattr(o, k, v)
+        self.check(self.L.iss_cuda_legacy_set_options(self.h, C.byref(o)), "legacy_set_options")
+        self.ncell = len(lab)
+
+    def legacy_compute_yields(self, want_cells=False, want_maximum=False):
+        dN = np.zeros(self.nspecies)
+        y = np.zeros((self.nspecies, self.ncell)) if want_cells else None
+        mx = np.zeros((self.nspecies, self.ncell)) if want_maximum else None
+        self.check(self.L.iss_cuda_legacy_compute_yields(
+            self.h, _ptr(dN), _ptr(y) if want_cells else None, _ptr(mx) if want_maximum else None),
+            "legacy_compute_yields")
+        return dN, y, mx
 
     def spectra_stats(self):
         """(evaluations, kernel milliseconds) of the last spectra() call."""

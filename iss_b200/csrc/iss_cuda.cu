@@ -97,6 +97,8 @@ __global__ void unpack_cells_kernel(const float *__restrict__ stage, int64_t fir
 int prepare_surface_buffers(iss_handle *h, int64_t ncell) {
     if (ncell >= (int64_t(1) << 31)) ISS_FAIL(h, ISS_ERR_ARG, "ncell must be < 2^31");
     h->ncell = ncell;
+    h->ncell_lrf = ncell;
+    h->legacy = false;
     h->ntile = (ncell + TILE - 1)/TILE;
     h->ncell_pad = h->ntile*TILE;
     h->have_yields = false;
@@ -170,6 +172,8 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
     cudaFree(h->d_qa); cudaFree(h->d_trace);
     cudaFree(h->d_own); cudaFree(h->d_wlist);
+    cudaFree(h->d_legpos); cudaFree(h->d_legcoef); cudaFree(h->d_zx); cudaFree(h->d_zy);
+    cudaFree(h->d_lambert); cudaFree(h->d_legmax);
     if (h->h_mail) cudaFreeHost(h->h_mail);
     if (h->h_evoff) cudaFreeHost(h->h_evoff);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -818,6 +822,47 @@ int iss_cuda_fp64_peak(iss_handle *h, double *tflops) {
     ISS_CUDA_TRY(h, cudaGetLastError());
     const double flops = 2.0*8.0*static_cast<double>(iters)*blocks*threads;
     *tflops = flops/(best*1e-3)/1e12;
+    return ISS_OK;
+}
+
+// ---- legacy sampler (MC_sampling = 2) -----------------------------------------------------------
+int iss_cuda_legacy_upload_positions(iss_handle *h, const float *pos, int64_t ncell) {
+    if (!h || !pos || ncell <= 0) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    ISS_ENSURE(h, h->d_legpos, h->legpos_bytes, sizeof(float4)*ncell);
+    ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_legpos, pos, sizeof(float4)*ncell, cudaMemcpyHostToDevice,
+                                    h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->nlegpos = ncell;
+    return ISS_OK;
+}
+
+int iss_cuda_legacy_upload_z_table(iss_handle *h, const double *x, const double *y, int32_t n) {
+    if (!h || !x || !y || n < 4) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    int rc = upload_doubles(h, &h->d_zx, x, n);
+    if (rc) return rc;
+    rc = upload_doubles(h, &h->d_zy, y, n);
+    if (rc) return rc;
+    h->nz = n;
+    return ISS_OK;
+}
+
+int iss_cuda_legacy_set_options(iss_handle *h, const iss_legacy_options *opt) {
+    if (!h || !opt) return ISS_ERR_ARG;
+    h->legopt = *opt;
+    h->have_legopt = true;
+    if (h->legacy) h->have_yields = false;
+    return ISS_OK;
+}
+
+int iss_cuda_legacy_compute_yields(iss_handle *h, double *dN_species_host, double *yields_host,
+                                   double *maximum_host) {
+    if (!h) return ISS_ERR_ARG;
+    cudaSetDevice(h->device);
+    int rc = run_legacy_yields(h, yields_host, maximum_host);
+    if (rc) return rc;
+    if (dN_species_host) memcpy(dN_species_host, h->h_total.data(), sizeof(double)*h->nspecies);
     return ISS_OK;
 }
 

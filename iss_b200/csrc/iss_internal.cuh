@@ -100,6 +100,15 @@ struct iss_handle {
     double *d_kappa = nullptr; iss::Grid2D gk{};
     // smooth spectra (spectra.cu)
     float *d_lab = nullptr; size_t lab_bytes = 0; int64_t nlab = 0;     // [nlab][ISS_LAB_NFIELD]
+    // legacy sampler (MC_sampling = 2, legacy.cuh) on the lab-frame surface d_lab
+    bool legacy = false;                // the yields / CDF held are those of the legacy path
+    int64_t ncell_lrf = 0;              // cells of the uploaded FSSW (local-rest-frame) surface
+    iss_legacy_options legopt{}; bool have_legopt = false;
+    float4 *d_legpos = nullptr; size_t legpos_bytes = 0; int64_t nlegpos = 0;   // x, y, eta_s, 0
+    double4 *d_legcoef = nullptr; size_t legcoef_bytes = 0;                     // c0, c1, c2, kappa
+    double *d_zx = nullptr, *d_zy = nullptr; int nz = 0;                        // z_exp_m_z.dat
+    double *d_lambert = nullptr;                                                // W0 table
+    double *d_legmax = nullptr; size_t legmax_bytes = 0;
     double *d_labrec = nullptr; size_t labrec_bytes = 0;                // per-cell double records
     double *d_spec_part = nullptr; size_t spec_part_bytes = 0;          // chunk partial sums
     double *d_spec_out = nullptr; size_t spec_out_bytes = 0;
@@ -273,6 +282,7 @@ int run_yields_local(iss_handle *h);
 int run_yields_finish(iss_handle *h);
 int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev);
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t total);
+int run_legacy_yields(iss_handle *h, double *yields_host, double *maximum_host);
 int run_decay(iss_handle *h, uint64_t seed);
 int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate);
 int run_momentum_unit(iss_handle *h, double m, double T, double mu, int sign, int64_t n,

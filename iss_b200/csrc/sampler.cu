@@ -1180,10 +1180,15 @@ static int chunk_select_work(iss_handle *h, const SamplerArgs &A, int64_t nev, i
     return ISS_OK;
 }
 
+}  // namespace iss
+#define ISS_LEGACY_WITH_SAMPLER
+#include "legacy.cuh"
+namespace iss {
+
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     const int ns = h->nspecies;
     const int64_t n = nev*ns;
-    int rc = ensure_momentum_tables(h);
+    int rc = h->legacy ? ISS_OK : ensure_momentum_tables(h);
     if (rc) return rc;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
@@ -1304,6 +1309,29 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         }
         A.trace_cell = h->d_trace;
         A.trace_tries = h->d_trace + h->trace_cap;
+    }
+
+    if (h->legacy) {
+        // legacy sampler (MC_sampling = 2): one persistent kernel, lanes take work items one by one
+        LegacyArgs G;
+        rc = legacy_args(h, G);
+        if (rc) return rc;
+        {
+            ScopedTimer t(h, ISS_T_SETUP);
+            work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
+                h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
+        }
+        const size_t smem_l = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
+        int64_t grid_l = static_cast<int64_t>(nsm)*4;
+        const int64_t useful = (A.nwork + LEGACY_THREADS - 1)/LEGACY_THREADS;
+        if (grid_l > useful) grid_l = useful;
+        {
+            ScopedTimer t(h, ISS_T_SAMPLE);
+            legacy_sample_kernel<<<static_cast<unsigned>(grid_l), LEGACY_THREADS, smem_l, h->stream>>>(A, G);
+            ISS_LAUNCHED(h);
+        }
+        ISS_CUDA_TRY(h, cudaGetLastError());
+        return ISS_OK;
     }
 
     // task list of the batch

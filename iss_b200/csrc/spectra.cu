@@ -20,6 +20,7 @@
 // This regroups the reference's sums (differences ~1e-15 relative; the parity tests allow 1e-10).
 #include "iss_internal.cuh"
 #include "coefficients.cuh"
+#include "legacy_bulk.cuh"
 
 #include <cmath>
 #include <type_traits>
@@ -49,32 +50,6 @@ enum {
     S_COUNT
 };
 
-// degree-10 polynomials in T [1/fm] of bulk_deltaf_kind 1..4 (emissionfunction.cpp:3659-3760)
-__constant__ double c_bulk_poly[4][2][11] = {
-    {{642096.624265727, -8163329.49562861, 47162768.4292073, -162590040.002683, 369637951.096896,
-      -578181331.809836, 629434830.225675, -470493661.096657, 230936465.421, -67175218.4629078,
-      8789472.32652964},
-     {1.18171174036192, -17.6740645873717, 136.298469057177, -635.999435106846, 1918.77100633321,
-      -3836.32258307711, 5136.35746882372, -4566.22991441914, 2593.45375240886, -853.908199724349,
-      124.260460450113}},
-    {{21091365.1182649, -290482229.281782, 1800423055.01882, -6608608560.99887, 15900800422.7138,
-      -26194517161.8205, 29912485360.2916, -23375101221.2855, 11960898238.0134, -3618358144.18576,
-      491369134.205902},
-     {4007863.29316896, -55199395.3534188, 342115196.396492, -1255681487.77798, 3021026280.08401,
-      -4976331606.85766, 5682163732.74188, -4439937810.57449, 2271692965.05568, -687164038.128814,
-      93308348.3137008}},
-    {{160421664.93603, -2212807124.97991, 13707913981.1425, -50204536518.1767, 120354649094.362,
-      -197298426823.223, 223953760788.288, -173790947240.829, 88231322888.0423, -26461154892.6963,
-      3559805050.19592},
-     {33369186.2536556, -460293490.420478, 2851449676.09981, -10443297927.601, 25035517099.7809,
-      -41040777943.4963, 46585225878.8723, -36150531001.3718, 18353035766.9323, -5504165325.05431,
-      740468257.784873}},
-    {{1167272041.90731, -16378866444.6842, 103037615761.617, -382670727905.111, 929111866739.436,
-      -1540948583116.54, 1767975890298.1, -1385606389545.0, 709922576963.213, -214726945096.326,
-      29116298091.9219},
-     {5103633637.7213, -71612903872.8163, 450509014334.964, -1673143669281.46, 4062340452589.89,
-      -6737468792456.4, 7730102407679.65, -6058276038129.83, 3103990764357.81, -938850005883.612,
-      127305171097.249}}};
 
 // exp() and reciprocal of the occupation number, written out so that every constant is a
 // constant-bank operand of the DFMA that uses it (the library exp() re-materialises its 64-bit
@@ -166,17 +141,7 @@ spectra_cell_kernel(const SpectraArgs A) {
         } else {
             bulkPi = static_cast<double>(f[ISS_L_BULKPI])/HBARC;
             if (kind >= 1 && kind <= 4) {
-                // powers by repeated multiplication, terms added left to right without
-                // contraction: the sums cancel to ~1e-7 of the largest term
-                const double x = T/HBARC;
-                double p = x;
-                c0 = c_bulk_poly[kind - 1][0][0];
-                c1 = c_bulk_poly[kind - 1][1][0];
-                for (int k = 1; k < 11; k++) {
-                    c0 = __dadd_rn(c0, __dmul_rn(c_bulk_poly[kind - 1][0][k], p));
-                    c1 = __dadd_rn(c1, __dmul_rn(c_bulk_poly[kind - 1][1][k], p));
-                    p = __dmul_rn(p, x);
-                }
+                legacy_bulk_poly(kind, T, c0, c1);
             }
         }
     }

@@ -13,6 +13,7 @@
 // All reductions have a fixed order, so totals are bit-reproducible run to run
 // and identical on every GPU that holds the same surface.
 #include "coefficients.cuh"
+#include "legacy.cuh"
 
 namespace iss {
 
@@ -368,8 +369,7 @@ __global__ void pack_sf4_kernel(const double *__restrict__ bessel, const double 
     sf4[i*4 + 3] = acc;
 }
 
-static int ensure_sf_tables(iss_handle *h) {
-    const bool need_diff = h->opt.include_deltaf_diffusion == 1;
+static int ensure_sf_tables(iss_handle *h, bool need_diff) {
     if (h->d_bessel && (!need_diff || h->d_expint) && h->d_sf4 && h->sf4_with_diff == need_diff)
         return ISS_OK;
     if (!h->d_bessel || (need_diff && !h->d_expint)) {
@@ -421,6 +421,14 @@ static int level_geometry(int64_t n0, int max_levels, int64_t *lev_n, int64_t *l
 // their 1024-cell tiles.  In surface-chunk mode the caller gathers the tile sums of all ranks
 // before part 2.
 int run_yields_local(iss_handle *h) {
+    if (h->legacy) {
+        // the prefix arrays were last sized for the lab-frame surface of the legacy path
+        h->ncell = h->ncell_lrf;
+        h->ntile = (h->ncell + TILE - 1)/TILE;
+        h->ncell_pad = h->ntile*TILE;
+        h->legacy = false;
+        h->have_yields = false;
+    }
     if (h->ncell <= 0 || !h->d_surf) ISS_FAIL(h, ISS_ERR_STATE, "no surface uploaded");
     if (h->nspecies <= 0) ISS_FAIL(h, ISS_ERR_STATE, "no species uploaded");
     if (!h->have_opt) ISS_FAIL(h, ISS_ERR_STATE, "options not set");
@@ -438,7 +446,7 @@ int run_yields_local(iss_handle *h) {
         ISS_FAIL(h, ISS_ERR_STATE, "14-moment bulk table not uploaded");
     if (mode.include_diff == 1 && !h->d_kappa)
         ISS_FAIL(h, ISS_ERR_STATE, "kappa_B table not uploaded");
-    int rc = ensure_sf_tables(h);
+    int rc = ensure_sf_tables(h, o.include_deltaf_diffusion == 1);
     if (rc) return rc;
 
     h->have_yields = false;
@@ -585,6 +593,133 @@ int run_yields_finish(iss_handle *h) {
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->have_yields = true;
     h->lambda_on_device = false;
+    return ISS_OK;
+}
+
+int legacy_args(iss_handle *h, LegacyArgs &G) {
+    if (!h->have_legopt) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_legacy_set_options must run first");
+    if (h->nlab <= 0 || !h->d_lab) ISS_FAIL(h, ISS_ERR_STATE, "no lab-frame surface uploaded");
+    if (h->nlegpos != h->nlab || !h->d_legpos)
+        ISS_FAIL(h, ISS_ERR_STATE, "cell positions of the lab-frame surface not uploaded");
+    if (!h->d_zx) ISS_FAIL(h, ISS_ERR_STATE, "z_exp_m_z table not uploaded");
+    const iss_legacy_options &o = h->legopt;
+    if (o.include_deltaf_bulk == 1 && o.bulk_deltaf_kind == 0)
+        ISS_FAIL(h, ISS_ERR_ARG, "legacy sampler: bulk_deltaf_kind 0 (table-driven 14-moment) is not supported");
+    if (o.include_deltaf_diffusion == 1 && !h->d_kappa)
+        ISS_FAIL(h, ISS_ERR_STATE, "kappa_B table not uploaded");
+    if (!(o.sample_pT_up_to > 0.) || !(o.sample_y_minus_eta_s_range > 0.))
+        ISS_FAIL(h, ISS_ERR_ARG, "legacy sampler: pT and y - eta_s ranges must be positive");
+    if (!h->d_lambert) {
+        ISS_CUDA_TRY(h, cudaMalloc(&h->d_lambert, sizeof(double)*LEGACY_LAMBERT_N));
+        legacy_lambert_kernel<<<(LEGACY_LAMBERT_N + 255)/256, 256, 0, h->stream>>>(h->d_lambert);
+        ISS_LAUNCHED(h);
+        ISS_CUDA_TRY(h, cudaGetLastError());
+    }
+    G.lab = h->d_lab;
+    G.pos = h->d_legpos;
+    G.coef = h->d_legcoef;
+    G.zx = h->d_zx;
+    G.zy = h->d_zy;
+    G.nz = h->nz;
+    G.lambert = h->d_lambert;
+    G.include_shear = o.include_deltaf_shear;
+    G.include_bulk = o.include_deltaf_bulk;
+    G.bulk_kind = o.bulk_deltaf_kind;
+    G.include_diff = o.include_deltaf_diffusion;
+    G.restrict_deltaf = o.restrict_deltaf;
+    G.deltaf_max_ratio = o.deltaf_max_ratio;
+    G.pT_to = o.sample_pT_up_to;
+    G.y_range = o.sample_y_minus_eta_s_range;
+    G.ncell = h->nlab;
+    G.ncell_pad = h->ncell_pad;
+    G.tab.bessel = h->d_bessel;
+    G.tab.expint = h->d_expint;
+    G.tab.sf = h->sf;
+    G.tab.ce = nullptr;
+    G.tab.mom22 = nullptr;
+    G.tab.ce_n = 0;
+    G.tab.mom14 = nullptr;
+    G.tab.g14 = h->g14;
+    G.tab.kappa = h->d_kappa;
+    G.tab.gk = h->gk;
+    G.yields = h->d_yields;
+    G.max_out = nullptr;
+    return ISS_OK;
+}
+
+// Yields of the legacy path over the lab-frame surface (h->d_lab), then the same fixed-order
+// prefix / search levels / totals as the FSSW path (run_yields_finish).
+int run_legacy_yields(iss_handle *h, double *yields_host, double *maximum_host) {
+    if (h->nspecies <= 0) ISS_FAIL(h, ISS_ERR_STATE, "no species uploaded");
+    if (!h->have_opt) ISS_FAIL(h, ISS_ERR_STATE, "options not set");
+    if (h->opt.local_charge_conservation == 1)
+        ISS_FAIL(h, ISS_ERR_ARG, "legacy sampler: local_charge_conservation is not supported");
+    if (!h->have_legopt) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_legacy_set_options must run first");
+    // K_n / E_n tables: built on the device unless the caller uploaded them
+    int rc = ensure_sf_tables(h, h->legopt.include_deltaf_diffusion == 1);
+    if (rc) return rc;
+    const int64_t ncell = h->nlab;
+    if (ncell <= 0) ISS_FAIL(h, ISS_ERR_STATE, "no lab-frame surface uploaded");
+    if (ncell >= (int64_t(1) << 31)) ISS_FAIL(h, ISS_ERR_ARG, "ncell must be < 2^31");
+    // the FSSW surface (if any) is superseded: the prefix arrays now describe the lab-frame cells
+    h->ncell = ncell;
+    h->ntile = (ncell + TILE - 1)/TILE;
+    h->ncell_pad = h->ntile*TILE;
+    h->chunk = false;
+    h->have_yields = false;
+    h->have_local_yields = false;
+    h->have_batch = false;
+    h->legacy = false;
+    const int64_t ns = h->nspecies;
+    const size_t nval = static_cast<size_t>(ns)*h->ncell_pad;
+    ISS_ENSURE(h, h->d_yields, h->yields_bytes, sizeof(double)*nval);
+    ISS_ENSURE(h, h->d_cdf, h->cdf_bytes, sizeof(double)*nval);
+    ISS_ENSURE(h, h->d_tilesum, h->tilesum_bytes, sizeof(double)*ns*h->ntile);
+    ISS_ENSURE(h, h->d_tilebase, h->tilebase_bytes, sizeof(double)*ns*(h->ntile + 1));
+    ISS_ENSURE(h, h->d_total, h->total_bytes, sizeof(double)*ns);
+    h->nlev = level_geometry(h->ncell_pad, 7, h->lev_n, h->lev_off, &h->lev_stride);
+    ISS_ENSURE(h, h->d_cdflev, h->cdflev_bytes, sizeof(double)*ns*h->lev_stride);
+    ISS_ENSURE(h, h->d_legcoef, h->legcoef_bytes, sizeof(double4)*ncell);
+    LegacyArgs G;
+    rc = legacy_args(h, G);
+    if (rc) return rc;
+    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_yields, 0, sizeof(double)*nval, h->stream));
+    {
+        ScopedTimer t(h, ISS_T_YIELDS);
+        legacy_coef_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(G);
+        ISS_LAUNCHED(h);
+        legacy_yields_kernel<<<static_cast<unsigned>((ncell + 127)/128), 128, 0, h->stream>>>(
+            G, h->d_species, static_cast<int>(ns)); ISS_LAUNCHED(h);
+    }
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    if (yields_host)
+        ISS_CUDA_TRY(h, cudaMemcpy2DAsync(yields_host, sizeof(double)*ncell, h->d_yields,
+                                          sizeof(double)*h->ncell_pad, sizeof(double)*ncell, ns,
+                                          cudaMemcpyDeviceToHost, h->stream));
+    if (maximum_host) {
+        ISS_ENSURE(h, h->d_legmax, h->legmax_bytes, sizeof(double)*ns*ncell);
+        G.max_out = h->d_legmax;
+        const int64_t n = ns*ncell;
+        legacy_max_kernel<<<static_cast<unsigned>((n + 127)/128), 128, 0, h->stream>>>(
+            G, h->d_species, static_cast<int>(ns)); ISS_LAUNCHED(h);
+        ISS_CUDA_TRY(h, cudaGetLastError());
+        ISS_CUDA_TRY(h, cudaMemcpyAsync(maximum_host, h->d_legmax, sizeof(double)*n,
+                                        cudaMemcpyDeviceToHost, h->stream));
+    }
+    {
+        ScopedTimer t(h, ISS_T_SCAN);
+        legacy_clamp_kernel<<<static_cast<unsigned>((nval + 255)/256), 256, 0, h->stream>>>(
+            h->d_yields, static_cast<int64_t>(nval)); ISS_LAUNCHED(h);
+        dim3 grid(static_cast<unsigned>(h->ntile), static_cast<unsigned>(ns));
+        tile_scan_kernel<1><<<grid, 256, 0, h->stream>>>(h->d_yields, h->d_cdf, h->d_tilesum, nullptr,
+                                                         nullptr, 0, h->ncell, h->ncell_pad, h->ntile,
+                                                         0, 0); ISS_LAUNCHED(h);
+    }
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    h->have_local_yields = true;
+    rc = run_yields_finish(h);
+    if (rc) return rc;
+    h->legacy = true;
     return ISS_OK;
 }
 

@@ -772,3 +772,308 @@ int64_t oracle_decay_once_many(int pid, int64_t n, uint64_t seed, const o_dspeci
     }
     return w;
 }
+
+/* ================================================================================================
+ * Legacy "conventional" sampler of EmissionFunctionArray (MC_sampling = 2):
+ * sample_using_dN_dxtdy_4all_particles_conventional (src/emissionfunction.cpp:3273-3623),
+ * estimate_maximum (:4006-4153, 4309-4421), sample_momemtum_from_a_fluid_cell (:4188-4306),
+ * get_deltaf_bulk (:4156-4186), add_one_sampled_particle (:4423-4475).
+ * Cells are the LAB-frame (Milne) records, 32 floats in the ISS_L_* order of include/iss_cuda.h,
+ * plus pos[4] = x, y, eta_s, 0.  coef[4] per cell = bulk coefficients c0, c1, c2
+ * (getbulkvisCoefficients, :3625-3762) and kappa_hat (get_deltaf_qmu_coeff, :3788-3823), which are
+ * species independent and restated in numpy (oracle/legacy_oracle.py).
+ * ================================================================================================ */
+enum { L_TAU = 0, L_U0, L_U1, L_U2, L_U3, L_DA0, L_DA1, L_DA2, L_DA3, L_T, L_P, L_E, L_MUB, L_MUS,
+       L_MUQ, L_PI00, L_PI01, L_PI02, L_PI03, L_PI11, L_PI12, L_PI13, L_PI22, L_PI23, L_PI33,
+       L_BULK, L_BN, L_Q0, L_Q1, L_Q2, L_Q3, L_SPARE, L_NFIELD };
+
+typedef struct {
+    int32_t include_shear, include_bulk, bulk_kind, include_diff;
+    int32_t restrict_deltaf, boost_invariant, reserved0, reserved1;
+    double deltaf_max_ratio, pT_to, y_minus_eta_s_range, y_LB, y_RB;
+} o_legacy_opt;
+
+/* principal branch of the Lambert W function for x >= 0 (Halley iteration); the reference calls
+ * gsl_sf_lambert_W0 (third party, not in the tree) */
+static double lambert_w0(double x) {
+    if (x == 0.) return 0.;
+    double w = (x < 1.) ? x*(1. - x + 1.5*x*x) : log(x) - log(log(x) + 1.);
+    if (!(w > 0.)) w = 0.5;
+    for (int it = 0; it < 60; it++) {
+        const double e = exp(w), f = w*e - x;
+        const double dw = f/(e*(w + 1.) - (w + 2.)*f/(2.*w + 2.));
+        w -= dw;
+        if (fabs(dw) <= 1e-16*(1. + fabs(w))) break;
+    }
+    return w;
+}
+
+#define LAMBERT_N 40001     /* (200 - 0)/0.005 + 1, :3858-3870 */
+static double lambert_tab[LAMBERT_N];
+static int lambert_ready = 0;
+static double legacy_lambertW(double arg) {     /* get_special_function_lambertW, :3936-3953 */
+    const double x_min = 0., x_max = 200.0, dx = 0.005;
+    if (!lambert_ready) {
+        for (int i = 0; i < LAMBERT_N; i++) lambert_tab[i] = lambert_w0(x_min + i*dx);
+        lambert_ready = 1;
+    }
+    if (arg < x_min || arg > x_max - dx) return lambert_w0(arg);
+    const int idx = (int)((arg - x_min)/dx);
+    const double fraction = (arg - x_min - idx*dx)/dx;
+    return (1. - fraction)*lambert_tab[idx] + fraction*lambert_tab[idx + 1];
+}
+double oracle_lambert_w0(double x) { return lambert_w0(x); }
+
+/* TableFunction::map with interpolation_model 5 = interpCubicDirect without extrapolation
+ * (src/arsenal.cpp:58-110) on iSS_tables/z_exp_m_z.dat; the reference exit(1)s outside the table,
+ * here NaN is returned */
+static double z_map(const double *x, const double *y, int size, double xx) {
+    const double dx = x[1] - x[0];
+    if (fabs(xx - x[0]) < dx*1e-30) return y[0];
+    const long idx = (long)floor((xx - x[0])/dx);
+    if (idx < 0 || idx >= size - 1) return NAN;
+    if (idx == 0) {
+        const double A0 = y[0], A1 = y[1], A2 = y[2], d = xx - x[0];
+        return (A0 - 2.0*A1 + A2)/(2.0*dx*dx)*d*d - (3.0*A0 - 4.0*A1 + A2)/(2.0*dx)*d + A0;
+    } else if (idx == size - 2) {
+        const double A0 = y[size - 3], A1 = y[size - 2], A2 = y[size - 1];
+        const double d = xx - (x[0] + (idx - 1)*dx);
+        return (A0 - 2.0*A1 + A2)/(2.0*dx*dx)*d*d - (3.0*A0 - 4.0*A1 + A2)/(2.0*dx)*d + A0;
+    }
+    const double A0 = y[idx - 1], A1 = y[idx], A2 = y[idx + 1], A3 = y[idx + 2];
+    const double d = xx - (x[0] + idx*dx);
+    return (-A0 + 3.0*A1 - 3.0*A2 + A3)/(6.0*dx*dx*dx)*d*d*d + (A0 - 2.0*A1 + A2)/(2.0*dx*dx)*d*d
+           - (2.0*A0 + 3.0*A1 - 6.0*A2 + A3)/(6.0*dx)*d + A1;
+}
+
+/* max over E >= mass of E^A f0(E): the common part of estimate_ideal_maximum (A = 1),
+ * estimate_shear_viscous_maximum (A = 3) and estimate_diffusion_maximum (A = 2) */
+static double legacy_power_max(int A, int sign, double mass, double T, double mu, double f0_mass,
+                               const double *zx, const double *zy, int nz) {
+    const double inv_T = 1./T;
+    double massA = mass;
+    for (int i = 1; i < A; i++) massA *= mass;
+    if (sign == 1) {
+        double Emax = T*(legacy_lambertW(A*exp(inv_T*mu - A)) + A);
+        if (Emax < mass) Emax = mass;
+        double EA = Emax;
+        for (int i = 1; i < A; i++) EA *= Emax;
+        return EA/(exp((Emax - mu)*inv_T) + sign);
+    }
+    const double rhs = A*exp(inv_T*mu - A);
+    if (rhs > 0.3678794) return massA*f0_mass;
+    const double Emax = T*(A - z_map(zx, zy, nz, rhs));
+    if (Emax < mass) return massA*f0_mass;      /* also taken when the table look-up is NaN: no */
+    double EA = Emax;
+    for (int i = 1; i < A; i++) EA *= Emax;
+    const double g1 = EA/(exp((Emax - mu)*inv_T) + sign), g2 = massA*f0_mass;
+    return g1 > g2 ? g1 : g2;
+}
+
+double oracle_legacy_estimate_maximum(const float *c, const double *coef, const o_legacy_opt *o,
+                                      double mass, int sign, int degen, int baryon, int strange,
+                                      int charge, const double *zx, const double *zy, int nz) {
+    const double prefactor = 1.0/(8.0*(M_PI*M_PI*M_PI))/HBARC/HBARC/HBARC;
+    const double Tdec = c[L_T], inv_Tdec = 1.0/Tdec, Pdec = c[L_P], Edec = c[L_E];
+    const double mu = baryon*c[L_MUB] + strange*c[L_MUS] + charge*c[L_MUQ];  /* float arithmetic */
+    double bulkPi = 0.0;
+    if (o->include_bulk == 1) bulkPi = (o->bulk_kind == 0) ? (double)c[L_BULK] : c[L_BULK]/HBARC;
+    double prefactor_qmu = 0.0;
+    if (o->include_diff == 1) prefactor_qmu = (double)c[L_BN]/(Edec + Pdec);
+    const double u_dot_dsigma = (double)(c[L_TAU]*(c[L_U0]*c[L_DA0] + c[L_U1]*c[L_DA1] + c[L_U2]*c[L_DA2]
+                                                   + c[L_U3]*c[L_DA3]/c[L_TAU]));
+    const double dsigma_sq = (double)(c[L_TAU]*c[L_TAU]*(c[L_DA0]*c[L_DA0] - c[L_DA1]*c[L_DA1]
+                                      - c[L_DA2]*c[L_DA2] - c[L_DA3]*c[L_DA3]/(c[L_TAU]*c[L_TAU])));
+    const double dsigmaT = sqrt(fabs(dsigma_sq - u_dot_dsigma*u_dot_dsigma));
+    const double dsigma_all = fabs(u_dot_dsigma) + dsigmaT;
+    const double f0_mass = 1./(exp((mass - mu)*inv_Tdec) + sign);
+    const double guess_ideal = legacy_power_max(1, sign, mass, Tdec, mu, f0_mass, zx, zy, nz);
+    double guess_viscous = 0.0;
+    if (o->include_shear == 1) {
+        const double pi[10] = {c[L_PI00], c[L_PI01], c[L_PI02], c[L_PI03], c[L_PI11], c[L_PI12],
+                               c[L_PI13], c[L_PI22], c[L_PI23], c[L_PI33]};
+        const double trace_Pi2 = (pi[0]*pi[0] + pi[4]*pi[4] + pi[7]*pi[7] + pi[9]*pi[9]
+                                  - 2.*pi[1]*pi[1] - 2.*pi[2]*pi[2] - 2.*pi[3]*pi[3]
+                                  + 2.*pi[5]*pi[5] + 2.*pi[6]*pi[6] + 2.*pi[8]*pi[8]);
+        const double pi_size = sqrt(trace_Pi2)/(Edec + Pdec);
+        const double tmp_factor = (sign == -1) ? 2.0 : 1.0;
+        guess_viscous = legacy_power_max(3, sign, mass, Tdec, mu, f0_mass, zx, zy, nz)
+                        *(tmp_factor/(2.0*Tdec*Tdec)*pi_size);
+    }
+    double guess_bulk = 0.0;
+    if (o->include_bulk == 1)
+        guess_bulk = fabs(bulkPi*coef[0])*mass*mass*inv_Tdec/3.*f0_mass*(1. - sign*f0_mass);
+    double guess_qmu = 0.0;
+    if (o->include_diff == 1) {
+        const float q[4] = {c[L_Q0], c[L_Q1], c[L_Q2], c[L_Q3]};         /* Vec4 is float */
+        const double qmu_sq = q[0]*q[0] - q[1]*q[1] - q[2]*q[2] - q[3]*q[3];
+        const double q_size = sqrt(fabs(qmu_sq))/coef[3];
+        guess_qmu = prefactor_qmu*legacy_power_max(2, sign, mass, Tdec, mu, f0_mass, zx, zy, nz);
+        if (baryon > 0) guess_qmu += baryon*guess_ideal;
+        guess_qmu *= ((sign == -1) ? 2.0 : 1.0)*q_size;
+    }
+    return prefactor*degen*dsigma_all*(guess_ideal + guess_viscous + guess_bulk + guess_qmu);
+}
+
+static double legacy_deltaf_bulk(const o_legacy_opt *o, double mass, double pdotu, double bulkPi,
+                                 double Tdec, int sign, double f0, const double *bc) {
+    if (o->include_bulk == 0) return 0.0;       /* get_deltaf_bulk, :4156-4186 */
+    const double stat = 1. - sign*f0;
+    if (o->bulk_kind == 0) {
+        return -stat*bulkPi*(bc[0]*mass*mass + bc[1]*pdotu + bc[2]*pdotu*pdotu);
+    } else if (o->bulk_kind == 1) {
+        const double E_over_T = pdotu/Tdec, mass_over_T = mass/Tdec;
+        return -1.0*stat*bc[0]*(mass_over_T*mass_over_T/(3.*E_over_T) - bc[1]*E_over_T)*bulkPi;
+    } else if (o->bulk_kind == 2) {
+        const double E_over_T = pdotu/Tdec;
+        return -1.*stat*bulkPi*(-bc[0] + bc[1]*E_over_T);
+    } else if (o->bulk_kind == 3) {
+        const double E_over_T = pdotu/Tdec;
+        return -1.*stat*bulkPi/sqrt(E_over_T)*(-bc[0] + bc[1]*E_over_T);
+    } else if (o->bulk_kind == 4) {
+        const double E_over_T = pdotu/Tdec;
+        return -1.*stat*bulkPi*(bc[0] - bc[1]/E_over_T);
+    }
+    return 0.0;
+}
+
+/* EmissionFunctionArray::sample_momemtum_from_a_fluid_cell (:4188-4306): 1 on accept, 0 after
+ * 4999 rejected tries.  One Philox block per try: w0 -> pT^2, w1 -> phi, w2 -> y - eta_s,
+ * w3 -> accept (32-bit uniforms). */
+static int legacy_sample_in_cell(const float *c, const double *coef, const o_legacy_opt *o,
+                                 double mass, double degen, int sign, int baryon, int strange,
+                                 int charge, double maximum_guess, o_stream *rng, int *ntries,
+                                 double *pT_out, double *phi_out, double *yme_out) {
+    const double Tdec = c[L_T];
+    const double mu = baryon*c[L_MUB] + strange*c[L_MUS] + charge*c[L_MUQ];
+    const double inv_Tdec = 1./Tdec;
+    const double prefactor = 1.0/(8.0*(M_PI*M_PI*M_PI)*(HBARC*HBARC*HBARC));
+    const double deltaf_prefactor = 1.0/(2.0*Tdec*Tdec*(c[L_E] + c[L_P]));
+    const double prefactor_qmu = c[L_BN]/(c[L_E] + c[L_P]);
+    int tries = 1;
+    while (tries < 5000) {
+        uint32_t w[4];
+        stream_block(rng, w);
+        (*ntries)++;
+        const double pT = sqrt(o->pT_to*o->pT_to*w32(w[0]));
+        const double phi = 2*M_PI*w32(w[1]);
+        const double yme = (1. - 2.*w32(w[2]))*o->y_minus_eta_s_range;
+        const double mT = sqrt(mass*mass + pT*pT);
+        const double px = pT*cos(phi), py = pT*sin(phi);
+        const double p0 = mT*cosh(yme), p3 = mT*sinh(yme);
+        const double pdotu = p0*c[L_U0] - px*c[L_U1] - py*c[L_U2] - p3*c[L_U3];
+        const double expon = (pdotu - mu)*inv_Tdec;
+        const double f0 = 1./(exp(expon) + sign);
+        const double pdsigma = p0*c[L_DA0] + px*c[L_DA1] + py*c[L_DA2] + p3*c[L_DA3]/c[L_TAU];
+        double delta_f_shear = 0.;
+        if (o->include_shear == 1) {
+            const double Wfactor = (p0*p0*c[L_PI00] - 2.0*p0*px*c[L_PI01] - 2.0*p0*py*c[L_PI02]
+                                    - 2.0*p0*p3*c[L_PI03] + px*px*c[L_PI11] + 2.0*px*py*c[L_PI12]
+                                    + 2.0*px*p3*c[L_PI13] + py*py*c[L_PI22] + 2.0*py*p3*c[L_PI23]
+                                    + p3*p3*c[L_PI33]);
+            delta_f_shear = (1. - sign*f0)*Wfactor*deltaf_prefactor;
+        }
+        double delta_f_bulk = 0.;
+        if (o->include_bulk == 1)
+            delta_f_bulk = legacy_deltaf_bulk(o, mass, pdotu, c[L_BULK]/HBARC, Tdec, sign, f0, coef);
+        double delta_f_qmu = 0.0;
+        if (o->include_diff == 1) {
+            const double qmufactor = p0*c[L_Q0] - px*c[L_Q1] - py*c[L_Q2] - p3*c[L_Q3];
+            delta_f_qmu = (1. - sign*f0)*(prefactor_qmu - baryon/pdotu)*qmufactor/coef[3];
+        }
+        double resize_factor = 1.0;
+        if (o->restrict_deltaf == 1) {
+            const double deltaf_size = fabs(delta_f_shear + delta_f_bulk + delta_f_qmu);
+            resize_factor = fmin(1., o->deltaf_max_ratio/(deltaf_size + 1e-10));
+        }
+        const double result = prefactor*degen*f0*pdsigma*c[L_TAU]
+                              *(1. + (delta_f_shear + delta_f_bulk + delta_f_qmu)*resize_factor);
+        const double accept_prob = result/(1.0*maximum_guess);
+        if (w32(w[3]) < accept_prob) {
+            *pT_out = pT; *phi_out = phi; *yme_out = yme;
+            return 1;
+        }
+        tries++;
+    }
+    return 0;
+}
+
+/* event/species/particle loops of sample_using_dN_dxtdy_4all_particles_conventional (:3330-3560)
+ * with the engine's stream keying (as oracle_sample above): stream (seed; SAMPLE, s, ev, k),
+ * block order  cell | tries (one block each) | after 4999 rejections: new cell | boost-invariant:
+ * rapidity.  yields [ns][ncell] may be negative (the reference does not clamp them; the CDF does,
+ * RandomVariable1DArray.cpp:38-50).  cdf_in (may be NULL): [ns][ncell+1] prefix to use instead of
+ * the sequential one (the engine's fixed-order prefix).  max_out (may be NULL): maximum_guess used
+ * for every hadron.  Returns the number of hadrons, -1 on capacity, -3 if a maximum is NaN (the
+ * reference exit(1)s in the z_exp_m_z look-up). */
+int64_t oracle_legacy_sample(const float *lab, const float *pos, int64_t ncell,
+                             const double *coef /*[ncell][4]*/, const double *yields,
+                             const double *cdf_in, const o_species *sp, int ns,
+                             const o_legacy_opt *o, const double *zx, const double *zy, int nz,
+                             uint64_t seed, int64_t ev_begin, int64_t nev, const int64_t *mult,
+                             o_hadron *out, int64_t cap, int32_t *out_cell, int32_t *out_tries) {
+    double *cdf = NULL;
+    if (!cdf_in) {
+        cdf = malloc(sizeof(double)*(size_t)ns*(ncell + 1));
+        for (int s = 0; s < ns; s++) {
+            double *c = cdf + (size_t)s*(ncell + 1);
+            c[0] = 0.;
+            for (int64_t l = 0; l < ncell; l++) c[l + 1] = c[l] + fmax(yields[(size_t)s*ncell + l], 0.);
+        }
+        cdf_in = cdf;
+    }
+    int64_t n = 0;
+    for (int64_t ev = 0; ev < nev; ev++)
+        for (int s = 0; s < ns; s++) {
+            const o_species *p = &sp[s];
+            const int64_t N = mult[ev*ns + s];
+            for (int64_t k = 0; k < N; k++) {
+                o_stream rng;
+                stream_init(&rng, seed, STREAM_SAMPLE, (uint32_t)s, (uint32_t)(ev_begin + ev), (uint32_t)k);
+                int ntries = 0;
+                double pT = 0, phi = 0, yme = 0;
+                int64_t cell;
+                for (;;) {
+                    uint32_t w[4];
+                    stream_block(&rng, w);
+                    cell = pick_cell(cdf_in + (size_t)s*(ncell + 1), ncell, w53(w[0], w[1]));
+                    const float *c = lab + cell*L_NFIELD;
+                    const double mx = oracle_legacy_estimate_maximum(c, coef + cell*4, o, p->mass,
+                        p->sign, p->gspin, p->baryon, p->strange, p->charge, zx, zy, nz);
+                    if (isnan(mx)) { free(cdf); return -3; }
+                    if (legacy_sample_in_cell(c, coef + cell*4, o, p->mass, (double)p->gspin, p->sign,
+                                              p->baryon, p->strange, p->charge, mx, &rng, &ntries,
+                                              &pT, &phi, &yme))
+                        break;
+                }
+                const float *c = lab + cell*L_NFIELD;
+                double eta_s = pos[cell*4 + 2];
+                if (o->boost_invariant) {
+                    uint32_t w[4];
+                    stream_block(&rng, w);
+                    const double rap = o->y_LB + (o->y_RB - o->y_LB)*w32(w[0]);
+                    eta_s = rap - yme;
+                }
+                if (n >= cap) { free(cdf); return -1; }
+                {   /* add_one_sampled_particle, :4423-4475 */
+                    o_hadron *h = &out[n];
+                    const double y = yme + eta_s;
+                    const double mT = sqrt(p->mass*p->mass + pT*pT);
+                    h->pid = p->pid;
+                    h->mass = p->mass;
+                    h->E = mT*cosh(y);
+                    h->px = pT*cos(phi);
+                    h->py = pT*sin(phi);
+                    h->pz = mT*sinh(y);
+                    h->t = c[L_TAU]*cosh(eta_s);
+                    h->x = pos[cell*4 + 0];
+                    h->y = pos[cell*4 + 1];
+                    h->z = c[L_TAU]*sinh(eta_s);
+                }
+                if (out_cell) { out_cell[n] = (int32_t)cell; out_tries[n] = ntries; }
+                n++;
+            }
+        }
+    free(cdf);
+    return n;
+}

@@ -279,6 +279,88 @@ static int run_spectra(int argc, char **argv) {
     return 0;
 }
 
+// ref_driver legacy <param_file> <work_path> <surface_file> <out_prefix> [key=value ...]
+//   MC_sampling is forced to 2 (EmissionFunctionArray "conventional" sampler,
+//   emissionfunction.cpp:3273-3623).  Dumps what that path computes before it draws anything:
+//   -> <out_prefix>.lab.bin     int64 ncell, ncell x 32 float32 (ISS_L_* order as in `spectra`)
+//      <out_prefix>.pos.bin     ncell x 4 float32: xpt, ypt, eta, 0
+//      <out_prefix>.species.txt sampling order (chosen_particles_sampling_table):
+//                               monval mass gspin baryon strange charge sign
+//      <out_prefix>.yields.bin  int64 ns, ncell, then ns x ncell float64 = dN_dxtdy_for_one_particle_species
+//                               (calculate_dN_dxtdy_for_one_particle_species, :2977-3097; NOT clamped)
+//      <out_prefix>.max.bin     ns x ncell float64 = estimate_maximum (:4309-4421)
+static int run_legacy(int argc, char **argv) {
+    if (argc < 6) { std::cerr << "usage: legacy param path surface out_prefix [k=v]\n"; return 2; }
+    std::string param = argv[2], path = argv[3], surface = argv[4], out = argv[5];
+    iSS sampler(path, "iSS_tables", "iSS_tables", param, surface);
+    for (int i = 6; i < argc; i++) sampler.paraRdr_ptr->phraseOneLine(argv[i]);
+    sampler.paraRdr_ptr->setVal("MC_sampling", 2);
+    sampler.read_in_FO_surface();
+    sampler.set_random_seed(1);
+    {
+        FILE *f = fopen((out + ".lab.bin").c_str(), "wb");
+        FILE *g = fopen((out + ".pos.bin").c_str(), "wb");
+        int64_t n = sampler.FOsurf_array_.size();
+        fwrite(&n, sizeof(n), 1, f);
+        for (auto const &c : sampler.FOsurf_array_) {
+            float rec[32] = {c.tau, c.u0, c.u1, c.u2, c.u3, c.da0, c.da1, c.da2, c.da3,
+                             c.Tdec, c.Pdec, c.Edec, c.muB, c.muS, c.muQ,
+                             c.pi00, c.pi01, c.pi02, c.pi03, c.pi11, c.pi12, c.pi13, c.pi22, c.pi23,
+                             c.pi33, c.bulkPi, c.Bn, c.qmu0, c.qmu1, c.qmu2, c.qmu3, 0.f};
+            fwrite(rec, sizeof(float), 32, f);
+            float pos[4] = {c.xpt, c.ypt, c.eta, 0.f};
+            fwrite(pos, sizeof(float), 4, g);
+        }
+        fclose(f);
+        fclose(g);
+    }
+    Table chosen_particles;
+    if (sampler.afterburner_type_ == AfterburnerType::SMASH) {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_SMASH.dat");
+    } else if (sampler.afterburner_type_ == AfterburnerType::UrQMD) {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_urqmd_v3.3+.dat");
+    } else {
+        chosen_particles.loadTableFromFile("iSS_tables/chosen_particles_s95p-v1.dat");
+    }
+    Table pT_tab("iSS_tables/bin_tables/pT_gauss_table.dat");
+    Table phi_tab("iSS_tables/bin_tables/phi_gauss_table.dat");
+    Table eta_tab("iSS_tables/bin_tables/eta_uni_table.dat");
+    EmissionFunctionArray efa(sampler.ran_gen_ptr_, &chosen_particles, &pT_tab, &phi_tab, &eta_tab,
+                              sampler.particle_, sampler.FOsurf_array_, sampler.flag_PCE_,
+                              sampler.paraRdr_ptr, path, "iSS_tables", sampler.afterburner_type_);
+    TableFunction z_exp_m_z(std::string("iSS_tables/z_exp_m_z.dat"));
+    z_exp_m_z.interpolation_model = 5;
+    const int64_t ns = efa.number_of_chosen_particles, nc = efa.FO_length;
+    std::ofstream sp(out + ".species.txt");
+    sp << std::setprecision(17);
+    FILE *fy = fopen((out + ".yields.bin").c_str(), "wb");
+    FILE *fm = fopen((out + ".max.bin").c_str(), "wb");
+    int64_t hdr[2] = {ns, nc};
+    fwrite(hdr, sizeof(int64_t), 2, fy);
+    std::vector<double> mx(nc);
+    for (int64_t n = 0; n < ns; n++) {
+        const int idx = efa.chosen_particles_sampling_table[n];
+        const particle_info &p = efa.particles[idx];
+        sp << p.monval << " " << p.mass << " " << p.gspin << " " << p.baryon << " "
+           << p.strange << " " << p.charge << " " << p.sign << "\n";
+        efa.calculate_dN_dxtdy_for_one_particle_species(idx);
+        fwrite(efa.dN_dxtdy_for_one_particle_species.data(), sizeof(double), nc, fy);
+        for (int64_t l = 0; l < nc; l++) {
+            const FO_surf *surf = &sampler.FOsurf_array_[l];
+            std::array<double, 3> bulk = {0.0};
+            if (efa.INCLUDE_BULK_DELTAF == 1) efa.getbulkvisCoefficients(surf->Tdec, bulk);
+            double kq = 1.0;
+            if (efa.INCLUDE_DIFFUSION_DELTAF == 1) kq = efa.get_deltaf_qmu_coeff(surf->Tdec, surf->muB);
+            mx[l] = efa.estimate_maximum(surf, idx, p.mass, p.sign, p.gspin, p.baryon, p.strange,
+                                         p.charge, z_exp_m_z, bulk, kq);
+        }
+        fwrite(mx.data(), sizeof(double), nc, fm);
+    }
+    fclose(fy);
+    fclose(fm);
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) { std::cerr << "usage: ref_driver yields|momentum|decay ...\n"; return 2; }
     std::string mode = argv[1];
@@ -287,6 +369,7 @@ int main(int argc, char **argv) {
     if (mode == "decay") return run_decay(argc, argv);
     if (mode == "writers") return run_writers(argc, argv);
     if (mode == "spectra") return run_spectra(argc, argv);
+    if (mode == "legacy") return run_legacy(argc, argv);
     std::cerr << "unknown mode " << mode << "\n";
     return 2;
 }

@@ -3,7 +3,7 @@
 (compiled by oracle/Makefile into oracle/_ref/) in THIS container.  The fixtures travel to the
 GPU box; /root/reference does not.
 
-    python tests/golden/make_golden.py [yields] [stats] [momentum] [decay] [writers] [spectra]
+    python tests/golden/make_golden.py [yields] [stats] [momentum] [decay] [writers] [spectra] [legacy]
 
 yields   : per-cell x per-species yields (FSSW::calculate_dN_dxtdy_for_one_particle_species)
            + the reference's local-rest-frame surface + species order, for the six runnable
@@ -12,6 +12,9 @@ stats    : histograms (tests/obs.py) of particle_samples.bin written by the refe
            sampler (iSS.e) with fixed seeds, >= 10^4 events each.
 momentum : |p| samples of MomentumSamplerShell::Sample_a_momentum reduced to histograms.
 decay    : daughters of particle_decay::perform_decays for a few resonances.
+legacy   : the MC_sampling = 2 path (EmissionFunctionArray "conventional" sampler): lab-frame cells,
+           per-cell yields and estimate_maximum values (ref_driver legacy) and histograms of the
+           reference's own samples.
 spectra  : dN/(pT dpT dphi dy) tables of EmissionFunctionArray::calculate_dN_pTdpTdphidy and the
            flow tables of calculate_flows for a few species on small synthetic surfaces, with the
            lab-frame cells the reference used.
@@ -185,6 +188,99 @@ def golden_stats(only=None):
         s = obs.summarize(rec, off)
         np.savez_compressed(os.path.join(HERE, "stats_%s.npz" % name), param=spec["param"],
                             overrides=np.array(spec["over"]), music=str(spec["music"]), **extra, **s)
+        print(name, "events", len(off) - 1, "hadrons", len(rec))
+        shutil.rmtree(d)
+
+
+
+# ---- legacy "conventional" sampler (MC_sampling = 2, EmissionFunctionArray) ---------------------
+LEGACY_COMMON = ["MC_sampling=2", "store_samples_in_memory=1", "output_samples_into_files=0"]
+LEGACY = {
+    "l3d_shear": dict(gen=dict(ncell=60, seed=31, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                      over=["include_deltaf_shear=1", "include_deltaf_bulk=0", "bulk_deltaf_kind=1"]),
+    "l3d_bulk1_diff": dict(gen=dict(ncell=60, seed=32, eos=14, rhob=1, diffusion=1, binary=1),
+                           param="iSS_parameters_CEdeltaf.dat",
+                           over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=1",
+                                 "include_deltaf_diffusion=1", "restrict_deltaf=1"]),
+    "l2d_ideal_smash": dict(gen=dict(ncell=60, seed=33, eos=91, boost_invariant=True),
+                            param="iSS_parameters_ideal.dat",
+                            over=["hydro_mode=1", "bulk_deltaf_kind=1", "grouping_particles=0"]),
+}
+LEGACY_STATS = {
+    # one moving cell with shear stress (Viscous2 fixture, volume scaled down), UrQMD list
+    "cell_shear": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=11,
+                       cell="testViscousOneFluidCell2.dat", scale=0.002,
+                       over=["include_deltaf_shear=1", "include_deltaf_bulk=0", "bulk_deltaf_kind=1"]),
+    "surf3d_bulk1": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=12,
+                         gen=dict(ncell=300, seed=2025, eos=14, rhob=1, diffusion=1, binary=1),
+                         over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=1",
+                               "include_deltaf_diffusion=1", "restrict_deltaf=1"]),
+}
+
+
+def golden_legacy(only=None):
+    for name, spec in LEGACY.items():
+        if only and name not in only:
+            continue
+        d = workdir()
+        case = os.path.join(d, "case")
+        os.makedirs(case)
+        cells = synthetic.make_case(case, **spec["gen"])
+        over = LEGACY_COMMON + spec["over"]
+        run([os.path.join(REF, "ref_driver"), "legacy", os.path.join(FIX, spec["param"]), "case",
+             "surface.dat", os.path.join(d, "out")] + over, d, os.path.join(d, "log"))
+        pre = os.path.join(d, "out")
+        with open(pre + ".lab.bin", "rb") as f:
+            n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+            lab = np.fromfile(f, dtype=np.float32).reshape(n, 32)
+        pos = np.fromfile(pre + ".pos.bin", dtype=np.float32).reshape(n, 4)
+        sp = np.loadtxt(pre + ".species.txt", ndmin=2)
+        with open(pre + ".yields.bin", "rb") as f:
+            ns, nc = np.fromfile(f, dtype=np.int64, count=2)
+            y = np.fromfile(f, dtype=np.float64).reshape(int(ns), int(nc))
+        mx = np.fromfile(pre + ".max.bin", dtype=np.float64).reshape(int(ns), int(nc))
+        np.savez_compressed(os.path.join(HERE, "legacy_%s.npz" % name), param=spec["param"],
+                            overrides=np.array(over), cells=cells,
+                            gen=np.array(sorted(spec["gen"].items()), dtype=object).astype(str),
+                            lab=lab, pos=pos, species=sp, yields=y, maximum=mx)
+        print(name, "cells", n, "species", int(ns), "sum", y.clip(0).sum())
+        shutil.rmtree(d)
+    for name, spec in LEGACY_STATS.items():
+        if only and name not in only:
+            continue
+        d = workdir()
+        case = os.path.join(d, "case")
+        os.makedirs(case)
+        extra = {}
+        if spec["music"] is not None:
+            shutil.copy(os.path.join(FIX, "music_input_" + spec["music"]),
+                        os.path.join(case, "music_input"))
+            v = small_cell(spec["cell"], spec["scale"])
+            np.savetxt(os.path.join(case, "surface.dat"), v[None, :], fmt="%.16e")
+            extra["cell_line"] = v
+        else:
+            extra["cells"] = synthetic.make_case(case, **spec["gen"])
+            extra["gen"] = np.array(sorted(spec["gen"].items()), dtype=object).astype(str)
+        over = LEGACY_COMMON + spec["over"]
+        run_over = ["number_of_repeated_sampling=%d" % spec["nev"], "randomSeed=%d" % spec["seed"],
+                    "use_OSCAR_format=0", "use_gzip_format=0", "use_binary_format=1",
+                    "perform_checks=0"] + over
+        run([os.path.join(REF, "iSS.e"), os.path.join(FIX, spec["param"]), "case", "surface.dat"]
+            + run_over, d, os.path.join(d, "log"))
+        rec, off = obs.read_reference_bin(os.path.join(d, "particle_samples.bin"))
+        s_ = obs.summarize(rec, off)
+        # the lab-frame cells and the species order the reference sampled from
+        run([os.path.join(REF, "ref_driver"), "legacy", os.path.join(FIX, spec["param"]), "case",
+             "surface.dat", os.path.join(d, "out")] + over, d, os.path.join(d, "log2"))
+        pre = os.path.join(d, "out")
+        with open(pre + ".lab.bin", "rb") as f:
+            n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+            extra["lab"] = np.fromfile(f, dtype=np.float32).reshape(n, 32)
+        extra["pos"] = np.fromfile(pre + ".pos.bin", dtype=np.float32).reshape(n, 4)
+        extra["species"] = np.loadtxt(pre + ".species.txt", ndmin=2)
+        np.savez_compressed(os.path.join(HERE, "legacy_stats_%s.npz" % name), param=spec["param"],
+                            overrides=np.array(over), music=str(spec["music"]),
+                            **extra, **s_)
         print(name, "events", len(off) - 1, "hadrons", len(rec))
         shutil.rmtree(d)
 
@@ -405,3 +501,5 @@ if __name__ == "__main__":
         golden_stats([w for w in what if w in STATS] or None)
     if "writers" in what:
         golden_writers()
+    if "legacy" in what:
+        golden_legacy([w for w in what if w in LEGACY or w in LEGACY_STATS] or None)

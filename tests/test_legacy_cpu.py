@@ -1,0 +1,79 @@
+"""Pins the CPU restatement of the reference's legacy sampler (MC_sampling = 2,
+EmissionFunctionArray::sample_using_dN_dxtdy_4all_particles_conventional,
+src/emissionfunction.cpp:3273-3623; oracle/legacy_oracle.py + oracle/iss_oracle.c) against the
+compiled reference: per-cell yields and estimate_maximum values dumped by oracle/ref_driver.cpp
+(tests/golden/legacy_*.npz) and the spectra of the reference's own samples
+(tests/golden/legacy_stats_*.npz)."""
+import numpy as np
+import pytest
+from scipy import special, stats
+
+import cases
+import legacy_cases as lc
+import obs
+from legacy_cases import lgo, orc
+
+
+def test_lambert_w_known_answers():
+    lib = orc.clib()
+    import ctypes as C
+    lib.oracle_lambert_w0.restype = C.c_double
+    for x in (0.0, 1e-6, 0.1, 1.0, np.e, 10.0, 150.0):
+        w = lib.oracle_lambert_w0(C.c_double(x))
+        assert abs(w - special.lambertw(x).real) <= 1e-14*(1 + abs(w))
+    assert abs(lib.oracle_lambert_w0(C.c_double(np.e)) - 1.0) < 1e-15
+
+
+@pytest.mark.parametrize("name", lc.YIELD_CASES)
+def test_oracle_yields_and_maxima_match_reference(name):
+    g = cases.load(name, "legacy")
+    par = lc.parameters(g)
+    opt = lc.oracle_options(par)
+    sp = lc.species_array(g["species"])
+    coef = lgo.cell_coefficients(g["lab"], opt, lgo.load_kappa())
+    y = lgo.yields(g["lab"], sp, opt, coef)
+    ref = g["yields"]
+    assert (ref < 0).any()          # the legacy yields are not clamped (cells with u.dsigma < 0)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert (np.abs(y - ref)/scale).max() < 1e-12
+    mx = lgo.estimate_maximum(g["lab"], coef, sp, opt, lgo.load_z_table())
+    assert not np.isnan(mx).any()
+    assert np.allclose(mx, g["maximum"], rtol=1e-12, atol=0)
+
+
+def test_oracle_sampler_matches_reference_sampler(tmp_path):
+    """chi2 of pT / y / phi spectra of the restated sampler against the reference's own samples
+    (10^4 events); acceptance as in tests/test_stats_gpu.py."""
+    name = "cell_shear"
+    g = cases.load(name, "legacy_stats")
+    par = lc.parameters(g)
+    opt = lc.oracle_options(par)
+    lab, pos, sp = g["lab"], g["pos"], lc.species_array(g["species"])
+    coef = lgo.cell_coefficients(lab, opt, lgo.load_kappa())
+    y = lgo.yields(lab, sp, opt, coef)
+    dN = np.maximum(y, 0).sum(axis=1)
+    if opt.boost_invariant:
+        dN = dN*(opt.y_RB - opt.y_LB)
+    nev, nev_ref = 4000, int(g["nev"])
+    mult, _ = orc.multiplicities(dN, orc.poisson_pmode(dN), sp, nev, 0, 99)
+    h, cell, tries = lgo.sample(lab, pos, coef, y, sp, opt, lgo.load_z_table(), 99, 0, mult,
+                                mult.sum() + 8)
+    assert len(h) == mult.sum()
+    assert tries.mean() > 50            # the legacy sampler needs hundreds of tries per hadron
+    off = np.concatenate([[0], np.cumsum(mult.sum(axis=1))])
+    mine = obs.summarize(h, off)
+    tot_chi2, tot_ndf, worst = 0.0, 0, (1.0, "")
+    for pid in obs.PIDS:
+        tag = "p%d" % pid if pid > 0 else "m%d" % (-pid)
+        for kind in ("pt", "y", "phi"):
+            chi2, ndf = obs.chi2_two_hist(mine[tag + "_" + kind], g[tag + "_" + kind], nev, nev_ref)
+            if ndf == 0:
+                continue
+            p = stats.chi2.sf(chi2, ndf)
+            tot_chi2 += chi2
+            tot_ndf += ndf
+            if p < worst[0]:
+                worst = (p, tag + "_" + kind)
+    assert worst[0] > 1e-4, worst
+    assert tot_ndf > 100
+    assert stats.chi2.sf(tot_chi2, tot_ndf) > 0.01, (tot_chi2, tot_ndf)

@@ -1,0 +1,125 @@
+"""GPU parity of the legacy "conventional" sampler (MC_sampling = 2,
+EmissionFunctionArray::sample_using_dN_dxtdy_4all_particles_conventional,
+src/emissionfunction.cpp:3273-3623) through the C ABI (iss_cuda_legacy_*):
+
+  - per-cell x per-species yields and estimate_maximum values against dumps of the compiled
+    reference (tests/golden/legacy_*.npz): 1e-10 of the species' largest yield (north_star asks
+    1e-6), maxima at 1e-9 relative;
+  - hadron by hadron against the CPU restatement (oracle/iss_oracle.c: oracle_legacy_sample) driven
+    by the same Philox streams: chosen cells and numbers of tries bit-exact, records within 4
+    float32 ulp (two maths libraries);
+  - spectra against the reference's own MC_sampling = 2 samples (chi2, >= 10^4 reference events)."""
+import numpy as np
+import pytest
+from scipy import stats
+
+import cases
+import legacy_cases as lc
+import obs
+import spectra_cases as sc
+from legacy_cases import lgo, orc
+from test_sampler_gpu import compare_hadrons
+
+pytestmark = pytest.mark.gpu
+
+
+def make_engine(capi, g, par):
+    e = capi.Engine(0)
+    sp = lc.species_array(g["species"])
+    e.upload_species(sp)
+    if int(par["include_deltaf_diffusion"]) == 1:
+        e.upload_table(capi.TABLE_KAPPA_B, sc.kappa_table(), 150, 100, [0.05, 0.001, 0.0, 0.007892])
+    e.set_options(hydro_mode=int(par["hydro_mode"]), y_LB=par["y_lb"], y_RB=par["y_rb"],
+                  dN_dy_sampling_model=30)
+    e.legacy_setup(g["lab"], g["pos"], lgo.load_z_table(), **lc.engine_options(par))
+    return e, sp
+
+
+@pytest.mark.parametrize("name", lc.YIELD_CASES)
+def test_legacy_yields_and_maxima_match_reference(name, built):
+    capi = built
+    g = cases.load(name, "legacy")
+    par = lc.parameters(g)
+    e, sp = make_engine(capi, g, par)
+    try:
+        dN, y, mx = e.legacy_compute_yields(want_cells=True, want_maximum=True)
+        ref = g["yields"]
+        scale = np.abs(ref).max(axis=1, keepdims=True)
+        assert (np.abs(y - ref)/scale).max() < 1e-10
+        assert np.allclose(dN, np.maximum(ref, 0).sum(axis=1), rtol=1e-10, atol=1e-300)
+        assert np.allclose(mx, g["maximum"], rtol=1e-9, atol=0)
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("name,nev", [("l3d_shear", 300), ("l3d_bulk1_diff", 300),
+                                      ("l2d_ideal_smash", 40)])
+def test_legacy_hadrons_match_oracle(name, nev, built):
+    capi = built
+    g = cases.load(name, "legacy")
+    par = lc.parameters(g)
+    e, sp = make_engine(capi, g, par)
+    try:
+        dN, y, _ = e.legacy_compute_yields(want_cells=True)
+        e.set_trace(True)
+        seed, ev0 = 987654321, 3
+        cnt = e.sample(seed, ev0, ev0 + nev)
+        mult = e.multiplicities(nev)
+        off = e.event_offsets(nev)
+        had = e.fetch_all()
+        cell, tries = e.get_trace(len(had))
+        lam, pm = e.poisson_params()
+        boost_inv = int(par["hydro_mode"]) != 2
+        assert np.array_equal(lam, dN*(par["y_rb"] - par["y_lb"]) if boost_inv else dN)
+        omult, ocount = orc.multiplicities(lam, pm, sp, nev, ev0, seed)
+        assert np.array_equal(mult, omult)
+        assert np.array_equal(off, np.concatenate([[0], np.cumsum(ocount.sum(axis=1))]))
+        assert cnt.n_hadrons == ocount.sum() == len(had) > 300
+
+        opt = lc.oracle_options(par)
+        coef = lgo.cell_coefficients(g["lab"], opt, lgo.load_kappa())
+        ohad, ocell, otries = lgo.sample(g["lab"], g["pos"], coef, y, sp, opt, lgo.load_z_table(),
+                                         seed, ev0, omult, ocount.sum() + 8)
+        assert len(ohad) == len(had)
+        same_path = (cell == ocell) & (tries == otries)
+        assert same_path.mean() >= 1 - 2e-3, "paths differ for %d of %d" % ((~same_path).sum(), len(had))
+        ident, close = compare_hadrons(had[same_path], ohad[same_path])
+        assert close.all(), "%d hadrons differ beyond 4 ulp" % (~close).sum()
+        assert ident.mean() >= 0.80, ident.mean()
+        assert tries.mean() > 50
+        assert abs(cnt.n_tries - otries.sum()) <= 10 + 20000*(~same_path).sum()
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("name", lc.STATS_CASES)
+def test_legacy_spectra_match_reference_sampler(name, built):
+    capi = built
+    g = cases.load(name, "legacy_stats")
+    par = lc.parameters(g)
+    e, sp = make_engine(capi, g, par)
+    try:
+        e.legacy_compute_yields()
+        nev_ref = int(g["nev"])
+        nev = nev_ref
+        e.sample(4242, 0, nev)
+        off = e.event_offsets(nev)
+        had = e.fetch_all()
+        mine = obs.summarize(had, off)
+    finally:
+        e.close()
+    tot_chi2, tot_ndf, worst = 0.0, 0, (1.0, "")
+    for pid in obs.PIDS:
+        tag = "p%d" % pid if pid > 0 else "m%d" % (-pid)
+        for kind in ("pt", "y", "phi"):
+            chi2, ndf = obs.chi2_two_hist(mine[tag + "_" + kind], g[tag + "_" + kind], nev, nev_ref)
+            if ndf == 0:
+                continue
+            p = stats.chi2.sf(chi2, ndf)
+            tot_chi2 += chi2
+            tot_ndf += ndf
+            if p < worst[0]:
+                worst = (p, tag + "_" + kind)
+    assert worst[0] > 1e-4, worst
+    assert tot_ndf > 100
+    assert stats.chi2.sf(tot_chi2, tot_ndf) > 0.01, (tot_chi2, tot_ndf)
