@@ -217,6 +217,24 @@ GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
     : paraRdr_(paraRdr), path_(path), table_path_(table_path),
       afterburner_type_(afterburner_type), particles_(particles), surf_(FOsurf_LRF),
       packed_lrf_(packed_lrf), seed_(seed) {
+    init_(chosen_monvals, flag_PCE);
+}
+
+namespace {
+const std::vector<FO_surf_LRF> k_no_lrf_surface;
+}
+
+GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
+                 const std::vector<particle_info> &particles,
+                 const std::vector<FO_surf> &FOsurf_lab, int flag_PCE, ParameterReader *paraRdr,
+                 std::string path, std::string table_path, AfterburnerType afterburner_type)
+    : paraRdr_(paraRdr), path_(path), table_path_(table_path),
+      afterburner_type_(afterburner_type), particles_(particles), surf_(k_no_lrf_surface),
+      lab_surf_(&FOsurf_lab), legacy_(true), seed_(seed) {
+    init_(chosen_monvals, flag_PCE);
+}
+
+void GpuFSSW::init_(const std::vector<int> &chosen_monvals, int flag_PCE) {
     if (flag_PCE != 0) {
         iss_host::error("partial chemical equilibrium EoS is not supported by the B200 engine");
         exit(1);
@@ -236,13 +254,32 @@ GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
     (void)paraRdr_->getVal("output_samples_into_files");
     flag_perform_decays_ = (paraRdr_->getVal("perform_decays") == 1) ? 1 : 0;
     const int spectator_mode = static_cast<int>(paraRdr_->getVal("include_spectators", 0));
-    flag_spectators_ = (spectator_mode != 0) ? 1 : 0;
+    // spectators are an FSSW feature (FSSW.cpp:349-350); the legacy class has none
+    flag_spectators_ = (spectator_mode != 0 && !legacy_) ? 1 : 0;
     if (flag_spectators_) read_spectators_(path_ + "/spectators.dat");
+    if (legacy_) {
+        // what the legacy path of this engine does not cover is refused, not approximated
+        if (paraRdr_->getVal("output_samples_into_files") == 1) {
+            iss_host::error("MC_sampling = 2: output_samples_into_files = 1 (per-species samples_*.dat "
+                            "files) is not supported by the B200 engine; use store_samples_in_memory = 1");
+            exit(-1);
+        }
+        if (paraRdr_->getVal("store_samples_in_memory") != 1)
+            iss_host::warning("MC_sampling = 2: samples are always kept in memory by the B200 engine");
+        if (paraRdr_->getVal("local_charge_conservation") == 1) {
+            iss_host::error("MC_sampling = 2: local_charge_conservation is not supported by the B200 engine");
+            exit(-1);
+        }
+        if (include_bulk_ == 1 && bulk_kind_ == 0) {
+            iss_host::error("MC_sampling = 2: bulk_deltaf_kind = 0 is not supported by the B200 engine");
+            exit(-1);
+        }
+    }
 
     device_ = iss_pool::default_device();
     h_ = iss_pool::acquire_handle(device_);
     { PhaseTimer t("select_species"); select_species_(chosen_monvals); }
-    { PhaseTimer t("upload_surface"); upload_surface_(); }
+    { PhaseTimer t("upload_surface"); if (legacy_) upload_lab_surface_(); else upload_surface_(); }
     { PhaseTimer t("upload_tables"); upload_tables_(); }
     { PhaseTimer t("upload_decay_table"); upload_decay_table_(); }
 
@@ -265,6 +302,70 @@ GpuFSSW::GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
         exit(-1);
     }
     check_(iss_cuda_set_options(h_, &opt), "iss_cuda_set_options");
+    if (legacy_) {
+        iss_legacy_options lo;
+        memset(&lo, 0, sizeof(lo));
+        lo.include_deltaf_shear = include_shear_;
+        lo.include_deltaf_bulk = include_bulk_;
+        lo.bulk_deltaf_kind = bulk_kind_;
+        lo.include_deltaf_diffusion = include_diff_;
+        lo.restrict_deltaf = static_cast<int>(paraRdr_->getVal("restrict_deltaf"));
+        lo.deltaf_max_ratio = paraRdr_->getVal("deltaf_max_ratio");
+        // emissionfunction.cpp:3302-3306
+        double pT_to = paraRdr_->getVal("sample_pT_up_to");
+        if (pT_to < 0) {
+            const std::string pT_file = table_path_ + "/bin_tables/pT_gauss_table.dat";
+            const std::vector<double> &pT_tab = cached_numbers(pT_file, 0);
+            if (pT_tab.size() < 2) {
+                iss_host::error("Can not found file: " + pT_file);
+                exit(1);
+            }
+            pT_to = pT_tab[pT_tab.size() - 2];      // first column of the last row
+        }
+        lo.sample_pT_up_to = pT_to;
+        lo.sample_y_minus_eta_s_range = paraRdr_->getVal("sample_y_minus_eta_s_range");
+        // TableFunction z_exp_m_z (emissionfunction.cpp:3284-3287)
+        const std::string zfile = table_path_ + "/z_exp_m_z.dat";
+        const std::vector<double> &z = cached_numbers(zfile, 0);
+        if (z.size() < 8) {
+            iss_host::error("Can not found file: " + zfile);
+            exit(1);
+        }
+        std::vector<double> zx(z.size()/2), zy(z.size()/2);
+        for (size_t i = 0; i < zx.size(); i++) {
+            zx[i] = z[2*i];
+            zy[i] = z[2*i + 1];
+        }
+        check_(iss_cuda_legacy_upload_z_table(h_, zx.data(), zy.data(), static_cast<int>(zx.size())),
+               "iss_cuda_legacy_upload_z_table");
+        check_(iss_cuda_legacy_set_options(h_, &lo), "iss_cuda_legacy_set_options");
+    }
+}
+
+// FO_surf -> the ISS_L_* record of include/iss_cuda.h and the cell positions (legacy mode)
+void GpuFSSW::upload_lab_surface_() {
+    const std::vector<FO_surf> &surf = *lab_surf_;
+    const int64_t n = static_cast<int64_t>(surf.size());
+    std::vector<float> rec(static_cast<size_t>(n)*ISS_LAB_NFIELD), pos(static_cast<size_t>(n)*4);
+    for (int64_t l = 0; l < n; l++) {
+        const FO_surf &c = surf[l];
+        float *r = rec.data() + l*ISS_LAB_NFIELD;
+        r[ISS_L_TAU] = c.tau;
+        r[ISS_L_U0] = c.u0; r[ISS_L_U1] = c.u1; r[ISS_L_U2] = c.u2; r[ISS_L_U3] = c.u3;
+        r[ISS_L_DA0] = c.da0; r[ISS_L_DA1] = c.da1; r[ISS_L_DA2] = c.da2; r[ISS_L_DA3] = c.da3;
+        r[ISS_L_T] = c.Tdec; r[ISS_L_P] = c.Pdec; r[ISS_L_E] = c.Edec;
+        r[ISS_L_MUB] = c.muB; r[ISS_L_MUS] = c.muS; r[ISS_L_MUQ] = c.muQ;
+        r[ISS_L_PI00] = c.pi00; r[ISS_L_PI01] = c.pi01; r[ISS_L_PI02] = c.pi02; r[ISS_L_PI03] = c.pi03;
+        r[ISS_L_PI11] = c.pi11; r[ISS_L_PI12] = c.pi12; r[ISS_L_PI13] = c.pi13;
+        r[ISS_L_PI22] = c.pi22; r[ISS_L_PI23] = c.pi23; r[ISS_L_PI33] = c.pi33;
+        r[ISS_L_BULKPI] = c.bulkPi; r[ISS_L_BN] = c.Bn;
+        r[ISS_L_Q0] = c.qmu0; r[ISS_L_Q1] = c.qmu1; r[ISS_L_Q2] = c.qmu2; r[ISS_L_Q3] = c.qmu3;
+        r[ISS_L_SPARE] = 0.f;
+        float *q = pos.data() + l*4;
+        q[0] = c.xpt; q[1] = c.ypt; q[2] = c.eta; q[3] = 0.f;
+    }
+    check_(iss_cuda_upload_surface_lab(h_, rec.data(), n), "iss_cuda_upload_surface_lab");
+    check_(iss_cuda_legacy_upload_positions(h_, pos.data(), n), "iss_cuda_legacy_upload_positions");
 }
 
 GpuFSSW::~GpuFSSW() {
@@ -281,7 +382,8 @@ GpuFSSW::~GpuFSSW() {
 // chosen list -> indices into the pdg table, unknown ids dropped with a warning, then a stable
 // ascending sort by mass (the reference's bubble sort only swaps on strict >, FSSW.cpp:115-162)
 std::vector<int> GpuFSSW::order_species(const std::vector<int> &chosen_monvals,
-                                        const std::vector<particle_info> &particles) {
+                                        const std::vector<particle_info> &particles,
+                                        bool sort_by_mass) {
     std::vector<int> order, missing;
     for (int monval : chosen_monvals) {
         int found = -1;
@@ -301,13 +403,16 @@ std::vector<int> GpuFSSW::order_species(const std::vector<int> &chosen_monvals,
         iss_host::warning("Their monte carlo numbers are:");
         for (int m : missing) iss_host::warning(std::to_string(m));
     }
-    std::stable_sort(order.begin(), order.end(),
-                     [&](int a, int b) { return particles[a].mass < particles[b].mass; });
+    if (sort_by_mass)
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int a, int b) { return particles[a].mass < particles[b].mass; });
     return order;
 }
 
 void GpuFSSW::select_species_(const std::vector<int> &chosen_monvals) {
-    species_table_idx_ = order_species(chosen_monvals, particles_);
+    // the legacy class sorts only when grouping_particles is set (emissionfunction.cpp:190-206)
+    const bool sort_by_mass = !legacy_ || paraRdr_->getVal("grouping_particles") != 0;
+    species_table_idx_ = order_species(chosen_monvals, particles_, sort_by_mass);
     for (int idx : species_table_idx_) {
         const particle_info &p = particles_[idx];
         iss_species s;
@@ -378,7 +483,7 @@ void GpuFSSW::upload_surface_() {
 void GpuFSSW::upload_tables_() {
     const bool smash = (afterburner_type_ == AfterburnerType::SMASH);
     const std::string dir = table_path_ + "/deltaf_tables";
-    if (include_bulk_ == 1 && bulk_kind_ == 11) {
+    if (!legacy_ && include_bulk_ == 1 && bulk_kind_ == 11) {
         // c0.dat, c1.dat, c2.dat: "101", "81", one text header, then rows "T muB value" with T
         // running fastest.  All three files have THREE header lines; the reference skips only two
         // for c0 and ends up with an unfilled c0 table -- parsed correctly here.
@@ -414,7 +519,9 @@ void GpuFSSW::upload_tables_() {
         check_(iss_cuda_upload_table(h_, ISS_TABLE_MOM14, tab.data(), nT, nmu, grid),
                "iss_cuda_upload_table(14-moment)");
     }
-    if (bulk_kind_ == 21) {
+    if (legacy_) {
+        // the legacy class has polynomial bulk coefficients only (emissionfunction.cpp:3625-3762)
+    } else if (bulk_kind_ == 21) {
         const std::string file = dir + (smash ? "/smash" : "/urqmd") + "/NEoSBQS_CE_deltafCoeff.dat";
         const std::vector<double> &v = cached_numbers(file, 1);
         if (v.size() < 200u*200u*5u) {
@@ -545,7 +652,11 @@ void GpuFSSW::reserve_hadrons_(int64_t need) {
 void GpuFSSW::compute_yields() {
     PhaseTimer t("compute_yields");
     dN_species_.assign(species_.size(), 0.);
-    check_(iss_cuda_compute_yields(h_, dN_species_.data(), nullptr), "iss_cuda_compute_yields");
+    if (legacy_)
+        check_(iss_cuda_legacy_compute_yields(h_, dN_species_.data(), nullptr, nullptr),
+               "iss_cuda_legacy_compute_yields");
+    else
+        check_(iss_cuda_compute_yields(h_, dN_species_.data(), nullptr), "iss_cuda_compute_yields");
 }
 
 // FSSW::compute_number_of_sampling_needed (FSSW.cpp:851-869): uses pdg-table entry 1 as "pi+"
@@ -555,7 +666,8 @@ int GpuFSSW::compute_number_of_sampling_needed_(int number_of_particles_needed) 
         if (species_table_idx_[n] == 1) dNdy_thermal_pion = dN_species_[n];
     int nev = static_cast<int>(number_of_particles_needed/(6.*dNdy_thermal_pion));
     if (hydro_mode_ == 2) nev *= 10;
-    const int max_ev = static_cast<int>(paraRdr_->getVal("maximum_sampling_events"));
+    // the legacy class caps at 10000 events (emissionfunction.cpp:3268)
+    const int max_ev = legacy_ ? 10000 : static_cast<int>(paraRdr_->getVal("maximum_sampling_events"));
     return std::max(1, std::min(max_ev, nev));
 }
 
@@ -604,7 +716,9 @@ void GpuFSSW::sample_events() {
     if (const char *e = getenv("ISS_BATCHES")) min_batches = std::max(1, atoi(e));
     if (hadrons_total > 4e6) batch = std::min<int64_t>(batch, (nev_ + min_batches - 1)/min_batches);
     batch = std::max<int64_t>(1, std::min<int64_t>(batch, nev_));
-    const bool decays_on = flag_perform_decays_ && afterburner_type_ != AfterburnerType::SMASH;
+    // FSSW::shell skips the feed-down for SMASH (FSSW.cpp:346); EmissionFunctionArray::shell does
+    // not (emissionfunction.cpp:2570-2572)
+    const bool decays_on = flag_perform_decays_ && (legacy_ || afterburner_type_ != AfterburnerType::SMASH);
     if (decays_on) std::cout << "perform resonance decays... " << std::endl;
     const int32_t qa_pids[2] = {211, 2212};
     const int64_t nsp = static_cast<int64_t>(spectators_.size());
@@ -671,7 +785,7 @@ void GpuFSSW::shell() {
     PhaseTimer t("shell total");
     compute_yields();
     { PhaseTimer t2("sample_events"); sample_events(); }
-    computeAvgTotalEnergyMomentum();
+    if (!legacy_) computeAvgTotalEnergyMomentum();
     // priority OSCAR > gzip > binary (FSSW.cpp:354-360)
     if (use_oscar_) combine_samples_to_OSCAR();
     else if (use_gzip_) combine_samples_to_gzip_file();

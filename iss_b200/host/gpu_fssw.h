@@ -23,6 +23,14 @@ class GpuFSSW {
             const std::vector<FO_surf_LRF> &FOsurf_LRF, int flag_PCE, ParameterReader *paraRdr,
             std::string path, std::string table_path, AfterburnerType afterburner_type,
             const float *packed_lrf = nullptr);
+    // Legacy mode: the reference's EmissionFunctionArray "conventional" sampler, MC_sampling = 2
+    // (src/emissionfunction.cpp:3273-3623), over the LAB-frame cells that iSS::read_in_FO_surface
+    // keeps when MC_sampling != 4 (src/iSS.cpp:105-109).  Everything downstream of the sampling
+    // kernel (event batches, decays, QA, hadron lists, writers) is shared with the FSSW mode.
+    GpuFSSW(long seed, const std::vector<int> &chosen_monvals,
+            const std::vector<particle_info> &particles, const std::vector<FO_surf> &FOsurf_lab,
+            int flag_PCE, ParameterReader *paraRdr, std::string path, std::string table_path,
+            AfterburnerType afterburner_type);
     ~GpuFSSW();
 
     // chosen list -> indices into the pdg table in sampling order: unknown ids dropped with a
@@ -32,7 +40,8 @@ class GpuFSSW {
     // repeated generate_samples() calls copy it to the device without repacking.
     static void pack_surface(const std::vector<FO_surf_LRF> &surf, float *dst, int64_t c0, int64_t c1);
     static std::vector<int> order_species(const std::vector<int> &chosen_monvals,
-                                          const std::vector<particle_info> &particles);
+                                          const std::vector<particle_info> &particles,
+                                          bool sort_by_mass = true);
 
     void shell();       // it all starts here, as in FSSW::shell (FSSW.cpp:344-361)
 
@@ -67,6 +76,8 @@ class GpuFSSW {
     const std::vector<particle_info> &particles_;
     const std::vector<FO_surf_LRF> &surf_;
     const float *packed_lrf_ = nullptr;     // optional: surf_ already packed in pinned memory
+    const std::vector<FO_surf> *lab_surf_ = nullptr;    // legacy mode (MC_sampling = 2)
+    bool legacy_ = false;
     long seed_;
     int hydro_mode_;
     int include_shear_, include_bulk_, include_diff_, bulk_kind_;
@@ -88,6 +99,8 @@ class GpuFSSW {
     std::vector<std::unique_ptr<std::vector<iSS_Hadron>>> event_cache_;
     std::vector<iSS_Hadron> spectators_;
 
+    void init_(const std::vector<int> &chosen_monvals, int flag_PCE);
+    void upload_lab_surface_();
     void check_(int rc, const char *what);
     void select_species_(const std::vector<int> &chosen_monvals);
     void upload_surface_();

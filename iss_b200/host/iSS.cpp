@@ -120,21 +120,24 @@ void iSS::clear() {
 }
 
 void iSS::require_fssw_() const {
-    if (paraRdr_ptr->getVal("MC_sampling") != 4) {
-        iss_host::error("the B200 engine samples with FSSW only: set MC_sampling = 4 "
-                        "(the legacy EmissionFunctionArray samplers MC_sampling = 1/2/3 are out of scope)");
+    const double mode = paraRdr_ptr->getVal("MC_sampling");
+    if (mode != 4 && mode != 2) {
+        iss_host::error("the B200 engine samples with FSSW (MC_sampling = 4) or with the legacy "
+                        "conventional sampler (MC_sampling = 2); the legacy EmissionFunctionArray "
+                        "samplers MC_sampling = 1/3 are out of scope");
         exit(-1);
     }
 }
 
-// MC_sampling = 4: FSSW sampler; MC_sampling = 0: smooth spectra and flows of the legacy class
+// MC_sampling = 4: FSSW sampler; MC_sampling = 2: the legacy "conventional" sampler of
+// EmissionFunctionArray; MC_sampling = 0: smooth spectra and flows of the legacy class
 // (calculate_vn = 1) without sampling.
 void iSS::require_supported_mode_() const {
     const double mode = paraRdr_ptr->getVal("MC_sampling");
-    if (mode != 4 && mode != 0) {
-        iss_host::error("the B200 engine implements MC_sampling = 4 (FSSW) and MC_sampling = 0 "
-                        "(smooth spectra and flows); the legacy EmissionFunctionArray samplers "
-                        "MC_sampling = 1/2/3 are out of scope");
+    if (mode != 4 && mode != 2 && mode != 0) {
+        iss_host::error("the B200 engine implements MC_sampling = 4 (FSSW), MC_sampling = 2 (legacy "
+                        "conventional sampler) and MC_sampling = 0 (smooth spectra and flows); the "
+                        "legacy EmissionFunctionArray samplers MC_sampling = 1/3 are out of scope");
         exit(-1);
     }
 }
@@ -415,6 +418,12 @@ int iSS::prepare_sampler() {
     if (!seed_set_) set_random_seed();
     const std::vector<int> chosen = read_chosen_particles();
     spectra_sampler_.reset();   // frees the previous batch before the new one is allocated
+    if (paraRdr_ptr->getVal("MC_sampling") == 2) {
+        // legacy conventional sampler over the lab-frame cells (iSS.cpp:151-163)
+        spectra_sampler_.reset(new GpuFSSW(randomSeed_, chosen, particle_, FOsurf_array_, flag_PCE_,
+                                           paraRdr_ptr, path_, table_path_, afterburner_type_));
+        return 0;
+    }
     ensure_packed_lrf_();
     spectra_sampler_.reset(new GpuFSSW(randomSeed_, chosen, particle_, FOsurf_LRF_array_, flag_PCE_,
                                        paraRdr_ptr, path_, table_path_, afterburner_type_,
@@ -426,7 +435,8 @@ int iSS::prepare_sampler() {
 int iSS::generate_samples() {
     info("Start computation and generating samples ...");
     require_supported_mode_();
-    if (paraRdr_ptr->getVal("MC_sampling") == 4) {
+    const double mc_mode = paraRdr_ptr->getVal("MC_sampling");
+    if (mc_mode == 4 || mc_mode == 2) {
         prepare_sampler();
         spectra_sampler_->shell();
     } else {

@@ -77,3 +77,24 @@ def test_oracle_sampler_matches_reference_sampler(tmp_path):
     assert worst[0] > 1e-4, worst
     assert tot_ndf > 100
     assert stats.chi2.sf(tot_chi2, tot_ndf) > 0.01, (tot_chi2, tot_ndf)
+
+
+def test_facade_refuses_what_the_legacy_mode_does_not_cover(built, tmp_path):
+    """class iSS with MC_sampling = 2: unsupported options end with a message and a non-zero exit
+    (before any device is touched); nothing is approximated or silently ignored."""
+    import os
+    import subprocess
+    capi = built
+    g = cases.load("cell_shear", "legacy_stats")
+    folder = str(tmp_path/"case")
+    param, surf, over = cases.materialise(g, folder)
+    exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iSS.e")
+    base = [exe, param, "case", surf] + ["%s=%g" % kv for kv in over.items()]
+    os.symlink(orc.TABLES, str(tmp_path/"iSS_tables"))
+    for extra, text in ((["local_charge_conservation=1"], "local_charge_conservation is not supported"),
+                        (["output_samples_into_files=1"], "output_samples_into_files = 1"),
+                        (["include_deltaf_bulk=1", "bulk_deltaf_kind=0"], "bulk_deltaf_kind = 0")):
+        r = subprocess.run(base + extra, cwd=str(tmp_path), capture_output=True, text=True,
+                           env=dict(os.environ, ISS_INGEST="host"))
+        assert r.returncode != 0
+        assert text in r.stdout + r.stderr, (extra, r.stdout[-400:])

@@ -123,3 +123,82 @@ def test_legacy_spectra_match_reference_sampler(name, built):
     assert worst[0] > 1e-4, worst
     assert tot_ndf > 100
     assert stats.chi2.sf(tot_chi2, tot_ndf) > 0.01, (tot_chi2, tot_ndf)
+
+
+# ---- through the drop-in facade (class iSS with MC_sampling = 2) ---------------------------------
+def _facade(capi, g, tmp_path, **extra):
+    param, surf, over = cases.materialise(g, str(tmp_path))
+    over.update(use_OSCAR_format=0, use_gzip_format=0, use_binary_format=0, perform_checks=0)
+    over.update(extra)
+    return capi.Sampler(str(tmp_path), param, surf, **over)
+
+
+@pytest.mark.parametrize("name", lc.STATS_CASES)
+def test_legacy_facade_matches_reference_sampler(name, built, tmp_path):
+    """iSS::read_in_FO_surface / generate_samples / hadron lists with MC_sampling = 2: species
+    totals against the reference's yields, spectra against the reference's own samples."""
+    capi = built
+    g = cases.load(name, "legacy_stats")
+    nev_ref = int(g["nev"])
+    nev = nev_ref
+    s = _facade(capi, g, tmp_path, number_of_repeated_sampling=nev)
+    try:
+        assert s.read_in_FO_surface() == 0
+        s.set_random_seed(777)
+        assert s.generate_samples() == 0
+        assert s.get_number_of_sampled_events() == nev
+        h, off = s.hadrons()
+        mine = obs.summarize(h, off)
+        # the species the facade sampled, in the reference's order, and their totals
+        sp = s.species()
+        assert np.array_equal(sp["pid"], g["species"][:, 0].astype(np.int64))
+        par = lc.parameters(g)
+        opt = lc.oracle_options(par)
+        coef = lgo.cell_coefficients(g["lab"], opt, lgo.load_kappa())
+        y = lgo.yields(g["lab"], lc.species_array(g["species"]), opt, coef)
+        assert np.allclose(s.species_dN(), np.maximum(y, 0).sum(axis=1), rtol=1e-9, atol=1e-300)
+    finally:
+        s.close()
+    tot_chi2, tot_ndf, worst = 0.0, 0, (1.0, "")
+    for pid in obs.PIDS:
+        tag = "p%d" % pid if pid > 0 else "m%d" % (-pid)
+        for kind in ("pt", "y", "phi"):
+            chi2, ndf = obs.chi2_two_hist(mine[tag + "_" + kind], g[tag + "_" + kind], nev, nev_ref)
+            if ndf == 0:
+                continue
+            p = stats.chi2.sf(chi2, ndf)
+            tot_chi2 += chi2
+            tot_ndf += ndf
+            if p < worst[0]:
+                worst = (p, tag + "_" + kind)
+    assert worst[0] > 1e-4, worst
+    assert stats.chi2.sf(tot_chi2, tot_ndf) > 0.01, (tot_chi2, tot_ndf)
+
+
+def test_legacy_facade_decays_also_for_smash(built, tmp_path):
+    """EmissionFunctionArray::shell runs the feed-down whatever the afterburner
+    (emissionfunction.cpp:2570-2572), unlike FSSW::shell (FSSW.cpp:346)."""
+    capi = built
+    g = cases.load("l2d_ideal_smash", "legacy")
+    stable = {211, -211, 111, 321, -321, 2212, -2212, 2112, -2112, 22}
+    out = {}
+    for decays in (0, 1):
+        s = _facade(capi, g, tmp_path/("d%d" % decays), number_of_repeated_sampling=200,
+                    perform_decays=decays)
+        try:
+            assert s.read_in_FO_surface() == 0
+            s.set_random_seed(5)
+            assert s.generate_samples() == 0
+            h, off = s.hadrons()
+            out[decays] = h.copy()
+        finally:
+            s.close()
+    assert len(out[1]) > len(out[0]) > 1000
+    frac0 = np.isin(out[0]["pid"], list(stable)).mean()
+    frac1 = np.isin(out[1]["pid"], list(stable)).mean()
+    assert frac1 > frac0 + 0.15
+    rho_omega = [113, 213, -213, 223]
+    assert np.isin(out[0]["pid"], rho_omega).any() and not np.isin(out[1]["pid"], rho_omega).any()
+    # energy is conserved by the feed-down up to the 4-body channels, which emit nothing
+    assert out[1]["E"].sum() <= out[0]["E"].sum()*(1 + 1e-5)
+    assert out[1]["E"].sum() > 0.8*out[0]["E"].sum()

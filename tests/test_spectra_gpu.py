@@ -168,15 +168,15 @@ def test_facade_spectra_and_flows_match_reference_files(which, tmp_path):
 
 
 def test_facade_rejects_legacy_samplers(tmp_path):
-    """MC_sampling = 1/2/3 (legacy EmissionFunctionArray samplers) exit with an error, they do
-    not fall back to anything"""
+    """MC_sampling = 1/3 (legacy EmissionFunctionArray grid samplers) exit with an error, they do
+    not fall back to anything (MC_sampling = 2 is implemented: tests/test_legacy_gpu.py)"""
     import subprocess
     import cases
     g = np.load(os.path.join(sc.GOLDEN, "flows_new.npz"), allow_pickle=False)
     folder = str(tmp_path/"case")
     param, surf, over = cases.materialise(g, folder)
     code = ("import sys; sys.path.insert(0, %r); from iss_b200 import capi; "
-            "s = capi.Sampler(%r, %r, %r, MC_sampling=2); s.read_in_FO_surface()" %
+            "s = capi.Sampler(%r, %r, %r, MC_sampling=3); s.read_in_FO_surface()" %
             (REPO, folder, param, surf))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode != 0
