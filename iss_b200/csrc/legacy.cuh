@@ -365,11 +365,15 @@ struct LegacyLane {
     double maximum;
 };
 
-static __global__ void __launch_bounds__(LEGACY_THREADS)
+constexpr int LEGACY_LANE_STRIDE = ISS_LAB_NFIELD + 1;    // floats per lane (odd: no bank conflicts)
+
+static __global__ void __launch_bounds__(LEGACY_THREADS, 2)
 legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
     extern __shared__ unsigned char smem_raw[];
     DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
     int64_t *sp_off = reinterpret_cast<int64_t *>(sp + A.ns);
+    // per-lane copy of the lab-frame cell record the tries read (written once per hadron)
+    float *f = reinterpret_cast<float *>(sp_off + A.ns + 1) + threadIdx.x*LEGACY_LANE_STRIDE;
     for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
     for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
         sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
@@ -380,10 +384,11 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
     LegacyLane L;
     L.cell = 0; L.s = 0; L.out_slot = 0; L.event = 0; L.draw = 0; L.block = 0; L.tries = 1;
     L.total_tries = 0; L.maximum = 1.;
-    float f[ISS_LAB_NFIELD];
 #pragma unroll
     for (int q = 0; q < ISS_LAB_NFIELD; q++) f[q] = 0.f;
     double4 cf = make_double4(0., 0., 0., 1.);
+    // per-hadron constants of the tries (same operations as the reference does per try)
+    double c_mu = 0., c_inv_T = 0., c_shear = 0., c_prefq = 0., c_bulkPi = 0.;
     bool busy = false, more = true;
     unsigned long long my_tries = 0, my_redraws = 0, my_giveup = 0;
 
@@ -398,6 +403,13 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
         L.maximum = legacy_estimate_maximum(G, f, cf, p.mass, p.sign, p.gspin, p.baryon, p.strange,
                                             p.charge);
         L.tries = 1;
+        const double Tdec = f[ISS_L_T];
+        const float e_plus_p = __fadd_rn(f[ISS_L_E], f[ISS_L_P]);       // float sum (:4204-4205)
+        c_mu = legacy_mu(f, p.baryon, p.strange, p.charge);
+        c_inv_T = 1./Tdec;
+        c_shear = 1.0/(2.0*Tdec*Tdec*e_plus_p);
+        c_prefq = __fdiv_rn(f[ISS_L_BN], e_plus_p);
+        c_bulkPi = static_cast<double>(f[ISS_L_BULKPI])/HBARC;
     };
 
     for (;;) {
@@ -430,8 +442,8 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
         philox_block(L.block++, L.draw, L.event, sample_stream_word3(L.s), key0, key1, w0, w1, w2, w3);
         my_tries++;
         L.total_tries++;
-        const double Tdec = f[ISS_L_T], inv_Tdec = 1./Tdec;
-        const double mu = legacy_mu(f, p.baryon, p.strange, p.charge);
+        const double Tdec = f[ISS_L_T], inv_Tdec = c_inv_T;
+        const double mu = c_mu;
         const double pT = sqrt(G.pT_to*G.pT_to*u32(w0));
         const double u_phi = u32(w1);
         const double yme = (1. - 2.*u32(w2))*G.y_range;
@@ -444,22 +456,19 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
         const double f0 = 1./(exp((pdotu - mu)*inv_Tdec) + sign);
         const double pdsigma = p0*f[ISS_L_DA0] + px*f[ISS_L_DA1] + py*f[ISS_L_DA2]
                                + p3*f[ISS_L_DA3]/f[ISS_L_TAU];
-        const float e_plus_p = __fadd_rn(f[ISS_L_E], f[ISS_L_P]);       // float sum (:4204-4205)
         double delta_f = 0.;
         if (G.include_shear == 1) {
             const double Wfactor = (p0*p0*f[ISS_L_PI00] - 2.0*p0*px*f[ISS_L_PI01] - 2.0*p0*py*f[ISS_L_PI02]
                                     - 2.0*p0*p3*f[ISS_L_PI03] + px*px*f[ISS_L_PI11]
                                     + 2.0*px*py*f[ISS_L_PI12] + 2.0*px*p3*f[ISS_L_PI13]
                                     + py*py*f[ISS_L_PI22] + 2.0*py*p3*f[ISS_L_PI23] + p3*p3*f[ISS_L_PI33]);
-            delta_f += (1. - sign*f0)*Wfactor*(1.0/(2.0*Tdec*Tdec*e_plus_p));
+            delta_f += (1. - sign*f0)*Wfactor*c_shear;
         }
         if (G.include_bulk == 1)
-            delta_f += legacy_deltaf_bulk(G.bulk_kind, mass, pdotu,
-                                          static_cast<double>(f[ISS_L_BULKPI])/HBARC, Tdec, sign, f0, cf);
+            delta_f += legacy_deltaf_bulk(G.bulk_kind, mass, pdotu, c_bulkPi, Tdec, sign, f0, cf);
         if (G.include_diff == 1) {
             const double qmufactor = p0*f[ISS_L_Q0] - px*f[ISS_L_Q1] - py*f[ISS_L_Q2] - p3*f[ISS_L_Q3];
-            const double prefactor_qmu = __fdiv_rn(f[ISS_L_BN], e_plus_p);
-            delta_f += (1. - sign*f0)*(prefactor_qmu - p.baryon/pdotu)*qmufactor/cf.w;
+            delta_f += (1. - sign*f0)*(c_prefq - p.baryon/pdotu)*qmufactor/cf.w;
         }
         double resize_factor = 1.0;
         if (G.restrict_deltaf == 1)

@@ -1321,10 +1321,15 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
             work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
                 h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
         }
-        const size_t smem_l = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
+        const size_t smem_l = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1)
+                              + sizeof(float)*LEGACY_LANE_STRIDE*LEGACY_THREADS;
         int64_t grid_l = static_cast<int64_t>(nsm)*4;
         const int64_t useful = (A.nwork + LEGACY_THREADS - 1)/LEGACY_THREADS;
         if (grid_l > useful) grid_l = useful;
+        if (smem_l > 48*1024)
+            ISS_CUDA_TRY(h, cudaFuncSetAttribute(legacy_sample_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 static_cast<int>(smem_l)));
         {
             ScopedTimer t(h, ISS_T_SAMPLE);
             legacy_sample_kernel<<<static_cast<unsigned>(grid_l), LEGACY_THREADS, smem_l, h->stream>>>(A, G);
