@@ -140,11 +140,20 @@ int iss_cuda_create(int device, iss_handle **out) {
         return ISS_ERR_CUDA;
     }
     h->own_stream = true;
-    cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
-    cudaEventCreateWithFlags(&h->batch_ready, cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->copy_done[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->copy_done[1], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&h->copy_done2, cudaEventDisableTiming);
+    // the kernels exist for sm_100a only: a device that cannot run them is refused here, not at
+    // the first launch
+    cudaFuncAttributes fa;
+    bool ok = cudaFuncGetAttributes(&fa, fp64_fma_kernel) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->batch_ready, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->copy_done[0], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->copy_done[1], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->copy_done2, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();     // clear the sticky-free error state of this thread
+        iss_cuda_destroy(h);
+        return ISS_ERR_CUDA;
+    }
     *out = h;
     return ISS_OK;
 }
