@@ -20,6 +20,12 @@
  * Those two pieces are restated here independently so that, GIVEN identical yields, the integer
  * bookkeeping is bit-exact and every hadron can be compared one to one.
  *
+ * The last part of the file restates the legacy "conventional" sampler of EmissionFunctionArray
+ * (MC_sampling = 2): estimate_maximum and the sampling loops; its yields are restated in numpy
+ * (oracle/legacy_oracle.py).  Pinned by tests/test_legacy_cpu.py against dumps of the compiled
+ * reference (oracle/ref_driver.cpp `legacy`: yields to 1e-12, maxima to 1e-12) and against the
+ * histograms of the reference's own MC_sampling = 2 samples.
+ *
  * Parity pinning: the reference algorithms in this file are pinned against the compiled reference
  * itself by tests/test_oracle_cpu.py (|p| spectra of MomentumSamplerShell and decay daughters of
  * particle_decay dumped by oracle/ref_driver.cpp into tests/golden/, and the reference's own
