@@ -347,12 +347,12 @@ ISS_API int iss_cuda_spectra_stats(iss_handle *h, double *evaluations, double *k
  * (pT^2, phi, y - eta_s) accepted against that maximum (sample_momemtum_from_a_fluid_cell,
  * :4188-4306), add_one_sampled_particle (:4423-4475).
  * Call order: upload_species / upload_table(BESSEL_K [, EXPINT, KAPPA_B]) / set_options (hydro_mode,
- * y_LB, y_RB, multiplicity model; local_charge_conservation must be 0) as for the FSSW path, then
+ * y_LB, y_RB, multiplicity model, local_charge_conservation) as for the FSSW path, then
  *   iss_cuda_upload_surface_lab(cells) -> iss_cuda_legacy_upload_positions ->
  *   iss_cuda_legacy_upload_z_table -> iss_cuda_legacy_set_options -> iss_cuda_legacy_compute_yields
  *   -> iss_cuda_sample / iss_cuda_decay / iss_cuda_histograms / fetch as usual.
  * Not supported (rejected with ISS_ERR_ARG): bulk_deltaf_kind 0 (needs the s95p-PCE coefficient
- * table), local charge conservation, PCE chemical potentials.                                  */
+ * table), PCE chemical potentials.                                                            */
 typedef struct {
     int32_t include_deltaf_shear;
     int32_t include_deltaf_bulk;

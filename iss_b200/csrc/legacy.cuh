@@ -363,6 +363,8 @@ struct LegacyLane {
     int tries;
     long long total_tries;
     double maximum;
+    int qsign;          // +1 primary, -1 charge-conservation partner (conjugate quantum numbers)
+    double eta_s;       // eta_s of the primary, reused by its partner (:3533-3536)
 };
 
 constexpr int LEGACY_LANE_STRIDE = ISS_LAB_NFIELD + 1;    // floats per lane (odd: no bank conflicts)
@@ -383,7 +385,7 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
     const double prefactor = 1.0/(8.0*(M_PI*M_PI*M_PI)*(HBARC*HBARC*HBARC));
     LegacyLane L;
     L.cell = 0; L.s = 0; L.out_slot = 0; L.event = 0; L.draw = 0; L.block = 0; L.tries = 1;
-    L.total_tries = 0; L.maximum = 1.;
+    L.total_tries = 0; L.maximum = 1.; L.qsign = 1; L.eta_s = 0.;
 #pragma unroll
     for (int q = 0; q < ISS_LAB_NFIELD; q++) f[q] = 0.f;
     double4 cf = make_double4(0., 0., 0., 1.);
@@ -424,7 +426,10 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
                 L.draw = static_cast<uint32_t>(k);
                 L.block = 0u;
                 L.total_tries = 0;
-                L.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k;
+                // local charge conservation: a positive hadron is followed by its partner
+                const int mult = (A.lcc == 1 && sp[s].charge > 0) ? 2 : 1;
+                L.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k*mult;
+                L.qsign = 1;
                 draw_cell();
                 busy = true;
             } else {
@@ -468,7 +473,7 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
             delta_f += legacy_deltaf_bulk(G.bulk_kind, mass, pdotu, c_bulkPi, Tdec, sign, f0, cf);
         if (G.include_diff == 1) {
             const double qmufactor = p0*f[ISS_L_Q0] - px*f[ISS_L_Q1] - py*f[ISS_L_Q2] - p3*f[ISS_L_Q3];
-            delta_f += (1. - sign*f0)*(c_prefq - p.baryon/pdotu)*qmufactor/cf.w;
+            delta_f += (1. - sign*f0)*(c_prefq - (L.qsign*p.baryon)/pdotu)*qmufactor/cf.w;
         }
         double resize_factor = 1.0;
         if (G.restrict_deltaf == 1)
@@ -478,18 +483,22 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
         if (u32(w3) < accept_prob) {
             // ---- accepted: add_one_sampled_particle (:4423-4475)
             const float4 pos = __ldg(&G.pos[L.cell]);
-            double eta_s = pos.z;
-            if (A.hydro_mode != 2) {
-                uint32_t r0, r1, r2, r3;
-                philox_block(L.block++, L.draw, L.event, sample_stream_word3(L.s), key0, key1,
-                             r0, r1, r2, r3);
-                const double rap = A.y_LB + (A.y_RB - A.y_LB)*u32(r0);
-                eta_s = rap - yme;
+            if (L.qsign > 0) {
+                double eta_s = pos.z;
+                if (A.hydro_mode != 2) {
+                    uint32_t r0, r1, r2, r3;
+                    philox_block(L.block++, L.draw, L.event, sample_stream_word3(L.s), key0, key1,
+                                 r0, r1, r2, r3);
+                    const double rap = A.y_LB + (A.y_RB - A.y_LB)*u32(r0);
+                    eta_s = rap - yme;
+                }
+                L.eta_s = eta_s;
             }
+            const double eta_s = L.eta_s;
             const double rapidity_y = yme + eta_s;
             const double tau = f[ISS_L_TAU];
             float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
-            dst[0] = make_float2(__int_as_float(p.pid), static_cast<float>(mass));
+            dst[0] = make_float2(__int_as_float(L.qsign > 0 ? p.pid : -p.pid), static_cast<float>(mass));
             dst[1] = make_float2(static_cast<float>(mT*cosh(rapidity_y)), static_cast<float>(px));
             dst[2] = make_float2(static_cast<float>(py), static_cast<float>(mT*sinh(rapidity_y)));
             dst[3] = make_float2(static_cast<float>(tau*cosh(eta_s)), pos.x);
@@ -499,6 +508,15 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
                 A.trace_tries[L.out_slot] = static_cast<int32_t>(L.total_tries);
             }
             busy = false;
+            if (A.lcc == 1 && L.qsign > 0 && p.charge > 0) {
+                // a negative partner from the SAME cell with the SAME maximum (:3517-3546)
+                L.qsign = -1;
+                L.out_slot += 1;
+                L.tries = 1;
+                L.total_tries = 0;
+                c_mu = legacy_mu(f, -p.baryon, -p.strange, -p.charge);
+                busy = true;
+            }
         } else {
             L.tries++;
             if (L.tries >= LEGACY_MAX_IMPATIENCE) {
@@ -508,10 +526,12 @@ legacy_sample_kernel(const SamplerArgs A, const LegacyArgs G) {
                     for (int q = 0; q < 5; q++) dst[q] = make_float2(0.f, 0.f);
                     my_giveup++;
                     busy = false;
-                } else {
+                } else if (L.qsign > 0) {
                     // status 0 -> `continue`: a NEW cell is drawn (:3478-3480)
                     my_redraws++;
                     draw_cell();
+                } else {
+                    L.tries = 1;    // the partner's do-while stays in the cell (:3521-3528)
                 }
             }
         }

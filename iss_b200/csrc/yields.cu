@@ -652,8 +652,6 @@ int legacy_args(iss_handle *h, LegacyArgs &G) {
 int run_legacy_yields(iss_handle *h, double *yields_host, double *maximum_host) {
     if (h->nspecies <= 0) ISS_FAIL(h, ISS_ERR_STATE, "no species uploaded");
     if (!h->have_opt) ISS_FAIL(h, ISS_ERR_STATE, "options not set");
-    if (h->opt.local_charge_conservation == 1)
-        ISS_FAIL(h, ISS_ERR_ARG, "legacy sampler: local_charge_conservation is not supported");
     if (!h->have_legopt) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_legacy_set_options must run first");
     // K_n / E_n tables: built on the device unless the caller uploaded them
     int rc = ensure_sf_tables(h, h->legopt.include_deltaf_diffusion == 1);

@@ -266,10 +266,6 @@ void GpuFSSW::init_(const std::vector<int> &chosen_monvals, int flag_PCE) {
         }
         if (paraRdr_->getVal("store_samples_in_memory") != 1)
             iss_host::warning("MC_sampling = 2: samples are always kept in memory by the B200 engine");
-        if (paraRdr_->getVal("local_charge_conservation") == 1) {
-            iss_host::error("MC_sampling = 2: local_charge_conservation is not supported by the B200 engine");
-            exit(-1);
-        }
         if (include_bulk_ == 1 && bulk_kind_ == 0) {
             iss_host::error("MC_sampling = 2: bulk_deltaf_kind = 0 is not supported by the B200 engine");
             exit(-1);

@@ -795,7 +795,7 @@ enum { L_TAU = 0, L_U0, L_U1, L_U2, L_U3, L_DA0, L_DA1, L_DA2, L_DA3, L_T, L_P, 
 
 typedef struct {
     int32_t include_shear, include_bulk, bulk_kind, include_diff;
-    int32_t restrict_deltaf, boost_invariant, reserved0, reserved1;
+    int32_t restrict_deltaf, boost_invariant, lcc, reserved1;
     double deltaf_max_ratio, pT_to, y_minus_eta_s_range, y_LB, y_RB;
 } o_legacy_opt;
 
@@ -1007,7 +1007,7 @@ static int legacy_sample_in_cell(const float *c, const double *coef, const o_leg
 /* event/species/particle loops of sample_using_dN_dxtdy_4all_particles_conventional (:3330-3560)
  * with the engine's stream keying (as oracle_sample above): stream (seed; SAMPLE, s, ev, k),
  * block order  cell | tries (one block each) | after 4999 rejections: new cell | boost-invariant:
- * rapidity.  yields [ns][ncell] may be negative (the reference does not clamp them; the CDF does,
+ * rapidity | charge-conservation partner: tries in the same cell.  yields [ns][ncell] may be negative (the reference does not clamp them; the CDF does,
  * RandomVariable1DArray.cpp:38-50).  cdf_in (may be NULL): [ns][ncell+1] prefix to use instead of
  * the sequential one (the engine's fixed-order prefix).  max_out (may be NULL): maximum_guess used
  * for every hadron.  Returns the number of hadrons, -1 on capacity, -3 if a maximum is NaN (the
@@ -1078,6 +1078,34 @@ int64_t oracle_legacy_sample(const float *lab, const float *pos, int64_t ncell,
                 }
                 if (out_cell) { out_cell[n] = (int32_t)cell; out_tries[n] = ntries; }
                 n++;
+                if (o->lcc == 1 && p->charge > 0) {
+                    /* a negative partner from the same cell, same maximum_guess, same eta_s
+                     * (:3517-3546); the do-while never draws a new cell */
+                    const double mx = oracle_legacy_estimate_maximum(c, coef + cell*4, o, p->mass,
+                        p->sign, p->gspin, p->baryon, p->strange, p->charge, zx, zy, nz);
+                    int nt2 = 0;
+                    double pT2 = 0, phi2 = 0, yme2 = 0;
+                    while (!legacy_sample_in_cell(c, coef + cell*4, o, p->mass, (double)p->gspin,
+                                                  p->sign, -p->baryon, -p->strange, -p->charge, mx,
+                                                  &rng, &nt2, &pT2, &phi2, &yme2)) {
+                    }
+                    if (n >= cap) { free(cdf); return -1; }
+                    o_hadron *h = &out[n];
+                    const double y = yme2 + eta_s;
+                    const double mT = sqrt(p->mass*p->mass + pT2*pT2);
+                    h->pid = -p->pid;
+                    h->mass = p->mass;
+                    h->E = mT*cosh(y);
+                    h->px = pT2*cos(phi2);
+                    h->py = pT2*sin(phi2);
+                    h->pz = mT*sinh(y);
+                    h->t = c[L_TAU]*cosh(eta_s);
+                    h->x = pos[cell*4 + 0];
+                    h->y = pos[cell*4 + 1];
+                    h->z = c[L_TAU]*sinh(eta_s);
+                    if (out_cell) { out_cell[n] = (int32_t)cell; out_tries[n] = nt2; }
+                    n++;
+                }
             }
         }
     free(cdf);

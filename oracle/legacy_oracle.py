@@ -29,19 +29,21 @@ class LegacyOpt(C.Structure):
     _fields_ = [("include_shear", C.c_int32), ("include_bulk", C.c_int32),
                 ("bulk_kind", C.c_int32), ("include_diff", C.c_int32),
                 ("restrict_deltaf", C.c_int32), ("boost_invariant", C.c_int32),
-                ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+                ("lcc", C.c_int32), ("reserved1", C.c_int32),
                 ("deltaf_max_ratio", C.c_double), ("pT_to", C.c_double),
                 ("y_minus_eta_s_range", C.c_double), ("y_LB", C.c_double), ("y_RB", C.c_double)]
 
 
 def make_opt(include_shear=0, include_bulk=0, bulk_kind=1, include_diff=0, restrict_deltaf=0,
-             deltaf_max_ratio=1.0, boost_invariant=0, pT_to=4.0, y_range=4.0, y_LB=-5.0, y_RB=5.0):
+             deltaf_max_ratio=1.0, boost_invariant=0, pT_to=4.0, y_range=4.0, y_LB=-5.0, y_RB=5.0,
+             lcc=0):
     o = LegacyOpt()
     o.include_shear, o.include_bulk, o.bulk_kind, o.include_diff = (include_shear, include_bulk,
                                                                     bulk_kind, include_diff)
     o.restrict_deltaf, o.boost_invariant = restrict_deltaf, boost_invariant
     o.deltaf_max_ratio, o.pT_to, o.y_minus_eta_s_range = deltaf_max_ratio, pT_to, y_range
     o.y_LB, o.y_RB = y_LB, y_RB
+    o.lcc = lcc
     return o
 
 

@@ -211,6 +211,11 @@ LEGACY_STATS = {
     "cell_shear": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=11,
                        cell="testViscousOneFluidCell2.dat", scale=0.002,
                        over=["include_deltaf_shear=1", "include_deltaf_bulk=0", "bulk_deltaf_kind=1"]),
+    # local charge conservation: negative species skipped, positive ones paired (:3326-3336, 3517-3546)
+    "cell_lcc": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=13,
+                     cell="testViscousOneFluidCell2.dat", scale=0.002,
+                     over=["include_deltaf_shear=1", "include_deltaf_bulk=0", "bulk_deltaf_kind=1",
+                           "local_charge_conservation=1"]),
     "surf3d_bulk1": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=12,
                          gen=dict(ncell=300, seed=2025, eos=14, rhob=1, diffusion=1, binary=1),
                          over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=1",

@@ -11,7 +11,7 @@ import iss_oracle as orc  # noqa: E402
 import legacy_oracle as lgo  # noqa: E402
 
 YIELD_CASES = ["l3d_shear", "l3d_bulk1_diff", "l2d_ideal_smash"]
-STATS_CASES = ["cell_shear", "surf3d_bulk1"]
+STATS_CASES = ["cell_shear", "surf3d_bulk1", "cell_lcc"]
 
 
 def species_array(sp):
@@ -51,7 +51,8 @@ def oracle_options(par):
                         deltaf_max_ratio=par["deltaf_max_ratio"],
                         boost_invariant=int(int(par["hydro_mode"]) != 2),
                         pT_to=par["sample_pt_up_to"], y_range=par["sample_y_minus_eta_s_range"],
-                        y_LB=par["y_lb"], y_RB=par["y_rb"])
+                        y_LB=par["y_lb"], y_RB=par["y_rb"],
+                        lcc=int(par.get("local_charge_conservation", 0)))
 
 
 def engine_options(par):

@@ -41,10 +41,10 @@ def test_oracle_yields_and_maxima_match_reference(name):
     assert np.allclose(mx, g["maximum"], rtol=1e-12, atol=0)
 
 
-def test_oracle_sampler_matches_reference_sampler(tmp_path):
+@pytest.mark.parametrize("name", ["cell_shear", "cell_lcc"])
+def test_oracle_sampler_matches_reference_sampler(name, tmp_path):
     """chi2 of pT / y / phi spectra of the restated sampler against the reference's own samples
     (10^4 events); acceptance as in tests/test_stats_gpu.py."""
-    name = "cell_shear"
     g = cases.load(name, "legacy_stats")
     par = lc.parameters(g)
     opt = lc.oracle_options(par)
@@ -55,12 +55,12 @@ def test_oracle_sampler_matches_reference_sampler(tmp_path):
     if opt.boost_invariant:
         dN = dN*(opt.y_RB - opt.y_LB)
     nev, nev_ref = 4000, int(g["nev"])
-    mult, _ = orc.multiplicities(dN, orc.poisson_pmode(dN), sp, nev, 0, 99)
+    mult, outc = orc.multiplicities(dN, orc.poisson_pmode(dN), sp, nev, 0, 99, lcc=opt.lcc)
     h, cell, tries = lgo.sample(lab, pos, coef, y, sp, opt, lgo.load_z_table(), 99, 0, mult,
-                                mult.sum() + 8)
-    assert len(h) == mult.sum()
+                                outc.sum() + 8)
+    assert len(h) == outc.sum()
     assert tries.mean() > 50            # the legacy sampler needs hundreds of tries per hadron
-    off = np.concatenate([[0], np.cumsum(mult.sum(axis=1))])
+    off = np.concatenate([[0], np.cumsum(outc.sum(axis=1))])
     mine = obs.summarize(h, off)
     tot_chi2, tot_ndf, worst = 0.0, 0, (1.0, "")
     for pid in obs.PIDS:
@@ -91,8 +91,7 @@ def test_facade_refuses_what_the_legacy_mode_does_not_cover(built, tmp_path):
     exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iSS.e")
     base = [exe, param, "case", surf] + ["%s=%g" % kv for kv in over.items()]
     os.symlink(orc.TABLES, str(tmp_path/"iSS_tables"))
-    for extra, text in ((["local_charge_conservation=1"], "local_charge_conservation is not supported"),
-                        (["output_samples_into_files=1"], "output_samples_into_files = 1"),
+    for extra, text in ((["output_samples_into_files=1"], "output_samples_into_files = 1"),
                         (["include_deltaf_bulk=1", "bulk_deltaf_kind=0"], "bulk_deltaf_kind = 0")):
         r = subprocess.run(base + extra, cwd=str(tmp_path), capture_output=True, text=True,
                            env=dict(os.environ, ISS_INGEST="host"))

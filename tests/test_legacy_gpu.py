@@ -30,7 +30,8 @@ def make_engine(capi, g, par):
     if int(par["include_deltaf_diffusion"]) == 1:
         e.upload_table(capi.TABLE_KAPPA_B, sc.kappa_table(), 150, 100, [0.05, 0.001, 0.0, 0.007892])
     e.set_options(hydro_mode=int(par["hydro_mode"]), y_LB=par["y_lb"], y_RB=par["y_rb"],
-                  dN_dy_sampling_model=30)
+                  dN_dy_sampling_model=30,
+                  local_charge_conservation=int(par.get("local_charge_conservation", 0)))
     e.legacy_setup(g["lab"], g["pos"], lgo.load_z_table(), **lc.engine_options(par))
     return e, sp
 
@@ -52,12 +53,16 @@ def test_legacy_yields_and_maxima_match_reference(name, built):
         e.close()
 
 
-@pytest.mark.parametrize("name,nev", [("l3d_shear", 300), ("l3d_bulk1_diff", 300),
-                                      ("l2d_ideal_smash", 40)])
-def test_legacy_hadrons_match_oracle(name, nev, built):
+@pytest.mark.parametrize("name,nev,extra", [
+    ("l3d_shear", 300, {}), ("l3d_bulk1_diff", 300, {}), ("l2d_ideal_smash", 40, {}),
+    ("l3d_shear", 300, {"local_charge_conservation": 1}),
+    ("l2d_ideal_smash", 40, {"local_charge_conservation": 1})])
+def test_legacy_hadrons_match_oracle(name, nev, extra, built):
     capi = built
     g = cases.load(name, "legacy")
     par = lc.parameters(g)
+    par.update(extra)
+    lcc = int(par.get("local_charge_conservation", 0))
     e, sp = make_engine(capi, g, par)
     try:
         dN, y, _ = e.legacy_compute_yields(want_cells=True)
@@ -71,7 +76,7 @@ def test_legacy_hadrons_match_oracle(name, nev, built):
         lam, pm = e.poisson_params()
         boost_inv = int(par["hydro_mode"]) != 2
         assert np.array_equal(lam, dN*(par["y_rb"] - par["y_lb"]) if boost_inv else dN)
-        omult, ocount = orc.multiplicities(lam, pm, sp, nev, ev0, seed)
+        omult, ocount = orc.multiplicities(lam, pm, sp, nev, ev0, seed, lcc=lcc)
         assert np.array_equal(mult, omult)
         assert np.array_equal(off, np.concatenate([[0], np.cumsum(ocount.sum(axis=1))]))
         assert cnt.n_hadrons == ocount.sum() == len(had) > 300
@@ -81,6 +86,15 @@ def test_legacy_hadrons_match_oracle(name, nev, built):
         ohad, ocell, otries = lgo.sample(g["lab"], g["pos"], coef, y, sp, opt, lgo.load_z_table(),
                                          seed, ev0, omult, ocount.sum() + 8)
         assert len(ohad) == len(had)
+        if lcc:
+            # every positive hadron is followed by its conjugate from the same cell
+            pos_charge = np.isin(had["pid"], sp["pid"][sp["charge"] > 0])
+            idx = np.nonzero(pos_charge)[0]
+            assert len(idx) > 100
+            assert np.array_equal(had["pid"][idx + 1], -had["pid"][idx])
+            assert np.array_equal(cell[idx + 1], cell[idx])
+            assert not np.isin(had["pid"][np.setdiff1d(np.arange(len(had)), idx + 1)],
+                               sp["pid"][sp["charge"] < 0]).any()
         same_path = (cell == ocell) & (tries == otries)
         assert same_path.mean() >= 1 - 2e-3, "paths differ for %d of %d" % ((~same_path).sum(), len(had))
         ident, close = compare_hadrons(had[same_path], ohad[same_path])
