@@ -97,3 +97,31 @@ def test_facade_refuses_what_the_legacy_mode_does_not_cover(built, tmp_path):
                            env=dict(os.environ, ISS_INGEST="host"))
         assert r.returncode != 0
         assert text in r.stdout + r.stderr, (extra, r.stdout[-400:])
+
+
+@pytest.mark.parametrize("kind,name", [("legacy", n) for n in lc.YIELD_CASES]
+                         + [("legacy_stats", n) for n in lc.STATS_CASES])
+def test_host_keeps_the_reference_lab_frame_cells(kind, name, built, tmp_path):
+    """With MC_sampling = 2 iSS::read_in_FO_surface keeps the lab-frame (Milne) cells
+    (src/iSS.cpp:105-109): records, positions and the legacy species order of the host code are
+    bit-identical to the dump of the compiled reference (binary and text surfaces, 3+1D and
+    boost-invariant, with and without grouping_particles)."""
+    import os
+    import subprocess
+    capi = built
+    g = cases.load(name, kind)
+    param, surf, over = cases.materialise(g, str(tmp_path/"case"))
+    os.symlink(orc.TABLES, str(tmp_path/"iSS_tables"))
+    exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iss_host_dump")
+    r = subprocess.run([exe, param, "case", surf, "out"] + ["%s=%g" % kv for kv in over.items()],
+                       cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       env=dict(os.environ, ISS_INGEST="host"))
+    assert r.returncode == 0, r.stdout.decode()[-1500:]
+    with open(tmp_path/"out.lab.bin", "rb") as f:
+        n = int(np.fromfile(f, dtype=np.int64, count=1)[0])
+        lab = np.fromfile(f, dtype=np.float32).reshape(n, 32)
+    pos = np.fromfile(tmp_path/"out.pos.bin", dtype=np.float32).reshape(n, 4)
+    assert np.array_equal(lab.view(np.uint32), g["lab"].view(np.uint32))
+    assert np.array_equal(pos.view(np.uint32), g["pos"].view(np.uint32))
+    sp = np.loadtxt(tmp_path/"out.species.txt", ndmin=2)
+    assert np.array_equal(sp[:, :7], g["species"][:, :7])
