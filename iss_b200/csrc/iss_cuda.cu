@@ -843,6 +843,10 @@ int iss_cuda_legacy_upload_positions(iss_handle *h, const float *pos, int64_t nc
                                     h->stream));
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->nlegpos = ncell;
+    if (h->legacy) {
+        h->have_yields = false;
+        h->have_batch = false;
+    }
     return ISS_OK;
 }
 

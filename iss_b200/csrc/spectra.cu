@@ -367,6 +367,10 @@ int iss_cuda_upload_surface_lab(iss_handle *h, const float *cells, int64_t ncell
                                     cudaMemcpyHostToDevice, h->stream));
     ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));      // the caller's buffer may be reused
     h->nlab = ncell;
+    if (h->legacy) {        // yields of the legacy sampler belonged to the previous cells
+        h->have_yields = false;
+        h->have_batch = false;
+    }
     return ISS_OK;
 }
 
