@@ -397,10 +397,12 @@ void GpuSpectra::calculate_dN_pTdpTdphidy_and_flows_4all_old_output() {
 void GpuSpectra::shell() {
     const int calculate_vn = static_cast<int>(paraRdr_->getVal("calculate_vn"));
     const int historic_format = static_cast<int>(paraRdr_->getVal("use_historic_flow_output_format"));
-    if (MC_sampling_ != 0) {
-        iss_host::error("the legacy EmissionFunctionArray samplers (MC_sampling = 1, 2, 3) are out of "
-                        "scope of the B200 engine: use MC_sampling = 4 (FSSW) to sample, or "
-                        "MC_sampling = 0 with calculate_vn = 1 for the smooth spectra and flows");
+    // MC_sampling = 2: EmissionFunctionArray::shell computes the spectra first when calculate_vn is
+    // set, then samples (emissionfunction.cpp:2554-2572); the sampling half is GpuFSSW's legacy mode
+    if (MC_sampling_ != 0 && MC_sampling_ != 2) {
+        iss_host::error("the legacy EmissionFunctionArray grid samplers (MC_sampling = 1, 3) are out of "
+                        "scope of the B200 engine: use MC_sampling = 4 (FSSW) or 2 (conventional) to "
+                        "sample, or MC_sampling = 0 with calculate_vn = 1 for the smooth spectra and flows");
         exit(-1);
     }
     if (calculate_vn) {

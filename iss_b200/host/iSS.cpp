@@ -436,6 +436,15 @@ int iSS::generate_samples() {
     info("Start computation and generating samples ...");
     require_supported_mode_();
     const double mc_mode = paraRdr_ptr->getVal("MC_sampling");
+    if (mc_mode == 2 && paraRdr_ptr->getVal("calculate_vn") == 1) {
+        // the legacy class writes the smooth spectra and flows before it samples
+        // (EmissionFunctionArray::shell, emissionfunction.cpp:2554-2561)
+        const std::vector<int> chosen = read_chosen_particles();
+        efa_.reset();
+        efa_.reset(new GpuSpectra(chosen, particle_, FOsurf_array_, flag_PCE_, paraRdr_ptr, path_,
+                                  table_path_, afterburner_type_));
+        efa_->shell();
+    }
     if (mc_mode == 4 || mc_mode == 2) {
         prepare_sampler();
         spectra_sampler_->shell();
