@@ -3,7 +3,8 @@
 // behind `class iSS` when MC_sampling == 0 and calculate_vn == 1.  The dense sum over
 // cells x (y - eta_s) x pT x phi runs on the GPU (iss_cuda_spectra); the flow harmonics, the
 // grouping of species with equal quantum numbers and the output files are host work.
-// The legacy Monte-Carlo samplers of that class (MC_sampling = 1, 2, 3) are out of scope.
+// The conventional sampler of that class (MC_sampling = 2) is GpuFSSW's legacy mode (gpu_fssw.h); its
+// grid samplers (MC_sampling = 1, 3) are out of scope.
 #ifndef ISS_B200_GPU_SPECTRA_H_
 #define ISS_B200_GPU_SPECTRA_H_
 
