@@ -6,7 +6,8 @@
 // accessors, clear() and transform_to_local_rest_frame.  Host code only parses input
 // and drives the device: yields, multiplicities, momentum sampling, boost, decays and
 // QA histograms run in the CUDA library behind include/iss_cuda.h.  There is no CPU
-// sampler in this library: MC_sampling must be 4 (FSSW path) and a B200-class GPU
+// sampler in this library: MC_sampling must be 4 (FSSW path), 2 (legacy conventional
+// sampler) or 0 (smooth spectra and flows) and a B200-class GPU
 // must be present, otherwise the call prints a message and exits like the reference's
 // other fatal errors (return 0 on success, exit(+-1) on failure; no exceptions).
 #ifndef ISS_H
