@@ -15,9 +15,14 @@
 //                         add_one_sampled_particle (:4423-4475).  Persistent lanes: a lane whose
 //                         hadron is accepted takes the next work item at once (the acceptance is
 //                         ~1/500 per try, so without the refill a warp would idle on its slowest lane).
+//                         The lane's cell record lives in shared memory (33 floats per lane), the
+//                         per-hadron divisions are done once at the hand-over.  Local charge
+//                         conservation: a positive hadron is followed by its conjugate from the same
+//                         cell under the same maximum (:3517-3546).
 // Random numbers: stream (seed; SAMPLE, species, event, draw), one Philox block per decision:
 //   block 0: cell (w0,w1 -> 53 bit) | one block per try: w0 -> pT^2, w1 -> phi, w2 -> y - eta_s,
-//   w3 -> accept | after 4999 rejected tries: new cell | boost-invariant: rapidity (w0).
+//   w3 -> accept | after 4999 rejected tries: new cell | boost-invariant: rapidity (w0) |
+//   charge-conservation partner: one block per try, never a new cell.
 #ifndef ISS_LEGACY_CUH_
 #define ISS_LEGACY_CUH_
 
