@@ -120,3 +120,32 @@ def test_text_surface_parallel_parse(boost_invariant, built, tmp_path):
     open(case/"surface.dat", "w").write(reflow)
     odd, _ = _dump_lrf(tmp_path, bench.PARAM, "surface.dat", over, 8, "t8c")
     assert np.array_equal(odd.view(np.uint32), one.view(np.uint32))
+
+
+def test_ctypes_mirrors_match_the_c_header(built, tmp_path):
+    """The ctypes structures of iss_b200/capi.py (tests, bench) and of the oracle have the size and
+    field offsets of the C structs in include/iss_cuda.h (compiled here with gcc)."""
+    import ctypes as C
+    pairs = [("iss_species", capi.Species), ("iss_options", capi.Options),
+             ("iss_decay_species", capi.DecaySpecies), ("iss_decay_channel", capi.DecayChannel),
+             ("iss_spectra_options", capi.SpectraOptions), ("iss_legacy_options", capi.LegacyOptions),
+             ("iss_ingest_options", capi.IngestOptions), ("iss_ingest_result", capi.IngestResult),
+             ("iss_counts", capi.Counts)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "iss_cuda.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        lines.append('printf("%s %%zu", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf(" %%zu", offsetof(%s, %s));' % (cname, fname))
+        lines.append('printf("\\n");')
+    lines += ['printf("hadron %zu\\n", sizeof(iss_hadron));', 'return 0; }']
+    src = tmp_path/"abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path/"abi"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(capi.REPO, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    got = {l.split()[0]: [int(x) for x in l.split()[1:]] for l in out if l.strip()}
+    for cname, cls in pairs:
+        want = [C.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert got[cname] == want, cname
+    assert got["hadron"] == [40] == [capi.HADRON_DTYPE.itemsize]
