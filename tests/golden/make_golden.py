@@ -206,6 +206,18 @@ LEGACY = {
                             param="iSS_parameters_ideal.dat",
                             over=["hydro_mode=1", "bulk_deltaf_kind=1", "grouping_particles=0"]),
 }
+# further delta-f modes of the legacy class, pinned on the CPU only so far (tests/test_legacy_cpu.py)
+LEGACY.update({
+    "l3d_bulk2": dict(gen=dict(ncell=40, seed=41, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                      over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=2"]),
+    "l3d_bulk3_norestrict": dict(gen=dict(ncell=40, seed=42, eos=14, rhob=1),
+                                 param="iSS_parameters_CEdeltaf.dat",
+                                 over=["include_deltaf_shear=0", "include_deltaf_bulk=1",
+                                       "bulk_deltaf_kind=3", "restrict_deltaf=0"]),
+    "l3d_bulk4_boltzmann": dict(gen=dict(ncell=40, seed=43, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                                over=["include_deltaf_shear=1", "include_deltaf_bulk=1",
+                                      "bulk_deltaf_kind=4", "quantum_statistics=0"]),
+})
 LEGACY_STATS = {
     # one moving cell with shear stress (Viscous2 fixture, volume scaled down), UrQMD list
     "cell_shear": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=11,
@@ -216,6 +228,10 @@ LEGACY_STATS = {
                      cell="testViscousOneFluidCell2.dat", scale=0.002,
                      over=["include_deltaf_shear=1", "include_deltaf_bulk=0", "bulk_deltaf_kind=1",
                            "local_charge_conservation=1"]),
+    # bulk delta f of kind 3 (1/sqrt(E/T) form) + shear, CPU pin of the oracle only so far
+    "cell_bulk3": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=14,
+                       cell="testViscousOneFluidCell2.dat", scale=0.002,
+                       over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=3"]),
     "surf3d_bulk1": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=12,
                          gen=dict(ncell=300, seed=2025, eos=14, rhob=1, diffusion=1, binary=1),
                          over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=1",
