@@ -81,3 +81,64 @@ def make_case(folder, ncell, seed, eos, boost_invariant=False, rhob=0, diffusion
     write_music_input(folder, eos, bulk, rhob, diffusion, binary)
     write_surface(os.path.join(folder, surface_name), cells, binary, bulk, rhob, diffusion)
     return cells
+
+
+# ---- synthetic 22-moment delta-f table ---------------------------------------------------------
+# The reference loads <tables>/deltaf_tables/{urqmd,smash}/NEoSBQS_22mom_deltafCoeff.dat
+# (reference src/FSSW.cpp:1341-1376) for bulk_deltaf_kind = 20, the kind its own CI parameter file
+# selects (tests/iSS_parameters.dat:19), but the blob is not part of the reference tree.  The
+# loader fixes the format: one header line, then 200 (e) x 200 (n_B) rows of 8 numbers
+# "e  n_B  c_shear  c1 .. c5" with n_B running fastest, a uniform e grid and per-e uniform n_B grids
+# starting at 0.  This generator writes such a file with smooth analytic columns, so that the
+# compiled reference and the engine can be run on identical input.
+def table_22mom():
+    """[200*200][8] float64, rounded to the 7 significant digits the file carries."""
+    ne = nb = 200
+    e = 0.01*(np.arange(ne) + 1.0)                    # GeV/fm^3, like the CE table's grid
+    out = np.zeros((ne, nb, 8))
+    for i in range(ne):
+        nB_max = 0.0097*(e[i]/0.01)**0.92               # widening n_B range with e
+        nB = nB_max*np.arange(nb)/(nb - 1.0)
+        x = nB/nB_max
+        T = 0.150*(e[i]/0.30)**0.25                     # GeV (conformal-like)
+        out[i, :, 0] = e[i]
+        out[i, :, 1] = nB
+        out[i, :, 2] = 1.0/(2.0*T*T*1.15*e[i])*(1.0 + 0.15*x)        # shear: ~1/(2 T^2 (e+P))
+        out[i, :, 3] = 14.0/(e[i] + 0.2)*(1.0 - 0.20*x*x)            # c1 (p0^2 term, with -c2)
+        out[i, :, 4] = 9.0/(e[i] + 0.2)*(1.0 + 0.10*x)               # c2 (m^2 term)
+        out[i, :, 5] = -2.5*x/(e[i] + 0.3)                           # c3 (baryon)
+        out[i, :, 6] = 1.2*x*(1.0 - 0.5*x)/(e[i] + 0.3)              # c4 (strangeness)
+        out[i, :, 7] = -0.6*x/(e[i] + 0.5)                           # c5 (charge)
+    flat = out.reshape(ne*nb, 8)
+    # the file is the contract: keep exactly what "%.6e" preserves
+    return np.array([[float("%.6e" % v) for v in row] for row in flat])
+
+
+def write_22mom_table(path):
+    tab = table_22mom()
+    with open(path, "w") as f:
+        f.write("# e(GeV/fm^3)  rho_B(1/fm^3)  c_shear  c1  c2  c3  c4  c5   (synthetic, "
+                "iss_b200/synthetic.py)\n")
+        for row in tab:
+            f.write("  " + "  ".join("%.6e" % v for v in row) + "\n")
+
+
+def tables_with_22mom(dst, src_tables):
+    """A table folder that mirrors `src_tables` through symlinks and adds the synthetic 22-moment
+    table for both hadron lists.  Returns dst."""
+    os.makedirs(dst, exist_ok=True)
+    for name in os.listdir(src_tables):
+        if name != "deltaf_tables":
+            os.symlink(os.path.join(src_tables, name), os.path.join(dst, name))
+    sd = os.path.join(src_tables, "deltaf_tables")
+    dd = os.path.join(dst, "deltaf_tables")
+    os.makedirs(dd)
+    for name in os.listdir(sd):
+        if name in ("urqmd", "smash"):
+            os.makedirs(os.path.join(dd, name))
+            for f in os.listdir(os.path.join(sd, name)):
+                os.symlink(os.path.join(sd, name, f), os.path.join(dd, name, f))
+            write_22mom_table(os.path.join(dd, name, "NEoSBQS_22mom_deltafCoeff.dat"))
+        else:
+            os.symlink(os.path.join(sd, name), os.path.join(dd, name))
+    return dst

@@ -10,6 +10,7 @@ Restated functions (paths relative to the reference tree, chunshen1987/iSS):
   sf tables / lerp    FSSW::initialize_special_function_arrays, get_special_function_K1/K2/K3/En
                                                                          src/FSSW.cpp:1609-1727
   coef_ce()           FSSW::getCENEOSBQSCoefficients                     src/FSSW.cpp:1433-1487
+  coef_22mom()        FSSW::get22momNEOSBQSCoefficients                  src/FSSW.cpp:1490-1543
   coef_14mom()        FSSW::getbulkvisCoefficients(T, muB)               src/FSSW.cpp:1379-1430
   coef_poly1()        FSSW::getbulkvisCoefficients(T), kind 1            src/FSSW.cpp:1109-1136
   coef_kappa()        FSSW::get_deltaf_qmu_coeff                         src/FSSW.cpp:1571-1606
@@ -49,8 +50,14 @@ class Tables:
         smash = afterburner.lower() == "smash"
         d = os.path.join(table_path, "deltaf_tables")
         self.ce = None
+        self.mom22 = None
         self.mom14 = None
         self.kappa = None
+        if kind == 20:
+            # not part of the reference tree: the tests generate it (iss_b200/synthetic.py) into
+            # the table folder both the compiled reference and the engine read
+            f = os.path.join(d, "smash" if smash else "urqmd", "NEoSBQS_22mom_deltafCoeff.dat")
+            self.mom22 = np.loadtxt(f, skiprows=1)[:200*200].reshape(200*200, 8)
         if kind == 21:
             f = os.path.join(d, "smash" if smash else "urqmd", "NEoSBQS_CE_deltafCoeff.dat")
             self.ce = np.loadtxt(f, skiprows=1)[:200*200].reshape(200*200, 5)
@@ -88,6 +95,35 @@ def sf_lerp(tab, exact, arg):
     if not inside.all():
         val = np.where(inside, val, exact(arg))
     return val
+
+
+def _neos_bqs_interp(tb, Edec, nB, ncol):
+    """bilinear look-up shared by the CE and 22-moment tables (FSSW.cpp:1433-1543): columns
+    2..ncol-1; the index in n_B is clamped from above only (from below as well here: a negative
+    index is undefined behaviour in the reference)."""
+    n = 200
+    de = tb[n, 0] - tb[0, 0]
+    idx_e = ((Edec - tb[0, 0])/de).astype(np.int64)
+    idx_e = np.clip(idx_e, 0, n - 2)
+    Ne1, Ne2 = idx_e*n, (idx_e + 1)*n
+    e_frac = (Edec - tb[Ne1, 0])/de
+    dnB1, dnB2 = tb[Ne1 + 1, 1], tb[Ne2 + 1, 1]
+    i1 = np.clip((nB/dnB1).astype(np.int64), 0, n - 2)
+    i2 = np.clip((nB/dnB2).astype(np.int64), 0, n - 2)
+    f1 = np.minimum(1., (nB - tb[Ne1 + i1, 1])/dnB1)
+    f2 = np.minimum(1., (nB - tb[Ne2 + i2, 1])/dnB2)
+    ip = []
+    for i in range(2, ncol):
+        t1 = tb[Ne1 + i1, i]*(1 - f1) + tb[Ne1 + i1 + 1, i]*f1
+        t2 = tb[Ne2 + i2, i]*(1 - f2) + tb[Ne2 + i2 + 1, i]*f2
+        ip.append(t1*(1. - e_frac) + t2*e_frac)
+    return ip
+
+
+def coef_22mom(tb, Edec, nB):
+    """FSSW::get22momNEOSBQSCoefficients (FSSW.cpp:1490-1543): the six interpolated columns as
+    they are (c[0] multiplies the shear W factor, c[1..5] enter the bulk term)."""
+    return np.stack(_neos_bqs_interp(tb, Edec, nB, 8), axis=1)
 
 
 def coef_ce(tb, Edec, nB):
@@ -169,7 +205,7 @@ def cell_coefficients(cells, tables, kind, include_bulk, include_diff):
     if kind == 21:
         out[:, 0:3] = coef_ce(tables.ce, c[:, F["e"]], c[:, F["nB"]])
     elif kind == 20:
-        raise NotImplementedError("22-moment table is a missing blob of the reference tree")
+        out[:, 0:6] = coef_22mom(tables.mom22, c[:, F["e"]], c[:, F["nB"]])
     if include_bulk == 1 and kind not in (20, 21):
         if kind == 11:
             out[:, 0:3] = coef_14mom(tables.mom14, tables.g14, c[:, F["T"]], c[:, F["muB"]])

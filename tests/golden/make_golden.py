@@ -46,6 +46,10 @@ ONE_CELL = {
     "ideal4": ("14", "iSS_parameters_ideal.dat", "testIdealOneFluidCell4.dat", ["bulk_deltaf_kind=21"]),
     "viscous1": ("91", "iSS_parameters_CEdeltaf.dat", "testViscousOneFluidCell1.dat", []),
     "viscous2": ("9", "iSS_parameters_CEdeltaf.dat", "testViscousOneFluidCell2.dat", []),
+    # the reference's own CI cases 3 and 4: bulk_deltaf_kind = 20 (22-moment), whose table is not in
+    # the reference tree -> run with the synthetic table of iss_b200/synthetic.py (needs_22mom)
+    "viscous3": ("14", "iSS_parameters.dat", "testViscousOneFluidCell3.dat", []),
+    "viscous4": ("14", "iSS_parameters.dat", "testViscousOneFluidCell4.dat", []),
 }
 
 # name -> dict(generator kwargs, parameter file, overrides)
@@ -66,12 +70,33 @@ SYNTH = {
                           param="iSS_parameters_CEdeltaf.dat", over=["hydro_mode=1"]),
     "s3d_boltzmann": dict(gen=dict(ncell=120, seed=5, eos=9), param="iSS_parameters_CEdeltaf.dat",
                           over=["quantum_statistics=0"]),
+    # 22-moment delta f (kind 20) on the synthetic table: shear + bulk, and with diffusion on top
+    "s3d_22mom": dict(gen=dict(ncell=240, seed=2020, eos=14, rhob=1), param="iSS_parameters.dat",
+                      over=[]),
+    "s3d_22mom_diff": dict(gen=dict(ncell=240, seed=2021, eos=14, rhob=1, diffusion=1, binary=1),
+                           param="iSS_parameters.dat", over=["include_deltaf_diffusion=1"]),
 }
 
 
-def workdir():
+def needs_22mom(param, over):
+    """bulk_deltaf_kind = 20 after the overrides?"""
+    kind = None
+    for line in open(os.path.join(FIX, param)):
+        line = line.split("#")[0]
+        if "=" in line and line.split("=")[0].strip() == "bulk_deltaf_kind":
+            kind = int(float(line.split("=")[1]))
+    for kv in over:
+        if kv.startswith("bulk_deltaf_kind="):
+            kind = int(float(kv.split("=")[1]))
+    return kind == 20
+
+
+def workdir(with_22mom=False):
     d = tempfile.mkdtemp(prefix="iss_golden_")
-    os.symlink(REF_TABLES, os.path.join(d, "iSS_tables"))
+    if with_22mom:
+        synthetic.tables_with_22mom(os.path.join(d, "iSS_tables"), REF_TABLES)
+    else:
+        os.symlink(REF_TABLES, os.path.join(d, "iSS_tables"))
     return d
 
 
@@ -95,7 +120,7 @@ def golden_yields(only=None):
     for name, (mi, param, surf, over) in ONE_CELL.items():
         if only and name not in only:
             continue
-        d = workdir()
+        d = workdir(needs_22mom(param, over))
         case = os.path.join(d, "case")
         os.makedirs(case)
         shutil.copy(os.path.join(FIX, "music_input_" + mi), os.path.join(case, "music_input"))
@@ -110,7 +135,7 @@ def golden_yields(only=None):
     for name, spec in SYNTH.items():
         if only and name not in only:
             continue
-        d = workdir()
+        d = workdir(needs_22mom(spec["param"], spec["over"]))
         g = dict(spec["gen"])
         cells = synthetic.make_case(os.path.join(d, "case"), **g)
         run([os.path.join(REF, "ref_driver"), "yields", os.path.join(FIX, spec["param"]), "case",
@@ -142,6 +167,12 @@ STATS = {
     # local charge conservation: positive species paired with their conjugates from the same cell
     "cell_lcc": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=20000, seed=7,
                      cell="viscous2_small", over=["local_charge_conservation=1"]),
+    # 22-moment delta f (kind 20, the reference CI default) on the synthetic table: one cell with
+    # shear + bulk, and a 3+1D surface with n_B
+    "cell_22mom": dict(music="14", param="iSS_parameters.dat", nev=20000, seed=8,
+                       cell="viscous4_small", over=[]),
+    "surf3d_22mom": dict(music=None, param="iSS_parameters.dat", nev=10000, seed=9,
+                         gen=dict(ncell=2000, seed=2020, eos=14, rhob=1), over=[]),
     "surf3d_ce_diff": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=4,
                            gen=dict(ncell=2000, seed=2024, eos=14, rhob=1, diffusion=1, binary=1),
                            over=["include_deltaf_diffusion=1"]),
@@ -162,7 +193,7 @@ def golden_stats(only=None):
     for name, spec in STATS.items():
         if only and name not in only:
             continue
-        d = workdir()
+        d = workdir(needs_22mom(spec["param"], spec["over"]))
         case = os.path.join(d, "case")
         os.makedirs(case)
         extra = {}

@@ -24,7 +24,7 @@ def test_lambert_w_known_answers():
     assert abs(lib.oracle_lambert_w0(C.c_double(np.e)) - 1.0) < 1e-15
 
 
-@pytest.mark.parametrize("name", lc.YIELD_CASES + lc.ORACLE_CASES)
+@pytest.mark.parametrize("name", lc.YIELD_CASES)
 def test_oracle_yields_and_maxima_match_reference(name):
     g = cases.load(name, "legacy")
     par = lc.parameters(g)
@@ -33,7 +33,7 @@ def test_oracle_yields_and_maxima_match_reference(name):
     coef = lgo.cell_coefficients(g["lab"], opt, lgo.load_kappa())
     y = lgo.yields(g["lab"], sp, opt, coef)
     ref = g["yields"]
-    assert (ref < 0).any() or name in lc.ORACLE_CASES   # not clamped (cells with u.dsigma < 0)
+    assert (ref < 0).any() or name in lc.MORE_CASES   # not clamped (cells with u.dsigma < 0)
     scale = np.abs(ref).max(axis=1, keepdims=True)
     assert (np.abs(y - ref)/scale).max() < 1e-12
     mx = lgo.estimate_maximum(g["lab"], coef, sp, opt, lgo.load_z_table())
@@ -99,7 +99,7 @@ def test_facade_refuses_what_the_legacy_mode_does_not_cover(built, tmp_path):
         assert text in r.stdout + r.stderr, (extra, r.stdout[-400:])
 
 
-@pytest.mark.parametrize("kind,name", [("legacy", n) for n in lc.YIELD_CASES + lc.ORACLE_CASES]
+@pytest.mark.parametrize("kind,name", [("legacy", n) for n in lc.YIELD_CASES]
                          + [("legacy_stats", n) for n in lc.STATS_CASES])
 def test_host_keeps_the_reference_lab_frame_cells(kind, name, built, tmp_path):
     """With MC_sampling = 2 iSS::read_in_FO_surface keeps the lab-frame (Milne) cells

@@ -55,6 +55,7 @@ def test_legacy_yields_and_maxima_match_reference(name, built):
 
 @pytest.mark.parametrize("name,nev,extra", [
     ("l3d_shear", 300, {}), ("l3d_bulk1_diff", 300, {}), ("l2d_ideal_smash", 40, {}),
+    ("l3d_bulk2", 300, {}), ("l3d_bulk3_norestrict", 300, {}), ("l3d_bulk4_boltzmann", 300, {}),
     ("l3d_shear", 300, {"local_charge_conservation": 1}),
     ("l2d_ideal_smash", 40, {"local_charge_conservation": 1})])
 def test_legacy_hadrons_match_oracle(name, nev, extra, built):

@@ -49,7 +49,8 @@ def mode_of(g):
 def test_oracle_yields_match_reference(name):
     g = cases.load(name)
     m = mode_of(g)
-    tabs = orc.Tables(afterburner=m["afterburner"], kind=m["kind"], include_bulk=m["include_bulk"],
+    tabs = orc.Tables(table_path=cases.tables_for(g), afterburner=m["afterburner"], kind=m["kind"],
+                      include_bulk=m["include_bulk"],
                       include_diff=m["include_diff"])
     y = orc.yields(g["lrf"], species_array(g), tabs, m["kind"], m["include_bulk"], m["include_diff"])
     ref = g["yields"]

@@ -28,14 +28,17 @@ CASES = [("viscous2", 3, {}), ("s3d_ce", 3000, {}), ("s3d_ce_diff", 3000, {}),
          ("s3d_14mom", 3000, {}), ("s2d_smash_ce", 400, {}), ("s3d_bulk1", 3000, {}),
          ("s3d_boltzmann", 3000, {}), ("s3d_ideal_b", 2000, {"local_charge_conservation": 1}),
          ("s2d_smash_ce", 300, {"local_charge_conservation": 1}),
-         ("s3d_ce", 2000, {"dN_dy_sampling_model": 1})]
+         ("s3d_ce", 2000, {"dN_dy_sampling_model": 1}),
+         # bulk_deltaf_kind = 20 (22-moment, synthetic table): shear c0 W, bulk with B, S, Q terms
+         ("s3d_22mom", 3000, {}), ("s3d_22mom_diff", 3000, {}), ("viscous4", 3, {}),
+         ("s3d_22mom", 2000, {"local_charge_conservation": 1})]
 
 
 def prepare(capi, name, tmp_path, extra):
     g = cases.load(name)
     param, surf, over = cases.materialise(g, str(tmp_path))
     over.update(extra)
-    s = capi.Sampler(str(tmp_path), param, surf, **over)
+    s = capi.Sampler(str(tmp_path), param, surf, table_path=cases.tables_for(g), **over)
     assert s.read_in_FO_surface() == 0
     s.set_random_seed(1)
     assert s.prepare_sampler() == 0
@@ -86,7 +89,7 @@ def test_hadrons_match_oracle(name, nev, extra, built, tmp_path):
 
         # ---- hadron by hadron
         lrf = s.lrf_surface()
-        tabs = orc.Tables(afterburner=m["afterburner"], kind=m["kind"],
+        tabs = orc.Tables(table_path=cases.tables_for(g), afterburner=m["afterburner"], kind=m["kind"],
                           include_bulk=m["include_bulk"], include_diff=m["include_diff"])
         coef = orc.cell_coefficients(lrf, tabs, m["kind"], m["include_bulk"], m["include_diff"])
         opt = orc.make_options(hydro_mode=m["hydro_mode"], include_shear=m["include_shear"],

@@ -19,7 +19,7 @@ def test_yields_match_reference(name, built, tmp_path):
     capi = built
     g = cases.load(name)
     param, surf, over = cases.materialise(g, str(tmp_path))
-    s = capi.Sampler(str(tmp_path), param, surf, **over)
+    s = capi.Sampler(str(tmp_path), param, surf, table_path=cases.tables_for(g), **over)
     try:
         assert s.read_in_FO_surface() == 0
         s.set_random_seed(1)
