@@ -275,7 +275,7 @@ int run_decay(iss_handle *h, uint64_t seed) {
     }
     int rc = ensure_capacity(h, &h->d_decay_cnt, &h->decay_cnt_cap, n_in + 1 + nev + 1);
     if (rc) return rc;
-    if (!h->d_counters) ISS_CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned long long)*8));
+    if (!h->d_counters) ISS_CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned long long)*N_COUNTERS));
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_counters + 4, 0, sizeof(unsigned long long)*2, h->stream));
 
     DecayArgs A;

@@ -63,6 +63,7 @@ void free_surface(iss_handle *h) {
     cudaFree(h->d_cdflev_g); h->d_cdflev_g = nullptr; h->cdflev_g_bytes = 0;
     h->have_yields = false;
     h->have_local_yields = false;
+    h->cellrec_valid = false;
     h->have_batch = false;
 }
 
@@ -178,6 +179,8 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_mult); cudaFree(h->d_off_out); cudaFree(h->d_off_work);
     cudaFree(h->d_hadbuf[0]); cudaFree(h->d_hadbuf[1]); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
     cudaFree(h->d_tasks); cudaFree(h->d_sampler_args); cudaFree(h->d_hints);
+    cudaFree(h->d_task_slot); cudaFree(h->d_cellid); cudaFree(h->d_cellcnt); cudaFree(h->d_cellrec);
+    cudaFree(h->d_wire[0]); cudaFree(h->d_wire[1]);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
     cudaFree(h->d_qa); cudaFree(h->d_trace);
     cudaFree(h->d_own); cudaFree(h->d_wlist);
@@ -377,6 +380,8 @@ int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data, int64
             t.trunc = static_cast<int>(grid4[1]);
             t.e0 = data[0];
             t.de = data[1] - data[0];
+            t.de_build = t.de;
+            t.generated = 0;
             t.exp_m0 = exp(t.m0);
             {
                 const bool fermion = (r >= 3);

@@ -16,7 +16,9 @@ namespace iss {
 constexpr double HBARC = 0.197327053;     // reference data_struct.h:9
 constexpr int TILE = 1024;                // cells per CDF tile (scan granularity)
 constexpr int MAX_SPECIES = 1024;
-constexpr int MAIL_WORDS = 64;          // [0..7] sampler counters, [8] scan total, [16..] spare
+constexpr int MAIL_WORDS = 64;          // [0..7] sampler counters, [8] scan total, [16..17] decay errors,
+                                        // [24..25] give-up info
+constexpr int N_COUNTERS = 16;          // device counters: [0..7] see SamplerArgs, [8..9] give-up info
 
 // special-function table grid (FSSW.cpp:1611-1615)
 struct SfGrid {
@@ -42,6 +44,8 @@ struct MomentumTable {      // one Boson/FermionMomentumSampler instance
     double a[10];           // exp(-m0 n), n = 0..9
     double inv_n1[10];      // 1/(n+1)
     double inv_denom0, inv_de;
+    double de_build;        // Etilde_[i] = fma(i, de_build, e0) for tables generated on the device
+    int generated;          // 0: uploaded by the host (arbitrary abscissa, never copied to smem)
 };
 
 constexpr int CELL_STRIDE = 32;   // floats per AoS cell record (28 fields + t, z + 2 spare)
@@ -181,7 +185,16 @@ struct iss_handle {
     int64_t event_off_cap = 0;
     void *d_sampler_args = nullptr;
     void *d_hints = nullptr; size_t hints_bytes = 0;
-    void *d_tasks = nullptr; size_t tasks_bytes = 0;     // sampler task list of the batch
+    void *d_tasks = nullptr; size_t tasks_bytes = 0;     // cell-sorted task list of the batch (Task32)
+    uint32_t *d_task_slot = nullptr;                     // output slot of every task (same capacity)
+    int32_t *d_cellid = nullptr;                         // cell of every work item (same capacity)
+    unsigned long long *d_cellcnt = nullptr; size_t cellcnt_bytes = 0;  // [ncell + 2] histogram / offsets
+    void *d_cellrec = nullptr; size_t cellrec_bytes = 0; // [ncell] CellRec (sampler.cu)
+    bool cellrec_valid = false;                          // reset with the yields
+    // 20-byte wire records beside the full ones (iss_cuda_set_wire_records), double-buffered like them
+    bool wire_on = false;
+    uint32_t *d_wire[2] = {nullptr, nullptr};
+    int64_t wire_cap[2] = {0, 0};
     unsigned long long *d_counters = nullptr;   // [8] tries, redraws, error flags...
     bool have_batch = false;
     bool trace = false;
@@ -282,6 +295,7 @@ int run_yields_local(iss_handle *h);
 int run_yields_finish(iss_handle *h);
 int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev);
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t total);
+int build_cellrec(iss_handle *h);
 int run_legacy_yields(iss_handle *h, double *yields_host, double *maximum_host);
 int run_decay(iss_handle *h, uint64_t seed);
 int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate);

@@ -113,7 +113,7 @@ __global__ void build_momentum_table_kernel(double *tab, int n, double e0, doubl
                                             int trunc, int fermion) {
     const int i = blockIdx.x*blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double Et = e0 + i*de;
+    const double Et = __fma_rn(static_cast<double>(i), de, e0);     // = e0 + i*de as compiled so far
     double c0, c1, c2;
     if (fermion) {
         cdf_012<true>(Et, m0, trunc, c0, c1, c2);
@@ -158,6 +158,8 @@ static int ensure_momentum_tables(iss_handle *h) {
         t.m0 = m0;
         t.e0 = E_min;
         t.de = (E_min + dE) - E_min;    // Etilde_[1] - Etilde_[0]
+        t.de_build = dE;
+        t.generated = 1;
         t.exp_m0 = exp(m0);
         t.denom0 = fermion ? (1. + exp(-m0)) : (1. - exp(-m0));
         t.inv_denom0 = 1.0/t.denom0;
@@ -217,21 +219,55 @@ __global__ void event_offset_kernel(const int64_t *__restrict__ off_out, int ns,
 }
 
 // ---------------------------------------------------------------------------------
-// K5: sampler = set-up kernel (one thread per hadron) + persistent proposal kernel
+// K5: sampler = cell pick -> cell-sorted task list -> persistent proposal kernel
 // ---------------------------------------------------------------------------------
-// One hadron to sample, produced by setup_kernel and consumed by propose_kernel (48 bytes).
-struct __align__(16) Task {
-    int64_t out_slot;       // index of the output record
+// One hadron to sample: 32 bytes (one DRAM sector), written by setup_kernel at its position in
+// the CELL-SORTED task list and streamed into shared memory by propose_kernel (cp.async.bulk).
+// The output slot travels beside it in task_slot[], so results do not depend on the order.
+struct __align__(16) Task32 {
     double m_term;          // CDF(a) term of MomentumSamplerBase::Sample_a_momentum
     double cdf_max;
-    int32_t cell;
-    int32_t s;              // species (sampling order)
+    uint32_t cell;          // (local) cell index
     uint32_t event;         // global event index
     uint32_t draw;          // index of the hadron inside (event, species)
-    int32_t tab_idx;        // momentum table (bits 0..2) | idx_min << 3; < 0: table range error
+    uint16_t s;             // species (sampling order)
+    uint16_t tab_idx;       // momentum table (bits 0..2) | idx_min << 3; TASK_RANGE_ERROR: table range error
+};
+static_assert(sizeof(Task32) == 32, "Task32 must stay 32 bytes");
+constexpr uint16_t TASK_RANGE_ERROR = 0xFFFFu;
+
+// Everything the proposal kernel needs from a cell, in final form: the fields of the try, the
+// emit fields and every quotient of the accept test that does not depend on the proposed momentum
+// (the reference recomputes them per sample, FSSW.cpp:1861-1913).  Built once per yields
+// computation by build_cellrec_kernel; 160 bytes = 10 chunks of 16 bytes, chunks 0..8 are copied
+// verbatim into the lane's shared-memory slot, chunk 9 is consumed at task hand-over.
+struct __align__(16) CellRec {
+    float4 da;              // [0] dsigma_mu (LRF)
+    float4 pa;              // [1] pixx, pixy, pixz, piyy
+    float4 pb;              // [2] piyz, qx, qy, qz
+    float4 u4;              // [3] ut, ux, uy, uz
+    float4 pos;             // [4] tau, x, y, eta
+    float2 tz;              // [5] t, z of the cell
+    double inv_T;           //     1/max(T, 1e-16)
+    double inv_dsig;        // [6] 1/(|dsigma_0| + |dsigma_vec|)
+    double shear;           //     shear delta-f prefactor (FSSW.cpp:1898-1913)
+    double cb;              // [7] c0 * Pi of the CE bulk delta f (kinds 1, 21)
+    double c1;
+    double inv_kappa;       // [8] 1/kappa_B
+    double prefq;           //     n_B/(e + P) (float division, FSSW.cpp:1866)
+    float4 th;              // [9] T, muB, muS, muQ
+};
+static_assert(sizeof(CellRec) == 160, "CellRec must stay 160 bytes");
+constexpr int CELLREC_SLOT_CHUNKS = 9;
+
+// what the proposal kernel reads per species (shared memory, 32 B)
+struct __align__(16) PropSpecies {
+    double mass, mass2;
+    int32_t pid;
+    int16_t baryon, strange, charge, sign;
     int32_t pad;
 };
-static_assert(sizeof(Task) == 48, "Task must stay 48 bytes");
+static_assert(sizeof(PropSpecies) == 32, "PropSpecies must stay 32 bytes");
 
 struct SamplerArgs {
     const float *cells;             // [ncell][CELL_STRIDE]
@@ -254,11 +290,18 @@ struct SamplerArgs {
     int hydro_mode, lcc;
     double y_LB, y_RB;
     uint64_t seed;
-    Task *tasks;                    // [nwork]
+    const CellRec *cellrec;         // [ncell] per-cell record of the proposal kernel
+    int32_t *cellid;                // [nwork] cell of every work item (pick_kernel -> setup_kernel)
+    unsigned long long *cell_cnt;   // [ncell + 1] cell histogram -> exclusive offsets -> bucket cursors
+    Task32 *tasks;                  // [nstage*RING_TASKS] cell-sorted task list
+    uint32_t *task_slot;            // [nstage*RING_TASKS] output slot of every task
+    uint32_t *wire;                 // optional [n_out][5]: 20-byte wire records (iss_wire_hadron)
+    unsigned long long *giveup_info;    // [2] (cell, species) of a hadron the sampler gave up on
+    int mt_smem;                    // regime-0 tables were generated on the device (uniform abscissa)
     const int2 *hints;              // [ceil(nwork/SETUP_THREADS)] (species, event) of item b*SETUP_THREADS
     iss_hadron *out;
-    unsigned long long *counters;   // [0] task cursor, [1] tries, [2] redraws, [3] range errors,
-                                    // [4],[5] decay errors, [6] hadrons given up
+    unsigned long long *counters;   // [0] task cursor (legacy), [1] tries, [2] redraws, [3] range errors,
+                                    // [4],[5] decay errors, [6] hadrons given up, [7] foreign re-draws
     int32_t *trace_cell;            // optional [n_out]
     int32_t *trace_tries;           // optional [n_out]
     // surface-chunk mode (iss_cuda_set_surface_chunk): cells/cdf/cdflev above are those of the
@@ -275,7 +318,6 @@ struct SamplerArgs {
 
 constexpr int SETUP_THREADS = 256;
 constexpr int SAMPLER_THREADS = 768;     // one CTA of 24 warps per SM (640: 16.8 ms, 1024: 16.2 ms, 768: 15.5 ms on C4) (96 KB of tables in smem)
-constexpr int TASK_CHUNK = 128;         // tasks a warp reserves at a time
 constexpr int MAX_IMPATIENCE = 5000;    // FSSW.cpp:1872
 constexpr int MAX_TRIES_PER_HADRON = 2000000;   // safety valve, see propose_kernel
 
@@ -442,6 +484,14 @@ __device__ __forceinline__ double species_mu(const DeviceSpecies &p, int qsign, 
     return fmin(mass, static_cast<double>(muf));
 }
 
+__device__ __forceinline__ double species_mu_bsq(int B, int S, int Q, float muB, float muS, float muQ,
+                                                 double mass) {
+    const float muf = __fadd_rn(__fadd_rn(__fmul_rn(static_cast<float>(B), muB),
+                                          __fmul_rn(static_cast<float>(S), muS)),
+                                __fmul_rn(static_cast<float>(Q), muQ));
+    return fmin(mass, static_cast<double>(muf));
+}
+
 __device__ __forceinline__ uint32_t sample_stream_word3(int s) {
     return (static_cast<uint32_t>(STREAM_SAMPLE) << 24) | static_cast<uint32_t>(s);
 }
@@ -545,10 +595,96 @@ __global__ void chunk_compact_kernel(const int64_t *__restrict__ own_pos, int64_
     if (own_pos[w + 1] != p) wlist[p] = w;
 }
 
+// per-cell record of the proposal kernel from the AoS cell record and the delta-f coefficients
+__global__ void build_cellrec_kernel(const float *__restrict__ cells, const double *__restrict__ cellcoef,
+                                     int64_t ncell, ModeFlags mode, CellRec *__restrict__ out) {
+    const int64_t c = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const float4 *cr = reinterpret_cast<const float4 *>(cells + c*CELL_STRIDE);
+    const float4 pos = __ldg(cr + 0), da = __ldg(cr + 1), u4 = __ldg(cr + 2);
+    const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
+    const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
+    const float4 tzq = __ldg(cr + 7);       // t, z, spare, spare
+    const double2 *cop = reinterpret_cast<const double2 *>(cellcoef + c*COEF_STRIDE);
+    const double2 c01 = __ldg(cop);
+    const double c2 = __ldg(&cop[1].x), kappa = __ldg(&cop[3].x);
+    CellRec r;
+    r.da = da;
+    r.pa = __ldg(cr + 5);
+    r.pb = __ldg(cr + 6);
+    r.u4 = u4;
+    r.pos = pos;
+    r.tz = make_float2(tzq.x, tzq.y);
+    const double Tdec = th0.y;
+    r.inv_T = 1.0/fmax(1e-16, Tdec);
+    // float arithmetic inside the sqrt as in FSSW.cpp:1867-1870
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
+                               __fmul_rn(da.w, da.w));
+    r.inv_dsig = 1.0/(fabs(static_cast<double>(da.x)) + sqrt(static_cast<double>(d2)));
+    // shear delta f prefactor (FSSW.cpp:1898-1913): CE W/(2 eta_hat p0 T), 22-moment W c0,
+    // otherwise W/(2 T^2 (e+P))
+    if (mode.neos == 1) r.shear = 1.0/(2.*c2);
+    else if (mode.neos == 0) r.shear = c01.x;
+    else r.shear = 1.0/(2.0*Tdec*Tdec*(static_cast<double>(__fadd_rn(th0.x, th0.z))));
+    // CE bulk delta f (kinds 1, 21): c0 * Pi with Pi in GeV/fm^3 (21) or fm^-4 (1)
+    const double bulkPi = (mode.kind == 21) ? static_cast<double>(th.w)
+                                            : static_cast<double>(th.w)/HBARC;
+    r.cb = c01.x*bulkPi;
+    r.c1 = c01.y;
+    r.inv_kappa = 1.0/kappa;
+    r.prefq = __fdiv_rn(th0.w, __fadd_rn(th0.x, th0.z));   // float division as in FSSW.cpp:1866
+    r.th = make_float4(th0.y, th.x, th.y, th.z);
+    out[c] = r;
+}
+
+// ---- cell-sorted task list -----------------------------------------------------------------------
+// The hadron list is a pure function of (seed, event, species, draw), so the ORDER in which the
+// hadrons of a batch are sampled is free.  The tasks are bucketed by cell (counting sort on the
+// cell id: histogram in pick_kernel, exclusive scan, scatter in setup_kernel): consecutive tasks
+// then share their cell record, which the proposal kernel finds in L1/L2 instead of gathering
+// 160 random bytes per hadron from DRAM.  The order inside a cell depends on atomic timing; the
+// results do not (the output slot travels with the task).
+
 // K5a: one thread per hadron of the batch: identity (species, event, draw) from the species-major
-// work offsets, output slot, cell choice (first block of the hadron's stream) and the two series
-// values of the |p| sampler.  Massively parallel, so the dependent loads of the two binary
-// searches are hidden by occupancy instead of stalling the proposal loop.
+// work offsets, cell choice (first block of the hadron's stream), histogram of the cells.
+__global__ void __launch_bounds__(SETUP_THREADS)
+pick_kernel(const SamplerArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    int64_t *sp_off = reinterpret_cast<int64_t *>(smem_raw);      // off_work[s*nev], s = 0..ns
+    for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
+        sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
+    __syncthreads();
+    const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = static_cast<int64_t>(blockIdx.x)*blockDim.x; base < A.nwork;
+         base += static_cast<int64_t>(gridDim.x)*blockDim.x) {
+        const int64_t j = base + threadIdx.x;
+        const bool valid = j < A.nwork;
+        int cell = -1 - lane;           // distinct dummies for the lanes past the end
+        if (valid) {
+            // surface-chunk mode: the rank's j-th hadron is work item wlist[j] of the whole batch
+            const int64_t w = A.chunk ? __ldg(&A.wlist[j]) : j;
+            int s;
+            int64_t ev, k;
+            work_identity(A, sp_off, w, s, ev, k);
+            uint32_t w0, w1, w2, w3;
+            philox_block(0u, static_cast<uint32_t>(k), static_cast<uint32_t>(A.ev_begin + ev),
+                         sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
+            cell = static_cast<int>(pick_cell(A, s, u53(w0, w1)));   // chunk mode: owned, hence >= 0
+            A.cellid[j] = cell;
+        }
+        // one atomic per distinct cell of the warp (one-cell surfaces put every hadron in one bin)
+        const unsigned peers = __match_any_sync(full, cell);
+        if (valid && lane == __ffs(peers) - 1)
+            atomicAdd(&A.cell_cnt[cell], static_cast<unsigned long long>(__popc(peers)));
+    }
+}
+
+// K5b: again one thread per hadron, after the exclusive scan of the histogram: the two series
+// values of the |p| sampler (MomentumSamplerBase::update_cache), the output slot, and the task
+// written to its place in the cell-sorted list.  Massively parallel, so the dependent loads are
+// hidden by occupancy instead of stalling the proposal loop.
 __global__ void __launch_bounds__(SETUP_THREADS)
 setup_kernel(const SamplerArgs A) {
     extern __shared__ unsigned char smem_raw[];
@@ -558,64 +694,121 @@ setup_kernel(const SamplerArgs A) {
     for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
         sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
     __syncthreads();
-    const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long my_range = 0;
-    for (int64_t j = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x; j < A.nwork;
-         j += static_cast<int64_t>(gridDim.x)*blockDim.x) {
-        // surface-chunk mode: the rank's j-th hadron is work item wlist[j] of the whole batch
-        const int64_t w = A.chunk ? __ldg(&A.wlist[j]) : j;
-        int s;
-        int64_t ev, k;
-        work_identity(A, sp_off, w, s, ev, k);
-        const DeviceSpecies p = sp[s];
-        const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
-        // position among the hadrons of (event, species) this rank writes
-        const int64_t k_out = A.chunk ? (__ldg(&A.own_pos[w]) - __ldg(&A.own_pos[w - k])) : k;
-        Task t;
-        t.out_slot = __ldg(&A.off_out[ev*A.ns + s]) + k_out*mult;
-        t.s = s;
-        t.event = static_cast<uint32_t>(A.ev_begin + ev);
-        t.draw = static_cast<uint32_t>(k);
-        uint32_t w0, w1, w2, w3;
-        philox_block(0u, t.draw, t.event, sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
-        const int64_t cell = pick_cell(A, s, u53(w0, w1));    // chunk mode: owned, hence >= 0
-        t.cell = static_cast<int32_t>(cell);
-        // T and the chemical potentials come from the 16-byte-per-cell copy (15 MB at C4: it stays in
-        // L2), not from the 128-byte record the proposal kernel gathers from DRAM
-        const float4 tm = __ldg(A.thermo + cell);
-        const float4 th = make_float4(tm.y, tm.z, tm.w, 0.f);
-        MomSetup M;
-        const bool ok = momentum_setup(A.mt, p.mass, p.sign, tm.x, species_mu(p, 1, th, p.mass), M);
-        t.m_term = M.m_term;
-        t.cdf_max = M.cdf_max;
-        t.tab_idx = ok ? (M.tab | (M.idx_min << 3)) : -1;
-        t.pad = 0;
-        if (!ok) my_range++;
-        A.tasks[j] = t;
+    for (int64_t base = static_cast<int64_t>(blockIdx.x)*blockDim.x; base < A.nwork;
+         base += static_cast<int64_t>(gridDim.x)*blockDim.x) {
+        const int64_t j = base + threadIdx.x;
+        const bool valid = j < A.nwork;
+        int cell = -1 - lane;
+        Task32 t;
+        uint32_t slot = 0;
+        if (valid) {
+            const int64_t w = A.chunk ? __ldg(&A.wlist[j]) : j;
+            int s;
+            int64_t ev, k;
+            work_identity(A, sp_off, w, s, ev, k);
+            cell = __ldg(&A.cellid[j]);
+            const DeviceSpecies p = sp[s];
+            const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
+            // position among the hadrons of (event, species) this rank writes
+            const int64_t k_out = A.chunk ? (__ldg(&A.own_pos[w]) - __ldg(&A.own_pos[w - k])) : k;
+            slot = static_cast<uint32_t>(__ldg(&A.off_out[ev*A.ns + s]) + k_out*mult);
+            // T and the chemical potentials come from the 16-byte-per-cell copy (15 MB at C4: it
+            // stays in L2)
+            const float4 tm = __ldg(A.thermo + cell);
+            const float4 th = make_float4(tm.y, tm.z, tm.w, 0.f);
+            MomSetup M;
+            const bool ok = momentum_setup(A.mt, p.mass, p.sign, tm.x, species_mu(p, 1, th, p.mass), M);
+            t.m_term = M.m_term;
+            t.cdf_max = M.cdf_max;
+            t.cell = static_cast<uint32_t>(cell);
+            t.event = static_cast<uint32_t>(A.ev_begin + ev);
+            t.draw = static_cast<uint32_t>(k);
+            t.s = static_cast<uint16_t>(s);
+            t.tab_idx = ok ? static_cast<uint16_t>(M.tab | (M.idx_min << 3)) : TASK_RANGE_ERROR;
+            if (!ok) my_range++;
+        }
+        // position in the cell's bucket: one atomic per distinct cell of the warp
+        const unsigned peers = __match_any_sync(full, cell);
+        const int leader = __ffs(peers) - 1;
+        unsigned long long bucket = 0;
+        if (valid && lane == leader)
+            bucket = atomicAdd(&A.cell_cnt[cell], static_cast<unsigned long long>(__popc(peers)));
+        bucket = __shfl_sync(full, bucket, leader);
+        if (valid) {
+            const int64_t pos = static_cast<int64_t>(bucket) + __popc(peers & lt_mask);
+            uint4 *dst = reinterpret_cast<uint4 *>(A.tasks + pos);
+            const uint4 *src = reinterpret_cast<const uint4 *>(&t);
+            dst[0] = src[0];
+            dst[1] = src[1];
+            A.task_slot[pos] = slot;
+        }
     }
     if (my_range) atomicAdd(&A.counters[3], my_range);
 }
 
+// ---- bulk-async plumbing of the proposal kernel (mbarrier + cp.async.bulk, PTX ISA 8.x) ----------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// global -> shared bulk copy (bytes: multiple of 16, both addresses 16-byte aligned); completion
+// is signalled on the mbarrier as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_addr(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // what a lane of the proposal kernel carries
 struct LaneState {
-    int64_t out_slot;
+    uint32_t slot;          // index of the output record
     int s;
     int cell;
     BlockStream rng;
     MomSetup M;
-    double dsigma_fac;
     int tries;
     int total_tries;
     int qsign;      // +1 primary, -1 charge-conservation partner (flips B,S,Q)
     double eta_s;   // boost-invariant mode: eta_s of the primary, reused by its partner
 };
 
+// chunks 0..8 of a cell record -> the lane's shared-memory slot ([chunk][lane] layout: 16-byte
+// accesses of a warp are conflict free)
+__device__ __forceinline__ void lane_slot_fill(float4 *lc, int tid, const CellRec *rec) {
+    const float4 *src = reinterpret_cast<const float4 *>(rec);
+#pragma unroll
+    for (int c = 0; c < CELLREC_SLOT_CHUNKS; c++) lc[c*SAMPLER_THREADS + tid] = __ldg(src + c);
+}
+
 // Rare paths of the proposal kernel, kept out of line so that the hot loop stays small.
 // (a) the reference's "impatience": after 4999 rejected tries a NEW cell is drawn (FSSW.cpp:1017-1018)
 // (b) local charge conservation: the partner is sampled from the same cell with conjugate
 //     quantum numbers (FSSW.cpp:1035-1048)
-__device__ __noinline__ bool lane_new_setup(const SamplerArgs *Ag, LaneState &L, const DeviceSpecies &p,
-                                            bool redraw_cell, uint32_t key0, uint32_t key1) {
+__device__ __noinline__ bool lane_new_setup(const SamplerArgs *Ag, LaneState &L, double mass, int sign,
+                                            int B, int S, int Q, bool redraw_cell, uint32_t key0,
+                                            uint32_t key1, float4 *lc, int tid) {
     // Ag: copy of the kernel arguments in global memory (taking the address of the by-value
     // kernel parameter would force a 1.2 KB per-thread stack copy)
     const SamplerArgs &A = *Ag;
@@ -627,22 +820,18 @@ __device__ __noinline__ bool lane_new_setup(const SamplerArgs *Ag, LaneState &L,
         if (c < 0) {
             // surface-chunk mode: the new cell belongs to another rank (include/iss_cuda.h)
             atomicAdd(&A.counters[7], 1ull);
-            float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
+            float2 *dst = reinterpret_cast<float2 *>(A.out + L.slot);
 #pragma unroll
             for (int q = 0; q < 5; q++) dst[q] = make_float2(0.f, 0.f);
             return false;
         }
         L.cell = static_cast<int>(c);
+        lane_slot_fill(lc, tid, A.cellrec + L.cell);
     }
-    const float4 *cr = reinterpret_cast<const float4 *>(A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
-    const float4 da = __ldg(cr + 1);
-    const float4 th0 = __ldg(cr + 3);
-    const float4 th = __ldg(cr + 4);
-    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
-                               __fmul_rn(da.w, da.w));
-    L.dsigma_fac = fabs(static_cast<double>(da.x)) + sqrt(static_cast<double>(d2));
+    const float4 th = __ldg(&A.cellrec[L.cell].th);      // T, muB, muS, muQ
     L.tries = 1;
-    return momentum_setup(A.mt, p.mass, p.sign, th0.y, species_mu(p, L.qsign, th, p.mass), L.M);
+    return momentum_setup(A.mt, mass, sign, th.x,
+                          species_mu_bsq(L.qsign*B, L.qsign*S, L.qsign*Q, th.y, th.z, th.w, mass), L.M);
 }
 
 // SPEC selects a compile-time specialisation of the run-time mode flags (smaller and faster
@@ -662,9 +851,53 @@ struct SpecMode {
     static constexpr int lcc = 0;
 };
 
-// K5b: persistent proposal kernel.  Every lane owns one hadron and repeats the reference's try
+// shared-memory copy of a regime-0 momentum table: [n][3] = CDF_0, CDF_1, CDF_2; the abscissa is
+// recomputed as fma(i, dE, E_0), the expression build_momentum_table_kernel stores
+__device__ __forceinline__ double table_F3(const double *tb, int i, double w1, double w0, double m_term) {
+    const double c0 = tb[3*i], c1 = tb[3*i + 1], c2 = tb[3*i + 2];
+    return c2 + w1*c1 + w0*c0 - m_term;
+}
+
+// MomentumSamplerBase::inverse_CDF (MomentumSamplerBase.cpp:61-93) on the shared-memory copy
+__device__ __forceinline__ double inverse_cdf_smem(const double *tb, int n, double e0, double dE,
+                                                   const MomSetup &M, double r) {
+    const double w1 = 2.*M.mu_tilde;
+    int lo = M.idx_min;
+    int hi = n - 1;
+    double r_min = table_F3(tb, lo, w1, M.w0, M.m_term);
+    double r_max = M.cdf_max;
+    while (hi - lo > 1) {
+        const int mid = (hi + lo)/2;
+        const double r_mid = table_F3(tb, mid, w1, M.w0, M.m_term);
+        if (r < r_mid) {
+            hi = mid;
+            r_max = r_mid;
+        } else {
+            lo = mid;
+            r_min = r_mid;
+        }
+    }
+    double E0 = __fma_rn(static_cast<double>(lo), dE, e0);
+    if (E0 < M.a_min) {
+        E0 = M.a_min;
+        r_min = 0.;
+    }
+    const double Ehi = __fma_rn(static_cast<double>(hi), dE, e0);
+    return E0 + (Ehi - E0)/fmax(1e-16, (r_max - r_min))*(r - r_min);
+}
+
+constexpr int RING_TASKS = 16;          // tasks per stage of a warp's task ring
+constexpr int RING_STAGES = 2;
+constexpr uint32_t RING_STAGE_BYTES = RING_TASKS*(sizeof(Task32) + sizeof(uint32_t));
+
+// K5c: persistent proposal kernel.  Every lane owns one hadron and repeats the reference's try
 // (|p| proposal, direction, accept test) until it is accepted, then boosts, emits the record and
 // immediately takes the next task: all 32 lanes of a warp stay busy whatever the acceptance rate.
+// Tasks: warp w of the grid owns the stages w, w + W, w + 2W, ... (16 consecutive tasks each) of the
+// cell-sorted list; lane 0 streams them two stages ahead into the warp's shared-memory ring with
+// cp.async.bulk, completion on one mbarrier per stage, so that a task hand-over is a
+// shared-memory read + one L1/L2-resident cell record (copied into the lane's slot with cp.async)
+// instead of a chain of three dependent DRAM gathers.
 template <int MIN_BLOCKS, int SPEC>
 __global__ void __launch_bounds__(SAMPLER_THREADS, MIN_BLOCKS)
 propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
@@ -678,143 +911,142 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     const int hydro_mode = SM::generic ? A.hydro_mode : SM::hydro_mode;
     const int lcc = SM::generic ? A.lcc : SM::lcc;
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
+    constexpr int NWARP = SAMPLER_THREADS/32;
 
-    // shared memory: species table, then the two regime-0 momentum tables (boson 32 KB, fermion
-    // 64 KB): they serve every species with (m - mu)/T < 30 and take the 11-step bisection of each
-    // proposal off the L1/LSU gather path
+    // shared memory: per-lane cell slots, the two regime-0 momentum tables without their abscissa
+    // (boson 24 KB, fermion 48 KB: they serve every species with (m - mu)/T < 30 and take the
+    // 11-step bisection of each proposal off the L1/LSU gather path), task rings, species table
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
+    float4 *lc = reinterpret_cast<float4 *>(smem_raw);                  // [9][SAMPLER_THREADS]
+    Task32 *ring_all = reinterpret_cast<Task32 *>(lc + CELLREC_SLOT_CHUNKS*SAMPLER_THREADS);
+    uint32_t *rslot_all = reinterpret_cast<uint32_t *>(ring_all + NWARP*RING_STAGES*RING_TASKS);
+    uint64_t *bar_all = reinterpret_cast<uint64_t *>(rslot_all + NWARP*RING_STAGES*RING_TASKS);
+    PropSpecies *sp = reinterpret_cast<PropSpecies *>(bar_all + NWARP*RING_STAGES);
     double *sm_boson = reinterpret_cast<double *>(sp + A.ns);
-    double *sm_fermion = sm_boson + 4*A.mt[0].n;
-    // per-lane copy of the cell fields every try reads (dsigma, thermodynamics, pi, q, delta-f
-    // coefficients): written once per hadron at task hand-over, so that the tries do not depend
-    // on the (small, table-squeezed) L1 keeping 768 scattered 128-byte cell records resident
-    float4 *lc_da = reinterpret_cast<float4 *>(sm_fermion + 4*A.mt[3].n);
-    float4 *lc_pa = lc_da + SAMPLER_THREADS;
-    float4 *lc_pb = lc_pa + SAMPLER_THREADS;
-    float4 *lc_u4 = lc_pb + SAMPLER_THREADS;        // ut, ux, uy, uz      (emit)
-    float4 *lc_pos = lc_u4 + SAMPLER_THREADS;       // tau, x, y, eta      (emit)
-    float2 *lc_tz = reinterpret_cast<float2 *>(lc_pos + SAMPLER_THREADS);   // t, z of the cell
-    // derived per-(cell, species) doubles, [k][lane]: every division of the accept test that does
-    // not depend on the proposed momentum is done once per hadron here
-    double *lc_d = reinterpret_cast<double *>(lc_tz + SAMPLER_THREADS);
-    enum { D_INV_T = 0, D_INV_DSIG, D_SHEAR, D_CB, D_C1, D_INV_KAPPA, D_PREFQ, D_COUNT };
+    double *sm_fermion = sm_boson + 3*A.mt[0].n;
     const int tid = threadIdx.x;
-    LaneState L;
-    L.qsign = 1;
-    auto fill_lane_cache = [&](const float4 *cr, const float4 &da, const float4 &th0, const float4 &th) {
-        const double2 *cop = reinterpret_cast<const double2 *>(
-            A.cellcoef + static_cast<int64_t>(L.cell)*COEF_STRIDE);
-        const double2 c01 = __ldg(cop);                     // c0, c1
-        const double c2 = __ldg(&cop[1].x), kappa = __ldg(&cop[3].x);
-        lc_da[tid] = da;
-        lc_pa[tid] = __ldg(cr + 5);             // pixx, pixy, pixz, piyy
-        lc_pb[tid] = __ldg(cr + 6);             // piyz, qx, qy, qz
-        lc_u4[tid] = __ldg(cr + 2);
-        lc_pos[tid] = __ldg(cr + 0);
-        {
-            const float4 tz = __ldg(cr + 7);    // t, z, spare, spare
-            lc_tz[tid] = make_float2(tz.x, tz.y);
-        }
-        const double Tdec = th0.y;
-        lc_d[D_INV_T*SAMPLER_THREADS + tid] = 1.0/L.M.T;
-        lc_d[D_INV_DSIG*SAMPLER_THREADS + tid] = 1.0/L.dsigma_fac;
-        // shear delta f prefactor (FSSW.cpp:1898-1913): CE W/(2 eta_hat p0 T), 22-moment W c0,
-        // otherwise W/(2 T^2 (e+P))
-        double sh;
-        if (mode.neos == 1) sh = 1.0/(2.*c2);
-        else if (mode.neos == 0) sh = c01.x;
-        else sh = 1.0/(2.0*Tdec*Tdec*(static_cast<double>(__fadd_rn(th0.x, th0.z))));
-        lc_d[D_SHEAR*SAMPLER_THREADS + tid] = sh;
-        // CE bulk delta f (kinds 1, 21): c0 * Pi with Pi in GeV/fm^3 (21) or fm^-4 (1)
-        const double bulkPi = (mode.kind == 21) ? static_cast<double>(th.w)
-                                                : static_cast<double>(th.w)/HBARC;
-        lc_d[D_CB*SAMPLER_THREADS + tid] = c01.x*bulkPi;
-        lc_d[D_C1*SAMPLER_THREADS + tid] = c01.y;
-        lc_d[D_INV_KAPPA*SAMPLER_THREADS + tid] = 1.0/kappa;
-        // float division as in FSSW.cpp:1866
-        lc_d[D_PREFQ*SAMPLER_THREADS + tid] = __fdiv_rn(th0.w, __fadd_rn(th0.x, th0.z));
-    };
-    for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
-    for (int i = threadIdx.x; i < 2*A.mt[0].n; i += blockDim.x)
-        reinterpret_cast<double2 *>(sm_boson)[i] = __ldg(reinterpret_cast<const double2 *>(A.mt[0].data) + i);
-    for (int i = threadIdx.x; i < 2*A.mt[3].n; i += blockDim.x)
-        reinterpret_cast<double2 *>(sm_fermion)[i] = __ldg(reinterpret_cast<const double2 *>(A.mt[3].data) + i);
+    const int lane = tid & 31, warp = tid >> 5;
+    Task32 *ring = ring_all + warp*RING_STAGES*RING_TASKS;
+    uint32_t *rslot = rslot_all + warp*RING_STAGES*RING_TASKS;
+    uint64_t *bar = bar_all + warp*RING_STAGES;
+    // slot chunks: 0 da | 1 pa | 2 pb | 3 u4 | 4 pos | 5 tz, inv_T | 6 inv_dsig, shear | 7 cb, c1 |
+    // 8 inv_kappa, prefq
+#define LC4(c) lc[(c)*SAMPLER_THREADS + tid]
+#define LCD(c, k) (reinterpret_cast<const double *>(&lc[(c)*SAMPLER_THREADS + tid])[k])
+
+    for (int i = tid; i < A.ns; i += SAMPLER_THREADS) {
+        const DeviceSpecies d = A.species[i];
+        PropSpecies q;
+        q.mass = d.mass;
+        q.mass2 = d.mass2;
+        q.pid = d.pid;
+        q.baryon = d.baryon;
+        q.strange = d.strange;
+        q.charge = d.charge;
+        q.sign = d.sign;
+        q.pad = 0;
+        sp[i] = q;
+    }
+    for (int i = tid; i < 3*A.mt[0].n; i += SAMPLER_THREADS)
+        sm_boson[i] = __ldg(A.mt[0].data + 4*(i/3) + 1 + i%3);
+    for (int i = tid; i < 3*A.mt[3].n; i += SAMPLER_THREADS)
+        sm_fermion[i] = __ldg(A.mt[3].data + 4*(i/3) + 1 + i%3);
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < RING_STAGES; b++) mbar_init(&bar[b], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
+    // stages of this warp: g = gw + k W, k = 0, 1, ...; stage k lives in ring buffer k & 1
+    const int64_t W = static_cast<int64_t>(gridDim.x)*NWARP;
+    const int64_t gw = static_cast<int64_t>(blockIdx.x)*NWARP + warp;
+    const int64_t nstage = (A.nwork + RING_TASKS - 1)/RING_TASKS;
+    auto issue_stage = [&](int buf, int64_t g) {
+        // (lane 0) the ring buffer was last read through the generic proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive_expect_tx(&bar[buf], RING_STAGE_BYTES);
+        bulk_g2s(ring + buf*RING_TASKS, A.tasks + g*RING_TASKS, RING_TASKS*sizeof(Task32), &bar[buf]);
+        bulk_g2s(rslot + buf*RING_TASKS, A.task_slot + g*RING_TASKS, RING_TASKS*sizeof(uint32_t), &bar[buf]);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int b = 0; b < RING_STAGES; b++)
+            if (gw + b*W < nstage) issue_stage(b, gw + b*W);
+    }
+    int k_stage = 0;            // stages this warp has used up
+    int cursor = 0;             // tasks of the current stage handed out
+    bool stage_ready = false;   // the current stage's bytes have landed
     bool busy = false;
-    int64_t chunk_next = 0, chunk_end = 0;      // tasks reserved by this warp
-    bool more_work = true;
+    LaneState L;
+    L.qsign = 1;
     unsigned long long my_tries = 0, my_redraws = 0, my_range = 0, my_giveup = 0;
 
     for (;;) {
         // ------------------------------------------------------------ hand tasks to idle lanes
         unsigned need_mask = __ballot_sync(full, !busy);
-        while (need_mask != 0u && more_work) {
-            if (chunk_next >= chunk_end) {
-                unsigned long long c = 0;
-                if (lane == 0) c = atomicAdd(&A.counters[0], (unsigned long long)TASK_CHUNK);
-                c = __shfl_sync(full, c, 0);
-                chunk_next = static_cast<int64_t>(c);
-                chunk_end = min(chunk_next + TASK_CHUNK, A.nwork);
-                if (chunk_next >= A.nwork) {
-                    more_work = false;
-                    break;
-                }
+        while (need_mask != 0u) {
+            const int64_t g = gw + static_cast<int64_t>(k_stage)*W;
+            if (g >= nstage) break;
+            const int buf = k_stage & (RING_STAGES - 1);
+            if (!stage_ready) {
+                const uint32_t parity = static_cast<uint32_t>(k_stage/RING_STAGES) & 1u;
+                while (!mbar_try_wait(&bar[buf], parity)) { }
+                stage_ready = true;
             }
+            const int64_t left = A.nwork - g*RING_TASKS;
+            const int n_cur = left < RING_TASKS ? static_cast<int>(left) : RING_TASKS;
             const int nneed = __popc(need_mask);
-            const int64_t avail = chunk_end - chunk_next;
-            const int take = static_cast<int>(avail < (int64_t)nneed ? avail : (int64_t)nneed);
+            const int take = min(nneed, n_cur - cursor);
             const int rank = __popc(need_mask & lt_mask);
             if (!busy && rank < take) {
-                const float4 *tp = reinterpret_cast<const float4 *>(A.tasks + chunk_next + rank);
-                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                L.out_slot = (static_cast<int64_t>(__float_as_uint(t0.y)) << 32)
-                             | static_cast<int64_t>(__float_as_uint(t0.x));
-                const double m_term = __hiloint2double(__float_as_int(t0.w), __float_as_int(t0.z));
-                const double cdf_max = __hiloint2double(__float_as_int(t1.y), __float_as_int(t1.x));
-                L.cell = __float_as_int(t1.z);
-                L.s = __float_as_int(t1.w);
-                L.rng.event = __float_as_uint(t2.x);
-                L.rng.draw = __float_as_uint(t2.y);
-                L.rng.block = 1u;               // block 0 chose the cell (setup_kernel)
-                const int tab_idx = __float_as_int(t2.z);
+                const int i = buf*RING_TASKS + cursor + rank;
+                const double2 t0 = *reinterpret_cast<const double2 *>(&ring[i]);       // m_term, cdf_max
+                const uint4 t1 = *(reinterpret_cast<const uint4 *>(&ring[i]) + 1);     // cell, event, draw, s | tab
+                L.slot = rslot[i];
+                L.cell = static_cast<int>(t1.x);
+                L.rng.event = t1.y;
+                L.rng.draw = t1.z;
+                L.rng.block = 1u;               // block 0 chose the cell (pick_kernel)
+                L.s = static_cast<int>(t1.w & 0xFFFFu);
+                const uint32_t tab_idx = t1.w >> 16;
                 L.qsign = 1;
                 L.tries = 1;
                 L.total_tries = 0;
-                if (tab_idx >= 0) {
-                    const DeviceSpecies p = sp[L.s];
-                    const float4 *cr = reinterpret_cast<const float4 *>(
-                        A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
-                    const float4 da = __ldg(cr + 1);
-                    const float4 th0 = __ldg(cr + 3);       // E, T, P, nB
-                    const float4 th = __ldg(cr + 4);        // muB, muS, muQ, bulkPi
-                    // float arithmetic inside the sqrt as in FSSW.cpp:1867-1870
-                    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(da.y, da.y), __fmul_rn(da.z, da.z)),
-                                               __fmul_rn(da.w, da.w));
-                    L.dsigma_fac = fabs(static_cast<double>(da.x)) + sqrt(static_cast<double>(d2));
-                    momentum_restore(p.mass, th0.y, species_mu(p, 1, th, p.mass), m_term, cdf_max,
-                                     tab_idx & 7, tab_idx >> 3, L.M);
-                    fill_lane_cache(cr, da, th0, th);
+                if (tab_idx != TASK_RANGE_ERROR) {
+                    const float4 *src = reinterpret_cast<const float4 *>(A.cellrec + L.cell);
+#pragma unroll
+                    for (int c = 0; c < CELLREC_SLOT_CHUNKS; c++) cp_async16(&LC4(c), src + c);
+                    cp_async_commit();
+                    const float4 th = __ldg(src + CELLREC_SLOT_CHUNKS);     // T, muB, muS, muQ
+                    const PropSpecies p = sp[L.s];
+                    momentum_restore(p.mass, th.x,
+                                     species_mu_bsq(p.baryon, p.strange, p.charge, th.y, th.z, th.w, p.mass),
+                                     t0.x, t0.y, static_cast<int>(tab_idx & 7u),
+                                     static_cast<int>(tab_idx >> 3), L.M);
                     busy = true;
                 }
-                // tab_idx < 0: momentum table range error, counted by setup_kernel; no record
+                // TASK_RANGE_ERROR: momentum table range error, counted by setup_kernel; no record
             }
-            chunk_next += take;
+            cursor += take;
+            if (cursor == n_cur) {
+                // every lane's reads of this ring buffer are done: refill it two stages ahead
+                __syncwarp();
+                if (lane == 0 && g + RING_STAGES*W < nstage) issue_stage(buf, g + RING_STAGES*W);
+                k_stage++;
+                cursor = 0;
+                stage_ready = false;
+            }
             need_mask = __ballot_sync(full, !busy);
-            if (take == 0) break;
         }
-        if (!__any_sync(full, busy)) {
-            if (!more_work) break;
-            continue;
-        }
+        if (!__any_sync(full, busy)) break;     // idle lanes are left only when the stages ran out
 
         // ------------------------------------------------------------ one try per busy lane
         if (busy) {
-            const DeviceSpecies p = sp[L.s];
+            cp_async_wait_all();                // the lane's slot (no-op after the first try)
+            const PropSpecies p = sp[L.s];
             const double mass = p.mass;
             const int sign = p.sign;
             const MomentumTable &mt = A.mt[L.M.tab];
@@ -824,8 +1056,8 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                          pw0, pw1, pw2, pw3);
             const double r = u53(pw0, pw1)*L.M.cdf_max;
             double Et;
-            if (L.M.tab == 0) Et = inverse_cdf<true>(sm_boson, mt.n, L.M, r);
-            else if (L.M.tab == 3) Et = inverse_cdf<true>(sm_fermion, mt.n, L.M, r);
+            if (L.M.tab == 0 && A.mt_smem) Et = inverse_cdf_smem(sm_boson, mt.n, mt.e0, mt.de_build, L.M, r);
+            else if (L.M.tab == 3 && A.mt_smem) Et = inverse_cdf_smem(sm_fermion, mt.n, mt.e0, mt.de_build, L.M, r);
             else Et = inverse_cdf<false>(mt.data, mt.n, L.M, r);
             const double E_sample = L.M.T*Et + L.M.mu;
             const double p_mag = sqrt(E_sample*E_sample - p.mass2);
@@ -850,32 +1082,30 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 const double py = pT*sphi;
                 const double p0 = sqrt(p.mass2 + p_mag*p_mag);
                 const double pz = p_mag*cos_theta;
-                const float4 *cr = reinterpret_cast<const float4 *>(
-                    A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
-                const float4 da = lc_da[tid];
+                const float4 da = LC4(0);
                 const double pdsigma = p0*da.x + px*da.y + py*da.z + pz*da.w;
                 const double inv_p0 = 1.0/p0;
                 // p.dsigma/(p0 (|dsigma0| + |dsigma_vec|)), FSSW.cpp:1939
-                double fact1 = pdsigma*inv_p0*lc_d[D_INV_DSIG*SAMPLER_THREADS + tid];
+                double fact1 = pdsigma*inv_p0*LCD(6, 0);
                 fact1 = fmax(0., fmin(1., fact1));
                 // the accept uniform is drawn whatever delta f is; since fact2 <= 1, u >= fact1
                 // already decides "reject" and the delta-f evaluation is skipped
                 const double u_acc = u32(qw1);
                 double accept_prob = 0.;
                 if (u_acc < fact1) {
-                    const double inv_T = lc_d[D_INV_T*SAMPLER_THREADS + tid];
+                    const double inv_T = LCD(5, 1);
                     const double f0 = 1./(exp((p0 - L.M.mu)*inv_T) + sign);
                     const double stat = 1. - sign*f0;
                     double delta_f = 0.;
                     if (mode.include_shear | mode.include_bulk | mode.include_diff) {
                         const int B = L.qsign*p.baryon, S = L.qsign*p.strange, Q = L.qsign*p.charge;
                         if (mode.include_shear == 1) {
-                            const float4 pa = lc_pa[tid];       // pixx, pixy, pixz, piyy
-                            const float4 pb = lc_pb[tid];       // piyz, qx, qy, qz
+                            const float4 pa = LC4(1);           // pixx, pixy, pixz, piyy
+                            const float4 pb = LC4(2);           // piyz, qx, qy, qz
                             const double Wfactor = (px*px*pa.x + 2.*px*py*pa.y + 2.*px*pz*pa.z
                                                     + py*py*pa.w + 2.*py*pz*pb.x
                                                     + pz*pz*(-pa.x - pa.w));
-                            const double sh = lc_d[D_SHEAR*SAMPLER_THREADS + tid];
+                            const double sh = LCD(6, 1);
                             if (mode.neos == 1) delta_f += stat*Wfactor*sh*inv_p0*inv_T;
                             else delta_f += stat*Wfactor*sh;
                         }
@@ -883,13 +1113,13 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                             // FSSW::get_deltaf_bulk (FSSW.cpp:1795-1849); kinds 0,2,3,4: bulkPi = 0
                             if (mode.kind == 21 || mode.kind == 1) {
                                 // -(1 -/+ f0) c0 (m^2/(3 T p0) - c1 p0/T) Pi
-                                delta_f += (-stat*lc_d[D_CB*SAMPLER_THREADS + tid]*inv_T
-                                            *(p.mass2*(1./3.)*inv_p0
-                                              - lc_d[D_C1*SAMPLER_THREADS + tid]*p0));
+                                delta_f += (-stat*LCD(7, 0)*inv_T
+                                            *(p.mass2*(1./3.)*inv_p0 - LCD(7, 1)*p0));
                             } else if (mode.kind == 11 || mode.kind == 20) {
                                 const double *__restrict__ co =
                                     A.cellcoef + static_cast<int64_t>(L.cell)*COEF_STRIDE;
-                                const double bulkPi = __ldg(cr + 4).w;
+                                const double bulkPi = __ldg(reinterpret_cast<const float4 *>(
+                                    A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE) + 4).w;
                                 if (mode.kind == 11) {
                                     delta_f += stat*bulkPi*(__ldg(&co[0])*p.mass2 + __ldg(&co[1])*B*p0
                                                             + __ldg(&co[2])*p0*p0);
@@ -902,10 +1132,9 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                             }
                         }
                         if (mode.include_diff == 1) {
-                            const float4 pb = lc_pb[tid];       // piyz, qx, qy, qz
+                            const float4 pb = LC4(2);           // piyz, qx, qy, qz
                             const double qmufactor = -px*pb.y - py*pb.z - pz*pb.w;
-                            delta_f += stat*(lc_d[D_PREFQ*SAMPLER_THREADS + tid] - B*inv_p0)*qmufactor
-                                       *lc_d[D_INV_KAPPA*SAMPLER_THREADS + tid];
+                            delta_f += stat*(LCD(8, 1) - B*inv_p0)*qmufactor*LCD(8, 0);
                         }
                     }
                     double fact2 = (1. + delta_f)/2.;
@@ -914,8 +1143,8 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 }
                 if (u_acc < accept_prob) {
                     // ---- accepted: boost to the lab frame and emit (FSSW.cpp:1946-1960, 1969-1996)
-                    const float4 pos = lc_pos[tid];         // tau, x, y, eta
-                    const float4 u4 = lc_u4[tid];           // ut, ux, uy, uz
+                    const float4 pos = LC4(4);          // tau, x, y, eta
+                    const float4 u4 = LC4(3);           // ut, ux, uy, uz
                     const float pl0 = static_cast<float>(p0), pl1 = static_cast<float>(px),
                                 pl2 = static_cast<float>(py), pl3 = static_cast<float>(pz);
                     double p_dot_u = 0.;
@@ -940,12 +1169,12 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                     if (hydro_mode == 2) {
                         // eta_s = cell eta: y = asinh(pz/mT) - eta + eta, p_z = mT sinh(y) = pLab[3],
                         // px = pT cos(atan2(py,px)) = pLab[1] up to FP64 rounding; t,z precomputed.
-                        const float2 tz = lc_tz[tid];       // t, z of the cell
+                        const float4 tzi = LC4(5);          // t, z of the cell (| inv_T)
                         const double pzl = lab3;
                         hd.pz = lab3;
                         hd.E = static_cast<float>(sqrt(mT*mT + pzl*pzl));
-                        hd.t = tz.x;
-                        hd.z = tz.y;
+                        hd.t = tzi.x;
+                        hd.z = tzi.y;
                     } else {
                         // boost-invariant: y ~ U(y_LB, y_RB), eta_s = y - (y - eta_s) (FSSW.cpp:1024-1029);
                         // the charge-conservation partner keeps the primary's eta_s (FSSW.cpp:1045-1047)
@@ -965,23 +1194,34 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                         hd.t = static_cast<float>(pos.x*cosh(eta_s));
                     }
                     // 40-byte record as five 8-byte stores (slots are 8-byte aligned)
-                    float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
+                    float2 *dst = reinterpret_cast<float2 *>(A.out + L.slot);
                     dst[0] = make_float2(__int_as_float(hd.pid), hd.mass);
                     dst[1] = make_float2(hd.E, hd.px);
                     dst[2] = make_float2(hd.py, hd.pz);
                     dst[3] = make_float2(hd.t, hd.x);
                     dst[4] = make_float2(hd.y, hd.z);
+                    if (A.wire) {
+                        // 20-byte wire record (include/iss_cuda.h, iss_wire_hadron): species and
+                        // position follow from the slot and the cell
+                        uint32_t *wr = A.wire + 5ull*L.slot;
+                        wr[0] = static_cast<uint32_t>(L.cell + A.cell_begin);
+                        wr[1] = __float_as_uint(hd.px);
+                        wr[2] = __float_as_uint(hd.py);
+                        wr[3] = __float_as_uint(hd.pz);
+                        wr[4] = __float_as_uint(hd.E);
+                    }
                     if (A.trace_cell) {
-                        A.trace_cell[L.out_slot] = L.cell;
-                        A.trace_tries[L.out_slot] = L.total_tries;
+                        A.trace_cell[L.slot] = L.cell;
+                        A.trace_tries[L.slot] = L.total_tries;
                     }
                     busy = false;
                     if (lcc == 1 && L.qsign > 0 && p.charge > 0) {
                         // partner with conjugate quantum numbers from the SAME cell
                         L.qsign = -1;
-                        L.out_slot += 1;
+                        L.slot += 1;
                         L.total_tries = 0;
-                        if (lane_new_setup(Ag, L, p, false, key0, key1)) busy = true;
+                        if (lane_new_setup(Ag, L, mass, sign, p.baryon, p.strange, p.charge, false,
+                                           key0, key1, lc, tid)) busy = true;
                         else my_range++;
                     }
                 } else {
@@ -990,22 +1230,24 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                         if (L.total_tries > MAX_TRIES_PER_HADRON) {
                             // The reference would loop forever on a (cell, species) pair that can
                             // never be accepted (FSSW.cpp:977-1018); a kernel must not.  The slot
-                            // gets a null record (pid 0) and the call reports ISS_ERR_RANGE.
-                            float2 *dst = reinterpret_cast<float2 *>(A.out + L.out_slot);
+                            // gets a null record (pid 0), the offender is recorded for the error
+                            // message and the call reports ISS_ERR_RANGE.
+                            float2 *dst = reinterpret_cast<float2 *>(A.out + L.slot);
 #pragma unroll
                             for (int q = 0; q < 5; q++) dst[q] = make_float2(0.f, 0.f);
+                            if (my_giveup == 0) {
+                                A.giveup_info[0] = static_cast<unsigned long long>(L.cell + A.cell_begin);
+                                A.giveup_info[1] = static_cast<unsigned long long>(L.s);
+                            }
                             my_giveup++;
                             busy = false;
                         } else if (L.qsign > 0) {
                             // the reference's "impatience" (FSSW.cpp:1017-1018 with status == 0)
                             my_redraws++;
-                            if (!lane_new_setup(Ag, L, p, true, key0, key1)) {
+                            if (!lane_new_setup(Ag, L, mass, sign, p.baryon, p.strange, p.charge, true,
+                                                key0, key1, lc, tid)) {
                                 my_range++;
                                 busy = false;
-                            } else {
-                                const float4 *cr2 = reinterpret_cast<const float4 *>(
-                                    A.cells + static_cast<int64_t>(L.cell)*CELL_STRIDE);
-                                fill_lane_cache(cr2, __ldg(cr2 + 1), __ldg(cr2 + 3), __ldg(cr2 + 4));
                             }
                         } else {
                             // partner sampling never re-picks the cell (do-while at FSSW.cpp:1039-1044)
@@ -1016,6 +1258,8 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
             }
         }
     }
+#undef LC4
+#undef LCD
     // warp-aggregated counters
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -1185,6 +1429,23 @@ static int chunk_select_work(iss_handle *h, const SamplerArgs &A, int64_t nev, i
 #include "legacy.cuh"
 namespace iss {
 
+// per-cell records of the proposal kernel (after the yield kernel has left the delta-f coefficients)
+int build_cellrec(iss_handle *h) {
+    ISS_ENSURE(h, h->d_cellrec, h->cellrec_bytes, sizeof(CellRec)*h->ncell);
+    const iss_options &o = h->opt;
+    ModeFlags mode;
+    mode.include_shear = o.include_deltaf_shear;
+    mode.include_bulk = o.include_deltaf_bulk;
+    mode.include_diff = o.include_deltaf_diffusion;
+    mode.kind = o.bulk_deltaf_kind;
+    mode.neos = (o.bulk_deltaf_kind == 21) ? 1 : (o.bulk_deltaf_kind == 20 ? 0 : -1);
+    build_cellrec_kernel<<<static_cast<unsigned>((h->ncell + 127)/128), 128, 0, h->stream>>>(
+        h->d_cells, h->d_cellcoef, h->ncell, mode, static_cast<CellRec *>(h->d_cellrec)); ISS_LAUNCHED(h);
+    ISS_CUDA_TRY(h, cudaGetLastError());
+    h->cellrec_valid = true;
+    return ISS_OK;
+}
+
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     const int ns = h->nspecies;
     const int64_t n = nev*ns;
@@ -1241,6 +1502,13 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.wlist = nullptr;
     A.hints = nullptr;
     A.tasks = nullptr;
+    A.task_slot = nullptr;
+    A.cellid = nullptr;
+    A.cell_cnt = nullptr;
+    A.cellrec = nullptr;
+    A.wire = nullptr;
+    A.giveup_info = nullptr;
+    A.mt_smem = 0;
     A.out = nullptr;
     A.counters = nullptr;
     A.nwork = 0;
@@ -1292,8 +1560,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         h->d_hadrons = h->d_hadbuf[b];
         h->hadron_cap = h->hadbuf_cap[b];
     }
-    if (!h->d_counters) ISS_CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned long long)*8));
-    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long)*8, h->stream));
+    if (!h->d_counters) ISS_CUDA_TRY(h, cudaMalloc(&h->d_counters, sizeof(unsigned long long)*N_COUNTERS));
+    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_counters, 0, sizeof(unsigned long long)*N_COUNTERS, h->stream));
     h->n_hadrons = total_out;
     h->n_primaries = total_out;
     if (A.nwork == 0) return ISS_OK;
@@ -1339,29 +1607,65 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         return ISS_OK;
     }
 
-    // task list of the batch
+    // cell-sorted task list of the batch (padded to whole ring stages: the proposal kernel copies
+    // whole stages) and the scratch of the counting sort
+    if (total_out >= (int64_t(1) << 32) || A.nwork >= (int64_t(1) << 32))
+        ISS_FAIL(h, ISS_ERR_ARG, "a batch must hold fewer than 2^32 hadrons (sample fewer events per call)");
+    const int64_t nstage = (A.nwork + RING_TASKS - 1)/RING_TASKS;
     {
-        const size_t need = sizeof(Task)*static_cast<size_t>(A.nwork);
+        const size_t need = sizeof(Task32)*static_cast<size_t>(nstage*RING_TASKS);
         if (need > h->tasks_bytes || !h->d_tasks) {
             if (h->d_tasks) cudaFree(h->d_tasks);
+            if (h->d_task_slot) cudaFree(h->d_task_slot);
+            if (h->d_cellid) cudaFree(h->d_cellid);
             h->d_tasks = nullptr;
+            h->d_task_slot = nullptr;
+            h->d_cellid = nullptr;
             h->tasks_bytes = need + need/8 + 4096;
+            const size_t cap = h->tasks_bytes/sizeof(Task32);
             ISS_CUDA_TRY(h, cudaMalloc(&h->d_tasks, h->tasks_bytes));
+            ISS_CUDA_TRY(h, cudaMalloc(&h->d_task_slot, sizeof(uint32_t)*cap));
+            ISS_CUDA_TRY(h, cudaMalloc(&h->d_cellid, sizeof(int32_t)*cap));
         }
-        A.tasks = static_cast<Task *>(h->d_tasks);
+        ISS_ENSURE(h, h->d_cellcnt, h->cellcnt_bytes, sizeof(unsigned long long)*(h->ncell + 2));
+        A.tasks = static_cast<Task32 *>(h->d_tasks);
+        A.task_slot = h->d_task_slot;
+        A.cellid = h->d_cellid;
+        A.cell_cnt = h->d_cellcnt;
+    }
+    if (!h->cellrec_valid) {
+        rc = build_cellrec(h);
+        if (rc) return rc;
+    }
+    A.cellrec = static_cast<const CellRec *>(h->d_cellrec);
+    A.giveup_info = h->d_counters + 8;
+    A.mt_smem = (h->momtab[0].generated && h->momtab[3].generated) ? 1 : 0;
+    A.wire = nullptr;
+    if (h->wire_on) {
+        const int b = h->cur_buf;
+        rc = ensure_capacity(h, &h->d_wire[b], &h->wire_cap[b], 5*total_out);
+        if (rc) return rc;
+        A.wire = h->d_wire[b];
     }
     if (!h->d_sampler_args) ISS_CUDA_TRY(h, cudaMalloc(&h->d_sampler_args, sizeof(SamplerArgs)));
     ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_sampler_args, &A, sizeof(SamplerArgs), cudaMemcpyHostToDevice,
                                     h->stream));
     {
         ScopedTimer t(h, ISS_T_SETUP);
-        const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
         int64_t grid = (A.nwork + SETUP_THREADS - 1)/SETUP_THREADS;
         if (grid > static_cast<int64_t>(nsm)*32) grid = static_cast<int64_t>(nsm)*32;
         if (!h->chunk) {    // (chunk mode: the hints exist already, chunk_select_work)
             work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
                 h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
         }
+        // counting sort of the batch's hadrons by cell: histogram, exclusive scan, scatter
+        ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_cellcnt, 0, sizeof(unsigned long long)*(h->ncell + 1), h->stream));
+        pick_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, sizeof(int64_t)*(ns + 1), h->stream>>>(A);
+        ISS_LAUNCHED(h);
+        rc = device_exclusive_scan_i64(h, reinterpret_cast<const int64_t *>(h->d_cellcnt),
+                                       reinterpret_cast<int64_t *>(h->d_cellcnt), h->ncell, nullptr);
+        if (rc) return rc;
+        const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
         setup_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
@@ -1383,8 +1687,11 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     void (*kern)(const SamplerArgs, const SamplerArgs *) =
         spec == 1 ? propose_kernel<1, 1> : spec == 2 ? propose_kernel<1, 2>
         : spec == 3 ? propose_kernel<1, 3> : propose_kernel<1, 0>;
-    const size_t smem = sizeof(DeviceSpecies)*ns + sizeof(double)*4*(A.mt[0].n + A.mt[3].n)
-                        + (5*sizeof(float4) + sizeof(float2) + 7*sizeof(double))*SAMPLER_THREADS;
+    constexpr int NWARP = SAMPLER_THREADS/32;
+    const size_t smem = sizeof(float4)*CELLREC_SLOT_CHUNKS*SAMPLER_THREADS
+                        + (sizeof(Task32) + sizeof(uint32_t))*NWARP*RING_STAGES*RING_TASKS
+                        + sizeof(uint64_t)*NWARP*RING_STAGES + sizeof(PropSpecies)*ns
+                        + sizeof(double)*3*(A.mt[0].n + A.mt[3].n);
     {
         int smem_max = 0;
         cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);

@@ -451,6 +451,7 @@ int run_yields_local(iss_handle *h) {
 
     h->have_yields = false;
     h->have_local_yields = false;
+    h->cellrec_valid = false;
     const int64_t ns = h->nspecies;
     const size_t nval = static_cast<size_t>(ns)*h->ncell_pad;
     ISS_ENSURE(h, h->d_yields, h->yields_bytes, sizeof(double)*nval);
@@ -666,6 +667,7 @@ int run_legacy_yields(iss_handle *h, double *yields_host, double *maximum_host) 
     h->chunk = false;
     h->have_yields = false;
     h->have_local_yields = false;
+    h->cellrec_valid = false;
     h->have_batch = false;
     h->legacy = false;
     const int64_t ns = h->nspecies;
