@@ -279,6 +279,21 @@ ISS_API int iss_cuda_histograms(iss_handle *h, const int32_t *pids, int32_t npid
 ISS_API int iss_cuda_qa_device_ptr(iss_handle *h, void **dptr);
 ISS_API int iss_cuda_qa_fetch(iss_handle *h, double *dst_host);
 
+/* ---- the one collective of the path: with one process per GPU and the
+ *      events (or surface chunks) sharded over the ranks, iSS::perform_checks (iSS.cpp:59-83)
+ *      needs the QA block summed over the ranks; everything else is rank-local.
+ *      iss_cuda_histograms_allreduce sums the device block in place over `nccl_comm` (an
+ *      ncclComm_t passed as void*) on the handle's stream; a NULL communicator selects the one
+ *      made by iss_cuda_nccl_init, and with neither the call is a no-op (single rank).  NCCL is
+ *      bound at run time (libnccl.so.2): hosts that never pass more than one rank need none.
+ *      iss_cuda_nccl_unique_id / iss_cuda_nccl_init wrap ncclGetUniqueId / ncclCommInitRank for
+ *      hosts without NCCL code of their own: rank 0 makes the 128-byte id, the host distributes
+ *      it (MPI_Bcast, a file, ...), every rank calls init with it.                           */
+ISS_API int iss_cuda_nccl_unique_id(void *id128 /* 128 bytes out */);
+ISS_API int iss_cuda_nccl_init(iss_handle *h, const void *id128, int32_t rank, int32_t nranks);
+ISS_API int iss_cuda_nccl_finalize(iss_handle *h);
+ISS_API int iss_cuda_histograms_allreduce(iss_handle *h, void *nccl_comm);
+
 /* ---- timing: accumulated device time per kernel family.  While enabled, every family span is
  *      bracketed by a pair of CUDA events recorded on the handle's stream WITHOUT synchronising;
  *      the pairs are resolved (one stream synchronisation) by the next call of this function.

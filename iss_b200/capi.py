@@ -110,6 +110,8 @@ CUDA_SYMBOLS = [
     "iss_cuda_chunk_yields_finish", "iss_cuda_upload_surface_aos_part",
     "iss_cuda_legacy_upload_positions", "iss_cuda_legacy_upload_z_table",
     "iss_cuda_legacy_set_options", "iss_cuda_legacy_compute_yields",
+    "iss_cuda_nccl_unique_id", "iss_cuda_nccl_init", "iss_cuda_nccl_finalize",
+    "iss_cuda_histograms_allreduce",
 ]
 HOST_SYMBOLS = [
     "iss_host_create", "iss_host_destroy", "iss_host_set_param", "iss_host_get_param",
@@ -190,6 +192,10 @@ def cuda_lib():
         "iss_cuda_legacy_compute_yields": (C.c_int, [vp, vp, vp, vp]),
         "iss_cuda_ingest_music_binary": (C.c_int, [vp, vp, i64, C.POINTER(IngestOptions), vp, vp, vp, vp,
                                                    C.POINTER(IngestResult)]),
+        "iss_cuda_nccl_unique_id": (C.c_int, [vp]),
+        "iss_cuda_nccl_init": (C.c_int, [vp, vp, i32, i32]),
+        "iss_cuda_nccl_finalize": (C.c_int, [vp]),
+        "iss_cuda_histograms_allreduce": (C.c_int, [vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

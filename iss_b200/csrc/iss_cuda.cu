@@ -179,7 +179,8 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_mult); cudaFree(h->d_off_out); cudaFree(h->d_off_work);
     cudaFree(h->d_hadbuf[0]); cudaFree(h->d_hadbuf[1]); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
     cudaFree(h->d_tasks); cudaFree(h->d_sampler_args); cudaFree(h->d_hints);
-    cudaFree(h->d_task_slot); cudaFree(h->d_cellid); cudaFree(h->d_cellcnt); cudaFree(h->d_cellrec);
+    cudaFree(h->d_task_slot); cudaFree(h->d_slot_unsorted); cudaFree(h->d_tasks_unsorted);
+    cudaFree(h->d_cellcnt); cudaFree(h->d_cellrec);
     cudaFree(h->d_wire[0]); cudaFree(h->d_wire[1]);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
     cudaFree(h->d_qa); cudaFree(h->d_trace);

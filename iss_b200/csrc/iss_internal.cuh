@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <cstring>
 #include <vector>
 #include <cstdio>
 
@@ -186,8 +187,9 @@ struct iss_handle {
     void *d_sampler_args = nullptr;
     void *d_hints = nullptr; size_t hints_bytes = 0;
     void *d_tasks = nullptr; size_t tasks_bytes = 0;     // cell-sorted task list of the batch (Task32)
-    uint32_t *d_task_slot = nullptr;                     // output slot of every task (same capacity)
-    int32_t *d_cellid = nullptr;                         // cell of every work item (same capacity)
+    void *d_tasks_unsorted = nullptr;                    // the same tasks in work order (same capacity)
+    uint32_t *d_task_slot = nullptr; size_t task_slot_bytes = 0;        // surface-chunk mode: output
+    uint32_t *d_slot_unsorted = nullptr; size_t slot_unsorted_bytes = 0;    // slots, sorted / work order
     unsigned long long *d_cellcnt = nullptr; size_t cellcnt_bytes = 0;  // [ncell + 2] histogram / offsets
     void *d_cellrec = nullptr; size_t cellrec_bytes = 0; // [ncell] CellRec (sampler.cu)
     bool cellrec_valid = false;                          // reset with the yields
@@ -218,6 +220,9 @@ struct iss_handle {
 
     // QA
     double *d_qa = nullptr;
+    // communicator made by iss_cuda_nccl_init (collective.cu); null: single rank
+    void *nccl_comm = nullptr;
+    int nccl_rank = 0, nccl_nranks = 0;
 
     // timing: event pairs are recorded on the stream without synchronising and resolved in
     // iss_cuda_timing(); t_launch counts every kernel launch of the library

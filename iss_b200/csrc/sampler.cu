@@ -223,7 +223,7 @@ __global__ void event_offset_kernel(const int64_t *__restrict__ off_out, int ns,
 // ---------------------------------------------------------------------------------
 // One hadron to sample: 32 bytes (one DRAM sector), written by setup_kernel at its position in
 // the CELL-SORTED task list and streamed into shared memory by propose_kernel (cp.async.bulk).
-// The output slot travels beside it in task_slot[], so results do not depend on the order.
+// The output slot follows from (event, species, draw), so results do not depend on the order.
 struct __align__(16) Task32 {
     double m_term;          // CDF(a) term of MomentumSamplerBase::Sample_a_momentum
     double cdf_max;
@@ -291,10 +291,11 @@ struct SamplerArgs {
     double y_LB, y_RB;
     uint64_t seed;
     const CellRec *cellrec;         // [ncell] per-cell record of the proposal kernel
-    int32_t *cellid;                // [nwork] cell of every work item (pick_kernel -> setup_kernel)
+    Task32 *tasks_unsorted;         // [nwork] tasks in work order (setup_kernel -> bucket_kernel)
+    uint32_t *slot_unsorted;        // [nwork] surface-chunk mode only: output slots in work order
     unsigned long long *cell_cnt;   // [ncell + 1] cell histogram -> exclusive offsets -> bucket cursors
     Task32 *tasks;                  // [nstage*RING_TASKS] cell-sorted task list
-    uint32_t *task_slot;            // [nstage*RING_TASKS] output slot of every task
+    uint32_t *task_slot;            // surface-chunk mode only: output slot of every sorted task
     uint32_t *wire;                 // optional [n_out][5]: 20-byte wire records (iss_wire_hadron)
     unsigned long long *giveup_info;    // [2] (cell, species) of a hadron the sampler gave up on
     int mt_smem;                    // regime-0 tables were generated on the device (uniform abscissa)
@@ -348,7 +349,8 @@ __device__ __forceinline__ void momentum_restore(double mass, double T_in, doubl
                                                  double cdf_max, int tab, int idx_min, MomSetup &M) {
     const double T = fmax(1e-16, T_in);
     const double m_tilde = mass/T;
-    const double mu_tilde = mu/T;
+    // (0/T = 0 exactly; a zero numerator sends the FP64 division down its slow path)
+    const double mu_tilde = (mu == 0.) ? mu : mu/T;
     M.T = T;
     M.mu = mu;
     M.mu_tilde = mu_tilde;
@@ -366,9 +368,9 @@ __device__ __forceinline__ bool momentum_setup(const MomentumTable *__restrict__
                                                int sign, double T_in, double mu, MomSetup &M) {
     const double T = fmax(1e-16, T_in);
     const double m_tilde = mass/T;
-    const double mu_tilde = mu/T;
+    const double mu_tilde = (mu == 0.) ? mu : mu/T;     // see momentum_restore
     const double a = m_tilde - mu_tilde;
-    const double m0tilde = mass/T - mu/T;
+    const double m0tilde = m_tilde - mu_tilde;
     const int regime = (m0tilde < 30.) ? 0 : (m0tilde < 50. ? 1 : 2);
     const bool fermion = (sign != -1);          // sign 0 -> fermion tables
     const int tab = (fermion ? 3 : 0) + regime;
@@ -640,23 +642,29 @@ __global__ void build_cellrec_kernel(const float *__restrict__ cells, const doub
 // ---- cell-sorted task list -----------------------------------------------------------------------
 // The hadron list is a pure function of (seed, event, species, draw), so the ORDER in which the
 // hadrons of a batch are sampled is free.  The tasks are bucketed by cell (counting sort on the
-// cell id: histogram in pick_kernel, exclusive scan, scatter in setup_kernel): consecutive tasks
+// cell id: histogram in setup_kernel, exclusive scan, scatter in bucket_kernel): consecutive tasks
 // then share their cell record, which the proposal kernel finds in L1/L2 instead of gathering
 // 160 random bytes per hadron from DRAM.  The order inside a cell depends on atomic timing; the
 // results do not (the output slot travels with the task).
 
-// K5a: one thread per hadron of the batch: identity (species, event, draw) from the species-major
-// work offsets, cell choice (first block of the hadron's stream), histogram of the cells.
+// K5a: one thread per hadron of the batch, in work order: identity (species, event, draw) from the
+// species-major work offsets, cell choice (first block of the hadron's stream), the two series
+// values of the |p| sampler (MomentumSamplerBase::update_cache), histogram of the cells.  The FP64
+// work of the series runs in the shadow of the dependent loads of the cell search.  The task is
+// written at its work index; bucket_kernel moves it to its place in the cell-sorted list.
 __global__ void __launch_bounds__(SETUP_THREADS)
-pick_kernel(const SamplerArgs A) {
+setup_kernel(const SamplerArgs A) {
     extern __shared__ unsigned char smem_raw[];
-    int64_t *sp_off = reinterpret_cast<int64_t *>(smem_raw);      // off_work[s*nev], s = 0..ns
+    DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
+    int64_t *sp_off = reinterpret_cast<int64_t *>(sp + A.ns);     // off_work[s*nev], s = 0..ns
+    for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
     for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
         sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
     __syncthreads();
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    unsigned long long my_range = 0;
     for (int64_t base = static_cast<int64_t>(blockIdx.x)*blockDim.x; base < A.nwork;
          base += static_cast<int64_t>(gridDim.x)*blockDim.x) {
         const int64_t j = base + threadIdx.x;
@@ -668,54 +676,15 @@ pick_kernel(const SamplerArgs A) {
             int s;
             int64_t ev, k;
             work_identity(A, sp_off, w, s, ev, k);
-            uint32_t w0, w1, w2, w3;
-            philox_block(0u, static_cast<uint32_t>(k), static_cast<uint32_t>(A.ev_begin + ev),
-                         sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
-            cell = static_cast<int>(pick_cell(A, s, u53(w0, w1)));   // chunk mode: owned, hence >= 0
-            A.cellid[j] = cell;
-        }
-        // one atomic per distinct cell of the warp (one-cell surfaces put every hadron in one bin)
-        const unsigned peers = __match_any_sync(full, cell);
-        if (valid && lane == __ffs(peers) - 1)
-            atomicAdd(&A.cell_cnt[cell], static_cast<unsigned long long>(__popc(peers)));
-    }
-}
-
-// K5b: again one thread per hadron, after the exclusive scan of the histogram: the two series
-// values of the |p| sampler (MomentumSamplerBase::update_cache), the output slot, and the task
-// written to its place in the cell-sorted list.  Massively parallel, so the dependent loads are
-// hidden by occupancy instead of stalling the proposal loop.
-__global__ void __launch_bounds__(SETUP_THREADS)
-setup_kernel(const SamplerArgs A) {
-    extern __shared__ unsigned char smem_raw[];
-    DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
-    int64_t *sp_off = reinterpret_cast<int64_t *>(sp + A.ns);     // off_work[s*nev], s = 0..ns
-    for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
-    for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
-        sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
-    __syncthreads();
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    unsigned long long my_range = 0;
-    for (int64_t base = static_cast<int64_t>(blockIdx.x)*blockDim.x; base < A.nwork;
-         base += static_cast<int64_t>(gridDim.x)*blockDim.x) {
-        const int64_t j = base + threadIdx.x;
-        const bool valid = j < A.nwork;
-        int cell = -1 - lane;
-        Task32 t;
-        uint32_t slot = 0;
-        if (valid) {
-            const int64_t w = A.chunk ? __ldg(&A.wlist[j]) : j;
-            int s;
-            int64_t ev, k;
-            work_identity(A, sp_off, w, s, ev, k);
-            cell = __ldg(&A.cellid[j]);
             const DeviceSpecies p = sp[s];
-            const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
-            // position among the hadrons of (event, species) this rank writes
-            const int64_t k_out = A.chunk ? (__ldg(&A.own_pos[w]) - __ldg(&A.own_pos[w - k])) : k;
-            slot = static_cast<uint32_t>(__ldg(&A.off_out[ev*A.ns + s]) + k_out*mult);
+            Task32 t;
+            t.s = static_cast<uint16_t>(s);
+            t.event = static_cast<uint32_t>(A.ev_begin + ev);
+            t.draw = static_cast<uint32_t>(k);
+            uint32_t w0, w1, w2, w3;
+            philox_block(0u, t.draw, t.event, sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
+            cell = static_cast<int>(pick_cell(A, s, u53(w0, w1)));   // chunk mode: owned, hence >= 0
+            t.cell = static_cast<uint32_t>(cell);
             // T and the chemical potentials come from the 16-byte-per-cell copy (15 MB at C4: it
             // stays in L2)
             const float4 tm = __ldg(A.thermo + cell);
@@ -724,12 +693,45 @@ setup_kernel(const SamplerArgs A) {
             const bool ok = momentum_setup(A.mt, p.mass, p.sign, tm.x, species_mu(p, 1, th, p.mass), M);
             t.m_term = M.m_term;
             t.cdf_max = M.cdf_max;
-            t.cell = static_cast<uint32_t>(cell);
-            t.event = static_cast<uint32_t>(A.ev_begin + ev);
-            t.draw = static_cast<uint32_t>(k);
-            t.s = static_cast<uint16_t>(s);
             t.tab_idx = ok ? static_cast<uint16_t>(M.tab | (M.idx_min << 3)) : TASK_RANGE_ERROR;
             if (!ok) my_range++;
+            uint4 *dst = reinterpret_cast<uint4 *>(A.tasks_unsorted + j);
+            const uint4 *src = reinterpret_cast<const uint4 *>(&t);
+            dst[0] = src[0];
+            dst[1] = src[1];
+            if (A.chunk) {
+                // position among the hadrons of (event, species) this rank writes
+                const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
+                const int64_t k_out = __ldg(&A.own_pos[w]) - __ldg(&A.own_pos[w - k]);
+                A.slot_unsorted[j] = static_cast<uint32_t>(__ldg(&A.off_out[ev*A.ns + s]) + k_out*mult);
+            }
+        }
+        // one atomic per distinct cell of the warp (one-cell surfaces put every hadron in one bin)
+        const unsigned peers = __match_any_sync(full, cell);
+        if (valid && lane == __ffs(peers) - 1)
+            atomicAdd(&A.cell_cnt[cell], static_cast<unsigned long long>(__popc(peers)));
+    }
+    if (my_range) atomicAdd(&A.counters[3], my_range);
+}
+
+// K5b: after the exclusive scan of the histogram: every task to its place in the cell-sorted list
+// (a permutation: 32 bytes in, one 32-byte sector out).
+__global__ void __launch_bounds__(SETUP_THREADS)
+bucket_kernel(const SamplerArgs A) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int64_t base = static_cast<int64_t>(blockIdx.x)*blockDim.x; base < A.nwork;
+         base += static_cast<int64_t>(gridDim.x)*blockDim.x) {
+        const int64_t j = base + threadIdx.x;
+        const bool valid = j < A.nwork;
+        int cell = -1 - lane;
+        uint4 t0 = make_uint4(0u, 0u, 0u, 0u), t1 = t0;
+        if (valid) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(A.tasks_unsorted + j);
+            t0 = __ldg(src);
+            t1 = __ldg(src + 1);
+            cell = static_cast<int>(t1.x);
         }
         // position in the cell's bucket: one atomic per distinct cell of the warp
         const unsigned peers = __match_any_sync(full, cell);
@@ -741,13 +743,11 @@ setup_kernel(const SamplerArgs A) {
         if (valid) {
             const int64_t pos = static_cast<int64_t>(bucket) + __popc(peers & lt_mask);
             uint4 *dst = reinterpret_cast<uint4 *>(A.tasks + pos);
-            const uint4 *src = reinterpret_cast<const uint4 *>(&t);
-            dst[0] = src[0];
-            dst[1] = src[1];
-            A.task_slot[pos] = slot;
+            dst[0] = t0;
+            dst[1] = t1;
+            if (A.chunk) A.task_slot[pos] = __ldg(&A.slot_unsorted[j]);
         }
     }
-    if (my_range) atomicAdd(&A.counters[3], my_range);
 }
 
 // ---- bulk-async plumbing of the proposal kernel (mbarrier + cp.async.bulk, PTX ISA 8.x) ----------
@@ -806,32 +806,41 @@ __device__ __forceinline__ void lane_slot_fill(float4 *lc, int tid, const CellRe
 // (a) the reference's "impatience": after 4999 rejected tries a NEW cell is drawn (FSSW.cpp:1017-1018)
 // (b) local charge conservation: the partner is sampled from the same cell with conjugate
 //     quantum numbers (FSSW.cpp:1035-1048)
-__device__ __noinline__ bool lane_new_setup(const SamplerArgs *Ag, LaneState &L, double mass, int sign,
+// The lane state crosses the call by value in a ColdIO block: a reference to LaneState itself
+// would pin the whole state of the hot loop to local memory.
+struct ColdIO {
+    MomSetup M;
+    uint32_t block, draw, event, slot;
+    int s, cell, qsign, ok;
+};
+
+__device__ __noinline__ void lane_new_setup(const SamplerArgs *Ag, ColdIO *io, double mass, int sign,
                                             int B, int S, int Q, bool redraw_cell, uint32_t key0,
                                             uint32_t key1, float4 *lc, int tid) {
     // Ag: copy of the kernel arguments in global memory (taking the address of the by-value
     // kernel parameter would force a 1.2 KB per-thread stack copy)
     const SamplerArgs &A = *Ag;
+    io->ok = 0;
     if (redraw_cell) {
         uint32_t w0, w1, w2, w3;
-        philox_block(L.rng.block++, L.rng.draw, L.rng.event, sample_stream_word3(L.s), key0, key1,
+        philox_block(io->block++, io->draw, io->event, sample_stream_word3(io->s), key0, key1,
                      w0, w1, w2, w3);
-        const int64_t c = pick_cell(A, L.s, u53(w0, w1));
+        const int64_t c = pick_cell(A, io->s, u53(w0, w1));
         if (c < 0) {
             // surface-chunk mode: the new cell belongs to another rank (include/iss_cuda.h)
             atomicAdd(&A.counters[7], 1ull);
-            float2 *dst = reinterpret_cast<float2 *>(A.out + L.slot);
+            float2 *dst = reinterpret_cast<float2 *>(A.out + io->slot);
 #pragma unroll
             for (int q = 0; q < 5; q++) dst[q] = make_float2(0.f, 0.f);
-            return false;
+            return;
         }
-        L.cell = static_cast<int>(c);
-        lane_slot_fill(lc, tid, A.cellrec + L.cell);
+        io->cell = static_cast<int>(c);
+        lane_slot_fill(lc, tid, A.cellrec + io->cell);
     }
-    const float4 th = __ldg(&A.cellrec[L.cell].th);      // T, muB, muS, muQ
-    L.tries = 1;
-    return momentum_setup(A.mt, mass, sign, th.x,
-                          species_mu_bsq(L.qsign*B, L.qsign*S, L.qsign*Q, th.y, th.z, th.w, mass), L.M);
+    const float4 th = __ldg(&A.cellrec[io->cell].th);      // T, muB, muS, muQ
+    io->ok = momentum_setup(A.mt, mass, sign, th.x,
+                            species_mu_bsq(io->qsign*B, io->qsign*S, io->qsign*Q, th.y, th.z, th.w, mass),
+                            io->M) ? 1 : 0;
 }
 
 // SPEC selects a compile-time specialisation of the run-time mode flags (smaller and faster
@@ -888,7 +897,7 @@ __device__ __forceinline__ double inverse_cdf_smem(const double *tb, int n, doub
 
 constexpr int RING_TASKS = 16;          // tasks per stage of a warp's task ring
 constexpr int RING_STAGES = 2;
-constexpr uint32_t RING_STAGE_BYTES = RING_TASKS*(sizeof(Task32) + sizeof(uint32_t));
+constexpr uint32_t RING_STAGE_BYTES = RING_TASKS*sizeof(Task32);
 
 // K5c: persistent proposal kernel.  Every lane owns one hadron and repeats the reference's try
 // (|p| proposal, direction, accept test) until it is accepted, then boosts, emits the record and
@@ -919,15 +928,13 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 *lc = reinterpret_cast<float4 *>(smem_raw);                  // [9][SAMPLER_THREADS]
     Task32 *ring_all = reinterpret_cast<Task32 *>(lc + CELLREC_SLOT_CHUNKS*SAMPLER_THREADS);
-    uint32_t *rslot_all = reinterpret_cast<uint32_t *>(ring_all + NWARP*RING_STAGES*RING_TASKS);
-    uint64_t *bar_all = reinterpret_cast<uint64_t *>(rslot_all + NWARP*RING_STAGES*RING_TASKS);
+    uint64_t *bar_all = reinterpret_cast<uint64_t *>(ring_all + NWARP*RING_STAGES*RING_TASKS);
     PropSpecies *sp = reinterpret_cast<PropSpecies *>(bar_all + NWARP*RING_STAGES);
     double *sm_boson = reinterpret_cast<double *>(sp + A.ns);
     double *sm_fermion = sm_boson + 3*A.mt[0].n;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     Task32 *ring = ring_all + warp*RING_STAGES*RING_TASKS;
-    uint32_t *rslot = rslot_all + warp*RING_STAGES*RING_TASKS;
     uint64_t *bar = bar_all + warp*RING_STAGES;
     // slot chunks: 0 da | 1 pa | 2 pb | 3 u4 | 4 pos | 5 tz, inv_T | 6 inv_dsig, shear | 7 cb, c1 |
     // 8 inv_kappa, prefq
@@ -968,8 +975,7 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
         // (lane 0) the ring buffer was last read through the generic proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(&bar[buf], RING_STAGE_BYTES);
-        bulk_g2s(ring + buf*RING_TASKS, A.tasks + g*RING_TASKS, RING_TASKS*sizeof(Task32), &bar[buf]);
-        bulk_g2s(rslot + buf*RING_TASKS, A.task_slot + g*RING_TASKS, RING_TASKS*sizeof(uint32_t), &bar[buf]);
+        bulk_g2s(ring + buf*RING_TASKS, A.tasks + g*RING_TASKS, RING_STAGE_BYTES, &bar[buf]);
     };
     if (lane == 0) {
 #pragma unroll
@@ -986,7 +992,13 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
 
     for (;;) {
         // ------------------------------------------------------------ hand tasks to idle lanes
+        // (a) fetch: idle lanes copy their task out of the ring (the loop turns again only when a
+        // stage runs out in the middle of a hand-over); (b) set-up, once per round for all of them
         unsigned need_mask = __ballot_sync(full, !busy);
+        bool fresh = false;
+        double2 t0 = make_double2(0., 0.);
+        uint4 t1 = make_uint4(0u, 0u, 0u, 0u);
+        int64_t task_pos = 0;
         while (need_mask != 0u) {
             const int64_t g = gw + static_cast<int64_t>(k_stage)*W;
             if (g >= nstage) break;
@@ -998,37 +1010,14 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
             }
             const int64_t left = A.nwork - g*RING_TASKS;
             const int n_cur = left < RING_TASKS ? static_cast<int>(left) : RING_TASKS;
-            const int nneed = __popc(need_mask);
-            const int take = min(nneed, n_cur - cursor);
+            const int take = min(__popc(need_mask), n_cur - cursor);
             const int rank = __popc(need_mask & lt_mask);
-            if (!busy && rank < take) {
+            if (!busy && !fresh && rank < take) {
                 const int i = buf*RING_TASKS + cursor + rank;
-                const double2 t0 = *reinterpret_cast<const double2 *>(&ring[i]);       // m_term, cdf_max
-                const uint4 t1 = *(reinterpret_cast<const uint4 *>(&ring[i]) + 1);     // cell, event, draw, s | tab
-                L.slot = rslot[i];
-                L.cell = static_cast<int>(t1.x);
-                L.rng.event = t1.y;
-                L.rng.draw = t1.z;
-                L.rng.block = 1u;               // block 0 chose the cell (pick_kernel)
-                L.s = static_cast<int>(t1.w & 0xFFFFu);
-                const uint32_t tab_idx = t1.w >> 16;
-                L.qsign = 1;
-                L.tries = 1;
-                L.total_tries = 0;
-                if (tab_idx != TASK_RANGE_ERROR) {
-                    const float4 *src = reinterpret_cast<const float4 *>(A.cellrec + L.cell);
-#pragma unroll
-                    for (int c = 0; c < CELLREC_SLOT_CHUNKS; c++) cp_async16(&LC4(c), src + c);
-                    cp_async_commit();
-                    const float4 th = __ldg(src + CELLREC_SLOT_CHUNKS);     // T, muB, muS, muQ
-                    const PropSpecies p = sp[L.s];
-                    momentum_restore(p.mass, th.x,
-                                     species_mu_bsq(p.baryon, p.strange, p.charge, th.y, th.z, th.w, p.mass),
-                                     t0.x, t0.y, static_cast<int>(tab_idx & 7u),
-                                     static_cast<int>(tab_idx >> 3), L.M);
-                    busy = true;
-                }
-                // TASK_RANGE_ERROR: momentum table range error, counted by setup_kernel; no record
+                t0 = *reinterpret_cast<const double2 *>(&ring[i]);          // m_term, cdf_max
+                t1 = *(reinterpret_cast<const uint4 *>(&ring[i]) + 1);      // cell, event, draw, s | tab
+                task_pos = g*RING_TASKS + cursor + rank;
+                fresh = true;
             }
             cursor += take;
             if (cursor == n_cur) {
@@ -1039,7 +1028,41 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 cursor = 0;
                 stage_ready = false;
             }
-            need_mask = __ballot_sync(full, !busy);
+            need_mask = __ballot_sync(full, !busy && !fresh);
+        }
+        if (fresh) {
+            L.cell = static_cast<int>(t1.x);
+            L.rng.event = t1.y;
+            L.rng.draw = t1.z;
+            L.rng.block = 1u;               // block 0 chose the cell (setup_kernel)
+            L.s = static_cast<int>(t1.w & 0xFFFFu);
+            const uint32_t tab_idx = t1.w >> 16;
+            L.qsign = 1;
+            L.tries = 1;
+            L.total_tries = 0;
+            if (tab_idx != TASK_RANGE_ERROR) {
+                const float4 *src = reinterpret_cast<const float4 *>(A.cellrec + L.cell);
+#pragma unroll
+                for (int c = 0; c < CELLREC_SLOT_CHUNKS; c++) cp_async16(&LC4(c), src + c);
+                cp_async_commit();
+                const float4 th = __ldg(src + CELLREC_SLOT_CHUNKS);     // T, muB, muS, muQ
+                const PropSpecies p = sp[L.s];
+                if (A.chunk) {
+                    L.slot = __ldg(&A.task_slot[task_pos]);
+                } else {
+                    // output slot: hadron `draw` of (event, species); pairs under charge conservation
+                    const int mult = (lcc == 1 && p.charge > 0) ? 2 : 1;
+                    const int64_t ev = static_cast<int64_t>(t1.y) - A.ev_begin;
+                    L.slot = static_cast<uint32_t>(__ldg(&A.off_out[ev*A.ns + L.s])
+                                                   + static_cast<int64_t>(t1.z)*mult);
+                }
+                momentum_restore(p.mass, th.x,
+                                 species_mu_bsq(p.baryon, p.strange, p.charge, th.y, th.z, th.w, p.mass),
+                                 t0.x, t0.y, static_cast<int>(tab_idx & 7u),
+                                 static_cast<int>(tab_idx >> 3), L.M);
+                busy = true;
+            }
+            // TASK_RANGE_ERROR: momentum table range error, counted by setup_kernel; no record
         }
         if (!__any_sync(full, busy)) break;     // idle lanes are left only when the stages ran out
 
@@ -1050,14 +1073,30 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
             const double mass = p.mass;
             const int sign = p.sign;
             const MomentumTable &mt = A.mt[L.M.tab];
+            // the rare paths exchange the lane state by value (ColdIO)
+            auto cold_setup = [&](bool redraw) -> bool {
+                ColdIO io;
+                io.block = L.rng.block; io.draw = L.rng.draw; io.event = L.rng.event;
+                io.slot = L.slot; io.s = L.s; io.cell = L.cell; io.qsign = L.qsign;
+                lane_new_setup(Ag, &io, mass, sign, p.baryon, p.strange, p.charge, redraw, key0, key1,
+                               lc, tid);
+                L.rng.block = io.block;
+                L.cell = io.cell;
+                L.M = io.M;
+                L.tries = 1;
+                return io.ok != 0;
+            };
             // |p| proposal (MomentumSamplerBase.cpp:48-56); an inner rejection restarts the try
             uint32_t pw0, pw1, pw2, pw3;
             philox_block(L.rng.block++, L.rng.draw, L.rng.event, sample_stream_word3(L.s), key0, key1,
                          pw0, pw1, pw2, pw3);
             const double r = u53(pw0, pw1)*L.M.cdf_max;
+            // regime-0 tables (every species with (m - mu)/T < 30): ONE code path for bosons and
+            // fermions, the lanes of a warp differ in the table base only (cell-sorted tasks mix
+            // the species inside a warp)
             double Et;
-            if (L.M.tab == 0 && A.mt_smem) Et = inverse_cdf_smem(sm_boson, mt.n, mt.e0, mt.de_build, L.M, r);
-            else if (L.M.tab == 3 && A.mt_smem) Et = inverse_cdf_smem(sm_fermion, mt.n, mt.e0, mt.de_build, L.M, r);
+            if ((L.M.tab == 0 || L.M.tab == 3) && A.mt_smem)
+                Et = inverse_cdf_smem(L.M.tab == 0 ? sm_boson : sm_fermion, mt.n, mt.e0, mt.de_build, L.M, r);
             else Et = inverse_cdf<false>(mt.data, mt.n, L.M, r);
             const double E_sample = L.M.T*Et + L.M.mu;
             const double p_mag = sqrt(E_sample*E_sample - p.mass2);
@@ -1220,8 +1259,7 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                         L.qsign = -1;
                         L.slot += 1;
                         L.total_tries = 0;
-                        if (lane_new_setup(Ag, L, mass, sign, p.baryon, p.strange, p.charge, false,
-                                           key0, key1, lc, tid)) busy = true;
+                        if (cold_setup(false)) busy = true;
                         else my_range++;
                     }
                 } else {
@@ -1244,8 +1282,7 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                         } else if (L.qsign > 0) {
                             // the reference's "impatience" (FSSW.cpp:1017-1018 with status == 0)
                             my_redraws++;
-                            if (!lane_new_setup(Ag, L, mass, sign, p.baryon, p.strange, p.charge, true,
-                                                key0, key1, lc, tid)) {
+                            if (!cold_setup(true)) {
                                 my_range++;
                                 busy = false;
                             }
@@ -1503,7 +1540,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.hints = nullptr;
     A.tasks = nullptr;
     A.task_slot = nullptr;
-    A.cellid = nullptr;
+    A.tasks_unsorted = nullptr;
+    A.slot_unsorted = nullptr;
     A.cell_cnt = nullptr;
     A.cellrec = nullptr;
     A.wire = nullptr;
@@ -1616,22 +1654,24 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         const size_t need = sizeof(Task32)*static_cast<size_t>(nstage*RING_TASKS);
         if (need > h->tasks_bytes || !h->d_tasks) {
             if (h->d_tasks) cudaFree(h->d_tasks);
-            if (h->d_task_slot) cudaFree(h->d_task_slot);
-            if (h->d_cellid) cudaFree(h->d_cellid);
+            if (h->d_tasks_unsorted) cudaFree(h->d_tasks_unsorted);
             h->d_tasks = nullptr;
-            h->d_task_slot = nullptr;
-            h->d_cellid = nullptr;
+            h->d_tasks_unsorted = nullptr;
             h->tasks_bytes = need + need/8 + 4096;
-            const size_t cap = h->tasks_bytes/sizeof(Task32);
             ISS_CUDA_TRY(h, cudaMalloc(&h->d_tasks, h->tasks_bytes));
-            ISS_CUDA_TRY(h, cudaMalloc(&h->d_task_slot, sizeof(uint32_t)*cap));
-            ISS_CUDA_TRY(h, cudaMalloc(&h->d_cellid, sizeof(int32_t)*cap));
+            ISS_CUDA_TRY(h, cudaMalloc(&h->d_tasks_unsorted, h->tasks_bytes));
         }
         ISS_ENSURE(h, h->d_cellcnt, h->cellcnt_bytes, sizeof(unsigned long long)*(h->ncell + 2));
         A.tasks = static_cast<Task32 *>(h->d_tasks);
-        A.task_slot = h->d_task_slot;
-        A.cellid = h->d_cellid;
+        A.tasks_unsorted = static_cast<Task32 *>(h->d_tasks_unsorted);
         A.cell_cnt = h->d_cellcnt;
+        if (h->chunk) {     // output slots travel through the sort (they do not follow from the draw index)
+            const size_t slot_need = sizeof(uint32_t)*static_cast<size_t>(nstage*RING_TASKS);
+            ISS_ENSURE(h, h->d_task_slot, h->task_slot_bytes, slot_need);
+            ISS_ENSURE(h, h->d_slot_unsorted, h->slot_unsorted_bytes, slot_need);
+            A.task_slot = h->d_task_slot;
+            A.slot_unsorted = h->d_slot_unsorted;
+        }
     }
     if (!h->cellrec_valid) {
         rc = build_cellrec(h);
@@ -1660,13 +1700,12 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         }
         // counting sort of the batch's hadrons by cell: histogram, exclusive scan, scatter
         ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_cellcnt, 0, sizeof(unsigned long long)*(h->ncell + 1), h->stream));
-        pick_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, sizeof(int64_t)*(ns + 1), h->stream>>>(A);
-        ISS_LAUNCHED(h);
+        const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
+        setup_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
         rc = device_exclusive_scan_i64(h, reinterpret_cast<const int64_t *>(h->d_cellcnt),
                                        reinterpret_cast<int64_t *>(h->d_cellcnt), h->ncell, nullptr);
         if (rc) return rc;
-        const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
-        setup_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
+        bucket_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, 0, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
 
@@ -1689,7 +1728,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         : spec == 3 ? propose_kernel<1, 3> : propose_kernel<1, 0>;
     constexpr int NWARP = SAMPLER_THREADS/32;
     const size_t smem = sizeof(float4)*CELLREC_SLOT_CHUNKS*SAMPLER_THREADS
-                        + (sizeof(Task32) + sizeof(uint32_t))*NWARP*RING_STAGES*RING_TASKS
+                        + sizeof(Task32)*NWARP*RING_STAGES*RING_TASKS
                         + sizeof(uint64_t)*NWARP*RING_STAGES + sizeof(PropSpecies)*ns
                         + sizeof(double)*3*(A.mt[0].n + A.mt[3].n);
     {
