@@ -580,10 +580,20 @@ int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_e
         ISS_FAIL(h, ISS_ERR_RANGE, buf);
     }
     if (cnt[6] != 0) {
-        char buf[200];
+        // which (cell, species) could not be sampled: the first one a warp gave up on
+        unsigned long long who[2] = {0, 0};
+        if (mail_post(h, h->d_counters + 8, 2, 24) == ISS_OK
+            && cudaStreamSynchronize(h->stream) == cudaSuccess) {
+            who[0] = *reinterpret_cast<volatile unsigned long long *>(h->h_mail + 24);
+            who[1] = *reinterpret_cast<volatile unsigned long long *>(h->h_mail + 25);
+        }
+        const int sidx = static_cast<int>(who[1]);
+        const int pid = (sidx >= 0 && sidx < h->nspecies) ? h->h_species[sidx].pid : 0;
+        char buf[320];
         snprintf(buf, sizeof(buf),
                  "sampler gave up on %llu hadrons after %d rejected tries each (zero acceptance in "
-                 "every cell drawn); their records are null (pid 0)", cnt[6], 2000000);
+                 "every cell drawn), e.g. species %d (pid %d) in cell %llu; their records are null (pid 0)",
+                 cnt[6], 2000000, sidx, pid, who[0]);
         ISS_FAIL(h, ISS_ERR_RANGE, buf);
     }
     if (cnt[3] != 0) {

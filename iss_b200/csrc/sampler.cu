@@ -318,7 +318,7 @@ struct SamplerArgs {
 };
 
 constexpr int SETUP_THREADS = 256;
-constexpr int SAMPLER_THREADS = 768;     // one CTA of 24 warps per SM (640: 16.8 ms, 1024: 16.2 ms, 768: 15.5 ms on C4) (96 KB of tables in smem)
+constexpr int SAMPLER_THREADS = 768;     // one CTA of 24 warps per SM (80 registers per thread)
 constexpr int MAX_IMPATIENCE = 5000;    // FSSW.cpp:1872
 constexpr int MAX_TRIES_PER_HADRON = 2000000;   // safety valve, see propose_kernel
 
@@ -344,13 +344,24 @@ __device__ __forceinline__ double table_F(const double *__restrict__ tb, int i, 
     return b.y + w1*b.x + w0*a.y - m_term;
 }
 
+// mu/T.  0/T = 0 exactly, but a zero numerator sends the FP64 division down its slow path (a quarter
+// of the hadrons: every species with B = S = Q = 0), so a harmless numerator is divided instead; the
+// empty asm keeps the compiler from folding the two selects back into one division.
+__device__ __forceinline__ double mu_over_T(double mu, double T) {
+    double num = (mu == 0.) ? 1. : mu;
+    asm volatile("" : "+d"(num));
+    const double q = num/T;
+    return (mu == 0.) ? mu : q;
+}
+
 // the cheap part: everything but the two series values, which travel in the Task
 __device__ __forceinline__ void momentum_restore(double mass, double T_in, double mu, double m_term,
                                                  double cdf_max, int tab, int idx_min, MomSetup &M) {
     const double T = fmax(1e-16, T_in);
     const double m_tilde = mass/T;
-    // (0/T = 0 exactly; a zero numerator sends the FP64 division down its slow path)
-    const double mu_tilde = (mu == 0.) ? mu : mu/T;
+    // 0/T = 0 exactly, but a zero numerator sends the FP64 division down its slow path (a quarter
+    // of the hadrons: every species with B = S = Q = 0): divide a harmless numerator instead
+    const double mu_tilde = mu_over_T(mu, T);
     M.T = T;
     M.mu = mu;
     M.mu_tilde = mu_tilde;
@@ -368,7 +379,7 @@ __device__ __forceinline__ bool momentum_setup(const MomentumTable *__restrict__
                                                int sign, double T_in, double mu, MomSetup &M) {
     const double T = fmax(1e-16, T_in);
     const double m_tilde = mass/T;
-    const double mu_tilde = (mu == 0.) ? mu : mu/T;     // see momentum_restore
+    const double mu_tilde = mu_over_T(mu, T);
     const double a = m_tilde - mu_tilde;
     const double m0tilde = m_tilde - mu_tilde;
     const int regime = (m0tilde < 30.) ? 0 : (m0tilde < 50. ? 1 : 2);
@@ -796,10 +807,10 @@ struct LaneState {
 
 // chunks 0..8 of a cell record -> the lane's shared-memory slot ([chunk][lane] layout: 16-byte
 // accesses of a warp are conflict free)
-__device__ __forceinline__ void lane_slot_fill(float4 *lc, int tid, const CellRec *rec) {
+__device__ __forceinline__ void lane_slot_fill(float4 *lc, int nthreads, int tid, const CellRec *rec) {
     const float4 *src = reinterpret_cast<const float4 *>(rec);
 #pragma unroll
-    for (int c = 0; c < CELLREC_SLOT_CHUNKS; c++) lc[c*SAMPLER_THREADS + tid] = __ldg(src + c);
+    for (int c = 0; c < CELLREC_SLOT_CHUNKS; c++) lc[c*nthreads + tid] = __ldg(src + c);
 }
 
 // Rare paths of the proposal kernel, kept out of line so that the hot loop stays small.
@@ -816,7 +827,7 @@ struct ColdIO {
 
 __device__ __noinline__ void lane_new_setup(const SamplerArgs *Ag, ColdIO *io, double mass, int sign,
                                             int B, int S, int Q, bool redraw_cell, uint32_t key0,
-                                            uint32_t key1, float4 *lc, int tid) {
+                                            uint32_t key1, float4 *lc, int nthreads, int tid) {
     // Ag: copy of the kernel arguments in global memory (taking the address of the by-value
     // kernel parameter would force a 1.2 KB per-thread stack copy)
     const SamplerArgs &A = *Ag;
@@ -835,7 +846,7 @@ __device__ __noinline__ void lane_new_setup(const SamplerArgs *Ag, ColdIO *io, d
             return;
         }
         io->cell = static_cast<int>(c);
-        lane_slot_fill(lc, tid, A.cellrec + io->cell);
+        lane_slot_fill(lc, nthreads, tid, A.cellrec + io->cell);
     }
     const float4 th = __ldg(&A.cellrec[io->cell].th);      // T, muB, muS, muQ
     io->ok = momentum_setup(A.mt, mass, sign, th.x,
@@ -907,9 +918,10 @@ constexpr uint32_t RING_STAGE_BYTES = RING_TASKS*sizeof(Task32);
 // cp.async.bulk, completion on one mbarrier per stage, so that a task hand-over is a
 // shared-memory read + one L1/L2-resident cell record (copied into the lane's slot with cp.async)
 // instead of a chain of three dependent DRAM gathers.
-template <int MIN_BLOCKS, int SPEC>
-__global__ void __launch_bounds__(SAMPLER_THREADS, MIN_BLOCKS)
+template <int NTHREADS, int SPEC>
+__global__ void __launch_bounds__(NTHREADS, 1)
 propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
+    constexpr int SAMPLER_THREADS = NTHREADS;
     using SM = SpecMode<SPEC>;
     ModeFlags mode;
     mode.include_shear = SM::generic ? A.mode.include_shear : SM::shear;
@@ -968,20 +980,28 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
     const unsigned full = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
     // stages of this warp: g = gw + k W, k = 0, 1, ...; stage k lives in ring buffer k & 1
-    const int64_t W = static_cast<int64_t>(gridDim.x)*NWARP;
-    const int64_t gw = static_cast<int64_t>(blockIdx.x)*NWARP + warp;
-    const int64_t nstage = (A.nwork + RING_TASKS - 1)/RING_TASKS;
-    auto issue_stage = [&](int buf, int64_t g) {
+    // (a batch holds fewer than 2^32 tasks: stage indices fit 32 bits)
+    const int W = static_cast<int>(gridDim.x)*NWARP;
+    const int gw = static_cast<int>(blockIdx.x)*NWARP + warp;
+    const int nstage = static_cast<int>((A.nwork + RING_TASKS - 1)/RING_TASKS);
+    auto issue_stage = [&](int buf, int g) {
         // (lane 0) the ring buffer was last read through the generic proxy
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         mbar_arrive_expect_tx(&bar[buf], RING_STAGE_BYTES);
-        bulk_g2s(ring + buf*RING_TASKS, A.tasks + g*RING_TASKS, RING_STAGE_BYTES, &bar[buf]);
+        bulk_g2s(ring + buf*RING_TASKS, A.tasks + static_cast<int64_t>(g)*RING_TASKS, RING_STAGE_BYTES,
+                 &bar[buf]);
     };
     if (lane == 0) {
 #pragma unroll
         for (int b = 0; b < RING_STAGES; b++)
             if (gw + b*W < nstage) issue_stage(b, gw + b*W);
     }
+    // tasks in stage g (0 past the end of the list)
+    const uint32_t nwork32 = static_cast<uint32_t>(A.nwork);
+    auto stage_tasks = [&](int g) -> int {
+        const uint32_t left = nwork32 - static_cast<uint32_t>(g)*RING_TASKS;
+        return left >= RING_TASKS ? RING_TASKS : static_cast<int>(left);
+    };
     int k_stage = 0;            // stages this warp has used up
     int cursor = 0;             // tasks of the current stage handed out
     bool stage_ready = false;   // the current stage's bytes have landed
@@ -998,9 +1018,9 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
         bool fresh = false;
         double2 t0 = make_double2(0., 0.);
         uint4 t1 = make_uint4(0u, 0u, 0u, 0u);
-        int64_t task_pos = 0;
+        uint32_t task_pos = 0;
         while (need_mask != 0u) {
-            const int64_t g = gw + static_cast<int64_t>(k_stage)*W;
+            const int g = gw + k_stage*W;
             if (g >= nstage) break;
             const int buf = k_stage & (RING_STAGES - 1);
             if (!stage_ready) {
@@ -1008,15 +1028,14 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 while (!mbar_try_wait(&bar[buf], parity)) { }
                 stage_ready = true;
             }
-            const int64_t left = A.nwork - g*RING_TASKS;
-            const int n_cur = left < RING_TASKS ? static_cast<int>(left) : RING_TASKS;
+            const int n_cur = stage_tasks(g);
             const int take = min(__popc(need_mask), n_cur - cursor);
             const int rank = __popc(need_mask & lt_mask);
             if (!busy && !fresh && rank < take) {
                 const int i = buf*RING_TASKS + cursor + rank;
                 t0 = *reinterpret_cast<const double2 *>(&ring[i]);          // m_term, cdf_max
                 t1 = *(reinterpret_cast<const uint4 *>(&ring[i]) + 1);      // cell, event, draw, s | tab
-                task_pos = g*RING_TASKS + cursor + rank;
+                task_pos = static_cast<uint32_t>(g)*RING_TASKS + cursor + rank;
                 fresh = true;
             }
             cursor += take;
@@ -1079,7 +1098,7 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                 io.block = L.rng.block; io.draw = L.rng.draw; io.event = L.rng.event;
                 io.slot = L.slot; io.s = L.s; io.cell = L.cell; io.qsign = L.qsign;
                 lane_new_setup(Ag, &io, mass, sign, p.baryon, p.strange, p.charge, redraw, key0, key1,
-                               lc, tid);
+                               lc, SAMPLER_THREADS, tid);
                 L.rng.block = io.block;
                 L.cell = io.cell;
                 L.M = io.M;
@@ -1723,13 +1742,23 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         force_generic = (e && atoi(e) == 1) ? 1 : 0;
     }
     if (force_generic) spec = 0;
+    // CTA size: 768 threads (80 registers each); ISS_SAMPLER_THREADS=640 / 512 select the tuning
+    // variants of the CE + diffusion specialisation (96 / 128 registers)
+    int nthreads = SAMPLER_THREADS;
     void (*kern)(const SamplerArgs, const SamplerArgs *) =
-        spec == 1 ? propose_kernel<1, 1> : spec == 2 ? propose_kernel<1, 2>
-        : spec == 3 ? propose_kernel<1, 3> : propose_kernel<1, 0>;
-    constexpr int NWARP = SAMPLER_THREADS/32;
-    const size_t smem = sizeof(float4)*CELLREC_SLOT_CHUNKS*SAMPLER_THREADS
-                        + sizeof(Task32)*NWARP*RING_STAGES*RING_TASKS
-                        + sizeof(uint64_t)*NWARP*RING_STAGES + sizeof(PropSpecies)*ns
+        spec == 1 ? propose_kernel<SAMPLER_THREADS, 1> : spec == 2 ? propose_kernel<SAMPLER_THREADS, 2>
+        : spec == 3 ? propose_kernel<SAMPLER_THREADS, 3> : propose_kernel<SAMPLER_THREADS, 0>;
+    static int tune_threads = -1;
+    if (tune_threads < 0) {
+        const char *e = getenv("ISS_SAMPLER_THREADS");
+        tune_threads = e ? atoi(e) : 0;
+    }
+    if (spec == 1 && tune_threads == 640) { kern = propose_kernel<640, 1>; nthreads = 640; }
+    if (spec == 1 && tune_threads == 512) { kern = propose_kernel<512, 1>; nthreads = 512; }
+    const int nwarp = nthreads/32;
+    const size_t smem = sizeof(float4)*CELLREC_SLOT_CHUNKS*nthreads
+                        + sizeof(Task32)*nwarp*RING_STAGES*RING_TASKS
+                        + sizeof(uint64_t)*nwarp*RING_STAGES + sizeof(PropSpecies)*ns
                         + sizeof(double)*3*(A.mt[0].n + A.mt[3].n);
     {
         int smem_max = 0;
@@ -1740,11 +1769,11 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     ISS_CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
     int64_t grid = nsm;         // persistent: one CTA per SM
-    const int64_t max_useful = (A.nwork + SAMPLER_THREADS - 1)/SAMPLER_THREADS;
+    const int64_t max_useful = (A.nwork + nthreads - 1)/nthreads;
     if (grid > max_useful) grid = max_useful;
     {
         ScopedTimer t(h, ISS_T_SAMPLE);
-        kern<<<static_cast<unsigned>(grid), SAMPLER_THREADS, smem, h->stream>>>(
+        kern<<<static_cast<unsigned>(grid), nthreads, smem, h->stream>>>(
             A, static_cast<const SamplerArgs *>(h->d_sampler_args)); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());

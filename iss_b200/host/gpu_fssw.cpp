@@ -679,17 +679,27 @@ void GpuFSSW::sample_events() {
     info("number of repeated sampling = " + std::to_string(number_of_repeated_sampling_));
     const double y_LB = paraRdr_->getVal("y_LB"), y_RB = paraRdr_->getVal("y_RB");
     double dN_event = 0.;
+    // the reference prints two lines per species here (FSSW.cpp:960-962); 642 lines per call are
+    // noise in front of a 50 ms call, so they appear only with ISS_VERBOSE=1 (or AMOUNT_OF_OUTPUT > 0)
+    static const bool per_species_log = (iSS_data::AMOUNT_OF_OUTPUT > 0)
+                                        || (getenv("ISS_VERBOSE") && atoi(getenv("ISS_VERBOSE")) > 0);
     for (size_t n = 0; n < species_.size(); n++) {
         const particle_info &p = particles_[species_table_idx_[n]];
         const double dN_dy = dN_species_[n];
         const double dN = (hydro_mode_ != 2) ? (y_RB - y_LB)*dN_dy : dN_dy;
         dN_event += dN;
+        if (!per_species_log) continue;
         std::ostringstream os;
         os << "Index: " << n << ", Name: " << p.name << ", Monte-carlo index: " << p.monval;
         info(os.str());
         std::ostringstream os2;
         os2 << " -- Sampling using dN_dy=" << dN_dy << ", dN=" << dN << "...";
         info(os2.str());
+    }
+    {
+        std::ostringstream os;
+        os << " -- Sampling " << species_.size() << " species, dN per event = " << dN_event;
+        info(os.str());
     }
 
     nev_ = number_of_repeated_sampling_;
@@ -770,11 +780,77 @@ void GpuFSSW::sample_events() {
     }
     { PhaseTimer tw("final fetch_wait"); check_(iss_cuda_fetch_wait(h_), "iss_cuda_fetch_wait"); }
     if (flag_spectators_) std::cout << "Add spectators to the hadron list... " << std::endl;
+    if (static_cast<int>(paraRdr_->getVal("reduce_checks_over_ranks", 0)) == 1) {
+        // one process per GPU, events sharded over the ranks (first_event_index): the QA block
+        // behind iSS::perform_checks is summed over the ranks; hadron lists stay rank-local
+        join_ranks_();
+        check_(iss_cuda_histograms_allreduce(h_, nullptr), "iss_cuda_histograms_allreduce");
+    }
     qa_.assign(iss_cuda_qa_size(), 0.);
     check_(iss_cuda_qa_fetch(h_, qa_.data()), "iss_cuda_qa_fetch");
     std::cout << std::endl
               << "sample_using_dN_dxtdy_4all_particles finished in " << seconds_since(t0)
               << " seconds." << std::endl;
+}
+
+// Rank and size of the job: parameters nccl_rank / nccl_nranks, else the environment of the
+// launcher (torchrun: RANK / WORLD_SIZE, Open MPI, PMI, Slurm).  Rendezvous through a file: rank 0
+// writes the 128-byte NCCL id to $ISS_NCCL_ID_FILE (default /tmp/iss_nccl_id_<MASTER_PORT>), the
+// others wait for it; ncclCommInitRank returns once every rank has joined, then rank 0 removes
+// the file.  The communicator lives on the pooled handle for the rest of the process.
+void GpuFSSW::join_ranks_() {
+    auto env_int = [](std::initializer_list<const char *> names, int fallback) {
+        for (const char *n : names)
+            if (const char *v = getenv(n)) return atoi(v);
+        return fallback;
+    };
+    int nranks = static_cast<int>(paraRdr_->getVal("nccl_nranks", -1));
+    int rank = static_cast<int>(paraRdr_->getVal("nccl_rank", -1));
+    if (nranks < 0)
+        nranks = env_int({"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS"}, 1);
+    if (rank < 0) rank = env_int({"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID"}, 0);
+    qa_ranks_ = std::max(1, nranks);
+    if (nranks <= 1) return;
+    static std::mutex mu;
+    static std::map<iss_handle *, int> joined;      // handle -> size of the communicator it holds
+    std::lock_guard<std::mutex> lk(mu);
+    if (joined.count(h_) && joined[h_] == nranks) return;
+    std::string file;
+    if (const char *f = getenv("ISS_NCCL_ID_FILE")) file = f;
+    else file = std::string("/tmp/iss_nccl_id_") + (getenv("MASTER_PORT") ? getenv("MASTER_PORT") : "0");
+    unsigned char id[128];
+    if (rank == 0) {
+        if (iss_cuda_nccl_unique_id(id) != ISS_OK) {
+            iss_host::error("reduce_checks_over_ranks: NCCL (libnccl.so.2) is not available");
+            exit(-1);
+        }
+        const std::string tmp = file + ".tmp";
+        FILE *f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(id, 1, sizeof(id), f) != sizeof(id)) {
+            iss_host::error("reduce_checks_over_ranks: can not write " + tmp);
+            exit(-1);
+        }
+        fclose(f);
+        rename(tmp.c_str(), file.c_str());
+    } else {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (;;) {
+            FILE *f = fopen(file.c_str(), "rb");
+            if (f) {
+                const size_t got = fread(id, 1, sizeof(id), f);
+                fclose(f);
+                if (got == sizeof(id)) break;
+            }
+            if (seconds_since(t0) > 300.) {
+                iss_host::error("reduce_checks_over_ranks: no NCCL id in " + file + " after 300 s");
+                exit(-1);
+            }
+            std::this_thread::sleep_for(std::chrono::milliseconds(20));
+        }
+    }
+    check_(iss_cuda_nccl_init(h_, id, rank, nranks), "iss_cuda_nccl_init");
+    if (rank == 0) remove(file.c_str());
+    joined[h_] = nranks;
 }
 
 void GpuFSSW::shell() {

@@ -65,6 +65,10 @@ class GpuFSSW {
     const std::vector<iss_species> &species() const { return species_; }
     const std::vector<double> &species_dN() const { return dN_species_; }
     const std::vector<double> &qa_block() const { return qa_; }
+    // events behind the QA block: this process's, or those of all ranks when the block was reduced
+    // over the ranks of the job (parameter reduce_checks_over_ranks = 1)
+    double qa_events() const { return qa_.empty() ? 0. : qa_[0]; }
+    int qa_ranks() const { return qa_ranks_; }
     const iSS_Hadron *hadron_buffer() const { return hadrons_; }
     const std::vector<int64_t> &event_offsets() const { return event_off_; }
     int number_of_chosen_particles() const { return static_cast<int>(species_.size()); }
@@ -91,6 +95,8 @@ class GpuFSSW {
     std::vector<int> species_table_idx_;    // index into particles_ (chosen_particles_sampling_table)
     std::vector<double> dN_species_;
     std::vector<double> qa_;
+    int qa_ranks_ = 1;
+    void join_ranks_();     // NCCL communicator of the job on the pooled handle (once per process)
 
     iSS_Hadron *hadrons_ = nullptr;         // pinned, all events
     int64_t hadron_cap_ = 0;

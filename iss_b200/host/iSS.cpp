@@ -628,7 +628,9 @@ void iSS::construct_Tmunu_from_particle_samples() {
     info("Constructing the fluid cell T^{mu nu} from samples ...");
     const std::vector<double> &qa = spectra_sampler_->qa_block();
     const double volume = FOsurf_LRF_array_[0].da_mu_LRF[0]/FOsurf_LRF_array_[0].u_tz[0];
-    const double nev = get_number_of_sampled_events();
+    // the events behind the block: all ranks' when it was reduced (reduce_checks_over_ranks = 1)
+    const double nev = (spectra_sampler_->qa_ranks() > 1) ? spectra_sampler_->qa_events()
+                                                          : get_number_of_sampled_events();
     std::ofstream output("checkReconstructedTmunu.dat");
     output << "# Tmunu_FOcell[GeV/fm^3]  Tmunu_Particles[GeV/fm^3]  diff" << std::endl;
     for (int i = 0; i < 4; i++)
@@ -660,7 +662,8 @@ void iSS::perform_checks() {
     info("Performing checks for the samples ...");
     construct_Tmunu_from_particle_samples();
     const std::vector<double> &qa = spectra_sampler_->qa_block();
-    const double nev = get_number_of_sampled_events();
+    const double nev = (spectra_sampler_->qa_ranks() > 1) ? spectra_sampler_->qa_events()
+                                                          : get_number_of_sampled_events();
     const char *files[2] = {"check_211_spectra.dat", "check_2212_spectra.dat"};
     const double bin_width = 5.0/(ISS_QA_NPT - 1);
     for (int k = 0; k < 2; k++) {

@@ -356,6 +356,7 @@ void read_FOdata::read_text_surface_3d_(std::vector<FO_surf> &surf, const std::s
     }
     const size_t len = buf.size() - 1;
     const int bulk = turn_on_bulk_, rhob = turn_on_rhob_, diff = turn_on_diff_;
+    const char *const file_end = buf.data() + len;
     auto parse_piece = [&](const char *p, const char *end, TextPiece &out) {
         for (;;) {
             RawCell r;
@@ -372,6 +373,13 @@ void read_FOdata::read_text_surface_3d_(std::vector<FO_surf> &surf, const std::s
                 for (int i = 0; i < 4 && ok; i++) { ok = parse_num(q, end, r.q[i]); got += ok; }
             if (!ok) {          // end of data (the reference stops at stream eof)
                 out.partial = got > 0;
+                break;
+            }
+            if (q >= file_end) {
+                // the cell's last number ends exactly at the end of the file: the reference's
+                // stream extraction has set eofbit by then and the cell is NOT kept
+                // (`if (!surfdat.eof())`, readindata.cpp:752)
+                out.partial = true;
                 break;
             }
             p = q;
@@ -421,6 +429,7 @@ void read_FOdata::read_text_surface_boost_invariant_(std::vector<FO_surf> &surf,
     size_t len = buf.size() - 1;
     while (len > 0 && buf[len - 1] != '\n') len--;
     const int bulk = turn_on_bulk_, rhob = turn_on_rhob_, diff = turn_on_diff_;
+    const char *const file_end = buf.data() + len;
     auto parse_piece = [&](const char *p, const char *end, TextPiece &out) {
         while (p < end) {
             const char *eol = static_cast<const char *>(memchr(p, '\n', end - p));
