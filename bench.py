@@ -41,6 +41,35 @@ OVERRIDES = dict(afterburner_type=1, include_deltaf_diffusion=1, include_deltaf_
                  use_OSCAR_format=0, use_gzip_format=0, use_binary_format=0, perform_checks=0,
                  MC_sampling=4, local_charge_conservation=0, sample_upto_desired_particle_number=0)
 SURFACE_SEED = 2024          # C4 seed
+# BASELINE.json configs: the default (and the configuration the metric is quoted on) is C4; the
+# others are selectable with --workload for measurements that are not the headline line.
+#   c3        configs[2]: 2+1D boost-invariant surface, 10^5 cells, SMASH list, CE delta-f, decays
+#             requested -- FSSW::shell skips the feed-down for SMASH (FSSW.cpp:346), so no decays run
+#   c3-decays the same surface with the UrQMD list, for which the reference does decay: times
+#             decay_kernel (roofline_decay)
+#   c5        configs[4]: C4's generator at 10^7 cells, 100 events per step
+WORKLOADS = {
+    "c4": dict(cells=1000000, events=1000, gen=dict(eos=14, rhob=1, diffusion=1, binary=1), over={},
+               label="C4 (BASELINE.json configs[3]): synthetic 3+1D MUSIC-format surface, %d cells, EOS 14 + "
+                     "rho_B + baryon diffusion, CE delta-f shear+bulk+diffusion, urqmd_v3.3+ list (321 "
+                     "species)"),
+    "c3": dict(cells=100000, events=1000, gen=dict(eos=91, boost_invariant=True, binary=0),
+               over=dict(hydro_mode=1, include_deltaf_diffusion=0, perform_decays=1, y_LB=-2.5, y_RB=2.5),
+               label="C3 (BASELINE.json configs[2]): synthetic 2+1D boost-invariant surface, %d cells, EOS 91, "
+                     "SMASH list (400 species), CE delta-f shear+bulk, |y| < 2.5, perform_decays = 1 (skipped "
+                     "for SMASH like FSSW::shell does)"),
+    "c3-decays": dict(cells=100000, events=1000, gen=dict(eos=9, boost_invariant=True, binary=0),
+                      over=dict(hydro_mode=1, include_deltaf_diffusion=0, perform_decays=1, y_LB=-2.5,
+                                y_RB=2.5),
+                      label="C3 surface with the UrQMD list: synthetic 2+1D boost-invariant surface, %d cells, "
+                            "EOS 9, urqmd_v3.3+ list (321 species), CE delta-f shear+bulk, |y| < 2.5, "
+                            "resonance decays on"),
+    "c5": dict(cells=10000000, events=100, gen=dict(eos=14, rhob=1, diffusion=1, binary=1), over={},
+               label="C5 (BASELINE.json configs[4]): C4's generator at %d cells, EOS 14 + rho_B + baryon "
+                     "diffusion, CE delta-f shear+bulk+diffusion, urqmd_v3.3+ list (321 species)"),
+}
+BYTES_PER_DECAY_IN = 40.0    # one primary record in; out: 40 B per final hadron (measured ratio)
+FLOP_PER_DECAY = 250.0
 # algorithmic work per unit (restated in DESIGN.md)
 BYTES_PER_HADRON = 152.0     # 40 B record out + 112 B cell record in
 FLOP_PER_HADRON = 1.0e3
@@ -120,16 +149,19 @@ def bind_to_gpu_numa_node(local):
         return "not bound (%s)" % type(exc).__name__
 
 
-def make_case(folder, ncell):
+def make_case(folder, ncell, workload="c4"):
     from iss_b200 import synthetic
-    synthetic.make_case(folder, ncell=ncell, seed=SURFACE_SEED, eos=14, rhob=1, diffusion=1, binary=1)
+    synthetic.make_case(folder, ncell=ncell, seed=SURFACE_SEED, **WORKLOADS[workload]["gen"])
 
 
-def workload_name(ncell, events):
-    return ("C4 (BASELINE.json configs[3]): synthetic 3+1D MUSIC-format surface, %d cells, EOS 14 + "
-            "rho_B + baryon diffusion, CE delta-f shear+bulk+diffusion, urqmd_v3.3+ list (321 "
-            "species); step = yields of all cells x species + CDF + multiplicities + %d sampled "
-            "events (+ QA histograms)" % (ncell, events))
+def overrides_of(workload):
+    return dict(OVERRIDES, **WORKLOADS[workload]["over"])
+
+
+def workload_name(ncell, events, workload="c4"):
+    return (WORKLOADS[workload]["label"] % ncell
+            + "; step = yields of all cells x species + CDF + multiplicities + %d sampled events"
+              "%s (+ QA histograms)" % (events, " + resonance decays" if workload == "c3-decays" else ""))
 
 
 def spectra_leg(cells=5000):
@@ -191,9 +223,10 @@ def run_engine(args):
 
     E = args.events_per_step
     work = tempfile.mkdtemp(prefix="iss_bench_r%d_" % rank)
-    make_case(work, args.cells)
+    make_case(work, args.cells, args.workload)
+    decays_on = args.workload == "c3-decays"
     try:
-        over = dict(OVERRIDES, number_of_repeated_sampling=E)
+        over = dict(overrides_of(args.workload), number_of_repeated_sampling=E)
         s = capi.Sampler(work, PARAM, "surface.dat", **over)
         s.read_in_FO_surface()
         s.set_random_seed(args.seed)
@@ -215,17 +248,24 @@ def run_engine(args):
             e.compute_yields()
             ev0, ev1 = sharding.weak_event_range(k, rank, world, E)
             c = e.sample(args.seed, ev0, ev1)
+            n_primary = c.n_hadrons
+            if decays_on:
+                c2 = e.decay(args.seed)
+                decay_counts[0] += n_primary
+                decay_counts[1] += c2.n_hadrons
             e.L.iss_cuda_histograms(e.h, capi._ptr(np.asarray(qa_pids, dtype=np.int32)),
                                     len(qa_pids), 0)
             if world > 1:       # NCCL: QA histograms only
                 sharding.allreduce_sum_(sharding.device_block_as_tensor(e.qa_device_ptr(), qa_n, "cuda"))
-            return c.n_hadrons, c.n_tries
+            return n_primary, c.n_tries
 
+        decay_counts = [0, 0]       # primaries in, final hadrons out (timed steps only)
         clocks = ClockSampler(local)    # sampled from the warm-up steps (same load) to the end
         clocks.start()
         for _ in range(args.warmup):
             step()
         e.timing(enable=True, reset=True)
+        decay_counts[0] = decay_counts[1] = 0
         barrier()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record(stream)
@@ -338,7 +378,8 @@ def run_engine(args):
         "unit": "hadrons/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max/args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.cells, E), "cells": ncell, "species": ns,
+        "config": {"workload": workload_name(args.cells, E, args.workload), "workload_key": args.workload,
+                   "cells": ncell, "species": ns,
                    "events_per_step_per_gpu": E, "sharding": "events (weak), surface replicated",
                    "l2": "inputs_larger_than_L2", "seed": args.seed, "host_placement": numa},
         "yields_per_sec": ycs/yields_s if yields_s > 0 else None,
@@ -353,6 +394,20 @@ def run_engine(args):
         "clocks": clk,
         "spectra": spectra,
     }
+    if decays_on and fam_ms["decay"] > 0 and decay_counts[0] > 0:
+        dec_s = fam_ms["decay"]*1e-3
+        per_primary = BYTES_PER_DECAY_IN + 40.0*decay_counts[1]/decay_counts[0]
+        line["roofline_decay"] = {
+            "kernel": "decay_kernel (count pass + write pass over every primary's decay tree) + offsets scan",
+            "bound": "hbm", "achieved": per_primary*decay_counts[0]/dec_s/1e9, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": per_primary*decay_counts[0]/dec_s/1e9/peaks["hbm_gbs"],
+            "algorithmic_bytes_per_primary": per_primary,
+            "final_hadrons_per_primary": decay_counts[1]/decay_counts[0],
+            "avg_ms_per_step": fam_ms["decay"]/args.steps,
+            "primaries_per_sec": decay_counts[0]/dec_s,
+            "fp64": {"achieved_tflops": FLOP_PER_DECAY*decay_counts[1]/dec_s/1e12, "peak_tflops": fp64_peak,
+                     "frac": FLOP_PER_DECAY*decay_counts[1]/dec_s/1e12/fp64_peak},
+            "note": "latency bound: one thread walks one primary's decay tree twice (count, write)"}
     if rank == 0:
         cb = None
         if world == 1 and not args.no_cpu_baseline:
@@ -381,14 +436,15 @@ def cpu_reference(args, quick):
     exe = ref_binary()
     if exe is None:
         return {"unavailable": "oracle/_ref/iSS.e not built (needs /root/reference at build time)"}
-    cores = os.cpu_count() or 1
-    ncell = max(1000, args.cells//50)
-    events = args.events_per_step
+    full = bool(getattr(args, "full_size", False))
+    cores = 1 if full else (os.cpu_count() or 1)
+    ncell = args.cells if full else max(1000, args.cells//50)
+    events = min(100, args.events_per_step) if full else args.events_per_step
     root = tempfile.mkdtemp(prefix="iss_ref_")
     try:
-        make_case(os.path.join(root, "case"), ncell)
+        make_case(os.path.join(root, "case"), ncell, args.workload)
         os.symlink(os.path.join(REPO, "iSS_tables"), os.path.join(root, "iSS_tables"))
-        over = dict(OVERRIDES, number_of_repeated_sampling=events, use_binary_format=0)
+        over = dict(overrides_of(args.workload), number_of_repeated_sampling=events, use_binary_format=0)
         procs = []
         t0 = time.perf_counter()
         for c in range(cores):
@@ -421,13 +477,22 @@ def cpu_reference(args, quick):
             rate += n/sec
             hadrons += n
             secs.append(sec)
-        return {"value": rate, "unit": "hadrons/s", "cores": cores, "kind": "reference",
-                "sample": "%d-cell surface (1/%d of the workload, same generator and seed), %d events, "
-                          "%d independent single-thread processes of oracle/_ref/iSS.e; hadrons = "
-                          "events x sum of species dN; time = reference timer line (yields + sampling)"
-                          % (ncell, args.cells//ncell, events, cores),
-                "per_core": rate/cores, "cpu_seconds_per_process": float(np.mean(secs)),
-                "wall_seconds": wall}
+        out = {"value": rate, "unit": "hadrons/s", "cores": cores, "kind": "reference",
+               "sample": "%d-cell surface (1/%d of the workload, same generator and seed), %d events, "
+                         "%d independent single-thread processes of oracle/_ref/iSS.e; hadrons = "
+                         "events x sum of species dN; time = reference timer line (yields + sampling)"
+                         % (ncell, args.cells//ncell, events, cores),
+               "per_core": rate/cores, "per_box": rate, "cpu_seconds_per_process": float(np.mean(secs)),
+               "wall_seconds": wall}
+        # one recorded run of the reference on the FULL-SIZE surface (bench.py --impl reference
+        # --full-size, minutes on one core) calibrates the 1/50 sample
+        chk = os.path.join(REPO, "profiles", "r2_reference_fullsize_%s.json" % args.workload)
+        if not full and os.path.exists(chk):
+            try:
+                out["full_size_check"] = json.load(open(chk))
+            except Exception:
+                pass
+        return out
     finally:
         shutil.rmtree(root, ignore_errors=True)
 
@@ -452,7 +517,8 @@ def run_reference(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.cells, args.events_per_step)},
+            "config": {"workload": workload_name(args.cells, args.events_per_step, args.workload),
+                       "workload_key": args.workload},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "hadrons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -464,16 +530,26 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--cells", type=int, default=1000000)
-    ap.add_argument("--events-per-step", type=int, default=1000)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--cells", type=int, default=None, help="default: the workload's size")
+    ap.add_argument("--events-per-step", type=int, default=None, help="default: the workload's")
+    ap.add_argument("--full-size", action="store_true",
+                    help="--impl reference only: ONE single-thread reference run on the full-size "
+                         "surface (calibrates the 1/50 sample; minutes)")
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spectra", action="store_true")
     args = ap.parse_args()
+    if args.cells is None:
+        args.cells = WORKLOADS[args.workload]["cells"]
+    if args.events_per_step is None:
+        args.events_per_step = WORKLOADS[args.workload]["events"]
     if args.impl == "reference":
         # a reference "step" is a full multi-process run of the binary: keep the count small
         args.steps = max(1, min(args.steps, 2))
         args.warmup = min(args.warmup, 0)
+        if args.full_size:
+            args.steps = 1
         run_reference(args)
     else:
         args.warmup = max(3, args.warmup)

@@ -85,14 +85,13 @@ std::vector<double> read_numbers(const std::string &file, int skip_lines) {
 struct HandlePool {
     std::mutex mu;
     std::map<int, std::vector<iss_handle *>> idle;     // by device
-    ~HandlePool() {
-        for (auto &kv : idle)
-            for (iss_handle *h : kv.second) iss_cuda_destroy(h);
-    }
 };
 HandlePool &handle_pool() {
-    static HandlePool p;
-    return p;
+    // never destroyed: CUDA runtime calls during static destruction (after main() has returned)
+    // are undefined, so the pooled handles are left to the driver at process exit, like the
+    // pinned blocks below
+    static HandlePool *p = new HandlePool();
+    return *p;
 }
 
 using iss_pool::PinnedBlock;
@@ -656,15 +655,38 @@ void GpuFSSW::compute_yields() {
 }
 
 // FSSW::compute_number_of_sampling_needed (FSSW.cpp:851-869): uses pdg-table entry 1 as "pi+"
-int GpuFSSW::compute_number_of_sampling_needed_(int number_of_particles_needed) {
-    double dNdy_thermal_pion = 0.;
+int GpuFSSW::compute_number_of_sampling_needed_(long number_of_particles_needed) {
+    double dNdy_thermal_pion = -1.;
     for (size_t n = 0; n < species_table_idx_.size(); n++)
         if (species_table_idx_[n] == 1) dNdy_thermal_pion = dN_species_[n];
-    int nev = static_cast<int>(number_of_particles_needed/(6.*dNdy_thermal_pion));
+    if (dNdy_thermal_pion < 0. && particles_.size() > 1 && !legacy_) {
+        // the reference evaluates pdg-table entry 1 whatever the chosen list holds
+        // (FSSW.cpp:851-869): one extra yield pass over that species alone, then the chosen
+        // list is put back
+        const particle_info &p = particles_[1];
+        iss_species one;
+        memset(&one, 0, sizeof(one));
+        one.pid = p.monval; one.gspin = p.gspin; one.baryon = p.baryon; one.strange = p.strange;
+        one.charge = p.charge; one.sign = p.sign; one.decay_idx = 1; one.mass = p.mass;
+        check_(iss_cuda_upload_species(h_, &one, 1), "iss_cuda_upload_species");
+        double dN1 = 0.;
+        check_(iss_cuda_compute_yields(h_, &dN1, nullptr), "iss_cuda_compute_yields");
+        dNdy_thermal_pion = dN1;
+        check_(iss_cuda_upload_species(h_, species_.data(), static_cast<int>(species_.size())),
+               "iss_cuda_upload_species");
+        compute_yields();
+    }
+    if (!(dNdy_thermal_pion > 0.)) {
+        iss_host::error("sample_upto_desired_particle_number: the thermal yield of pdg-table entry 1 "
+                        "is not positive, can not derive the number of events");
+        exit(-1);
+    }
+    // int(...) as in the reference, evaluated in 64 bits so that large requests do not overflow
+    long nev = static_cast<long>(std::min(1.0e15, number_of_particles_needed/(6.*dNdy_thermal_pion)));
     if (hydro_mode_ == 2) nev *= 10;
     // the legacy class caps at 10000 events (emissionfunction.cpp:3268)
-    const int max_ev = legacy_ ? 10000 : static_cast<int>(paraRdr_->getVal("maximum_sampling_events"));
-    return std::max(1, std::min(max_ev, nev));
+    const long max_ev = legacy_ ? 10000 : static_cast<long>(paraRdr_->getVal("maximum_sampling_events"));
+    return static_cast<int>(std::max<long>(1, std::min(max_ev, nev)));
 }
 
 void GpuFSSW::sample_events() {
@@ -673,7 +695,7 @@ void GpuFSSW::sample_events() {
     if (dN_species_.empty()) compute_yields();
     if (static_cast<int>(paraRdr_->getVal("sample_upto_desired_particle_number")) == 1) {
         number_of_repeated_sampling_ = compute_number_of_sampling_needed_(
-            static_cast<int>(paraRdr_->getVal("number_of_particles_needed")));
+            static_cast<long>(paraRdr_->getVal("number_of_particles_needed")));
     }
     info("Sampling using dN/dy with sample_using_dN_dxtdy_4all_particles function.");
     info("number of repeated sampling = " + std::to_string(number_of_repeated_sampling_));

@@ -114,7 +114,7 @@ class GpuFSSW {
     void upload_decay_table_();
     void read_spectators_(const std::string &file);
     void reserve_hadrons_(int64_t need);
-    int compute_number_of_sampling_needed_(int number_of_particles_needed);
+    int compute_number_of_sampling_needed_(long number_of_particles_needed);
 };
 
 #endif  // ISS_B200_GPU_FSSW_H_

@@ -429,7 +429,6 @@ void read_FOdata::read_text_surface_boost_invariant_(std::vector<FO_surf> &surf,
     size_t len = buf.size() - 1;
     while (len > 0 && buf[len - 1] != '\n') len--;
     const int bulk = turn_on_bulk_, rhob = turn_on_rhob_, diff = turn_on_diff_;
-    const char *const file_end = buf.data() + len;
     auto parse_piece = [&](const char *p, const char *end, TextPiece &out) {
         while (p < end) {
             const char *eol = static_cast<const char *>(memchr(p, '\n', end - p));
