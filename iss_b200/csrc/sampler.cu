@@ -291,9 +291,11 @@ struct SamplerArgs {
     double y_LB, y_RB;
     uint64_t seed;
     const CellRec *cellrec;         // [ncell] per-cell record of the proposal kernel
-    Task32 *tasks_unsorted;         // [nwork] tasks in work order (setup_kernel -> bucket_kernel)
+    Task32 *tasks_unsorted;         // [nwork] tasks in work order (setup_kernel -> partition_kernel)
     uint32_t *slot_unsorted;        // [nwork] surface-chunk mode only: output slots in work order
-    unsigned long long *cell_cnt;   // [ncell + 1] cell histogram -> exclusive offsets -> bucket cursors
+    unsigned long long *bucket_cnt; // [nbucket + 1] histogram of the cell blocks -> exclusive offsets
+                                    // -> write cursors of the partition
+    int bucket_shift, nbucket;      // bucket = cell >> bucket_shift
     Task32 *tasks;                  // [nstage*RING_TASKS] cell-sorted task list
     uint32_t *task_slot;            // surface-chunk mode only: output slot of every sorted task
     uint32_t *wire;                 // optional [n_out][5]: 20-byte wire records (iss_wire_hadron)
@@ -652,35 +654,36 @@ __global__ void build_cellrec_kernel(const float *__restrict__ cells, const doub
 
 // ---- cell-sorted task list -----------------------------------------------------------------------
 // The hadron list is a pure function of (seed, event, species, draw), so the ORDER in which the
-// hadrons of a batch are sampled is free.  The tasks are bucketed by cell (counting sort on the
-// cell id: histogram in setup_kernel, exclusive scan, scatter in bucket_kernel): consecutive tasks
-// then share their cell record, which the proposal kernel finds in L1/L2 instead of gathering
-// 160 random bytes per hadron from DRAM.  The order inside a cell depends on atomic timing; the
-// results do not (the output slot travels with the task).
+// hadrons of a batch are sampled is free.  The tasks are partitioned by cell block (a few hundred
+// blocks of 2^k consecutive cells: histogram in setup_kernel, exclusive scan, scatter in
+// partition_kernel): the tasks in flight at any time then share a few hundred KB of cell
+// records, which the proposal kernel finds in L2 instead of gathering 160 random bytes per hadron
+// from DRAM.  The order inside a block depends on atomic timing; the results do not (the output
+// slot follows from the task).
 
 // K5a: one thread per hadron of the batch, in work order: identity (species, event, draw) from the
 // species-major work offsets, cell choice (first block of the hadron's stream), the two series
 // values of the |p| sampler (MomentumSamplerBase::update_cache), histogram of the cells.  The FP64
 // work of the series runs in the shadow of the dependent loads of the cell search.  The task is
-// written at its work index; bucket_kernel moves it to its place in the cell-sorted list.
+// written at its work index; partition_kernel moves it into the region of its cell block.
 __global__ void __launch_bounds__(SETUP_THREADS)
 setup_kernel(const SamplerArgs A) {
     extern __shared__ unsigned char smem_raw[];
     DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
     int64_t *sp_off = reinterpret_cast<int64_t *>(sp + A.ns);     // off_work[s*nev], s = 0..ns
+    unsigned int *hist = reinterpret_cast<unsigned int *>(sp_off + A.ns + 1);      // [nbucket]
     for (int i = threadIdx.x; i < A.ns; i += blockDim.x) sp[i] = A.species[i];
     for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
         sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
+    for (int b = threadIdx.x; b < A.nbucket; b += blockDim.x) hist[b] = 0u;
     __syncthreads();
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
     unsigned long long my_range = 0;
     for (int64_t base = static_cast<int64_t>(blockIdx.x)*blockDim.x; base < A.nwork;
          base += static_cast<int64_t>(gridDim.x)*blockDim.x) {
         const int64_t j = base + threadIdx.x;
         const bool valid = j < A.nwork;
-        int cell = -1 - lane;           // distinct dummies for the lanes past the end
+        int cell = 0;
         if (valid) {
             // surface-chunk mode: the rank's j-th hadron is work item wlist[j] of the whole batch
             const int64_t w = A.chunk ? __ldg(&A.wlist[j]) : j;
@@ -717,48 +720,87 @@ setup_kernel(const SamplerArgs A) {
                 A.slot_unsorted[j] = static_cast<uint32_t>(__ldg(&A.off_out[ev*A.ns + s]) + k_out*mult);
             }
         }
-        // one atomic per distinct cell of the warp (one-cell surfaces put every hadron in one bin)
-        const unsigned peers = __match_any_sync(full, cell);
-        if (valid && lane == __ffs(peers) - 1)
-            atomicAdd(&A.cell_cnt[cell], static_cast<unsigned long long>(__popc(peers)));
+        if (valid) atomicAdd(&hist[cell >> A.bucket_shift], 1u);
     }
+    __syncthreads();
+    for (int b = threadIdx.x; b < A.nbucket; b += blockDim.x)
+        if (hist[b]) atomicAdd(&A.bucket_cnt[b], static_cast<unsigned long long>(hist[b]));
     if (my_range) atomicAdd(&A.counters[3], my_range);
 }
 
-// K5b: after the exclusive scan of the histogram: every task to its place in the cell-sorted list
-// (a permutation: 32 bytes in, one 32-byte sector out).
-__global__ void __launch_bounds__(SETUP_THREADS)
-bucket_kernel(const SamplerArgs A) {
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    for (int64_t base = static_cast<int64_t>(blockIdx.x)*blockDim.x; base < A.nwork;
-         base += static_cast<int64_t>(gridDim.x)*blockDim.x) {
-        const int64_t j = base + threadIdx.x;
-        const bool valid = j < A.nwork;
-        int cell = -1 - lane;
-        uint4 t0 = make_uint4(0u, 0u, 0u, 0u), t1 = t0;
-        if (valid) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(A.tasks_unsorted + j);
-            t0 = __ldg(src);
-            t1 = __ldg(src + 1);
-            cell = static_cast<int>(t1.x);
+// K5b: after the exclusive scan of the histogram: every task to the region of its cell block.
+// A CTA takes a tile of PART_TILE consecutive tasks, counts them per block in shared memory,
+// reserves the tile's share of every block with ONE global atomic per (tile, block) and writes the
+// tasks of a block side by side, so that the 32-byte records leave the L2 as (mostly) full lines.
+// Inside a block the order depends on atomic timing; the results do not.
+constexpr int PART_THREADS = 256;
+constexpr int PART_ITEMS = 8;
+constexpr int PART_TILE = PART_THREADS*PART_ITEMS;
+constexpr int MAX_BUCKETS = 1024;
+
+__global__ void __launch_bounds__(PART_THREADS)
+partition_kernel(const SamplerArgs A) {
+    __shared__ unsigned int cnt[MAX_BUCKETS];
+    __shared__ unsigned long long gbase[MAX_BUCKETS];
+    const int64_t ntile = (A.nwork + PART_TILE - 1)/PART_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        for (int b = threadIdx.x; b < A.nbucket; b += PART_THREADS) cnt[b] = 0u;
+        __syncthreads();
+        uint4 t0[PART_ITEMS], t1[PART_ITEMS];
+        unsigned int rank[PART_ITEMS];
+        const int64_t base = tile*PART_TILE;
+#pragma unroll
+        for (int i = 0; i < PART_ITEMS; i++) {
+            const int64_t j = base + i*PART_THREADS + threadIdx.x;
+            if (j < A.nwork) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(A.tasks_unsorted + j);
+                t0[i] = __ldg(src);
+                t1[i] = __ldg(src + 1);
+            }
         }
-        // position in the cell's bucket: one atomic per distinct cell of the warp
-        const unsigned peers = __match_any_sync(full, cell);
-        const int leader = __ffs(peers) - 1;
-        unsigned long long bucket = 0;
-        if (valid && lane == leader)
-            bucket = atomicAdd(&A.cell_cnt[cell], static_cast<unsigned long long>(__popc(peers)));
-        bucket = __shfl_sync(full, bucket, leader);
-        if (valid) {
-            const int64_t pos = static_cast<int64_t>(bucket) + __popc(peers & lt_mask);
-            uint4 *dst = reinterpret_cast<uint4 *>(A.tasks + pos);
-            dst[0] = t0;
-            dst[1] = t1;
-            if (A.chunk) A.task_slot[pos] = __ldg(&A.slot_unsorted[j]);
+#pragma unroll
+        for (int i = 0; i < PART_ITEMS; i++) {
+            const int64_t j = base + i*PART_THREADS + threadIdx.x;
+            if (j < A.nwork) rank[i] = atomicAdd(&cnt[t1[i].x >> A.bucket_shift], 1u);
         }
+        __syncthreads();
+        for (int b = threadIdx.x; b < A.nbucket; b += PART_THREADS)
+            if (cnt[b]) gbase[b] = atomicAdd(&A.bucket_cnt[b], static_cast<unsigned long long>(cnt[b]));
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PART_ITEMS; i++) {
+            const int64_t j = base + i*PART_THREADS + threadIdx.x;
+            if (j < A.nwork) {
+                const int64_t pos = static_cast<int64_t>(gbase[t1[i].x >> A.bucket_shift]) + rank[i];
+                uint4 *dst = reinterpret_cast<uint4 *>(A.tasks + pos);
+                dst[0] = t0[i];
+                dst[1] = t1[i];
+                if (A.chunk) A.task_slot[pos] = __ldg(&A.slot_unsorted[j]);
+            }
+        }
+        __syncthreads();
     }
+}
+
+// exclusive scan of the block histogram (at most MAX_BUCKETS entries): one CTA
+__global__ void __launch_bounds__(MAX_BUCKETS)
+bucket_scan_kernel(unsigned long long *__restrict__ cnt, int n) {
+    __shared__ unsigned long long warp_tot[32];
+    const int i = threadIdx.x;
+    const int lane = i & 31, warp = i >> 5;
+    const unsigned long long v = (i < n) ? cnt[i] : 0ull;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += warp_tot[w];
+    if (i < n) cnt[i] = wbase + incl - v;
+    if (i == n) cnt[n] = wbase + incl - v;
 }
 
 // ---- bulk-async plumbing of the proposal kernel (mbarrier + cp.async.bulk, PTX ISA 8.x) ----------
@@ -1561,7 +1603,9 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.task_slot = nullptr;
     A.tasks_unsorted = nullptr;
     A.slot_unsorted = nullptr;
-    A.cell_cnt = nullptr;
+    A.bucket_cnt = nullptr;
+    A.bucket_shift = 0;
+    A.nbucket = 1;
     A.cellrec = nullptr;
     A.wire = nullptr;
     A.giveup_info = nullptr;
@@ -1680,10 +1724,15 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
             ISS_CUDA_TRY(h, cudaMalloc(&h->d_tasks, h->tasks_bytes));
             ISS_CUDA_TRY(h, cudaMalloc(&h->d_tasks_unsorted, h->tasks_bytes));
         }
-        ISS_ENSURE(h, h->d_cellcnt, h->cellcnt_bytes, sizeof(unsigned long long)*(h->ncell + 2));
+        ISS_ENSURE(h, h->d_cellcnt, h->cellcnt_bytes, sizeof(unsigned long long)*(MAX_BUCKETS + 2));
         A.tasks = static_cast<Task32 *>(h->d_tasks);
         A.tasks_unsorted = static_cast<Task32 *>(h->d_tasks_unsorted);
-        A.cell_cnt = h->d_cellcnt;
+        A.bucket_cnt = h->d_cellcnt;
+        // cell blocks of the partition: at most 512 (tasks of a tile land in runs of ~8 per block),
+        // at least 256 cells each
+        A.bucket_shift = 8;
+        while (((h->ncell - 1) >> A.bucket_shift) + 1 > 512) A.bucket_shift++;
+        A.nbucket = static_cast<int>(((h->ncell - 1) >> A.bucket_shift) + 1);
         if (h->chunk) {     // output slots travel through the sort (they do not follow from the draw index)
             const size_t slot_need = sizeof(uint32_t)*static_cast<size_t>(nstage*RING_TASKS);
             ISS_ENSURE(h, h->d_task_slot, h->task_slot_bytes, slot_need);
@@ -1717,14 +1766,15 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
             work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
                 h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
         }
-        // counting sort of the batch's hadrons by cell: histogram, exclusive scan, scatter
-        ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_cellcnt, 0, sizeof(unsigned long long)*(h->ncell + 1), h->stream));
-        const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1);
+        // partition of the batch's hadrons by cell block: histogram, exclusive scan, scatter
+        ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_cellcnt, 0, sizeof(unsigned long long)*(A.nbucket + 1), h->stream));
+        const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1)
+                                  + sizeof(unsigned int)*A.nbucket;
         setup_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
-        rc = device_exclusive_scan_i64(h, reinterpret_cast<const int64_t *>(h->d_cellcnt),
-                                       reinterpret_cast<int64_t *>(h->d_cellcnt), h->ncell, nullptr);
-        if (rc) return rc;
-        bucket_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, 0, h->stream>>>(A); ISS_LAUNCHED(h);
+        bucket_scan_kernel<<<1, MAX_BUCKETS, 0, h->stream>>>(h->d_cellcnt, A.nbucket); ISS_LAUNCHED(h);
+        int64_t pgrid = (A.nwork + PART_TILE - 1)/PART_TILE;
+        if (pgrid > static_cast<int64_t>(nsm)*8) pgrid = static_cast<int64_t>(nsm)*8;
+        partition_kernel<<<static_cast<unsigned>(pgrid), PART_THREADS, 0, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
 

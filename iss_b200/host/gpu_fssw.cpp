@@ -810,6 +810,7 @@ void GpuFSSW::sample_events() {
     }
     qa_.assign(iss_cuda_qa_size(), 0.);
     check_(iss_cuda_qa_fetch(h_, qa_.data()), "iss_cuda_qa_fetch");
+    if (nsp > 0) add_spectators_to_qa_(qa_pids, 2);
     std::cout << std::endl
               << "sample_using_dN_dxtdy_4all_particles finished in " << seconds_since(t0)
               << " seconds." << std::endl;
@@ -898,20 +899,83 @@ std::vector<iSS_Hadron> *GpuFSSW::get_hadron_list_iev(const int iev) {
     return event_cache_[iev].get();
 }
 
-// FSSW::computeAvgTotalEnergyMomentum (FSSW.cpp:2028-2059).  The per-event sums of P^mu and
-// their squares were accumulated on the device with the other QA quantities (QA block [1..8]);
-// spectators, which are appended on the host, are added here.
-void GpuFSSW::computeAvgTotalEnergyMomentum() {
-    double sp[4] = {0, 0, 0, 0};
+// The QA block is accumulated on the device from the sampled hadrons; the reference runs its checks
+// over Hadron_list AFTER addSpectatorsToHadronList (FSSW.cpp:349-352, iSS.cpp:59-83), so the same
+// spectators, appended to every event, are folded in here: with a per-event constant c added to a
+// per-event quantity a,  sum (a + c) = S1 + n c  and  sum (a + c)^2 = S2 + 2 c S1 + n c^2.
+// Binning as in qa_kernel (iss_b200/csrc/qa.cu).  n = events behind the block (all ranks' when it
+// was reduced; every rank appends the same spectators).
+void GpuFSSW::add_spectators_to_qa_(const int32_t *pids, int npid) {
+    const double n = qa_[0];
+    double sp[4] = {0, 0, 0, 0}, T[16] = {0}, net[3] = {0, 0, 0};
     for (const iSS_Hadron &hd : spectators_) {
-        sp[0] += hd.E; sp[1] += hd.px; sp[2] += hd.py; sp[3] += hd.pz;
+        const double p[4] = {hd.E, hd.px, hd.py, hd.pz};
+        for (int a = 0; a < 4; a++) {
+            sp[a] += p[a];
+            for (int c = 0; c < 4; c++) T[4*a + c] += p[a]*p[c]/p[0];
+        }
+        net[0] += 1.;                               // nucleons
+        net[2] += (hd.pid == 2212) ? 1. : 0.;
     }
+    for (int i = 0; i < 4; i++) {
+        const double S1 = qa_[1 + i];
+        qa_[1 + i] = S1 + n*sp[i];
+        qa_[5 + i] = qa_[5 + i] + 2.*sp[i]*S1 + n*sp[i]*sp[i];
+    }
+    for (int i = 0; i < 16; i++) qa_[9 + i] += n*T[i];
+    qa_[25] += n*static_cast<double>(spectators_.size());
+    for (int i = 0; i < 3; i++) qa_[26 + i] += n*net[i];
+    for (int k = 0; k < npid; k++) {
+        double *blk = qa_.data() + ISS_QA_HEAD + static_cast<size_t>(k)*ISS_QA_PER;
+        double c_pt[ISS_QA_NPT] = {0}, s_pt[ISS_QA_NPT] = {0};
+        double c_tot = 0.;
+        for (const iSS_Hadron &hd : spectators_) {
+            if (hd.pid != pids[k]) continue;
+            c_tot += 1.;
+            const double pT = std::sqrt(static_cast<double>(hd.px)*hd.px + static_cast<double>(hd.py)*hd.py);
+            const int ib = static_cast<int>(pT/(5.0/(ISS_QA_NPT - 1)));
+            if (ib >= 0 && ib < ISS_QA_NPT) {
+                c_pt[ib] += 1.;
+                s_pt[ib] += pT;
+            }
+            const double y = std::asinh(hd.pz/std::sqrt(static_cast<double>(hd.mass)*hd.mass + pT*pT));
+            const int iy = static_cast<int>(std::floor((y + 5.0)/(10.0/ISS_QA_NY)));
+            if (iy >= 0 && iy < ISS_QA_NY) blk[3*ISS_QA_NPT + iy] += n;
+            const double phi = std::atan2(static_cast<double>(hd.py), static_cast<double>(hd.px));
+            int iphi = static_cast<int>(std::floor((phi + M_PI)/(2.*M_PI/ISS_QA_NPHI)));
+            iphi = std::min(ISS_QA_NPHI - 1, std::max(0, iphi));
+            blk[3*ISS_QA_NPT + ISS_QA_NY + iphi] += n;
+            const int iv = static_cast<int>(pT/(3.0/ISS_QA_NV2));
+            if (iv < ISS_QA_NV2) {
+                const double c2 = (pT > 0.) ? (static_cast<double>(hd.px)*hd.px
+                                               - static_cast<double>(hd.py)*hd.py)/(pT*pT) : 0.;
+                blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + iv] += n*c2;
+                blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + ISS_QA_NV2 + iv] += n;
+            }
+        }
+        for (int ib = 0; ib < ISS_QA_NPT; ib++) {
+            if (c_pt[ib] == 0.) continue;
+            const double cnt = blk[ib];
+            blk[2*ISS_QA_NPT + ib] += 2.*c_pt[ib]*cnt + n*c_pt[ib]*c_pt[ib];
+            blk[ib] = cnt + n*c_pt[ib];
+            blk[ISS_QA_NPT + ib] += n*s_pt[ib];
+        }
+        if (c_tot > 0.) {
+            const double tot = blk[ISS_QA_PER - 2];
+            blk[ISS_QA_PER - 1] += 2.*c_tot*tot + n*c_tot*c_tot;
+            blk[ISS_QA_PER - 2] = tot + n*c_tot;
+        }
+    }
+}
+
+// FSSW::computeAvgTotalEnergyMomentum (FSSW.cpp:2028-2059) from the QA block (spectators included)
+void GpuFSSW::computeAvgTotalEnergyMomentum() {
     info("Averaged total energy and momentum:");
     for (int i = 0; i < 4; i++) {
-        // sum (P + s) = S1 + n s ;  sum (P + s)^2 = S2 + 2 s S1 + n s^2
-        const double S1 = qa_[1 + i], S2 = qa_[5 + i], n = static_cast<double>(nev_);
-        const double avg = (S1 + n*sp[i])/n;
-        const double sq = (S2 + 2.*sp[i]*S1 + n*sp[i]*sp[i])/n;
+        const double S1 = qa_[1 + i], S2 = qa_[5 + i];
+        const double n = (qa_ranks_ > 1) ? qa_[0] : static_cast<double>(nev_);
+        const double avg = S1/n;
+        const double sq = S2/n;
         const double err = std::sqrt(std::max(0., sq - avg*avg)/n);
         std::ostringstream os;
         os << "<P[" << i << "]> = " << avg << " +/- " << err << " GeV.";

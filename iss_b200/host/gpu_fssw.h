@@ -96,6 +96,7 @@ class GpuFSSW {
     std::vector<double> dN_species_;
     std::vector<double> qa_;
     int qa_ranks_ = 1;
+    void add_spectators_to_qa_(const int32_t *pids, int npid);
     void join_ranks_();     // NCCL communicator of the job on the pooled handle (once per process)
 
     iSS_Hadron *hadrons_ = nullptr;         // pinned, all events

@@ -482,12 +482,16 @@ void read_FOdata::regulate_surface_cells(std::vector<FO_surf> &surf, bool announ
     if (regulateTemperature && announce)
         std::cout << "Regulate local temperature with pure HRG EoS." << std::endl;
     const int64_t n = static_cast<int64_t>(surf.size());
-    iss_host::parallel_ranges(n, iss_host::ingest_threads(n), [&](int64_t c0, int64_t c1, int) {
+    // "ed is out of range" warnings are collected per thread and printed in cell order afterwards
+    // (the reference is serial: its warnings come in file order)
+    const int nthread = iss_host::ingest_threads(n);
+    std::vector<std::vector<std::string>> warnings(std::max(1, nthread));
+    iss_host::parallel_ranges(n, nthread, [&](int64_t c0, int64_t c1, int tix) {
         std::vector<double> eos;
         for (int64_t c = c0; c < c1; c++) {
             FO_surf &s = surf[c];
             if (regulateTemperature) {
-                if (getValuesFromHRGEOS(s.Edec, s.Bn, eos) == 0) {
+                if (getValuesFromHRGEOS(s.Edec, s.Bn, eos, &warnings[tix]) == 0) {
                     s.Tdec = static_cast<float>(eos[1]);
                     s.muB = static_cast<float>(eos[2]);
                     s.muS = static_cast<float>(eos[3]);
@@ -512,6 +516,8 @@ void read_FOdata::regulate_surface_cells(std::vector<FO_surf> &surf, bool announ
             s.pi23 = static_cast<float>(R[2][3]); s.pi33 = static_cast<float>(R[3][3]);
         }
     });
+    for (const auto &per_thread : warnings)
+        for (const std::string &w : per_thread) iss_host::warning(w);
 }
 
 // transverse, traceless projection (readindata.cpp:1216-1246)
@@ -535,7 +541,8 @@ void read_FOdata::regulate_Wmunu(double u[4], double W[4][4], double R[4][4]) {
 }
 
 // bilinear (e, n_B) interpolation of the HRG table (readindata.cpp:1249-1309)
-int read_FOdata::getValuesFromHRGEOS(double ed, double nB, std::vector<double> &eosVar) {
+int read_FOdata::getValuesFromHRGEOS(double ed, double nB, std::vector<double> &eosVar,
+                                     std::vector<std::string> *deferred_warnings) {
     eosVar.assign(5, 0.);       // {P, T, muB, muS, muQ}
     const int nBlen = (iEOS_MUSIC_ == 12 || iEOS_MUSIC_ == 14) ? 200 : 1;
     auto H = [&](long row, int col) { return hrg_[row*7 + col]; };
@@ -545,7 +552,8 @@ int read_FOdata::getValuesFromHRGEOS(double ed, double nB, std::vector<double> &
     if (e_idx < 0 || e_idx >= static_cast<int>(hrg_rows_/nBlen) - 2) {
         std::ostringstream os;
         os << "ed is out of range: ed = " << ed << " GeV/fm^3. Can not regulate this fluid cell!";
-        iss_host::warning(os.str());
+        if (deferred_warnings) deferred_warnings->push_back(os.str());
+        else iss_host::warning(os.str());
         return -1;
     }
     const long r1 = static_cast<long>(e_idx)*nBlen;

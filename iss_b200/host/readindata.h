@@ -54,7 +54,8 @@ class read_FOdata {
     int read_resonances_list(std::vector<particle_info> &particles);
     void regulate_surface_cells(std::vector<FO_surf> &surf, bool announce = true);
     void regulate_Wmunu(double u[4], double Wmunu[4][4], double Wmunu_regulated[4][4]);
-    int getValuesFromHRGEOS(double ed, double nB, std::vector<double> &eos);
+    int getValuesFromHRGEOS(double ed, double nB, std::vector<double> &eos,
+                            std::vector<std::string> *deferred_warnings = nullptr);
 
  private:
     ParameterReader *paraRdr_;

@@ -85,6 +85,30 @@ def test_facade_decays_and_spectators(built, tmp_path):
         s.set_random_seed(5)
         s.generate_samples()
         h, off = s.hadrons()
+        # the QA block behind iSS::perform_checks covers the lists the host sees, spectators
+        # included (the reference checks Hadron_list after addSpectatorsToHadronList)
+        qa = s.qa_block()
+        E, px, py, pz = (h[k].astype(np.float64) for k in ("E", "px", "py", "pz"))
+        evi = np.repeat(np.arange(nev), np.diff(off))
+        assert qa[0] == nev and qa[25] == len(h)
+        for i, a in enumerate((E, px, py, pz)):
+            P = np.bincount(evi, weights=a, minlength=nev)
+            assert np.isclose(qa[1 + i], P.sum(), rtol=1e-9)
+            assert np.isclose(qa[5 + i], (P**2).sum(), rtol=1e-9)
+        p4 = np.stack([E, px, py, pz])
+        assert np.allclose(qa[9:25].reshape(4, 4), np.einsum("in,jn->ij", p4, p4/E), rtol=1e-9, atol=1e-9)
+        pT = np.hypot(px, py)
+        m = h["pid"] == 2212                       # second tracked species of the facade
+        blk = qa[capi.QA_HEAD + capi.QA_PER: capi.QA_HEAD + 2*capi.QA_PER]
+        ib = (pT[m]/(5.0/99)).astype(int)
+        ok = ib < 100
+        assert np.array_equal(blk[:100], np.bincount(ib[ok], minlength=100))
+        per_ev = np.zeros((nev, 100))
+        np.add.at(per_ev, (evi[m][ok], ib[ok]), 1)
+        assert np.array_equal(blk[200:300], (per_ev**2).sum(axis=0))
+        nper = np.bincount(evi[m], minlength=nev)
+        assert blk[-2] == nper.sum() and blk[-1] == (nper**2).sum()
+        assert (h["pid"][off[1] - 32:off[1]] == 2212).sum() > 0        # the spectators do hold protons
         e = s.engine()
         e.compute_yields()
         e.sample(5, 0, nev)
