@@ -293,9 +293,10 @@ struct SamplerArgs {
     const CellRec *cellrec;         // [ncell] per-cell record of the proposal kernel
     Task32 *tasks_unsorted;         // [nwork] tasks in work order (setup_kernel -> partition_kernel)
     uint32_t *slot_unsorted;        // [nwork] surface-chunk mode only: output slots in work order
-    unsigned long long *bucket_cnt; // [nbucket + 1] histogram of the cell blocks -> exclusive offsets
-                                    // -> write cursors of the partition
-    int bucket_shift, nbucket;      // bucket = cell >> bucket_shift
+    unsigned long long *bucket_cnt; // [nbucket][nseg] (+1) tasks per (cell block, segment of PART_TILE
+                                    // work items) -> exclusive scan: write offset of every run
+    int bucket_shift, nbucket;      // block = cell >> bucket_shift
+    int64_t nseg;                   // segments of the batch
     Task32 *tasks;                  // [nstage*RING_TASKS] cell-sorted task list
     uint32_t *task_slot;            // surface-chunk mode only: output slot of every sorted task
     uint32_t *wire;                 // optional [n_out][5]: 20-byte wire records (iss_wire_hadron)
@@ -320,6 +321,10 @@ struct SamplerArgs {
 };
 
 constexpr int SETUP_THREADS = 256;
+constexpr int PART_THREADS = 256;       // partition_kernel: tasks of a segment per thread
+constexpr int PART_ITEMS = 8;
+constexpr int PART_TILE = PART_THREADS*PART_ITEMS;      // work items per segment
+constexpr int MAX_BUCKETS = 64;         // cell blocks of the partition
 constexpr int SAMPLER_THREADS = 768;     // one CTA of 24 warps per SM (80 registers per thread)
 constexpr int MAX_IMPATIENCE = 5000;    // FSSW.cpp:1872
 constexpr int MAX_TRIES_PER_HADRON = 2000000;   // safety valve, see propose_kernel
@@ -679,9 +684,11 @@ setup_kernel(const SamplerArgs A) {
     __syncthreads();
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
     unsigned long long my_range = 0;
-    for (int64_t base = static_cast<int64_t>(blockIdx.x)*blockDim.x; base < A.nwork;
-         base += static_cast<int64_t>(gridDim.x)*blockDim.x) {
-        const int64_t j = base + threadIdx.x;
+    // a CTA works through segments of PART_TILE consecutive work items (the tiles of
+    // partition_kernel) and leaves the histogram of every segment over the cell blocks
+    for (int64_t seg = blockIdx.x; seg < A.nseg; seg += gridDim.x) {
+      for (int it = 0; it < PART_TILE/SETUP_THREADS; it++) {
+        const int64_t j = seg*PART_TILE + it*SETUP_THREADS + threadIdx.x;
         const bool valid = j < A.nwork;
         int cell = 0;
         if (valid) {
@@ -721,34 +728,36 @@ setup_kernel(const SamplerArgs A) {
             }
         }
         if (valid) atomicAdd(&hist[cell >> A.bucket_shift], 1u);
+      }
+      __syncthreads();
+      // [block][segment]: the exclusive scan of this table in memory order is the write offset of
+      // every (block, segment) run
+      for (int b = threadIdx.x; b < A.nbucket; b += blockDim.x) {
+          A.bucket_cnt[static_cast<int64_t>(b)*A.nseg + seg] = hist[b];
+          hist[b] = 0u;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    for (int b = threadIdx.x; b < A.nbucket; b += blockDim.x)
-        if (hist[b]) atomicAdd(&A.bucket_cnt[b], static_cast<unsigned long long>(hist[b]));
     if (my_range) atomicAdd(&A.counters[3], my_range);
 }
 
-// K5b: after the exclusive scan of the histogram: every task to the region of its cell block.
-// A CTA takes a tile of PART_TILE consecutive tasks, counts them per block in shared memory,
-// reserves the tile's share of every block with ONE global atomic per (tile, block) and writes the
-// tasks of a block side by side, so that the 32-byte records leave the L2 as (mostly) full lines.
-// Inside a block the order depends on atomic timing; the results do not.
-constexpr int PART_THREADS = 256;
-constexpr int PART_ITEMS = 8;
-constexpr int PART_TILE = PART_THREADS*PART_ITEMS;
-constexpr int MAX_BUCKETS = 1024;
-
+// K5b: after the exclusive scan of the [block][segment] histogram: every task to the region of its
+// cell block.  A CTA takes a segment of PART_TILE consecutive tasks; the tasks of one block leave
+// side by side in a run that starts at the scanned offset of (block, segment), so the 32-byte
+// records reach DRAM as runs of ~1 KB.  No global atomics; inside a run the order depends on the
+// timing of shared-memory atomics, the results do not.
 __global__ void __launch_bounds__(PART_THREADS)
 partition_kernel(const SamplerArgs A) {
     __shared__ unsigned int cnt[MAX_BUCKETS];
-    __shared__ unsigned long long gbase[MAX_BUCKETS];
-    const int64_t ntile = (A.nwork + PART_TILE - 1)/PART_TILE;
-    for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
-        for (int b = threadIdx.x; b < A.nbucket; b += PART_THREADS) cnt[b] = 0u;
+    __shared__ long long gbase[MAX_BUCKETS];
+    for (int64_t seg = blockIdx.x; seg < A.nseg; seg += gridDim.x) {
+        for (int b = threadIdx.x; b < A.nbucket; b += PART_THREADS) {
+            cnt[b] = 0u;
+            gbase[b] = static_cast<long long>(A.bucket_cnt[static_cast<int64_t>(b)*A.nseg + seg]);
+        }
         __syncthreads();
         uint4 t0[PART_ITEMS], t1[PART_ITEMS];
-        unsigned int rank[PART_ITEMS];
-        const int64_t base = tile*PART_TILE;
+        const int64_t base = seg*PART_TILE;
 #pragma unroll
         for (int i = 0; i < PART_ITEMS; i++) {
             const int64_t j = base + i*PART_THREADS + threadIdx.x;
@@ -761,17 +770,9 @@ partition_kernel(const SamplerArgs A) {
 #pragma unroll
         for (int i = 0; i < PART_ITEMS; i++) {
             const int64_t j = base + i*PART_THREADS + threadIdx.x;
-            if (j < A.nwork) rank[i] = atomicAdd(&cnt[t1[i].x >> A.bucket_shift], 1u);
-        }
-        __syncthreads();
-        for (int b = threadIdx.x; b < A.nbucket; b += PART_THREADS)
-            if (cnt[b]) gbase[b] = atomicAdd(&A.bucket_cnt[b], static_cast<unsigned long long>(cnt[b]));
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < PART_ITEMS; i++) {
-            const int64_t j = base + i*PART_THREADS + threadIdx.x;
             if (j < A.nwork) {
-                const int64_t pos = static_cast<int64_t>(gbase[t1[i].x >> A.bucket_shift]) + rank[i];
+                const unsigned int b = t1[i].x >> A.bucket_shift;
+                const int64_t pos = gbase[b] + atomicAdd(&cnt[b], 1u);
                 uint4 *dst = reinterpret_cast<uint4 *>(A.tasks + pos);
                 dst[0] = t0[i];
                 dst[1] = t1[i];
@@ -780,27 +781,6 @@ partition_kernel(const SamplerArgs A) {
         }
         __syncthreads();
     }
-}
-
-// exclusive scan of the block histogram (at most MAX_BUCKETS entries): one CTA
-__global__ void __launch_bounds__(MAX_BUCKETS)
-bucket_scan_kernel(unsigned long long *__restrict__ cnt, int n) {
-    __shared__ unsigned long long warp_tot[32];
-    const int i = threadIdx.x;
-    const int lane = i & 31, warp = i >> 5;
-    const unsigned long long v = (i < n) ? cnt[i] : 0ull;
-    unsigned long long incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    unsigned long long wbase = 0;
-    for (int w = 0; w < warp; w++) wbase += warp_tot[w];
-    if (i < n) cnt[i] = wbase + incl - v;
-    if (i == n) cnt[n] = wbase + incl - v;
 }
 
 // ---- bulk-async plumbing of the proposal kernel (mbarrier + cp.async.bulk, PTX ISA 8.x) ----------
@@ -1606,6 +1586,7 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.bucket_cnt = nullptr;
     A.bucket_shift = 0;
     A.nbucket = 1;
+    A.nseg = 0;
     A.cellrec = nullptr;
     A.wire = nullptr;
     A.giveup_info = nullptr;
@@ -1724,15 +1705,18 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
             ISS_CUDA_TRY(h, cudaMalloc(&h->d_tasks, h->tasks_bytes));
             ISS_CUDA_TRY(h, cudaMalloc(&h->d_tasks_unsorted, h->tasks_bytes));
         }
-        ISS_ENSURE(h, h->d_cellcnt, h->cellcnt_bytes, sizeof(unsigned long long)*(MAX_BUCKETS + 2));
+        // cell blocks of the partition: at most MAX_BUCKETS (the 2048 tasks of a segment leave in
+        // runs of >= 32 per block = 1 KB), at least 256 cells each; the cell records of the one or two
+        // blocks in flight (2.6 MB each at C4) stay in L2
+        A.bucket_shift = 8;
+        while (((h->ncell - 1) >> A.bucket_shift) + 1 > MAX_BUCKETS) A.bucket_shift++;
+        A.nbucket = static_cast<int>(((h->ncell - 1) >> A.bucket_shift) + 1);
+        A.nseg = (A.nwork + PART_TILE - 1)/PART_TILE;
+        ISS_ENSURE(h, h->d_cellcnt, h->cellcnt_bytes,
+                   sizeof(unsigned long long)*(static_cast<size_t>(A.nbucket)*A.nseg + 2));
         A.tasks = static_cast<Task32 *>(h->d_tasks);
         A.tasks_unsorted = static_cast<Task32 *>(h->d_tasks_unsorted);
         A.bucket_cnt = h->d_cellcnt;
-        // cell blocks of the partition: at most 512 (tasks of a tile land in runs of ~8 per block),
-        // at least 256 cells each
-        A.bucket_shift = 8;
-        while (((h->ncell - 1) >> A.bucket_shift) + 1 > 512) A.bucket_shift++;
-        A.nbucket = static_cast<int>(((h->ncell - 1) >> A.bucket_shift) + 1);
         if (h->chunk) {     // output slots travel through the sort (they do not follow from the draw index)
             const size_t slot_need = sizeof(uint32_t)*static_cast<size_t>(nstage*RING_TASKS);
             ISS_ENSURE(h, h->d_task_slot, h->task_slot_bytes, slot_need);
@@ -1760,20 +1744,21 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
                                     h->stream));
     {
         ScopedTimer t(h, ISS_T_SETUP);
-        int64_t grid = (A.nwork + SETUP_THREADS - 1)/SETUP_THREADS;
-        if (grid > static_cast<int64_t>(nsm)*32) grid = static_cast<int64_t>(nsm)*32;
         if (!h->chunk) {    // (chunk mode: the hints exist already, chunk_select_work)
             work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
                 h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
         }
-        // partition of the batch's hadrons by cell block: histogram, exclusive scan, scatter
-        ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_cellcnt, 0, sizeof(unsigned long long)*(A.nbucket + 1), h->stream));
+        // partition of the batch's hadrons by cell block: histogram per segment, exclusive scan, scatter
         const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1)
                                   + sizeof(unsigned int)*A.nbucket;
-        setup_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
-        bucket_scan_kernel<<<1, MAX_BUCKETS, 0, h->stream>>>(h->d_cellcnt, A.nbucket); ISS_LAUNCHED(h);
-        int64_t pgrid = (A.nwork + PART_TILE - 1)/PART_TILE;
-        if (pgrid > static_cast<int64_t>(nsm)*8) pgrid = static_cast<int64_t>(nsm)*8;
+        const int64_t sgrid = std::min<int64_t>(A.nseg, static_cast<int64_t>(nsm)*32);
+        setup_kernel<<<static_cast<unsigned>(sgrid), SETUP_THREADS, smem_setup, h->stream>>>(A); ISS_LAUNCHED(h);
+        const int64_t ncnt = static_cast<int64_t>(A.nbucket)*A.nseg;
+        ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_cellcnt + ncnt, 0, sizeof(unsigned long long), h->stream));
+        rc = device_exclusive_scan_i64(h, reinterpret_cast<const int64_t *>(h->d_cellcnt),
+                                       reinterpret_cast<int64_t *>(h->d_cellcnt), ncnt, nullptr);
+        if (rc) return rc;
+        const int64_t pgrid = std::min<int64_t>(A.nseg, static_cast<int64_t>(nsm)*16);
         partition_kernel<<<static_cast<unsigned>(pgrid), PART_THREADS, 0, h->stream>>>(A); ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
