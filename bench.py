@@ -85,44 +85,59 @@ def load_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md): ONE
+    long-lived `nvidia-smi -lms 200` for the GPUs of the job, started by rank 0 before the warm-up
+    steps and stopped after the timed region (a process per sample and per rank perturbs the CUDA
+    calls of an 8-rank run)."""
 
-    def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.rows = []
-        self.stop_flag = threading.Event()
-
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.05)
+
+    def __init__(self, indices):
+        self.indices = [int(i) for i in indices]
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="iss_clocks_", suffix=".csv")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=fd, stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
+            except Exception:
+                try:
+                    self.proc.kill()
+                except Exception:
+                    pass
+            try:
+                rows = [[x.strip() for x in ln.split(",")] for ln in open(self.path) if ln.strip()]
+                os.remove(self.path)
+            except Exception:
+                rows = []
+        rows = [r for r in rows if len(r) >= 8]
+        sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for n, v in zip(names, r[3:7]):
+        for r in rows:
+            for n, v in zip(names, r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(rows), "gpus": self.indices}
 
 
 def bind_to_gpu_numa_node(local):
@@ -260,8 +275,10 @@ def run_engine(args):
             return n_primary, c.n_tries
 
         decay_counts = [0, 0]       # primaries in, final hadrons out (timed steps only)
-        clocks = ClockSampler(local)    # sampled from the warm-up steps (same load) to the end
-        clocks.start()
+        # sampled from the warm-up steps (same load) to the end, by rank 0 for all GPUs of the job
+        clocks = ClockSampler(range(world)) if rank == 0 else None
+        if clocks:
+            clocks.start()
         for _ in range(args.warmup):
             step()
         e.timing(enable=True, reset=True)
@@ -270,15 +287,26 @@ def run_engine(args):
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record(stream)
         hadrons = tries = 0
+        trace = os.environ.get("ISS_BENCH_TRACE") == "1"    # per-step host wall times on stderr
         for _ in range(args.steps):
+            w_a = time.perf_counter()
             h, t = step()
+            if trace:
+                sys.stderr.write("[bench trace] rank %d step wall %.2f ms\n"
+                                 % (rank, 1e3*(time.perf_counter() - w_a)))
             hadrons += h
             tries += t
         t1.record(stream)
         barrier()
         ms = t0.elapsed_time(t1)
         fam_ms, fam_n = e.timing(enable=False)
-        clk = clocks.summary()
+        clk = clocks.summary() if clocks else None
+        # per-rank step time (a slow rank shows here; `ms_per_step` is the max)
+        tr = torch.zeros(world, dtype=torch.float64, device="cuda")
+        tr[rank] = ms/args.steps
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.SUM)
+        ms_per_rank = [round(float(x), 3) for x in tr.tolist()]
         tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
         th = torch.tensor([float(hadrons)], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -391,6 +419,7 @@ def run_engine(args):
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "call": "iSS::generate_samples() (class iSS facade, host surface -> host hadron lists)"},
         "gpu_launches": launches,
+        "ms_per_step_per_rank": ms_per_rank,
         "clocks": clk,
         "spectra": spectra,
     }

@@ -58,6 +58,7 @@ void free_surface(iss_handle *h) {
     cudaFree(h->d_tilebase); h->d_tilebase = nullptr; h->tilebase_bytes = 0;
     cudaFree(h->d_total); h->d_total = nullptr; h->total_bytes = 0;
     cudaFree(h->d_cdflev); h->d_cdflev = nullptr; h->cdflev_bytes = 0;
+    cudaFree(h->d_guide); h->d_guide = nullptr; h->guide_bytes = 0; h->guide_M = 0;
     cudaFree(h->d_tilesum_g); h->d_tilesum_g = nullptr; h->tilesum_g_bytes = 0;
     cudaFree(h->d_tilebase_g); h->d_tilebase_g = nullptr; h->tilebase_g_bytes = 0;
     cudaFree(h->d_cdflev_g); h->d_cdflev_g = nullptr; h->cdflev_g_bytes = 0;

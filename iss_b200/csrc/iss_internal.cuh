@@ -141,6 +141,9 @@ struct iss_handle {
     int nlev = 0;                       // number of levels above the prefix itself
     int64_t lev_n[8] = {0}, lev_off[8] = {0}, lev_stride = 0;
     size_t yields_bytes = 0, cdf_bytes = 0, tilesum_bytes = 0, tilebase_bytes = 0, total_bytes = 0;
+    // guide table of the cell search over level 1 (yields.cu, guide_kernel): [ns][guide_M + 1]
+    // pairs {G[k], G[k+1]}; guide_M = 0: not built (surface-chunk mode)
+    void *d_guide = nullptr; size_t guide_bytes = 0; int64_t guide_M = 0;
     bool have_yields = false;
     bool have_local_yields = false;     // yields + tile sums of the local cells (part 1 of run_yields)
     // surface-chunk sharding (iss_cuda_set_surface_chunk): this handle holds cells

@@ -279,6 +279,8 @@ struct SamplerArgs {
     int nlev;
     int64_t lev_off[8], lev_stride;
     const double *total;            // [ns]
+    const int2 *guide;              // [ns][guide_M + 1] {G[k], G[k+1]} over level 1, or null
+    int64_t guide_M;
     const DeviceSpecies *species;
     int ns;
     int64_t nev, ev_begin;
@@ -487,7 +489,22 @@ __device__ __forceinline__ int64_t pick_cell(const SamplerArgs &A, int s, double
         if (cl + A.cell_begin >= A.g_ncell) cl = A.g_ncell - 1 - A.cell_begin;
         return cl;
     }
-    for (int k = A.nlev; k >= 1; k--) q = 16*q + count_below_16(lev + A.lev_off[k] + 16*q, v);
+    if (A.guide) {
+        // guide table (yields.cu, guide_kernel): u M is exact (M a power of two), the number of
+        // level-1 entries below v lies in [G[k], G[k+1]]
+        const int64_t k = static_cast<int64_t>(u*static_cast<double>(A.guide_M));
+        const int2 g = __ldg(&A.guide[static_cast<int64_t>(s)*(A.guide_M + 1) + k]);
+        const double *__restrict__ L1 = lev + A.lev_off[1];
+        int lo = g.x, hi = g.y;
+        while (hi - lo > 4) {               // wide brackets (flat stretches of the prefix): bisect
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(&L1[mid]) < v) lo = mid + 1; else hi = mid;
+        }
+        while (lo < hi && __ldg(&L1[lo]) < v) lo++;
+        q = lo;
+    } else {
+        for (int k = A.nlev; k >= 1; k--) q = 16*q + count_below_16(lev + A.lev_off[k] + 16*q, v);
+    }
     const double *__restrict__ P = A.cdf + static_cast<int64_t>(s)*A.ncell_pad;
     int64_t cell = 16*q + count_below_16(P + 16*q, v);
     if (cell >= A.ncell) cell = A.ncell - 1;
@@ -1546,6 +1563,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     for (int k = 0; k < 8; k++) A.lev_off[k] = h->lev_off[k];
     A.lev_stride = h->lev_stride;
     A.total = h->d_total;
+    A.guide = (h->guide_M > 0 && !h->chunk) ? static_cast<const int2 *>(h->d_guide) : nullptr;
+    A.guide_M = h->guide_M;
     A.species = h->d_species;
     A.ns = ns;
     A.nev = nev;
@@ -1712,15 +1731,20 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         while (((h->ncell - 1) >> A.bucket_shift) + 1 > MAX_BUCKETS) A.bucket_shift++;
         A.nbucket = static_cast<int>(((h->ncell - 1) >> A.bucket_shift) + 1);
         A.nseg = (A.nwork + PART_TILE - 1)/PART_TILE;
-        ISS_ENSURE(h, h->d_cellcnt, h->cellcnt_bytes,
-                   sizeof(unsigned long long)*(static_cast<size_t>(A.nbucket)*A.nseg + 2));
+        // (capacities with head-room: the batch size fluctuates from call to call, and a
+        // cudaFree + cudaMalloc pair synchronises the device)
+        if (sizeof(unsigned long long)*(static_cast<size_t>(A.nbucket)*A.nseg + 2) > h->cellcnt_bytes)
+            ISS_ENSURE(h, h->d_cellcnt, h->cellcnt_bytes,
+                       sizeof(unsigned long long)*(static_cast<size_t>(A.nbucket)*(A.nseg + A.nseg/8 + 16) + 2));
         A.tasks = static_cast<Task32 *>(h->d_tasks);
         A.tasks_unsorted = static_cast<Task32 *>(h->d_tasks_unsorted);
         A.bucket_cnt = h->d_cellcnt;
         if (h->chunk) {     // output slots travel through the sort (they do not follow from the draw index)
             const size_t slot_need = sizeof(uint32_t)*static_cast<size_t>(nstage*RING_TASKS);
-            ISS_ENSURE(h, h->d_task_slot, h->task_slot_bytes, slot_need);
-            ISS_ENSURE(h, h->d_slot_unsorted, h->slot_unsorted_bytes, slot_need);
+            if (slot_need > h->task_slot_bytes || slot_need > h->slot_unsorted_bytes) {
+                ISS_ENSURE(h, h->d_task_slot, h->task_slot_bytes, slot_need + slot_need/8 + 4096);
+                ISS_ENSURE(h, h->d_slot_unsorted, h->slot_unsorted_bytes, slot_need + slot_need/8 + 4096);
+            }
             A.task_slot = h->d_task_slot;
             A.slot_unsorted = h->d_slot_unsorted;
         }

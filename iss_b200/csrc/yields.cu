@@ -318,6 +318,52 @@ __global__ void cdf_level_pad_kernel(double *__restrict__ lev, const double *__r
         lev[static_cast<int64_t>(s)*lev_stride + off + j] = __ldg(&total[s]);
 }
 
+// K3f: guide table of the cell search (whole-surface mode).  The search needs, for v = (total -
+// 1e-15) u, the number of level-1 entries below v (level 1 = the prefix at the end of every 16-cell
+// block).  For k = 0..M (M a power of two) G[k] is that number at v_k = (total - 1e-15) (k/M); u in
+// [k/M, (k+1)/M) gives v_k <= v <= v_{k+1} (k/M is exact, the product is monotone in its factor), so
+// the answer lies in [G[k], G[k+1]]: with M ~ 2 x the number of blocks the bracket holds ~1 entry
+// instead of a four-level descent.  One thread per level-1 entry j claims the k with
+// L1[j-1] < v_k <= L1[j]; entries are stored as pairs {G[k], G[k+1]} (one 8-byte load).
+__global__ void guide_kernel(const double *__restrict__ lev, int64_t lev_stride, int64_t off1, int64_t n1,
+                             const double *__restrict__ total, int2 *__restrict__ guide, int64_t M) {
+    const int s = blockIdx.y;
+    const int64_t j = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
+    if (j >= n1) return;
+    const double *__restrict__ L = lev + static_cast<int64_t>(s)*lev_stride + off1;
+    int2 *__restrict__ G = guide + static_cast<int64_t>(s)*(M + 1);
+    const double Tp = total[s] - 1e-15;
+    const double invM = 1.0/static_cast<double>(M);
+    auto claim = [&](int64_t k) {
+        G[k].x = static_cast<int>(j);
+        if (k > 0) G[k - 1].y = static_cast<int>(j);
+    };
+    if (!(Tp > 0.)) {
+        // empty species: every v is <= 0 <= L1[0], the count is 0 (entries zeroed by the caller)
+        return;
+    }
+    const double prev = (j == 0) ? -1.0 : L[j - 1];      // (prefix values are >= 0)
+    const double cur = L[j];
+    const bool last = (j == n1 - 1);
+    if (!(cur > prev) && !last) return;
+    int64_t kf = 0;
+    if (j > 0) {
+        kf = static_cast<int64_t>(floor(prev/Tp*static_cast<double>(M)));
+        kf = max(static_cast<int64_t>(0), min(M, kf));
+        while (kf > 0 && Tp*(static_cast<double>(kf - 1)*invM) > prev) kf--;
+        while (kf <= M && !(Tp*(static_cast<double>(kf)*invM) > prev)) kf++;
+    }
+    int64_t kl = M;
+    if (!last) {
+        kl = static_cast<int64_t>(floor(cur/Tp*static_cast<double>(M)));
+        kl = max(static_cast<int64_t>(0), min(M, kl));
+        while (kl < M && Tp*(static_cast<double>(kl + 1)*invM) <= cur) kl++;
+        while (kl >= 0 && !(Tp*(static_cast<double>(kl)*invM) <= cur)) kl--;
+    }
+    for (int64_t k = kf; k <= kl; k++) claim(k);
+    if (last) G[M].y = static_cast<int>(j);
+}
+
 // Surface-chunk mode: level 3 of the GLOBAL search tree from the gathered tile sums.  Entry j is the
 // prefix value of the last cell of the 4096-cell block j, which is the last value tile 4j+3 writes in
 // pass 2: tilesum + tilebase, the same two operands in the same order, hence the same bits as the
@@ -560,6 +606,20 @@ int run_yields_finish(iss_handle *h) {
             cdf_level_kernel<<<g3, 128, 0, h->stream>>>(h->d_cdflev, h->d_total, h->lev_stride,
                                                         h->lev_off[k - 1], h->lev_n[k - 1],
                                                         h->lev_off[k], np_); ISS_LAUNCHED(h);
+        }
+        h->guide_M = 0;
+        if (!h->chunk && h->nlev >= 1) {
+            // guide table of the cell search: M = power of two >= 2 x (number of 16-cell blocks)
+            int64_t M = 16;
+            while (M < 2*h->lev_n[1] && M < (int64_t(1) << 26)) M <<= 1;
+            ISS_ENSURE(h, h->d_guide, h->guide_bytes, sizeof(int2)*static_cast<size_t>(ns)*(M + 1));
+            ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_guide, 0, sizeof(int2)*static_cast<size_t>(ns)*(M + 1),
+                                            h->stream));
+            dim3 gg(static_cast<unsigned>((h->lev_n[1] + 127)/128), static_cast<unsigned>(ns));
+            guide_kernel<<<gg, 128, 0, h->stream>>>(h->d_cdflev, h->lev_stride, h->lev_off[1], h->lev_n[1],
+                                                    h->d_total, static_cast<int2 *>(h->d_guide), M);
+            ISS_LAUNCHED(h);
+            h->guide_M = M;
         }
         if (h->chunk) {
             // global levels 3..g_nlev in their own array (offsets relative to level 3)

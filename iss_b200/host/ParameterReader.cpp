@@ -98,6 +98,11 @@ double ParameterReader::getVal(string name, double defaultValue) {
     return defaultValue;
 }
 
+double ParameterReader::getValQuiet(string name, double defaultValue) {
+    const long idx = find_(name);
+    return idx >= 0 ? entries_[idx].second : defaultValue;
+}
+
 void ParameterReader::echo() {
     if (entries_.empty()) return;
     for (auto const &e : entries_) std::cout << e.first << "=" << e.second << "  ";

@@ -28,6 +28,9 @@ class ParameterReader {
     void setVal(string name, double value);
     double getVal(string name);
     double getVal(string name, double defaultValue);
+    // engine addition: like getVal(name, defaultValue) without the "not found" message, for the keys
+    // the reference does not know (first_event_index, reduce_checks_over_ranks, nccl_rank, ...)
+    double getValQuiet(string name, double defaultValue);
     void echo();
 
  private:

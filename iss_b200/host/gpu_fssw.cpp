@@ -758,7 +758,7 @@ void GpuFSSW::sample_events() {
     // first, first + 1, ...  Every random stream is keyed by (seed, event index, ...), so processes
     // that share the seed and use disjoint index ranges (one per GPU) produce together exactly the
     // events a single process would produce for the whole range.
-    const int64_t ev_base = static_cast<int64_t>(paraRdr_->getVal("first_event_index", 0));
+    const int64_t ev_base = static_cast<int64_t>(paraRdr_->getValQuiet("first_event_index", 0));
     if (ev_base < 0) {
         iss_host::error("first_event_index must be >= 0");
         exit(-1);
@@ -802,7 +802,7 @@ void GpuFSSW::sample_events() {
     }
     { PhaseTimer tw("final fetch_wait"); check_(iss_cuda_fetch_wait(h_), "iss_cuda_fetch_wait"); }
     if (flag_spectators_) std::cout << "Add spectators to the hadron list... " << std::endl;
-    if (static_cast<int>(paraRdr_->getVal("reduce_checks_over_ranks", 0)) == 1) {
+    if (static_cast<int>(paraRdr_->getValQuiet("reduce_checks_over_ranks", 0)) == 1) {
         // one process per GPU, events sharded over the ranks (first_event_index): the QA block
         // behind iSS::perform_checks is summed over the ranks; hadron lists stay rank-local
         join_ranks_();
@@ -827,8 +827,8 @@ void GpuFSSW::join_ranks_() {
             if (const char *v = getenv(n)) return atoi(v);
         return fallback;
     };
-    int nranks = static_cast<int>(paraRdr_->getVal("nccl_nranks", -1));
-    int rank = static_cast<int>(paraRdr_->getVal("nccl_rank", -1));
+    int nranks = static_cast<int>(paraRdr_->getValQuiet("nccl_nranks", -1));
+    int rank = static_cast<int>(paraRdr_->getValQuiet("nccl_rank", -1));
     if (nranks < 0)
         nranks = env_int({"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS"}, 1);
     if (rank < 0) rank = env_int({"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID"}, 0);

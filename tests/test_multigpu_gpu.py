@@ -54,15 +54,24 @@ def test_facade_reduces_checks_over_two_ranks(built, tmp_path):
     capi = built
     name, nev = "viscous2", 40
     idfile = str(tmp_path/"nccl_id")
-    procs = []
+    procs, logs = [], []
     for r in range(2):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), ISS_NCCL_ID_FILE=idfile)
+        logs.append(open(tmp_path/("rank%d.log" % r), "w"))      # files: a full pipe would stall a rank
         procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "multigpu_worker.py"), name,
                                        str(nev), str(tmp_path/("rank%d.npz" % r))], env=env,
-                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
-    outs = [p.communicate(timeout=600)[0].decode() for p in procs]
-    for p, o in zip(procs, outs):
-        assert p.returncode == 0, o[-3000:]
+                                      stdout=logs[-1], stderr=subprocess.STDOUT))
+    try:
+        for p in procs:
+            p.wait(timeout=240)
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        for f in logs:
+            f.close()
+    for r, p in enumerate(procs):
+        assert p.returncode == 0, open(tmp_path/("rank%d.log" % r)).read()[-3000:]
     r0, r1 = (np.load(tmp_path/("rank%d.npz" % r)) for r in range(2))
     assert np.array_equal(r0["qa"], r1["qa"])
     assert r0["qa"][0] == 2*nev and r0["n_events"] == nev
@@ -103,7 +112,7 @@ def test_surface_chunks_over_nccl_reproduce_the_whole_surface(built):
            "--master-addr", "127.0.0.1", "--master-port", "29533",
            os.path.join(REPO, "tools", "chunk_probe.py"), "--cells", "300000", "--events", "100",
            "--steps", "1"]
-    r = subprocess.run(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    r = subprocess.run(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=420)
     assert r.returncode == 0, r.stderr.decode()[-3000:]
     line = json.loads([ln for ln in r.stdout.decode().splitlines() if ln.startswith("{")][-1])
     assert line["n_gpus"] == n
