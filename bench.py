@@ -255,6 +255,9 @@ def run_engine(args):
         from iss_b200 import sharding
         qa_n = int(capi.cuda_lib().iss_cuda_qa_size())
 
+        # the one collective of the path goes through the C ABI (iss_cuda_histograms_allreduce on a
+        # communicator the handle owns); torch.distributed only carries the NCCL id to the ranks
+        qa_via_c_abi = world > 1 and sharding.join_engine_communicator(e)
         step_counter = [0]
 
         def step():
@@ -271,7 +274,10 @@ def run_engine(args):
             e.L.iss_cuda_histograms(e.h, capi._ptr(np.asarray(qa_pids, dtype=np.int32)),
                                     len(qa_pids), 0)
             if world > 1:       # NCCL: QA histograms only
-                sharding.allreduce_sum_(sharding.device_block_as_tensor(e.qa_device_ptr(), qa_n, "cuda"))
+                if qa_via_c_abi:
+                    e.check(e.L.iss_cuda_histograms_allreduce(e.h, None), "iss_cuda_histograms_allreduce")
+                else:
+                    sharding.allreduce_sum_(sharding.device_block_as_tensor(e.qa_device_ptr(), qa_n, "cuda"))
             return n_primary, c.n_tries
 
         decay_counts = [0, 0]       # primaries in, final hadrons out (timed steps only)
@@ -314,6 +320,8 @@ def run_engine(args):
             dist.all_reduce(th, op=dist.ReduceOp.SUM)
         ms_max, hadrons_all = float(tm.item()), float(th.item())
 
+        if qa_via_c_abi:
+            e.L.iss_cuda_nccl_finalize(e.h)
         fp64_peak = e.fp64_peak()
         # (generate_samples() below builds a new device sampler: `e` must not be used after it)
 
@@ -409,6 +417,9 @@ def run_engine(args):
         "config": {"workload": workload_name(args.cells, E, args.workload), "workload_key": args.workload,
                    "cells": ncell, "species": ns,
                    "events_per_step_per_gpu": E, "sharding": "events (weak), surface replicated",
+                   "qa_allreduce": ("none (1 rank)" if world == 1 else
+                                    "iss_cuda_histograms_allreduce (C ABI, NCCL)" if qa_via_c_abi
+                                    else "torch.distributed all_reduce (NCCL)"),
                    "l2": "inputs_larger_than_L2", "seed": args.seed, "host_placement": numa},
         "yields_per_sec": ycs/yields_s if yields_s > 0 else None,
         "sampler_hadrons_per_sec_kernel": hadrons/sample_s if sample_s > 0 else None,

@@ -326,7 +326,8 @@ constexpr int SETUP_THREADS = 256;
 constexpr int PART_THREADS = 256;       // partition_kernel: tasks of a segment per thread
 constexpr int PART_ITEMS = 8;
 constexpr int PART_TILE = PART_THREADS*PART_ITEMS;      // work items per segment
-constexpr int MAX_BUCKETS = 64;         // cell blocks of the partition
+constexpr int MAX_BUCKETS = 64;         // cell blocks of the partition (partition_kernel scans them with one warp)
+static_assert(MAX_BUCKETS == 64, "partition_kernel scans two counters per lane of one warp");
 constexpr int SAMPLER_THREADS = 768;     // one CTA of 24 warps per SM (80 registers per thread)
 constexpr int MAX_IMPATIENCE = 5000;    // FSSW.cpp:1872
 constexpr int MAX_TRIES_PER_HADRON = 2000000;   // safety valve, see propose_kernel
@@ -759,14 +760,20 @@ setup_kernel(const SamplerArgs A) {
 }
 
 // K5b: after the exclusive scan of the [block][segment] histogram: every task to the region of its
-// cell block.  A CTA takes a segment of PART_TILE consecutive tasks; the tasks of one block leave
-// side by side in a run that starts at the scanned offset of (block, segment), so the 32-byte
-// records reach DRAM as runs of ~1 KB.  No global atomics; inside a run the order depends on the
-// timing of shared-memory atomics, the results do not.
+// cell block.  A CTA takes a segment of PART_TILE consecutive tasks, orders them by block in shared
+// memory (rank inside the block from a shared-memory counter, block bases from a scan of the
+// counters) and copies the ordered tile out: consecutive threads write consecutive 16-byte halves,
+// so every (block, segment) run of ~1 KB leaves as full, coalesced sectors at its scanned offset.
+// No global atomics; inside a run the order depends on the timing of shared-memory atomics, the
+// results do not.
 __global__ void __launch_bounds__(PART_THREADS)
 partition_kernel(const SamplerArgs A) {
-    __shared__ unsigned int cnt[MAX_BUCKETS];
-    __shared__ long long gbase[MAX_BUCKETS];
+    extern __shared__ __align__(16) unsigned char part_smem[];
+    uint4 *stage = reinterpret_cast<uint4 *>(part_smem);                          // [PART_TILE][2]
+    uint32_t *sslot = reinterpret_cast<uint32_t *>(stage + 2*PART_TILE);          // [PART_TILE] (chunk mode)
+    __shared__ unsigned int cnt[MAX_BUCKETS];       // tasks of the segment per block
+    __shared__ unsigned int lbase[MAX_BUCKETS + 1]; // exclusive scan of cnt
+    __shared__ long long gbase[MAX_BUCKETS];        // global offset of the (block, segment) run
     for (int64_t seg = blockIdx.x; seg < A.nseg; seg += gridDim.x) {
         for (int b = threadIdx.x; b < A.nbucket; b += PART_THREADS) {
             cnt[b] = 0u;
@@ -774,27 +781,60 @@ partition_kernel(const SamplerArgs A) {
         }
         __syncthreads();
         uint4 t0[PART_ITEMS], t1[PART_ITEMS];
+        unsigned int rank[PART_ITEMS];
         const int64_t base = seg*PART_TILE;
+        const int ntask = static_cast<int>(min(static_cast<int64_t>(PART_TILE), A.nwork - base));
 #pragma unroll
         for (int i = 0; i < PART_ITEMS; i++) {
-            const int64_t j = base + i*PART_THREADS + threadIdx.x;
-            if (j < A.nwork) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(A.tasks_unsorted + j);
+            const int l = i*PART_THREADS + threadIdx.x;
+            if (l < ntask) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(A.tasks_unsorted + base + l);
                 t0[i] = __ldg(src);
                 t1[i] = __ldg(src + 1);
             }
         }
 #pragma unroll
         for (int i = 0; i < PART_ITEMS; i++) {
-            const int64_t j = base + i*PART_THREADS + threadIdx.x;
-            if (j < A.nwork) {
-                const unsigned int b = t1[i].x >> A.bucket_shift;
-                const int64_t pos = gbase[b] + atomicAdd(&cnt[b], 1u);
-                uint4 *dst = reinterpret_cast<uint4 *>(A.tasks + pos);
-                dst[0] = t0[i];
-                dst[1] = t1[i];
-                if (A.chunk) A.task_slot[pos] = __ldg(&A.slot_unsorted[j]);
+            const int l = i*PART_THREADS + threadIdx.x;
+            if (l < ntask) rank[i] = atomicAdd(&cnt[t1[i].x >> A.bucket_shift], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            // exclusive scan of at most MAX_BUCKETS (= 64) counters by one warp
+            const int b0 = threadIdx.x, b1 = threadIdx.x + 32;
+            const unsigned int c0 = (b0 < A.nbucket) ? cnt[b0] : 0u, c1 = (b1 < A.nbucket) ? cnt[b1] : 0u;
+            unsigned int i0 = c0, i1 = c1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int x0 = __shfl_up_sync(0xffffffffu, i0, d);
+                const unsigned int x1 = __shfl_up_sync(0xffffffffu, i1, d);
+                if (threadIdx.x >= d) { i0 += x0; i1 += x1; }
             }
+            const unsigned int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+            lbase[b0] = i0 - c0;
+            lbase[b1] = tot0 + i1 - c1;
+            if (threadIdx.x == 31) lbase[MAX_BUCKETS] = tot0 + i1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < PART_ITEMS; i++) {
+            const int l = i*PART_THREADS + threadIdx.x;
+            if (l < ntask) {
+                const unsigned int p = lbase[t1[i].x >> A.bucket_shift] + rank[i];
+                stage[2*p] = t0[i];
+                stage[2*p + 1] = t1[i];
+                if (A.chunk) sslot[p] = __ldg(&A.slot_unsorted[base + l]);
+            }
+        }
+        __syncthreads();
+        // copy out: 16-byte half h of the ordered tile belongs to local task p = h/2, whose block
+        // is read from the task itself (second half, word 0 = cell)
+        for (int hidx = threadIdx.x; hidx < 2*ntask; hidx += PART_THREADS) {
+            const int p = hidx >> 1;
+            const unsigned int b = stage[2*p + 1].x >> A.bucket_shift;
+            const int64_t pos = gbase[b] + (p - static_cast<int>(lbase[b]));
+            reinterpret_cast<uint4 *>(A.tasks + pos)[hidx & 1] = stage[hidx];
+            if (A.chunk && (hidx & 1) == 0) A.task_slot[pos] = sslot[p];
         }
         __syncthreads();
     }
@@ -1783,7 +1823,11 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
                                        reinterpret_cast<int64_t *>(h->d_cellcnt), ncnt, nullptr);
         if (rc) return rc;
         const int64_t pgrid = std::min<int64_t>(A.nseg, static_cast<int64_t>(nsm)*16);
-        partition_kernel<<<static_cast<unsigned>(pgrid), PART_THREADS, 0, h->stream>>>(A); ISS_LAUNCHED(h);
+        const size_t smem_part = (sizeof(uint4)*2 + sizeof(uint32_t))*PART_TILE;
+        ISS_CUDA_TRY(h, cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             static_cast<int>(smem_part)));
+        partition_kernel<<<static_cast<unsigned>(pgrid), PART_THREADS, smem_part, h->stream>>>(A);
+        ISS_LAUNCHED(h);
     }
     ISS_CUDA_TRY(h, cudaGetLastError());
 

@@ -123,6 +123,35 @@ def allreduce_sum_(t):
     return t
 
 
+def join_engine_communicator(engine):
+    """Gives the engine's handle its own NCCL communicator over the ranks of the torch process group
+    (iss_cuda_nccl_unique_id on rank 0, the 128-byte id broadcast with torch.distributed,
+    iss_cuda_nccl_init on every rank): afterwards iss_cuda_histograms_allreduce(h, NULL) reduces the
+    QA block through the C ABI, the way a C++ host does it.  Returns True on success."""
+    import ctypes as C
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return False
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ident = torch.zeros(128, dtype=torch.uint8)
+    ok = torch.ones(1, dtype=torch.int32)
+    if rank == 0:
+        buf = (C.c_ubyte*128)()
+        if engine.L.iss_cuda_nccl_unique_id(buf) == 0:
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        else:
+            ok[0] = 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    ident, ok = ident.to(dev), ok.to(dev)
+    dist.broadcast(ident, 0)
+    dist.broadcast(ok, 0)
+    if int(ok.item()) == 0:
+        return False
+    raw = (C.c_ubyte*128)(*[int(x) for x in ident.cpu().tolist()])
+    rc = torch.tensor([engine.L.iss_cuda_nccl_init(engine.h, raw, rank, world)], dtype=torch.int32, device=dev)
+    dist.all_reduce(rc, op=dist.ReduceOp.MAX)
+    return int(rc.item()) == 0
+
+
 def device_block_as_tensor(device_ptr, n_doubles, device):
     """Wraps a device pointer of the engine (e.g. iss_cuda_qa_device_ptr) as a torch tensor so that
     NCCL can reduce it in place."""
