@@ -91,7 +91,7 @@ class ClockSampler:
     steps and stopped after the timed region (a process per sample and per rank perturbs the CUDA
     calls of an 8-rank run)."""
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
@@ -105,12 +105,32 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(prefix="iss_clocks_", suffix=".csv")
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "200"], stdout=fd, stderr=subprocess.DEVNULL)
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=fd, stderr=subprocess.DEVNULL)
             os.close(fd)
         except Exception:
             self.proc = None
 
-    def summary(self):
+    def stop(self):
+        if self.proc is not None and self.proc.poll() is None:
+            try:
+                self.proc.terminate()
+                self.proc.wait(timeout=5)
+            except Exception:
+                try:
+                    self.proc.kill()
+                except Exception:
+                    pass
+
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
+    def summary(self, t_begin=None, t_end=None):
+        """samples inside [t_begin, t_end] (epoch seconds of the load: warm-up + timed steps)"""
         rows = []
         if self.proc is not None:
             try:
@@ -126,7 +146,16 @@ class ClockSampler:
                 os.remove(self.path)
             except Exception:
                 rows = []
-        rows = [r for r in rows if len(r) >= 8]
+        rows = [r for r in rows if len(r) >= 9]
+        if t_begin is not None and t_end is not None:
+            inside = []
+            for r in rows:
+                t = self._epoch(r[0])
+                if t is not None and t_begin - 0.05 <= t <= t_end + 0.05:
+                    inside.append(r)
+            if inside:
+                rows = inside
+        rows = [r[1:] for r in rows]
         sm = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -237,6 +266,11 @@ def run_engine(args):
         torch.cuda.synchronize()
 
     E = args.events_per_step
+    # one nvidia-smi loop for all GPUs of the job, started early so that it samples at full cadence
+    # when the load begins; only the samples of the load window (warm-up + timed steps) are kept
+    clocks = ClockSampler(range(world)) if rank == 0 else None
+    if clocks:
+        clocks.start()
     work = tempfile.mkdtemp(prefix="iss_bench_r%d_" % rank)
     make_case(work, args.cells, args.workload)
     decays_on = args.workload == "c3-decays"
@@ -281,10 +315,7 @@ def run_engine(args):
             return n_primary, c.n_tries
 
         decay_counts = [0, 0]       # primaries in, final hadrons out (timed steps only)
-        # sampled from the warm-up steps (same load) to the end, by rank 0 for all GPUs of the job
-        clocks = ClockSampler(range(world)) if rank == 0 else None
-        if clocks:
-            clocks.start()
+        t_load_begin = time.time()
         for _ in range(args.warmup):
             step()
         e.timing(enable=True, reset=True)
@@ -306,7 +337,7 @@ def run_engine(args):
         barrier()
         ms = t0.elapsed_time(t1)
         fam_ms, fam_n = e.timing(enable=False)
-        clk = clocks.summary() if clocks else None
+        clk = clocks.summary(t_load_begin, time.time()) if clocks else None
         # per-rank step time (a slow rank shows here; `ms_per_step` is the max)
         tr = torch.zeros(world, dtype=torch.float64, device="cuda")
         tr[rank] = ms/args.steps
@@ -365,6 +396,8 @@ def run_engine(args):
             except Exception as exc:        # secondary figure: never fails the headline line
                 spectra = {"error": "%s: %s" % (type(exc).__name__, exc)}
     finally:
+        if clocks:
+            clocks.stop()
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         shutil.rmtree(work, ignore_errors=True)

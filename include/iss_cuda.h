@@ -94,6 +94,9 @@ typedef struct {
  *  MOM22      : data[n0*n1][8]                                             (FSSW.cpp:1341-1376)
  *  MOM14      : data[3][n0(T)][n1(mu)] c0,c1,c2; grid = {T0,dT,mu0,dmu}    (FSSW.cpp:1215-1300)
  *  KAPPA_B    : data[n0(T)][n1(mu)];           grid = {T0,dT,mu0,dmu}      (FSSW.cpp:1546-1568)
+ *  BULK14     : data[n0][4] rows {T [1/fm], B0, D0, E0} of
+ *               deltaf_tables/BulkDf_Coefficients_Hadrons_s95p-v0-PCE.dat, n1 = 4: the legacy class's
+ *               bulk_deltaf_kind 0 (emissionfunction.cpp:298-301, 3633-3647)
  *  MOMENTUM_* : data[4][n0] = Etilde, CDF_0, CDF_1, CDF_2 of one sampler   (Boson/FermionMomentumSampler.cpp)
  *               regime r in {0,1,2}: kind = ISS_TABLE_MOMENTUM_BOSON0 + r etc.
  */
@@ -104,6 +107,7 @@ enum {
     ISS_TABLE_MOM22 = 4,
     ISS_TABLE_MOM14 = 5,
     ISS_TABLE_KAPPA_B = 6,
+    ISS_TABLE_BULK14 = 7,
     ISS_TABLE_MOMENTUM_BOSON0 = 10,     /* +0,+1,+2 : regimes m0 = 0.05, 30, 50 */
     ISS_TABLE_MOMENTUM_FERMION0 = 13    /* +0,+1,+2 : regimes m0 = 0,    30, 50 */
 };
@@ -366,13 +370,14 @@ ISS_API int iss_cuda_spectra_stats(iss_handle *h, double *evaluations, double *k
  *   iss_cuda_upload_surface_lab(cells) -> iss_cuda_legacy_upload_positions ->
  *   iss_cuda_legacy_upload_z_table -> iss_cuda_legacy_set_options -> iss_cuda_legacy_compute_yields
  *   -> iss_cuda_sample / iss_cuda_decay / iss_cuda_histograms / fetch as usual.
- * Not supported (rejected with ISS_ERR_ARG): bulk_deltaf_kind 0 (needs the s95p-PCE coefficient
- * table), PCE chemical potentials.                                                            */
+ * bulk_deltaf_kind 0 needs iss_cuda_upload_table(ISS_TABLE_BULK14).  Not supported: PCE chemical
+ * potentials (unreachable in the reference as shipped).                                       */
 typedef struct {
     int32_t include_deltaf_shear;
     int32_t include_deltaf_bulk;
-    int32_t bulk_deltaf_kind;           /* 1..4 (the yields carry a bulk term for kind 1 only,
-                                           emissionfunction.cpp:3143-3147); others: zero coefficients */
+    int32_t bulk_deltaf_kind;           /* 0..4 (the yields carry a bulk term for kind 1 only,
+                                           emissionfunction.cpp:3143-3147; 0: table ISS_TABLE_BULK14);
+                                           others: zero coefficients */
     int32_t include_deltaf_diffusion;   /* needs ISS_TABLE_KAPPA_B and ISS_TABLE_EXPINT */
     int32_t restrict_deltaf;
     int32_t reserved;

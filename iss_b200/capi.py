@@ -25,7 +25,7 @@ QA_NSPEC, QA_NPT, QA_NY, QA_NPHI, QA_NV2, QA_HEAD = 16, 100, 100, 64, 20, 32
 QA_PER = 3*QA_NPT + QA_NY + QA_NPHI + 2*QA_NV2 + 2
 T_KINDS = ["yields", "scan", "mult", "sample", "decay", "qa", "setup"]
 
-TABLE_BESSEL_K, TABLE_EXPINT, TABLE_CE, TABLE_MOM22, TABLE_MOM14, TABLE_KAPPA_B = 1, 2, 3, 4, 5, 6
+TABLE_BESSEL_K, TABLE_EXPINT, TABLE_CE, TABLE_MOM22, TABLE_MOM14, TABLE_KAPPA_B, TABLE_BULK14 = 1, 2, 3, 4, 5, 6, 7
 
 
 class Species(C.Structure):

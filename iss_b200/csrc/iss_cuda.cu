@@ -187,7 +187,7 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_qa); cudaFree(h->d_trace);
     cudaFree(h->d_own); cudaFree(h->d_wlist);
     cudaFree(h->d_legpos); cudaFree(h->d_legcoef); cudaFree(h->d_zx); cudaFree(h->d_zy);
-    cudaFree(h->d_lambert); cudaFree(h->d_legmax);
+    cudaFree(h->d_lambert); cudaFree(h->d_legmax); cudaFree(h->d_bulk0);
     if (h->h_mail) cudaFreeHost(h->h_mail);
     if (h->h_evoff) cudaFreeHost(h->h_evoff);
     for (auto &sp : h->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
@@ -360,6 +360,15 @@ int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data, int64
         h->g14 = Grid2D{grid4[0], grid4[1], grid4[2], grid4[3], static_cast<int>(n0),
                         static_cast<int>(n1)};
         return upload_doubles(h, &h->d_mom14, data, 3*n0*n1);
+    case ISS_TABLE_BULK14: {
+        // rows "T[1/fm] B0 D0 E0" -> four columns (Table::interp works column-wise)
+        if (n1 != 4 || n0 < 4) ISS_FAIL(h, ISS_ERR_ARG, "14-moment bulk table: n0 >= 4 rows of 4 numbers");
+        std::vector<double> cols(static_cast<size_t>(4)*n0);
+        for (int64_t i = 0; i < n0; i++)
+            for (int c = 0; c < 4; c++) cols[c*n0 + i] = data[i*4 + c];
+        h->nbulk0 = static_cast<int>(n0);
+        return upload_doubles(h, &h->d_bulk0, cols.data(), cols.size());
+    }
     case ISS_TABLE_KAPPA_B:
         if (!grid4 || n1 <= 0) return ISS_ERR_ARG;
         h->gk = Grid2D{grid4[0], grid4[1], grid4[2], grid4[3], static_cast<int>(n0),

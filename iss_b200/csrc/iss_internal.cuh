@@ -112,6 +112,7 @@ struct iss_handle {
     float4 *d_legpos = nullptr; size_t legpos_bytes = 0; int64_t nlegpos = 0;   // x, y, eta_s, 0
     double4 *d_legcoef = nullptr; size_t legcoef_bytes = 0;                     // c0, c1, c2, kappa
     double *d_zx = nullptr, *d_zy = nullptr; int nz = 0;                        // z_exp_m_z.dat
+    double *d_bulk0 = nullptr; int nbulk0 = 0;      // [4][n] bulk coefficients of kind 0 (T, B0, D0, E0)
     double *d_lambert = nullptr;                                                // W0 table
     double *d_legmax = nullptr; size_t legmax_bytes = 0;
     double *d_labrec = nullptr; size_t labrec_bytes = 0;                // per-cell double records

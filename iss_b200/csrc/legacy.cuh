@@ -43,6 +43,8 @@ struct LegacyArgs {
     const float *lab;       // [ncell][ISS_LAB_NFIELD]
     const float4 *pos;      // [ncell] x, y, eta_s, 0
     double4 *coef;          // [ncell] c0, c1, c2, kappa_hat
+    const double *bulk0;    // [4][nbulk0] T [1/fm], B0, D0, E0 (bulk_deltaf_kind 0), or null
+    int nbulk0;
     const double *zx, *zy;  // iSS_tables/z_exp_m_z.dat
     int nz;
     const double *lambert;  // [LEGACY_LAMBERT_N] W0 on x = 0.005 i
@@ -82,12 +84,11 @@ __device__ __forceinline__ double legacy_lambertW(const LegacyArgs &A, double ar
     return (1. - fraction)*__ldg(&A.lambert[idx]) + fraction*__ldg(&A.lambert[idx + 1]);
 }
 
-// TableFunction::map, interpolation_model 5 = interpCubicDirect without extrapolation
-// (src/arsenal.cpp:58-110); NaN where the reference exit(1)s
-__device__ __forceinline__ double legacy_z_map(const LegacyArgs &A, double xx) {
-    const double *__restrict__ x = A.zx;
-    const double *__restrict__ y = A.zy;
-    const int size = A.nz;
+// interpCubicDirect without extrapolation (src/arsenal.cpp:58-110) on an equally spaced table;
+// NaN where the reference exit(1)s.  Used as TableFunction::map with interpolation_model 5
+// (z_exp_m_z) and as Table::interp(1, col, x, 5) (bulk coefficients of kind 0).
+__device__ __forceinline__ double legacy_cubic_direct(const double *__restrict__ x,
+                                                      const double *__restrict__ y, int size, double xx) {
     const double x0 = __ldg(&x[0]);
     const double dx = __ldg(&x[1]) - x0;
     if (fabs(xx - x0) < dx*1e-30) return __ldg(&y[0]);
@@ -106,6 +107,10 @@ __device__ __forceinline__ double legacy_z_map(const LegacyArgs &A, double xx) {
     const double d = xx - (x0 + idx*dx);
     return (-A0 + 3.0*A1 - 3.0*A2 + A3)/(6.0*dx*dx*dx)*d*d*d + (A0 - 2.0*A1 + A2)/(2.0*dx*dx)*d*d
            - (2.0*A0 + 3.0*A1 - 6.0*A2 + A3)/(6.0*dx)*d + A1;
+}
+
+__device__ __forceinline__ double legacy_z_map(const LegacyArgs &A, double xx) {
+    return legacy_cubic_direct(A.zx, A.zy, A.nz, xx);
 }
 
 // max over E >= mass of E^A f0(E): shared by estimate_ideal_maximum (A = 1, :4006-4053),
@@ -213,12 +218,21 @@ static __global__ void legacy_coef_kernel(const LegacyArgs A) {
     if (cell >= A.ncell) return;
     const float *f = A.lab + cell*ISS_LAB_NFIELD;
     const double T = __ldg(&f[ISS_L_T]);
-    double c0 = 0., c1 = 0.;
+    double c0 = 0., c1 = 0., c2 = 0.;
     if (A.include_bulk == 1 && A.bulk_kind >= 1 && A.bulk_kind <= 4)
         legacy_bulk_poly(A.bulk_kind, T, c0, c1);
+    if (A.include_bulk == 1 && A.bulk_kind == 0) {
+        // 14-moment coefficients from BulkDf_Coefficients_Hadrons_s95p-v0-PCE.dat
+        // (emissionfunction.cpp:3633-3647): B0, E0 in fm^3/GeV^3, D0 in fm^3/GeV^2
+        const double T_fm = T/HBARC;
+        const int n = A.nbulk0;
+        c0 = legacy_cubic_direct(A.bulk0, A.bulk0 + n, n, T_fm)/(HBARC*HBARC*HBARC);
+        c1 = legacy_cubic_direct(A.bulk0, A.bulk0 + 2*n, n, T_fm)/(HBARC*HBARC);
+        c2 = legacy_cubic_direct(A.bulk0, A.bulk0 + 3*n, n, T_fm)/(HBARC*HBARC*HBARC);
+    }
     double kappa = 1.0;
     if (A.include_diff == 1) kappa = coef_kappa(A.tab, T, static_cast<double>(__ldg(&f[ISS_L_MUB])));
-    A.coef[cell] = make_double4(c0, c1, 0., kappa);
+    A.coef[cell] = make_double4(c0, c1, c2, kappa);
 }
 
 // K_1, K_2 look-ups: lerp inside [x_min, x_max - dx], exact outside (:3875-3911)

@@ -664,8 +664,9 @@ int legacy_args(iss_handle *h, LegacyArgs &G) {
         ISS_FAIL(h, ISS_ERR_STATE, "cell positions of the lab-frame surface not uploaded");
     if (!h->d_zx) ISS_FAIL(h, ISS_ERR_STATE, "z_exp_m_z table not uploaded");
     const iss_legacy_options &o = h->legopt;
-    if (o.include_deltaf_bulk == 1 && o.bulk_deltaf_kind == 0)
-        ISS_FAIL(h, ISS_ERR_ARG, "legacy sampler: bulk_deltaf_kind 0 (table-driven 14-moment) is not supported");
+    if (o.include_deltaf_bulk == 1 && o.bulk_deltaf_kind == 0 && !h->d_bulk0)
+        ISS_FAIL(h, ISS_ERR_STATE, "legacy sampler: bulk_deltaf_kind 0 needs the 14-moment coefficient "
+                                   "table (iss_cuda_upload_table, ISS_TABLE_BULK14)");
     if (o.include_deltaf_diffusion == 1 && !h->d_kappa)
         ISS_FAIL(h, ISS_ERR_STATE, "kappa_B table not uploaded");
     if (!(o.sample_pT_up_to > 0.) || !(o.sample_y_minus_eta_s_range > 0.))
@@ -679,6 +680,8 @@ int legacy_args(iss_handle *h, LegacyArgs &G) {
     G.lab = h->d_lab;
     G.pos = h->d_legpos;
     G.coef = h->d_legcoef;
+    G.bulk0 = h->d_bulk0;
+    G.nbulk0 = h->nbulk0;
     G.zx = h->d_zx;
     G.zy = h->d_zy;
     G.nz = h->nz;

@@ -265,10 +265,6 @@ void GpuFSSW::init_(const std::vector<int> &chosen_monvals, int flag_PCE) {
         }
         if (paraRdr_->getVal("store_samples_in_memory") != 1)
             iss_host::warning("MC_sampling = 2: samples are always kept in memory by the B200 engine");
-        if (include_bulk_ == 1 && bulk_kind_ == 0) {
-            iss_host::error("MC_sampling = 2: bulk_deltaf_kind = 0 is not supported by the B200 engine");
-            exit(-1);
-        }
     }
 
     device_ = iss_pool::default_device();
@@ -515,7 +511,19 @@ void GpuFSSW::upload_tables_() {
                "iss_cuda_upload_table(14-moment)");
     }
     if (legacy_) {
-        // the legacy class has polynomial bulk coefficients only (emissionfunction.cpp:3625-3762)
+        // polynomial bulk coefficients for kinds 1-4 (emissionfunction.cpp:3625-3762); kind 0 reads
+        // "T[1/fm] B0 D0 E0" rows (emissionfunction.cpp:298-301)
+        if (include_bulk_ == 1 && bulk_kind_ == 0) {
+            const std::string file = dir + "/BulkDf_Coefficients_Hadrons_s95p-v0-PCE.dat";
+            const std::vector<double> &v = cached_numbers(file, 0);
+            if (v.size() < 16 || v.size() % 4 != 0) {
+                iss_host::error("Can not found file: " + file);
+                exit(1);
+            }
+            check_(iss_cuda_upload_table(h_, ISS_TABLE_BULK14, v.data(), static_cast<int64_t>(v.size()/4),
+                                         4, nullptr),
+                   "iss_cuda_upload_table(14-moment bulk, kind 0)");
+        }
     } else if (bulk_kind_ == 21) {
         const std::string file = dir + (smash ? "/smash" : "/urqmd") + "/NEoSBQS_CE_deltafCoeff.dat";
         const std::vector<double> &v = cached_numbers(file, 1);

@@ -57,14 +57,54 @@ def load_kappa(table_path=O.TABLES):
     return v[:150*100, 2].reshape(100, 150).T.copy()   # [T][mu]
 
 
-def cell_coefficients(lab, opt, kappa_tb=None):
-    """[ncell][4]: bulkvisCoefficients c0..c2 (getbulkvisCoefficients(T), :3625-3762; kinds 1-4,
-    kind 0 needs a table and is not supported here) and kappa_hat (1 when diffusion is off)."""
+def cubic_direct(x, y, xx):
+    """interpCubicDirect without extrapolation (arsenal.cpp:58-110) on an equally spaced table,
+    vectorised over xx: the edge intervals use the parabola through three points, the others the
+    cubic through four."""
+    x, y, xx = np.asarray(x, float), np.asarray(y, float), np.asarray(xx, float)
+    n = len(x)
+    x0, dx = x[0], x[1] - x[0]
+    idx = np.floor((xx - x0)/dx).astype(np.int64)
+    if np.any((idx < 0) | (idx >= n - 1)):
+        raise ValueError("interpCubicDirect: x out of bounds (the reference exits)")
+    out = np.empty_like(xx)
+    lo, hi = idx == 0, idx == n - 2
+    for sel, base in ((lo, 0), (hi, n - 3)):
+        if sel.any():
+            A0, A1, A2 = y[base], y[base + 1], y[base + 2]
+            d = xx[sel] - (x0 + base*dx)
+            out[sel] = ((A0 - 2.0*A1 + A2)/(2.0*dx*dx)*d*d - (3.0*A0 - 4.0*A1 + A2)/(2.0*dx)*d + A0)
+    mid = ~(lo | hi)
+    if mid.any():
+        i = idx[mid]
+        A0, A1, A2, A3 = y[i - 1], y[i], y[i + 1], y[i + 2]
+        d = xx[mid] - (x0 + i*dx)
+        out[mid] = ((-A0 + 3.0*A1 - 3.0*A2 + A3)/(6.0*dx*dx*dx)*d*d*d + (A0 - 2.0*A1 + A2)/(2.0*dx*dx)*d*d
+                    - (2.0*A0 + 3.0*A1 - 6.0*A2 + A3)/(6.0*dx)*d + A1)
+    return out
+
+
+def load_bulk14(table_path=O.TABLES):
+    """rows T[1/fm], B0, D0, E0 (emissionfunction.cpp:298-301)"""
+    return np.loadtxt(os.path.join(table_path, "deltaf_tables",
+                                   "BulkDf_Coefficients_Hadrons_s95p-v0-PCE.dat"))
+
+
+def cell_coefficients(lab, opt, kappa_tb=None, bulk14=None):
+    """[ncell][4]: bulkvisCoefficients c0..c2 (getbulkvisCoefficients(T), :3625-3762: polynomials
+    for kinds 1-4, cubic interpolation of the s95p-PCE table for kind 0) and kappa_hat (1 when
+    diffusion is off)."""
     lab = np.asarray(lab, dtype=np.float32)
     T = lab[:, L["T"]].astype(np.float64)
     out = np.zeros((len(lab), 4))
     out[:, 3] = 1.0
-    if opt.include_bulk == 1:
+    if opt.include_bulk == 1 and opt.bulk_kind == 0:
+        tb = load_bulk14() if bulk14 is None else bulk14
+        T_fm = T/HBARC
+        out[:, 0] = cubic_direct(tb[:, 0], tb[:, 1], T_fm)/HBARC**3
+        out[:, 1] = cubic_direct(tb[:, 0], tb[:, 2], T_fm)/HBARC**2
+        out[:, 2] = cubic_direct(tb[:, 0], tb[:, 3], T_fm)/HBARC**3
+    elif opt.include_bulk == 1:
         out[:, 0:3] = SO.bulk_coefficients(opt.bulk_kind, T)
     if opt.include_diff == 1:
         out[:, 3] = O.coef_kappa(kappa_tb, T, lab[:, L["muB"]].astype(np.float64))

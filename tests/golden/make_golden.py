@@ -248,6 +248,9 @@ LEGACY.update({
     "l3d_bulk4_boltzmann": dict(gen=dict(ncell=40, seed=43, eos=9), param="iSS_parameters_CEdeltaf.dat",
                                 over=["include_deltaf_shear=1", "include_deltaf_bulk=1",
                                       "bulk_deltaf_kind=4", "quantum_statistics=0"]),
+    # kind 0: 14-moment coefficients from BulkDf_Coefficients_Hadrons_s95p-v0-PCE.dat
+    "l3d_bulk0": dict(gen=dict(ncell=40, seed=44, eos=9), param="iSS_parameters_CEdeltaf.dat",
+                      over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=0"]),
 })
 LEGACY_STATS = {
     # one moving cell with shear stress (Viscous2 fixture, volume scaled down), UrQMD list
@@ -263,6 +266,10 @@ LEGACY_STATS = {
     "cell_bulk3": dict(music="9", param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=14,
                        cell="testViscousOneFluidCell2.dat", scale=0.002,
                        over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=3"]),
+    # kind 0 on a surface with bulk pressure (the one-cell fixtures have Pi = 0)
+    "surf3d_bulk0": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=15,
+                         gen=dict(ncell=300, seed=2026, eos=9),
+                         over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=0"]),
     "surf3d_bulk1": dict(music=None, param="iSS_parameters_CEdeltaf.dat", nev=10000, seed=12,
                          gen=dict(ncell=300, seed=2025, eos=14, rhob=1, diffusion=1, binary=1),
                          over=["include_deltaf_shear=1", "include_deltaf_bulk=1", "bulk_deltaf_kind=1",

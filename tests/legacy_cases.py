@@ -13,9 +13,9 @@ import legacy_oracle as lgo  # noqa: E402
 # bulk kinds 2-4, Boltzmann statistics and unrestricted delta f (MORE_CASES) run on the GPU like
 # the first three; on the CPU the oracle is pinned against the reference for all of them
 BASE_CASES = ["l3d_shear", "l3d_bulk1_diff", "l2d_ideal_smash"]
-MORE_CASES = ["l3d_bulk2", "l3d_bulk3_norestrict", "l3d_bulk4_boltzmann"]
+MORE_CASES = ["l3d_bulk2", "l3d_bulk3_norestrict", "l3d_bulk4_boltzmann", "l3d_bulk0"]
 YIELD_CASES = BASE_CASES + MORE_CASES
-STATS_CASES = ["cell_shear", "surf3d_bulk1", "cell_lcc", "cell_bulk3"]
+STATS_CASES = ["cell_shear", "surf3d_bulk1", "cell_lcc", "cell_bulk3", "surf3d_bulk0"]
 
 
 def species_array(sp):

@@ -41,7 +41,7 @@ def test_oracle_yields_and_maxima_match_reference(name):
     assert np.allclose(mx, g["maximum"], rtol=1e-12, atol=0)
 
 
-@pytest.mark.parametrize("name", ["cell_shear", "cell_lcc", "cell_bulk3"])
+@pytest.mark.parametrize("name", ["cell_shear", "cell_lcc", "cell_bulk3", "surf3d_bulk0"])
 def test_oracle_sampler_matches_reference_sampler(name, tmp_path):
     """chi2 of pT / y / phi spectra of the restated sampler against the reference's own samples
     (10^4 events); acceptance as in tests/test_stats_gpu.py."""
@@ -91,8 +91,7 @@ def test_facade_refuses_what_the_legacy_mode_does_not_cover(built, tmp_path):
     exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iSS.e")
     base = [exe, param, "case", surf] + ["%s=%g" % kv for kv in over.items()]
     os.symlink(orc.TABLES, str(tmp_path/"iSS_tables"))
-    for extra, text in ((["output_samples_into_files=1"], "output_samples_into_files = 1"),
-                        (["include_deltaf_bulk=1", "bulk_deltaf_kind=0"], "bulk_deltaf_kind = 0")):
+    for extra, text in ((["output_samples_into_files=1"], "output_samples_into_files = 1"),):
         r = subprocess.run(base + extra, cwd=str(tmp_path), capture_output=True, text=True,
                            env=dict(os.environ, ISS_INGEST="host"))
         assert r.returncode != 0

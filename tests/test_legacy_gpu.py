@@ -29,6 +29,9 @@ def make_engine(capi, g, par):
     e.upload_species(sp)
     if int(par["include_deltaf_diffusion"]) == 1:
         e.upload_table(capi.TABLE_KAPPA_B, sc.kappa_table(), 150, 100, [0.05, 0.001, 0.0, 0.007892])
+    if int(par["include_deltaf_bulk"]) == 1 and int(par["bulk_deltaf_kind"]) == 0:
+        tb = np.ascontiguousarray(lgo.load_bulk14())
+        e.upload_table(capi.TABLE_BULK14, tb, len(tb), 4)
     e.set_options(hydro_mode=int(par["hydro_mode"]), y_LB=par["y_lb"], y_RB=par["y_rb"],
                   dN_dy_sampling_model=30,
                   local_charge_conservation=int(par.get("local_charge_conservation", 0)))
@@ -56,6 +59,7 @@ def test_legacy_yields_and_maxima_match_reference(name, built):
 @pytest.mark.parametrize("name,nev,extra", [
     ("l3d_shear", 300, {}), ("l3d_bulk1_diff", 300, {}), ("l2d_ideal_smash", 40, {}),
     ("l3d_bulk2", 300, {}), ("l3d_bulk3_norestrict", 300, {}), ("l3d_bulk4_boltzmann", 300, {}),
+    ("l3d_bulk0", 300, {}),
     ("l3d_shear", 300, {"local_charge_conservation": 1}),
     ("l2d_ideal_smash", 40, {"local_charge_conservation": 1})])
 def test_legacy_hadrons_match_oracle(name, nev, extra, built):
