@@ -75,7 +75,7 @@ BYTES_PER_HADRON = 152.0     # 40 B record out + 112 B cell record in
 FLOP_PER_HADRON = 1.0e3
 BYTES_PER_YIELD = 8.2        # 8 B FP64 yield out + 64 B of cell fields / 321 species
 FLOP_PER_YIELD = 175.0       # CE bulk + diffusion series
-NCU_PROPOSE_TRAFFIC_BYTES = 14.29e9   # 11.71 GB read + 2.58 GB written per launch (profiles/r1_ncu_final.csv)
+NCU_PROPOSE_TRAFFIC_BYTES = 8.14e9    # 4.65 GB read + 3.48 GB written per launch (profiles/r2_ncu_sampler_kernels.json)
 
 
 def load_peaks():
@@ -409,8 +409,9 @@ def run_engine(args):
     yields_s = fam_ms["yields"]*1e-3
     n_launch_sample = max(1, int(fam_n["sample"]))
     roof = {
-        "kernel": "propose_kernel (persistent momentum sampler fused with boost/emit); the set-up "
-                  "kernel that feeds it is timed separately (kernel_ms.setup)",
+        "kernel": "propose_kernel (persistent momentum sampler fused with boost/emit, tasks streamed with "
+                  "cp.async.bulk); the set-up and partition kernels that feed it are timed separately "
+                  "(kernel_ms.setup)",
         "bound": "hbm",
         "achieved": BYTES_PER_HADRON*hadrons/sample_s/1e9 if sample_s > 0 else None,
         "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -418,13 +419,14 @@ def run_engine(args):
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch on this workload, from the
         # ncu --set full capture summarised in profiles/ (static evidence, not measured here)
         "traffic": NCU_PROPOSE_TRAFFIC_BYTES if (args.cells == 1000000 and E == 1000) else None,
-        "traffic_source": "profiles/r1_ncu_final.csv",
+        "traffic_source": "profiles/r2_ncu_sampler_kernels.json (ncu --set full, one launch of this workload)",
         "algorithmic_bytes_per_launch": BYTES_PER_HADRON*hadrons/max(1, n_launch_sample),
         "peak_source": peak_src,
         "avg_launch_ms": fam_ms["sample"]/n_launch_sample,
         "share_of_step": fam_ms["sample"]/ms if ms > 0 else None,
-        "note": "the sampler is FP64/transcendental and divergence bound, not HBM bound "
-                "(SURVEY.md 8(d)); see fp64",
+        "note": "the sampler is bound by instruction issue (70 % of the slots), the shared-memory data "
+                "pipe (72 %) and divergence (22.7 of 32 lanes), not by HBM (SURVEY.md 8(d)); see fp64 and "
+                "profiles/r2_ncu_propose_source.txt",
         "fp64": {"achieved_tflops": FLOP_PER_HADRON*hadrons/sample_s/1e12 if sample_s > 0 else None,
                  "peak_tflops": fp64_peak, "peak_source": "DFMA microbenchmark run in this process "
                  "(iss_cuda_fp64_peak)",

@@ -52,6 +52,11 @@ struct QaShared {
     double pt_sum[ISS_QA_NSPEC][ISS_QA_NPT];
     double v2_num[ISS_QA_NSPEC][ISS_QA_NV2];
     double red[QA_THREADS/32];
+    // bin edges of the rapidity and azimuth histograms as the quantities the bins are decided on:
+    // sinh(y_i) (compared with p_z/m_T) and the unit vectors of the sector boundaries (sign of a
+    // cross product), so that no asinh / atan2 in double precision is needed per hadron
+    double y_edge[ISS_QA_NY + 1];
+    double phi_cos[ISS_QA_NPHI + 1], phi_sin[ISS_QA_NPHI + 1];
     // pid -> (tracked slot, B, S, Q): open-addressing hash, built once per CTA.  Hadrons are
     // species-ordered inside an event, but most of the ~300 species have fewer hadrons per event
     // than the CTA has threads, so nearly every record a thread reads has a new pid.
@@ -96,6 +101,10 @@ qa_kernel(const QaArgs A) {
     for (int i = threadIdx.x; i < static_cast<int>(sizeof(QaShared)/4); i += blockDim.x)
         reinterpret_cast<unsigned int *>(qa_smem)[i] = 0u;
     __syncthreads();
+    for (int i = threadIdx.x; i <= ISS_QA_NY; i += blockDim.x)
+        S.y_edge[i] = sinh(-5.0 + i*(10.0/ISS_QA_NY));
+    for (int i = threadIdx.x; i <= ISS_QA_NPHI; i += blockDim.x)
+        sincos(-M_PI + i*(2.*M_PI/ISS_QA_NPHI), &S.phi_sin[i], &S.phi_cos[i]);
     // tracked pids first (charges 0), then the particle table (overwrites with the charges)
     if (threadIdx.x < A.npid && A.pids[threadIdx.x] != 0)
         qa_hash_insert(S, A.pids[threadIdx.x], qa_pack(threadIdx.x, 0, 0, 0));
@@ -174,12 +183,27 @@ qa_kernel(const QaArgs A) {
                     atomicAdd(&S.pt_sum[k][ib], pT);
                 }
                 const double mT2 = static_cast<double>(hd.mass)*hd.mass + pT*pT;
-                const double y = asinh(hd.pz/sqrt(mT2));
-                const int iy = static_cast<int>(floor((y + 5.0)/(10.0/ISS_QA_NY)));
+                // iy = floor((asinh(pz/mT) + 5)/0.1): float estimate, made exact against the
+                // double-precision edges sinh(y_i)
+                const double shy = hd.pz/sqrt(mT2);
+                int iy = static_cast<int>(floorf((asinhf(static_cast<float>(shy)) + 5.f)
+                                                 *(ISS_QA_NY/10.f)));
+                iy = min(ISS_QA_NY, max(-1, iy));
+                while (iy >= 0 && shy < S.y_edge[iy]) iy--;
+                while (iy < ISS_QA_NY && shy >= S.y_edge[iy + 1]) iy++;
                 if (iy >= 0 && iy < ISS_QA_NY) atomicAdd(&S.y_cnt[k][iy], 1u);
-                const double phi = atan2(static_cast<double>(hd.py), static_cast<double>(hd.px));
-                int iphi = static_cast<int>(floor((phi + M_PI)/(2.*M_PI/ISS_QA_NPHI)));
-                iphi = min(ISS_QA_NPHI - 1, max(0, iphi));
+                // iphi = floor((atan2(py, px) + pi)/(2 pi/64)) clamped to [0, 63]: float estimate,
+                // made exact with the sign of (cos, sin)(boundary) x (px, py)
+                const double dpx = hd.px, dpy = hd.py;
+                int iphi = ISS_QA_NPHI/2;           // atan2(0, 0) = 0
+                if (dpx != 0. || dpy != 0.) {
+                    iphi = static_cast<int>(floorf((atan2f(hd.py, hd.px) + 3.14159265f)
+                                                   *(ISS_QA_NPHI/6.28318531f)));
+                    iphi = min(ISS_QA_NPHI - 1, max(0, iphi));
+                    while (iphi > 0 && dpy*S.phi_cos[iphi] - dpx*S.phi_sin[iphi] < 0.) iphi--;
+                    while (iphi < ISS_QA_NPHI - 1
+                           && dpy*S.phi_cos[iphi + 1] - dpx*S.phi_sin[iphi + 1] >= 0.) iphi++;
+                }
                 atomicAdd(&S.phi_cnt[k][iphi], 1u);
                 const int iv = static_cast<int>(pT/(3.0/ISS_QA_NV2));
                 if (iv < ISS_QA_NV2) {

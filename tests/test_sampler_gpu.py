@@ -275,6 +275,13 @@ def test_qa_block_matches_numpy(built, tmp_path):
             nper = np.bincount(ev[m], minlength=nev)
             assert blk[-2] == nper.sum() and blk[-1] == (nper**2).sum()
             assert blk[300:400].sum() <= m.sum() and blk[400:464].sum() == m.sum()
+            # rapidity and azimuth bins (decided on sinh / cross-product edges in the kernel)
+            yy = np.arcsinh(pz[m]/np.sqrt(had["mass"][m].astype(np.float64)**2 + pT[m]**2))
+            iy = np.floor((yy + 5.0)/0.1).astype(int)
+            oky = (iy >= 0) & (iy < 100)
+            assert np.abs(blk[300:400] - np.bincount(iy[oky], minlength=100)).sum() <= 2
+            ip = np.clip(np.floor((np.arctan2(py[m], px[m]) + np.pi)/(2*np.pi/64)).astype(int), 0, 63)
+            assert np.abs(blk[400:464] - np.bincount(ip, minlength=64)).sum() <= 2
             iv = (pT[m]/(3.0/20)).astype(int)
             okv = iv < 20
             assert np.array_equal(blk[484:504], np.bincount(iv[okv], minlength=20))
