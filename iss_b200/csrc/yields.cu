@@ -324,7 +324,8 @@ __global__ void cdf_level_pad_kernel(double *__restrict__ lev, const double *__r
 // [k/M, (k+1)/M) gives v_k <= v <= v_{k+1} (k/M is exact, the product is monotone in its factor), so
 // the answer lies in [G[k], G[k+1]]: with M ~ 2 x the number of blocks the bracket holds ~1 entry
 // instead of a four-level descent.  One thread per level-1 entry j claims the k with
-// L1[j-1] < v_k <= L1[j]; entries are stored as pairs {G[k], G[k+1]} (one 8-byte load).
+// L1[j-1] < v_k <= L1[j] (every k in [0, M] has exactly one such j: the last entry claims the rest);
+// entries are stored as pairs {G[k], G[k+1]} (one 8-byte load).
 __global__ void guide_kernel(const double *__restrict__ lev, int64_t lev_stride, int64_t off1, int64_t n1,
                              const double *__restrict__ total, int2 *__restrict__ guide, int64_t M) {
     const int s = blockIdx.y;
@@ -339,7 +340,8 @@ __global__ void guide_kernel(const double *__restrict__ lev, int64_t lev_stride,
         if (k > 0) G[k - 1].y = static_cast<int>(j);
     };
     if (!(Tp > 0.)) {
-        // empty species: every v is <= 0 <= L1[0], the count is 0 (entries zeroed by the caller)
+        // empty species: every v is <= 0 <= L1[0], the count is 0 for every k
+        for (int64_t k = j*(M + 1)/n1; k < (j + 1)*(M + 1)/n1; k++) G[k] = make_int2(0, 0);
         return;
     }
     const double prev = (j == 0) ? -1.0 : L[j - 1];      // (prefix values are >= 0)
@@ -613,8 +615,6 @@ int run_yields_finish(iss_handle *h) {
             int64_t M = 16;
             while (M < 2*h->lev_n[1] && M < (int64_t(1) << 26)) M <<= 1;
             ISS_ENSURE(h, h->d_guide, h->guide_bytes, sizeof(int2)*static_cast<size_t>(ns)*(M + 1));
-            ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_guide, 0, sizeof(int2)*static_cast<size_t>(ns)*(M + 1),
-                                            h->stream));
             dim3 gg(static_cast<unsigned>((h->lev_n[1] + 127)/128), static_cast<unsigned>(ns));
             guide_kernel<<<gg, 128, 0, h->stream>>>(h->d_cdflev, h->lev_stride, h->lev_off[1], h->lev_n[1],
                                                     h->d_total, static_cast<int2 *>(h->d_guide), M);

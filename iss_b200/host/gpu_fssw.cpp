@@ -257,12 +257,10 @@ void GpuFSSW::init_(const std::vector<int> &chosen_monvals, int flag_PCE) {
     flag_spectators_ = (spectator_mode != 0 && !legacy_) ? 1 : 0;
     if (flag_spectators_) read_spectators_(path_ + "/spectators.dat");
     if (legacy_) {
-        // what the legacy path of this engine does not cover is refused, not approximated
-        if (paraRdr_->getVal("output_samples_into_files") == 1) {
-            iss_host::error("MC_sampling = 2: output_samples_into_files = 1 (per-species samples_*.dat "
-                            "files) is not supported by the B200 engine; use store_samples_in_memory = 1");
-            exit(-1);
-        }
+        // per-species samples_<monval>.dat / samples_control_<monval>.dat / samples_format.dat
+        // (emissionfunction.cpp:3353-3375, 3441-3560, 3578-3617); the samples are kept in memory
+        // as well, whatever store_samples_in_memory says
+        flag_sample_files_ = (paraRdr_->getVal("output_samples_into_files") == 1) ? 1 : 0;
         if (paraRdr_->getVal("store_samples_in_memory") != 1)
             iss_host::warning("MC_sampling = 2: samples are always kept in memory by the B200 engine");
     }
@@ -772,11 +770,16 @@ void GpuFSSW::sample_events() {
         exit(-1);
     }
     PhaseTimer tb("batches (sample+copy)");
+    if (flag_sample_files_) {
+        begin_sample_files_();
+        check_(iss_cuda_set_trace(h_, 1), "iss_cuda_set_trace");
+    }
     for (int64_t ev0 = 0; ev0 < nev_; ev0 += batch) {
         const int64_t ev1 = std::min<int64_t>(nev_, ev0 + batch);
         iss_counts cnt;
         check_(iss_cuda_sample(h_, static_cast<uint64_t>(seed_), ev_base + ev0, ev_base + ev1, &cnt),
                "iss_cuda_sample");
+        if (flag_sample_files_) append_sample_files_(ev1 - ev0, cnt.n_hadrons);
         if (decays_on) {
             // FSSW::shell skips the feed-down for SMASH (FSSW.cpp:346)
             check_(iss_cuda_decay(h_, static_cast<uint64_t>(seed_), &cnt), "iss_cuda_decay");
@@ -809,6 +812,10 @@ void GpuFSSW::sample_events() {
         }
     }
     { PhaseTimer tw("final fetch_wait"); check_(iss_cuda_fetch_wait(h_), "iss_cuda_fetch_wait"); }
+    if (flag_sample_files_) {
+        end_sample_files_();
+        check_(iss_cuda_set_trace(h_, 0), "iss_cuda_set_trace");
+    }
     if (flag_spectators_) std::cout << "Add spectators to the hadron list... " << std::endl;
     if (static_cast<int>(paraRdr_->getValQuiet("reduce_checks_over_ranks", 0)) == 1) {
         // one process per GPU, events sharded over the ranks (first_event_index): the QA block
@@ -882,6 +889,96 @@ void GpuFSSW::join_ranks_() {
     check_(iss_cuda_nccl_init(h_, id, rank, nranks), "iss_cuda_nccl_init");
     if (rank == 0) remove(file.c_str());
     joined[h_] = nranks;
+}
+
+// ---- per-species sample files of the legacy class (output_samples_into_files = 1) ---------------
+// One text line per PRIMARY hadron in samples_<monval>.dat, events one after the other, and the
+// number of draws of every event in samples_control_<monval>.dat.  Quirks kept: under local charge
+// conservation the conjugate partner is written into the positive species' file while the control
+// file counts the draws (emissionfunction.cpp:3441-3546); negative species get empty files only
+// if they were reached before the `continue` (they are not: no files for them, :3343-3349).
+void GpuFSSW::begin_sample_files_() {
+    sample_files_.assign(species_.size(), nullptr);
+    control_files_.assign(species_.size(), nullptr);
+    const int lcc = static_cast<int>(paraRdr_->getVal("local_charge_conservation"));
+    for (size_t s = 0; s < species_.size(); s++) {
+        const std::string a = path_ + "/samples_control_" + std::to_string(species_[s].pid) + ".dat";
+        const std::string b = path_ + "/samples_" + std::to_string(species_[s].pid) + ".dat";
+        if (lcc == 1 && species_[s].charge < 0) continue;       // skipped before the files are made
+        remove(a.c_str());
+        remove(b.c_str());
+        control_files_[s] = fopen(a.c_str(), "w");
+        sample_files_[s] = fopen(b.c_str(), "w");
+        if (!control_files_[s] || !sample_files_[s]) {
+            iss_host::error("can not open " + b);
+            exit(-1);
+        }
+    }
+}
+
+void GpuFSSW::append_sample_files_(int64_t nev_batch, int64_t n_hadrons) {
+    const int ns = static_cast<int>(species_.size());
+    const int lcc = static_cast<int>(paraRdr_->getVal("local_charge_conservation"));
+    std::vector<int64_t> mult(static_cast<size_t>(nev_batch)*ns);
+    check_(iss_cuda_get_multiplicities(h_, mult.data()), "iss_cuda_get_multiplicities");
+    std::vector<iss_hadron> had(static_cast<size_t>(std::max<int64_t>(n_hadrons, 1)));
+    std::vector<int32_t> cell(had.size()), tries(had.size());
+    int64_t got = 0;
+    check_(iss_cuda_fetch_all(h_, had.data(), static_cast<int64_t>(had.size()), &got), "iss_cuda_fetch_all");
+    if (got > 0) check_(iss_cuda_get_trace(h_, cell.data(), tries.data()), "iss_cuda_get_trace");
+    const std::vector<FO_surf> &surf = *lab_surf_;
+    int64_t pos = 0;
+    for (int64_t ev = 0; ev < nev_batch; ev++)
+        for (int s = 0; s < ns; s++) {
+            const int64_t n = mult[ev*ns + s];
+            const int64_t nout = (lcc == 1 && species_[s].charge > 0) ? 2*n : n;
+            if (!control_files_[s]) continue;       // (negative species under charge pairing: n = 0)
+            fprintf(control_files_[s], "%lu\n", static_cast<unsigned long>(n));
+            for (int64_t i = 0; i < nout; i++, pos++) {
+                const iss_hadron &h = had[pos];
+                const FO_surf &c = surf[cell[pos]];
+                const double px = h.px, py = h.py, pz = h.pz, E = h.E, t = h.t, z = h.z;
+                if (use_oscar_) {
+                    fprintf(sample_files_[s],
+                            "%24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e  %24.16e\n",
+                            px, py, pz, E, static_cast<double>(h.mass), static_cast<double>(h.x),
+                            static_cast<double>(h.y), z, t);
+                    continue;
+                }
+                const double pT = std::sqrt(px*px + py*py);
+                double phi = std::atan2(py, px);
+                if (phi < 0.) phi += 2.*M_PI;           // the reference samples phi in [0, 2 pi)
+                const double rap = 0.5*std::log((E + pz)/(E - pz));
+                const double eta_s = 0.5*std::log((t + z)/(t - z));
+                fprintf(sample_files_[s],
+                        "%lu  %e  %e  %e  %e  %e  %e  %e  %e  %e  %e  %e  %e  %e  %e  %e  %e  %e\n",
+                        static_cast<unsigned long>(cell[pos]), c.tau, c.xpt, c.ypt, rap - eta_s, pT, phi,
+                        c.da0, c.da1, c.da2, c.u1/c.u0, c.u2/c.u0, rap, eta_s, E, pz, t, z);
+            }
+        }
+}
+
+void GpuFSSW::end_sample_files_() {
+    for (FILE *f : sample_files_) if (f) fclose(f);
+    for (FILE *f : control_files_) if (f) fclose(f);
+    sample_files_.clear();
+    control_files_.clear();
+    // emissionfunction.cpp:3578-3617 (ParameterReader lower-cases the keys when it reads them back)
+    std::ofstream of((path_ + "/samples_format.dat").c_str());
+    if (!use_oscar_) {
+        of << "Total_number_of_columns = " << 18 << std::endl << "FZ_cell_idx = " << 1 << std::endl
+           << "tau = " << 2 << std::endl << "FZ_x = " << 3 << std::endl << "FZ_y = " << 4 << std::endl
+           << "y_minus_eta_s = " << 5 << std::endl << "pT = " << 6 << std::endl << "phi = " << 7 << std::endl
+           << "surf_da0 = " << 8 << std::endl << "surf_da1 = " << 9 << std::endl << "surf_da2 = " << 10
+           << std::endl << "surf_vx = " << 11 << std::endl << "surf_vy = " << 12 << std::endl
+           << "y = " << 13 << std::endl << "eta_s = " << 14 << std::endl << "E = " << 15 << std::endl
+           << "p_z = " << 16 << std::endl << "t = " << 17 << std::endl << "z = " << 18 << std::endl;
+    } else {
+        of << "Total_number_of_columns = " << 9 << std::endl << "t = " << 9 << std::endl
+           << "FZ_x = " << 6 << std::endl << "FZ_y = " << 7 << std::endl << "z = " << 8 << std::endl
+           << "E = " << 4 << std::endl << "px = " << 1 << std::endl << "py = " << 2 << std::endl
+           << "p_z = " << 3 << std::endl << "mass =" << 5 << std::endl;
+    }
 }
 
 void GpuFSSW::shell() {

@@ -8,6 +8,7 @@
 #define ISS_B200_GPU_FSSW_H_
 
 #include <cstdint>
+#include <cstdio>
 #include <memory>
 #include <string>
 #include <vector>
@@ -97,6 +98,12 @@ class GpuFSSW {
     std::vector<double> qa_;
     int qa_ranks_ = 1;
     void add_spectators_to_qa_(const int32_t *pids, int npid);
+    // per-species text files of the legacy class (output_samples_into_files = 1)
+    int flag_sample_files_ = 0;
+    std::vector<FILE *> sample_files_, control_files_;
+    void begin_sample_files_();
+    void append_sample_files_(int64_t nev_batch, int64_t n_hadrons);
+    void end_sample_files_();
     void join_ranks_();     // NCCL communicator of the job on the pooled handle (once per process)
 
     iSS_Hadron *hadrons_ = nullptr;         // pinned, all events

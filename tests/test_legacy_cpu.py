@@ -79,9 +79,10 @@ def test_oracle_sampler_matches_reference_sampler(name, tmp_path):
     assert stats.chi2.sf(tot_chi2, tot_ndf) > 0.01, (tot_chi2, tot_ndf)
 
 
-def test_facade_refuses_what_the_legacy_mode_does_not_cover(built, tmp_path):
-    """class iSS with MC_sampling = 2: unsupported options end with a message and a non-zero exit
-    (before any device is touched); nothing is approximated or silently ignored."""
+def test_facade_refuses_what_the_legacy_class_offers_beyond_the_conventional_sampler(built, tmp_path):
+    """class iSS: the grid samplers of the legacy class (MC_sampling = 1 / 3) are out of scope and end
+    with a message and a non-zero exit (before any device is touched); nothing is approximated or
+    silently ignored."""
     import os
     import subprocess
     capi = built
@@ -91,7 +92,7 @@ def test_facade_refuses_what_the_legacy_mode_does_not_cover(built, tmp_path):
     exe = os.path.join(os.path.dirname(capi.host_lib_path()), "iSS.e")
     base = [exe, param, "case", surf] + ["%s=%g" % kv for kv in over.items()]
     os.symlink(orc.TABLES, str(tmp_path/"iSS_tables"))
-    for extra, text in ((["output_samples_into_files=1"], "output_samples_into_files = 1"),):
+    for extra, text in ((["MC_sampling=1"], "MC_sampling = 1/3"), (["MC_sampling=3"], "MC_sampling = 1/3")):
         r = subprocess.run(base + extra, cwd=str(tmp_path), capture_output=True, text=True,
                            env=dict(os.environ, ISS_INGEST="host"))
         assert r.returncode != 0

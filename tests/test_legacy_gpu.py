@@ -144,6 +144,44 @@ def test_legacy_spectra_match_reference_sampler(name, built):
     assert stats.chi2.sf(tot_chi2, tot_ndf) > 0.01, (tot_chi2, tot_ndf)
 
 
+def test_legacy_per_species_sample_files(built, tmp_path):
+    """output_samples_into_files = 1 (emissionfunction.cpp:3353-3375, 3441-3560, 3578-3617): one
+    samples_<monval>.dat / samples_control_<monval>.dat pair per species and samples_format.dat; the
+    lines are the primaries of the hadron lists, event after event, in the 18-column layout."""
+    capi = built
+    g = cases.load("surf3d_bulk1", "legacy_stats")
+    nev = 25
+    s = _facade(capi, g, tmp_path, number_of_repeated_sampling=nev, output_samples_into_files=1)
+    try:
+        assert s.read_in_FO_surface() == 0
+        s.set_random_seed(3)
+        assert s.generate_samples() == 0
+        h, off = s.hadrons()
+    finally:
+        s.close()
+    fmt = open(tmp_path/"samples_format.dat").read()
+    assert "Total_number_of_columns = 18" in fmt and "p_z = 16" in fmt
+    n_lines = 0
+    for pid in np.unique(h["pid"]):
+        ctl = np.loadtxt(tmp_path/("samples_control_%d.dat" % pid), ndmin=1).astype(int)
+        rows = np.loadtxt(tmp_path/("samples_%d.dat" % pid), ndmin=2)
+        assert len(ctl) == nev and ctl.sum() == len(rows) == (h["pid"] == pid).sum()
+        assert rows.shape[1] == 18
+        mine = h[h["pid"] == pid]
+        per_ev = [(h["pid"][off[e]:off[e + 1]] == pid).sum() for e in range(nev)]
+        assert np.array_equal(ctl, per_ev)
+        # columns 15..18: E, p_z, t, z; 3, 4: x, y of the cell; 6, 7: pT, phi; 13: y
+        for col, key in ((14, "E"), (15, "pz"), (16, "t"), (17, "z"), (2, "x"), (3, "y")):
+            assert np.allclose(rows[:, col], mine[key], rtol=2e-6, atol=1e-6), key
+        assert np.allclose(rows[:, 5]*np.cos(rows[:, 6]), mine["px"], rtol=1e-5, atol=1e-6)
+        assert np.all((rows[:, 6] >= 0) & (rows[:, 6] < 2*np.pi + 1e-6))
+        assert np.allclose(rows[:, 12], rows[:, 4] + rows[:, 13], atol=1e-5)     # y = (y - eta_s) + eta_s
+        cells = rows[:, 0].astype(int)
+        assert np.allclose(rows[:, 1], g["lab"][cells, 0], rtol=2e-6)           # tau of the cell
+        n_lines += len(rows)
+    assert n_lines == len(h) > 100
+
+
 # ---- through the drop-in facade (class iSS with MC_sampling = 2) ---------------------------------
 def _facade(capi, g, tmp_path, **extra):
     param, surf, over = cases.materialise(g, str(tmp_path))
