@@ -234,6 +234,12 @@ ISS_API int iss_cuda_chunk_yields_finish(iss_handle *h, const double *const *ran
                                          const int64_t *rank_ntile, int32_t nranks, int on_device,
                                          double *dN_species_host);
 
+/* load balance: block_yield_host[j] <- sum over species of the yield of cells [4096 j, 4096 (j+1))
+ * of the WHOLE surface (known on every rank after the finish step; nblock = ceil(ncell_global /
+ * 4096)); a host that samples many events per surface re-cuts the chunks with it
+ * (iss_b200/sharding.py::split_cells_weighted) so that every rank owns the same number of hadrons. */
+ISS_API int iss_cuda_chunk_block_yields(iss_handle *h, double *block_yield_host, int64_t nblock);
+
 /* ---- sampling: FSSW::sample_using_dN_dxtdy_4all_particles_conventional (FSSW.cpp:873-1071)
  *      for events [ev_begin, ev_end): multiplicities, offsets, momenta, boost, emit. */
 ISS_API int iss_cuda_sample(iss_handle *h, uint64_t seed, int64_t ev_begin, int64_t ev_end,
@@ -297,6 +303,12 @@ ISS_API int iss_cuda_nccl_unique_id(void *id128 /* 128 bytes out */);
 ISS_API int iss_cuda_nccl_init(iss_handle *h, const void *id128, int32_t rank, int32_t nranks);
 ISS_API int iss_cuda_nccl_finalize(iss_handle *h);
 ISS_API int iss_cuda_histograms_allreduce(iss_handle *h, void *nccl_comm);
+/* surface-chunk mode, the three steps chunk_yields_local -> all-gather -> chunk_yields_finish as
+ * one call on the handle's stream (ncclAllGather of equal [nspecies][max ntile] blocks, no host
+ * synchronisation in between): rank_ntile[r] = tiles (1024 cells) of rank r's chunk, in rank order;
+ * nccl_comm as for iss_cuda_histograms_allreduce; nranks = 1 needs no communicator.            */
+ISS_API int iss_cuda_chunk_yields_allgather(iss_handle *h, const int64_t *rank_ntile, int32_t nranks,
+                                            void *nccl_comm, double *dN_species_host);
 
 /* ---- timing: accumulated device time per kernel family.  While enabled, every family span is
  *      bracketed by a pair of CUDA events recorded on the handle's stream WITHOUT synchronising;

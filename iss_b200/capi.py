@@ -107,7 +107,7 @@ CUDA_SYMBOLS = [
     "iss_cuda_fetch_all_async", "iss_cuda_fetch_wait", "iss_cuda_sample_momentum",
     "iss_cuda_upload_surface_lab", "iss_cuda_spectra", "iss_cuda_spectra_stats",
     "iss_cuda_ingest_music_binary", "iss_cuda_set_surface_chunk", "iss_cuda_chunk_yields_local",
-    "iss_cuda_chunk_yields_finish", "iss_cuda_upload_surface_aos_part",
+    "iss_cuda_chunk_yields_finish", "iss_cuda_chunk_yields_allgather", "iss_cuda_chunk_block_yields", "iss_cuda_upload_surface_aos_part",
     "iss_cuda_legacy_upload_positions", "iss_cuda_legacy_upload_z_table",
     "iss_cuda_legacy_set_options", "iss_cuda_legacy_compute_yields",
     "iss_cuda_nccl_unique_id", "iss_cuda_nccl_init", "iss_cuda_nccl_finalize",
@@ -158,6 +158,8 @@ def cuda_lib():
         "iss_cuda_set_surface_chunk": (C.c_int, [vp, i64, i64]),
         "iss_cuda_chunk_yields_local": (C.c_int, [vp, C.POINTER(vp), i64p]),
         "iss_cuda_chunk_yields_finish": (C.c_int, [vp, C.POINTER(vp), i64p, i32, C.c_int, vp]),
+        "iss_cuda_chunk_yields_allgather": (C.c_int, [vp, i64p, i32, vp, vp]),
+        "iss_cuda_chunk_block_yields": (C.c_int, [vp, vp, i64]),
         "iss_cuda_sample": (C.c_int, [vp, u64, i64, i64, C.POINTER(Counts)]),
         "iss_cuda_get_multiplicities": (C.c_int, [vp, vp]),
         "iss_cuda_get_poisson_params": (C.c_int, [vp, vp, vp]),
@@ -383,6 +385,23 @@ class Engine:
         dN = np.zeros(self.nspecies)
         self.check(self.L.iss_cuda_chunk_yields_finish(self.h, ptrs, nt, nr, 1 if on_device else 0,
                                                        _ptr(dN)), "chunk_yields_finish")
+        return dN
+
+    def chunk_block_yields(self, ncell_global):
+        """yield (all species) of every 4096-cell block of the whole surface, after the finish step"""
+        nb = (int(ncell_global) + 4095)//4096
+        out = np.zeros(nb)
+        self.check(self.L.iss_cuda_chunk_block_yields(self.h, _ptr(out), nb), "chunk_block_yields")
+        return out
+
+    def chunk_yields_allgather(self, ntiles, comm=None):
+        """local yields, all-gather of the tile sums over the handle's (or the given) NCCL communicator
+        and the global part, one call on the handle's stream; ntiles: tiles of every rank's chunk"""
+        nr = len(ntiles)
+        nt = (C.c_int64*nr)(*[int(x) for x in ntiles])
+        dN = np.zeros(self.nspecies)
+        self.check(self.L.iss_cuda_chunk_yields_allgather(self.h, nt, nr, comm, _ptr(dN)),
+                   "chunk_yields_allgather")
         return dN
 
     def sample(self, seed, ev_begin, ev_end):

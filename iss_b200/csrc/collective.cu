@@ -1,6 +1,7 @@
-// collective.cu -- the one collective of the hot path behind the C ABI: the QA block
+// collective.cu -- the collectives of the hot path behind the C ABI: the QA block
 // (iSS::perform_checks, reference src/iSS.cpp:59-83, 296-363: every entry is a plain sum over
-// hadrons / events) summed over the ranks of a one-process-per-GPU job.  NCCL is bound at run
+// hadrons / events) summed over the ranks of a one-process-per-GPU job, and, in surface-chunk
+// mode, the all-gather of the ranks' tile sums between the local and the global part of the yields.  NCCL is bound at run
 // time (dlopen of libnccl.so.2), so single-GPU hosts need no NCCL at all; a null communicator
 // means "local": the block is left as it is.
 #include <dlfcn.h>
@@ -16,6 +17,7 @@ typedef void *NcclComm;
 typedef int (*GetUniqueIdFn)(NcclUniqueId *);
 typedef int (*CommInitRankFn)(NcclComm *, int, NcclUniqueId, int);
 typedef int (*AllReduceFn)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t);
+typedef int (*AllGatherFn)(const void *, void *, size_t, int, NcclComm, cudaStream_t);
 typedef int (*CommDestroyFn)(NcclComm);
 typedef const char *(*GetErrorStringFn)(int);
 constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
@@ -25,6 +27,7 @@ struct NcclApi {
     GetUniqueIdFn get_unique_id = nullptr;
     CommInitRankFn comm_init_rank = nullptr;
     AllReduceFn all_reduce = nullptr;
+    AllGatherFn all_gather = nullptr;
     CommDestroyFn comm_destroy = nullptr;
     GetErrorStringFn error_string = nullptr;
     std::string err;
@@ -46,10 +49,12 @@ NcclApi &nccl() {
     api.get_unique_id = reinterpret_cast<GetUniqueIdFn>(dlsym(api.lib, "ncclGetUniqueId"));
     api.comm_init_rank = reinterpret_cast<CommInitRankFn>(dlsym(api.lib, "ncclCommInitRank"));
     api.all_reduce = reinterpret_cast<AllReduceFn>(dlsym(api.lib, "ncclAllReduce"));
+    api.all_gather = reinterpret_cast<AllGatherFn>(dlsym(api.lib, "ncclAllGather"));
     api.comm_destroy = reinterpret_cast<CommDestroyFn>(dlsym(api.lib, "ncclCommDestroy"));
     api.error_string = reinterpret_cast<GetErrorStringFn>(dlsym(api.lib, "ncclGetErrorString"));
-    if (!api.get_unique_id || !api.comm_init_rank || !api.all_reduce || !api.comm_destroy) {
-        api.err = "libnccl.so.2 lacks ncclGetUniqueId / ncclCommInitRank / ncclAllReduce / ncclCommDestroy";
+    if (!api.get_unique_id || !api.comm_init_rank || !api.all_reduce || !api.all_gather || !api.comm_destroy) {
+        api.err = "libnccl.so.2 lacks ncclGetUniqueId / ncclCommInitRank / ncclAllReduce / ncclAllGather / "
+                  "ncclCommDestroy";
         api.lib = nullptr;
     }
     return api;
@@ -119,6 +124,44 @@ int iss_cuda_histograms_allreduce(iss_handle *h, void *nccl_comm) {
                                   NCCL_FLOAT64, NCCL_SUM, comm, h->stream);
     if (rc != 0) ISS_FAIL(h, ISS_ERR_CUDA, nccl_error(api, "ncclAllReduce", rc));
     return ISS_OK;
+}
+
+int iss_cuda_chunk_yields_allgather(iss_handle *h, const int64_t *rank_ntile, int32_t nranks,
+                                    void *nccl_comm, double *dN_species_host) {
+    if (!h || !rank_ntile || nranks <= 0) return ISS_ERR_ARG;
+    if (!h->chunk) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_set_surface_chunk must run first");
+    NcclComm comm = nccl_comm ? nccl_comm : h->nccl_comm;
+    if (nranks > 1 && !comm)
+        ISS_FAIL(h, ISS_ERR_STATE, "no communicator: pass an ncclComm_t or call iss_cuda_nccl_init first");
+    cudaSetDevice(h->device);
+    // equal blocks of [nspecies][width] doubles per rank: a rank's [nspecies][ntile] table is the
+    // head of its block (the send buffer is the tile-sum table itself, allocated with that size)
+    int64_t width = 0;
+    for (int r = 0; r < nranks; r++) {
+        if (rank_ntile[r] < 0) return ISS_ERR_ARG;
+        width = std::max(width, rank_ntile[r]);
+    }
+    const int64_t ns = h->nspecies;
+    const size_t block = static_cast<size_t>(ns)*static_cast<size_t>(width);
+    if (sizeof(double)*block > h->tilesum_bytes || !h->d_tilesum) {
+        ISS_ENSURE(h, h->d_tilesum, h->tilesum_bytes, sizeof(double)*block);
+        ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_tilesum, 0, sizeof(double)*block, h->stream));
+    }
+    int rc = iss::run_yields_local(h);
+    if (rc) return rc;
+    if (h->ntile > width) ISS_FAIL(h, ISS_ERR_ARG, "rank_ntile does not list this handle's chunk");
+    std::vector<const double *> blocks(nranks);
+    if (nranks == 1) {
+        blocks[0] = h->d_tilesum;
+    } else {
+        NcclApi &api = nccl();
+        if (!api.lib) ISS_FAIL(h, ISS_ERR_STATE, api.err);
+        ISS_ENSURE(h, h->d_tilesum_all, h->tilesum_all_bytes, sizeof(double)*block*nranks);
+        const int nrc = api.all_gather(h->d_tilesum, h->d_tilesum_all, block, NCCL_FLOAT64, comm, h->stream);
+        if (nrc != 0) ISS_FAIL(h, ISS_ERR_CUDA, nccl_error(api, "ncclAllGather", nrc));
+        for (int r = 0; r < nranks; r++) blocks[r] = h->d_tilesum_all + block*r;
+    }
+    return iss::chunk_combine_tile_sums(h, blocks.data(), rank_ntile, nranks, 1, dN_species_host);
 }
 
 }  // extern "C"

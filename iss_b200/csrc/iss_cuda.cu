@@ -125,6 +125,44 @@ int upload_doubles(iss_handle *h, double **dptr, const double *src, size_t n) {
 
 }  // namespace
 
+namespace iss {
+
+// Surface-chunk mode: the ranks' tile sums ([nspecies][rank_ntile[r]] each, in rank = cell order)
+// into the columns of the [nspecies][g_ntile] table of the whole surface, then the fixed-order
+// combination every rank evaluates (run_yields_finish).
+int chunk_combine_tile_sums(iss_handle *h, const double *const *rank_tilesums, const int64_t *rank_ntile,
+                            int32_t nranks, int on_device, double *dN_species_host) {
+    int64_t sum = 0;
+    bool mine = false;
+    for (int r = 0; r < nranks; r++) {
+        if (rank_ntile[r] < 0 || !rank_tilesums[r]) return ISS_ERR_ARG;
+        if (sum == h->chunk_tile_begin && rank_ntile[r] == h->ntile) mine = true;
+        sum += rank_ntile[r];
+    }
+    if (sum != h->g_ntile || !mine)
+        ISS_FAIL(h, ISS_ERR_ARG, "the ranks' tile counts do not add up to the surface declared by "
+                                 "iss_cuda_set_surface_chunk, or this handle's chunk is not among them");
+    const int64_t ns = h->nspecies;
+    ISS_ENSURE(h, h->d_tilesum_g, h->tilesum_g_bytes, sizeof(double)*ns*h->g_ntile);
+    int64_t t0 = 0;
+    for (int r = 0; r < nranks; r++) {
+        // [ns][rank_ntile[r]] -> columns [t0, t0 + rank_ntile[r]) of [ns][g_ntile]
+        if (rank_ntile[r] > 0)
+            ISS_CUDA_TRY(h, cudaMemcpy2DAsync(h->d_tilesum_g + t0, sizeof(double)*h->g_ntile,
+                                              rank_tilesums[r], sizeof(double)*rank_ntile[r],
+                                              sizeof(double)*rank_ntile[r], ns,
+                                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                              h->stream));
+        t0 += rank_ntile[r];
+    }
+    int rc = run_yields_finish(h);
+    if (rc) return rc;
+    if (dN_species_host) memcpy(dN_species_host, h->h_total.data(), sizeof(double)*h->nspecies);
+    return ISS_OK;
+}
+
+}  // namespace iss
+
 extern "C" {
 
 int iss_cuda_create(int device, iss_handle **out) {
@@ -180,7 +218,7 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_mult); cudaFree(h->d_off_out); cudaFree(h->d_off_work);
     cudaFree(h->d_hadbuf[0]); cudaFree(h->d_hadbuf[1]); cudaFree(h->d_hadrons2); cudaFree(h->d_event_off);
     cudaFree(h->d_tasks); cudaFree(h->d_sampler_args); cudaFree(h->d_hints);
-    cudaFree(h->d_task_slot); cudaFree(h->d_slot_unsorted); cudaFree(h->d_tasks_unsorted);
+    cudaFree(h->d_task_slot); cudaFree(h->d_tasks_unsorted);
     cudaFree(h->d_cellcnt); cudaFree(h->d_cellrec);
     cudaFree(h->d_wire[0]); cudaFree(h->d_wire[1]);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
@@ -526,32 +564,28 @@ int iss_cuda_chunk_yields_finish(iss_handle *h, const double *const *rank_tilesu
     if (!h->chunk) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_set_surface_chunk must run first");
     if (!h->have_local_yields) ISS_FAIL(h, ISS_ERR_STATE, "iss_cuda_chunk_yields_local must run first");
     cudaSetDevice(h->device);
-    int64_t sum = 0;
-    bool mine = false;
-    for (int r = 0; r < nranks; r++) {
-        if (rank_ntile[r] < 0 || !rank_tilesums[r]) return ISS_ERR_ARG;
-        if (sum == h->chunk_tile_begin && rank_ntile[r] == h->ntile) mine = true;
-        sum += rank_ntile[r];
-    }
-    if (sum != h->g_ntile || !mine)
-        ISS_FAIL(h, ISS_ERR_ARG, "the ranks' tile counts do not add up to the surface declared by "
-                                 "iss_cuda_set_surface_chunk, or this handle's chunk is not among them");
+    return iss::chunk_combine_tile_sums(h, rank_tilesums, rank_ntile, nranks, on_device, dN_species_host);
+}
+
+int iss_cuda_chunk_block_yields(iss_handle *h, double *block_yield_host, int64_t nblock) {
+    if (!h || !block_yield_host) return ISS_ERR_ARG;
+    if (!h->chunk || !h->have_yields || h->g_nlev < 3 || !h->d_cdflev_g)
+        ISS_FAIL(h, ISS_ERR_STATE, "surface-chunk yields must be complete (iss_cuda_chunk_yields_finish)");
+    const int64_t nb = (h->g_ncell + ISS_CHUNK_ALIGN - 1)/ISS_CHUNK_ALIGN;
+    if (nblock != nb) ISS_FAIL(h, ISS_ERR_ARG, "nblock must be ceil(ncell_global/4096)");
+    cudaSetDevice(h->device);
+    // level 3 of the global search tree: inclusive prefix at the end of every block, per species
     const int64_t ns = h->nspecies;
-    ISS_ENSURE(h, h->d_tilesum_g, h->tilesum_g_bytes, sizeof(double)*ns*h->g_ntile);
-    int64_t t0 = 0;
-    for (int r = 0; r < nranks; r++) {
-        // [ns][rank_ntile[r]] -> columns [t0, t0 + rank_ntile[r]) of [ns][g_ntile]
-        if (rank_ntile[r] > 0)
-            ISS_CUDA_TRY(h, cudaMemcpy2DAsync(h->d_tilesum_g + t0, sizeof(double)*h->g_ntile,
-                                              rank_tilesums[r], sizeof(double)*rank_ntile[r],
-                                              sizeof(double)*rank_ntile[r], ns,
-                                              on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                              h->stream));
-        t0 += rank_ntile[r];
+    std::vector<double> lev(static_cast<size_t>(ns)*nb);
+    ISS_CUDA_TRY(h, cudaMemcpy2DAsync(lev.data(), sizeof(double)*nb, h->d_cdflev_g + h->g_lev_off[3],
+                                      sizeof(double)*h->g_lev_stride, sizeof(double)*nb, ns,
+                                      cudaMemcpyDeviceToHost, h->stream));
+    ISS_CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int64_t j = 0; j < nb; j++) block_yield_host[j] = 0.;
+    for (int64_t s = 0; s < ns; s++) {
+        const double *row = lev.data() + s*nb;
+        for (int64_t j = 0; j < nb; j++) block_yield_host[j] += row[j] - (j ? row[j - 1] : 0.);
     }
-    int rc = run_yields_finish(h);
-    if (rc) return rc;
-    if (dN_species_host) memcpy(dN_species_host, h->h_total.data(), sizeof(double)*h->nspecies);
     return ISS_OK;
 }
 

@@ -159,8 +159,9 @@ struct iss_handle {
     size_t tilesum_g_bytes = 0, tilebase_g_bytes = 0, cdflev_g_bytes = 0;
     int g_nlev = 0;
     int64_t g_lev_n[8] = {0}, g_lev_off[8] = {0}, g_lev_stride = 0;
-    int64_t *d_own = nullptr; int64_t own_cap = 0;        // [nwork+1] ownership flags -> prefix
-    int64_t *d_wlist = nullptr; int64_t wlist_cap = 0;    // work items of the batch this rank owns
+    double *d_tilesum_all = nullptr; size_t tilesum_all_bytes = 0;  // all-gather of the ranks' tile sums
+    int64_t *d_own = nullptr; int64_t own_cap = 0;        // [ns*nev + 1] owned draws per (species, event) -> prefix
+    int64_t *d_wlist = nullptr; int64_t wlist_cap = 0;    // uint4 identity per owned hadron (two int64 each)
     std::vector<double> h_total;        // dN per species (3+1D sum)
     std::vector<double> h_lambda, h_pmode;
     double *d_lambda = nullptr, *d_pmode = nullptr;
@@ -192,8 +193,7 @@ struct iss_handle {
     void *d_hints = nullptr; size_t hints_bytes = 0;
     void *d_tasks = nullptr; size_t tasks_bytes = 0;     // cell-sorted task list of the batch (Task32)
     void *d_tasks_unsorted = nullptr;                    // the same tasks in work order (same capacity)
-    uint32_t *d_task_slot = nullptr; size_t task_slot_bytes = 0;        // surface-chunk mode: output
-    uint32_t *d_slot_unsorted = nullptr; size_t slot_unsorted_bytes = 0;    // slots, sorted / work order
+    uint32_t *d_task_slot = nullptr; size_t task_slot_bytes = 0;        // surface-chunk mode: output slots, sorted
     unsigned long long *d_cellcnt = nullptr; size_t cellcnt_bytes = 0;  // [ncell + 2] histogram / offsets
     void *d_cellrec = nullptr; size_t cellrec_bytes = 0; // [ncell] CellRec (sampler.cu)
     bool cellrec_valid = false;                          // reset with the yields
@@ -302,6 +302,8 @@ int device_exclusive_scan_i64(iss_handle *h, const int64_t *d_in, int64_t *d_out
 int run_yields(iss_handle *h);
 int run_yields_local(iss_handle *h);
 int run_yields_finish(iss_handle *h);
+int chunk_combine_tile_sums(iss_handle *h, const double *const *rank_tilesums, const int64_t *rank_ntile,
+                            int32_t nranks, int on_device, double *dN_species_host);
 int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev);
 int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t total);
 int build_cellrec(iss_handle *h);

@@ -294,7 +294,6 @@ struct SamplerArgs {
     uint64_t seed;
     const CellRec *cellrec;         // [ncell] per-cell record of the proposal kernel
     Task32 *tasks_unsorted;         // [nwork] tasks in work order (setup_kernel -> partition_kernel)
-    uint32_t *slot_unsorted;        // [nwork] surface-chunk mode only: output slots in work order
     unsigned long long *bucket_cnt; // [nbucket][nseg] (+1) tasks per (cell block, segment of PART_TILE
                                     // work items) -> exclusive scan: write offset of every run
     int bucket_shift, nbucket;      // block = cell >> bucket_shift
@@ -318,8 +317,7 @@ struct SamplerArgs {
     int64_t g_lev_off[8], g_lev_stride;
     int64_t blk_begin, blk_end;     // 4096-cell blocks of the whole surface this rank owns
     int64_t cell_begin, g_ncell;
-    const int64_t *own_pos;         // [nwork_global + 1] exclusive prefix of the ownership flags
-    const int64_t *wlist;           // [nwork] global work-item index of the rank's k-th hadron
+    const uint4 *ident;             // [nwork] (species, event - ev_begin, draw, output slot) of the rank's hadrons
 };
 
 constexpr int SETUP_THREADS = 256;
@@ -579,58 +577,71 @@ __device__ __forceinline__ void work_identity(const SamplerArgs &A, const int64_
     k_out = w - __ldg(&ow[elo]);
 }
 
-// Surface-chunk mode, step 1: one thread per hadron of the WHOLE batch (all ranks run this over
-// the same work items): own[w] = 1 if the hadron's cell lies in this rank's cell range.  Only the
-// global levels of the search tree are read (a few KB per species, cache resident).
-__global__ void __launch_bounds__(SETUP_THREADS)
-owner_kernel(const SamplerArgs A, int64_t nwork_global, int64_t *__restrict__ own) {
-    extern __shared__ unsigned char smem_raw[];
-    int64_t *sp_off = reinterpret_cast<int64_t *>(smem_raw);
-    for (int i = threadIdx.x; i <= A.ns; i += blockDim.x)
-        sp_off[i] = A.off_work[static_cast<int64_t>(i)*A.nev];
-    __syncthreads();
+// Surface-chunk mode: which draws of the batch land in this rank's cells.  pick_cell counts the
+// prefix entries below v; the entries of level 3 of the tree are the inclusive prefix at the end
+// of every 4096-cell block, and the prefix is monotone, so "the block of the descent lies in
+// [blk_begin, blk_end)" is the same statement as P_end[blk_begin - 1] < v <= P_end[blk_end - 1]: two
+// comparisons with numbers every rank holds (chunk_level3_kernel), no descent, no per-hadron
+// arrays.  One warp per (species, event) pair, lanes over its draws (one Philox block each).
+//   FILL = false: owned draws per pair -> cnt[s*nev + ev] and the rank's per-(event, species)
+//                 output counts off_out[ev*ns + s] (unscanned);
+//   FILL = true : after the scans of both, the identity (species, event, draw, output slot) of
+//                 every owned draw in work order (species-major, event, draw) -> ident.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+chunk_own_kernel(const SamplerArgs A, int64_t *__restrict__ cnt, int64_t *__restrict__ off_out,
+                 const int64_t *__restrict__ own_off, uint4 *__restrict__ ident) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
-    for (int64_t w = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x; w < nwork_global;
-         w += static_cast<int64_t>(gridDim.x)*blockDim.x) {
-        int s;
-        int64_t ev, k;
-        work_identity(A, sp_off, w, s, ev, k);
-        uint32_t w0, w1, w2, w3;
-        philox_block(0u, static_cast<uint32_t>(k), static_cast<uint32_t>(A.ev_begin + ev),
-                     sample_stream_word3(s), key0, key1, w0, w1, w2, w3);
-        const double v = (__ldg(&A.total[s]) - 1e-15)*u53(w0, w1);
-        const double *__restrict__ levg = A.cdflev_g + static_cast<int64_t>(s)*A.g_lev_stride;
-        int64_t q = 0;
-        for (int l = A.g_nlev; l >= 3; l--) q = 16*q + count_below_16(levg + A.g_lev_off[l] + 16*q, v);
-        own[w] = (q >= A.blk_begin && q < A.blk_end) ? 1 : 0;
+    const int64_t npair = static_cast<int64_t>(A.ns)*A.nev;
+    const int64_t nwarp = static_cast<int64_t>(gridDim.x)*(blockDim.x >> 5);
+    const bool has_lo = A.blk_begin > 0, has_hi = A.blk_end < (int64_t(1) << 61);
+    for (int64_t j = static_cast<int64_t>(blockIdx.x)*(blockDim.x >> 5) + (threadIdx.x >> 5); j < npair;
+         j += nwarp) {
+        const int64_t n = __ldg(&A.off_work[j + 1]) - __ldg(&A.off_work[j]);
+        const int s = static_cast<int>(j/A.nev);
+        const int64_t ev = j - static_cast<int64_t>(s)*A.nev;
+        const int mult = (A.lcc == 1 && __ldg(&A.species[s].charge) > 0) ? 2 : 1;
+        int64_t running = 0;
+        if (n > 0) {
+            const double *__restrict__ l3 = A.cdflev_g + static_cast<int64_t>(s)*A.g_lev_stride + A.g_lev_off[3];
+            const double lo = has_lo ? __ldg(&l3[A.blk_begin - 1]) : 0.;
+            const double hi = has_hi ? __ldg(&l3[A.blk_end - 1]) : 0.;
+            const double scale = __ldg(&A.total[s]) - 1e-15;
+            const uint32_t event = static_cast<uint32_t>(A.ev_begin + ev);
+            int64_t base = 0, slot0 = 0;
+            if (FILL) {
+                base = __ldg(&own_off[j]);
+                if (__ldg(&own_off[j + 1]) == base) continue;       // nothing of this pair is ours
+                slot0 = __ldg(&off_out[ev*A.ns + s]);
+            }
+            for (int64_t k0 = 0; k0 < n; k0 += 32) {
+                const int64_t k = k0 + lane;
+                bool own = false;
+                if (k < n) {
+                    uint32_t w0, w1, w2, w3;
+                    philox_block(0u, static_cast<uint32_t>(k), event, sample_stream_word3(s), key0, key1,
+                                 w0, w1, w2, w3);
+                    const double v = scale*u53(w0, w1);
+                    own = (!has_lo || lo < v) && (!has_hi || !(hi < v));
+                }
+                const unsigned m = __ballot_sync(full, own);
+                if (FILL && own) {
+                    const int64_t r = running + __popc(m & lt_mask);
+                    ident[base + r] = make_uint4(static_cast<uint32_t>(s), static_cast<uint32_t>(ev),
+                                                 static_cast<uint32_t>(k),
+                                                 static_cast<uint32_t>(slot0 + r*mult));
+                }
+                running += __popc(m);
+            }
+        }
+        if (!FILL && lane == 0) {
+            cnt[j] = running;
+            off_out[ev*A.ns + s] = running*mult;
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) own[nwork_global] = 0;
-}
-
-// step 2 (after the prefix sum of the flags): hadrons this rank writes per (event, species) and
-// the list of the work items it owns, in work-item order
-__global__ void chunk_count_kernel(const int64_t *__restrict__ own_pos, const int64_t *__restrict__ off_work,
-                                   const DeviceSpecies *__restrict__ species, int ns, int64_t nev,
-                                   int lcc, int64_t *__restrict__ out_count) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
-    if (i > nev*ns) return;
-    if (i == nev*ns) {
-        out_count[i] = 0;
-        return;
-    }
-    const int64_t ev = i/ns;
-    const int s = static_cast<int>(i - ev*ns);
-    const int64_t j = static_cast<int64_t>(s)*nev + ev;
-    const int64_t n = own_pos[off_work[j + 1]] - own_pos[off_work[j]];
-    out_count[i] = (lcc == 1 && species[s].charge > 0) ? 2*n : n;
-}
-
-__global__ void chunk_compact_kernel(const int64_t *__restrict__ own_pos, int64_t nwork_global,
-                                     int64_t *__restrict__ wlist) {
-    const int64_t w = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
-    if (w >= nwork_global) return;
-    const int64_t p = own_pos[w];
-    if (own_pos[w + 1] != p) wlist[p] = w;
 }
 
 // per-cell record of the proposal kernel from the AoS cell record and the delta-f coefficients
@@ -710,11 +721,17 @@ setup_kernel(const SamplerArgs A) {
         const bool valid = j < A.nwork;
         int cell = 0;
         if (valid) {
-            // surface-chunk mode: the rank's j-th hadron is work item wlist[j] of the whole batch
-            const int64_t w = A.chunk ? __ldg(&A.wlist[j]) : j;
+            // surface-chunk mode: the rank's hadrons are listed by chunk_own_kernel
             int s;
             int64_t ev, k;
-            work_identity(A, sp_off, w, s, ev, k);
+            if (A.chunk) {
+                const uint4 id = __ldg(&A.ident[j]);
+                s = static_cast<int>(id.x);
+                ev = id.y;
+                k = id.z;
+            } else {
+                work_identity(A, sp_off, j, s, ev, k);
+            }
             const DeviceSpecies p = sp[s];
             Task32 t;
             t.s = static_cast<uint16_t>(s);
@@ -738,12 +755,6 @@ setup_kernel(const SamplerArgs A) {
             const uint4 *src = reinterpret_cast<const uint4 *>(&t);
             dst[0] = src[0];
             dst[1] = src[1];
-            if (A.chunk) {
-                // position among the hadrons of (event, species) this rank writes
-                const int mult = (A.lcc == 1 && p.charge > 0) ? 2 : 1;
-                const int64_t k_out = __ldg(&A.own_pos[w]) - __ldg(&A.own_pos[w - k]);
-                A.slot_unsorted[j] = static_cast<uint32_t>(__ldg(&A.off_out[ev*A.ns + s]) + k_out*mult);
-            }
         }
         if (valid) atomicAdd(&hist[cell >> A.bucket_shift], 1u);
       }
@@ -823,7 +834,7 @@ partition_kernel(const SamplerArgs A) {
                 const unsigned int p = lbase[t1[i].x >> A.bucket_shift] + rank[i];
                 stage[2*p] = t0[i];
                 stage[2*p + 1] = t1[i];
-                if (A.chunk) sslot[p] = __ldg(&A.slot_unsorted[base + l]);
+                if (A.chunk) sslot[p] = __ldg(&A.ident[base + l]).w;
             }
         }
         __syncthreads();
@@ -1529,34 +1540,20 @@ int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev) {
     return ISS_OK;
 }
 
-// Surface-chunk mode: which hadrons of the batch are this rank's.  d_off_work holds the scanned
+// Surface-chunk mode: how many hadrons of the batch are this rank's.  d_off_work holds the scanned
 // work offsets of the WHOLE batch (identical on every rank); on return d_own holds the exclusive
-// prefix of the ownership flags, d_wlist the owned work items, d_off_out the UNSCANNED per
+// prefix over the (species, event) pairs of the owned draws, d_off_out the UNSCANNED per
 // (event, species) output counts of this rank and *n_owned their number.
-static int chunk_select_work(iss_handle *h, const SamplerArgs &A, int64_t nev, int64_t total_work,
-                             int64_t nhint, int nsm, int64_t *n_owned) {
-    const int ns = h->nspecies;
-    int rc = ensure_capacity(h, &h->d_own, &h->own_cap, total_work + 1);
+static int chunk_count_work(iss_handle *h, const SamplerArgs &A, int64_t nev, int nsm, int64_t *n_owned) {
+    const int64_t npair = nev*h->nspecies;
+    int rc = ensure_capacity(h, &h->d_own, &h->own_cap, npair + 1);
     if (rc) return rc;
-    work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
-        h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
-    int64_t grid = (total_work + SETUP_THREADS - 1)/SETUP_THREADS;
-    if (grid > static_cast<int64_t>(nsm)*32) grid = static_cast<int64_t>(nsm)*32;
-    owner_kernel<<<static_cast<unsigned>(grid), SETUP_THREADS, sizeof(int64_t)*(ns + 1), h->stream>>>(
-        A, total_work, h->d_own); ISS_LAUNCHED(h);
+    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_own + npair, 0, sizeof(int64_t), h->stream));
+    const int64_t grid = std::min<int64_t>((npair + 7)/8, static_cast<int64_t>(nsm)*8);
+    chunk_own_kernel<false><<<static_cast<unsigned>(grid), 256, 0, h->stream>>>(
+        A, h->d_own, h->d_off_out, nullptr, nullptr); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
-    rc = device_exclusive_scan_i64(h, h->d_own, h->d_own, total_work, n_owned);
-    if (rc) return rc;
-    const int64_t n = nev*ns;
-    chunk_count_kernel<<<static_cast<unsigned>((n + 1 + 255)/256), 256, 0, h->stream>>>(
-        h->d_own, h->d_off_work, h->d_species, ns, nev, h->opt.local_charge_conservation,
-        h->d_off_out); ISS_LAUNCHED(h);
-    rc = ensure_capacity(h, &h->d_wlist, &h->wlist_cap, *n_owned + 1);
-    if (rc) return rc;
-    chunk_compact_kernel<<<static_cast<unsigned>((total_work + 255)/256), 256, 0, h->stream>>>(
-        h->d_own, total_work, h->d_wlist); ISS_LAUNCHED(h);
-    ISS_CUDA_TRY(h, cudaGetLastError());
-    return ISS_OK;
+    return device_exclusive_scan_i64(h, h->d_own, h->d_own, npair, n_owned);
 }
 
 }  // namespace iss
@@ -1635,13 +1632,11 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     // the last chunk also owns the partly filled block at the end of the surface
     A.blk_end = (h->chunk_cell_begin + h->ncell >= h->g_ncell)
                     ? (int64_t(1) << 62) : (h->chunk_cell_begin + h->ncell)/ISS_CHUNK_ALIGN;
-    A.own_pos = nullptr;
-    A.wlist = nullptr;
+    A.ident = nullptr;
     A.hints = nullptr;
     A.tasks = nullptr;
     A.task_slot = nullptr;
     A.tasks_unsorted = nullptr;
-    A.slot_unsorted = nullptr;
     A.bucket_cnt = nullptr;
     A.bucket_shift = 0;
     A.nbucket = 1;
@@ -1672,10 +1667,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         }
         if (h->chunk && total_work > 0) {
             int64_t n_owned = 0;
-            rc = chunk_select_work(h, A, nev, total_work, nhint, nsm, &n_owned);
+            rc = chunk_count_work(h, A, nev, nsm, &n_owned);
             if (rc) return rc;
-            A.own_pos = h->d_own;
-            A.wlist = h->d_wlist;
             A.nwork = n_owned;
         } else {
             A.nwork = total_work;
@@ -1781,12 +1774,13 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         A.bucket_cnt = h->d_cellcnt;
         if (h->chunk) {     // output slots travel through the sort (they do not follow from the draw index)
             const size_t slot_need = sizeof(uint32_t)*static_cast<size_t>(nstage*RING_TASKS);
-            if (slot_need > h->task_slot_bytes || slot_need > h->slot_unsorted_bytes) {
+            if (slot_need > h->task_slot_bytes)
                 ISS_ENSURE(h, h->d_task_slot, h->task_slot_bytes, slot_need + slot_need/8 + 4096);
-                ISS_ENSURE(h, h->d_slot_unsorted, h->slot_unsorted_bytes, slot_need + slot_need/8 + 4096);
-            }
             A.task_slot = h->d_task_slot;
-            A.slot_unsorted = h->d_slot_unsorted;
+            // identities of the rank's hadrons: two int64 of d_wlist per hadron
+            rc = ensure_capacity(h, &h->d_wlist, &h->wlist_cap, 2*A.nwork + 2);
+            if (rc) return rc;
+            A.ident = reinterpret_cast<const uint4 *>(h->d_wlist);
         }
     }
     if (!h->cellrec_valid) {
@@ -1808,9 +1802,15 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
                                     h->stream));
     {
         ScopedTimer t(h, ISS_T_SETUP);
-        if (!h->chunk) {    // (chunk mode: the hints exist already, chunk_select_work)
+        if (!h->chunk) {
             work_hint_kernel<<<static_cast<unsigned>((nhint + 127)/128), 128, 0, h->stream>>>(
                 h->d_off_work, ns, nev, total_work, static_cast<int2 *>(h->d_hints), nhint); ISS_LAUNCHED(h);
+        } else {
+            // (d_off_out is scanned by now: the output slots are known)
+            const int64_t npair = nev*ns;
+            const int64_t cgrid = std::min<int64_t>((npair + 7)/8, static_cast<int64_t>(nsm)*8);
+            chunk_own_kernel<true><<<static_cast<unsigned>(cgrid), 256, 0, h->stream>>>(
+                A, nullptr, h->d_off_out, h->d_own, reinterpret_cast<uint4 *>(h->d_wlist)); ISS_LAUNCHED(h);
         }
         // partition of the batch's hadrons by cell block: histogram per segment, exclusive scan, scatter
         const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1)

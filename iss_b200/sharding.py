@@ -37,6 +37,33 @@ def split_cells(ncell, world):
     return out
 
 
+def split_cells_weighted(block_cost, ncell, world):
+    """Contiguous cell ranges [b, e) per rank on multiples of CHUNK_ALIGN whose summed cost is as even
+    as a cut at block boundaries allows.  block_cost[j]: cost of cells [4096 j, 4096 (j+1)), e.g.
+    a*cells + b*events*yield from iss_cuda_chunk_block_yields; every rank gets at least one block."""
+    import numpy as np
+    cost = np.asarray(block_cost, dtype=np.float64)
+    nblk = (int(ncell) + CHUNK_ALIGN - 1)//CHUNK_ALIGN
+    if len(cost) != nblk:
+        raise ValueError("block_cost must have ceil(ncell/4096) = %d entries" % nblk)
+    if nblk < world:
+        return split_cells(ncell, world)
+    cum = np.concatenate([[0.], np.cumsum(cost)])
+    cuts = [0]
+    for r in range(1, world):
+        # first boundary whose cumulative cost reaches r/world of the total, leaving a block for
+        # every rank before and after
+        j = int(np.searchsorted(cum, cum[-1]*r/world, side="left"))
+        if j > 0 and abs(cum[j - 1] - cum[-1]*r/world) < abs(cum[j] - cum[-1]*r/world):
+            j -= 1
+        j = max(j, cuts[-1] + 1)
+        j = min(j, nblk - (world - r))
+        cuts.append(j)
+    cuts.append(nblk)
+    return [(min(cuts[r]*CHUNK_ALIGN, int(ncell)), min(cuts[r + 1]*CHUNK_ALIGN, int(ncell)))
+            for r in range(world)]
+
+
 def ntiles_of(cell_range):
     return (cell_range[1] - cell_range[0] + TILE - 1)//TILE
 

@@ -182,3 +182,29 @@ def test_chunked_prefix_equals_single_process(tmp_path):
             assert np.array_equal(np.minimum(local + b, y.shape[1] - 1), cell[mine])
             claimed += mine
         assert np.all(claimed == 1)
+
+
+def test_weighted_cell_split_is_a_partition_on_block_boundaries():
+    """sharding.split_cells_weighted: contiguous, aligned, every rank at least one block, and the
+    heaviest rank close to the mean for a peaked cost profile"""
+    import numpy as np
+    from iss_b200 import sharding
+    ncell = 966924
+    nblk = (ncell + sharding.CHUNK_ALIGN - 1)//sharding.CHUNK_ALIGN
+    x = np.linspace(-3, 3, nblk)
+    cost = 0.02 + np.exp(-x**2)                 # hot mid-rapidity blocks
+    for world in (1, 2, 3, 8):
+        r = sharding.split_cells_weighted(cost, ncell, world)
+        assert len(r) == world and r[0][0] == 0 and r[-1][1] == ncell
+        for (b0, e0), (b1, e1) in zip(r[:-1], r[1:]):
+            assert e0 == b1 and e0 % sharding.CHUNK_ALIGN == 0
+        assert all(e > b for b, e in r)
+        per = [cost[b//sharding.CHUNK_ALIGN:(e + sharding.CHUNK_ALIGN - 1)//sharding.CHUNK_ALIGN].sum()
+               for b, e in r]
+        assert max(per) < 1.15*cost.sum()/world
+    even = sharding.split_cells(ncell, 8)
+    per_even = [cost[b//sharding.CHUNK_ALIGN:(e + sharding.CHUNK_ALIGN - 1)//sharding.CHUNK_ALIGN].sum()
+                for b, e in even]
+    assert max(per_even) > 1.5*cost.sum()/8     # what the weights are for
+    # fewer blocks than ranks: the even cut (trailing ranks empty)
+    assert sharding.split_cells_weighted(np.ones(2), 8000, 4) == sharding.split_cells(8000, 4)
