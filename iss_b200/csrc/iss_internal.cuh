@@ -161,6 +161,7 @@ struct iss_handle {
     int64_t g_lev_n[8] = {0}, g_lev_off[8] = {0}, g_lev_stride = 0;
     double *d_tilesum_all = nullptr; size_t tilesum_all_bytes = 0;  // all-gather of the ranks' tile sums
     int64_t *d_own = nullptr; int64_t own_cap = 0;        // [ns*nev + 1] owned draws per (species, event) -> prefix
+    uint32_t *d_ownmask = nullptr; int64_t ownmask_cap = 0;   // ballot words of the ownership pass
     int64_t *d_wlist = nullptr; int64_t wlist_cap = 0;    // uint4 identity per owned hadron (two int64 each)
     std::vector<double> h_total;        // dN per species (3+1D sum)
     std::vector<double> h_lambda, h_pmode;

@@ -582,18 +582,20 @@ __device__ __forceinline__ void work_identity(const SamplerArgs &A, const int64_
 // of every 4096-cell block, and the prefix is monotone, so "the block of the descent lies in
 // [blk_begin, blk_end)" is the same statement as P_end[blk_begin - 1] < v <= P_end[blk_end - 1]: two
 // comparisons with numbers every rank holds (chunk_level3_kernel), no descent, no per-hadron
-// arrays.  One warp per (species, event) pair, lanes over its draws (one Philox block each).
-//   FILL = false: owned draws per pair -> cnt[s*nev + ev] and the rank's per-(event, species)
-//                 output counts off_out[ev*ns + s] (unscanned);
-//   FILL = true : after the scans of both, the identity (species, event, draw, output slot) of
-//                 every owned draw in work order (species-major, event, draw) -> ident.
-template <bool FILL>
+// arrays.  One warp per (species, event) pair, lanes over its draws (one Philox block each):
+// owned draws per pair -> cnt[s*nev + ev], the rank's per-(event, species) output counts ->
+// off_out[ev*ns + s] (unscanned), and one ballot word per 32 draws -> mask (word chunk_mask_word
+// (j) + i for draws 32 i .. 32 i + 31 of pair j) for chunk_fill_kernel.
+__device__ __forceinline__ int64_t chunk_mask_word(const int64_t *__restrict__ off_work, int64_t j) {
+    // pair j needs ceil(n_j/32) words; floor(off_work[j]/32) + j never overlaps the next pair's range
+    return (__ldg(&off_work[j]) >> 5) + j;
+}
+
 __global__ void __launch_bounds__(256)
 chunk_own_kernel(const SamplerArgs A, int64_t *__restrict__ cnt, int64_t *__restrict__ off_out,
-                 const int64_t *__restrict__ own_off, uint4 *__restrict__ ident) {
+                 uint32_t *__restrict__ mask) {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
     const uint32_t key0 = static_cast<uint32_t>(A.seed), key1 = static_cast<uint32_t>(A.seed >> 32);
     const int64_t npair = static_cast<int64_t>(A.ns)*A.nev;
     const int64_t nwarp = static_cast<int64_t>(gridDim.x)*(blockDim.x >> 5);
@@ -611,12 +613,7 @@ chunk_own_kernel(const SamplerArgs A, int64_t *__restrict__ cnt, int64_t *__rest
             const double hi = has_hi ? __ldg(&l3[A.blk_end - 1]) : 0.;
             const double scale = __ldg(&A.total[s]) - 1e-15;
             const uint32_t event = static_cast<uint32_t>(A.ev_begin + ev);
-            int64_t base = 0, slot0 = 0;
-            if (FILL) {
-                base = __ldg(&own_off[j]);
-                if (__ldg(&own_off[j + 1]) == base) continue;       // nothing of this pair is ours
-                slot0 = __ldg(&off_out[ev*A.ns + s]);
-            }
+            uint32_t *__restrict__ mw = mask + chunk_mask_word(A.off_work, j);
             for (int64_t k0 = 0; k0 < n; k0 += 32) {
                 const int64_t k = k0 + lane;
                 bool own = false;
@@ -628,18 +625,60 @@ chunk_own_kernel(const SamplerArgs A, int64_t *__restrict__ cnt, int64_t *__rest
                     own = (!has_lo || lo < v) && (!has_hi || !(hi < v));
                 }
                 const unsigned m = __ballot_sync(full, own);
-                if (FILL && own) {
-                    const int64_t r = running + __popc(m & lt_mask);
-                    ident[base + r] = make_uint4(static_cast<uint32_t>(s), static_cast<uint32_t>(ev),
-                                                 static_cast<uint32_t>(k),
-                                                 static_cast<uint32_t>(slot0 + r*mult));
-                }
+                if (lane == 0) mw[k0 >> 5] = m;
                 running += __popc(m);
             }
         }
-        if (!FILL && lane == 0) {
+        if (lane == 0) {
             cnt[j] = running;
             off_out[ev*A.ns + s] = running*mult;
+        }
+    }
+}
+
+// after the scans of cnt (own_off) and off_out: the identity (species, event, draw, output slot) of
+// every owned draw in work order (species-major, event, draw) from the ballot words.  One warp per
+// pair, one word per lane, the set bits of a word written one after the other.
+__global__ void __launch_bounds__(256)
+chunk_fill_kernel(const SamplerArgs A, const int64_t *__restrict__ own_off,
+                  const int64_t *__restrict__ off_out, const uint32_t *__restrict__ mask,
+                  uint4 *__restrict__ ident) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t npair = static_cast<int64_t>(A.ns)*A.nev;
+    const int64_t nwarp = static_cast<int64_t>(gridDim.x)*(blockDim.x >> 5);
+    for (int64_t j = static_cast<int64_t>(blockIdx.x)*(blockDim.x >> 5) + (threadIdx.x >> 5); j < npair;
+         j += nwarp) {
+        const int64_t base = __ldg(&own_off[j]);
+        if (__ldg(&own_off[j + 1]) == base) continue;       // nothing of this pair is ours
+        const int64_t n = __ldg(&A.off_work[j + 1]) - __ldg(&A.off_work[j]);
+        const int s = static_cast<int>(j/A.nev);
+        const int64_t ev = j - static_cast<int64_t>(s)*A.nev;
+        const int mult = (A.lcc == 1 && __ldg(&A.species[s].charge) > 0) ? 2 : 1;
+        const int64_t slot0 = __ldg(&off_out[ev*A.ns + s]);
+        const uint32_t *__restrict__ mw = mask + chunk_mask_word(A.off_work, j);
+        const int64_t nword = (n + 31) >> 5;
+        int64_t running = 0;
+        for (int64_t i0 = 0; i0 < nword; i0 += 32) {
+            const int64_t i = i0 + lane;
+            uint32_t m = (i < nword) ? __ldg(&mw[i]) : 0u;
+            const int c = __popc(m);
+            int incl = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int x = __shfl_up_sync(full, incl, d);
+                if (lane >= d) incl += x;
+            }
+            int64_t r = running + (incl - c);
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1u;
+                ident[base + r] = make_uint4(static_cast<uint32_t>(s), static_cast<uint32_t>(ev),
+                                             static_cast<uint32_t>(32*i + b),
+                                             static_cast<uint32_t>(slot0 + r*mult));
+                r++;
+            }
+            running += __shfl_sync(full, incl, 31);
         }
     }
 }
@@ -1541,19 +1580,24 @@ int run_multiplicities(iss_handle *h, uint64_t seed, int64_t nev) {
 }
 
 // Surface-chunk mode: how many hadrons of the batch are this rank's.  d_off_work holds the scanned
-// work offsets of the WHOLE batch (identical on every rank); on return d_own holds the exclusive
-// prefix over the (species, event) pairs of the owned draws, d_off_out the UNSCANNED per
-// (event, species) output counts of this rank and *n_owned their number.
-static int chunk_count_work(iss_handle *h, const SamplerArgs &A, int64_t nev, int nsm, int64_t *n_owned) {
+// work offsets of the WHOLE batch (identical on every rank); afterwards d_own holds the exclusive
+// prefix over the (species, event) pairs of the owned draws, d_ownmask the ballot words, d_off_out
+// the UNSCANNED per (event, species) output counts of this rank; their number is posted to mail
+// slot 9 (read after the next stream synchronisation).
+static int chunk_count_work(iss_handle *h, const SamplerArgs &A, int64_t nev, int64_t total_work, int nsm) {
     const int64_t npair = nev*h->nspecies;
     int rc = ensure_capacity(h, &h->d_own, &h->own_cap, npair + 1);
     if (rc) return rc;
+    rc = ensure_capacity(h, &h->d_ownmask, &h->ownmask_cap, (total_work >> 5) + npair + 2);
+    if (rc) return rc;
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_own + npair, 0, sizeof(int64_t), h->stream));
     const int64_t grid = std::min<int64_t>((npair + 7)/8, static_cast<int64_t>(nsm)*8);
-    chunk_own_kernel<false><<<static_cast<unsigned>(grid), 256, 0, h->stream>>>(
-        A, h->d_own, h->d_off_out, nullptr, nullptr); ISS_LAUNCHED(h);
+    chunk_own_kernel<<<static_cast<unsigned>(grid), 256, 0, h->stream>>>(A, h->d_own, h->d_off_out,
+                                                                        h->d_ownmask); ISS_LAUNCHED(h);
     ISS_CUDA_TRY(h, cudaGetLastError());
-    return device_exclusive_scan_i64(h, h->d_own, h->d_own, npair, n_owned);
+    rc = device_exclusive_scan_i64(h, h->d_own, h->d_own, npair, nullptr);
+    if (rc) return rc;
+    return mail_post(h, h->d_own + npair, 1, 9);
 }
 
 }  // namespace iss
@@ -1665,16 +1709,16 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
             }
             A.hints = static_cast<const int2 *>(h->d_hints);
         }
-        if (h->chunk && total_work > 0) {
-            int64_t n_owned = 0;
-            rc = chunk_count_work(h, A, nev, nsm, &n_owned);
+        const bool chunk_work = h->chunk && total_work > 0;
+        if (chunk_work) {
+            rc = chunk_count_work(h, A, nev, total_work, nsm);
             if (rc) return rc;
-            A.nwork = n_owned;
-        } else {
-            A.nwork = total_work;
         }
         rc = device_exclusive_scan_i64(h, h->d_off_out, h->d_off_out, n, &total_out);
         if (rc) return rc;
+        // (the scan's synchronisation also delivered the number of owned hadrons)
+        A.nwork = chunk_work ? static_cast<int64_t>(*reinterpret_cast<volatile unsigned long long *>(h->h_mail + 9))
+                             : total_work;
         rc = ensure_mapped_event_offsets(h, nev + 1);
         if (rc) return rc;
         event_offset_kernel<<<static_cast<unsigned>((nev + 1 + 255)/256), 256, 0, h->stream>>>(
@@ -1809,8 +1853,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
             // (d_off_out is scanned by now: the output slots are known)
             const int64_t npair = nev*ns;
             const int64_t cgrid = std::min<int64_t>((npair + 7)/8, static_cast<int64_t>(nsm)*8);
-            chunk_own_kernel<true><<<static_cast<unsigned>(cgrid), 256, 0, h->stream>>>(
-                A, nullptr, h->d_off_out, h->d_own, reinterpret_cast<uint4 *>(h->d_wlist)); ISS_LAUNCHED(h);
+            chunk_fill_kernel<<<static_cast<unsigned>(cgrid), 256, 0, h->stream>>>(
+                A, h->d_own, h->d_off_out, h->d_ownmask, reinterpret_cast<uint4 *>(h->d_wlist)); ISS_LAUNCHED(h);
         }
         // partition of the batch's hadrons by cell block: histogram per segment, exclusive scan, scatter
         const size_t smem_setup = sizeof(DeviceSpecies)*ns + sizeof(int64_t)*(ns + 1)
