@@ -220,10 +220,9 @@ int iss_cuda_destroy(iss_handle *h) {
     cudaFree(h->d_tasks); cudaFree(h->d_sampler_args); cudaFree(h->d_hints);
     cudaFree(h->d_task_slot); cudaFree(h->d_tasks_unsorted);
     cudaFree(h->d_cellcnt); cudaFree(h->d_cellrec);
-    cudaFree(h->d_wire[0]); cudaFree(h->d_wire[1]);
     cudaFree(h->d_counters); cudaFree(h->d_decay_cnt); cudaFree(h->d_scan_tmp);
     cudaFree(h->d_qa); cudaFree(h->d_trace);
-    cudaFree(h->d_own); cudaFree(h->d_wlist); cudaFree(h->d_ownmask); cudaFree(h->d_tilesum_all);
+    cudaFree(h->d_qa_scratch); cudaFree(h->d_own); cudaFree(h->d_wlist); cudaFree(h->d_ownmask); cudaFree(h->d_tilesum_all);
     cudaFree(h->d_legpos); cudaFree(h->d_legcoef); cudaFree(h->d_zx); cudaFree(h->d_zy);
     cudaFree(h->d_lambert); cudaFree(h->d_legmax); cudaFree(h->d_bulk0);
     if (h->h_mail) cudaFreeHost(h->h_mail);

@@ -198,10 +198,6 @@ struct iss_handle {
     unsigned long long *d_cellcnt = nullptr; size_t cellcnt_bytes = 0;  // [ncell + 2] histogram / offsets
     void *d_cellrec = nullptr; size_t cellrec_bytes = 0; // [ncell] CellRec (sampler.cu)
     bool cellrec_valid = false;                          // reset with the yields
-    // 20-byte wire records beside the full ones (iss_cuda_set_wire_records), double-buffered like them
-    bool wire_on = false;
-    uint32_t *d_wire[2] = {nullptr, nullptr};
-    int64_t wire_cap[2] = {0, 0};
     unsigned long long *d_counters = nullptr;   // [8] tries, redraws, error flags...
     bool have_batch = false;
     bool trace = false;
@@ -225,6 +221,7 @@ struct iss_handle {
 
     // QA
     double *d_qa = nullptr;
+    double *d_qa_scratch = nullptr; size_t qa_scratch_bytes = 0;   // per-CTA FP64 sums of the QA kernel
     // communicator made by iss_cuda_nccl_init (collective.cu); null: single rank
     void *nccl_comm = nullptr;
     int nccl_rank = 0, nccl_nranks = 0;

@@ -21,10 +21,16 @@ struct QaArgs {
     const iss_decay_species *dsp;
     int ndsp;
     double *qa;
+    double *scratch;        // [gridDim.x][QA_SCRATCH] zeroed: per-CTA FP64 sums (pT per bin, v2 numerators)
 };
 
 constexpr int QA_THREADS = 256;
 constexpr int QA_HASH_BITS = 11, QA_HASH = 1 << QA_HASH_BITS;
+// FP64 sums per (tracked species, bin).  Shared memory has no native FP64 add (a compare-and-swap
+// loop: a third of the kernel's stall samples when these sums lived there), global memory has one
+// that needs no answer (RED.ADD.F64 at the L2): every CTA adds into its own L2-resident block and
+// folds it into the QA block at the end.
+constexpr int QA_SCRATCH = ISS_QA_NSPEC*(ISS_QA_NPT + ISS_QA_NV2);
 
 __device__ __forceinline__ double block_sum(double v, double *red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -49,8 +55,6 @@ struct QaShared {
     unsigned int y_cnt[ISS_QA_NSPEC][ISS_QA_NY];
     unsigned int phi_cnt[ISS_QA_NSPEC][ISS_QA_NPHI];
     unsigned int v2_den[ISS_QA_NSPEC][ISS_QA_NV2];
-    double pt_sum[ISS_QA_NSPEC][ISS_QA_NPT];
-    double v2_num[ISS_QA_NSPEC][ISS_QA_NV2];
     double red[QA_THREADS/32];
     // bin edges of the rapidity and azimuth histograms as the quantities the bins are decided on:
     // sinh(y_i) (compared with p_z/m_T) and the unit vectors of the sector boundaries (sign of a
@@ -98,6 +102,8 @@ qa_kernel(const QaArgs A) {
     extern __shared__ __align__(16) unsigned char qa_smem[];
     QaShared &S = *reinterpret_cast<QaShared *>(qa_smem);
     double *qa = A.qa;
+    double *my_pt_sum = A.scratch + static_cast<int64_t>(blockIdx.x)*QA_SCRATCH;    // [NSPEC][NPT]
+    double *my_v2_num = my_pt_sum + ISS_QA_NSPEC*ISS_QA_NPT;                        // [NSPEC][NV2]
     for (int i = threadIdx.x; i < static_cast<int>(sizeof(QaShared)/4); i += blockDim.x)
         reinterpret_cast<unsigned int *>(qa_smem)[i] = 0u;
     __syncthreads();
@@ -180,7 +186,7 @@ qa_kernel(const QaArgs A) {
                 const int ib = static_cast<int>(pT/bw);
                 if (ib >= 0 && ib < ISS_QA_NPT) {
                     atomicAdd(&S.pt_evt[k][ib], 1);
-                    atomicAdd(&S.pt_sum[k][ib], pT);
+                    atomicAdd(&my_pt_sum[k*ISS_QA_NPT + ib], pT);
                 }
                 const double mT2 = static_cast<double>(hd.mass)*hd.mass + pT*pT;
                 // iy = floor((asinh(pz/mT) + 5)/0.1): float estimate, made exact against the
@@ -210,7 +216,7 @@ qa_kernel(const QaArgs A) {
                     const double c2 = (pT > 0.) ? (static_cast<double>(hd.px)*hd.px
                                                    - static_cast<double>(hd.py)*hd.py)/(pT*pT)
                                                 : 0.;
-                    atomicAdd(&S.v2_num[k][iv], c2);
+                    atomicAdd(&my_v2_num[k*ISS_QA_NV2 + iv], c2);
                     atomicAdd(&S.v2_den[k][iv], 1u);
                 }
                 atomicAdd(&S.n_evt[k], 1);
@@ -268,13 +274,15 @@ qa_kernel(const QaArgs A) {
         atomicAdd(&qa[0], static_cast<double>(n_evt_done));
         atomicAdd(&qa[25], static_cast<double>(n_had));
     }
+    // (the CTA's own reductions at the L2 are complete before it reads them back, past the L1)
+    __threadfence();
     __syncthreads();
     for (int k = 0; k < A.npid; k++) {
         double *blk = qa + ISS_QA_HEAD + static_cast<int64_t>(k)*ISS_QA_PER;
         for (int i = threadIdx.x; i < ISS_QA_NPT; i += blockDim.x) {
             if (S.pt_cnt[k][i]) {
                 atomicAdd(&blk[i], static_cast<double>(S.pt_cnt[k][i]));
-                atomicAdd(&blk[ISS_QA_NPT + i], S.pt_sum[k][i]);
+                atomicAdd(&blk[ISS_QA_NPT + i], __ldcg(&my_pt_sum[k*ISS_QA_NPT + i]));
                 atomicAdd(&blk[2*ISS_QA_NPT + i], static_cast<double>(S.pt_sq[k][i]));
             }
         }
@@ -285,7 +293,8 @@ qa_kernel(const QaArgs A) {
                 atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + i], static_cast<double>(S.phi_cnt[k][i]));
         for (int i = threadIdx.x; i < ISS_QA_NV2; i += blockDim.x)
             if (S.v2_den[k][i]) {
-                atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + i], S.v2_num[k][i]);
+                atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + i],
+                          __ldcg(&my_v2_num[k*ISS_QA_NV2 + i]));
                 atomicAdd(&blk[3*ISS_QA_NPT + ISS_QA_NY + ISS_QA_NPHI + ISS_QA_NV2 + i],
                           static_cast<double>(S.v2_den[k][i]));
             }
@@ -322,6 +331,10 @@ int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate) {
                                          static_cast<int>(smem)));
     int64_t grid = std::min<int64_t>(A.nev, static_cast<int64_t>(nsm)*2);
     if (grid < 1) grid = 1;
+    ISS_ENSURE(h, h->d_qa_scratch, h->qa_scratch_bytes, sizeof(double)*QA_SCRATCH*static_cast<size_t>(nsm)*2);
+    ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_qa_scratch, 0, sizeof(double)*QA_SCRATCH*static_cast<size_t>(grid),
+                                    h->stream));
+    A.scratch = h->d_qa_scratch;
     {
         ScopedTimer t(h, ISS_T_QA);
         qa_kernel<<<static_cast<unsigned>(grid), QA_THREADS, smem, h->stream>>>(A); ISS_LAUNCHED(h);

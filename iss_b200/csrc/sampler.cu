@@ -300,7 +300,6 @@ struct SamplerArgs {
     int64_t nseg;                   // segments of the batch
     Task32 *tasks;                  // [nstage*RING_TASKS] cell-sorted task list
     uint32_t *task_slot;            // surface-chunk mode only: output slot of every sorted task
-    uint32_t *wire;                 // optional [n_out][5]: 20-byte wire records (iss_wire_hadron)
     unsigned long long *giveup_info;    // [2] (cell, species) of a hadron the sampler gave up on
     int mt_smem;                    // regime-0 tables were generated on the device (uniform abscissa)
     const int2 *hints;              // [ceil(nwork/SETUP_THREADS)] (species, event) of item b*SETUP_THREADS
@@ -1387,16 +1386,6 @@ propose_kernel(const SamplerArgs A, const SamplerArgs *Ag) {
                     dst[2] = make_float2(hd.py, hd.pz);
                     dst[3] = make_float2(hd.t, hd.x);
                     dst[4] = make_float2(hd.y, hd.z);
-                    if (A.wire) {
-                        // 20-byte wire record (include/iss_cuda.h, iss_wire_hadron): species and
-                        // position follow from the slot and the cell
-                        uint32_t *wr = A.wire + 5ull*L.slot;
-                        wr[0] = static_cast<uint32_t>(L.cell + A.cell_begin);
-                        wr[1] = __float_as_uint(hd.px);
-                        wr[2] = __float_as_uint(hd.py);
-                        wr[3] = __float_as_uint(hd.pz);
-                        wr[4] = __float_as_uint(hd.E);
-                    }
                     if (A.trace_cell) {
                         A.trace_cell[L.slot] = L.cell;
                         A.trace_tries[L.slot] = L.total_tries;
@@ -1686,7 +1675,6 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.nbucket = 1;
     A.nseg = 0;
     A.cellrec = nullptr;
-    A.wire = nullptr;
     A.giveup_info = nullptr;
     A.mt_smem = 0;
     A.out = nullptr;
@@ -1834,13 +1822,6 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     A.cellrec = static_cast<const CellRec *>(h->d_cellrec);
     A.giveup_info = h->d_counters + 8;
     A.mt_smem = (h->momtab[0].generated && h->momtab[3].generated) ? 1 : 0;
-    A.wire = nullptr;
-    if (h->wire_on) {
-        const int b = h->cur_buf;
-        rc = ensure_capacity(h, &h->d_wire[b], &h->wire_cap[b], 5*total_out);
-        if (rc) return rc;
-        A.wire = h->d_wire[b];
-    }
     if (!h->d_sampler_args) ISS_CUDA_TRY(h, cudaMalloc(&h->d_sampler_args, sizeof(SamplerArgs)));
     ISS_CUDA_TRY(h, cudaMemcpyAsync(h->d_sampler_args, &A, sizeof(SamplerArgs), cudaMemcpyHostToDevice,
                                     h->stream));
