@@ -25,6 +25,7 @@ struct QaArgs {
 };
 
 constexpr int QA_THREADS = 256;
+constexpr int QA_CTAS_PER_SM = 3;       // 85 registers per thread, 69 KB of shared memory per CTA
 constexpr int QA_HASH_BITS = 11, QA_HASH = 1 << QA_HASH_BITS;
 // FP64 sums per (tracked species, bin).  Shared memory has no native FP64 add (a compare-and-swap
 // loop: a third of the kernel's stall samples when these sums lived there), global memory has one
@@ -56,6 +57,8 @@ struct QaShared {
     unsigned int phi_cnt[ISS_QA_NSPEC][ISS_QA_NPHI];
     unsigned int v2_den[ISS_QA_NSPEC][ISS_QA_NV2];
     double red[QA_THREADS/32];
+    double P1[4], P2[4];        // sum over this CTA's events of P^mu and of its square (thread 0)
+    long long n_had, n_evt_done;
     // bin edges of the rapidity and azimuth histograms as the quantities the bins are decided on:
     // sinh(y_i) (compared with p_z/m_T) and the unit vectors of the sector boundaries (sign of a
     // cross product), so that no asinh / atan2 in double precision is needed per hadron
@@ -97,7 +100,7 @@ __device__ __forceinline__ int qa_hash_find(const QaShared &S, int pid) {
     }
 }
 
-__global__ void __launch_bounds__(QA_THREADS)
+__global__ void __launch_bounds__(QA_THREADS, QA_CTAS_PER_SM)
 qa_kernel(const QaArgs A) {
     extern __shared__ __align__(16) unsigned char qa_smem[];
     QaShared &S = *reinterpret_cast<QaShared *>(qa_smem);
@@ -131,8 +134,6 @@ qa_kernel(const QaArgs A) {
 #pragma unroll
     for (int i = 0; i < 16; i++) T[i] = 0.;
     double net[3] = {0., 0., 0.};
-    double P1[4] = {0., 0., 0., 0.}, P2[4] = {0., 0., 0., 0.};   // thread 0: sum_ev P, sum_ev P^2
-    long long n_had = 0, n_evt_done = 0;
     int last_pid = 0, last_k = -1;
     double last_q[3] = {0., 0., 0.};
 
@@ -226,8 +227,8 @@ qa_kernel(const QaArgs A) {
         for (int a = 0; a < 4; a++) {
             const double t = block_sum(P[a], S.red);
             if (threadIdx.x == 0) {
-                P1[a] += t;
-                P2[a] += t*t;
+                S.P1[a] += t;
+                S.P2[a] += t*t;
             }
         }
         __syncthreads();
@@ -247,8 +248,8 @@ qa_kernel(const QaArgs A) {
             S.n_evt[threadIdx.x] = 0;
         }
         if (threadIdx.x == 0) {
-            n_had += e - b;
-            n_evt_done++;
+            S.n_had += e - b;
+            S.n_evt_done++;
         }
         __syncthreads();
     }
@@ -266,13 +267,13 @@ qa_kernel(const QaArgs A) {
         const double t = block_sum(net[a], S.red);
         if (threadIdx.x == 0 && t != 0.) atomicAdd(&qa[26 + a], t);
     }
-    if (threadIdx.x == 0 && n_evt_done > 0) {
+    if (threadIdx.x == 0 && S.n_evt_done > 0) {
         for (int a = 0; a < 4; a++) {
-            atomicAdd(&qa[1 + a], P1[a]);
-            atomicAdd(&qa[5 + a], P2[a]);
+            atomicAdd(&qa[1 + a], S.P1[a]);
+            atomicAdd(&qa[5 + a], S.P2[a]);
         }
-        atomicAdd(&qa[0], static_cast<double>(n_evt_done));
-        atomicAdd(&qa[25], static_cast<double>(n_had));
+        atomicAdd(&qa[0], static_cast<double>(S.n_evt_done));
+        atomicAdd(&qa[25], static_cast<double>(S.n_had));
     }
     // (the CTA's own reductions at the L2 are complete before it reads them back, past the L1)
     __threadfence();
@@ -329,9 +330,9 @@ int run_qa(iss_handle *h, const int32_t *pids, int npid, int accumulate) {
     // per device and cheap: set on every call (a process may drive several devices)
     ISS_CUDA_TRY(h, cudaFuncSetAttribute(qa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem)));
-    int64_t grid = std::min<int64_t>(A.nev, static_cast<int64_t>(nsm)*2);
+    int64_t grid = std::min<int64_t>(A.nev, static_cast<int64_t>(nsm)*QA_CTAS_PER_SM);
     if (grid < 1) grid = 1;
-    ISS_ENSURE(h, h->d_qa_scratch, h->qa_scratch_bytes, sizeof(double)*QA_SCRATCH*static_cast<size_t>(nsm)*2);
+    ISS_ENSURE(h, h->d_qa_scratch, h->qa_scratch_bytes, sizeof(double)*QA_SCRATCH*static_cast<size_t>(nsm)*QA_CTAS_PER_SM);
     ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_qa_scratch, 0, sizeof(double)*QA_SCRATCH*static_cast<size_t>(grid),
                                     h->stream));
     A.scratch = h->d_qa_scratch;
