@@ -202,6 +202,40 @@ def overrides_of(workload):
     return dict(OVERRIDES, **WORKLOADS[workload]["over"])
 
 
+def d2h_link_probe(torch, dist, world, barrier, nbytes=1 << 29, reps=3):
+    """Pinned device->host bandwidth of this rank's GPU with all ranks copying at the same time (the
+    ceiling of the end-to-end figure), and the PCIe link state nvidia-smi reports."""
+    out = {}
+    try:
+        dev = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        dev.fill_(1)
+        host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        host.copy_(dev)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            host.copy_(dev, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, nbytes/(time.perf_counter() - t0)/1e9)
+        t = torch.tensor([best], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        out["gbs_per_rank_all_ranks_busy"] = float(t.item())
+        del dev, host
+    except Exception as exc:
+        out["error"] = "%s: %s" % (type(exc).__name__, exc)
+    try:
+        q = subprocess.run(["nvidia-smi", "--query-gpu=pcie.link.gen.current,pcie.link.width.current",
+                            "--format=csv,noheader", "-i", str(torch.cuda.current_device())],
+                           capture_output=True, text=True, timeout=10).stdout.strip()
+        out["pcie_gen_width"] = q
+    except Exception:
+        pass
+    return out
+
+
 def workload_name(ncell, events, workload="c4"):
     return (WORKLOADS[workload]["label"] % ncell
             + "; step = yields of all cells x species + CDF + multiplicities + %d sampled events"
@@ -389,6 +423,7 @@ def run_engine(args):
         h2d = ncell*28*4 + table_bytes
         d2h = int(e2e_hadrons/e2e_steps)*40 + (E + 1)*8
         s.close()
+        link = d2h_link_probe(torch, dist, world, barrier)
         spectra = None
         if world == 1 and not args.no_spectra:
             try:
@@ -463,7 +498,12 @@ def run_engine(args):
         "roofline": roof, "roofline_yields": roof_y,
         "e2e": {"value": e2e_value, "unit": "hadrons/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                "call": "iSS::generate_samples() (class iSS facade, host surface -> host hadron lists)"},
+                "call": "iSS::generate_samples() (class iSS facade, host surface -> host hadron lists)",
+                # what bounds this figure: the device->host copy of the 40-byte records of a step over
+                # THIS box's link (measured right after the timed calls; the boxes of the pool differ)
+                "d2h_link": dict(link, floor_ms_per_call=(d2h/(link["gbs_per_rank_all_ranks_busy"]*1e9)*1e3
+                                                          if link.get("gbs_per_rank_all_ranks_busy") else None),
+                                 measured_ms_per_call=float(te.item())/e2e_steps*1e3)},
         "gpu_launches": launches,
         "ms_per_step_per_rank": ms_per_rank,
         "clocks": clk,

@@ -154,6 +154,35 @@ def test_chunk_mode_with_charge_pairing_and_qa(surf):
         e.compute_yields()
 
 
+def test_allgather_entry_point_and_block_yields(surf):
+    """iss_cuda_chunk_yields_allgather with one rank (no communicator needed: the same code path minus
+    the NCCL call; the multi-rank case runs under torchrun, tests/test_multigpu_gpu.py) and
+    iss_cuda_chunk_block_yields, the input of sharding.split_cells_weighted"""
+    capi, s, lrf = surf
+    e = s.engine()
+    ref = whole_run(e, lrf)
+    try:
+        e.upload_surface(lrf)
+        e.set_surface_chunk(0, len(lrf))
+        dN = e.chunk_yields_allgather([sharding.ntiles_of((0, len(lrf)))])
+        assert np.array_equal(dN, ref["dN"])
+        by = e.chunk_block_yields(len(lrf))
+        blk = np.add.reduceat(ref["y"].sum(axis=0), np.arange(0, len(lrf), sharding.CHUNK_ALIGN))
+        assert len(by) == len(blk)
+        np.testing.assert_allclose(by, blk, rtol=1e-10)
+        cut = sharding.split_cells_weighted(by, len(lrf), 3)
+        assert cut[0][0] == 0 and cut[-1][1] == len(lrf) and all(b < en for b, en in cut)
+        e.set_trace(True)
+        c = e.sample(SEED, EV0, EV0 + NEV)
+        assert c.n_hadrons == len(ref["had"])
+        assert e.fetch_all().tobytes() == ref["had"].tobytes()
+        with pytest.raises(capi.IssError):
+            e.chunk_yields_allgather([3, 4])                # two ranks, no communicator
+    finally:
+        e.upload_surface(lrf)
+        e.compute_yields()
+
+
 def test_chunk_argument_checks(surf):
     capi, s, lrf = surf
     e = s.engine()
