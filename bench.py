@@ -522,7 +522,7 @@ def run_engine(args):
             "primaries_per_sec": decay_counts[0]/dec_s,
             "fp64": {"achieved_tflops": FLOP_PER_DECAY*decay_counts[1]/dec_s/1e12, "peak_tflops": fp64_peak,
                      "frac": FLOP_PER_DECAY*decay_counts[1]/dec_s/1e12/fp64_peak},
-            "note": "latency bound: one thread walks one primary's decay tree twice (count, write)"}
+            "note": "latency and divergence bound (18 of 32 lanes): one thread walks one primary's decay tree, first as a tree of species only (count pass: channel picks and the three-body energy rejection, the other random numbers skipped), then with the kinematics (write pass)"}
     if rank == 0:
         cb = None
         if world == 1 and not args.no_cpu_baseline:

@@ -6,7 +6,11 @@
 // whole decay tree depth-first with a small stack; the walk is run twice with the
 // same Philox stream (count pass, then write pass after an integer prefix sum), so
 // no intermediate lists are materialised and the output is a pure function of
-// (seed, event, index of the primary inside its event).
+// (seed, event, index of the primary inside its event).  The count pass walks the tree
+// of SPECIES only: which channel is taken depends on the random numbers and on pole
+// masses, never on momenta, so it draws the channel, runs the three-body energy
+// rejection (the one place where the number of random numbers consumed varies) and
+// skips the numbers of the angles and of the life time without generating them.
 //
 // Reference semantics kept: pole masses (no Breit-Wigner), float mother fields,
 // channel pick by cumulative branching ratio, only 2- and 3-body channels emit
@@ -20,6 +24,7 @@
 namespace iss {
 
 constexpr int DECAY_STACK = 24;
+constexpr int DECAY_THREADS = 128;
 
 struct DecayArgs {
     const iss_hadron *in;
@@ -42,14 +47,23 @@ struct Part {
     int idx;            // row in dsp
     float mass, E, px, py, pz, t, x, y, z;
 };
+struct PartSpecies {    // what the count pass keeps of a particle
+    int idx;
+    float mass;
+};
+template <bool WRITE> struct PartOf { typedef Part type; };
+template <> struct PartOf<false> { typedef PartSpecies type; };
 
-__device__ __forceinline__ int find_pid(const DecayArgs &A, int pid) {
-    int lo = 0, hi = A.ndsp - 1;
+// row of a pid in the particle table: bisection of the CTA's shared-memory copy of the sorted
+// (pid, row) pairs (the same search through global memory was a chain of nine dependent loads, the
+// first stall of both passes)
+__device__ __forceinline__ int find_pid(const int2 *__restrict__ pid_row, int n, int pid) {
+    int lo = 0, hi = n - 1;
     while (lo <= hi) {
         const int mid = (lo + hi) >> 1;
-        const int v = __ldg(&A.sorted_pid[mid]);
-        if (v == pid) return __ldg(&A.sorted_idx[mid]);
-        if (v < pid) lo = mid + 1; else hi = mid - 1;
+        const int2 v = pid_row[mid];
+        if (v.x == pid) return v.y;
+        if (v.x < pid) lo = mid + 1; else hi = mid - 1;
     }
     return -1;
 }
@@ -67,17 +81,28 @@ __device__ __forceinline__ void boost_daughter(Part &d, double E_lrf, double px,
 }
 
 template <bool WRITE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(DECAY_THREADS)
 decay_kernel(const DecayArgs A) {
-    const int64_t i = static_cast<int64_t>(blockIdx.x)*blockDim.x + threadIdx.x;
-    if (i >= A.n_in) return;
-    // event of this primary (binary search in the event offsets) -> RNG key
-    int64_t lo = 0, hi = A.nev;
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (__ldg(&A.event_off_in[mid]) <= i) lo = mid; else hi = mid;
+    extern __shared__ int2 pid_row[];       // [ndsp] sorted by pid
+    __shared__ long long ev_first;          // event of the CTA's first primary
+    for (int j = threadIdx.x; j < A.ndsp; j += DECAY_THREADS)
+        pid_row[j] = make_int2(__ldg(&A.sorted_pid[j]), __ldg(&A.sorted_idx[j]));
+    if (threadIdx.x == 0) {
+        // one bisection of the event offsets per CTA; its primaries are consecutive, so every
+        // thread finds its own event a step or two further on
+        const int64_t i0 = static_cast<int64_t>(blockIdx.x)*DECAY_THREADS;
+        int64_t lo = 0, hi = A.nev;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(&A.event_off_in[mid]) <= i0) lo = mid; else hi = mid;
+        }
+        ev_first = lo;
     }
-    const int64_t ev = lo;
+    __syncthreads();
+    const int64_t i = static_cast<int64_t>(blockIdx.x)*DECAY_THREADS + threadIdx.x;
+    if (i >= A.n_in) return;
+    int64_t ev = ev_first;
+    while (ev + 1 < A.nev && __ldg(&A.event_off_in[ev + 1]) <= i) ev++;
     const int64_t k = i - __ldg(&A.event_off_in[ev]);
     Stream rng;
     // (surface-chunk mode: k counts the rank's primaries of the event; the chunk id keeps the
@@ -85,16 +110,20 @@ decay_kernel(const DecayArgs A) {
     rng.init(A.seed, STREAM_DECAY, A.chunk_id, static_cast<uint32_t>(A.ev_begin + ev),
              static_cast<uint32_t>(k));
 
+    typedef typename PartOf<WRITE>::type P;
     const iss_hadron h0 = A.in[i];
-    Part stack[DECAY_STACK];
+    P stack[DECAY_STACK];
     int sp = 0;
     int64_t nout = 0;
     int64_t wpos = WRITE ? A.count[i] : 0;
     {
-        Part p;
-        p.idx = find_pid(A, h0.pid);
-        p.mass = h0.mass; p.E = h0.E; p.px = h0.px; p.py = h0.py; p.pz = h0.pz;
-        p.t = h0.t; p.x = h0.x; p.y = h0.y; p.z = h0.z;
+        P p;
+        p.idx = find_pid(pid_row, A.ndsp, h0.pid);
+        p.mass = h0.mass;
+        if constexpr (WRITE) {
+            p.E = h0.E; p.px = h0.px; p.py = h0.py; p.pz = h0.pz;
+            p.t = h0.t; p.x = h0.x; p.y = h0.y; p.z = h0.z;
+        }
         if (p.idx < 0) {
             // not in the decay table (cannot happen for species taken from the same pdg file):
             // keep it as it is
@@ -105,10 +134,10 @@ decay_kernel(const DecayArgs A) {
         stack[sp++] = p;
     }
     while (sp > 0) {
-        const Part m = stack[--sp];
+        const P m = stack[--sp];
         const iss_decay_species ms = A.dsp[m.idx];
         if (ms.stable == 1) {
-            if (WRITE) {
+            if constexpr (WRITE) {
                 iss_hadron o;
                 o.pid = ms.pid; o.mass = m.mass; o.E = m.E; o.px = m.px; o.py = m.py; o.pz = m.pz;
                 o.t = m.t; o.x = m.x; o.y = m.y; o.z = m.z;
@@ -133,11 +162,45 @@ decay_kernel(const DecayArgs A) {
         bool bad = false;
         for (int d = 0; d < ch.n_part; d++) bad |= (ch.daughter[d] < 0);
         if (bad || sp + ch.n_part > DECAY_STACK) {
-            atomicAdd(&A.errors[bad ? 1 : 0], 1ull);
+            if (WRITE) atomicAdd(&A.errors[bad ? 1 : 0], 1ull);     // (both passes take the same path)
             continue;
         }
         const double M = m.mass;            // float pole mass, as iSS_Hadron stores it
         const double width = ms.width;
+        if constexpr (!WRITE) {
+            // species and random-number bookkeeping of the same decay (see the header)
+            P d[3];
+            for (int q = 0; q < ch.n_part; q++) {
+                d[q].idx = ch.daughter[q];
+                d[q].mass = static_cast<float>(A.dsp[d[q].idx].mass);
+            }
+            if (ch.n_part == 2) {
+                if (M < static_cast<double>(d[0].mass) + static_cast<double>(d[1].mass)) continue;
+                rng.skip(2 + (width > 1e-10 ? 1 : 0));      // phi, cos(theta), life time
+                stack[sp++] = d[1];
+                stack[sp++] = d[0];
+            } else {
+                const double m1 = d[0].mass, m2 = d[1].mass, m3 = d[2].mass;
+                if (M < m1 + m2 + m3) continue;
+                const double range = M - m1 - m2 - m3;
+                double E1, E2, E3, p1, p2, cos12;
+                int guard = 0;
+                do {
+                    do {
+                        E1 = rng.next()*range + m1;
+                        E2 = rng.next()*range + m2;
+                    } while (E1 + E2 > M);
+                    p1 = sqrt(E1*E1 - m1*m1);
+                    p2 = sqrt(E2*E2 - m2*m2);
+                    E3 = M - E1 - E2;
+                    cos12 = (E3*E3 - p1*p1 - p2*p2 - m3*m3)/(2.*p1*p2);
+                } while ((cos12 < -1.0 || cos12 > 1.0) && ++guard < 100000);
+                rng.skip((width > 1e-10 ? 1 : 0) + 3);      // life time, phi, ksi, cos(theta)
+                stack[sp++] = d[2];
+                stack[sp++] = d[1];
+                stack[sp++] = d[0];
+            }
+        } else {
         // mother velocity: float divisions (particle_decay.cpp:382-384)
         const double vx = __fdiv_rn(m.px, m.E), vy = __fdiv_rn(m.py, m.E), vz = __fdiv_rn(m.pz, m.E);
         const double v2 = vx*vx + vy*vy + vz*vz;
@@ -249,6 +312,7 @@ decay_kernel(const DecayArgs A) {
             stack[sp++] = d2;
             stack[sp++] = d1;
         }
+        }   // WRITE
     }
     if (!WRITE) A.count[i] = nout;
 }
@@ -295,12 +359,14 @@ int run_decay(iss_handle *h, uint64_t seed) {
     A.out = nullptr;
     A.errors = h->d_counters + 4;
 
-    const unsigned grid = static_cast<unsigned>((n_in + 127)/128);
+    const unsigned grid = static_cast<unsigned>((n_in + DECAY_THREADS - 1)/DECAY_THREADS);
+    const size_t smem = sizeof(int2)*static_cast<size_t>(h->ndsp);
+    if (smem > 40*1024) ISS_FAIL(h, ISS_ERR_ARG, "particle table too large for the decay kernel's pid table");
     int64_t total = 0;
     {
         ScopedTimer t(h, ISS_T_DECAY);
         ISS_CUDA_TRY(h, cudaMemsetAsync(h->d_decay_cnt + n_in, 0, sizeof(int64_t), h->stream));
-        decay_kernel<false><<<grid, 128, 0, h->stream>>>(A); ISS_LAUNCHED(h);
+        decay_kernel<false><<<grid, DECAY_THREADS, smem, h->stream>>>(A); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
         rc = device_exclusive_scan_i64(h, h->d_decay_cnt, h->d_decay_cnt, n_in, &total);
         if (rc) return rc;
@@ -311,7 +377,7 @@ int run_decay(iss_handle *h, uint64_t seed) {
         rc = ensure_capacity(h, &h->d_hadrons2, &h->hadron2_cap, total);
         if (rc) return rc;
         A.out = h->d_hadrons2;
-        decay_kernel<true><<<grid, 128, 0, h->stream>>>(A); ISS_LAUNCHED(h);
+        decay_kernel<true><<<grid, DECAY_THREADS, smem, h->stream>>>(A); ISS_LAUNCHED(h);
         ISS_CUDA_TRY(h, cudaGetLastError());
         // new per-event offsets (into a scratch area behind the counts, then copied over)
         int64_t *tmp = h->d_decay_cnt + n_in + 1;

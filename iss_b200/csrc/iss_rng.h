@@ -120,6 +120,21 @@ struct Stream {
         return u53(hi, lo);
     }
     ISS_HD double next32() { return u32(word()); }
+    // the state after n calls of next() whose values nobody needs (whole blocks are not generated)
+    ISS_HD void skip(int n) {
+        int w = 2*n - (4 - pos);        // words beyond the buffered ones
+        if (w <= 0) {
+            pos += 2*n;
+            return;
+        }
+        ctr[0] += static_cast<uint32_t>(w >> 2);
+        pos = 4;
+        if (w & 3) {
+            philox4x32_10(ctr, key, buf);
+            ctr[0]++;
+            pos = w & 3;
+        }
+    }
 };
 
 // Block-granular view of the same streams, used by the sampler kernel: every random decision
