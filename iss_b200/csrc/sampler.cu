@@ -987,15 +987,16 @@ __device__ __noinline__ void lane_new_setup(const SamplerArgs *Ag, ColdIO *io, d
 //   1: 3+1D, Chapman-Enskog (kind 21) shear + bulk + baryon diffusion, no charge pairing
 //   2: 3+1D, Chapman-Enskog (kind 21) shear + bulk, no diffusion, no charge pairing
 //   3: 3+1D, no delta f, no charge pairing
+//   4: boost-invariant (2+1D), CE shear + bulk, no charge pairing (BASELINE.json configs[2])
 template <int SPEC>
 struct SpecMode {
     static constexpr bool generic = (SPEC == 0);
-    static constexpr int shear = (SPEC == 1 || SPEC == 2) ? 1 : 0;
-    static constexpr int bulk = (SPEC == 1 || SPEC == 2) ? 1 : 0;
+    static constexpr int shear = (SPEC == 1 || SPEC == 2 || SPEC == 4) ? 1 : 0;
+    static constexpr int bulk = (SPEC == 1 || SPEC == 2 || SPEC == 4) ? 1 : 0;
     static constexpr int diff = (SPEC == 1) ? 1 : 0;
     static constexpr int kind = 21;
     static constexpr int neos = (SPEC == 3) ? -1 : 1;
-    static constexpr int hydro_mode = 2;
+    static constexpr int hydro_mode = (SPEC == 4) ? 1 : 2;
     static constexpr int lcc = 0;
 };
 
@@ -1864,6 +1865,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
         else if (A.mode.include_shear != 1 && A.mode.include_bulk != 1 && A.mode.include_diff != 1
                  && A.mode.kind != 20 && A.mode.kind != 21) spec = 3;
     }
+    if (A.hydro_mode != 2 && A.lcc != 1 && A.mode.kind == 21 && A.mode.include_shear == 1
+        && A.mode.include_bulk == 1 && A.mode.include_diff != 1) spec = 4;
     static int force_generic = -1;
     if (force_generic < 0) {
         const char *e = getenv("ISS_SAMPLER_GENERIC");
@@ -1875,7 +1878,8 @@ int run_sampler(iss_handle *h, uint64_t seed, int64_t nev, int64_t /*unused*/) {
     int nthreads = SAMPLER_THREADS;
     void (*kern)(const SamplerArgs, const SamplerArgs *) =
         spec == 1 ? propose_kernel<SAMPLER_THREADS, 1> : spec == 2 ? propose_kernel<SAMPLER_THREADS, 2>
-        : spec == 3 ? propose_kernel<SAMPLER_THREADS, 3> : propose_kernel<SAMPLER_THREADS, 0>;
+        : spec == 3 ? propose_kernel<SAMPLER_THREADS, 3> : spec == 4 ? propose_kernel<SAMPLER_THREADS, 4>
+        : propose_kernel<SAMPLER_THREADS, 0>;
     static int tune_threads = -1;
     if (tune_threads < 0) {
         const char *e = getenv("ISS_SAMPLER_THREADS");
