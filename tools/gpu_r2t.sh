@@ -1,5 +1,7 @@
 #!/bin/bash
-# round 2, call T: variants of the cell search of setup_kernel (ISS_SETUP_TUNE), parity + timing
+# round 2, call T: variants of the cell search of setup_kernel (ISS_SETUP_TUNE), parity + timing.
+# Kept for the record: all variants were slower (history) and were removed from
+# sampler.cu after this call, so ISS_SETUP_TUNE has no effect on the committed code.
 mkdir -p gpurun_out
 for t in 4 5; do
 ISS_SETUP_TUNE=$t timeout 600 python -m pytest tests/test_sampler_gpu.py tests/test_chunk_gpu.py -q -x > gpurun_out/t_pytest_$t.txt 2>&1
