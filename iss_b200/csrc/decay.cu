@@ -25,6 +25,10 @@ namespace iss {
 
 constexpr int DECAY_STACK = 24;
 constexpr int DECAY_THREADS = 128;
+// both passes wait on loads and on their divergent lanes; resident warps hide it better than registers
+// do (64 / 48 registers with spills into the L1: 4.96 ms at 4 / 5 CTAs -> 4.62 (5 / 6) -> 4.29 (6 / 8) ->
+// 4.13 (8 / 10) -> 4.21 (10 / 12) on the C3 + decays step)
+constexpr int DECAY_CTAS_WRITE = 8, DECAY_CTAS_COUNT = 10;
 
 struct DecayArgs {
     const iss_hadron *in;
@@ -81,7 +85,7 @@ __device__ __forceinline__ void boost_daughter(Part &d, double E_lrf, double px,
 }
 
 template <bool WRITE>
-__global__ void __launch_bounds__(DECAY_THREADS)
+__global__ void __launch_bounds__(DECAY_THREADS, WRITE ? DECAY_CTAS_WRITE : DECAY_CTAS_COUNT)
 decay_kernel(const DecayArgs A) {
     extern __shared__ int2 pid_row[];       // [ndsp] sorted by pid
     __shared__ long long ev_first;          // event of the CTA's first primary
