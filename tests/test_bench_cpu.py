@@ -39,3 +39,46 @@ def test_reference_arm_on_other_ranks_exits_quietly():
                        cwd=REPO, env=env)
     assert r.returncode == 0
     assert r.stdout.strip() == ""
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+NO_GPU_FACADE = """
+import sys, tempfile
+sys.path.insert(0, %(repo)r); sys.path.insert(0, %(tests)r)
+import cases
+from iss_b200 import capi
+g = cases.load(cases.ONE_CELL[0])
+d = tempfile.mkdtemp()
+param, surf, over = cases.materialise(g, d)
+over.update(number_of_repeated_sampling=5, perform_checks=0, use_OSCAR_format=0)
+s = capi.Sampler(d, param, surf, table_path=cases.tables_for(g), **over)
+assert s.read_in_FO_surface() == 0
+s.set_random_seed(1)
+print("generate_samples returned", s.generate_samples())
+"""
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="needs a host without a GPU")
+def test_no_cpu_fallback_without_a_gpu(tmp_path):
+    """the product path has no CPU fallback: the C ABI refuses to make a handle and class iSS ends the
+    run the way the reference ends on a fatal error (message + exit(-1)), it does not sample on the host"""
+    import ctypes as C
+    sys.path.insert(0, REPO)
+    from iss_b200 import capi
+    L = capi.cuda_lib()
+    h = C.c_void_p()
+    assert L.iss_cuda_create(0, C.byref(h)) == 1        # ISS_ERR_CUDA
+    assert not h.value
+    script = tmp_path/"facade.py"
+    script.write_text(NO_GPU_FACADE % dict(repo=REPO, tests=os.path.join(REPO, "tests")))
+    r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "generate_samples returned" not in r.stdout
+    assert "no usable CUDA device" in (r.stdout + r.stderr)
