@@ -1013,19 +1013,15 @@ __device__ __forceinline__ double inverse_cdf_smem(const double *tb, int n, doub
     const double w1 = 2.*M.mu_tilde;
     int lo = M.idx_min;
     int hi = n - 1;
-    double r_min = table_F3(tb, lo, w1, M.w0, M.m_term);
-    double r_max = M.cdf_max;
     while (hi - lo > 1) {
-        const int mid = (hi + lo)/2;
+        const int mid = static_cast<int>(static_cast<unsigned>(hi + lo) >> 1);  // (indices are >= 0)
         const double r_mid = table_F3(tb, mid, w1, M.w0, M.m_term);
-        if (r < r_mid) {
-            hi = mid;
-            r_max = r_mid;
-        } else {
-            lo = mid;
-            r_min = r_mid;
-        }
+        if (r < r_mid) hi = mid; else lo = mid;
     }
+    // the values the bisection compared with at the final bracket (table_F3 is a pure function of the
+    // index; hi = n - 1 was never probed: the reference starts from the cached maximum there)
+    double r_min = table_F3(tb, lo, w1, M.w0, M.m_term);
+    const double r_max = (hi == n - 1) ? M.cdf_max : table_F3(tb, hi, w1, M.w0, M.m_term);
     double E0 = __fma_rn(static_cast<double>(lo), dE, e0);
     if (E0 < M.a_min) {
         E0 = M.a_min;
