@@ -459,9 +459,9 @@ def run_engine(args):
         "peak_source": peak_src,
         "avg_launch_ms": fam_ms["sample"]/n_launch_sample,
         "share_of_step": fam_ms["sample"]/ms if ms > 0 else None,
-        "note": "the sampler is bound by instruction issue (70 % of the slots), the shared-memory data "
-                "pipe (72 %) and divergence (22.7 of 32 lanes), not by HBM (SURVEY.md 8(d)); see fp64 and "
-                "profiles/r2_ncu_propose_source.txt",
+        "note": "the sampler is bound by the shared-memory data pipe (78 %: the random 8-byte table loads "
+                "of the bisection), instruction issue (69 % of the slots) and divergence (22.6 of 32 lanes), "
+                "not by HBM (SURVEY.md 8(d)); see fp64 and profiles/r2_ncu_propose_source_final.txt",
         "fp64": {"achieved_tflops": FLOP_PER_HADRON*hadrons/sample_s/1e12 if sample_s > 0 else None,
                  "peak_tflops": fp64_peak, "peak_source": "DFMA microbenchmark run in this process "
                  "(iss_cuda_fp64_peak)",
