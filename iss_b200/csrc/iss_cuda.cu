@@ -436,10 +436,7 @@ int iss_cuda_upload_table(iss_handle *h, int32_t kind, const double *data, int64
                 t.denom0 = fermion ? (1. + exp(-t.m0)) : (1. - exp(-t.m0));
                 t.inv_denom0 = 1.0/t.denom0;
                 t.inv_de = 1.0/t.de;
-                for (int n = 0; n < 10; n++) {
-                    t.a[n] = exp(-t.m0*n);
-                    t.inv_n1[n] = 1.0/(n + 1);
-                }
+                momentum_series_constants(t, fermion);
             }
             return ISS_OK;
         }

@@ -47,7 +47,31 @@ struct MomentumTable {      // one Boson/FermionMomentumSampler instance
     double inv_denom0, inv_de;
     double de_build;        // Etilde_[i] = fma(i, de_build, e0) for tables generated on the device
     int generated;          // 0: uploaded by the host (arbitrary abscissa, never copied to smem)
+    // the 10-term series as polynomials in exp(m0 - Etilde) (momentum_series_constants):
+    // q1[n] = a[n]/(n+1), q2[n] = a[n]/(n+1)^2, q3[n] = a[n]/(n+1)^3, k1 / k2 = the Etilde-independent
+    // parts of CDF_1 / CDF_2
+    double q1[10], q2[10], q3[10], k1, k2;
 };
+
+// fills the series constants of a table from m0, trunc and the statistics
+inline void momentum_series_constants(MomentumTable &t, bool fermion) {
+    t.k1 = 0.;
+    t.k2 = 0.;
+    double sign = 1.;
+    for (int n = 0; n < 10; n++) {
+        t.a[n] = exp(-t.m0*n);
+        t.inv_n1[n] = 1.0/(n + 1);
+        const double inv = t.inv_n1[n], n1 = n + 1;
+        t.q1[n] = t.a[n]*inv;
+        t.q2[n] = t.a[n]*inv*inv;
+        t.q3[n] = t.a[n]*inv*inv*inv;
+        if (n < t.trunc) {
+            t.k1 += (fermion ? sign : 1.)*inv*inv*t.a[n]*(t.m0*n1 + 1);
+            t.k2 += inv*inv*inv*t.a[n]*(t.m0*n1*(t.m0*n1 + 2) + 2);
+        }
+        sign = -sign;
+    }
+}
 
 constexpr int CELL_STRIDE = 32;   // floats per AoS cell record (28 fields + t, z + 2 spare)
 constexpr int CELL_T = 28;        // tau*cosh(eta)

@@ -71,11 +71,44 @@ __host__ __device__ inline void cdf_012(double Et, double m0, int trunc, double 
 // (MomentumSamplerBase::update_cache), with the table constants exp(-m0 n) precomputed and
 // exp((m0 - a)(n+1)) formed as powers of exp(m0 - a): 2 exp + 1 log instead of 22 exp + 1 log.
 // Differs from the literal series only by FP64 rounding (~1e-16 relative).
-template <bool FERMION>
+template <bool FERMION, bool POLY>
 __device__ __forceinline__ void cdf_012_lane(const MomentumTable &mt, double Et, double &c0,
                                              double &c1, double &c2) {
     const double m0 = mt.m0;
     const double e1 = exp(m0 - Et);
+    if (POLY && mt.trunc == 10) {
+        // the ten terms as polynomials in e1 = exp(m0 - Et) (Horner, 3 + 2 of them):
+        //   CDF_2 = k2 - (Et^2 P1(e1) + 2 Et P2(e1) + 2 P3(e1)),  P_j(x) = sum_n a_n/(n+1)^j x^(n+1)
+        //   CDF_1 = k1 - (Et P1 + P2) for bosons; the alternating sign of the fermion series is the
+        //   same polynomial at -e1: sum_n (-1)^n q_n x^(n+1) = -P(-x)
+        // Same terms as the loop below, another order of the additions (~5e-16 of the totals).
+        double p1 = mt.q1[9], p2 = mt.q2[9], p3 = mt.q3[9];
+#pragma unroll
+        for (int n = 8; n >= 0; n--) {
+            p1 = __fma_rn(p1, e1, mt.q1[n]);
+            p2 = __fma_rn(p2, e1, mt.q2[n]);
+            p3 = __fma_rn(p3, e1, mt.q3[n]);
+        }
+        p1 *= e1;
+        p2 *= e1;
+        p3 *= e1;
+        c2 = mt.k2 - (Et*Et*p1 + 2.*Et*p2 + 2.*p3);
+        if (FERMION) {
+            const double x = -e1;
+            double s1 = mt.q1[9], s2 = mt.q2[9];
+#pragma unroll
+            for (int n = 8; n >= 0; n--) {
+                s1 = __fma_rn(s1, x, mt.q1[n]);
+                s2 = __fma_rn(s2, x, mt.q2[n]);
+            }
+            c1 = mt.k1 - (Et*(s1*e1) + s2*e1);      // -P(-e1) = (P(x)/x at x = -e1) e1
+            c0 = -mt.exp_m0*log((1. + e1*mt.a[1])*mt.inv_denom0);
+        } else {
+            c1 = mt.k1 - (Et*p1 + p2);
+            c0 = mt.exp_m0*log((1. - e1*mt.a[1])*mt.inv_denom0);
+        }
+        return;
+    }
     double b = 1.;
     double s0 = 0.;
     c1 = 0.;
@@ -164,10 +197,7 @@ static int ensure_momentum_tables(iss_handle *h) {
         t.denom0 = fermion ? (1. + exp(-m0)) : (1. - exp(-m0));
         t.inv_denom0 = 1.0/t.denom0;
         t.inv_de = 1.0/t.de;
-        for (int n = 0; n < 10; n++) {
-            t.a[n] = exp(-m0*n);
-            t.inv_n1[n] = 1.0/(n + 1);
-        }
+        momentum_series_constants(t, fermion);
     }
     return ISS_OK;
 }
@@ -382,6 +412,9 @@ __device__ __forceinline__ void momentum_restore(double mass, double T_in, doubl
 
 // full set-up for (species, cell); returns false if (m - mu)/T is outside the table
 // (reference: exit(1), MomentumSamplerBase.cpp:35-43)
+// POLY: the polynomial form of the ten-term series (the set-up kernel, one call per hadron); the
+// rare paths inside the proposal kernel keep the rolled loop, which costs that kernel no registers
+template <bool POLY = false>
 __device__ __forceinline__ bool momentum_setup(const MomentumTable *__restrict__ mts, double mass,
                                                int sign, double T_in, double mu, MomSetup &M) {
     const double T = fmax(1e-16, T_in);
@@ -395,9 +428,9 @@ __device__ __forceinline__ bool momentum_setup(const MomentumTable *__restrict__
     const MomentumTable &mt = mts[tab];
     double c0, c1, c2;
     if (fermion) {
-        cdf_012_lane<true>(mt, a, c0, c1, c2);
+        cdf_012_lane<true, POLY>(mt, a, c0, c1, c2);
     } else {
-        cdf_012_lane<false>(mt, a, c0, c1, c2);
+        cdf_012_lane<false, POLY>(mt, a, c0, c1, c2);
     }
     const double w1 = 2.*mu_tilde;
     const double w0 = mu_tilde*mu_tilde - m_tilde*m_tilde/2.;
@@ -738,7 +771,7 @@ __global__ void build_cellrec_kernel(const float *__restrict__ cells, const doub
 // values of the |p| sampler (MomentumSamplerBase::update_cache), histogram of the cells.  The FP64
 // work of the series runs in the shadow of the dependent loads of the cell search.  The task is
 // written at its work index; partition_kernel moves it into the region of its cell block.
-__global__ void __launch_bounds__(SETUP_THREADS)
+__global__ void __launch_bounds__(SETUP_THREADS, 5)
 setup_kernel(const SamplerArgs A) {
     extern __shared__ unsigned char smem_raw[];
     DeviceSpecies *sp = reinterpret_cast<DeviceSpecies *>(smem_raw);
@@ -784,7 +817,7 @@ setup_kernel(const SamplerArgs A) {
             const float4 tm = __ldg(A.thermo + cell);
             const float4 th = make_float4(tm.y, tm.z, tm.w, 0.f);
             MomSetup M;
-            const bool ok = momentum_setup(A.mt, p.mass, p.sign, tm.x, species_mu(p, 1, th, p.mass), M);
+            const bool ok = momentum_setup<true>(A.mt, p.mass, p.sign, tm.x, species_mu(p, 1, th, p.mass), M);
             t.m_term = M.m_term;
             t.cdf_max = M.cdf_max;
             t.tab_idx = ok ? static_cast<uint16_t>(M.tab | (M.idx_min << 3)) : TASK_RANGE_ERROR;
