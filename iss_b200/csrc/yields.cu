@@ -135,7 +135,7 @@ yields_kernel(const YieldArgs a) {
     const double sigma = common*dsigma_dot_u;
     const double q_pref = with_diff ? common*dsigma_dot_q/cc.kappa : 0.;
 
-#pragma unroll 2
+#pragma unroll 1
     for (int is = 0; is < s_end - s_begin; is++) {
         const DeviceSpecies p = sp[is];
         const double mass = p.mass;
